@@ -1,0 +1,158 @@
+/*
+ * opm_gpu_solver.h -- C ABI of the B200-native Newton-step linear solver.
+ *
+ * Drop-in boundary: the body of
+ *     NewtonIterationBlackoilInterleavedImpl<3,double>::computeNewtonIncrement
+ *     (opm/autodiff/NewtonIterationBlackoilInterleaved.cpp:202-292)
+ * minus the host-side well elimination/recovery, i.e. formInterleavedSystem (:110-194),
+ * the rhs/solution interleave (:263-283) and ISTLSolver::solve (opm/autodiff/ISTLSolver.hpp:
+ * 283-306 -> :124-189 ILU0 construction -> :250-274 BiCGSTAB -> :358-368 checkConvergence).
+ * Precedent in the reference for a raw-array solver signature:
+ * LinearSolverInterface::solve(size,nnz,ia,ja,sa,rhs,solution) at
+ * opm/core/linalg/LinearSolverInterface.hpp:67-74 and struct CSRMatrix at
+ * opm/core/linalg/sparse_sys.h:38-47.
+ *
+ * Conventions: every function returns an opmgpu_status (0 = ok); no exception crosses the
+ * ABI; all pointers are HOST pointers unless the name ends in _dev; block size is 3
+ * (np = 3, water/oil/gas); FP64 values, int32 indices.  A handle owns one GPU (one CUDA
+ * stream); it is not re-entrant, matching the reference's single-threaded caller
+ * (BlackoilModelBase_impl.hpp:289).  There is no CPU fallback: without a usable sm_100
+ * device opmgpu_create fails.
+ */
+#ifndef OPM_GPU_SOLVER_H
+#define OPM_GPU_SOLVER_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct opmgpu_solver* opmgpu_handle;
+
+typedef enum {
+    OPMGPU_OK             = 0,
+    OPMGPU_NOT_CONVERGED  = 1,   /* -> Opm::LinearSolverProblem (ISTLSolver.hpp:364-367)            */
+    OPMGPU_SINGULAR_BLOCK = 2,   /* ILU0 pivot block singular/missing -> Dune::MatrixBlockError class */
+    OPMGPU_BREAKDOWN      = 3,   /* |rho|,|omega| <= 1e-80 or |h| < 1e-80 -> Dune::SolverAbort class   */
+    OPMGPU_BAD_PATTERN    = 4,   /* Jacobian entry outside the pattern (dune throws in istlA[r][c])   */
+    OPMGPU_BAD_ARGUMENT   = 5,
+    OPMGPU_CUDA_ERROR     = -1,  /* -> std::runtime_error; text in opmgpu_last_error                  */
+    OPMGPU_NCCL_ERROR     = -2
+} opmgpu_status;
+
+/* The keys FlowLinearSolverParameters reads from the ParameterGroup (member names visible at
+ * ISTLSolver.hpp:142,204-208,255-262,364 and ...Interleaved.cpp:127); there are no hidden
+ * defaults below the ABI -- opmgpu_default_params fills in upstream's 2019.04 values. */
+typedef struct {
+    double linear_solver_reduction;                /* 1e-2 */
+    int    linear_solver_maxiter;                  /* 150  */
+    double ilu_relaxation;                         /* 0.9  */
+    int    linear_solver_verbosity;                /* 0    */
+    int    linear_solver_ignoreconvergencefailure; /* 0    */
+    int    require_full_sparsity_pattern;          /* 0    */
+    int    max_half_steps;                         /* -1; >=0 stops after that many half iterations
+                                                      (parity checks at equal half-step counts)      */
+} opmgpu_params;
+
+/* Dune::InverseOperatorResult plus what the benchmark reports. */
+typedef struct {
+    int    iterations;        /* ceil(it), valid also on failure (BlackoilModelBase_impl.hpp:291,295) */
+    int    converged;
+    int    half_steps;
+    int    bad_row;           /* OPMGPU_SINGULAR_BLOCK: block row of the failing pivot */
+    double reduction;         /* |r| / |r0| at exit */
+    double norm0;
+    double ms_analysis;       /* pattern analysis (only non-zero when the pattern changed) */
+    double ms_h2d;            /* host->device copies                                       */
+    double ms_interleave;     /* K1 scatter of the CSC blocks into BCRS                    */
+    double ms_factor;         /* K3 ILU0 factorisation                                     */
+    double ms_solve;          /* BiCGStab loop                                             */
+    double ms_d2h;
+} opmgpu_result;
+
+/* One scalar Jacobian block d(eq p1)/d(var p2) in Eigen's column-major compressed layout
+ * (AutoDiffMatrix::getSparse, opm/autodiff/AutoDiffMatrix.hpp:635-648). */
+typedef struct {
+    const int*    colptr;     /* N+1  (outerIndexPtr) */
+    const int*    rowidx;     /* nnz  (innerIndexPtr), ascending per column */
+    const double* val;        /* nnz  (valuePtr) */
+} opmgpu_csc;
+
+void opmgpu_default_params(opmgpu_params* p);
+
+/* Lifetime: created once where FlowMain::setupLinearSolver builds fis_solver_
+ * (opm/autodiff/FlowMain.hpp:806-830) and kept for the whole run. */
+int  opmgpu_create(int device, opmgpu_handle* out);
+int  opmgpu_destroy(opmgpu_handle h);
+const char* opmgpu_last_error(opmgpu_handle h);          /* h may be NULL: creation errors */
+
+/* Multi-GPU (one process per GPU): rank r of `world` owns the contiguous block rows
+ * [row_begin, row_end) of the global system.  nccl_unique_id is the 128-byte ncclUniqueId
+ * rank 0 obtained from opmgpu_nccl_unique_id and distributed by any means. */
+int  opmgpu_nccl_unique_id(void* id128);
+int  opmgpu_create_distributed(int device, int rank, int world, const void* nccl_unique_id,
+                               opmgpu_handle* out);
+
+/* Launch on this stream (a cudaStream_t) instead of the handle's own. */
+int  opmgpu_set_stream(opmgpu_handle h, void* cuda_stream);
+
+/* ---- the Newton-step solve ----------------------------------------------------------- */
+
+/* Replaces the pattern half of formInterleavedSystem (...Interleaved.cpp:118-155) when the
+ * caller already holds BCRS: rowptr[N+1], colidx[nnzb] ascending per row, diagonal present.
+ * Runs the dependency analysis of the ILU0 sweeps; cached until the next call.
+ * Distributed handles pass their LOCAL rows with GLOBAL column ids plus the global row
+ * range they own. */
+int  opmgpu_set_pattern_bcrs(opmgpu_handle h, int N, int nnzb, const int* rowptr, const int* colidx);
+int  opmgpu_set_pattern_bcrs_distributed(opmgpu_handle h, int N_local, int nnzb_local,
+                                         const int* rowptr, const int* colidx_global,
+                                         long long row_begin, long long N_global);
+
+/* Replaces ISTLSolver::solve(A,x,b) (ISTLSolver.hpp:283-306): vals[nnzb*9] row-major 3x3
+ * blocks [eq][var], rhs/x cell-major [cell][3], x0 = 0 (...Interleaved.cpp:272-273). */
+int  opmgpu_solve_bcrs3(opmgpu_handle h, const double* vals, const double* rhs, double* x,
+                        const opmgpu_params* params, opmgpu_result* result);
+/* Same with device-resident inputs/outputs (benchmarks; a caller that assembles on the GPU). */
+int  opmgpu_solve_bcrs3_dev(opmgpu_handle h, const double* vals_dev, const double* rhs_dev,
+                            double* x_dev, const opmgpu_params* params, opmgpu_result* result);
+
+/* Replaces ...Interleaved.cpp:234-283 in one call: eq p1 of the nine CSC blocks is scaled by
+ * matbalscale[p1] (:234-236), the pattern is the union of the pressure-derivative patterns
+ * (:118-123; all nine with require_full_sparsity_pattern :127-134) and is re-analysed only
+ * when it changed, values are scattered on the device (:178-193), rhs_eqmajor (3N, stride N,
+ * unscaled equation values) is scaled and interleaved (:263-269), the system is solved and
+ * dx_varmajor (3N, stride N) de-interleaved (:279-283). */
+int  opmgpu_solve_from_csc_blocks(opmgpu_handle h, int N, const opmgpu_csc blocks[9],
+                                  const double matbalscale[3], const double* rhs_eqmajor,
+                                  double* dx_varmajor, const opmgpu_params* params,
+                                  opmgpu_result* result);
+
+/* ---- kernel-level entry points (parity tests, micro-benchmarks) -------------------------- */
+
+/* Upload BCRS values for the current pattern (device copy kept in the handle). */
+int  opmgpu_set_values_bcrs3(opmgpu_handle h, const double* vals);
+int  opmgpu_set_values_bcrs3_dev(opmgpu_handle h, const double* vals_dev);
+/* y = A x  (Dune::MatrixAdapter::apply, ISTLSolver.hpp:303). */
+int  opmgpu_spmv(opmgpu_handle h, const double* x, double* y);
+int  opmgpu_spmv_dev(opmgpu_handle h, const double* x_dev, double* y_dev);
+/* ILU0 of the current values (ParallelOverlappingILU0 ctor, ISTLSolver.hpp:201-211). */
+int  opmgpu_ilu0_factor(opmgpu_handle h, int* bad_row);
+/* Copy the factors back in the BCRS layout of the pattern, diagonal blocks inverted. */
+int  opmgpu_ilu0_get_factors(opmgpu_handle h, double* lu);
+/* v = w U^-1 L^-1 d  (ParallelOverlappingILU0::apply). */
+int  opmgpu_ilu0_apply(opmgpu_handle h, double w, const double* d, double* v);
+int  opmgpu_ilu0_apply_dev(opmgpu_handle h, double w, const double* d_dev, double* v_dev);
+/* sum_i x_i y_i (Dune::SeqScalarProduct::dot), deterministic tree order. */
+int  opmgpu_dot(opmgpu_handle h, const double* x, const double* y, int n, double* out);
+
+/* Analysis facts for reports: ILU0 dependency levels, kernel launches since creation. */
+int  opmgpu_num_levels(opmgpu_handle h, int* lower_levels, int* upper_levels);
+long long opmgpu_launch_count(opmgpu_handle h);
+/* |r| after every half step of the last solve (verbosity / parity reports). */
+int  opmgpu_residual_history(opmgpu_handle h, double* out, int cap, int* n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

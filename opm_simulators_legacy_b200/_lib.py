@@ -1,0 +1,100 @@
+"""ctypes binding of libopmgpu.so (the C ABI declared in include/opm_gpu_solver.h).
+
+The library is built in-tree by `__graft_entry__.build()` / `make -C csrc`.  There is no
+fallback of any kind: if the shared object is missing or no sm_100 device is usable, the
+calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libopmgpu.so")
+
+# every symbol include/opm_gpu_solver.h declares (tests check the export list against this)
+EXPORTS = [
+    "opmgpu_default_params", "opmgpu_create", "opmgpu_destroy", "opmgpu_last_error",
+    "opmgpu_nccl_unique_id", "opmgpu_create_distributed", "opmgpu_set_stream",
+    "opmgpu_set_pattern_bcrs", "opmgpu_set_pattern_bcrs_distributed",
+    "opmgpu_solve_bcrs3", "opmgpu_solve_bcrs3_dev", "opmgpu_solve_from_csc_blocks",
+    "opmgpu_set_values_bcrs3", "opmgpu_set_values_bcrs3_dev", "opmgpu_spmv", "opmgpu_spmv_dev",
+    "opmgpu_ilu0_factor", "opmgpu_ilu0_get_factors", "opmgpu_ilu0_apply", "opmgpu_ilu0_apply_dev",
+    "opmgpu_dot", "opmgpu_num_levels", "opmgpu_launch_count", "opmgpu_residual_history",
+]
+
+OK, NOT_CONVERGED, SINGULAR_BLOCK, BREAKDOWN, BAD_PATTERN, BAD_ARGUMENT = 0, 1, 2, 3, 4, 5
+CUDA_ERROR, NCCL_ERROR = -1, -2
+
+
+class Params(C.Structure):
+    _fields_ = [("linear_solver_reduction", C.c_double),
+                ("linear_solver_maxiter", C.c_int),
+                ("ilu_relaxation", C.c_double),
+                ("linear_solver_verbosity", C.c_int),
+                ("linear_solver_ignoreconvergencefailure", C.c_int),
+                ("require_full_sparsity_pattern", C.c_int),
+                ("max_half_steps", C.c_int)]
+
+
+class Result(C.Structure):
+    _fields_ = [("iterations", C.c_int), ("converged", C.c_int), ("half_steps", C.c_int),
+                ("bad_row", C.c_int), ("reduction", C.c_double), ("norm0", C.c_double),
+                ("ms_analysis", C.c_double), ("ms_h2d", C.c_double), ("ms_interleave", C.c_double),
+                ("ms_factor", C.c_double), ("ms_solve", C.c_double), ("ms_d2h", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class Csc(C.Structure):
+    _fields_ = [("colptr", C.POINTER(C.c_int)), ("rowidx", C.POINTER(C.c_int)),
+                ("val", C.POINTER(C.c_double))]
+
+
+_lib = None
+
+
+def load():
+    """Load libopmgpu.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(or make -C opm_simulators_legacy_b200/csrc). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    H = C.c_void_p
+    ip, dp, vp = C.POINTER(C.c_int), C.POINTER(C.c_double), C.c_void_p
+    PP, RP = C.POINTER(Params), C.POINTER(Result)
+    sig = {
+        "opmgpu_default_params": (None, [PP]),
+        "opmgpu_create": (C.c_int, [C.c_int, C.POINTER(H)]),
+        "opmgpu_destroy": (C.c_int, [H]),
+        "opmgpu_last_error": (C.c_char_p, [H]),
+        "opmgpu_nccl_unique_id": (C.c_int, [vp]),
+        "opmgpu_create_distributed": (C.c_int, [C.c_int, C.c_int, C.c_int, vp, C.POINTER(H)]),
+        "opmgpu_set_stream": (C.c_int, [H, vp]),
+        "opmgpu_set_pattern_bcrs": (C.c_int, [H, C.c_int, C.c_int, ip, ip]),
+        "opmgpu_set_pattern_bcrs_distributed": (C.c_int, [H, C.c_int, C.c_int, ip, ip, C.c_longlong, C.c_longlong]),
+        "opmgpu_solve_bcrs3": (C.c_int, [H, dp, dp, dp, PP, RP]),
+        "opmgpu_solve_bcrs3_dev": (C.c_int, [H, vp, vp, vp, PP, RP]),
+        "opmgpu_solve_from_csc_blocks": (C.c_int, [H, C.c_int, C.POINTER(Csc), dp, dp, dp, PP, RP]),
+        "opmgpu_set_values_bcrs3": (C.c_int, [H, dp]),
+        "opmgpu_set_values_bcrs3_dev": (C.c_int, [H, vp]),
+        "opmgpu_spmv": (C.c_int, [H, dp, dp]),
+        "opmgpu_spmv_dev": (C.c_int, [H, vp, vp]),
+        "opmgpu_ilu0_factor": (C.c_int, [H, ip]),
+        "opmgpu_ilu0_get_factors": (C.c_int, [H, dp]),
+        "opmgpu_ilu0_apply": (C.c_int, [H, C.c_double, dp, dp]),
+        "opmgpu_ilu0_apply_dev": (C.c_int, [H, C.c_double, vp, vp]),
+        "opmgpu_dot": (C.c_int, [H, dp, dp, C.c_int, dp]),
+        "opmgpu_num_levels": (C.c_int, [H, ip, ip]),
+        "opmgpu_launch_count": (C.c_longlong, [H]),
+        "opmgpu_residual_history": (C.c_int, [H, dp, C.c_int, ip]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(lib, name)
+        f.restype, f.argtypes = res, args
+    _lib = lib
+    return lib

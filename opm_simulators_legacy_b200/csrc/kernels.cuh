@@ -1,0 +1,457 @@
+// Device code of the B200-native Newton-step linear solver (sm_100a).
+//
+// All kernels are FP64 and HBM-bound (SpMV: 18 flop per 76 B); none uses tensor cores --
+// 3x3 blocks are not a dense contraction (BASELINE.json north_star).  Arithmetic order inside
+// a block row follows the reference's dune-istl loops so that SpMV, the ILU0 factors and the
+// ILU0 sweeps are bit-identical to the CPU oracle: every `y +-= a*x` is one fma(), nothing
+// else is contracted (the file is compiled with -fmad=false).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace opmgpu {
+
+constexpr int kBS = 3;
+constexpr int kBB = 9;
+constexpr int kExtBitDev = 0x40000000;
+
+// ---- device scalar block of the BiCGStab recurrences (lives in HBM, read by every kernel)
+enum ScalarSlot {
+    S_RHO_OLD = 0, S_ALPHA = 1, S_OMEGA = 2, S_H = 3, S_TR = 4, S_TT = 5,
+    S_NRM2 = 6, S_RHO_NEW = 7, S_DOT = 8, S_COUNT = 16
+};
+
+// ------------------------------------------------------------------------------------------
+// Deterministic grid reduction: fixed-shape shuffle tree per block, per-block partials in
+// HBM, the last block to arrive (ticket) folds the partials in a fixed order.  No floating
+// point atomics, so results are reproducible run to run for a given launch shape.
+// ------------------------------------------------------------------------------------------
+struct ReduceWs {
+    double*   partials;      // [kMaxRed][kMaxBlocks]
+    unsigned* ticket;        // wraps to 0 by atomicInc
+};
+constexpr int kMaxRedBlocks = 2048;
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int NRED>
+__device__ __forceinline__ void block_sum(double (&v)[NRED], double* smem /*[NRED*32]*/)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int r = 0; r < NRED; ++r) {
+        v[r] = warp_sum(v[r]);
+        if (lane == 0) smem[r * 32 + wid] = v[r];
+    }
+    __syncthreads();
+    if (wid == 0) {
+#pragma unroll
+        for (int r = 0; r < NRED; ++r) {
+            double t = (lane < nw) ? smem[r * 32 + lane] : 0.0;
+            v[r] = warp_sum(t);
+        }
+    }
+    __syncthreads();
+}
+
+// Finaliser hook: called by thread 0 of the last block with the NRED totals.
+template <int NRED, class Fin>
+__device__ __forceinline__ void grid_reduce(double (&v)[NRED], ReduceWs ws, Fin fin)
+{
+    __shared__ double red_smem[NRED * 32];
+    __shared__ bool is_last;
+    block_sum<NRED>(v, red_smem);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int r = 0; r < NRED; ++r) ws.partials[r * kMaxRedBlocks + blockIdx.x] = v[r];
+        __threadfence();
+        const unsigned t = atomicInc(ws.ticket, gridDim.x - 1);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        double acc[NRED];
+#pragma unroll
+        for (int r = 0; r < NRED; ++r) {
+            acc[r] = 0.0;
+            for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x)
+                acc[r] += __ldcg(&ws.partials[r * kMaxRedBlocks + b]);
+        }
+        block_sum<NRED>(acc, red_smem);
+        if (threadIdx.x == 0) fin(acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2  BCRS 3x3 SpMV  y = A x   (Dune::MatrixAdapter::apply -> BCRSMatrix::mv -> umv;
+// call site opm/autodiff/ISTLSolver.hpp:303).  One thread per (block row, component),
+// blocks visited in ascending column order.  MODE 0: plain.  MODE 1: also S[S_H] = w1.y.
+// MODE 2: also S[S_TR] = y.w1, S[S_TT] = y.y.  (fused dot epilogues of BiCGStab)
+// ------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256)
+spmv3_kernel(int N, const int* __restrict__ rowptr, const int* __restrict__ colidx,
+             const double* __restrict__ vals, const double* __restrict__ x,
+             double* __restrict__ y, const double* __restrict__ w1, double* S, ReduceWs ws)
+{
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = (int)(gid / 3), c = (int)(gid - 3LL * row);
+    double acc = 0.0;
+    if (row < N) {
+        const int kb = __ldg(rowptr + row), ke = __ldg(rowptr + row + 1);
+        for (int k = kb; k < ke; ++k) {
+            const double* a = vals + (size_t)k * kBB + c * kBS;
+            const double* xj = x + (size_t)__ldg(colidx + k) * kBS;
+            acc = fma(__ldcs(a + 0), xj[0], acc);
+            acc = fma(__ldcs(a + 1), xj[1], acc);
+            acc = fma(__ldcs(a + 2), xj[2], acc);
+        }
+        y[gid] = acc;
+    }
+    if (MODE == 1) {
+        double v[1] = { row < N ? w1[gid] * acc : 0.0 };
+        grid_reduce<1>(v, ws, [=](double (&t)[1]) { S[S_H] = t[0]; });
+    } else if (MODE == 2) {
+        double v[2] = { row < N ? acc * w1[gid] : 0.0, row < N ? acc * acc : 0.0 };
+        grid_reduce<2>(v, ws, [=](double (&t)[2]) { S[S_TR] = t[0]; S[S_TT] = t[1]; });
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K5  fused BiCGStab vector kernels (Dune::BiCGSTABSolver::apply; elementwise order as there:
+// p.axpy(-omega,v); p*=beta; p+=r   /   x.axpy(alpha,y); r.axpy(-alpha,v)).
+// ------------------------------------------------------------------------------------------
+// S[S_NRM2] = S[S_RHO_NEW] = r.r ; recurrences reset (rho = alpha = omega = 1)
+__global__ void __launch_bounds__(256)
+bicg_init_kernel(size_t n, const double* __restrict__ r, double* S, ReduceWs ws)
+{
+    double v[1] = {0.0};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        v[0] = fma(r[i], r[i], v[0]);
+    grid_reduce<1>(v, ws, [=](double (&t)[1]) {
+        S[S_NRM2] = t[0]; S[S_RHO_NEW] = t[0];
+        S[S_RHO_OLD] = 1.0; S[S_ALPHA] = 1.0; S[S_OMEGA] = 1.0;
+    });
+}
+
+// p = r + beta (p - omega v),  beta = (rho_new/rho)(alpha/omega)
+__global__ void __launch_bounds__(256)
+bicg_update_p_kernel(size_t n, double* __restrict__ p, const double* __restrict__ r,
+                     const double* __restrict__ v, const double* __restrict__ S)
+{
+    const double omega = S[S_OMEGA];
+    const double beta = (S[S_RHO_NEW] / S[S_RHO_OLD]) * (S[S_ALPHA] / omega);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        double pq = fma(-omega, v[i], p[i]);
+        pq *= beta;
+        p[i] = pq + r[i];
+    }
+}
+
+// alpha = rho_new / h ; x += alpha y ; r -= alpha v ; S[S_NRM2] = r.r
+__global__ void __launch_bounds__(256)
+bicg_update1_kernel(size_t n, double* __restrict__ x, double* __restrict__ r,
+                    const double* __restrict__ y, const double* __restrict__ v, double* S, ReduceWs ws)
+{
+    const double alpha = S[S_RHO_NEW] / S[S_H];
+    double s[1] = {0.0};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        x[i] = fma(alpha, y[i], x[i]);
+        const double ri = fma(-alpha, v[i], r[i]);
+        r[i] = ri;
+        s[0] = fma(ri, ri, s[0]);
+    }
+    grid_reduce<1>(s, ws, [=](double (&t)[1]) { S[S_NRM2] = t[0]; S[S_ALPHA] = alpha; });
+}
+
+// omega = (t.r)/(t.t) ; x += omega y ; r -= omega t ; S[S_NRM2] = r.r ; rho <- rho_new ; rho_new = rt.r
+__global__ void __launch_bounds__(256)
+bicg_update2_kernel(size_t n, double* __restrict__ x, double* __restrict__ r,
+                    const double* __restrict__ y, const double* __restrict__ t,
+                    const double* __restrict__ rt, double* S, ReduceWs ws)
+{
+    const double omega = S[S_TR] / S[S_TT];
+    double s[2] = {0.0, 0.0};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        x[i] = fma(omega, y[i], x[i]);
+        const double ri = fma(-omega, t[i], r[i]);
+        r[i] = ri;
+        s[0] = fma(ri, ri, s[0]);
+        s[1] = fma(rt[i], ri, s[1]);
+    }
+    grid_reduce<2>(s, ws, [=](double (&u)[2]) {
+        S[S_OMEGA] = omega;
+        S[S_RHO_OLD] = S[S_RHO_NEW];
+        S[S_NRM2] = u[0];
+        S[S_RHO_NEW] = u[1];
+    });
+}
+
+__global__ void __launch_bounds__(256)
+dot_kernel(size_t n, const double* __restrict__ a, const double* __restrict__ b, double* S, ReduceWs ws)
+{
+    double v[1] = {0.0};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        v[0] = fma(a[i], b[i], v[0]);
+    grid_reduce<1>(v, ws, [=](double (&t)[1]) { S[S_DOT] = t[0]; });
+}
+
+// ------------------------------------------------------------------------------------------
+// 3x3 helpers mirroring dune's DenseMatrix::{left,right}multiply and OPM's MatrixBlock inverse
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mat3_mul(const double* A, const double* B, double* C)
+{
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) s = fma(A[i * 3 + k], B[k * 3 + j], s);
+            C[i * 3 + j] = s;
+        }
+}
+
+// adjugate / determinant, same operation order as Opm::MatrixBlock<double,3,3>::invert
+__device__ __forceinline__ double mat3_invert(double* M)
+{
+    double A[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) A[q] = M[q];
+    const double t4 = A[0] * A[4], t6 = A[0] * A[5], t8 = A[1] * A[3];
+    const double t10 = A[2] * A[3], t12 = A[1] * A[6], t14 = A[2] * A[6];
+    const double det = (t4 * A[8] - t6 * A[7] - t8 * A[8] + t10 * A[7] + t12 * A[5] - t14 * A[4]);
+    const double t17 = 1.0 / det;
+    M[0] = (A[4] * A[8] - A[5] * A[7]) * t17;
+    M[1] = -(A[1] * A[8] - A[2] * A[7]) * t17;
+    M[2] = (A[1] * A[5] - A[2] * A[4]) * t17;
+    M[3] = -(A[3] * A[8] - A[5] * A[6]) * t17;
+    M[4] = (A[0] * A[8] - t14) * t17;
+    M[5] = -(t6 - t10) * t17;
+    M[6] = (A[3] * A[7] - A[4] * A[6]) * t17;
+    M[7] = -(A[0] * A[7] - t12) * t17;
+    M[8] = (t4 - t8) * t17;
+    return det;
+}
+
+// ------------------------------------------------------------------------------------------
+// K3  block ILU0 factorisation, natural order, one dependency level per launch
+// (Opm::ParallelOverlappingILU0 ctor -> Dune::bilu0_decomposition; ISTLSolver.hpp:201-211).
+// One thread per row of the level; rows of a level are independent by construction.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+ilu0_factor_level_kernel(const int* __restrict__ lvl_rows, int begin, int end,
+                         const int* __restrict__ rowptr, const int* __restrict__ colidx,
+                         const int* __restrict__ diag, double* lu, int* bad_row)
+{
+    const int q = begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= end) return;
+    const int i = lvl_rows[q];
+    const int iend = rowptr[i + 1], idiag = diag[i];
+    for (int ij = rowptr[i]; ij < idiag; ++ij) {
+        const int j = colidx[ij];
+        double Aij[9], Dj[9], L[9];
+        const int jd = diag[j];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) { Aij[t] = lu[(size_t)ij * 9 + t]; Dj[t] = lu[(size_t)jd * 9 + t]; }
+        mat3_mul(Aij, Dj, L);                                 // L_ij = A_ij * inv(A_jj)
+#pragma unroll
+        for (int t = 0; t < 9; ++t) lu[(size_t)ij * 9 + t] = L[t];
+        int jk = jd + 1, ik = ij + 1;
+        const int jend = rowptr[j + 1];
+        while (ik < iend && jk < jend) {
+            const int ci = colidx[ik], cj = colidx[jk];
+            if (ci == cj) {
+                double Ajk[9], B[9];
+#pragma unroll
+                for (int t = 0; t < 9; ++t) Ajk[t] = lu[(size_t)jk * 9 + t];
+                mat3_mul(L, Ajk, B);                          // B = L_ij * A_jk
+#pragma unroll
+                for (int t = 0; t < 9; ++t) lu[(size_t)ik * 9 + t] -= B[t];
+                ++ik; ++jk;
+            } else if (ci < cj) ++ik;
+            else ++jk;
+        }
+    }
+    double D[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) D[t] = lu[(size_t)idiag * 9 + t];
+    const double det = mat3_invert(D);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) lu[(size_t)idiag * 9 + t] = D[t];
+    if (!(det != 0.0) || isinf(det) || isnan(det)) atomicMin(bad_row, i);
+}
+
+// factors (BCRS order) -> the sweep programs' streaming layout
+__global__ void __launch_bounds__(256)
+repack_blocks_kernel(size_t nblk, const int* __restrict__ psrc, const double* __restrict__ lu,
+                     double* __restrict__ pval)
+{
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;     // one double each
+    if (e >= nblk * 9) return;
+    const size_t b = e / 9;
+    pval[e] = lu[(size_t)psrc[b] * 9 + (e - b * 9)];
+}
+__global__ void __launch_bounds__(256)
+repack_dinv_kernel(int N, const int* __restrict__ prow, const int* __restrict__ diag,
+                   const double* __restrict__ lu, double* __restrict__ pdinv)
+{
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (size_t)N * 9) return;
+    const size_t q = e / 9;
+    pdinv[e] = lu[(size_t)diag[prow[q]] * 9 + (e - q * 9)];
+}
+
+// ------------------------------------------------------------------------------------------
+// K4  ILU0 apply  v = w U^-1 L^-1 d   (Opm::ParallelOverlappingILU0::apply).
+// Persistent cooperative grid: CTA c runs its program (analysis.hpp) step by step; rows of
+// a step are independent; dependencies owned by the same CTA are ordered by __syncthreads,
+// dependencies owned by another CTA by a per-row flag carrying the sweep's epoch
+// (point-to-point, no grid-wide barrier -> the CTAs form a pipelined wavefront).
+// ------------------------------------------------------------------------------------------
+struct SweepDev {
+    const int* cta_step_ptr;
+    const int* step_row_ptr;
+    const int* prow;
+    const int* pblk_ptr;
+    const int* pcol;
+    const unsigned char* publish;
+    const double* pval;      // [nblk*9] program order
+    const double* pdinv;     // [N*9]    program-row order (upper only)
+};
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v)
+{
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+constexpr unsigned kSpinLimit = 1u << 22;
+
+template <bool LOWER>
+__global__ void __launch_bounds__(256)
+ilu0_sweep_kernel(SweepDev pg, const double* __restrict__ rhs, double* work, double* out,
+                  double w, int scale, int* flags, int epoch, int* err)
+{
+    // LOWER: rhs = d, work = yL (written), out unused.
+    // UPPER: rhs = yL, work = vU (unscaled, written, read by dependants), out = w * vU.
+    const int s_begin = pg.cta_step_ptr[blockIdx.x], s_end = pg.cta_step_ptr[blockIdx.x + 1];
+    for (int s = s_begin; s < s_end; ++s) {
+        const int q0 = pg.step_row_ptr[s], q1 = pg.step_row_ptr[s + 1];
+        for (int q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
+            const int row = pg.prow[q];
+            double r0 = rhs[(size_t)row * 3], r1 = rhs[(size_t)row * 3 + 1], r2 = rhs[(size_t)row * 3 + 2];
+            const int b0 = pg.pblk_ptr[q], b1 = pg.pblk_ptr[q + 1];
+            for (int b = b0; b < b1; ++b) {
+                const int c = pg.pcol[b];
+                const int j = c & ~kExtBitDev;
+                double y0, y1, y2;
+                if (c & kExtBitDev) {
+                    unsigned spins = 0;
+                    while (ld_acquire_gpu(flags + j) != epoch) {
+                        if (++spins > kSpinLimit) { atomicExch(err, 1); break; }
+                        if ((spins & 1023u) == 0 && *(volatile int*)err) break;
+                    }
+                    y0 = __ldcg(work + (size_t)j * 3); y1 = __ldcg(work + (size_t)j * 3 + 1); y2 = __ldcg(work + (size_t)j * 3 + 2);
+                } else {
+                    y0 = work[(size_t)j * 3]; y1 = work[(size_t)j * 3 + 1]; y2 = work[(size_t)j * 3 + 2];
+                }
+                const double* a = pg.pval + (size_t)b * 9;
+                r0 = fma(-a[0], y0, r0); r0 = fma(-a[1], y1, r0); r0 = fma(-a[2], y2, r0);
+                r1 = fma(-a[3], y0, r1); r1 = fma(-a[4], y1, r1); r1 = fma(-a[5], y2, r1);
+                r2 = fma(-a[6], y0, r2); r2 = fma(-a[7], y1, r2); r2 = fma(-a[8], y2, r2);
+            }
+            if (!LOWER) {
+                const double* di = pg.pdinv + (size_t)q * 9;
+                double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+                v0 = fma(di[0], r0, v0); v0 = fma(di[1], r1, v0); v0 = fma(di[2], r2, v0);
+                v1 = fma(di[3], r0, v1); v1 = fma(di[4], r1, v1); v1 = fma(di[5], r2, v1);
+                v2 = fma(di[6], r0, v2); v2 = fma(di[7], r1, v2); v2 = fma(di[8], r2, v2);
+                r0 = v0; r1 = v1; r2 = v2;
+                if (scale) { v0 *= w; v1 *= w; v2 *= w; }
+                out[(size_t)row * 3] = v0; out[(size_t)row * 3 + 1] = v1; out[(size_t)row * 3 + 2] = v2;
+            }
+            work[(size_t)row * 3] = r0; work[(size_t)row * 3 + 1] = r1; work[(size_t)row * 3 + 2] = r2;
+            if (pg.publish[q]) {
+                __threadfence();
+                st_release_gpu(flags + row, epoch);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1  interleave: nine CSC scalar blocks -> row-major 3x3 BCRS blocks
+// (formInterleavedSystem value scatter, ...Interleaved.cpp:178-193, with the matbalscale
+// row scaling of :234-236 folded in).  The gather map is built once per pattern on the device.
+// ------------------------------------------------------------------------------------------
+// one thread per (scalar block q, column c): locate every CSC entry in the BCRS pattern
+__global__ void __launch_bounds__(256)
+build_gather_map_kernel(int N, int q, const int* __restrict__ colptr, const int* __restrict__ rowidx,
+                        long long base, const int* __restrict__ rowptr, const int* __restrict__ colidx,
+                        long long* __restrict__ map9, int* bad)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= N) return;
+    for (int k = colptr[c]; k < colptr[c + 1]; ++k) {
+        const int row = rowidx[k];
+        int lo = rowptr[row], hi = rowptr[row + 1] - 1, pos = -1;
+        while (lo <= hi) {
+            const int mid = (lo + hi) >> 1;
+            const int cm = colidx[mid];
+            if (cm == c) { pos = mid; break; }
+            if (cm < c) lo = mid + 1; else hi = mid - 1;
+        }
+        if (pos < 0) { atomicExch(bad, 1); continue; }
+        map9[(size_t)pos * 9 + q] = base + k;
+    }
+}
+
+// one thread per output double: vals[slot][p1][p2] = cscval[map] * scale[p1]  (0 if absent)
+__global__ void __launch_bounds__(256)
+interleave_gather_kernel(size_t nvals, const long long* __restrict__ map9,
+                         const double* __restrict__ cscval, double s0, double s1, double s2,
+                         double* __restrict__ vals)
+{
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nvals) return;
+    const long long m = map9[e];
+    const int p1 = (int)((e % 9) / 3);
+    const double sc = p1 == 0 ? s0 : (p1 == 1 ? s1 : s2);
+    vals[e] = m >= 0 ? cscval[m] * sc : 0.0;
+}
+
+// a8  rhs interleave (+ scaling) and solution de-interleave (...Interleaved.cpp:263-269, 279-283)
+__global__ void __launch_bounds__(256)
+interleave_rhs_kernel(int N, const double* __restrict__ b_eqmajor, double s0, double s1, double s2,
+                      double* __restrict__ b_cellmajor)
+{
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (size_t)N * 3) return;
+    const size_t i = e / 3;
+    const int p = (int)(e - i * 3);
+    const double sc = p == 0 ? s0 : (p == 1 ? s1 : s2);
+    b_cellmajor[e] = b_eqmajor[(size_t)p * N + i] * sc;
+}
+__global__ void __launch_bounds__(256)
+deinterleave_x_kernel(int N, const double* __restrict__ x_cellmajor, double* __restrict__ dx_varmajor)
+{
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (size_t)N * 3) return;
+    const size_t p = e / N, i = e - p * N;
+    dx_varmajor[e] = x_cellmajor[i * 3 + p];
+}
+
+}  // namespace opmgpu

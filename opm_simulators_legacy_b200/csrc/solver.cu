@@ -1,0 +1,818 @@
+// C ABI (include/opm_gpu_solver.h) and host driver of the B200-native Newton-step linear
+// solver.  Replaces, behind NewtonIterationBlackoilInterface::computeNewtonIncrement, the
+// reference's formInterleavedSystem + ISTLSolver::solve
+// (opm/autodiff/NewtonIterationBlackoilInterleaved.cpp:110-194, :234-283;
+//  opm/autodiff/ISTLSolver.hpp:124-189, 201-211, 250-274, 283-306, 358-368).
+// There is no CPU fallback anywhere in this file.
+#include "../../include/opm_gpu_solver.h"
+#include "analysis.hpp"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace opmgpu;
+
+namespace {
+
+std::string g_create_error;
+
+template <class T>
+struct DevArr {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc((void**)&p, std::max<size_t>(n, 1) * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct ProgramDevMem {
+    DevArr<int> cta_step_ptr, step_row_ptr, prow, pblk_ptr, pcol, psrc;
+    DevArr<unsigned char> publish;
+    DevArr<double> pval, pdinv;
+    size_t nblk = 0;
+    int P = 0;
+    void release()
+    {
+        cta_step_ptr.release(); step_row_ptr.release(); prow.release(); pblk_ptr.release();
+        pcol.release(); psrc.release(); publish.release(); pval.release(); pdinv.release();
+    }
+};
+
+}  // namespace
+
+struct opmgpu_solver {
+    int device = 0;
+    int sm_count = 0;
+    int sweep_ctas = 0;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
+    std::string err;
+    long long launches = 0;
+
+    // pattern
+    bool have_pattern = false, have_values = false, have_factors = false;
+    int N = 0, nnzb = 0, nlevL = 0, nlevU = 0;
+    PatternAnalysis an;
+    DevArr<int> d_rowptr, d_colidx, d_diag, d_lvl_rows;
+    ProgramDevMem progL, progU;
+
+    // values and factors
+    DevArr<double> d_vals_own, d_lu;
+    const double* d_vals = nullptr;
+
+    // vectors (3N each)
+    DevArr<double> d_x, d_r, d_rt, d_p, d_v, d_t, d_y, d_yL, d_vU, d_tmp, d_tmp2;
+    DevArr<double> d_S, d_partials;
+    DevArr<unsigned> d_ticket;
+    DevArr<int> d_flags, d_err, d_bad;
+    int epoch = 0;
+    double* h_S = nullptr;       // pinned
+    int* h_flags2 = nullptr;     // pinned: [0] sweep watchdog, [1] bad row / bad pattern
+    cudaEvent_t ev[8] = {};
+
+    // CSC front end cache
+    std::vector<std::vector<int>> csc_colptr, csc_rowidx;
+    std::vector<long long> csc_base;
+    long long csc_total = 0;
+    bool csc_full_pattern = false;
+    DevArr<long long> d_map9;
+    DevArr<double> d_cscval, d_rhs_stage;
+
+    std::vector<double> history;
+
+    int fail(cudaError_t e, const char* what)
+    {
+        char buf[512];
+        snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+        err = buf;
+        return OPMGPU_CUDA_ERROR;
+    }
+    int bad(const char* what) { err = what; return OPMGPU_BAD_ARGUMENT; }
+    ReduceWs ws() { return ReduceWs{d_partials.p, d_ticket.p}; }
+};
+
+#define CK(call)                                                          \
+    do {                                                                  \
+        cudaError_t e__ = (call);                                         \
+        if (e__ != cudaSuccess) return h->fail(e__, #call);               \
+    } while (0)
+
+namespace {
+
+constexpr int kVecBlocks = 148 * 4;      // fixed launch shape of the vector kernels (determinism)
+
+template <class T>
+int upload(opmgpu_handle h, DevArr<T>& d, const std::vector<T>& v)
+{
+    CK(d.ensure(v.size()));
+    if (!v.empty()) CK(cudaMemcpyAsync(d.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    return 0;
+}
+
+int upload_program(opmgpu_handle h, const SweepProgram& p, ProgramDevMem& d, bool upper)
+{
+    int rc;
+    if ((rc = upload(h, d.cta_step_ptr, p.cta_step_ptr))) return rc;
+    if ((rc = upload(h, d.step_row_ptr, p.step_row_ptr))) return rc;
+    if ((rc = upload(h, d.prow, p.prow))) return rc;
+    if ((rc = upload(h, d.pblk_ptr, p.pblk_ptr))) return rc;
+    if ((rc = upload(h, d.pcol, p.pcol))) return rc;
+    if ((rc = upload(h, d.psrc, p.psrc))) return rc;
+    if ((rc = upload(h, d.publish, p.publish))) return rc;
+    d.nblk = p.pcol.size();
+    d.P = p.P;
+    CK(d.pval.ensure(d.nblk * 9));
+    if (upper) CK(d.pdinv.ensure((size_t)h->N * 9));
+    return 0;
+}
+
+SweepDev sweep_dev(const ProgramDevMem& d)
+{
+    SweepDev s;
+    s.cta_step_ptr = d.cta_step_ptr.p; s.step_row_ptr = d.step_row_ptr.p; s.prow = d.prow.p;
+    s.pblk_ptr = d.pblk_ptr.p; s.pcol = d.pcol.p; s.publish = d.publish.p;
+    s.pval = d.pval.p; s.pdinv = d.pdinv.p;
+    return s;
+}
+
+int ensure_vectors(opmgpu_handle h)
+{
+    const size_t n = (size_t)h->N * 3;
+    CK(h->d_x.ensure(n)); CK(h->d_r.ensure(n)); CK(h->d_rt.ensure(n)); CK(h->d_p.ensure(n));
+    CK(h->d_v.ensure(n)); CK(h->d_t.ensure(n)); CK(h->d_y.ensure(n)); CK(h->d_yL.ensure(n));
+    CK(h->d_vU.ensure(n)); CK(h->d_tmp.ensure(n)); CK(h->d_tmp2.ensure(n));
+    return 0;
+}
+
+int set_pattern(opmgpu_handle h, int N, int nnzb, const int* rowptr, const int* colidx)
+{
+    if (N < 1 || nnzb < N || rowptr[0] != 0 || rowptr[N] != nnzb) return h->bad("bad BCRS pattern sizes");
+    for (int i = 0; i < N; ++i) {
+        if (rowptr[i + 1] < rowptr[i]) return h->bad("rowptr not monotone");
+        for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+            if (colidx[k] < 0 || colidx[k] >= N) return h->bad("column index out of range");
+            if (k > rowptr[i] && colidx[k] <= colidx[k - 1]) return h->bad("columns not strictly ascending in a row");
+        }
+    }
+    h->have_pattern = h->have_values = h->have_factors = false;
+    analyse_pattern(N, rowptr, colidx, h->sweep_ctas, h->an);
+    if (h->an.missing_diag_row >= 0) {
+        h->err = "diagonal entry missing in block row " + std::to_string(h->an.missing_diag_row);
+        return OPMGPU_SINGULAR_BLOCK;
+    }
+    h->N = N; h->nnzb = nnzb;
+    CK(h->d_rowptr.ensure((size_t)N + 1));
+    CK(h->d_colidx.ensure(nnzb));
+    CK(cudaMemcpyAsync(h->d_rowptr.p, rowptr, sizeof(int) * ((size_t)N + 1), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_colidx.p, colidx, sizeof(int) * (size_t)nnzb, cudaMemcpyHostToDevice, h->stream));
+    int rc;
+    if ((rc = upload(h, h->d_diag, h->an.diag))) return rc;
+    if ((rc = upload(h, h->d_lvl_rows, h->an.lvl_rows))) return rc;
+    if ((rc = upload_program(h, h->an.lower, h->progL, false))) return rc;
+    if ((rc = upload_program(h, h->an.upper, h->progU, true))) return rc;
+    CK(h->d_lu.ensure((size_t)nnzb * 9));
+    if ((rc = ensure_vectors(h))) return rc;
+    CK(h->d_flags.ensure(N));
+    CK(cudaMemsetAsync(h->d_flags.p, 0, sizeof(int) * (size_t)N, h->stream));
+    h->epoch = 0;
+    CK(cudaStreamSynchronize(h->stream));      // host vectors of the analysis may now be dropped
+    // keep only what the host still needs
+    h->nlevL = h->an.lower.nlevels; h->nlevU = h->an.upper.nlevels;
+    h->an.lower = SweepProgram(); h->an.upper = SweepProgram();
+    h->have_pattern = true;
+    return OPMGPU_OK;
+}
+
+int launch_spmv(opmgpu_handle h, int mode, const double* x, double* y, const double* w1)
+{
+    const long long threads = 3LL * h->N;
+    const unsigned grid = (unsigned)((threads + 255) / 256);
+    if (mode != 0 && grid > kMaxRedBlocks) {
+        // fused reduction epilogue has a bounded partial array: fall back to SpMV + dot kernels
+        spmv3_kernel<0><<<grid, 256, 0, h->stream>>>(h->N, h->d_rowptr.p, h->d_colidx.p, h->d_vals, x, y, nullptr, h->d_S.p, h->ws());
+        h->launches++;
+        return -100;
+    }
+    if (mode == 0) spmv3_kernel<0><<<grid, 256, 0, h->stream>>>(h->N, h->d_rowptr.p, h->d_colidx.p, h->d_vals, x, y, w1, h->d_S.p, h->ws());
+    else if (mode == 1) spmv3_kernel<1><<<grid, 256, 0, h->stream>>>(h->N, h->d_rowptr.p, h->d_colidx.p, h->d_vals, x, y, w1, h->d_S.p, h->ws());
+    else spmv3_kernel<2><<<grid, 256, 0, h->stream>>>(h->N, h->d_rowptr.p, h->d_colidx.p, h->d_vals, x, y, w1, h->d_S.p, h->ws());
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// separate (non-fused) dots for systems too large for the fused epilogue
+__global__ void dot_to_slot_kernel(size_t n, const double* __restrict__ a, const double* __restrict__ b,
+                                   double* S, int slot, ReduceWs ws)
+{
+    double v[1] = {0.0};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        v[0] = fma(a[i], b[i], v[0]);
+    grid_reduce<1>(v, ws, [=](double (&t)[1]) { S[slot] = t[0]; });
+}
+
+int spmv_with_dots(opmgpu_handle h, int mode, const double* x, double* y, const double* w1)
+{
+    int rc = launch_spmv(h, mode, x, y, w1);
+    if (rc == -100) {
+        const size_t n = (size_t)h->N * 3;
+        if (mode == 1) {
+            dot_to_slot_kernel<<<kVecBlocks, 256, 0, h->stream>>>(n, w1, y, h->d_S.p, S_H, h->ws());
+            h->launches++;
+        } else {
+            dot_to_slot_kernel<<<kVecBlocks, 256, 0, h->stream>>>(n, y, w1, h->d_S.p, S_TR, h->ws());
+            dot_to_slot_kernel<<<kVecBlocks, 256, 0, h->stream>>>(n, y, y, h->d_S.p, S_TT, h->ws());
+            h->launches += 2;
+        }
+        CK(cudaGetLastError());
+        rc = 0;
+    }
+    return rc;
+}
+
+int factor(opmgpu_handle h, int* bad_row)
+{
+    if (!h->have_values) return h->bad("no matrix values set");
+    const size_t nv = (size_t)h->nnzb * 9;
+    CK(cudaMemcpyAsync(h->d_lu.p, h->d_vals, nv * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    const int big = 0x7fffffff;
+    CK(cudaMemcpyAsync(h->d_bad.p, &big, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    const std::vector<int>& lp = h->an.lvl_ptr;
+    for (size_t l = 0; l + 1 < lp.size(); ++l) {
+        const int n = lp[l + 1] - lp[l];
+        if (n <= 0) continue;
+        ilu0_factor_level_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(
+            h->d_lvl_rows.p, lp[l], lp[l + 1], h->d_rowptr.p, h->d_colidx.p, h->d_diag.p, h->d_lu.p, h->d_bad.p);
+        h->launches++;
+    }
+    CK(cudaGetLastError());
+    // stream the factors into the sweep programs' layout
+    if (h->progL.nblk) {
+        const size_t e = h->progL.nblk * 9;
+        repack_blocks_kernel<<<(unsigned)((e + 255) / 256), 256, 0, h->stream>>>(h->progL.nblk, h->progL.psrc.p, h->d_lu.p, h->progL.pval.p);
+        h->launches++;
+    }
+    if (h->progU.nblk) {
+        const size_t e = h->progU.nblk * 9;
+        repack_blocks_kernel<<<(unsigned)((e + 255) / 256), 256, 0, h->stream>>>(h->progU.nblk, h->progU.psrc.p, h->d_lu.p, h->progU.pval.p);
+        h->launches++;
+    }
+    {
+        const size_t e = (size_t)h->N * 9;
+        repack_dinv_kernel<<<(unsigned)((e + 255) / 256), 256, 0, h->stream>>>(h->N, h->progU.prow.p, h->d_diag.p, h->d_lu.p, h->progU.pdinv.p);
+        h->launches++;
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(&h->h_flags2[1], h->d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->h_flags2[1] != big) {
+        if (bad_row) *bad_row = h->h_flags2[1];
+        h->err = "singular diagonal block in ILU0 at block row " + std::to_string(h->h_flags2[1]);
+        h->have_factors = false;
+        return OPMGPU_SINGULAR_BLOCK;
+    }
+    if (bad_row) *bad_row = -1;
+    h->have_factors = true;
+    return OPMGPU_OK;
+}
+
+// v = w U^-1 L^-1 d, all device pointers; asynchronous
+int apply_precond(opmgpu_handle h, double w, const double* d, double* v)
+{
+    const int scale = std::fabs(w - 1.0) > 1e-15 ? 1 : 0;      // relaxation_ flag of the reference
+    {
+        SweepDev pg = sweep_dev(h->progL);
+        const double* rhs = d; double* work = h->d_yL.p; double* out = nullptr;
+        int* flags = h->d_flags.p; int epoch = ++h->epoch; int* err = h->d_err.p;
+        void* args[] = {&pg, &rhs, &work, &out, &w, (void*)&scale, &flags, &epoch, &err};
+        CK(cudaLaunchCooperativeKernel((void*)ilu0_sweep_kernel<true>, dim3(h->progL.P), dim3(256), args, 0, h->stream));
+        h->launches++;
+    }
+    {
+        SweepDev pg = sweep_dev(h->progU);
+        const double* rhs = h->d_yL.p; double* work = h->d_vU.p; double* out = v;
+        int* flags = h->d_flags.p; int epoch = ++h->epoch; int* err = h->d_err.p;
+        void* args[] = {&pg, &rhs, &work, &out, &w, (void*)&scale, &flags, &epoch, &err};
+        CK(cudaLaunchCooperativeKernel((void*)ilu0_sweep_kernel<false>, dim3(h->progU.P), dim3(256), args, 0, h->stream));
+        h->launches++;
+    }
+    return 0;
+}
+
+int read_scalars(opmgpu_handle h)
+{
+    CK(cudaMemcpyAsync(h->h_S, h->d_S.p, sizeof(double) * S_COUNT, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(&h->h_flags2[0], h->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->h_flags2[0]) {
+        h->err = "ILU0 sweep watchdog: a dependency flag was never published";
+        return OPMGPU_CUDA_ERROR;
+    }
+    return 0;
+}
+
+// Dune::BiCGSTABSolver::apply on device vectors.  In: d_r = b (x0 = 0).  Out: d_x.
+int bicgstab(opmgpu_handle h, const opmgpu_params* prm, opmgpu_result* res)
+{
+    const double EPSILON = 1e-80;
+    const size_t n = (size_t)h->N * 3;
+    const double red = prm->linear_solver_reduction, w = prm->ilu_relaxation;
+    const int maxit = prm->linear_solver_maxiter, half_limit = prm->max_half_steps;
+    int rc;
+    h->history.clear();
+    CK(cudaMemsetAsync(h->d_x.p, 0, n * sizeof(double), h->stream));
+    CK(cudaMemcpyAsync(h->d_rt.p, h->d_r.p, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    bicg_init_kernel<<<kVecBlocks, 256, 0, h->stream>>>(n, h->d_r.p, h->d_S.p, h->ws());
+    h->launches++;
+    if ((rc = read_scalars(h))) return rc;
+    const double norm0 = std::sqrt(h->h_S[S_NRM2]);
+    double norm = norm0, rho = 1.0, omega = 1.0, it = 0.0;
+    int half = 0, status = OPMGPU_OK, converged = 0;
+    res->norm0 = norm0;
+    if (norm < norm0 * red || norm < 1e-30) {
+        res->converged = 1; res->iterations = 0; res->reduction = 0.0; res->half_steps = 0;
+        return OPMGPU_OK;
+    }
+    for (it = 0.5; it < maxit; it += 0.5) {
+        if (half_limit >= 0 && half >= half_limit) break;
+        if (std::fabs(rho) <= EPSILON || std::fabs(omega) <= EPSILON) { status = OPMGPU_BREAKDOWN; break; }
+        if (it < 1) {
+            CK(cudaMemcpyAsync(h->d_p.p, h->d_r.p, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        } else {
+            bicg_update_p_kernel<<<kVecBlocks, 256, 0, h->stream>>>(n, h->d_p.p, h->d_r.p, h->d_v.p, h->d_S.p);
+            h->launches++;
+        }
+        if ((rc = apply_precond(h, w, h->d_p.p, h->d_y.p))) return rc;
+        if ((rc = spmv_with_dots(h, 1, h->d_y.p, h->d_v.p, h->d_rt.p))) return rc;
+        bicg_update1_kernel<<<kVecBlocks, 256, 0, h->stream>>>(n, h->d_x.p, h->d_r.p, h->d_y.p, h->d_v.p, h->d_S.p, h->ws());
+        h->launches++;
+        if ((rc = read_scalars(h))) return rc;
+        if (std::fabs(h->h_S[S_H]) < EPSILON) { status = OPMGPU_BREAKDOWN; break; }
+        norm = std::sqrt(h->h_S[S_NRM2]);
+        h->history.push_back(norm);
+        ++half;
+        if (norm < norm0 * red) { converged = 1; break; }
+        it += 0.5;
+        if (half_limit >= 0 && half >= half_limit) break;
+
+        if ((rc = apply_precond(h, w, h->d_r.p, h->d_y.p))) return rc;
+        if ((rc = spmv_with_dots(h, 2, h->d_y.p, h->d_t.p, h->d_r.p))) return rc;
+        bicg_update2_kernel<<<kVecBlocks, 256, 0, h->stream>>>(n, h->d_x.p, h->d_r.p, h->d_y.p, h->d_t.p, h->d_rt.p, h->d_S.p, h->ws());
+        h->launches++;
+        if ((rc = read_scalars(h))) return rc;
+        omega = h->h_S[S_OMEGA];
+        rho = h->h_S[S_RHO_OLD];
+        norm = std::sqrt(h->h_S[S_NRM2]);
+        h->history.push_back(norm);
+        ++half;
+        if (norm < norm0 * red || norm < 1e-30) { converged = 1; break; }
+    }
+    if (it > maxit) it = maxit;
+    res->iterations = (int)std::ceil(it);
+    res->converged = converged;
+    res->half_steps = half;
+    res->reduction = norm / norm0;
+    if (status == OPMGPU_OK && !converged) status = OPMGPU_NOT_CONVERGED;
+    if (status == OPMGPU_BREAKDOWN) h->err = "breakdown in BiCGSTAB (rho, omega or h below 1e-80)";
+    return status;
+}
+
+float ev_ms(cudaEvent_t a, cudaEvent_t b)
+{
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    return ms;
+}
+
+// factor + BiCGStab on the values/rhs already in place (d_vals, d_r); leaves the result in d_x
+int solve_resident(opmgpu_handle h, const opmgpu_params* prm, opmgpu_result* res)
+{
+    cudaEventRecord(h->ev[0], h->stream);
+    int badrow = -1;
+    int rc = factor(h, &badrow);
+    cudaEventRecord(h->ev[1], h->stream);
+    if (rc) { res->bad_row = badrow; return rc; }
+    rc = bicgstab(h, prm, res);
+    cudaEventRecord(h->ev[2], h->stream);
+    cudaEventSynchronize(h->ev[2]);
+    res->ms_factor = ev_ms(h->ev[0], h->ev[1]);
+    res->ms_solve = ev_ms(h->ev[1], h->ev[2]);
+    if (rc == OPMGPU_NOT_CONVERGED && prm->linear_solver_ignoreconvergencefailure) rc = OPMGPU_OK;
+    return rc;
+}
+
+bool same_csc_pattern(opmgpu_handle h, int N, const opmgpu_csc* b, bool full)
+{
+    if (!h->have_pattern || h->csc_colptr.size() != 9 || h->N != N || h->csc_full_pattern != full) return false;
+    for (int q = 0; q < 9; ++q) {
+        if ((int)h->csc_colptr[q].size() != N + 1) return false;
+        if (std::memcmp(h->csc_colptr[q].data(), b[q].colptr, sizeof(int) * ((size_t)N + 1))) return false;
+        const size_t nnz = (size_t)b[q].colptr[N];
+        if (h->csc_rowidx[q].size() != nnz) return false;
+        if (nnz && std::memcmp(h->csc_rowidx[q].data(), b[q].rowidx, sizeof(int) * nnz)) return false;
+    }
+    return true;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+void opmgpu_default_params(opmgpu_params* p)
+{
+    // FlowLinearSolverParameters::reset() of opm-simulators 2019.04 (not under /root/reference;
+    // the same keys with CPR's defaults are visible at NewtonIterationBlackoilCPR.cpp:61-66).
+    p->linear_solver_reduction = 1e-2;
+    p->linear_solver_maxiter = 150;
+    p->ilu_relaxation = 0.9;
+    p->linear_solver_verbosity = 0;
+    p->linear_solver_ignoreconvergencefailure = 0;
+    p->require_full_sparsity_pattern = 0;
+    p->max_half_steps = -1;
+}
+
+const char* opmgpu_last_error(opmgpu_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int opmgpu_create(int device, opmgpu_handle* out)
+{
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                         " (this solver has no CPU fallback)";
+        return OPMGPU_CUDA_ERROR;
+    }
+    if (device < 0 || device >= ndev) { g_create_error = "device index out of range"; return OPMGPU_BAD_ARGUMENT; }
+    cudaDeviceProp prop;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+        g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+        return OPMGPU_CUDA_ERROR;
+    }
+    if (prop.major != 10) {
+        g_create_error = "device is sm_" + std::to_string(prop.major * 10 + prop.minor) +
+                         "; this library is built for sm_100a (B200) only";
+        return OPMGPU_CUDA_ERROR;
+    }
+    opmgpu_handle h = new opmgpu_solver();
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    int per_sm = 1;
+    if (const char* s = getenv("OPMGPU_SWEEP_CTAS_PER_SM")) per_sm = std::max(1, atoi(s));
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ilu0_sweep_kernel<true>, 256, 0);
+    per_sm = std::min(per_sm, std::max(occ, 1));
+    h->sweep_ctas = h->sm_count * per_sm;
+    if ((e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e);
+        delete h;
+        return OPMGPU_CUDA_ERROR;
+    }
+    h->stream = h->own_stream;
+    bool ok = cudaMallocHost((void**)&h->h_S, sizeof(double) * S_COUNT) == cudaSuccess &&
+              cudaMallocHost((void**)&h->h_flags2, sizeof(int) * 4) == cudaSuccess &&
+              h->d_S.ensure(S_COUNT) == cudaSuccess && h->d_partials.ensure((size_t)4 * kMaxRedBlocks) == cudaSuccess &&
+              h->d_ticket.ensure(1) == cudaSuccess && h->d_err.ensure(1) == cudaSuccess && h->d_bad.ensure(1) == cudaSuccess;
+    for (int i = 0; i < 8 && ok; ++i) ok = cudaEventCreate(&h->ev[i]) == cudaSuccess;
+    if (ok) {
+        cudaMemset(h->d_S.p, 0, sizeof(double) * S_COUNT);
+        cudaMemset(h->d_ticket.p, 0, sizeof(unsigned));
+        cudaMemset(h->d_err.p, 0, sizeof(int));
+    } else {
+        g_create_error = "allocation of solver workspace failed";
+        delete h;
+        return OPMGPU_CUDA_ERROR;
+    }
+    *out = h;
+    return OPMGPU_OK;
+}
+
+int opmgpu_destroy(opmgpu_handle h)
+{
+    if (!h) return OPMGPU_OK;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    h->d_rowptr.release(); h->d_colidx.release(); h->d_diag.release(); h->d_lvl_rows.release();
+    h->progL.release(); h->progU.release();
+    h->d_vals_own.release(); h->d_lu.release();
+    h->d_x.release(); h->d_r.release(); h->d_rt.release(); h->d_p.release(); h->d_v.release();
+    h->d_t.release(); h->d_y.release(); h->d_yL.release(); h->d_vU.release(); h->d_tmp.release(); h->d_tmp2.release();
+    h->d_S.release(); h->d_partials.release(); h->d_ticket.release(); h->d_flags.release();
+    h->d_err.release(); h->d_bad.release(); h->d_map9.release(); h->d_cscval.release(); h->d_rhs_stage.release();
+    if (h->h_S) cudaFreeHost(h->h_S);
+    if (h->h_flags2) cudaFreeHost(h->h_flags2);
+    for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return OPMGPU_OK;
+}
+
+int opmgpu_set_stream(opmgpu_handle h, void* cuda_stream)
+{
+    if (!h) return OPMGPU_BAD_ARGUMENT;
+    cudaStreamSynchronize(h->stream);
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return OPMGPU_OK;
+}
+
+int opmgpu_set_pattern_bcrs(opmgpu_handle h, int N, int nnzb, const int* rowptr, const int* colidx)
+{
+    if (!h || !rowptr || !colidx) return OPMGPU_BAD_ARGUMENT;
+    CK(cudaSetDevice(h->device));
+    h->csc_colptr.clear(); h->csc_rowidx.clear();
+    return set_pattern(h, N, nnzb, rowptr, colidx);
+}
+
+int opmgpu_set_values_bcrs3(opmgpu_handle h, const double* vals)
+{
+    if (!h || !vals) return OPMGPU_BAD_ARGUMENT;
+    if (!h->have_pattern) return h->bad("set the pattern first");
+    CK(cudaSetDevice(h->device));
+    const size_t nv = (size_t)h->nnzb * 9;
+    CK(h->d_vals_own.ensure(nv));
+    CK(cudaMemcpyAsync(h->d_vals_own.p, vals, nv * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->d_vals = h->d_vals_own.p;
+    h->have_values = true; h->have_factors = false;
+    return OPMGPU_OK;
+}
+
+int opmgpu_set_values_bcrs3_dev(opmgpu_handle h, const double* vals_dev)
+{
+    if (!h || !vals_dev) return OPMGPU_BAD_ARGUMENT;
+    if (!h->have_pattern) return h->bad("set the pattern first");
+    h->d_vals = vals_dev;
+    h->have_values = true; h->have_factors = false;
+    return OPMGPU_OK;
+}
+
+int opmgpu_spmv_dev(opmgpu_handle h, const double* x_dev, double* y_dev)
+{
+    if (!h || !h->have_values) return OPMGPU_BAD_ARGUMENT;
+    CK(cudaSetDevice(h->device));
+    return launch_spmv(h, 0, x_dev, y_dev, nullptr);
+}
+
+int opmgpu_spmv(opmgpu_handle h, const double* x, double* y)
+{
+    if (!h || !h->have_values) return OPMGPU_BAD_ARGUMENT;
+    CK(cudaSetDevice(h->device));
+    const size_t n = (size_t)h->N * 3;
+    CK(cudaMemcpyAsync(h->d_tmp.p, x, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    int rc = launch_spmv(h, 0, h->d_tmp.p, h->d_tmp2.p, nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(y, h->d_tmp2.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return OPMGPU_OK;
+}
+
+int opmgpu_ilu0_factor(opmgpu_handle h, int* bad_row)
+{
+    if (!h) return OPMGPU_BAD_ARGUMENT;
+    CK(cudaSetDevice(h->device));
+    return factor(h, bad_row);
+}
+
+int opmgpu_ilu0_get_factors(opmgpu_handle h, double* lu)
+{
+    if (!h || !h->have_factors) return OPMGPU_BAD_ARGUMENT;
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(lu, h->d_lu.p, (size_t)h->nnzb * 9 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return OPMGPU_OK;
+}
+
+int opmgpu_ilu0_apply_dev(opmgpu_handle h, double w, const double* d_dev, double* v_dev)
+{
+    if (!h || !h->have_factors) return OPMGPU_BAD_ARGUMENT;
+    CK(cudaSetDevice(h->device));
+    return apply_precond(h, w, d_dev, v_dev);
+}
+
+int opmgpu_ilu0_apply(opmgpu_handle h, double w, const double* d, double* v)
+{
+    if (!h || !h->have_factors) return OPMGPU_BAD_ARGUMENT;
+    CK(cudaSetDevice(h->device));
+    const size_t n = (size_t)h->N * 3;
+    CK(cudaMemcpyAsync(h->d_tmp.p, d, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    int rc = apply_precond(h, w, h->d_tmp.p, h->d_tmp2.p);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(v, h->d_tmp2.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(&h->h_flags2[0], h->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->h_flags2[0]) { h->err = "ILU0 sweep watchdog: a dependency flag was never published"; return OPMGPU_CUDA_ERROR; }
+    return OPMGPU_OK;
+}
+
+int opmgpu_dot(opmgpu_handle h, const double* x, const double* y, int n, double* out)
+{
+    if (!h || n < 0) return OPMGPU_BAD_ARGUMENT;
+    CK(cudaSetDevice(h->device));
+    DevArr<double> a, b;
+    CK(a.ensure(n)); CK(b.ensure(n));
+    CK(cudaMemcpyAsync(a.p, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(b.p, y, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    dot_kernel<<<kVecBlocks, 256, 0, h->stream>>>((size_t)n, a.p, b.p, h->d_S.p, h->ws());
+    h->launches++;
+    CK(cudaMemcpyAsync(h->h_S, h->d_S.p, sizeof(double) * S_COUNT, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    *out = h->h_S[S_DOT];
+    a.release(); b.release();
+    return OPMGPU_OK;
+}
+
+int opmgpu_solve_bcrs3_dev(opmgpu_handle h, const double* vals_dev, const double* rhs_dev, double* x_dev,
+                           const opmgpu_params* params, opmgpu_result* result)
+{
+    if (!h || !vals_dev || !rhs_dev || !x_dev || !params || !result) return OPMGPU_BAD_ARGUMENT;
+    if (!h->have_pattern) return h->bad("set the pattern first");
+    std::memset(result, 0, sizeof *result);
+    result->bad_row = -1;
+    CK(cudaSetDevice(h->device));
+    const size_t n = (size_t)h->N * 3;
+    h->d_vals = vals_dev;
+    h->have_values = true; h->have_factors = false;
+    CK(cudaMemcpyAsync(h->d_r.p, rhs_dev, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    int rc = solve_resident(h, params, result);
+    if (rc == OPMGPU_OK || rc == OPMGPU_NOT_CONVERGED) {
+        CK(cudaMemcpyAsync(x_dev, h->d_x.p, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    return rc;
+}
+
+int opmgpu_solve_bcrs3(opmgpu_handle h, const double* vals, const double* rhs, double* x,
+                       const opmgpu_params* params, opmgpu_result* result)
+{
+    if (!h || !vals || !rhs || !x || !params || !result) return OPMGPU_BAD_ARGUMENT;
+    if (!h->have_pattern) return h->bad("set the pattern first");
+    std::memset(result, 0, sizeof *result);
+    result->bad_row = -1;
+    CK(cudaSetDevice(h->device));
+    const size_t n = (size_t)h->N * 3, nv = (size_t)h->nnzb * 9;
+    CK(h->d_vals_own.ensure(nv));
+    cudaEventRecord(h->ev[3], h->stream);
+    CK(cudaMemcpyAsync(h->d_vals_own.p, vals, nv * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_r.p, rhs, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    cudaEventRecord(h->ev[4], h->stream);
+    h->d_vals = h->d_vals_own.p;
+    h->have_values = true; h->have_factors = false;
+    int rc = solve_resident(h, params, result);
+    result->ms_h2d = ev_ms(h->ev[3], h->ev[4]);
+    if (rc == OPMGPU_OK || rc == OPMGPU_NOT_CONVERGED) {
+        cudaEventRecord(h->ev[5], h->stream);
+        CK(cudaMemcpyAsync(x, h->d_x.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        cudaEventRecord(h->ev[6], h->stream);
+        CK(cudaStreamSynchronize(h->stream));
+        result->ms_d2h = ev_ms(h->ev[5], h->ev[6]);
+    }
+    return rc;
+}
+
+int opmgpu_solve_from_csc_blocks(opmgpu_handle h, int N, const opmgpu_csc blocks[9],
+                                 const double matbalscale[3], const double* rhs_eqmajor,
+                                 double* dx_varmajor, const opmgpu_params* params, opmgpu_result* result)
+{
+    if (!h || !blocks || !matbalscale || !rhs_eqmajor || !dx_varmajor || !params || !result || N < 1)
+        return OPMGPU_BAD_ARGUMENT;
+    std::memset(result, 0, sizeof *result);
+    result->bad_row = -1;
+    CK(cudaSetDevice(h->device));
+    const bool full = params->require_full_sparsity_pattern != 0;
+    if (!same_csc_pattern(h, N, blocks, full)) {
+        cudaEventRecord(h->ev[3], h->stream);
+        // pattern = union of the pressure-derivative patterns (all nine when required)
+        std::vector<CscView> sel;
+        for (int p1 = 0; p1 < 3; ++p1) sel.push_back({blocks[p1 * 3].colptr, blocks[p1 * 3].rowidx});
+        if (full)
+            for (int p1 = 0; p1 < 3; ++p1)
+                for (int p2 = 1; p2 < 3; ++p2) sel.push_back({blocks[p1 * 3 + p2].colptr, blocks[p1 * 3 + p2].rowidx});
+        std::vector<int> rowptr, colidx;
+        union_pattern_from_csc(N, sel.data(), (int)sel.size(), rowptr, colidx);
+        int rc = set_pattern(h, N, rowptr[N], rowptr.data(), colidx.data());
+        if (rc) return rc;
+        // cache the CSC index arrays (host, for the next call's comparison) and build the gather map
+        h->csc_colptr.assign(9, {}); h->csc_rowidx.assign(9, {}); h->csc_base.assign(10, 0);
+        for (int q = 0; q < 9; ++q) {
+            h->csc_colptr[q].assign(blocks[q].colptr, blocks[q].colptr + N + 1);
+            h->csc_rowidx[q].assign(blocks[q].rowidx, blocks[q].rowidx + blocks[q].colptr[N]);
+            h->csc_base[q + 1] = h->csc_base[q] + blocks[q].colptr[N];
+        }
+        h->csc_total = h->csc_base[9];
+        h->csc_full_pattern = full;
+        const size_t nmap = (size_t)h->nnzb * 9;
+        CK(h->d_map9.ensure(nmap));
+        CK(cudaMemsetAsync(h->d_map9.p, 0xff, nmap * sizeof(long long), h->stream));
+        CK(cudaMemsetAsync(h->d_bad.p, 0, sizeof(int), h->stream));
+        DevArr<int> d_cp, d_ri;
+        CK(d_cp.ensure((size_t)N + 1));
+        size_t maxnnz = 1;
+        for (int q = 0; q < 9; ++q) maxnnz = std::max(maxnnz, h->csc_rowidx[q].size());
+        CK(d_ri.ensure(maxnnz));
+        for (int q = 0; q < 9; ++q) {
+            CK(cudaMemcpyAsync(d_cp.p, h->csc_colptr[q].data(), sizeof(int) * ((size_t)N + 1), cudaMemcpyHostToDevice, h->stream));
+            if (!h->csc_rowidx[q].empty())
+                CK(cudaMemcpyAsync(d_ri.p, h->csc_rowidx[q].data(), sizeof(int) * h->csc_rowidx[q].size(), cudaMemcpyHostToDevice, h->stream));
+            build_gather_map_kernel<<<(N + 255) / 256, 256, 0, h->stream>>>(N, q, d_cp.p, d_ri.p, h->csc_base[q],
+                                                                            h->d_rowptr.p, h->d_colidx.p, h->d_map9.p, h->d_bad.p);
+            h->launches++;
+        }
+        CK(cudaMemcpyAsync(&h->h_flags2[1], h->d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        cudaEventRecord(h->ev[4], h->stream);
+        CK(cudaStreamSynchronize(h->stream));
+        d_cp.release(); d_ri.release();
+        result->ms_analysis = ev_ms(h->ev[3], h->ev[4]);
+        if (h->h_flags2[1]) {
+            h->have_pattern = false;
+            h->err = "Jacobian entry outside the interleaved sparsity pattern (set require_full_sparsity_pattern)";
+            return OPMGPU_BAD_PATTERN;
+        }
+        CK(h->d_cscval.ensure((size_t)std::max<long long>(h->csc_total, 1)));
+        CK(h->d_rhs_stage.ensure((size_t)N * 3));
+        CK(h->d_vals_own.ensure(nmap));
+    }
+    const size_t n = (size_t)N * 3, nv = (size_t)h->nnzb * 9;
+    cudaEventRecord(h->ev[3], h->stream);
+    for (int q = 0; q < 9; ++q) {
+        const size_t nnz = (size_t)(h->csc_base[q + 1] - h->csc_base[q]);
+        if (nnz) CK(cudaMemcpyAsync(h->d_cscval.p + h->csc_base[q], blocks[q].val, nnz * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    }
+    CK(cudaMemcpyAsync(h->d_rhs_stage.p, rhs_eqmajor, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    cudaEventRecord(h->ev[4], h->stream);
+    interleave_gather_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, h->stream>>>(nv, h->d_map9.p, h->d_cscval.p,
+        matbalscale[0], matbalscale[1], matbalscale[2], h->d_vals_own.p);
+    interleave_rhs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(N, h->d_rhs_stage.p,
+        matbalscale[0], matbalscale[1], matbalscale[2], h->d_r.p);
+    h->launches += 2;
+    CK(cudaGetLastError());
+    cudaEventRecord(h->ev[5], h->stream);
+    h->d_vals = h->d_vals_own.p;
+    h->have_values = true; h->have_factors = false;
+    int rc = solve_resident(h, params, result);
+    result->ms_h2d = ev_ms(h->ev[3], h->ev[4]);
+    result->ms_interleave = ev_ms(h->ev[4], h->ev[5]);
+    if (rc == OPMGPU_OK || rc == OPMGPU_NOT_CONVERGED) {
+        cudaEventRecord(h->ev[5], h->stream);
+        deinterleave_x_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(N, h->d_x.p, h->d_tmp.p);
+        h->launches++;
+        CK(cudaMemcpyAsync(dx_varmajor, h->d_tmp.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        cudaEventRecord(h->ev[6], h->stream);
+        CK(cudaStreamSynchronize(h->stream));
+        result->ms_d2h = ev_ms(h->ev[5], h->ev[6]);
+    }
+    return rc;
+}
+
+int opmgpu_num_levels(opmgpu_handle h, int* lower_levels, int* upper_levels)
+{
+    if (!h || !h->have_pattern) return OPMGPU_BAD_ARGUMENT;
+    if (lower_levels) *lower_levels = h->nlevL;
+    if (upper_levels) *upper_levels = h->nlevU;
+    return OPMGPU_OK;
+}
+
+long long opmgpu_launch_count(opmgpu_handle h) { return h ? h->launches : 0; }
+
+int opmgpu_residual_history(opmgpu_handle h, double* out, int cap, int* n)
+{
+    if (!h || !n) return OPMGPU_BAD_ARGUMENT;
+    *n = (int)h->history.size();
+    for (int i = 0; i < cap && i < *n; ++i) out[i] = h->history[i];
+    return OPMGPU_OK;
+}
+
+// ---- multi-GPU entry points -------------------------------------------------------------------
+int opmgpu_nccl_unique_id(void* id128)
+{
+    (void)id128;
+    g_create_error = "distributed mode not built yet";
+    return OPMGPU_NCCL_ERROR;
+}
+int opmgpu_create_distributed(int device, int rank, int world, const void* nccl_unique_id, opmgpu_handle* out)
+{
+    (void)device; (void)rank; (void)world; (void)nccl_unique_id;
+    *out = nullptr;
+    g_create_error = "distributed mode not built yet";
+    return OPMGPU_NCCL_ERROR;
+}
+int opmgpu_set_pattern_bcrs_distributed(opmgpu_handle h, int N_local, int nnzb_local, const int* rowptr,
+                                        const int* colidx_global, long long row_begin, long long N_global)
+{
+    (void)N_local; (void)nnzb_local; (void)rowptr; (void)colidx_global; (void)row_begin; (void)N_global;
+    return h ? h->bad("distributed mode not built yet") : OPMGPU_BAD_ARGUMENT;
+}
+
+}  // extern "C"

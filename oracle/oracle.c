@@ -1,0 +1,410 @@
+/*
+ * oracle.c -- CPU restatement of the reference's Newton-step linear solve (np = 3).
+ * See oracle.h for the status of this file (test infrastructure, parity unpinned at the
+ * dune-istl level) and for the floating-point contract.  Single-threaded like the
+ * reference (sequential dune-istl; OpenMP is off by default, CMakeLists.txt:23).
+ *
+ * Each function names the reference call site it follows (paths relative to the
+ * reference root) and, where the arithmetic is external, the upstream routine restated.
+ */
+#include "oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define BS 3          /* block size np */
+#define BB 9          /* BS*BS         */
+
+void oracle_free(void* p) { free(p); }
+
+/* ------------------------------------------------------------------------------------
+ * a7  formInterleavedSystem -- pattern (opm/autodiff/NewtonIterationBlackoilInterleaved.cpp:110-155)
+ * ---------------------------------------------------------------------------------- */
+static int cmp_int(const void* a, const void* b)
+{
+    const int x = *(const int*)a, y = *(const int*)b;
+    return (x > y) - (x < y);
+}
+
+int oracle_interleave_pattern(int N, int np, const oracle_csc* blocks, int require_full,
+                              int* rowptr, int** colidx_out)
+{
+    /* Which scalar blocks contribute: d(eq)/d(pressure) always (:118-123), all of them
+     * when require_full_sparsity_pattern (:127-134). */
+    int nsel = 0;
+    int sel[36];
+    for (int p1 = 0; p1 < np; ++p1) sel[nsel++] = p1 * np + 0;
+    if (require_full)
+        for (int p1 = 0; p1 < np; ++p1)
+            for (int p2 = 1; p2 < np; ++p2) sel[nsel++] = p1 * np + p2;
+
+    int cap = 16;
+    int* tmp = (int*)malloc(sizeof(int) * cap);
+    /* pass 1: union per column, count per row.  pass 2: fill (columns visited ascending,
+     * so every row receives ascending column ids -- the row-major conversion at :137). */
+    int* colidx = NULL;
+    int* fill = (int*)calloc((size_t)N + 1, sizeof(int));
+    for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 1) {
+            rowptr[0] = 0;
+            for (int r = 0; r < N; ++r) rowptr[r + 1] = rowptr[r] + fill[r];
+            colidx = (int*)malloc(sizeof(int) * (size_t)(rowptr[N] > 0 ? rowptr[N] : 1));
+            for (int r = 0; r < N; ++r) fill[r] = rowptr[r];
+        }
+        for (int c = 0; c < N; ++c) {
+            int n = 0;
+            for (int s = 0; s < nsel; ++s) {
+                const oracle_csc* m = &blocks[sel[s]];
+                for (int k = m->colptr[c]; k < m->colptr[c + 1]; ++k) {
+                    if (n == cap) { cap *= 2; tmp = (int*)realloc(tmp, sizeof(int) * cap); }
+                    tmp[n++] = m->rowidx[k];
+                }
+            }
+            qsort(tmp, n, sizeof(int), cmp_int);
+            int last = -1;
+            for (int q = 0; q < n; ++q) {
+                if (tmp[q] == last) continue;
+                last = tmp[q];
+                if (pass == 0) fill[last]++;
+                else colidx[fill[last]++] = c;
+            }
+        }
+    }
+    free(tmp);
+    free(fill);
+    *colidx_out = colidx;
+    return rowptr[N];
+}
+
+/* a6 + a7  scaling and value scatter (...Interleaved.cpp:234-236, :178-193).
+ * AutoDiffBlock * scalar multiplies every Jacobian value once (AutoDiffBlock.hpp:617-626). */
+int oracle_interleave_values(int N, int np, const oracle_csc* blocks, const double* scale,
+                             const int* rowptr, const int* colidx, double* vals)
+{
+    memset(vals, 0, sizeof(double) * (size_t)rowptr[N] * np * np);
+    for (int p1 = 0; p1 < np; ++p1) {
+        for (int p2 = 0; p2 < np; ++p2) {
+            const oracle_csc* s = &blocks[p1 * np + p2];
+            for (int col = 0; col < N; ++col) {
+                for (int k = s->colptr[col]; k < s->colptr[col + 1]; ++k) {
+                    const int row = s->rowidx[k];
+                    /* istlA[row][col]: binary search in the row */
+                    int lo = rowptr[row], hi = rowptr[row + 1] - 1, pos = -1;
+                    while (lo <= hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (colidx[mid] == col) { pos = mid; break; }
+                        if (colidx[mid] < col) lo = mid + 1; else hi = mid - 1;
+                    }
+                    if (pos < 0) return -(k + 1);
+                    vals[(size_t)pos * np * np + p1 * np + p2] = s->val[k] * scale[p1];
+                }
+            }
+        }
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------
+ * a10  operator apply: Dune::MatrixAdapter::apply -> BCRSMatrix::mv -> block umv
+ * (call site opm/autodiff/ISTLSolver.hpp:303)
+ * ---------------------------------------------------------------------------------- */
+void oracle_spmv3(int N, const int* rowptr, const int* colidx, const double* vals,
+                  const double* x, double* y)
+{
+    for (int i = 0; i < N; ++i) {
+        double y0 = 0.0, y1 = 0.0, y2 = 0.0;
+        for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+            const double* a = vals + (size_t)k * BB;
+            const double* xj = x + (size_t)colidx[k] * BS;
+            /* umv: y[r] += a[r][c] * x[c], r outer, c inner */
+            y0 = fma(a[0], xj[0], y0); y0 = fma(a[1], xj[1], y0); y0 = fma(a[2], xj[2], y0);
+            y1 = fma(a[3], xj[0], y1); y1 = fma(a[4], xj[1], y1); y1 = fma(a[5], xj[2], y1);
+            y2 = fma(a[6], xj[0], y2); y2 = fma(a[7], xj[1], y2); y2 = fma(a[8], xj[2], y2);
+        }
+        y[(size_t)i * BS + 0] = y0; y[(size_t)i * BS + 1] = y1; y[(size_t)i * BS + 2] = y2;
+    }
+}
+
+/* ------------------------------------------------------------------------------------
+ * a9  ILU0 factorisation: Opm::ParallelOverlappingILU0 ctor -> Dune::bilu0_decomposition
+ * (call site opm/autodiff/ISTLSolver.hpp:201-211; 3x3 inverse is OPM's own, :192-194)
+ * ---------------------------------------------------------------------------------- */
+/* C = A * B with dune's DenseMatrix::{right,left}multiply accumulation: each entry starts
+ * at 0 and adds k = 0,1,2 in turn. */
+static void mat3_mul(const double* A, const double* B, double* C)
+{
+    for (int i = 0; i < BS; ++i)
+        for (int j = 0; j < BS; ++j) {
+            double s = 0.0;
+            for (int k = 0; k < BS; ++k) s = fma(A[i * BS + k], B[k * BS + j], s);
+            C[i * BS + j] = s;
+        }
+}
+
+/* Opm::MatrixBlock<double,3,3>::invert -> ISTLUtility::invertMatrix (adjugate / det,
+ * "code generated by maple").  Returns the determinant. */
+static double mat3_invert(double* M)
+{
+    double A[BB];
+    memcpy(A, M, sizeof A);
+    const double t4 = A[0] * A[4];
+    const double t6 = A[0] * A[5];
+    const double t8 = A[1] * A[3];
+    const double t10 = A[2] * A[3];
+    const double t12 = A[1] * A[6];
+    const double t14 = A[2] * A[6];
+    const double det = (t4 * A[8] - t6 * A[7] - t8 * A[8] + t10 * A[7] + t12 * A[5] - t14 * A[4]);
+    const double t17 = 1.0 / det;
+    M[0] = (A[4] * A[8] - A[5] * A[7]) * t17;
+    M[1] = -(A[1] * A[8] - A[2] * A[7]) * t17;
+    M[2] = (A[1] * A[5] - A[2] * A[4]) * t17;
+    M[3] = -(A[3] * A[8] - A[5] * A[6]) * t17;
+    M[4] = (A[0] * A[8] - t14) * t17;
+    M[5] = -(t6 - t10) * t17;
+    M[6] = (A[3] * A[7] - A[4] * A[6]) * t17;
+    M[7] = -(A[0] * A[7] - t12) * t17;
+    M[8] = (t4 - t8) * t17;
+    return det;
+}
+
+static int find_diag(const int* rowptr, const int* colidx, int i)
+{
+    for (int k = rowptr[i]; k < rowptr[i + 1]; ++k)
+        if (colidx[k] == i) return k;
+    return -1;
+}
+
+int oracle_ilu0_factor3(int N, const int* rowptr, const int* colidx, double* lu)
+{
+    int* diag = (int*)malloc(sizeof(int) * (size_t)(N > 0 ? N : 1));
+    for (int i = 0; i < N; ++i) {
+        diag[i] = find_diag(rowptr, colidx, i);
+        if (diag[i] < 0) { free(diag); return 1 + i; }     /* "diagonal entry missing" */
+    }
+    for (int i = 0; i < N; ++i) {
+        const int iend = rowptr[i + 1];
+        for (int ij = rowptr[i]; colidx[ij] < i; ++ij) {
+            const int j = colidx[ij];
+            double* Aij = lu + (size_t)ij * BB;
+            /* L_ij = A_ij * inv(A_jj)   ((*ij).rightmultiply(*jj)) */
+            double L[BB];
+            mat3_mul(Aij, lu + (size_t)diag[j] * BB, L);
+            memcpy(Aij, L, sizeof L);
+            /* A_ik -= L_ij * A_jk for k > j present in both rows */
+            int jk = diag[j] + 1, ik = ij + 1;
+            const int jend = rowptr[j + 1];
+            while (ik < iend && jk < jend) {
+                if (colidx[ik] == colidx[jk]) {
+                    double B[BB];
+                    mat3_mul(L, lu + (size_t)jk * BB, B);        /* B.leftmultiply(*ij) */
+                    double* Aik = lu + (size_t)ik * BB;
+                    for (int q = 0; q < BB; ++q) Aik[q] -= B[q];
+                    ++ik; ++jk;
+                } else if (colidx[ik] < colidx[jk]) ++ik;
+                else ++jk;
+            }
+        }
+        const double det = mat3_invert(lu + (size_t)diag[i] * BB);
+        if (!(det != 0.0) || !isfinite(det)) { free(diag); return 1 + i; }
+    }
+    free(diag);
+    return 0;
+}
+
+/* a10  preconditioner apply: Opm::ParallelOverlappingILU0::apply, sequential case.
+ * Lower sweep walks columns ascending; the upper factor is stored by convertToCRS in
+ * reverse order, so the upper sweep walks columns DESCENDING; then v *= w. */
+void oracle_ilu0_apply3(int N, const int* rowptr, const int* colidx, const double* lu,
+                        double w, const double* d, double* v)
+{
+    for (int i = 0; i < N; ++i) {
+        double r0 = d[(size_t)i * BS], r1 = d[(size_t)i * BS + 1], r2 = d[(size_t)i * BS + 2];
+        for (int k = rowptr[i]; k < rowptr[i + 1] && colidx[k] < i; ++k) {
+            const double* a = lu + (size_t)k * BB;
+            const double* vj = v + (size_t)colidx[k] * BS;
+            /* mmv: y[r] -= a[r][c] * x[c] */
+            r0 = fma(-a[0], vj[0], r0); r0 = fma(-a[1], vj[1], r0); r0 = fma(-a[2], vj[2], r0);
+            r1 = fma(-a[3], vj[0], r1); r1 = fma(-a[4], vj[1], r1); r1 = fma(-a[5], vj[2], r1);
+            r2 = fma(-a[6], vj[0], r2); r2 = fma(-a[7], vj[1], r2); r2 = fma(-a[8], vj[2], r2);
+        }
+        v[(size_t)i * BS] = r0; v[(size_t)i * BS + 1] = r1; v[(size_t)i * BS + 2] = r2;
+    }
+    for (int i = N - 1; i >= 0; --i) {
+        double r0 = v[(size_t)i * BS], r1 = v[(size_t)i * BS + 1], r2 = v[(size_t)i * BS + 2];
+        int k = rowptr[i + 1] - 1;
+        for (; colidx[k] > i; --k) {
+            const double* a = lu + (size_t)k * BB;
+            const double* vj = v + (size_t)colidx[k] * BS;
+            r0 = fma(-a[0], vj[0], r0); r0 = fma(-a[1], vj[1], r0); r0 = fma(-a[2], vj[2], r0);
+            r1 = fma(-a[3], vj[0], r1); r1 = fma(-a[4], vj[1], r1); r1 = fma(-a[5], vj[2], r1);
+            r2 = fma(-a[6], vj[0], r2); r2 = fma(-a[7], vj[1], r2); r2 = fma(-a[8], vj[2], r2);
+        }
+        const double* di = lu + (size_t)k * BB;               /* k is the diagonal now */
+        /* inv_[i].mv(rhs, vBlock): y[r] = 0; y[r] += a[r][c]*x[c] */
+        double y0 = 0.0, y1 = 0.0, y2 = 0.0;
+        y0 = fma(di[0], r0, y0); y0 = fma(di[1], r1, y0); y0 = fma(di[2], r2, y0);
+        y1 = fma(di[3], r0, y1); y1 = fma(di[4], r1, y1); y1 = fma(di[5], r2, y1);
+        y2 = fma(di[6], r0, y2); y2 = fma(di[7], r1, y2); y2 = fma(di[8], r2, y2);
+        v[(size_t)i * BS] = y0; v[(size_t)i * BS + 1] = y1; v[(size_t)i * BS + 2] = y2;
+    }
+    if (fabs(w - 1.0) > 1e-15)                                /* relaxation_ flag */
+        for (size_t q = 0; q < (size_t)N * BS; ++q) v[q] *= w;
+}
+
+/* ------------------------------------------------------------------------------------
+ * a10  Dune::BiCGSTABSolver::apply  (call site opm/autodiff/ISTLSolver.hpp:267-272),
+ * Dune::SeqScalarProduct dot / norm: per-block partial sums accumulated in block order.
+ * ---------------------------------------------------------------------------------- */
+static double vdot(int N, const double* x, const double* y)
+{
+    double sum = 0.0;
+    for (int i = 0; i < N; ++i) {
+        double s = 0.0;
+        s = fma(x[(size_t)i * BS], y[(size_t)i * BS], s);
+        s = fma(x[(size_t)i * BS + 1], y[(size_t)i * BS + 1], s);
+        s = fma(x[(size_t)i * BS + 2], y[(size_t)i * BS + 2], s);
+        sum += s;
+    }
+    return sum;
+}
+static double vnorm(int N, const double* x) { return sqrt(vdot(N, x, x)); }
+
+static void precond(int N, const int* rowptr, const int* colidx, const double* lu, double w,
+                    const double* d, double* v)
+{
+    if (lu) oracle_ilu0_apply3(N, rowptr, colidx, lu, w, d, v);
+    else memcpy(v, d, sizeof(double) * (size_t)N * BS);
+}
+
+void oracle_bicgstab3(int N, const int* rowptr, const int* colidx, const double* vals,
+                      const double* lu, double w, double* b, double* x,
+                      double reduction, int maxiter, int max_half_steps,
+                      double* history, int history_cap, oracle_result* res)
+{
+    const double EPSILON = 1e-80;
+    const size_t n = (size_t)N * BS;
+    double* r = b;                                            /* X& r = b */
+    double* p = (double*)calloc(n ? n : 1, sizeof(double));
+    double* v = (double*)calloc(n ? n : 1, sizeof(double));
+    double* t = (double*)calloc(n ? n : 1, sizeof(double));
+    double* y = (double*)calloc(n ? n : 1, sizeof(double));
+    double* rt = (double*)malloc(sizeof(double) * (n ? n : 1));
+    double rho = 1.0, alpha = 1.0, omega = 1.0, rho_new, beta, h;
+    double norm, norm_0, it;
+    int half = 0;
+
+    memset(res, 0, sizeof *res);
+    /* r = b - A x   (_op.applyscaleadd(-1,x,r)); t doubles as scratch */
+    oracle_spmv3(N, rowptr, colidx, vals, x, t);
+    for (size_t q = 0; q < n; ++q) r[q] -= t[q];
+    memcpy(rt, r, sizeof(double) * n);
+    norm = norm_0 = vnorm(N, r);
+    res->norm0 = norm_0;
+
+    if (norm < norm_0 * reduction || norm < 1e-30) {
+        res->converged = 1; res->iterations = 0; res->reduction = 0.0;
+        goto done;
+    }
+
+    for (it = 0.5; it < maxiter; it += 0.5) {
+        if (max_half_steps >= 0 && half >= max_half_steps) break;
+        rho_new = vdot(N, rt, r);
+        if (fabs(rho) <= EPSILON || fabs(omega) <= EPSILON) { res->status = 3; break; }
+        if (it < 1) {
+            memcpy(p, r, sizeof(double) * n);
+        } else {
+            beta = (rho_new / rho) * (alpha / omega);
+            for (size_t q = 0; q < n; ++q) {                  /* p.axpy(-omega,v); p*=beta; p+=r */
+                double pq = fma(-omega, v[q], p[q]);
+                pq *= beta;
+                p[q] = pq + r[q];
+            }
+        }
+        memset(y, 0, sizeof(double) * n);
+        precond(N, rowptr, colidx, lu, w, p, y);
+        oracle_spmv3(N, rowptr, colidx, vals, y, v);
+        h = vdot(N, rt, v);
+        if (fabs(h) < EPSILON) { res->status = 3; break; }
+        alpha = rho_new / h;
+        for (size_t q = 0; q < n; ++q) x[q] = fma(alpha, y[q], x[q]);
+        for (size_t q = 0; q < n; ++q) r[q] = fma(-alpha, v[q], r[q]);
+        norm = vnorm(N, r);
+        if (history && half < history_cap) history[half] = norm;
+        ++half;
+        if (norm < norm_0 * reduction) { res->converged = 1; break; }
+        it += 0.5;
+        if (max_half_steps >= 0 && half >= max_half_steps) break;
+
+        memset(y, 0, sizeof(double) * n);
+        precond(N, rowptr, colidx, lu, w, r, y);
+        oracle_spmv3(N, rowptr, colidx, vals, y, t);
+        omega = vdot(N, t, r) / vdot(N, t, t);
+        for (size_t q = 0; q < n; ++q) x[q] = fma(omega, y[q], x[q]);
+        for (size_t q = 0; q < n; ++q) r[q] = fma(-omega, t[q], r[q]);
+        rho = rho_new;
+        norm = vnorm(N, r);
+        if (history && half < history_cap) history[half] = norm;
+        ++half;
+        if (norm < norm_0 * reduction || norm < 1e-30) { res->converged = 1; break; }
+    }
+    if (it > maxiter) it = maxiter;                           /* it = min(maxit, it) */
+    res->iterations = (int)ceil(it);
+    res->reduction = norm / norm_0;
+    if (!res->converged && res->status == 0) res->status = 1;
+
+done:
+    res->half_steps = half;
+    free(p); free(v); free(t); free(y); free(rt);
+}
+
+void oracle_solve_bcrs3(int N, const int* rowptr, const int* colidx, const double* vals,
+                        const double* rhs_cellmajor, double* x_cellmajor,
+                        double reduction, int maxiter, double relax, int max_half_steps,
+                        oracle_result* res)
+{
+    const size_t nnzb = (size_t)rowptr[N];
+    double* lu = (double*)malloc(sizeof(double) * (nnzb ? nnzb : 1) * BB);
+    double* b = (double*)malloc(sizeof(double) * ((size_t)N * BS + 1));
+    memcpy(lu, vals, sizeof(double) * nnzb * BB);             /* ILU works on a copy of A */
+    memcpy(b, rhs_cellmajor, sizeof(double) * (size_t)N * BS);
+    memset(x_cellmajor, 0, sizeof(double) * (size_t)N * BS);  /* x = 0.0, ...Interleaved.cpp:272-273 */
+    const int bad = oracle_ilu0_factor3(N, rowptr, colidx, lu);
+    if (bad) {
+        memset(res, 0, sizeof *res);
+        res->status = 2; res->bad_row = bad - 1;
+    } else {
+        oracle_bicgstab3(N, rowptr, colidx, vals, lu, relax, b, x_cellmajor, reduction, maxiter,
+                         max_half_steps, NULL, 0, res);
+    }
+    free(lu); free(b);
+}
+
+/* a6..a11  Impl<3,double>::computeNewtonIncrement without wells (...Interleaved.cpp:234-283) */
+void oracle_solve_from_csc_blocks(int N, const oracle_csc* blocks9, const double* matbalscale,
+                                  const double* rhs_eqmajor, double* dx_varmajor,
+                                  double reduction, int maxiter, double relax,
+                                  int require_full, oracle_result* res)
+{
+    int* rowptr = (int*)malloc(sizeof(int) * ((size_t)N + 1));
+    int* colidx = NULL;
+    const int nnzb = oracle_interleave_pattern(N, BS, blocks9, require_full, rowptr, &colidx);
+    double* vals = (double*)malloc(sizeof(double) * (size_t)(nnzb > 0 ? nnzb : 1) * BB);
+    double* b = (double*)malloc(sizeof(double) * ((size_t)N * BS + 1));
+    double* x = (double*)malloc(sizeof(double) * ((size_t)N * BS + 1));
+    const int bad = oracle_interleave_values(N, BS, blocks9, matbalscale, rowptr, colidx, vals);
+    if (bad) {
+        memset(res, 0, sizeof *res);
+        res->status = 4;                                      /* entry outside pattern */
+    } else {
+        /* b is the concatenation of the SCALED equation values (:234-253), interleaved at :263-269 */
+        for (int i = 0; i < N; ++i)
+            for (int pp = 0; pp < BS; ++pp)
+                b[(size_t)i * BS + pp] = rhs_eqmajor[(size_t)pp * N + i] * matbalscale[pp];
+        oracle_solve_bcrs3(N, rowptr, colidx, vals, b, x, reduction, maxiter, relax, -1, res);
+        for (int i = 0; i < N; ++i)                           /* :279-283 */
+            for (int pp = 0; pp < BS; ++pp)
+                dx_varmajor[(size_t)pp * N + i] = x[(size_t)i * BS + pp];
+    }
+    free(rowptr); free(colidx); free(vals); free(b); free(x);
+}

@@ -1,0 +1,178 @@
+"""ctypes face of the CPU oracle (oracle/oracle.c).
+
+TEST INFRASTRUCTURE ONLY -- imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package never imports this module.
+Parity status: unpinned at the dune-istl level, see oracle.h.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "liboracle.so")
+
+
+class OracleResult(C.Structure):
+    _fields_ = [("iterations", C.c_int), ("converged", C.c_int), ("half_steps", C.c_int),
+                ("status", C.c_int), ("bad_row", C.c_int), ("reduction", C.c_double),
+                ("norm0", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class OracleCsc(C.Structure):
+    _fields_ = [("colptr", C.POINTER(C.c_int)), ("rowidx", C.POINTER(C.c_int)),
+                ("val", C.POINTER(C.c_double))]
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        try:
+            _lib = C.CDLL(build())
+        except OSError:
+            _lib = C.CDLL(build(force=True))
+        ip, dp = C.POINTER(C.c_int), C.POINTER(C.c_double)
+        _lib.oracle_interleave_pattern.argtypes = [C.c_int, C.c_int, C.POINTER(OracleCsc), C.c_int, ip, C.POINTER(ip)]
+        _lib.oracle_interleave_pattern.restype = C.c_int
+        _lib.oracle_interleave_values.argtypes = [C.c_int, C.c_int, C.POINTER(OracleCsc), dp, ip, ip, dp]
+        _lib.oracle_interleave_values.restype = C.c_int
+        _lib.oracle_spmv3.argtypes = [C.c_int, ip, ip, dp, dp, dp]
+        _lib.oracle_spmv3.restype = None
+        _lib.oracle_ilu0_factor3.argtypes = [C.c_int, ip, ip, dp]
+        _lib.oracle_ilu0_factor3.restype = C.c_int
+        _lib.oracle_ilu0_apply3.argtypes = [C.c_int, ip, ip, dp, C.c_double, dp, dp]
+        _lib.oracle_ilu0_apply3.restype = None
+        _lib.oracle_bicgstab3.argtypes = [C.c_int, ip, ip, dp, dp, C.c_double, dp, dp, C.c_double,
+                                          C.c_int, C.c_int, dp, C.c_int, C.POINTER(OracleResult)]
+        _lib.oracle_bicgstab3.restype = None
+        _lib.oracle_solve_bcrs3.argtypes = [C.c_int, ip, ip, dp, dp, dp, C.c_double, C.c_int,
+                                            C.c_double, C.c_int, C.POINTER(OracleResult)]
+        _lib.oracle_solve_bcrs3.restype = None
+        _lib.oracle_solve_from_csc_blocks.argtypes = [C.c_int, C.POINTER(OracleCsc), dp, dp, dp,
+                                                      C.c_double, C.c_int, C.c_double, C.c_int,
+                                                      C.POINTER(OracleResult)]
+        _lib.oracle_solve_from_csc_blocks.restype = None
+        _lib.oracle_free.argtypes = [C.c_void_p]
+        _lib.oracle_free.restype = None
+    return _lib
+
+
+def _i(a):
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    return a, a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def _d(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _csc_array(blocks):
+    keep = []
+    arr = (OracleCsc * len(blocks))()
+    for k, (cp, ri, v) in enumerate(blocks):
+        cp, pcp = _i(cp); ri, pri = _i(ri); v, pv = _d(v)
+        keep += [cp, ri, v]
+        arr[k].colptr, arr[k].rowidx, arr[k].val = pcp, pri, pv
+    return arr, keep
+
+
+def interleave(N, blocks, scale, require_full=False, np_=3):
+    """-> rowptr, colidx, vals[nnzb, np*np] of the interleaved BCRS system."""
+    arr, keep = _csc_array(blocks)
+    rowptr = np.zeros(N + 1, dtype=np.int32)
+    out = C.POINTER(C.c_int)()
+    nnzb = lib().oracle_interleave_pattern(N, np_, arr, int(require_full),
+                                           rowptr.ctypes.data_as(C.POINTER(C.c_int)), C.byref(out))
+    colidx = np.ctypeslib.as_array(out, shape=(max(nnzb, 1),))[:nnzb].copy()
+    lib().oracle_free(out)
+    vals = np.zeros((nnzb, np_ * np_))
+    sc, psc = _d(scale)
+    rc = lib().oracle_interleave_values(N, np_, arr, psc, rowptr.ctypes.data_as(C.POINTER(C.c_int)),
+                                        colidx.ctypes.data_as(C.POINTER(C.c_int)),
+                                        vals.ctypes.data_as(C.POINTER(C.c_double)))
+    if rc != 0:
+        raise ValueError("Jacobian entry outside the pressure-derivative pattern (dune would throw)")
+    return rowptr, colidx, vals
+
+
+def spmv(rowptr, colidx, vals, x):
+    rowptr, prp = _i(rowptr); colidx, pci = _i(colidx); vals, pv = _d(vals); x, px = _d(x)
+    N = rowptr.size - 1
+    y = np.zeros(N * 3)
+    lib().oracle_spmv3(N, prp, pci, pv, px, y.ctypes.data_as(C.POINTER(C.c_double)))
+    return y.reshape(N, 3)
+
+
+def ilu0_factor(rowptr, colidx, vals):
+    """-> (lu[nnzb,9] with inverted diagonal blocks, bad_row or -1)."""
+    rowptr, prp = _i(rowptr); colidx, pci = _i(colidx)
+    lu = np.array(vals, dtype=np.float64, copy=True, order="C")
+    rc = lib().oracle_ilu0_factor3(rowptr.size - 1, prp, pci, lu.ctypes.data_as(C.POINTER(C.c_double)))
+    return lu, rc - 1
+
+
+def ilu0_apply(rowptr, colidx, lu, w, d):
+    rowptr, prp = _i(rowptr); colidx, pci = _i(colidx); lu, plu = _d(lu); d, pd = _d(d)
+    N = rowptr.size - 1
+    v = np.zeros(N * 3)
+    lib().oracle_ilu0_apply3(N, prp, pci, plu, float(w), pd, v.ctypes.data_as(C.POINTER(C.c_double)))
+    return v.reshape(N, 3)
+
+
+def solve_bcrs(rowptr, colidx, vals, rhs, reduction=1e-2, maxiter=150, relax=0.9, max_half_steps=-1):
+    rowptr, prp = _i(rowptr); colidx, pci = _i(colidx); vals, pv = _d(vals); rhs, pr = _d(rhs)
+    N = rowptr.size - 1
+    x = np.zeros(N * 3)
+    res = OracleResult()
+    lib().oracle_solve_bcrs3(N, prp, pci, pv, pr, x.ctypes.data_as(C.POINTER(C.c_double)),
+                             float(reduction), int(maxiter), float(relax), int(max_half_steps),
+                             C.byref(res))
+    return x.reshape(N, 3), res.as_dict()
+
+
+def bicgstab(rowptr, colidx, vals, lu, w, rhs, reduction=1e-2, maxiter=150, max_half_steps=-1,
+             history_cap=0):
+    """lu=None -> identity preconditioner.  Returns x, result dict, |r| history."""
+    rowptr, prp = _i(rowptr); colidx, pci = _i(colidx); vals, pv = _d(vals)
+    N = rowptr.size - 1
+    b = np.array(rhs, dtype=np.float64, copy=True).reshape(-1)
+    x = np.zeros(N * 3)
+    hist = np.zeros(max(history_cap, 1))
+    plu = None
+    if lu is not None:
+        lu, plu = _d(lu)
+    res = OracleResult()
+    lib().oracle_bicgstab3(N, prp, pci, pv, plu, float(w), b.ctypes.data_as(C.POINTER(C.c_double)),
+                           x.ctypes.data_as(C.POINTER(C.c_double)), float(reduction), int(maxiter),
+                           int(max_half_steps), hist.ctypes.data_as(C.POINTER(C.c_double)),
+                           int(history_cap), C.byref(res))
+    return x.reshape(N, 3), res.as_dict(), hist[:min(history_cap, res.half_steps)]
+
+
+def solve_from_csc_blocks(N, blocks9, matbalscale, rhs_eqmajor, reduction=1e-2, maxiter=150,
+                          relax=0.9, require_full=False):
+    arr, keep = _csc_array(blocks9)
+    sc, psc = _d(matbalscale); rhs, pr = _d(rhs_eqmajor)
+    dx = np.zeros(3 * N)
+    res = OracleResult()
+    lib().oracle_solve_from_csc_blocks(N, arr, psc, pr, dx.ctypes.data_as(C.POINTER(C.c_double)),
+                                       float(reduction), int(maxiter), float(relax),
+                                       int(require_full), C.byref(res))
+    return dx, res.as_dict()

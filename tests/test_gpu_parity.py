@@ -1,0 +1,167 @@
+"""GPU parity tests proper: every call goes through the C ABI (libopmgpu.so) and is checked
+against the CPU oracle on the same seeded inputs.
+
+Tolerances.  SpMV, ILU0 factors and ILU0 sweeps follow the reference's operation order and
+must be BIT-IDENTICAL to the oracle.  Dot products are tree reductions (rel 1e-13).  The
+Newton increment must agree within rel 1e-8 (BASELINE.json north_star) at equal half-step
+counts and at a tight reduction; iteration counts must be equal.
+"""
+import numpy as np
+import pytest
+
+from opm_simulators_legacy_b200.jacobian import synth_blackoil_jacobian, random_bcrs
+from opm_simulators_legacy_b200.solver import (GpuLinearSolver, LinearSolverProblem, NumericalIssue,
+                                               make_params)
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    "c1_spe1_shape": dict(dims=(10, 10, 3), perm="homogeneous"),
+    "small_lognormal": dict(dims=(24, 20, 12), perm="lognormal"),
+    "slab_1d": dict(dims=(64, 1, 1), perm="homogeneous"),
+    "plane_2d": dict(dims=(30, 17, 1), perm="lognormal"),
+    "mid_lognormal": dict(dims=(40, 40, 20), perm="lognormal"),
+}
+
+
+def _np(s):
+    return s.rowptr.numpy(), s.colidx.numpy(), s.vals.numpy(), s.rhs.numpy()
+
+
+@pytest.fixture(scope="module", params=list(CASES))
+def case(request):
+    cfg = CASES[request.param]
+    return synth_blackoil_jacobian(*cfg["dims"], perm=cfg["perm"])
+
+
+def test_spmv_bit_exact(gpu_solver, oracle, case):
+    rp, ci, v, b = _np(case)
+    gpu_solver.set_pattern(rp, ci)
+    gpu_solver.set_values(v)
+    x = case.xstar.numpy()
+    assert np.array_equal(gpu_solver.spmv(x), oracle.spmv(rp, ci, v, x))
+
+
+def test_ilu0_factor_and_apply_bit_exact(gpu_solver, oracle, case):
+    rp, ci, v, b = _np(case)
+    gpu_solver.set_pattern(rp, ci)
+    gpu_solver.set_values(v)
+    assert gpu_solver.ilu0_factor() == -1
+    lu_ref, bad = oracle.ilu0_factor(rp, ci, v)
+    assert bad == -1
+    lu = gpu_solver.ilu0_factors()
+    assert np.array_equal(lu, lu_ref)
+    for w in (0.9, 1.0):
+        got = gpu_solver.ilu0_apply(w, b)
+        assert np.array_equal(got, oracle.ilu0_apply(rp, ci, lu_ref, w, b))
+
+
+def test_solve_default_tolerance_iteration_parity(gpu_solver, oracle, case):
+    rp, ci, v, b = _np(case)
+    gpu_solver.set_pattern(rp, ci)
+    x, res = gpu_solver.solve_bcrs(v, b)
+    x_ref, ref = oracle.solve_bcrs(rp, ci, v, b)
+    assert res["iterations"] == ref["iterations"] and res["half_steps"] == ref["half_steps"]
+    assert res["converged"] == 1 and res["reduction"] < 1e-2
+    scale = np.abs(x_ref).max(0)
+    assert (np.abs(x - x_ref).max(0) <= 1e-8 * scale).all()
+    hist = gpu_solver.residual_history()
+    assert len(hist) == ref["half_steps"]
+
+
+def test_solve_equal_half_steps_and_tight(gpu_solver, oracle, case):
+    rp, ci, v, b = _np(case)
+    gpu_solver.set_pattern(rp, ci)
+    for hs in (1, 2, 5):
+        x, res = gpu_solver.solve_bcrs(v, b, raise_on_failure=False, linear_solver_reduction=1e-30, max_half_steps=hs)
+        x_ref, ref = oracle.solve_bcrs(rp, ci, v, b, reduction=1e-30, max_half_steps=hs)
+        if ref["half_steps"] < hs:
+            continue
+        assert res["half_steps"] == ref["half_steps"]
+        scale = np.abs(x_ref).max(0)
+        assert (np.abs(x - x_ref).max(0) <= 1e-8 * scale).all()
+    x, res = gpu_solver.solve_bcrs(v, b, linear_solver_reduction=1e-10, linear_solver_maxiter=400)
+    x_ref, ref = oracle.solve_bcrs(rp, ci, v, b, reduction=1e-10, maxiter=400)
+    assert res["converged"] == 1
+    assert abs(res["iterations"] - ref["iterations"]) <= max(2, ref["iterations"] // 10)
+    scale = np.abs(x_ref).max(0)
+    assert (np.abs(x - x_ref).max(0) <= 1e-6 * scale).all()     # both are 1e-10-residual solutions
+
+
+def test_csc_blocks_path_matches_oracle(gpu_solver, oracle, case):
+    blocks = case.csc_blocks()
+    rhs = case.rhs_eqmajor_unscaled.numpy()
+    dx, res = gpu_solver.solve_from_csc_blocks(case.N, blocks, case.matbalscale, rhs)
+    dx_ref, ref = oracle.solve_from_csc_blocks(case.N, blocks, case.matbalscale, rhs)
+    assert res["iterations"] == ref["iterations"]
+    sc = np.abs(dx_ref.reshape(3, -1)).max(1).repeat(case.N)
+    assert (np.abs(dx - dx_ref) <= 1e-8 * sc).all()
+    # second call, same pattern: analysis is cached
+    dx2, res2 = gpu_solver.solve_from_csc_blocks(case.N, blocks, case.matbalscale, rhs)
+    assert res2["ms_analysis"] == 0.0 and np.array_equal(dx, dx2)
+
+
+def test_general_pattern_with_dense_well_coupling(gpu_solver, oracle):
+    rp, ci, v = random_bcrs(700, extra_per_row=3, seed=7, dense_group=12)
+    rng = np.random.default_rng(3)
+    b = rng.standard_normal((700, 3))
+    gpu_solver.set_pattern(rp, ci)
+    gpu_solver.set_values(v)
+    assert np.array_equal(gpu_solver.spmv(b), oracle.spmv(rp, ci, v, b))
+    assert gpu_solver.ilu0_factor() == -1
+    lu_ref, _ = oracle.ilu0_factor(rp, ci, v)
+    assert np.array_equal(gpu_solver.ilu0_factors(), lu_ref)
+    assert np.array_equal(gpu_solver.ilu0_apply(0.9, b), oracle.ilu0_apply(rp, ci, lu_ref, 0.9, b))
+    x, res = gpu_solver.solve_bcrs(v, b, linear_solver_reduction=1e-8)
+    x_ref, ref = oracle.solve_bcrs(rp, ci, v, b, reduction=1e-8)
+    assert res["iterations"] == ref["iterations"]
+    assert np.abs(x - x_ref).max() <= 1e-8 * np.abs(x_ref).max()
+
+
+def test_dot_deterministic_and_close(gpu_solver):
+    rng = np.random.default_rng(0)
+    a, b = rng.standard_normal(300001), rng.standard_normal(300001)
+    d1, d2 = gpu_solver.dot(a, b), gpu_solver.dot(a, b)
+    assert d1 == d2
+    assert abs(d1 - float(np.dot(a, b))) <= 1e-13 * float(np.abs(a * b).sum())
+
+
+def test_zero_rhs_returns_zero_iterations(gpu_solver, oracle):
+    s = synth_blackoil_jacobian(6, 5, 4)
+    rp, ci, v, b = _np(s)
+    gpu_solver.set_pattern(rp, ci)
+    x, res = gpu_solver.solve_bcrs(v, np.zeros_like(b))
+    assert res["iterations"] == 0 and res["converged"] == 1 and not x.any()
+
+
+def test_error_contract(gpu_solver, oracle):
+    s = synth_blackoil_jacobian(8, 8, 4, perm="lognormal")
+    rp, ci, v, b = _np(s)
+    gpu_solver.set_pattern(rp, ci)
+    # not converged -> LinearSolverProblem, iterations still reported (ISTLSolver.hpp:358-368)
+    with pytest.raises(LinearSolverProblem):
+        gpu_solver.solve_bcrs(v, b, linear_solver_reduction=1e-14, linear_solver_maxiter=2)
+    assert gpu_solver.last["iterations"] == 2 and gpu_solver.last["converged"] == 0
+    x, res = gpu_solver.solve_bcrs(v, b, linear_solver_reduction=1e-14, linear_solver_maxiter=2,
+                                   linear_solver_ignoreconvergencefailure=True)
+    assert res["status"] == 0 and res["converged"] == 0
+    # singular pivot block -> NumericalIssue naming the row the oracle names
+    v2 = v.copy()
+    row = 37
+    d = np.searchsorted(ci[rp[row]:rp[row + 1]], row) + rp[row]
+    v2[d] = 0.0
+    for k in range(rp[row], rp[row + 1]):
+        if ci[k] < row:
+            v2[k] = 0.0
+    _, bad = oracle.ilu0_factor(rp, ci, v2)
+    with pytest.raises(NumericalIssue):
+        gpu_solver.solve_bcrs(v2, b)
+    assert gpu_solver.last["bad_row"] == bad == row
+    # an entry outside the pressure pattern -> ValueError (dune throws in istlA[row][col])
+    blocks = [list(t) for t in s.csc_blocks()]
+    cp, ri, val = blocks[1]
+    cp = cp.copy(); ri = np.concatenate([[s.N - 1], ri]).astype(np.int32); val = np.concatenate([[1.0], val])
+    cp[1:] += 1
+    blocks[1] = (cp, ri, val)
+    with pytest.raises(ValueError):
+        gpu_solver.solve_from_csc_blocks(s.N, blocks, s.matbalscale, s.rhs_eqmajor_unscaled.numpy())
