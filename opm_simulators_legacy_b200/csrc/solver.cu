@@ -524,7 +524,7 @@ int opmgpu_set_stream(opmgpu_handle h, void* cuda_stream)
 {
     if (!h) return OPMGPU_BAD_ARGUMENT;
     cudaStreamSynchronize(h->stream);
-    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    h->stream = (cudaStream_t)cuda_stream;      // NULL is the legacy default stream
     return OPMGPU_OK;
 }
 

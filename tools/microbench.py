@@ -31,6 +31,8 @@ def main():
     s = synth_blackoil_jacobian(nx, ny, nz, perm=perm)
     tgen = time.time() - t0
     g = GpuLinearSolver(0)
+    st = torch.cuda.Stream()
+    torch.cuda.set_stream(st)
     g.use_torch_stream()
     t0 = time.time()
     g.set_pattern(s.rowptr.numpy(), s.colidx.numpy())
