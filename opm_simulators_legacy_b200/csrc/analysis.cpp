@@ -58,13 +58,15 @@ void infer_grid(int N, const int* rowptr, const int* colidx, int& nx, int& ny, i
 
 void choose_tiling(int nx, int ny, int P, int& pa, int& pb)
 {
-    long long best = -1;
+    long long best = -(1LL << 60);
     double best_sq = 0;
     pa = pb = 1;
     for (int a = 1; a <= std::min(nx, P); ++a) {
         const int b = std::min(ny, P / a);
         if (b < 1) break;
-        const long long cnt = (long long)a * b;
+        long long cnt = (long long)a * b;
+        // a level of a tile has at most ceil(nx/a)*ceil(ny/b) rows: keep it within one pass
+        if ((long long)((nx + a - 1) / a) * ((ny + b - 1) / b) > kLeanStepRows) cnt -= 1000000;
         const double sq = std::fabs(std::log((double(nx) / a) / (double(ny) / b)));
         if (cnt > best || (cnt == best && sq < best_sq)) { best = cnt; best_sq = sq; pa = a; pb = b; }
     }
@@ -136,9 +138,241 @@ void build_program(int N, const int* rowptr, const int* colidx, const std::vecto
     for (int q = 0; q < N; ++q) prog.publish[q] = pub_row[order[q]];
 }
 
+
+// ---- pipelined program ---------------------------------------------------------------------
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct RecLayout {
+    size_t cf, dinv, rowints, lists, tail_end, xpush_end, tail_dep, xpush_slot, tail_vals, total;
+};
+RecLayout rec_layout(int n, int ntail, int npushx, bool upper, bool has_lists)
+{
+    RecLayout L;
+    size_t o = 32;
+    L.cf = o; o += (size_t)3 * n * 72;
+    L.dinv = o; if (upper) o += (size_t)3 * n * 24;
+    o = align_up(o, 16);
+    L.rowints = o; o += (size_t)n * 32;
+    L.lists = o;
+    L.tail_end = o; if (has_lists) o += (size_t)n * 4;
+    L.xpush_end = o; if (has_lists) o += (size_t)n * 4;
+    L.tail_dep = o; o += (size_t)ntail * 4;
+    L.xpush_slot = o; o += (size_t)npushx * 4;
+    o = align_up(o, 16);
+    L.tail_vals = o; o += (size_t)ntail * 72;
+    L.total = align_up(o, 16);
+    return L;
+}
+
+// upos_of_row: for the lower program, position of every natural row in the upper program's
+// order (the lower sweep hands its result to the upper sweep in that order); null for upper.
+void build_pipe_program(int N, const int* rowptr, const int* colidx, const std::vector<int>& diag,
+                        const std::vector<int>& level, int nlevels, const std::vector<int>& owner,
+                        int P, bool lower, const std::vector<int>* upos_of_row, PipeProgram& pg)
+{
+    pg = PipeProgram();
+    pg.P = P;
+    pg.nlevels = nlevels;
+    const bool upper = !lower;
+    std::vector<int> order(N);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        if (owner[a] != owner[b]) return owner[a] < owner[b];
+        return level[a] < level[b];
+    });
+    std::vector<int> nblk(N, 0), next(N, 0), npush(N, 0);
+    auto for_deps = [&](int r, auto&& fn) {
+        if (lower) { for (int k = rowptr[r]; k < diag[r]; ++k) fn(k); }
+        else       { for (int k = rowptr[r + 1] - 1; k > diag[r]; --k) fn(k); }
+    };
+    for (int r = 0; r < N; ++r)
+        for_deps(r, [&](int k) {
+            ++nblk[r];
+            if (owner[colidx[k]] != owner[r]) { ++next[r]; ++npush[colidx[k]]; }
+        });
+    auto tail_of = [&](int r) { return std::max(0, nblk[r] - kFastBlocks); };
+    auto pushx_of = [&](int r) { return std::max(0, npush[r] - 2); };
+    // steps: split CTA row lists at level changes and at the record limits
+    struct Step { int q0, q1; };
+    std::vector<Step> steps;
+    std::vector<int> qlocal(N, 0);
+    pg.cta_step_ptr.assign(P + 1, 0);
+    {
+        int q = 0;
+        for (int c = 0; c < P; ++c) {
+            pg.cta_step_ptr[c] = (int)steps.size();
+            const int cbeg = q;
+            int cur_level = -1, rows = 0, tail = 0, ext = 0, pushx = 0;
+            while (q < N && owner[order[q]] == c) {
+                const int r = order[q];
+                const bool fits = rows > 0 && level[r] == cur_level && rows + 1 <= kMaxStepRows &&
+                                  ext + next[r] <= kMaxStepExt &&
+                                  rec_layout(rows + 1, tail + tail_of(r), pushx + pushx_of(r), upper, true).total <= (size_t)kMaxStepBytes;
+                if (!fits) {
+                    if (rows > 0) steps.back().q1 = q;
+                    steps.push_back({q, q});
+                    cur_level = level[r]; rows = tail = ext = pushx = 0;
+                    if (rec_layout(1, tail_of(r), pushx_of(r), upper, true).total > (size_t)kMaxStepBytes || next[r] > kMaxStepExt)
+                        return;                           // a single row exceeds a record: not pipelinable
+                }
+                ++rows; tail += tail_of(r); ext += next[r]; pushx += pushx_of(r);
+                qlocal[r] = q - cbeg;
+                ++q;
+            }
+            if (rows > 0) steps.back().q1 = q;
+        }
+        pg.cta_step_ptr[P] = (int)steps.size();
+    }
+    // push slots: ordinals in consumption order per CTA
+    pg.cta_ext_base.assign(P + 1, 0);
+    std::vector<int> push_ptr(N + 1, 0);
+    for (int r = 0; r < N; ++r) push_ptr[r + 1] = push_ptr[r] + npush[r];
+    std::vector<long long> push_slot(push_ptr[N]);
+    std::vector<int> push_fill(push_ptr.begin(), push_ptr.end() - 1);
+    {
+        long long base = 0;
+        int q = 0;
+        for (int c = 0; c < P; ++c) {
+            pg.cta_ext_base[c] = base;
+            long long e = 0;
+            while (q < N && owner[order[q]] == c) {
+                const int r = order[q];
+                for_deps(r, [&](int k) {
+                    const int j = colidx[k];
+                    if (owner[j] != c) { push_slot[push_fill[j]++] = base + e; ++e; }
+                });
+                ++q;
+            }
+            base += e;
+        }
+        pg.cta_ext_base[P] = base;
+        pg.total_ext = base;
+        if (base >= (1LL << 31)) return;
+    }
+    // program-order positions (rhs segments are fetched by bulk copies: even row counts)
+    pg.step_rhs_row.resize(steps.size());
+    pg.step_rhs_bytes.resize(steps.size());
+    std::vector<int> step_end_q(N), pos_of_row(N);
+    {
+        long long pos = 0;
+        for (int c = 0; c < P; ++c) {
+            int cbeg = -1;
+            for (int sidx = pg.cta_step_ptr[c]; sidx < pg.cta_step_ptr[c + 1]; ++sidx) {
+                if (cbeg < 0) cbeg = steps[sidx].q0;
+                const int rows = steps[sidx].q1 - steps[sidx].q0;
+                const int padded = (rows + 1) & ~1;
+                pg.step_rhs_row[sidx] = (unsigned)pos;
+                pg.step_rhs_bytes[sidx] = (unsigned)padded * 24u;
+                for (int q = steps[sidx].q0; q < steps[sidx].q1; ++q) {
+                    step_end_q[order[q]] = steps[sidx].q1 - cbeg;
+                    pos_of_row[order[q]] = (int)(pos + (q - steps[sidx].q0));
+                }
+                pos += padded;
+                pg.max_step_rows = std::max(pg.max_step_rows, padded);
+            }
+        }
+        if (pos >= (1LL << 31)) return;
+        pg.nperm = pos;
+        pg.perm_row.assign((size_t)pos, -1);
+        for (int r = 0; r < N; ++r) pg.perm_row[pos_of_row[r]] = r;
+    }
+    // own results older than the window must also live in HBM (natural order)
+    std::vector<unsigned char> write_global(N, 0);
+    for (int r = 0; r < N; ++r)
+        for_deps(r, [&](int k) {
+            const int j = colidx[k];
+            if (owner[j] == owner[r] && qlocal[j] + kWindowRows < step_end_q[r]) write_global[j] = 1;
+        });
+    // record sizes
+    size_t total_bytes = 0;
+    pg.step_off16.resize(steps.size());
+    pg.step_bytes.resize(steps.size());
+    std::vector<RecLayout> lay(steps.size());
+    for (size_t sidx = 0; sidx < steps.size(); ++sidx) {
+        int rows = steps[sidx].q1 - steps[sidx].q0, tail = 0, pushx = 0;
+        for (int q = steps[sidx].q0; q < steps[sidx].q1; ++q) { tail += tail_of(order[q]); pushx += pushx_of(order[q]); }
+        lay[sidx] = rec_layout(rows, tail, pushx, upper, tail + pushx > 0);
+        pg.step_off16[sidx] = (unsigned)(total_bytes / 16);
+        pg.step_bytes[sidx] = (unsigned)lay[sidx].total;
+        total_bytes += lay[sidx].total;
+        pg.max_step_bytes = std::max(pg.max_step_bytes, (int)lay[sidx].total);
+    }
+    if (total_bytes / 16 >= (1ull << 32) || total_bytes / 8 >= (1ull << 32)) return;
+    pg.buf.assign(total_bytes + 16, 0);
+    bool any_slow = false, any_global = false;
+    // emit
+    for (int c = 0; c < P; ++c) {
+        long long e = 0;
+        for (int sidx = pg.cta_step_ptr[c]; sidx < pg.cta_step_ptr[c + 1]; ++sidx) {
+            const size_t rec_off = (size_t)pg.step_off16[sidx] * 16;
+            unsigned char* rec = pg.buf.data() + rec_off;
+            const long long e_before = e;
+            const int cta_q0 = steps[pg.cta_step_ptr[c]].q0;
+            const RecLayout& L = lay[sidx];
+            const int n = steps[sidx].q1 - steps[sidx].q0;
+            const bool has_lists = L.tail_dep > L.lists;      // the cumulative arrays are present
+            int* hdr = (int*)rec;
+            int* rowints = (int*)(rec + L.rowints);
+            int* tail_end = (int*)(rec + L.tail_end);
+            int* xpush_end = (int*)(rec + L.xpush_end);
+            int* tail_dep = (int*)(rec + L.tail_dep);
+            int* xpush_slot = (int*)(rec + L.xpush_slot);
+            int nt = 0, npx = 0, rr = 0;
+            for (int q = steps[sidx].q0; q < steps[sidx].q1; ++q, ++rr) {
+                const int r = order[q];
+                int* ri = rowints + 8 * rr;
+                int kb = 0;
+                for (int k3 = 0; k3 < kFastBlocks; ++k3) ri[1 + k3] = kDepZeroSlot * 3;
+                for_deps(r, [&](int k) {
+                    const int j = colidx[k];
+                    int code;
+                    if (owner[j] != c) code = (kWindowRows + (int)((e++) % kExtRing)) * 3;
+                    else if (qlocal[j] + kWindowRows >= step_end_q[r]) code = (qlocal[j] % kWindowRows) * 3;
+                    else code = kDepGlobalBit | j;
+                    if (kb < kFastBlocks) {
+                        ri[1 + kb] = code;
+                        pg.val_src.push_back(k);
+                        pg.val_dst8.push_back((unsigned)((rec_off + L.cf) / 8 + (size_t)(3 * rr) * 9 + kb * 3));
+                        pg.val_stride.push_back(9);
+                    } else {
+                        tail_dep[nt] = code;
+                        pg.val_src.push_back(k);
+                        pg.val_dst8.push_back((unsigned)((rec_off + L.tail_vals) / 8 + (size_t)nt * 9));
+                        pg.val_stride.push_back(3);
+                        ++nt;
+                    }
+                    ++kb;
+                });
+                int np = 0;
+                ri[5] = -1; ri[6] = -1; ri[7] = 0;
+                for (int t = push_ptr[r]; t < push_ptr[r + 1]; ++t, ++np) {
+                    if (np < 2) ri[5 + np] = (int)push_slot[t];
+                    else xpush_slot[npx++] = (int)push_slot[t];
+                }
+                if (has_lists) { tail_end[rr] = nt; xpush_end[rr] = npx; }
+                const bool slow = kb > kFastBlocks || np > 2;
+                any_slow |= slow; any_global |= write_global[r] != 0;
+                ri[0] = r | (write_global[r] ? kRowWriteGlobal : 0) | (slow ? kRowSlow : 0);
+                ri[4] = (lower && upos_of_row) ? (*upos_of_row)[r] : 0;
+                if (upper) {
+                    pg.val_src.push_back(diag[r]);
+                    pg.val_dst8.push_back((unsigned)((rec_off + L.dinv) / 8 + (size_t)(3 * rr) * 3));
+                    pg.val_stride.push_back(3);
+                }
+            }
+            hdr[0] = n; hdr[1] = steps[sidx].q0 - cta_q0; hdr[2] = (int)e; hdr[3] = (int)(e - e_before);
+            hdr[4] = nt; hdr[5] = (int)(L.lists / 8); hdr[6] = (int)(L.tail_vals / 8);
+            hdr[7] = has_lists ? 1 : 0;
+        }
+    }
+    pg.lean = !any_slow && !any_global && pg.max_step_rows <= kLeanStepRows;
+    pg.valid = true;
+}
+
 }  // namespace
 
-void analyse_pattern(int N, const int* rowptr, const int* colidx, int P, PatternAnalysis& out)
+void analyse_pattern(int N, const int* rowptr, const int* colidx, int P, PatternAnalysis& out,
+                     bool force_simple)
 {
     out = PatternAnalysis();
     out.N = N;
@@ -197,8 +431,127 @@ void analyse_pattern(int N, const int* rowptr, const int* colidx, int P, Pattern
             for (int q = 0; q < sz; ++q) owner[out.lvl_rows[b + q]] = (int)((long long)q * P / sz);
         }
     }
-    build_program(N, rowptr, colidx, lvlL, nL, owner, P, true, out.lower);
-    build_program(N, rowptr, colidx, lvlU, nU, owner, P, false, out.upper);
+    build_pipe_program(N, rowptr, colidx, out.diag, lvlU, nU, owner, P, false, nullptr, out.pipeU);
+    if (out.pipeU.valid) {
+        std::vector<int> upos(N, 0);
+        for (size_t q = 0; q < out.pipeU.perm_row.size(); ++q)
+            if (out.pipeU.perm_row[q] >= 0) upos[out.pipeU.perm_row[q]] = (int)q;
+        build_pipe_program(N, rowptr, colidx, out.diag, lvlL, nL, owner, P, true, &upos, out.pipeL);
+    }
+    out.nlevL = nL; out.nlevU = nU;
+    if (force_simple || !out.pipeL.valid || !out.pipeU.valid) {
+        out.pipeL = PipeProgram(); out.pipeU = PipeProgram();
+        build_program(N, rowptr, colidx, lvlL, nL, owner, P, true, out.lower);
+        build_program(N, rowptr, colidx, lvlU, nU, owner, P, false, out.upper);
+    }
+}
+
+// Sequential interpreter of the pipelined programs (debug / CPU tests): executes the records
+// exactly as the kernel does -- thread-slot arrays, window slots, own-global reads, pushed
+// results, program-order right-hand sides -- advancing each CTA as far as its pushed inputs
+// allow.  rhs_perm is in this program's order; hand_off (lower only) receives the result in
+// the upper program's order; out (upper only) is in natural order.  Returns false on a deadlock.
+bool interpret_pipe_program(const PipeProgram& pg, bool upper, const double* rhs_perm, double* work,
+                            double* hand_off, double* out, double w, int scale)
+{
+    const int P = pg.P;
+    std::vector<double> ext((size_t)std::max<long long>(pg.total_ext, 1) * 3);
+    std::vector<unsigned char> ext_valid((size_t)std::max<long long>(pg.total_ext, 1), 0);
+    std::vector<int> cur(P);
+    std::vector<std::vector<double>> dep(P, std::vector<double>((size_t)(kDepZeroSlot + 1) * 3, 0.0));
+    std::vector<long long> qbase(P, 0), ext_seen(P, 0);
+    for (int c = 0; c < P; ++c) cur[c] = pg.cta_step_ptr[c];
+    bool progress = true, done = false;
+    while (progress && !done) {
+        progress = false; done = true;
+        for (int c = 0; c < P; ++c) {
+            while (cur[c] < pg.cta_step_ptr[c + 1]) {
+                done = false;
+                const int sidx = cur[c];
+                const unsigned char* rec = pg.buf.data() + (size_t)pg.step_off16[sidx] * 16;
+                const int* hdr = (const int*)rec;
+                const int n = hdr[0];
+                const double* cf = (const double*)(rec + 32);
+                const double* dinv = cf + (size_t)3 * n * 9;
+                const int* rowints = (const int*)(rec + ((32 + (size_t)3 * n * 72 + (upper ? (size_t)3 * n * 24 : 0) + 15) / 16) * 16);
+                const int* lists = (const int*)(rec + (size_t)hdr[5] * 8);
+                const bool has_lists = hdr[7] != 0;
+                const int* tail_end = lists;
+                const int* xpush_end = lists + (has_lists ? n : 0);
+                const int* tail_dep = lists + (has_lists ? 2 * n : 0);
+                const int* xpush_slot = tail_dep + hdr[4];
+                const double* tail_vals = (const double*)(rec + (size_t)hdr[6] * 8);
+                const long long ext_begin = ext_seen[c], ext_end = hdr[2];
+                bool ready = true;
+                for (long long e = ext_begin; e < ext_end && ready; ++e)
+                    if (!ext_valid[pg.cta_ext_base[c] + e]) ready = false;
+                if (!ready) break;
+                // the helper stages pushed results into the ring part of the dependency array
+                for (long long e = ext_begin; e < ext_end; ++e)
+                    for (int t = 0; t < 3; ++t)
+                        dep[c][(size_t)(kWindowRows + e % kExtRing) * 3 + t] = ext[(size_t)(pg.cta_ext_base[c] + e) * 3 + t];
+                std::vector<double> res((size_t)n * 3);
+                const double* rhs = rhs_perm + (size_t)pg.step_rhs_row[sidx] * 3;
+                auto yptr = [&](int code) -> const double* {
+                    return code < 0 ? &work[(size_t)(code & kDepValueMask) * 3] : &dep[c][(size_t)code];
+                };
+                for (int rr = 0; rr < n; ++rr) {
+                    double acc[3];
+                    for (int cc = 0; cc < 3; ++cc) {
+                        const int j = 3 * rr + cc;
+                        double a = rhs[j];
+                        for (int k = 0; k < kFastBlocks; ++k) {
+                            const double* y = yptr(rowints[8 * rr + 1 + k]);
+                            for (int e = 0; e < 3; ++e) a = std::fma(-cf[(size_t)j * 9 + k * 3 + e], y[e], a);
+                        }
+                        if (rowints[8 * rr] & kRowSlow) {
+                            for (int t = rr ? tail_end[rr - 1] : 0; t < tail_end[rr]; ++t) {
+                                const double* y = yptr(tail_dep[t]);
+                                const double* av = tail_vals + (size_t)t * 9 + cc * 3;
+                                for (int e = 0; e < 3; ++e) a = std::fma(-av[e], y[e], a);
+                            }
+                        }
+                        acc[cc] = a;
+                    }
+                    const int row = rowints[8 * rr] & kRowMask;
+                    if (upper) {
+                        double v[3];
+                        for (int cc = 0; cc < 3; ++cc) {
+                            const int j = 3 * rr + cc;
+                            double t = 0.0;
+                            for (int e = 0; e < 3; ++e) t = std::fma(dinv[(size_t)j * 3 + e], acc[e], t);
+                            v[cc] = t;
+                        }
+                        for (int cc = 0; cc < 3; ++cc) { acc[cc] = v[cc]; out[(size_t)row * 3 + cc] = scale ? v[cc] * w : v[cc]; }
+                    } else {
+                        for (int cc = 0; cc < 3; ++cc) hand_off[(size_t)rowints[8 * rr + 4] * 3 + cc] = acc[cc];
+                    }
+                    for (int cc = 0; cc < 3; ++cc) res[(size_t)rr * 3 + cc] = acc[cc];
+                }
+                for (int rr = 0; rr < n; ++rr) {
+                    const int rowinfo_rr = rowints[8 * rr];
+                    const int row = rowinfo_rr & kRowMask;
+                    const size_t slot = (size_t)((qbase[c] + rr) % kWindowRows) * 3;
+                    for (int t = 0; t < 3; ++t) dep[c][slot + t] = res[(size_t)rr * 3 + t];
+                    if (rowinfo_rr & kRowWriteGlobal)
+                        for (int t = 0; t < 3; ++t) work[(size_t)row * 3 + t] = res[(size_t)rr * 3 + t];
+                    auto push_to = [&](int slot_id) {
+                        for (int u = 0; u < 3; ++u) ext[(size_t)slot_id * 3 + u] = res[(size_t)rr * 3 + u];
+                        ext_valid[slot_id] = 1;
+                    };
+                    if (rowints[8 * rr + 5] >= 0) push_to(rowints[8 * rr + 5]);
+                    if (rowints[8 * rr + 6] >= 0) push_to(rowints[8 * rr + 6]);
+                    if (rowinfo_rr & kRowSlow)
+                        for (int t = rr ? xpush_end[rr - 1] : 0; t < xpush_end[rr]; ++t) push_to(xpush_slot[t]);
+                }
+                qbase[c] += n;
+                ext_seen[c] = ext_end;
+                ++cur[c];
+                progress = true;
+            }
+        }
+    }
+    return done;
 }
 
 void union_pattern_from_csc(int N, const CscView* blocks, int nblocks,
@@ -232,3 +585,41 @@ void union_pattern_from_csc(int N, const CscView* blocks, int nblocks,
 }
 
 }  // namespace opmgpu
+
+// Debug entry (not part of the public ABI; used by the CPU test-suite to validate the host
+// analysis without a GPU): runs both pipelined sweep programs through the sequential
+// interpreter on factors given in BCRS layout.  Returns 0, or a negative code.
+extern "C" int opmgpu_debug_host_program_apply(int N, const int* rowptr, const int* colidx,
+                                               const double* lu, int P, double w,
+                                               const double* d, double* v, int* info /*[8]*/)
+{
+    using namespace opmgpu;
+    PatternAnalysis an;
+    analyse_pattern(N, rowptr, colidx, P, an, false);
+    if (an.missing_diag_row >= 0) return -1;
+    if (!an.pipeL.valid || !an.pipeU.valid) return -2;
+    for (PipeProgram* pg : {&an.pipeL, &an.pipeU}) {
+        double* base = (double*)pg->buf.data();
+        for (size_t b = 0; b < pg->val_src.size(); ++b)
+            for (int c = 0; c < 3; ++c)
+                for (int e = 0; e < 3; ++e) {
+                    const size_t dst = (size_t)pg->val_dst8[b] + (size_t)c * pg->val_stride[b] + e;
+                    base[dst] = lu[(size_t)pg->val_src[b] * 9 + c * 3 + e];
+                }
+    }
+    std::vector<double> dperm((size_t)an.pipeL.nperm * 3, 0.0), yLperm((size_t)an.pipeU.nperm * 3, 0.0);
+    std::vector<double> workL((size_t)N * 3, 0.0), workU((size_t)N * 3, 0.0);
+    for (size_t q = 0; q < an.pipeL.perm_row.size(); ++q)
+        if (an.pipeL.perm_row[q] >= 0)
+            for (int t = 0; t < 3; ++t) dperm[q * 3 + t] = d[(size_t)an.pipeL.perm_row[q] * 3 + t];
+    const int scale = std::fabs(w - 1.0) > 1e-15 ? 1 : 0;
+    if (!interpret_pipe_program(an.pipeL, false, dperm.data(), workL.data(), yLperm.data(), nullptr, w, scale)) return -3;
+    if (!interpret_pipe_program(an.pipeU, true, yLperm.data(), workU.data(), nullptr, v, w, scale)) return -4;
+    if (info) {
+        info[0] = an.grid_nx; info[1] = an.grid_ny; info[2] = an.grid_nz;
+        info[3] = an.pipeL.nlevels; info[4] = an.pipeL.max_step_rows; info[5] = an.pipeL.max_step_bytes;
+        info[6] = (int)std::min<long long>(an.pipeL.total_ext, 0x7fffffff);
+        info[7] = (int)(an.pipeL.cta_step_ptr[P]);
+    }
+    return 0;
+}

@@ -33,6 +33,63 @@ struct SweepProgram {
     std::vector<unsigned char> publish;      // [N]   program row has a consumer in another CTA
 };
 
+// ---- pipelined sweep program (the fast path) ---------------------------------------------------
+// Per CTA a byte stream of step records, one record per step, consumed linearly through a
+// shared-memory ring filled by bulk async copies (TMA).  A record is laid out for the thread
+// that consumes it: thread slot j = 3*r + c owns component c of the step's r-th row and finds
+// everything it needs at fixed offsets from one base address.  Record layout:
+//   int hdr[8]: nrows, qbase (program row of the first row, CTA-local), ext_end, ext entries of
+//               this step, ntail, off_lists/8, off_tailvals/8, has_lists
+//   double cf[3n][9]       cf[j][k*3+e]: entry [c][e] of the k-th off-diagonal block of row r
+//                          (k < kFastBlocks, reference visiting order; absent blocks are 0)
+//   double dinv[3n][3]     dinv[j][e]: entry [c][e] of the inverted diagonal block (upper only)
+//   int rowints[n][8]      rowinfo (global row | kRowWriteGlobal | kRowSlow), dep[3], upos,
+//                          push[2], -.   dep[k]: dependency of block k = index (in doubles)
+//                          into the CTA's shared dependency array, or kDepGlobalBit | global
+//                          row; upos (lower only): position of the row in the upper sweep's
+//                          program order; push: global push slot ids (-1: none)
+//   -- only when the step has slow rows (more than 3 blocks / more than 2 pushes):
+//   int tail_end[n], xpush_end[n]; int tail_dep[ntail]; int xpush_slot[npushx];
+//   double tail_vals[ntail][9]
+// The shared dependency array holds 3-double entries: [0, kWindowRows) the CTA's own recent
+// results (slot = program row % kWindowRows), [kWindowRows, kWindowRows+kExtRing) results
+// pushed by other CTAs (slot = kWindowRows + ordinal % kExtRing), then one all-zero entry that
+// absent blocks point to.
+constexpr int kFastBlocks = 3;
+constexpr int kDepGlobalBit = (int)0x80000000;
+constexpr int kDepValueMask = 0x3fffffff;
+constexpr int kRowWriteGlobal = 1 << 30;
+constexpr int kRowSlow = (int)0x80000000;
+constexpr int kRowMask = (1 << 30) - 1;
+constexpr int kWindowRows = 512;          // W: results kept in shared memory per CTA
+constexpr int kExtRing = 512;             // R: pushed results staged in shared memory per CTA
+constexpr int kDepZeroSlot = kWindowRows + kExtRing;
+constexpr int kMaxStepRows = 240;
+constexpr int kMaxStepBytes = 64 * 1024;
+constexpr int kMaxStepExt = kExtRing - 96;
+constexpr int kLeanStepRows = 80;         // rows one pass of the compute warps covers
+
+struct PipeProgram {
+    bool valid = false;
+    bool lean = false;                        // no slow rows, no own-global reads, steps <= one pass
+    int P = 0, nlevels = 0;
+    int max_step_bytes = 0, max_step_rows = 0;   // rows padded to even
+    long long total_ext = 0;
+    long long nperm = 0;                      // length (rows) of vectors in this program's order
+    std::vector<unsigned char> buf;           // all records, CTA after CTA
+    std::vector<int> cta_step_ptr;            // [P+1]
+    std::vector<unsigned> step_off16;         // [nsteps] record offset / 16
+    std::vector<unsigned> step_bytes;         // [nsteps]
+    std::vector<unsigned> step_rhs_row;       // [nsteps] first row of the step in program order (even)
+    std::vector<unsigned> step_rhs_bytes;     // [nsteps] bytes of its rhs segment (rows padded to even)
+    std::vector<int> perm_row;                // [nperm] natural row at each program position (-1 pad)
+    std::vector<long long> cta_ext_base;      // [P+1] first global push slot of the CTA
+    // where the factorisation's values go: (BCRS slot, element) -> double index in buf
+    std::vector<int> val_src;                 // [nval] BCRS slot
+    std::vector<unsigned> val_dst8;           // [nval] double index of element [0][0]...
+    std::vector<int> val_stride;              // [nval] element [c][e] goes to dst8 + c*stride + e
+};
+
 struct PatternAnalysis {
     int N = 0, nnzb = 0;
     std::vector<int> diag;                   // [N] BCRS slot of the diagonal block
@@ -40,11 +97,18 @@ struct PatternAnalysis {
     std::vector<int> lvl_ptr, lvl_rows;
     int grid_nx = 0, grid_ny = 0, grid_nz = 0;   // inferred Cartesian structure (0 = none)
     SweepProgram lower, upper;
+    PipeProgram pipeL, pipeU;
     int missing_diag_row = -1;
+    int nlevL = 0, nlevU = 0;
 };
 
 // P = number of persistent CTAs the sweeps will be launched with.
-void analyse_pattern(int N, const int* rowptr, const int* colidx, int P, PatternAnalysis& out);
+void analyse_pattern(int N, const int* rowptr, const int* colidx, int P, PatternAnalysis& out,
+                     bool force_simple = false);
+
+// Sequential interpreter of a pipelined program (debug / CPU tests of the host analysis).
+bool interpret_pipe_program(const PipeProgram& pg, bool upper, const double* rhs_perm, double* work,
+                            double* hand_off, double* out, double w, int scale);
 
 // Union pattern of the pressure-derivative CSC blocks -> row-major ascending
 // (formInterleavedSystem, ...Interleaved.cpp:118-155).

@@ -298,6 +298,20 @@ repack_blocks_kernel(size_t nblk, const int* __restrict__ psrc, const double* __
     const size_t b = e / 9;
     pval[e] = lu[(size_t)psrc[b] * 9 + (e - b * 9)];
 }
+// factors (BCRS order) -> step records of the pipelined sweeps.  Element [c][e] of source block
+// b goes to double index dst8[b] + c*stride[b] + e.
+__global__ void __launch_bounds__(256)
+repack_pipe_kernel(size_t n, const int* __restrict__ src, const unsigned* __restrict__ dst8,
+                   const int* __restrict__ stride, const double* __restrict__ lu, double* __restrict__ bufd)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * 9) return;
+    const size_t b = t / 9;
+    const int q = (int)(t - b * 9), c = q / 3, e = q - c * 3;
+    const int st = stride[b];
+    const size_t dst = (size_t)dst8[b] + (size_t)c * st + e;
+    bufd[dst] = lu[(size_t)src[b] * 9 + q];
+}
 __global__ void __launch_bounds__(256)
 repack_dinv_kernel(int N, const int* __restrict__ prow, const int* __restrict__ diag,
                    const double* __restrict__ lu, double* __restrict__ pdinv)

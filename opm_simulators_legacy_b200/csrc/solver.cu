@@ -7,6 +7,7 @@
 #include "../../include/opm_gpu_solver.h"
 #include "analysis.hpp"
 #include "kernels.cuh"
+#include "sweep_pipe.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -51,6 +52,24 @@ struct ProgramDevMem {
     }
 };
 
+struct PipeDevMem {
+    DevArr<unsigned char> buf;
+    DevArr<int> cta_step_ptr, val_src, val_stride, perm_row;
+    DevArr<unsigned> step_off16, step_bytes, step_rhs_row, step_rhs_bytes, val_dst8;
+    DevArr<long long> cta_ext_base;
+    DevArr<double> ext, rhs_perm;
+    size_t nval = 0, next = 0, nperm = 0;
+    int P = 0, nstages = 0, stage_bytes = 0, rhs_bytes = 0;
+    bool lean = false;
+    size_t smem = 0;
+    void release()
+    {
+        buf.release(); cta_step_ptr.release(); val_src.release(); val_stride.release(); perm_row.release();
+        step_off16.release(); step_bytes.release(); step_rhs_row.release(); step_rhs_bytes.release();
+        val_dst8.release(); cta_ext_base.release(); ext.release(); rhs_perm.release();
+    }
+};
+
 }  // namespace
 
 struct opmgpu_solver {
@@ -67,6 +86,11 @@ struct opmgpu_solver {
     PatternAnalysis an;
     DevArr<int> d_rowptr, d_colidx, d_diag, d_lvl_rows;
     ProgramDevMem progL, progU;
+    PipeDevMem pipeL, pipeU;
+    bool use_pipe = false, force_simple = false;
+    int trace_cta = -1;
+    DevArr<long long> d_trace;
+    int max_smem_optin = 0;
 
     // values and factors
     DevArr<double> d_vals_own, d_lu;
@@ -138,6 +162,48 @@ int upload_program(opmgpu_handle h, const SweepProgram& p, ProgramDevMem& d, boo
     return 0;
 }
 
+int upload_pipe(opmgpu_handle h, const PipeProgram& p, PipeDevMem& d)
+{
+    int rc;
+    CK(d.buf.ensure(p.buf.size()));
+    CK(cudaMemcpyAsync(d.buf.p, p.buf.data(), p.buf.size(), cudaMemcpyHostToDevice, h->stream));
+    if ((rc = upload(h, d.cta_step_ptr, p.cta_step_ptr))) return rc;
+    if ((rc = upload(h, d.step_off16, p.step_off16))) return rc;
+    if ((rc = upload(h, d.step_bytes, p.step_bytes))) return rc;
+    if ((rc = upload(h, d.step_rhs_row, p.step_rhs_row))) return rc;
+    if ((rc = upload(h, d.step_rhs_bytes, p.step_rhs_bytes))) return rc;
+    if ((rc = upload(h, d.cta_ext_base, p.cta_ext_base))) return rc;
+    if ((rc = upload(h, d.val_src, p.val_src))) return rc;
+    if ((rc = upload(h, d.val_dst8, p.val_dst8))) return rc;
+    if ((rc = upload(h, d.val_stride, p.val_stride))) return rc;
+    if ((rc = upload(h, d.perm_row, p.perm_row))) return rc;
+    d.nval = p.val_src.size(); d.next = (size_t)p.total_ext; d.P = p.P; d.nperm = (size_t)p.nperm; d.lean = p.lean;
+    CK(d.ext.ensure(std::max<size_t>(d.next, 1) * 3));
+    CK(cudaMemsetAsync(d.ext.p, 0xff, std::max<size_t>(d.next, 1) * 3 * sizeof(double), h->stream));
+    CK(d.rhs_perm.ensure(std::max<size_t>(d.nperm, 2) * 3));
+    CK(cudaMemsetAsync(d.rhs_perm.p, 0, std::max<size_t>(d.nperm, 2) * 3 * sizeof(double), h->stream));
+    // ring geometry: as many stages as fit next to the dependency array
+    d.stage_bytes = (p.max_step_bytes + 15) / 16 * 16;
+    d.rhs_bytes = (p.max_step_rows * 24 + 15) / 16 * 16;
+    const size_t fixed = pipe_smem_bytes(0, 0, 0);
+    const size_t per_stage = (size_t)d.stage_bytes + d.rhs_bytes;
+    int S = (int)(((size_t)h->max_smem_optin - fixed) / per_stage);
+    d.nstages = std::min(S, kPipeMaxStages);
+    d.smem = pipe_smem_bytes(d.nstages, d.stage_bytes, d.rhs_bytes);
+    return 0;
+}
+
+PipeDev pipe_dev(const PipeDevMem& d)
+{
+    PipeDev p;
+    p.buf = d.buf.p; p.cta_step_ptr = d.cta_step_ptr.p; p.step_off16 = d.step_off16.p; p.step_bytes = d.step_bytes.p;
+    p.step_rhs_row = d.step_rhs_row.p; p.step_rhs_bytes = d.step_rhs_bytes.p;
+    p.cta_ext_base = d.cta_ext_base.p; p.ext = d.ext.p;
+    p.stage_bytes = d.stage_bytes; p.rhs_bytes = d.rhs_bytes; p.nstages = d.nstages;
+    p.trace = nullptr; p.trace_cta = -1;
+    return p;
+}
+
 SweepDev sweep_dev(const ProgramDevMem& d)
 {
     SweepDev s;
@@ -167,7 +233,7 @@ int set_pattern(opmgpu_handle h, int N, int nnzb, const int* rowptr, const int* 
         }
     }
     h->have_pattern = h->have_values = h->have_factors = false;
-    analyse_pattern(N, rowptr, colidx, h->sweep_ctas, h->an);
+    analyse_pattern(N, rowptr, colidx, h->sweep_ctas, h->an, h->force_simple);
     if (h->an.missing_diag_row >= 0) {
         h->err = "diagonal entry missing in block row " + std::to_string(h->an.missing_diag_row);
         return OPMGPU_SINGULAR_BLOCK;
@@ -180,8 +246,20 @@ int set_pattern(opmgpu_handle h, int N, int nnzb, const int* rowptr, const int* 
     int rc;
     if ((rc = upload(h, h->d_diag, h->an.diag))) return rc;
     if ((rc = upload(h, h->d_lvl_rows, h->an.lvl_rows))) return rc;
-    if ((rc = upload_program(h, h->an.lower, h->progL, false))) return rc;
-    if ((rc = upload_program(h, h->an.upper, h->progU, true))) return rc;
+    h->use_pipe = h->an.pipeL.valid && h->an.pipeU.valid;
+    if (h->use_pipe) {
+        if ((rc = upload_pipe(h, h->an.pipeL, h->pipeL))) return rc;
+        if ((rc = upload_pipe(h, h->an.pipeU, h->pipeU))) return rc;
+        if (h->pipeL.nstages < 3 || h->pipeU.nstages < 3) h->use_pipe = false;
+    }
+    if (!h->use_pipe) {
+        if (h->an.lower.prow.empty()) analyse_pattern(N, rowptr, colidx, h->sweep_ctas, h->an, true);
+        if ((rc = upload_program(h, h->an.lower, h->progL, false))) return rc;
+        if ((rc = upload_program(h, h->an.upper, h->progU, true))) return rc;
+        h->pipeL.release(); h->pipeU.release();
+    } else {
+        h->progL.release(); h->progU.release();
+    }
     CK(h->d_lu.ensure((size_t)nnzb * 9));
     if ((rc = ensure_vectors(h))) return rc;
     CK(h->d_flags.ensure(N));
@@ -189,8 +267,9 @@ int set_pattern(opmgpu_handle h, int N, int nnzb, const int* rowptr, const int* 
     h->epoch = 0;
     CK(cudaStreamSynchronize(h->stream));      // host vectors of the analysis may now be dropped
     // keep only what the host still needs
-    h->nlevL = h->an.lower.nlevels; h->nlevU = h->an.upper.nlevels;
+    h->nlevL = h->an.nlevL; h->nlevU = h->an.nlevU;
     h->an.lower = SweepProgram(); h->an.upper = SweepProgram();
+    h->an.pipeL = PipeProgram(); h->an.pipeU = PipeProgram();
     h->have_pattern = true;
     return OPMGPU_OK;
 }
@@ -259,7 +338,16 @@ int factor(opmgpu_handle h, int* bad_row)
     }
     CK(cudaGetLastError());
     // stream the factors into the sweep programs' layout
-    if (h->progL.nblk) {
+    if (h->use_pipe) {
+        for (PipeDevMem* d : {&h->pipeL, &h->pipeU}) {
+            if (d->nval) {
+                const size_t e = d->nval * 9;
+                repack_pipe_kernel<<<(unsigned)((e + 255) / 256), 256, 0, h->stream>>>(d->nval, d->val_src.p, d->val_dst8.p, d->val_stride.p, h->d_lu.p, (double*)d->buf.p);
+                h->launches++;
+            }
+        }
+    } else if (h->progL.nblk || h->progU.nblk || true) {
+      if (h->progL.nblk) {
         const size_t e = h->progL.nblk * 9;
         repack_blocks_kernel<<<(unsigned)((e + 255) / 256), 256, 0, h->stream>>>(h->progL.nblk, h->progL.psrc.p, h->d_lu.p, h->progL.pval.p);
         h->launches++;
@@ -273,6 +361,7 @@ int factor(opmgpu_handle h, int* bad_row)
         const size_t e = (size_t)h->N * 9;
         repack_dinv_kernel<<<(unsigned)((e + 255) / 256), 256, 0, h->stream>>>(h->N, h->progU.prow.p, h->d_diag.p, h->d_lu.p, h->progU.pdinv.p);
         h->launches++;
+    }
     }
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(&h->h_flags2[1], h->d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -292,6 +381,30 @@ int factor(opmgpu_handle h, int* bad_row)
 int apply_precond(opmgpu_handle h, double w, const double* d, double* v)
 {
     const int scale = std::fabs(w - 1.0) > 1e-15 ? 1 : 0;      // relaxation_ flag of the reference
+    if (h->use_pipe) {
+        {
+            const size_t e = h->pipeL.nperm * 3;
+            permute_rows_kernel<<<(unsigned)((e + 255) / 256), 256, 0, h->stream>>>(h->pipeL.nperm, h->pipeL.perm_row.p, d, h->pipeL.rhs_perm.p);
+        }
+        {
+            PipeDev pg = pipe_dev(h->pipeL);
+            if (h->trace_cta >= 0 && h->d_trace.p) { pg.trace = h->d_trace.p; pg.trace_cta = h->trace_cta; }
+            const double* rhs = h->pipeL.rhs_perm.p; double* work = h->d_yL.p; double* hand = h->pipeU.rhs_perm.p;
+            double* out = nullptr; int* err = h->d_err.p;
+            void* args[] = {&pg, &rhs, &work, &hand, &out, &w, (void*)&scale, &err};
+            CK(cudaLaunchCooperativeKernel(h->pipeL.lean ? (void*)ilu0_sweep_pipe_kernel<false, true> : (void*)ilu0_sweep_pipe_kernel<false, false>, dim3(h->pipeL.P), dim3(kPipeThreads), args, h->pipeL.smem, h->stream));
+        }
+        {
+            PipeDev pg = pipe_dev(h->pipeU);
+            if (h->trace_cta >= 0 && h->d_trace.p) { pg.trace = h->d_trace.p + 512 * 16; pg.trace_cta = h->trace_cta; }
+            const double* rhs = h->pipeU.rhs_perm.p; double* work = h->d_vU.p; double* hand = nullptr;
+            double* out = v; int* err = h->d_err.p;
+            void* args[] = {&pg, &rhs, &work, &hand, &out, &w, (void*)&scale, &err};
+            CK(cudaLaunchCooperativeKernel(h->pipeU.lean ? (void*)ilu0_sweep_pipe_kernel<true, true> : (void*)ilu0_sweep_pipe_kernel<true, false>, dim3(h->pipeU.P), dim3(kPipeThreads), args, h->pipeU.smem, h->stream));
+        }
+        h->launches += 3;
+        return 0;
+    }
     {
         SweepDev pg = sweep_dev(h->progL);
         const double* rhs = d; double* work = h->d_yL.p; double* out = nullptr;
@@ -311,15 +424,23 @@ int apply_precond(opmgpu_handle h, double w, const double* d, double* v)
     return 0;
 }
 
+int sweep_watchdog(opmgpu_handle h)
+{
+    h->err = "ILU0 sweep watchdog (code " + std::to_string(h->h_flags2[0]) + "): a dependency was never delivered";
+    // re-arm: clear the error word and every push slot, so the handle stays usable
+    cudaMemsetAsync(h->d_err.p, 0, sizeof(int), h->stream);
+    for (PipeDevMem* d : {&h->pipeL, &h->pipeU})
+        if (d->ext.p) cudaMemsetAsync(d->ext.p, 0xff, std::max<size_t>(d->next, 1) * 3 * sizeof(double), h->stream);
+    cudaStreamSynchronize(h->stream);
+    return OPMGPU_CUDA_ERROR;
+}
+
 int read_scalars(opmgpu_handle h)
 {
     CK(cudaMemcpyAsync(h->h_S, h->d_S.p, sizeof(double) * S_COUNT, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(&h->h_flags2[0], h->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    if (h->h_flags2[0]) {
-        h->err = "ILU0 sweep watchdog: a dependency flag was never published";
-        return OPMGPU_CUDA_ERROR;
-    }
+    if (h->h_flags2[0]) return sweep_watchdog(h);
     return 0;
 }
 
@@ -476,6 +597,22 @@ int opmgpu_create(int device, opmgpu_handle* out)
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ilu0_sweep_kernel<true>, 256, 0);
     per_sm = std::min(per_sm, std::max(occ, 1));
     h->sweep_ctas = h->sm_count * per_sm;
+    if (const char* s = getenv("OPMGPU_SIMPLE_SWEEP")) h->force_simple = atoi(s) != 0;
+    cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
+    cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
+    cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
+    cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
+    if (!h->force_simple) h->sweep_ctas = h->sm_count;      // the pipelined sweep owns a whole SM per CTA
+    if (getenv("OPMGPU_DEBUG")) {
+        cudaFuncAttributes fa;
+        cudaFuncGetAttributes(&fa, ilu0_sweep_pipe_kernel<false, true>);
+        int occ0 = -1, occ1 = -1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ0, ilu0_sweep_pipe_kernel<false, true>, kPipeThreads, 100 * 1024);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, ilu0_sweep_pipe_kernel<false, true>, kPipeThreads, (size_t)h->max_smem_optin);
+        fprintf(stderr, "[opmgpu] sweep kernel: regs %d, maxThreadsPerBlock %d, static smem %zu, local %zu, optin %d, occ(100KB) %d occ(max) %d, threads %d\n",
+                fa.numRegs, fa.maxThreadsPerBlock, fa.sharedSizeBytes, fa.localSizeBytes, h->max_smem_optin, occ0, occ1, kPipeThreads);
+    }
     if ((e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
         g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e);
         delete h;
@@ -506,7 +643,7 @@ int opmgpu_destroy(opmgpu_handle h)
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     h->d_rowptr.release(); h->d_colidx.release(); h->d_diag.release(); h->d_lvl_rows.release();
-    h->progL.release(); h->progU.release();
+    h->progL.release(); h->progU.release(); h->pipeL.release(); h->pipeU.release();
     h->d_vals_own.release(); h->d_lu.release();
     h->d_x.release(); h->d_r.release(); h->d_rt.release(); h->d_p.release(); h->d_v.release();
     h->d_t.release(); h->d_y.release(); h->d_yL.release(); h->d_vU.release(); h->d_tmp.release(); h->d_tmp2.release();
@@ -613,7 +750,7 @@ int opmgpu_ilu0_apply(opmgpu_handle h, double w, const double* d, double* v)
     CK(cudaMemcpyAsync(v, h->d_tmp2.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(&h->h_flags2[0], h->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    if (h->h_flags2[0]) { h->err = "ILU0 sweep watchdog: a dependency flag was never published"; return OPMGPU_CUDA_ERROR; }
+    if (h->h_flags2[0]) return sweep_watchdog(h);
     return OPMGPU_OK;
 }
 
@@ -791,6 +928,24 @@ int opmgpu_residual_history(opmgpu_handle h, double* out, int cap, int* n)
     if (!h || !n) return OPMGPU_BAD_ARGUMENT;
     *n = (int)h->history.size();
     for (int i = 0; i < cap && i < *n; ++i) out[i] = h->history[i];
+    return OPMGPU_OK;
+}
+
+// Debug (not in the public header): clock64 stamps of one CTA of the next pipelined apply.
+// out[2][512][8]: lower then upper sweep; per step {enter, landed, computed, after barrier,
+// nrows, bulk issued, rhs gather issued, -}.
+int opmgpu_debug_trace_apply(opmgpu_handle h, int cta, double w, const double* d_dev, double* v_dev, long long* out)
+{
+    if (!h || !h->have_factors || !h->use_pipe) return OPMGPU_BAD_ARGUMENT;
+    CK(cudaSetDevice(h->device));
+    CK(h->d_trace.ensure(2 * 512 * 16));
+    CK(cudaMemsetAsync(h->d_trace.p, 0, sizeof(long long) * 2 * 512 * 16, h->stream));
+    h->trace_cta = cta;
+    int rc = apply_precond(h, w, d_dev, v_dev);
+    h->trace_cta = -1;
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out, h->d_trace.p, sizeof(long long) * 2 * 512 * 16, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
     return OPMGPU_OK;
 }
 
