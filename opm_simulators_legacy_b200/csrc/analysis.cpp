@@ -344,7 +344,8 @@ void build_pipe_program(int N, const int* rowptr, const int* colidx, const std::
                     ++kb;
                 });
                 int np = 0;
-                ri[5] = -1; ri[6] = -1; ri[7] = 0;
+                ri[5] = -1; ri[6] = -1;
+                ri[7] = ((steps[sidx].q0 - cta_q0 + rr) % kWindowRows) * 3;      // own window slot (doubles)
                 for (int t = push_ptr[r]; t < push_ptr[r + 1]; ++t, ++np) {
                     if (np < 2) ri[5 + np] = (int)push_slot[t];
                     else xpush_slot[npx++] = (int)push_slot[t];

@@ -44,7 +44,7 @@ struct SweepProgram {
 //                          (k < kFastBlocks, reference visiting order; absent blocks are 0)
 //   double dinv[3n][3]     dinv[j][e]: entry [c][e] of the inverted diagonal block (upper only)
 //   int rowints[n][8]      rowinfo (global row | kRowWriteGlobal | kRowSlow), dep[3], upos,
-//                          push[2], -.   dep[k]: dependency of block k = index (in doubles)
+//                          push[2], own window slot (doubles).   dep[k]: dependency of block k = index (in doubles)
 //                          into the CTA's shared dependency array, or kDepGlobalBit | global
 //                          row; upos (lower only): position of the row in the upper sweep's
 //                          program order; push: global push slot ids (-1: none)

@@ -604,6 +604,7 @@ int opmgpu_create(int device, opmgpu_handle* out)
     cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
     cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
     if (!h->force_simple) h->sweep_ctas = h->sm_count;      // the pipelined sweep owns a whole SM per CTA
+    if (const char* s = getenv("OPMGPU_PIPE_CTAS")) h->sweep_ctas = std::max(1, std::min(h->sm_count, atoi(s)));
     if (getenv("OPMGPU_DEBUG")) {
         cudaFuncAttributes fa;
         cudaFuncGetAttributes(&fa, ilu0_sweep_pipe_kernel<false, true>);

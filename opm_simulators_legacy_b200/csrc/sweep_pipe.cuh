@@ -257,7 +257,7 @@ __device__ __forceinline__ double sweep_row_chain(const StepPre<UPPER>& p, const
             acc = v;
         }
     }
-    if (p.on) dep[((p.qbase + r) & (kWindowRows - 1)) * 3 + c] = acc;
+    if (p.on) dep[p.ri1.w + c] = acc;
     return acc;
 }
 // ... and the part nobody inside the CTA waits for: results to HBM, pushes to other CTAs
@@ -412,12 +412,7 @@ ilu0_sweep_pipe_kernel(PipeDev pg, const double* __restrict__ rhs_perm, double* 
             }
             if (tr) pg.trace[s * 16 + 0] = clock64();
             if (s > 0) asm volatile("bar.sync %0, %1;" ::"r"(2 - g), "n"(NPP) : "memory");     // step s-1 done
-            if (tr) pg.trace[s * 16 + 1] = clock64();
-            // every warp of this group is past its step s-2 now: release that stage
-            if (elected && st_prev >= 0) {
-                ctl->ext_consumed = ext_prev_end;
-                mbar_arrive(&ctl->empty[st_prev]);
-            }
+            if (tr) pg.trace[s * 16 + 1] = clock64() + (ctl->abort_flag == 12345);
             // pushed inputs of this step staged by the helper warp?  (ring data is written
             // before ext_ready, and shared-memory accesses of a thread are not reordered)
             if (!dead && p.ext_cnt > 0) {
@@ -429,6 +424,12 @@ ilu0_sweep_pipe_kernel(PipeDev pg, const double* __restrict__ rhs_perm, double* 
                 sweep_extra_rows<UPPER>(stage, pg.rhs_bytes, p.n, r_first, c, rl, lane_on, dep, work, hand_off, out, pg.ext, w, scale);
             if (tr) { pg.trace[s * 16 + 2] = clock64(); pg.trace[s * 16 + 4] = p.n; }
             asm volatile("bar.arrive %0, %1;" ::"r"(1 + g), "n"(NPP) : "memory");             // step s done
+            // every warp of this group passed the bar.sync of this step, i.e. is done with its
+            // step s-2: release that stage and its pushed-result ring entries
+            if (elected && st_prev >= 0) {
+                ctl->ext_consumed = ext_prev_end;
+                mbar_arrive(&ctl->empty[st_prev]);
+            }
             sweep_row_stores<UPPER, LEAN>(p, stage + pg.rhs_bytes, r_first, c, acc, work, hand_off, out, pg.ext, w, scale);
             if (tr) pg.trace[s * 16 + 3] = clock64();
             st_prev = st; ext_prev_end = p.ext_end;
