@@ -12,7 +12,7 @@
  * opm/core/linalg/LinearSolverInterface.hpp:67-74 and struct CSRMatrix at
  * opm/core/linalg/sparse_sys.h:38-47.
  *
- * Conventions: every function returns an opmgpu_status (0 = ok); no exception crosses the
+ * Conventions: every function returns an opmgpu_status value, 0 = ok; no exception crosses the
  * ABI; all pointers are HOST pointers unless the name ends in _dev; block size is 3
  * (np = 3, water/oil/gas); FP64 values, int32 indices.  A handle owns one GPU (one CUDA
  * stream); it is not re-entrant, matching the reference's single-threaded caller
@@ -149,6 +149,12 @@ int  opmgpu_dot(opmgpu_handle h, const double* x, const double* y, int n, double
 /* Analysis facts for reports: ILU0 dependency levels, kernel launches since creation. */
 int  opmgpu_num_levels(opmgpu_handle h, int* lower_levels, int* upper_levels);
 long long opmgpu_launch_count(opmgpu_handle h);
+/* Per-kernel-class device time of the solves since profiling was switched on, from CUDA events
+ * recorded on the launching stream: [0] ILU0 applies, [1] SpMV (+fused dots), [2] BiCGStab
+ * vector kernels, [3] ILU0 factorisation (the reference's own split is one number,
+ * report.linear_solve_time, BlackoilModelBase_impl.hpp:290-294). */
+int  opmgpu_set_profiling(opmgpu_handle h, int on);
+int  opmgpu_get_profile(opmgpu_handle h, double ms[4], long long count[4]);
 /* |r| after every half step of the last solve (verbosity / parity reports). */
 int  opmgpu_residual_history(opmgpu_handle h, double* out, int cap, int* n);
 

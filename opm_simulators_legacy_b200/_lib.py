@@ -21,6 +21,7 @@ EXPORTS = [
     "opmgpu_set_values_bcrs3", "opmgpu_set_values_bcrs3_dev", "opmgpu_spmv", "opmgpu_spmv_dev",
     "opmgpu_ilu0_factor", "opmgpu_ilu0_get_factors", "opmgpu_ilu0_apply", "opmgpu_ilu0_apply_dev",
     "opmgpu_dot", "opmgpu_num_levels", "opmgpu_launch_count", "opmgpu_residual_history",
+    "opmgpu_set_profiling", "opmgpu_get_profile",
 ]
 
 OK, NOT_CONVERGED, SINGULAR_BLOCK, BREAKDOWN, BAD_PATTERN, BAD_ARGUMENT = 0, 1, 2, 3, 4, 5
@@ -92,6 +93,8 @@ def load():
         "opmgpu_num_levels": (C.c_int, [H, ip, ip]),
         "opmgpu_launch_count": (C.c_longlong, [H]),
         "opmgpu_residual_history": (C.c_int, [H, dp, C.c_int, ip]),
+        "opmgpu_set_profiling": (C.c_int, [H, C.c_int]),
+        "opmgpu_get_profile": (C.c_int, [H, dp, C.POINTER(C.c_longlong)]),
     }
     for name, (res, args) in sig.items():
         f = getattr(lib, name)

@@ -116,6 +116,39 @@ struct opmgpu_solver {
 
     std::vector<double> history;
 
+    // optional per-kernel-class timing (CUDA events on the launching stream)
+    bool profile = false;
+    std::vector<cudaEvent_t> prof_pool;
+    std::vector<int> prof_kind;             // kind of each recorded [begin,end) pair
+    size_t prof_used = 0;
+    double prof_ms[4] = {0, 0, 0, 0};       // 0 precond apply, 1 spmv(+dots), 2 vector kernels, 3 factor
+    long long prof_cnt[4] = {0, 0, 0, 0};
+    void prof_begin(int kind)
+    {
+        if (!profile) return;
+        if (prof_used + 2 > prof_pool.size()) {
+            const size_t old = prof_pool.size();
+            prof_pool.resize(old + 256);
+            for (size_t i = old; i < prof_pool.size(); ++i) cudaEventCreate(&prof_pool[i]);
+        }
+        prof_kind.push_back(kind);
+        cudaEventRecord(prof_pool[prof_used++], stream);
+    }
+    void prof_end() { if (profile) cudaEventRecord(prof_pool[prof_used++], stream); }
+    void prof_collect()
+    {
+        if (!profile) return;
+        cudaStreamSynchronize(stream);
+        for (size_t i = 0; i < prof_kind.size(); ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, prof_pool[2 * i], prof_pool[2 * i + 1]);
+            prof_ms[prof_kind[i]] += ms;
+            prof_cnt[prof_kind[i]]++;
+        }
+        prof_kind.clear();
+        prof_used = 0;
+    }
+
     int fail(cudaError_t e, const char* what)
     {
         char buf[512];
@@ -472,12 +505,20 @@ int bicgstab(opmgpu_handle h, const opmgpu_params* prm, opmgpu_result* res)
         if (it < 1) {
             CK(cudaMemcpyAsync(h->d_p.p, h->d_r.p, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
         } else {
+            h->prof_begin(2);
             bicg_update_p_kernel<<<kVecBlocks, 256, 0, h->stream>>>(n, h->d_p.p, h->d_r.p, h->d_v.p, h->d_S.p);
+            h->prof_end();
             h->launches++;
         }
+        h->prof_begin(0);
         if ((rc = apply_precond(h, w, h->d_p.p, h->d_y.p))) return rc;
+        h->prof_end();
+        h->prof_begin(1);
         if ((rc = spmv_with_dots(h, 1, h->d_y.p, h->d_v.p, h->d_rt.p))) return rc;
+        h->prof_end();
+        h->prof_begin(2);
         bicg_update1_kernel<<<kVecBlocks, 256, 0, h->stream>>>(n, h->d_x.p, h->d_r.p, h->d_y.p, h->d_v.p, h->d_S.p, h->ws());
+        h->prof_end();
         h->launches++;
         if ((rc = read_scalars(h))) return rc;
         if (std::fabs(h->h_S[S_H]) < EPSILON) { status = OPMGPU_BREAKDOWN; break; }
@@ -488,9 +529,15 @@ int bicgstab(opmgpu_handle h, const opmgpu_params* prm, opmgpu_result* res)
         it += 0.5;
         if (half_limit >= 0 && half >= half_limit) break;
 
+        h->prof_begin(0);
         if ((rc = apply_precond(h, w, h->d_r.p, h->d_y.p))) return rc;
+        h->prof_end();
+        h->prof_begin(1);
         if ((rc = spmv_with_dots(h, 2, h->d_y.p, h->d_t.p, h->d_r.p))) return rc;
+        h->prof_end();
+        h->prof_begin(2);
         bicg_update2_kernel<<<kVecBlocks, 256, 0, h->stream>>>(n, h->d_x.p, h->d_r.p, h->d_y.p, h->d_t.p, h->d_rt.p, h->d_S.p, h->ws());
+        h->prof_end();
         h->launches++;
         if ((rc = read_scalars(h))) return rc;
         omega = h->h_S[S_OMEGA];
@@ -522,7 +569,9 @@ int solve_resident(opmgpu_handle h, const opmgpu_params* prm, opmgpu_result* res
 {
     cudaEventRecord(h->ev[0], h->stream);
     int badrow = -1;
+    h->prof_begin(3);
     int rc = factor(h, &badrow);
+    h->prof_end();
     cudaEventRecord(h->ev[1], h->stream);
     if (rc) { res->bad_row = badrow; return rc; }
     rc = bicgstab(h, prm, res);
@@ -530,6 +579,7 @@ int solve_resident(opmgpu_handle h, const opmgpu_params* prm, opmgpu_result* res
     cudaEventSynchronize(h->ev[2]);
     res->ms_factor = ev_ms(h->ev[0], h->ev[1]);
     res->ms_solve = ev_ms(h->ev[1], h->ev[2]);
+    h->prof_collect();
     if (rc == OPMGPU_NOT_CONVERGED && prm->linear_solver_ignoreconvergencefailure) rc = OPMGPU_OK;
     return rc;
 }
@@ -929,6 +979,21 @@ int opmgpu_residual_history(opmgpu_handle h, double* out, int cap, int* n)
     if (!h || !n) return OPMGPU_BAD_ARGUMENT;
     *n = (int)h->history.size();
     for (int i = 0; i < cap && i < *n; ++i) out[i] = h->history[i];
+    return OPMGPU_OK;
+}
+
+int opmgpu_set_profiling(opmgpu_handle h, int on)
+{
+    if (!h) return OPMGPU_BAD_ARGUMENT;
+    h->profile = on != 0;
+    for (int k = 0; k < 4; ++k) { h->prof_ms[k] = 0; h->prof_cnt[k] = 0; }
+    return OPMGPU_OK;
+}
+
+int opmgpu_get_profile(opmgpu_handle h, double ms[4], long long count[4])
+{
+    if (!h) return OPMGPU_BAD_ARGUMENT;
+    for (int k = 0; k < 4; ++k) { ms[k] = h->prof_ms[k]; count[k] = h->prof_cnt[k]; }
     return OPMGPU_OK;
 }
 

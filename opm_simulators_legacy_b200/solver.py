@@ -147,6 +147,17 @@ class GpuLinearSolver:
         self._check(self.lib.opmgpu_num_levels(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def set_profiling(self, on: bool = True):
+        self._check(self.lib.opmgpu_set_profiling(self.h, int(on)))
+
+    def profile(self):
+        """-> {class: (ms, launches)} for ilu_apply, spmv, vector, factor since set_profiling."""
+        ms = (C.c_double * 4)()
+        cnt = (C.c_longlong * 4)()
+        self._check(self.lib.opmgpu_get_profile(self.h, ms, cnt))
+        names = ("ilu_apply", "spmv", "vector", "factor")
+        return {n: (ms[i], int(cnt[i])) for i, n in enumerate(names)}
+
     def launch_count(self) -> int:
         return int(self.lib.opmgpu_launch_count(self.h))
 

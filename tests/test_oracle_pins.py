@@ -1,0 +1,158 @@
+"""Pins for the CPU oracle itself (no GPU).  The reference's tests assert no result at this
+boundary (tests/test_linearsolver.cpp:109-121 computes `exact` and drops it), so the oracle is
+pinned by (1) the reference's own fixtures turned into known-answer tests, (2) scipy as an
+independent implementation, (3) defining properties of ILU0, (4) the committed golden vectors."""
+import ctypes
+import glob
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spl
+
+from opm_simulators_legacy_b200.jacobian import synth_blackoil_jacobian, random_bcrs
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+def block_replicate(rowptr, colidx, data):
+    """Scalar CSR -> 3x3 BCRS with each scalar a times a fixed well-conditioned 3x3 matrix."""
+    B = np.array([[2.0, 0.5, 0.0], [0.25, 1.5, 0.5], [0.0, 0.75, 3.0]])
+    vals = np.asarray(data)[:, None] * B.reshape(1, 9)
+    return np.asarray(rowptr, dtype=np.int32), np.asarray(colidx, dtype=np.int32), vals
+
+
+def laplacian_5pt(N):
+    """createLaplacian, tests/test_linearsolver.cpp:50-87."""
+    rowptr, col, dat = [0], [], []
+    for row in range(N * N):
+        x, y = row % N, row // N
+        if y > 0: col.append(row - N); dat.append(-1.0)
+        if x > 0: col.append(row - 1); dat.append(-1.0)
+        col.append(row); dat.append(4.0)
+        if x < N - 1: col.append(row + 1); dat.append(-1.0)
+        if y < N - 1: col.append(row + N); dat.append(-1.0)
+        rowptr.append(len(col))
+    return rowptr, col, dat
+
+
+def c_rand_vector(n):
+    """x = (rand() % 100) / 10 with the C library's default seed, tests/test_linearsolver.cpp:92-94."""
+    libc = ctypes.CDLL("libc.so.6")
+    libc.srand(1)
+    return np.array([(libc.rand() % 100) / 10.0 for _ in range(n)])
+
+
+def test_reference_fixture_laplacian_known_answer(oracle):
+    rp, ci, v = block_replicate(*laplacian_5pt(4))
+    x_exact = c_rand_vector(16 * 3).reshape(16, 3)
+    b = oracle.spmv(rp, ci, v, x_exact)
+    x, res = oracle.solve_bcrs(rp, ci, v, b, reduction=1e-12, maxiter=200)
+    assert res["converged"] == 1
+    assert np.abs(x - x_exact).max() <= 1e-9 * np.abs(x_exact).max()
+
+
+def test_reference_fixture_1d_laplacian_known_answer(oracle):
+    """Owner rows [-1 2 -1], N = 100 (tests/DuneIstlTestHelpers.hpp:132-148).  Block tridiagonal:
+    ILU0 is the exact LU, so with w = 1 BiCGStab must converge in one iteration."""
+    N = 100
+    rowptr, col, dat = [0], [], []
+    for r in range(N):
+        if r > 0: col.append(r - 1); dat.append(-1.0)
+        col.append(r); dat.append(2.0)
+        if r < N - 1: col.append(r + 1); dat.append(-1.0)
+        rowptr.append(len(col))
+    rp, ci, v = block_replicate(rowptr, col, dat)
+    x_exact = np.linspace(1.0, 2.0, 3 * N).reshape(N, 3)
+    b = oracle.spmv(rp, ci, v, x_exact)
+    x, res = oracle.solve_bcrs(rp, ci, v, b, reduction=1e-10, relax=1.0)
+    assert res["iterations"] == 1 and res["converged"] == 1
+    assert np.abs(x - x_exact).max() <= 1e-10 * np.abs(x_exact).max()
+    # with the reference's default relaxation 0.9 the preconditioned operator is 0.9 I: still one iteration
+    x, res = oracle.solve_bcrs(rp, ci, v, b, reduction=1e-10, relax=0.9)
+    assert res["iterations"] == 1
+
+
+@pytest.mark.parametrize("dims,perm", [((10, 10, 3), "homogeneous"), ((14, 11, 6), "lognormal")])
+def test_against_scipy(oracle, dims, perm):
+    s = synth_blackoil_jacobian(*dims, perm=perm)
+    rp, ci, v, b = s.rowptr.numpy(), s.colidx.numpy(), s.vals.numpy(), s.rhs.numpy()
+    A = sp.bsr_matrix((v.reshape(-1, 3, 3), ci, rp), shape=(3 * s.N, 3 * s.N))
+    x = s.xstar.numpy()
+    y = oracle.spmv(rp, ci, v, x)
+    assert np.abs(y.ravel() - A @ x.ravel()).max() <= 1e-12 * np.abs(A).dot(np.abs(x.ravel())).max()
+    xs, res = oracle.solve_bcrs(rp, ci, v, b, reduction=1e-12, maxiter=500)
+    xd = spl.spsolve(A.tocsc(), b.ravel()).reshape(-1, 3)
+    assert res["converged"] == 1
+    assert (np.abs(xs - xd).max(0) <= 1e-6 * np.abs(xd).max(0)).all()
+    # the csc-blocks entry point restates ...Interleaved.cpp:234-283 and must give the same system
+    dx, r2 = oracle.solve_from_csc_blocks(s.N, s.csc_blocks(), s.matbalscale, s.rhs_eqmajor_unscaled.numpy())
+    x1, r1 = oracle.solve_bcrs(rp, ci, v, b)
+    assert r2["iterations"] == r1["iterations"] and np.array_equal(dx.reshape(3, -1).T, x1)
+    rp2, ci2, v2 = oracle.interleave(s.N, s.csc_blocks(), s.matbalscale)
+    assert np.array_equal(rp2, rp) and np.array_equal(ci2, ci) and np.array_equal(v2, v)
+
+
+def test_ilu0_defining_property(oracle):
+    """(L U)_ij = A_ij on the sparsity pattern."""
+    rp, ci, v = random_bcrs(150, extra_per_row=3, seed=5, dense_group=6)
+    lu, bad = oracle.ilu0_factor(rp, ci, v)
+    assert bad == -1
+    N = len(rp) - 1
+    L = np.zeros((3 * N, 3 * N)); U = np.zeros((3 * N, 3 * N)); A = np.zeros((3 * N, 3 * N))
+    for i in range(N):
+        for k in range(rp[i], rp[i + 1]):
+            j = ci[k]
+            blk = lu[k].reshape(3, 3)
+            A[3 * i:3 * i + 3, 3 * j:3 * j + 3] = v[k].reshape(3, 3)
+            if j < i: L[3 * i:3 * i + 3, 3 * j:3 * j + 3] = blk
+            elif j == i: U[3 * i:3 * i + 3, 3 * j:3 * j + 3] = np.linalg.inv(blk)
+            else: U[3 * i:3 * i + 3, 3 * j:3 * j + 3] = blk
+    L += np.eye(3 * N)
+    P = L @ U
+    mask = A != 0
+    assert np.abs(P - A)[mask].max() <= 1e-10 * np.abs(A).max()
+    # and the apply is w * U^-1 L^-1 d
+    d = np.random.default_rng(1).standard_normal((N, 3))
+    ref = 0.9 * np.linalg.solve(U, np.linalg.solve(L, d.ravel()))
+    got = oracle.ilu0_apply(rp, ci, lu, 0.9, d).ravel()
+    assert np.abs(got - ref).max() <= 1e-10 * np.abs(ref).max()
+
+
+def test_singular_pivot_reported(oracle):
+    s = synth_blackoil_jacobian(5, 4, 3)
+    rp, ci, v = s.rowptr.numpy(), s.colidx.numpy(), s.vals.numpy().copy()
+    row = 7
+    for k in range(rp[row], rp[row + 1]):
+        if ci[k] <= row:
+            v[k] = 0.0
+    _, bad = oracle.ilu0_factor(rp, ci, v)
+    assert bad == row
+    _, res = oracle.solve_bcrs(rp, ci, v, s.rhs.numpy())
+    assert res["status"] == 2 and res["bad_row"] == row
+
+
+def test_dune_iteration_counting(oracle):
+    """res.iterations = ceil(it): a stop after the first half step of iteration k reports k."""
+    s = synth_blackoil_jacobian(9, 8, 5, perm="lognormal")
+    rp, ci, v, b = s.rowptr.numpy(), s.colidx.numpy(), s.vals.numpy(), s.rhs.numpy()
+    x, res = oracle.solve_bcrs(rp, ci, v, b)
+    assert res["iterations"] == (res["half_steps"] + 1) // 2
+    _, r0 = oracle.solve_bcrs(rp, ci, v, np.zeros_like(b))
+    assert r0["iterations"] == 0 and r0["converged"] == 1
+    _, rmax = oracle.solve_bcrs(rp, ci, v, b, reduction=1e-30, maxiter=3)
+    assert rmax["iterations"] == 3 and rmax["converged"] == 0 and rmax["status"] == 1
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_oracle_reproduces_golden(oracle, path):
+    g = np.load(path)
+    rp, ci, v, b = g["rowptr"], g["colidx"], g["vals"], g["rhs"]
+    assert np.array_equal(oracle.spmv(rp, ci, v, g["x_probe"]), g["spmv"])
+    lu, bad = oracle.ilu0_factor(rp, ci, v)
+    assert bad == -1 and np.array_equal(lu, g["lu"])
+    assert np.array_equal(oracle.ilu0_apply(rp, ci, lu, 0.9, b), g["apply_w09"])
+    assert np.array_equal(oracle.ilu0_apply(rp, ci, lu, 1.0, b), g["apply_w1"])
+    x, res = oracle.solve_bcrs(rp, ci, v, b)
+    assert res["iterations"] == int(g["iterations"]) and np.array_equal(x, g["x"])
