@@ -88,8 +88,14 @@ int  opmgpu_destroy(opmgpu_handle h);
 const char* opmgpu_last_error(opmgpu_handle h);          /* h may be NULL: creation errors */
 
 /* Multi-GPU (one process per GPU): rank r of `world` owns the contiguous block rows
- * [row_begin, row_end) of the global system.  nccl_unique_id is the 128-byte ncclUniqueId
- * rank 0 obtained from opmgpu_nccl_unique_id and distributed by any means. */
+ * [row_offsets[r], row_offsets[r+1]) of the global system.  The operator is the global one
+ * (x is exchanged over NVLink with ncclSend/ncclRecv before every SpMV, dot products are
+ * ncclAllReduce'd); the preconditioner is block-Jacobi ILU0 (couplings to other ranks dropped),
+ * the counterpart of the reference's per-subdomain ILU0 under MPI (ISTLSolver.hpp:218-235,
+ * 286-298).  nccl_unique_id is the 128-byte ncclUniqueId rank 0 obtained from
+ * opmgpu_nccl_unique_id and distributed by any means.  After set_pattern_bcrs_distributed the
+ * solve / set_values / spmv entry points take the rank's LOCAL rows (values in the order of the
+ * local pattern passed here) and the solves are collective. */
 int  opmgpu_nccl_unique_id(void* id128);
 int  opmgpu_create_distributed(int device, int rank, int world, const void* nccl_unique_id,
                                opmgpu_handle* out);
@@ -102,12 +108,12 @@ int  opmgpu_set_stream(opmgpu_handle h, void* cuda_stream);
 /* Replaces the pattern half of formInterleavedSystem (...Interleaved.cpp:118-155) when the
  * caller already holds BCRS: rowptr[N+1], colidx[nnzb] ascending per row, diagonal present.
  * Runs the dependency analysis of the ILU0 sweeps; cached until the next call.
- * Distributed handles pass their LOCAL rows with GLOBAL column ids plus the global row
- * range they own. */
+ * Distributed handles pass their LOCAL rows with GLOBAL column ids plus every rank's row
+ * range. */
 int  opmgpu_set_pattern_bcrs(opmgpu_handle h, int N, int nnzb, const int* rowptr, const int* colidx);
 int  opmgpu_set_pattern_bcrs_distributed(opmgpu_handle h, int N_local, int nnzb_local,
-                                         const int* rowptr, const int* colidx_global,
-                                         long long row_begin, long long N_global);
+                                         const int* rowptr, const long long* colidx_global,
+                                         const long long* row_offsets /* [world+1] */);
 
 /* Replaces ISTLSolver::solve(A,x,b) (ISTLSolver.hpp:283-306): vals[nnzb*9] row-major 3x3
  * blocks [eq][var], rhs/x cell-major [cell][3], x0 = 0 (...Interleaved.cpp:272-273). */

@@ -77,7 +77,7 @@ def load():
         "opmgpu_create_distributed": (C.c_int, [C.c_int, C.c_int, C.c_int, vp, C.POINTER(H)]),
         "opmgpu_set_stream": (C.c_int, [H, vp]),
         "opmgpu_set_pattern_bcrs": (C.c_int, [H, C.c_int, C.c_int, ip, ip]),
-        "opmgpu_set_pattern_bcrs_distributed": (C.c_int, [H, C.c_int, C.c_int, ip, ip, C.c_longlong, C.c_longlong]),
+        "opmgpu_set_pattern_bcrs_distributed": (C.c_int, [H, C.c_int, C.c_int, ip, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
         "opmgpu_solve_bcrs3": (C.c_int, [H, dp, dp, dp, PP, RP]),
         "opmgpu_solve_bcrs3_dev": (C.c_int, [H, vp, vp, vp, PP, RP]),
         "opmgpu_solve_from_csc_blocks": (C.c_int, [H, C.c_int, C.POINTER(Csc), dp, dp, dp, PP, RP]),

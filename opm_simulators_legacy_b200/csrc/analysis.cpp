@@ -136,6 +136,29 @@ void build_program(int N, const int* rowptr, const int* colidx, const std::vecto
     }
     prog.publish.resize(N);
     for (int q = 0; q < N; ++q) prog.publish[q] = pub_row[order[q]];
+    if (lower) {
+        // update lists of Dune::bilu0_decomposition: merge row j (right of its diagonal) with row i
+        prog.pair_ptr.assign(nblk + 1, 0);
+        prog.pair_jk.clear(); prog.pair_ik.clear();
+        for (size_t b = 0; b < nblk; ++b) {
+            const int ij = prog.psrc[b], j = colidx[ij];
+            int i = 0;
+            {   // row of slot ij
+                int lo = 0, hi = N;
+                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (rowptr[mid] <= ij) lo = mid; else hi = mid; }
+                i = lo;
+            }
+            int jk = rowptr[j], ik = ij + 1;
+            while (jk < rowptr[j + 1] && colidx[jk] <= j) ++jk;
+            const int jend = rowptr[j + 1], iend = rowptr[i + 1];
+            while (ik < iend && jk < jend) {
+                if (colidx[ik] == colidx[jk]) { prog.pair_jk.push_back(jk); prog.pair_ik.push_back(ik); ++ik; ++jk; }
+                else if (colidx[ik] < colidx[jk]) ++ik;
+                else ++jk;
+            }
+            prog.pair_ptr[b + 1] = (int)prog.pair_jk.size();
+        }
+    }
 }
 
 
@@ -440,9 +463,9 @@ void analyse_pattern(int N, const int* rowptr, const int* colidx, int P, Pattern
         build_pipe_program(N, rowptr, colidx, out.diag, lvlL, nL, owner, P, true, &upos, out.pipeL);
     }
     out.nlevL = nL; out.nlevU = nU;
+    build_program(N, rowptr, colidx, lvlL, nL, owner, P, true, out.lower);       // also drives the factorisation
     if (force_simple || !out.pipeL.valid || !out.pipeU.valid) {
         out.pipeL = PipeProgram(); out.pipeU = PipeProgram();
-        build_program(N, rowptr, colidx, lvlL, nL, owner, P, true, out.lower);
         build_program(N, rowptr, colidx, lvlU, nU, owner, P, false, out.upper);
     }
 }
@@ -555,6 +578,47 @@ bool interpret_pipe_program(const PipeProgram& pg, bool upper, const double* rhs
     return done;
 }
 
+void partition_local_rows(int N_local, const int* rowptr, const long long* colidx_global,
+                          const long long* row_offsets, int world, int rank, LocalPartition& out)
+{
+    out = LocalPartition();
+    out.N_local = N_local;
+    const long long lo = row_offsets[rank], hi = row_offsets[rank + 1];
+    const int nnz = rowptr[N_local];
+    std::vector<long long> ghosts;
+    for (int k = 0; k < nnz; ++k)
+        if (colidx_global[k] < lo || colidx_global[k] >= hi) ghosts.push_back(colidx_global[k]);
+    std::sort(ghosts.begin(), ghosts.end());
+    ghosts.erase(std::unique(ghosts.begin(), ghosts.end()), ghosts.end());
+    out.ghost_global = ghosts;
+    out.n_ghost = (int)ghosts.size();
+    out.recv_cnt.assign(world, 0);
+    out.recv_off.assign(world, 0);
+    {
+        int p = 0;
+        for (size_t g = 0; g < ghosts.size(); ++g) {
+            while (ghosts[g] >= row_offsets[p + 1]) ++p;
+            out.recv_cnt[p]++;
+        }
+        for (int q = 1; q < world; ++q) out.recv_off[q] = out.recv_off[q - 1] + out.recv_cnt[q - 1];
+    }
+    out.colidx_full.resize(nnz);
+    out.rowptr_diag.assign(N_local + 1, 0);
+    for (int i = 0; i < N_local; ++i) {
+        for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+            const long long c = colidx_global[k];
+            if (c >= lo && c < hi) {
+                out.colidx_full[k] = (int)(c - lo);
+                out.colidx_diag.push_back((int)(c - lo));
+                out.lu_src.push_back(k);
+            } else {
+                out.colidx_full[k] = N_local + (int)(std::lower_bound(ghosts.begin(), ghosts.end(), c) - ghosts.begin());
+            }
+        }
+        out.rowptr_diag[i + 1] = (int)out.colidx_diag.size();
+    }
+}
+
 void union_pattern_from_csc(int N, const CscView* blocks, int nblocks,
                             std::vector<int>& rowptr, std::vector<int>& colidx)
 {
@@ -623,4 +687,26 @@ extern "C" int opmgpu_debug_host_program_apply(int N, const int* rowptr, const i
         info[7] = (int)(an.pipeL.cta_step_ptr[P]);
     }
     return 0;
+}
+
+// Debug entry (CPU tests of the row-partition logic, no GPU / NCCL needed): local pattern,
+// ghost list and diagonal block of one rank.  Arrays are caller-allocated with nnzb_local
+// (colidx_full, colidx_diag, lu_src) or N_local+1 / world entries.  Returns n_ghost, writes
+// nnzb_diag to *nnzb_diag_out; ghost_global must hold nnzb_local entries.
+extern "C" int opmgpu_debug_partition(int N_local, const int* rowptr, const long long* colidx_global,
+                                      const long long* row_offsets, int world, int rank,
+                                      int* colidx_full, long long* ghost_global, int* recv_cnt,
+                                      int* rowptr_diag, int* colidx_diag, int* lu_src, int* nnzb_diag_out)
+{
+    using namespace opmgpu;
+    LocalPartition lp;
+    partition_local_rows(N_local, rowptr, colidx_global, row_offsets, world, rank, lp);
+    std::copy(lp.colidx_full.begin(), lp.colidx_full.end(), colidx_full);
+    std::copy(lp.ghost_global.begin(), lp.ghost_global.end(), ghost_global);
+    std::copy(lp.recv_cnt.begin(), lp.recv_cnt.end(), recv_cnt);
+    std::copy(lp.rowptr_diag.begin(), lp.rowptr_diag.end(), rowptr_diag);
+    std::copy(lp.colidx_diag.begin(), lp.colidx_diag.end(), colidx_diag);
+    std::copy(lp.lu_src.begin(), lp.lu_src.end(), lu_src);
+    *nnzb_diag_out = (int)lp.colidx_diag.size();
+    return lp.n_ghost;
 }

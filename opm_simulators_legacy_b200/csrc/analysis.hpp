@@ -31,6 +31,9 @@ struct SweepProgram {
     std::vector<int> pcol;                   // [nblk] dependency row | kExtBit
     std::vector<int> psrc;                   // [nblk] BCRS slot the block comes from
     std::vector<unsigned char> publish;      // [N]   program row has a consumer in another CTA
+    // factorisation only (lower program): for every block (i,j) the pairs (slot of A_jk, slot of
+    // A_ik), k > j present in both rows, that A_ik -= L_ij * A_jk touches
+    std::vector<int> pair_ptr, pair_jk, pair_ik;
 };
 
 // ---- pipelined sweep program (the fast path) ---------------------------------------------------
@@ -109,6 +112,20 @@ void analyse_pattern(int N, const int* rowptr, const int* colidx, int P, Pattern
 // Sequential interpreter of a pipelined program (debug / CPU tests of the host analysis).
 bool interpret_pipe_program(const PipeProgram& pg, bool upper, const double* rhs_perm, double* work,
                             double* hand_off, double* out, double w, int scale);
+
+// Row-partitioned system: split a rank's local rows (global column ids) into the local
+// operator pattern (own columns first, then ghost columns in ascending global order, grouped
+// by owner) and the diagonal block the rank's ILU0 is built on (block-Jacobi).
+struct LocalPartition {
+    int N_local = 0, n_ghost = 0;
+    std::vector<int> colidx_full;            // [nnzb_local] local ids; ghosts are N_local + g
+    std::vector<long long> ghost_global;     // [n_ghost] ascending
+    std::vector<int> recv_cnt, recv_off;     // [world] ghosts owned by each rank (contiguous)
+    std::vector<int> rowptr_diag, colidx_diag;   // diagonal block (ascending columns)
+    std::vector<int> lu_src;                 // [nnzb_diag] slot in the full local pattern
+};
+void partition_local_rows(int N_local, const int* rowptr, const long long* colidx_global,
+                          const long long* row_offsets, int world, int rank, LocalPartition& out);
 
 // Union pattern of the pressure-derivative CSC blocks -> row-major ascending
 // (formInterleavedSystem, ...Interleaved.cpp:118-155).

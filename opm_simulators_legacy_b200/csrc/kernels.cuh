@@ -288,6 +288,96 @@ ilu0_factor_level_kernel(const int* __restrict__ lvl_rows, int begin, int end,
     if (!(det != 0.0) || isinf(det) || isnan(det)) atomicMin(bad_row, i);
 }
 
+// ------------------------------------------------------------------------------------------
+// K3 (fast path)  block ILU0 factorisation as a pipelined wavefront of persistent CTAs: the
+// rows of a CTA's tile are processed level by level (one thread per row, __syncthreads
+// between levels); a row of another tile is awaited through its per-row flag.  The update
+// lists (which A_ik a given L_ij touches) are precomputed on the host, so every address is
+// known up front.  Arithmetic order is Dune::bilu0_decomposition's (bit parity).
+// ------------------------------------------------------------------------------------------
+struct FactorDev {
+    const int* cta_step_ptr;
+    const int* step_row_ptr;
+    const int* prow;
+    const int* pblk_ptr;
+    const int* pcol;          // dependency row | kExtBitDev
+    const int* psrc;          // BCRS slot of A_ij
+    const int* pair_ptr;
+    const int* pair_jk;
+    const int* pair_ik;
+    const unsigned char* publish;
+    const int* diag;
+};
+
+__device__ __forceinline__ int ld_acquire_gpu_f(const int* p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(128)
+ilu0_factor_tile_kernel(FactorDev pg, double* lu, int* flags, int epoch, int* bad_row, int* err)
+{
+    const int s_begin = pg.cta_step_ptr[blockIdx.x], s_end = pg.cta_step_ptr[blockIdx.x + 1];
+    for (int s = s_begin; s < s_end; ++s) {
+        const int q0 = pg.step_row_ptr[s], q1 = pg.step_row_ptr[s + 1];
+        for (int q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
+            const int i = pg.prow[q];
+            const int idiag = pg.diag[i];
+            double D[9];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) D[t] = lu[(size_t)idiag * 9 + t];
+            const int b0 = pg.pblk_ptr[q], b1 = pg.pblk_ptr[q + 1];
+            for (int b = b0; b < b1; ++b) {
+                const int c = pg.pcol[b];
+                const int j = c & ~kExtBitDev;
+                const int ij = pg.psrc[b], jd = pg.diag[j];
+                const bool ext = (c & kExtBitDev) != 0;
+                if (ext) {
+                    unsigned spins = 0;
+                    while (ld_acquire_gpu_f(flags + j) != epoch) {
+                        if (++spins > (1u << 22)) { atomicExch(err, 5); break; }
+                        if ((spins & 1023u) == 0 && *(volatile int*)err) break;
+                    }
+                }
+                double Aij[9], Dj[9], L[9];
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                    Aij[t] = lu[(size_t)ij * 9 + t];
+                    Dj[t] = ext ? __ldcg(lu + (size_t)jd * 9 + t) : lu[(size_t)jd * 9 + t];
+                }
+                mat3_mul(Aij, Dj, L);                                 // L_ij = A_ij * inv(A_jj)
+#pragma unroll
+                for (int t = 0; t < 9; ++t) lu[(size_t)ij * 9 + t] = L[t];
+                for (int pp = pg.pair_ptr[b]; pp < pg.pair_ptr[b + 1]; ++pp) {
+                    const int jk = pg.pair_jk[pp], ik = pg.pair_ik[pp];
+                    double Ajk[9], B[9];
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) Ajk[t] = ext ? __ldcg(lu + (size_t)jk * 9 + t) : lu[(size_t)jk * 9 + t];
+                    mat3_mul(L, Ajk, B);                              // B = L_ij * A_jk
+                    if (ik == idiag) {
+#pragma unroll
+                        for (int t = 0; t < 9; ++t) D[t] -= B[t];
+                    } else {
+#pragma unroll
+                        for (int t = 0; t < 9; ++t) lu[(size_t)ik * 9 + t] -= B[t];
+                    }
+                }
+            }
+            const double det = mat3_invert(D);
+#pragma unroll
+            for (int t = 0; t < 9; ++t) lu[(size_t)idiag * 9 + t] = D[t];
+            if (!(det != 0.0) || isinf(det) || isnan(det)) atomicMin(bad_row, i);
+            if (pg.publish[q]) {
+                __threadfence();
+                asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flags + i), "r"(epoch) : "memory");
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // factors (BCRS order) -> the sweep programs' streaming layout
 __global__ void __launch_bounds__(256)
 repack_blocks_kernel(size_t nblk, const int* __restrict__ psrc, const double* __restrict__ lu,

@@ -9,6 +9,9 @@
 #include "kernels.cuh"
 #include "sweep_pipe.cuh"
 
+#include <dlfcn.h>
+#include <nccl.h>      // types only: the library is resolved at run time with dlopen
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -22,6 +25,45 @@ using namespace opmgpu;
 namespace {
 
 std::string g_create_error;
+
+// NCCL is only needed by distributed handles and is resolved lazily (inside a PyTorch
+// process this picks up the libnccl.so.2 torch already loaded).
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool load(std::string& err)
+    {
+        if (lib) return true;
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+            lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (lib) break;
+        }
+        if (!lib) { err = std::string("cannot load NCCL: ") + dlerror(); return false; }
+        bool ok = true;
+        auto sym = [&](const char* n) { void* p = dlsym(lib, n); if (!p) ok = false; return p; };
+        GetUniqueId = (decltype(GetUniqueId))sym("ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))sym("ncclCommInitRank");
+        CommDestroy = (decltype(CommDestroy))sym("ncclCommDestroy");
+        AllReduce = (decltype(AllReduce))sym("ncclAllReduce");
+        AllGather = (decltype(AllGather))sym("ncclAllGather");
+        Send = (decltype(Send))sym("ncclSend");
+        Recv = (decltype(Recv))sym("ncclRecv");
+        GroupStart = (decltype(GroupStart))sym("ncclGroupStart");
+        GroupEnd = (decltype(GroupEnd))sym("ncclGroupEnd");
+        GetErrorString = (decltype(GetErrorString))sym("ncclGetErrorString");
+        if (!ok) { err = "NCCL library lacks a required symbol"; lib = nullptr; }
+        return ok;
+    }
+} g_nccl;
 
 template <class T>
 struct DevArr {
@@ -42,6 +84,7 @@ struct DevArr {
 struct ProgramDevMem {
     DevArr<int> cta_step_ptr, step_row_ptr, prow, pblk_ptr, pcol, psrc;
     DevArr<unsigned char> publish;
+    DevArr<int> pair_ptr, pair_jk, pair_ik;
     DevArr<double> pval, pdinv;
     size_t nblk = 0;
     int P = 0;
@@ -49,6 +92,7 @@ struct ProgramDevMem {
     {
         cta_step_ptr.release(); step_row_ptr.release(); prow.release(); pblk_ptr.release();
         pcol.release(); psrc.release(); publish.release(); pval.release(); pdinv.release();
+        pair_ptr.release(); pair_jk.release(); pair_ik.release();
     }
 };
 
@@ -87,7 +131,7 @@ struct opmgpu_solver {
     DevArr<int> d_rowptr, d_colidx, d_diag, d_lvl_rows;
     ProgramDevMem progL, progU;
     PipeDevMem pipeL, pipeU;
-    bool use_pipe = false, force_simple = false;
+    bool use_pipe = false, force_simple = false, factor_by_levels = false;
     int trace_cta = -1;
     DevArr<long long> d_trace;
     int max_smem_optin = 0;
@@ -105,6 +149,20 @@ struct opmgpu_solver {
     double* h_S = nullptr;       // pinned
     int* h_flags2 = nullptr;     // pinned: [0] sweep watchdog, [1] bad row / bad pattern
     cudaEvent_t ev[8] = {};
+
+    // distributed (one process per GPU): row partition, halo plan, NCCL communicator
+    int rank = 0, world = 1;
+    ncclComm_t comm = nullptr;
+    int n_ghost = 0, nnzb_full = 0;
+    DevArr<int> d_rowptr_full, d_colidx_full, d_lu_src, d_send_rows;
+    DevArr<double> d_sendbuf;
+    std::vector<int> send_cnt, send_off, recv_cnt, recv_off;
+    int n_send = 0;
+    int nccl_fail(ncclResult_t r, const char* what)
+    {
+        err = std::string("NCCL error at ") + what + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+        return OPMGPU_NCCL_ERROR;
+    }
 
     // CSC front end cache
     std::vector<std::vector<int>> csc_colptr, csc_rowidx;
@@ -160,6 +218,12 @@ struct opmgpu_solver {
     ReduceWs ws() { return ReduceWs{d_partials.p, d_ticket.p}; }
 };
 
+#define NK(call)                                                          \
+    do {                                                                  \
+        ncclResult_t r__ = (call);                                        \
+        if (r__ != ncclSuccess) return h->nccl_fail(r__, #call);          \
+    } while (0)
+
 #define CK(call)                                                          \
     do {                                                                  \
         cudaError_t e__ = (call);                                         \
@@ -178,9 +242,14 @@ int upload(opmgpu_handle h, DevArr<T>& d, const std::vector<T>& v)
     return 0;
 }
 
-int upload_program(opmgpu_handle h, const SweepProgram& p, ProgramDevMem& d, bool upper)
+int upload_program(opmgpu_handle h, const SweepProgram& p, ProgramDevMem& d, bool upper, bool with_values = true)
 {
     int rc;
+    if (!upper) {
+        if ((rc = upload(h, d.pair_ptr, p.pair_ptr))) return rc;
+        if ((rc = upload(h, d.pair_jk, p.pair_jk))) return rc;
+        if ((rc = upload(h, d.pair_ik, p.pair_ik))) return rc;
+    }
     if ((rc = upload(h, d.cta_step_ptr, p.cta_step_ptr))) return rc;
     if ((rc = upload(h, d.step_row_ptr, p.step_row_ptr))) return rc;
     if ((rc = upload(h, d.prow, p.prow))) return rc;
@@ -190,8 +259,10 @@ int upload_program(opmgpu_handle h, const SweepProgram& p, ProgramDevMem& d, boo
     if ((rc = upload(h, d.publish, p.publish))) return rc;
     d.nblk = p.pcol.size();
     d.P = p.P;
-    CK(d.pval.ensure(d.nblk * 9));
-    if (upper) CK(d.pdinv.ensure((size_t)h->N * 9));
+    if (with_values) {
+        CK(d.pval.ensure(d.nblk * 9));
+        if (upper) CK(d.pdinv.ensure((size_t)h->N * 9));
+    }
     return 0;
 }
 
@@ -250,8 +321,8 @@ int ensure_vectors(opmgpu_handle h)
 {
     const size_t n = (size_t)h->N * 3;
     CK(h->d_x.ensure(n)); CK(h->d_r.ensure(n)); CK(h->d_rt.ensure(n)); CK(h->d_p.ensure(n));
-    CK(h->d_v.ensure(n)); CK(h->d_t.ensure(n)); CK(h->d_y.ensure(n)); CK(h->d_yL.ensure(n));
-    CK(h->d_vU.ensure(n)); CK(h->d_tmp.ensure(n)); CK(h->d_tmp2.ensure(n));
+    CK(h->d_v.ensure(n)); CK(h->d_t.ensure(n)); CK(h->d_y.ensure(n + (size_t)h->n_ghost * 3)); CK(h->d_yL.ensure(n));
+    CK(h->d_vU.ensure(n)); CK(h->d_tmp.ensure(n + (size_t)h->n_ghost * 3)); CK(h->d_tmp2.ensure(n));
     return 0;
 }
 
@@ -286,12 +357,13 @@ int set_pattern(opmgpu_handle h, int N, int nnzb, const int* rowptr, const int* 
         if (h->pipeL.nstages < 3 || h->pipeU.nstages < 3) h->use_pipe = false;
     }
     if (!h->use_pipe) {
-        if (h->an.lower.prow.empty()) analyse_pattern(N, rowptr, colidx, h->sweep_ctas, h->an, true);
+        if (h->an.upper.prow.empty()) analyse_pattern(N, rowptr, colidx, h->sweep_ctas, h->an, true);
         if ((rc = upload_program(h, h->an.lower, h->progL, false))) return rc;
         if ((rc = upload_program(h, h->an.upper, h->progU, true))) return rc;
         h->pipeL.release(); h->pipeU.release();
     } else {
-        h->progL.release(); h->progU.release();
+        if ((rc = upload_program(h, h->an.lower, h->progL, false, false))) return rc;   // factorisation program only
+        h->progU.release();
     }
     CK(h->d_lu.ensure((size_t)nnzb * 9));
     if ((rc = ensure_vectors(h))) return rc;
@@ -307,19 +379,63 @@ int set_pattern(opmgpu_handle h, int N, int nnzb, const int* rowptr, const int* 
     return OPMGPU_OK;
 }
 
+// gather kernels of the distributed path
+__global__ void __launch_bounds__(256)
+pack_rows_kernel(int n, const int* __restrict__ rows, const double* __restrict__ x, double* __restrict__ buf)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n * 3) return;
+    const int k = e / 3;
+    buf[e] = x[(size_t)rows[k] * 3 + (e - k * 3)];
+}
+__global__ void __launch_bounds__(256)
+gather_blocks_kernel(size_t nblk, const int* __restrict__ src, const double* __restrict__ vals, double* __restrict__ lu)
+{
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nblk * 9) return;
+    const size_t b = e / 9;
+    lu[e] = vals[(size_t)src[b] * 9 + (e - b * 9)];
+}
+
+// x[N_local .. N_local + n_ghost) <- the owners' rows (ncclSend/ncclRecv over NVLink)
+int halo_exchange(opmgpu_handle h, double* x)
+{
+    if (h->world == 1) return 0;
+    if (h->n_send) {
+        pack_rows_kernel<<<(h->n_send * 3 + 255) / 256, 256, 0, h->stream>>>(h->n_send, h->d_send_rows.p, x, h->d_sendbuf.p);
+        h->launches++;
+    }
+    NK(g_nccl.GroupStart());
+    for (int p = 0; p < h->world; ++p) {
+        if (h->send_cnt[p]) NK(g_nccl.Send(h->d_sendbuf.p + (size_t)h->send_off[p] * 3, (size_t)h->send_cnt[p] * 3, ncclDouble, p, h->comm, h->stream));
+        if (h->recv_cnt[p]) NK(g_nccl.Recv(x + ((size_t)h->N + h->recv_off[p]) * 3, (size_t)h->recv_cnt[p] * 3, ncclDouble, p, h->comm, h->stream));
+    }
+    NK(g_nccl.GroupEnd());
+    return 0;
+}
+
+int allreduce_slots(opmgpu_handle h, int slot, int count)
+{
+    if (h->world == 1) return 0;
+    NK(g_nccl.AllReduce(h->d_S.p + slot, h->d_S.p + slot, (size_t)count, ncclDouble, ncclSum, h->comm, h->stream));
+    return 0;
+}
+
 int launch_spmv(opmgpu_handle h, int mode, const double* x, double* y, const double* w1)
 {
+    const int* rowptr = h->world > 1 ? h->d_rowptr_full.p : h->d_rowptr.p;
+    const int* colidx = h->world > 1 ? h->d_colidx_full.p : h->d_colidx.p;
     const long long threads = 3LL * h->N;
     const unsigned grid = (unsigned)((threads + 255) / 256);
     if (mode != 0 && grid > kMaxRedBlocks) {
         // fused reduction epilogue has a bounded partial array: fall back to SpMV + dot kernels
-        spmv3_kernel<0><<<grid, 256, 0, h->stream>>>(h->N, h->d_rowptr.p, h->d_colidx.p, h->d_vals, x, y, nullptr, h->d_S.p, h->ws());
+        spmv3_kernel<0><<<grid, 256, 0, h->stream>>>(h->N, rowptr, colidx, h->d_vals, x, y, nullptr, h->d_S.p, h->ws());
         h->launches++;
         return -100;
     }
-    if (mode == 0) spmv3_kernel<0><<<grid, 256, 0, h->stream>>>(h->N, h->d_rowptr.p, h->d_colidx.p, h->d_vals, x, y, w1, h->d_S.p, h->ws());
-    else if (mode == 1) spmv3_kernel<1><<<grid, 256, 0, h->stream>>>(h->N, h->d_rowptr.p, h->d_colidx.p, h->d_vals, x, y, w1, h->d_S.p, h->ws());
-    else spmv3_kernel<2><<<grid, 256, 0, h->stream>>>(h->N, h->d_rowptr.p, h->d_colidx.p, h->d_vals, x, y, w1, h->d_S.p, h->ws());
+    if (mode == 0) spmv3_kernel<0><<<grid, 256, 0, h->stream>>>(h->N, rowptr, colidx, h->d_vals, x, y, w1, h->d_S.p, h->ws());
+    else if (mode == 1) spmv3_kernel<1><<<grid, 256, 0, h->stream>>>(h->N, rowptr, colidx, h->d_vals, x, y, w1, h->d_S.p, h->ws());
+    else spmv3_kernel<2><<<grid, 256, 0, h->stream>>>(h->N, rowptr, colidx, h->d_vals, x, y, w1, h->d_S.p, h->ws());
     h->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -335,9 +451,11 @@ __global__ void dot_to_slot_kernel(size_t n, const double* __restrict__ a, const
     grid_reduce<1>(v, ws, [=](double (&t)[1]) { S[slot] = t[0]; });
 }
 
-int spmv_with_dots(opmgpu_handle h, int mode, const double* x, double* y, const double* w1)
+int spmv_with_dots(opmgpu_handle h, int mode, double* x, double* y, const double* w1)
 {
-    int rc = launch_spmv(h, mode, x, y, w1);
+    int rc = halo_exchange(h, x);
+    if (rc) return rc;
+    rc = launch_spmv(h, mode, x, y, w1);
     if (rc == -100) {
         const size_t n = (size_t)h->N * 3;
         if (mode == 1) {
@@ -351,22 +469,43 @@ int spmv_with_dots(opmgpu_handle h, int mode, const double* x, double* y, const 
         CK(cudaGetLastError());
         rc = 0;
     }
+    if (rc == 0 && mode == 1) rc = allreduce_slots(h, S_H, 1);
+    if (rc == 0 && mode == 2) rc = allreduce_slots(h, S_TR, 2);
     return rc;
 }
+
+int sweep_watchdog(opmgpu_handle h);
 
 int factor(opmgpu_handle h, int* bad_row)
 {
     if (!h->have_values) return h->bad("no matrix values set");
     const size_t nv = (size_t)h->nnzb * 9;
-    CK(cudaMemcpyAsync(h->d_lu.p, h->d_vals, nv * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    if (h->world > 1) {
+        gather_blocks_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, h->stream>>>((size_t)h->nnzb, h->d_lu_src.p, h->d_vals, h->d_lu.p);
+        h->launches++;
+    } else {
+        CK(cudaMemcpyAsync(h->d_lu.p, h->d_vals, nv * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    }
     const int big = 0x7fffffff;
     CK(cudaMemcpyAsync(h->d_bad.p, &big, sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    const std::vector<int>& lp = h->an.lvl_ptr;
-    for (size_t l = 0; l + 1 < lp.size(); ++l) {
-        const int n = lp[l + 1] - lp[l];
-        if (n <= 0) continue;
-        ilu0_factor_level_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(
-            h->d_lvl_rows.p, lp[l], lp[l + 1], h->d_rowptr.p, h->d_colidx.p, h->d_diag.p, h->d_lu.p, h->d_bad.p);
+    if (h->factor_by_levels) {
+        const std::vector<int>& lp = h->an.lvl_ptr;
+        for (size_t l = 0; l + 1 < lp.size(); ++l) {
+            const int n = lp[l + 1] - lp[l];
+            if (n <= 0) continue;
+            ilu0_factor_level_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(
+                h->d_lvl_rows.p, lp[l], lp[l + 1], h->d_rowptr.p, h->d_colidx.p, h->d_diag.p, h->d_lu.p, h->d_bad.p);
+            h->launches++;
+        }
+    } else {
+        FactorDev pg;
+        pg.cta_step_ptr = h->progL.cta_step_ptr.p; pg.step_row_ptr = h->progL.step_row_ptr.p; pg.prow = h->progL.prow.p;
+        pg.pblk_ptr = h->progL.pblk_ptr.p; pg.pcol = h->progL.pcol.p; pg.psrc = h->progL.psrc.p;
+        pg.pair_ptr = h->progL.pair_ptr.p; pg.pair_jk = h->progL.pair_jk.p; pg.pair_ik = h->progL.pair_ik.p;
+        pg.publish = h->progL.publish.p; pg.diag = h->d_diag.p;
+        double* lu = h->d_lu.p; int* flags = h->d_flags.p; int epoch = ++h->epoch; int* bad = h->d_bad.p; int* err = h->d_err.p;
+        void* args[] = {&pg, &lu, &flags, &epoch, &bad, &err};
+        CK(cudaLaunchCooperativeKernel((void*)ilu0_factor_tile_kernel, dim3(h->progL.P), dim3(128), args, 0, h->stream));
         h->launches++;
     }
     CK(cudaGetLastError());
@@ -398,7 +537,9 @@ int factor(opmgpu_handle h, int* bad_row)
     }
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(&h->h_flags2[1], h->d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(&h->h_flags2[0], h->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    if (h->h_flags2[0]) return sweep_watchdog(h);
     if (h->h_flags2[1] != big) {
         if (bad_row) *bad_row = h->h_flags2[1];
         h->err = "singular diagonal block in ILU0 at block row " + std::to_string(h->h_flags2[1]);
@@ -490,6 +631,7 @@ int bicgstab(opmgpu_handle h, const opmgpu_params* prm, opmgpu_result* res)
     CK(cudaMemcpyAsync(h->d_rt.p, h->d_r.p, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     bicg_init_kernel<<<kVecBlocks, 256, 0, h->stream>>>(n, h->d_r.p, h->d_S.p, h->ws());
     h->launches++;
+    if ((rc = allreduce_slots(h, S_NRM2, 2))) return rc;
     if ((rc = read_scalars(h))) return rc;
     const double norm0 = std::sqrt(h->h_S[S_NRM2]);
     double norm = norm0, rho = 1.0, omega = 1.0, it = 0.0;
@@ -520,6 +662,7 @@ int bicgstab(opmgpu_handle h, const opmgpu_params* prm, opmgpu_result* res)
         bicg_update1_kernel<<<kVecBlocks, 256, 0, h->stream>>>(n, h->d_x.p, h->d_r.p, h->d_y.p, h->d_v.p, h->d_S.p, h->ws());
         h->prof_end();
         h->launches++;
+        if ((rc = allreduce_slots(h, S_NRM2, 1))) return rc;
         if ((rc = read_scalars(h))) return rc;
         if (std::fabs(h->h_S[S_H]) < EPSILON) { status = OPMGPU_BREAKDOWN; break; }
         norm = std::sqrt(h->h_S[S_NRM2]);
@@ -539,6 +682,7 @@ int bicgstab(opmgpu_handle h, const opmgpu_params* prm, opmgpu_result* res)
         bicg_update2_kernel<<<kVecBlocks, 256, 0, h->stream>>>(n, h->d_x.p, h->d_r.p, h->d_y.p, h->d_t.p, h->d_rt.p, h->d_S.p, h->ws());
         h->prof_end();
         h->launches++;
+        if ((rc = allreduce_slots(h, S_NRM2, 2))) return rc;
         if ((rc = read_scalars(h))) return rc;
         omega = h->h_S[S_OMEGA];
         rho = h->h_S[S_RHO_OLD];
@@ -648,6 +792,7 @@ int opmgpu_create(int device, opmgpu_handle* out)
     per_sm = std::min(per_sm, std::max(occ, 1));
     h->sweep_ctas = h->sm_count * per_sm;
     if (const char* s = getenv("OPMGPU_SIMPLE_SWEEP")) h->force_simple = atoi(s) != 0;
+    if (const char* s = getenv("OPMGPU_FACTOR_BY_LEVELS")) h->factor_by_levels = atoi(s) != 0;
     cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
     cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
@@ -699,6 +844,8 @@ int opmgpu_destroy(opmgpu_handle h)
     h->d_x.release(); h->d_r.release(); h->d_rt.release(); h->d_p.release(); h->d_v.release();
     h->d_t.release(); h->d_y.release(); h->d_yL.release(); h->d_vU.release(); h->d_tmp.release(); h->d_tmp2.release();
     h->d_S.release(); h->d_partials.release(); h->d_ticket.release(); h->d_flags.release();
+    h->d_rowptr_full.release(); h->d_colidx_full.release(); h->d_lu_src.release(); h->d_send_rows.release(); h->d_sendbuf.release();
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     h->d_err.release(); h->d_bad.release(); h->d_map9.release(); h->d_cscval.release(); h->d_rhs_stage.release();
     if (h->h_S) cudaFreeHost(h->h_S);
     if (h->h_flags2) cudaFreeHost(h->h_flags2);
@@ -719,6 +866,7 @@ int opmgpu_set_stream(opmgpu_handle h, void* cuda_stream)
 int opmgpu_set_pattern_bcrs(opmgpu_handle h, int N, int nnzb, const int* rowptr, const int* colidx)
 {
     if (!h || !rowptr || !colidx) return OPMGPU_BAD_ARGUMENT;
+    if (h->world > 1) return h->bad("distributed handle: use opmgpu_set_pattern_bcrs_distributed");
     CK(cudaSetDevice(h->device));
     h->csc_colptr.clear(); h->csc_rowidx.clear();
     return set_pattern(h, N, nnzb, rowptr, colidx);
@@ -729,7 +877,7 @@ int opmgpu_set_values_bcrs3(opmgpu_handle h, const double* vals)
     if (!h || !vals) return OPMGPU_BAD_ARGUMENT;
     if (!h->have_pattern) return h->bad("set the pattern first");
     CK(cudaSetDevice(h->device));
-    const size_t nv = (size_t)h->nnzb * 9;
+    const size_t nv = (size_t)(h->world > 1 ? h->nnzb_full : h->nnzb) * 9;
     CK(h->d_vals_own.ensure(nv));
     CK(cudaMemcpyAsync(h->d_vals_own.p, vals, nv * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -751,6 +899,12 @@ int opmgpu_spmv_dev(opmgpu_handle h, const double* x_dev, double* y_dev)
 {
     if (!h || !h->have_values) return OPMGPU_BAD_ARGUMENT;
     CK(cudaSetDevice(h->device));
+    if (h->world > 1) {          // x_dev has no ghost rows: stage it
+        CK(cudaMemcpyAsync(h->d_tmp.p, x_dev, (size_t)h->N * 3 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        int rc = halo_exchange(h, h->d_tmp.p);
+        if (rc) return rc;
+        return launch_spmv(h, 0, h->d_tmp.p, y_dev, nullptr);
+    }
     return launch_spmv(h, 0, x_dev, y_dev, nullptr);
 }
 
@@ -760,7 +914,9 @@ int opmgpu_spmv(opmgpu_handle h, const double* x, double* y)
     CK(cudaSetDevice(h->device));
     const size_t n = (size_t)h->N * 3;
     CK(cudaMemcpyAsync(h->d_tmp.p, x, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    int rc = launch_spmv(h, 0, h->d_tmp.p, h->d_tmp2.p, nullptr);
+    int rc = halo_exchange(h, h->d_tmp.p);
+    if (rc) return rc;
+    rc = launch_spmv(h, 0, h->d_tmp.p, h->d_tmp2.p, nullptr);
     if (rc) return rc;
     CK(cudaMemcpyAsync(y, h->d_tmp2.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -850,7 +1006,7 @@ int opmgpu_solve_bcrs3(opmgpu_handle h, const double* vals, const double* rhs, d
     std::memset(result, 0, sizeof *result);
     result->bad_row = -1;
     CK(cudaSetDevice(h->device));
-    const size_t n = (size_t)h->N * 3, nv = (size_t)h->nnzb * 9;
+    const size_t n = (size_t)h->N * 3, nv = (size_t)(h->world > 1 ? h->nnzb_full : h->nnzb) * 9;
     CK(h->d_vals_own.ensure(nv));
     cudaEventRecord(h->ev[3], h->stream);
     CK(cudaMemcpyAsync(h->d_vals_own.p, vals, nv * sizeof(double), cudaMemcpyHostToDevice, h->stream));
@@ -1018,22 +1174,96 @@ int opmgpu_debug_trace_apply(opmgpu_handle h, int cta, double w, const double* d
 // ---- multi-GPU entry points -------------------------------------------------------------------
 int opmgpu_nccl_unique_id(void* id128)
 {
-    (void)id128;
-    g_create_error = "distributed mode not built yet";
-    return OPMGPU_NCCL_ERROR;
+    if (!id128) return OPMGPU_BAD_ARGUMENT;
+    if (!g_nccl.load(g_create_error)) return OPMGPU_NCCL_ERROR;
+    ncclUniqueId id;
+    const ncclResult_t r = g_nccl.GetUniqueId(&id);
+    if (r != ncclSuccess) { g_create_error = std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(r); return OPMGPU_NCCL_ERROR; }
+    std::memcpy(id128, &id, sizeof id);
+    return OPMGPU_OK;
 }
+
 int opmgpu_create_distributed(int device, int rank, int world, const void* nccl_unique_id, opmgpu_handle* out)
 {
-    (void)device; (void)rank; (void)world; (void)nccl_unique_id;
     *out = nullptr;
-    g_create_error = "distributed mode not built yet";
-    return OPMGPU_NCCL_ERROR;
+    if (world < 1 || rank < 0 || rank >= world || !nccl_unique_id) { g_create_error = "bad rank / world / id"; return OPMGPU_BAD_ARGUMENT; }
+    if (!g_nccl.load(g_create_error)) return OPMGPU_NCCL_ERROR;
+    opmgpu_handle h = nullptr;
+    int rc = opmgpu_create(device, &h);
+    if (rc) return rc;
+    h->rank = rank; h->world = world;
+    ncclUniqueId id;
+    std::memcpy(&id, nccl_unique_id, sizeof id);
+    const ncclResult_t r = g_nccl.CommInitRank(&h->comm, world, id, rank);
+    if (r != ncclSuccess) {
+        g_create_error = std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r);
+        opmgpu_destroy(h);
+        return OPMGPU_NCCL_ERROR;
+    }
+    *out = h;
+    return OPMGPU_OK;
 }
+
 int opmgpu_set_pattern_bcrs_distributed(opmgpu_handle h, int N_local, int nnzb_local, const int* rowptr,
-                                        const int* colidx_global, long long row_begin, long long N_global)
+                                        const long long* colidx_global, const long long* row_offsets)
 {
-    (void)N_local; (void)nnzb_local; (void)rowptr; (void)colidx_global; (void)row_begin; (void)N_global;
-    return h ? h->bad("distributed mode not built yet") : OPMGPU_BAD_ARGUMENT;
+    if (!h || !rowptr || !colidx_global || !row_offsets) return OPMGPU_BAD_ARGUMENT;
+    if (!h->comm) return h->bad("handle was not created with opmgpu_create_distributed");
+    if (N_local != (int)(row_offsets[h->rank + 1] - row_offsets[h->rank]) || rowptr[N_local] != nnzb_local)
+        return h->bad("local row count does not match row_offsets");
+    CK(cudaSetDevice(h->device));
+    LocalPartition lp;
+    partition_local_rows(N_local, rowptr, colidx_global, row_offsets, h->world, h->rank, lp);
+    h->n_ghost = lp.n_ghost;
+    h->nnzb_full = nnzb_local;
+    h->csc_colptr.clear(); h->csc_rowidx.clear();
+    int rc = set_pattern(h, N_local, (int)lp.colidx_diag.size(), lp.rowptr_diag.data(), lp.colidx_diag.data());
+    if (rc) return rc;
+    h->have_pattern = false;
+    CK(h->d_rowptr_full.ensure((size_t)N_local + 1));
+    CK(cudaMemcpyAsync(h->d_rowptr_full.p, rowptr, sizeof(int) * ((size_t)N_local + 1), cudaMemcpyHostToDevice, h->stream));
+    if ((rc = upload(h, h->d_colidx_full, lp.colidx_full))) return rc;
+    if ((rc = upload(h, h->d_lu_src, lp.lu_src))) return rc;
+    // halo plan: tell every owner which of its rows this rank needs
+    const int W = h->world;
+    h->recv_cnt = lp.recv_cnt; h->recv_off = lp.recv_off;
+    DevArr<int> d_cnt_mine, d_cnt_all;
+    CK(d_cnt_mine.ensure(W)); CK(d_cnt_all.ensure((size_t)W * W));
+    CK(cudaMemcpyAsync(d_cnt_mine.p, lp.recv_cnt.data(), sizeof(int) * W, cudaMemcpyHostToDevice, h->stream));
+    NK(g_nccl.AllGather(d_cnt_mine.p, d_cnt_all.p, (size_t)W, ncclInt32, h->comm, h->stream));
+    std::vector<int> cnt_all((size_t)W * W);
+    CK(cudaMemcpyAsync(cnt_all.data(), d_cnt_all.p, sizeof(int) * W * W, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->send_cnt.assign(W, 0); h->send_off.assign(W, 0);
+    for (int p = 0; p < W; ++p) h->send_cnt[p] = cnt_all[(size_t)p * W + h->rank];      // what p wants from me
+    for (int p = 1; p < W; ++p) h->send_off[p] = h->send_off[p - 1] + h->send_cnt[p - 1];
+    h->n_send = h->send_off[W - 1] + h->send_cnt[W - 1];
+    DevArr<long long> d_want, d_asked;
+    CK(d_want.ensure(std::max(lp.n_ghost, 1)));
+    CK(d_asked.ensure(std::max(h->n_send, 1)));
+    if (lp.n_ghost) CK(cudaMemcpyAsync(d_want.p, lp.ghost_global.data(), sizeof(long long) * lp.n_ghost, cudaMemcpyHostToDevice, h->stream));
+    NK(g_nccl.GroupStart());
+    for (int p = 0; p < W; ++p) {
+        if (lp.recv_cnt[p]) NK(g_nccl.Send(d_want.p + lp.recv_off[p], (size_t)lp.recv_cnt[p], ncclInt64, p, h->comm, h->stream));
+        if (h->send_cnt[p]) NK(g_nccl.Recv(d_asked.p + h->send_off[p], (size_t)h->send_cnt[p], ncclInt64, p, h->comm, h->stream));
+    }
+    NK(g_nccl.GroupEnd());
+    std::vector<long long> asked(std::max(h->n_send, 1));
+    if (h->n_send) CK(cudaMemcpyAsync(asked.data(), d_asked.p, sizeof(long long) * h->n_send, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    std::vector<int> send_rows(std::max(h->n_send, 1), 0);
+    for (int k = 0; k < h->n_send; ++k) {
+        const long long loc = asked[k] - row_offsets[h->rank];
+        if (loc < 0 || loc >= N_local) return h->bad("a peer asked for a row this rank does not own");
+        send_rows[k] = (int)loc;
+    }
+    if ((rc = upload(h, h->d_send_rows, send_rows))) return rc;
+    CK(h->d_sendbuf.ensure((size_t)std::max(h->n_send, 1) * 3));
+    if ((rc = ensure_vectors(h))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    d_cnt_mine.release(); d_cnt_all.release(); d_want.release(); d_asked.release();
+    h->have_pattern = true;
+    return OPMGPU_OK;
 }
 
 }  // extern "C"
