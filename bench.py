@@ -183,8 +183,24 @@ def run_gpu(args, rank, world):
     prof = g.profile()
     g.set_profiling(False)
 
-    # ---- end to end through the adapter-facing C-ABI call with host buffers (rank-local system)
+    # ---- end to end through the C-ABI call with host buffers (rank-local system)
     e2e = None
+    if world > 1:
+        vals_h = g.vals.cpu().pin_memory().numpy()
+        rhs_h = g.rhs.cpu().pin_memory().numpy()
+        for _ in range(2):
+            g.solve_bcrs(vals_h, rhs_h, params=params)
+        barrier()
+        ev0.record()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            g.solve_bcrs(vals_h, rhs_h, params=params)
+        ev1.record()
+        barrier()
+        t = torch.tensor([max((time.perf_counter() - t0) * 1e3, ev0.elapsed_time(ev1)) / args.steps], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": float(t), "unit": "ms", "h2d_bytes_per_step": int(vals_h.nbytes + rhs_h.nbytes),
+               "d2h_bytes_per_step": int(rhs_h.nbytes), "call": "opmgpu_solve_bcrs3 (pinned host buffers, this rank's rows; bytes are per rank)"}
     if world == 1:
         blocks = s.csc_blocks()
         pinned = []
@@ -217,8 +233,11 @@ def run_gpu(args, rank, world):
     peak_src = "measured (MEASURED_PEAKS.json)"
     if not peak:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    N, nnzb = s.N, s.nnzb
-    b_ilu = 76 * (nnzb - N) + 176 * N           # SURVEY.md §8d, bytes per apply
+    # per launch = per rank: rank 0's rows (its diagonal block for the block-Jacobi ILU0)
+    N, nnzb = (s.N, s.nnzb) if world == 1 else (g.N, g.nnzb)
+    plane = s.dims[0] * s.dims[1]
+    nnzb_ilu = nnzb if world == 1 else nnzb - plane * (1 if world == 2 else 1)      # rank 0 has one neighbour slab
+    b_ilu = 76 * (nnzb_ilu - N) + 176 * N       # SURVEY.md §8d, bytes per apply
     b_spmv = 76 * nnzb + 52 * N
     ap_ms, ap_n = prof["ilu_apply"]
     sp_ms, sp_n = prof["spmv"]
