@@ -287,3 +287,13 @@ def test_full_size_properties(dims, perm):
     res2 = g.solve_bcrs_dev(vals, rhs, xb)
     assert res2["iterations"] == res["iterations"] and torch.equal(x, xb)
     g.close()
+
+
+def test_cpp_host_mirror_selftest():
+    """csrc/host/NewtonIterationBlackoilGPU.{hpp,cpp}: the C++ class with the reference's interface,
+    wells eliminated on the host, cells solved on the GPU through the C ABI."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "opm_simulators_legacy_b200", "host_selftest")
+    assert os.path.exists(exe), "run __graft_entry__.build() first"
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
