@@ -158,6 +158,29 @@ void build_program(int N, const int* rowptr, const int* colidx, const std::vecto
             }
             prog.pair_ptr[b + 1] = (int)prog.pair_jk.size();
         }
+        prog.frow.assign((size_t)N * 4, 0);
+        prog.fent.assign(nblk * 8, 0);
+        for (int q = 0; q < N; ++q) {
+            const int r = order[q];
+            int dslot = rowptr[r];
+            while (colidx[dslot] != r) ++dslot;
+            const int b0 = prog.pblk_ptr[q], b1 = prog.pblk_ptr[q + 1];
+            bool simple = b1 - b0 <= 3;
+            for (int b = b0; b < b1; ++b) {
+                const int j = prog.pcol[b] & ~kExtBit;
+                int jd = rowptr[j];
+                while (colidx[jd] != j) ++jd;
+                const int np = prog.pair_ptr[b + 1] - prog.pair_ptr[b];
+                int* e = &prog.fent[(size_t)b * 8];
+                e[0] = prog.psrc[b]; e[1] = jd; e[2] = prog.pcol[b]; e[3] = np;
+                e[4] = np ? prog.pair_jk[prog.pair_ptr[b]] : -1;
+                e[5] = np ? prog.pair_ik[prog.pair_ptr[b]] : -1;
+                e[6] = prog.pair_ptr[b]; e[7] = 0;
+                if (np > 1 || (np == 1 && e[5] != dslot)) simple = false;
+            }
+            int* fr = &prog.frow[(size_t)q * 4];
+            fr[0] = r; fr[1] = dslot; fr[2] = b0; fr[3] = (b1 - b0) | (simple ? kFactorSimple : 0);
+        }
     }
 }
 

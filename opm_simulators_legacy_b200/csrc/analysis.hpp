@@ -34,7 +34,12 @@ struct SweepProgram {
     // factorisation only (lower program): for every block (i,j) the pairs (slot of A_jk, slot of
     // A_ik), k > j present in both rows, that A_ik -= L_ij * A_jk touches
     std::vector<int> pair_ptr, pair_jk, pair_ik;
+    // the same, packed for the factorisation kernel: frow[q] = {row, diag slot, first entry,
+    // entry count | kFactorSimple}, fent[b] = {slot ij, diag slot of j, dep row | kExtBit,
+    // pair count, first pair's jk, first pair's ik, pair_ptr, -}
+    std::vector<int> frow, fent;
 };
+constexpr int kFactorSimple = 1 << 30;       // <= 3 entries, each touching only the row's diagonal
 
 // ---- pipelined sweep program (the fast path) ---------------------------------------------------
 // Per CTA a byte stream of step records, one record per step, consumed linearly through a

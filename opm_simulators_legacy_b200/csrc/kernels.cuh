@@ -298,22 +298,33 @@ ilu0_factor_level_kernel(const int* __restrict__ lvl_rows, int begin, int end,
 struct FactorDev {
     const int* cta_step_ptr;
     const int* step_row_ptr;
-    const int* prow;
-    const int* pblk_ptr;
-    const int* pcol;          // dependency row | kExtBitDev
-    const int* psrc;          // BCRS slot of A_ij
-    const int* pair_ptr;
+    const int4* frow;         // {row, diag slot, first entry, count | kFactorSimpleDev}
+    const int4* fent;         // two per entry: {ij, jd, dep | ext, npairs} {jk0, ik0, pair_ptr, -}
     const int* pair_jk;
     const int* pair_ik;
     const unsigned char* publish;
-    const int* diag;
 };
+constexpr int kFactorSimpleDev = 1 << 30;
 
 __device__ __forceinline__ int ld_acquire_gpu_f(const int* p)
 {
     int v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+__device__ __forceinline__ void load9(double (&d)[9], const double* p, bool bypass_l1)
+{
+#pragma unroll
+    for (int t = 0; t < 9; ++t) d[t] = bypass_l1 ? __ldcg(p + t) : p[t];
+}
+__device__ __forceinline__ bool factor_wait_row(const int* flags, int j, int epoch, int* err)
+{
+    unsigned spins = 0;
+    while (ld_acquire_gpu_f(flags + j) != epoch) {
+        if (++spins > (1u << 22)) { atomicExch(err, 5); return false; }
+        if ((spins & 1023u) == 0 && *(volatile int*)err) return false;
+    }
+    return true;
 }
 
 __global__ void __launch_bounds__(128)
@@ -322,46 +333,87 @@ ilu0_factor_tile_kernel(FactorDev pg, double* lu, int* flags, int epoch, int* ba
     const int s_begin = pg.cta_step_ptr[blockIdx.x], s_end = pg.cta_step_ptr[blockIdx.x + 1];
     for (int s = s_begin; s < s_end; ++s) {
         const int q0 = pg.step_row_ptr[s], q1 = pg.step_row_ptr[s + 1];
+        // pull the coming levels towards L2 while this one computes: row records two levels
+        // ahead, entry records and the row's own blocks (lower part + diagonal are contiguous in
+        // BCRS) one level ahead
+        if (s + 2 < s_end) {
+            const int qn = pg.step_row_ptr[s + 2] + threadIdx.x;
+            if (qn < pg.step_row_ptr[s + 3]) asm volatile("prefetch.global.L2 [%0];" ::"l"(pg.frow + qn));
+        }
+        if (s + 1 < s_end) {
+            const int qn = q1 + threadIdx.x;
+            if (qn < pg.step_row_ptr[s + 2]) {
+                const int4 fn = pg.frow[qn];
+                const int nn = fn.w & ~kFactorSimpleDev;
+                const char* e = reinterpret_cast<const char*>(pg.fent + 2 * fn.z);
+                for (int o = 0; o < nn * 32; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(e + o));
+                const char* blk = reinterpret_cast<const char*>(lu + (size_t)(fn.y - nn) * 9);
+                for (int o = 0; o < (nn + 1) * 72 + 127; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(blk + o));
+            }
+        }
         for (int q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
-            const int i = pg.prow[q];
-            const int idiag = pg.diag[i];
+            const int4 fr = pg.frow[q];
+            const int i = fr.x, idiag = fr.y, e0 = fr.z, n = fr.w & ~kFactorSimpleDev;
             double D[9];
+            if (fr.w & kFactorSimpleDev) {
+                // stencil rows: every address is known now, issue all loads before any arithmetic
+                int4 ea[3], eb[3];
+                double A[3][9], Dj[3][9], Ajk[3][9];
 #pragma unroll
-            for (int t = 0; t < 9; ++t) D[t] = lu[(size_t)idiag * 9 + t];
-            const int b0 = pg.pblk_ptr[q], b1 = pg.pblk_ptr[q + 1];
-            for (int b = b0; b < b1; ++b) {
-                const int c = pg.pcol[b];
-                const int j = c & ~kExtBitDev;
-                const int ij = pg.psrc[b], jd = pg.diag[j];
-                const bool ext = (c & kExtBitDev) != 0;
-                if (ext) {
-                    unsigned spins = 0;
-                    while (ld_acquire_gpu_f(flags + j) != epoch) {
-                        if (++spins > (1u << 22)) { atomicExch(err, 5); break; }
-                        if ((spins & 1023u) == 0 && *(volatile int*)err) break;
+                for (int k = 0; k < 3; ++k)
+                    if (k < n) { ea[k] = pg.fent[2 * (e0 + k)]; eb[k] = pg.fent[2 * (e0 + k) + 1]; }
+                load9(D, lu + (size_t)idiag * 9, false);
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    if (k < n) load9(A[k], lu + (size_t)ea[k].x * 9, false);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    if (k < n) {
+                        const bool ext = (ea[k].z & kExtBitDev) != 0;
+                        if (ext) factor_wait_row(flags, ea[k].z & ~kExtBitDev, epoch, err);
+                        load9(Dj[k], lu + (size_t)ea[k].y * 9, ext);
+                        if (ea[k].w) load9(Ajk[k], lu + (size_t)eb[k].x * 9, ext);
                     }
                 }
-                double Aij[9], Dj[9], L[9];
 #pragma unroll
-                for (int t = 0; t < 9; ++t) {
-                    Aij[t] = lu[(size_t)ij * 9 + t];
-                    Dj[t] = ext ? __ldcg(lu + (size_t)jd * 9 + t) : lu[(size_t)jd * 9 + t];
+                for (int k = 0; k < 3; ++k) {
+                    if (k < n) {
+                        double L[9], B[9];
+                        mat3_mul(A[k], Dj[k], L);                     // L_ij = A_ij * inv(A_jj)
+#pragma unroll
+                        for (int t = 0; t < 9; ++t) lu[(size_t)ea[k].x * 9 + t] = L[t];
+                        if (ea[k].w) {
+                            mat3_mul(L, Ajk[k], B);                   // A_ii -= L_ij * A_ji
+#pragma unroll
+                            for (int t = 0; t < 9; ++t) D[t] -= B[t];
+                        }
+                    }
                 }
-                mat3_mul(Aij, Dj, L);                                 // L_ij = A_ij * inv(A_jj)
+            } else {
+                load9(D, lu + (size_t)idiag * 9, false);
+                for (int b = e0; b < e0 + n; ++b) {
+                    const int4 ea = pg.fent[2 * b], eb = pg.fent[2 * b + 1];
+                    const int ij = ea.x;
+                    const bool ext = (ea.z & kExtBitDev) != 0;
+                    if (ext) factor_wait_row(flags, ea.z & ~kExtBitDev, epoch, err);
+                    double Aij[9], Dj[9], L[9];
+                    load9(Aij, lu + (size_t)ij * 9, false);
+                    load9(Dj, lu + (size_t)ea.y * 9, ext);
+                    mat3_mul(Aij, Dj, L);
 #pragma unroll
-                for (int t = 0; t < 9; ++t) lu[(size_t)ij * 9 + t] = L[t];
-                for (int pp = pg.pair_ptr[b]; pp < pg.pair_ptr[b + 1]; ++pp) {
-                    const int jk = pg.pair_jk[pp], ik = pg.pair_ik[pp];
-                    double Ajk[9], B[9];
+                    for (int t = 0; t < 9; ++t) lu[(size_t)ij * 9 + t] = L[t];
+                    for (int pp = eb.z; pp < eb.z + ea.w; ++pp) {
+                        const int jk = pg.pair_jk[pp], ik = pg.pair_ik[pp];
+                        double Ajk[9], B[9];
+                        load9(Ajk, lu + (size_t)jk * 9, ext);
+                        mat3_mul(L, Ajk, B);
+                        if (ik == idiag) {
 #pragma unroll
-                    for (int t = 0; t < 9; ++t) Ajk[t] = ext ? __ldcg(lu + (size_t)jk * 9 + t) : lu[(size_t)jk * 9 + t];
-                    mat3_mul(L, Ajk, B);                              // B = L_ij * A_jk
-                    if (ik == idiag) {
+                            for (int t = 0; t < 9; ++t) D[t] -= B[t];
+                        } else {
 #pragma unroll
-                        for (int t = 0; t < 9; ++t) D[t] -= B[t];
-                    } else {
-#pragma unroll
-                        for (int t = 0; t < 9; ++t) lu[(size_t)ik * 9 + t] -= B[t];
+                            for (int t = 0; t < 9; ++t) lu[(size_t)ik * 9 + t] -= B[t];
+                        }
                     }
                 }
             }

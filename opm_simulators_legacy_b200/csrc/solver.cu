@@ -8,6 +8,7 @@
 #include "analysis.hpp"
 #include "kernels.cuh"
 #include "sweep_pipe.cuh"
+#include "spmv_tma.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>      // types only: the library is resolved at run time with dlopen
@@ -16,6 +17,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstdint>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -84,7 +86,7 @@ struct DevArr {
 struct ProgramDevMem {
     DevArr<int> cta_step_ptr, step_row_ptr, prow, pblk_ptr, pcol, psrc;
     DevArr<unsigned char> publish;
-    DevArr<int> pair_ptr, pair_jk, pair_ik;
+    DevArr<int> pair_ptr, pair_jk, pair_ik, frow, fent;
     DevArr<double> pval, pdinv;
     size_t nblk = 0;
     int P = 0;
@@ -92,7 +94,7 @@ struct ProgramDevMem {
     {
         cta_step_ptr.release(); step_row_ptr.release(); prow.release(); pblk_ptr.release();
         pcol.release(); psrc.release(); publish.release(); pval.release(); pdinv.release();
-        pair_ptr.release(); pair_jk.release(); pair_ik.release();
+        pair_ptr.release(); pair_jk.release(); pair_ik.release(); frow.release(); fent.release();
     }
 };
 
@@ -131,7 +133,7 @@ struct opmgpu_solver {
     DevArr<int> d_rowptr, d_colidx, d_diag, d_lvl_rows;
     ProgramDevMem progL, progU;
     PipeDevMem pipeL, pipeU;
-    bool use_pipe = false, force_simple = false, factor_by_levels = false;
+    bool use_pipe = false, force_simple = false, factor_by_levels = false, spmv_tma = true;
     int trace_cta = -1;
     DevArr<long long> d_trace;
     int max_smem_optin = 0;
@@ -249,6 +251,8 @@ int upload_program(opmgpu_handle h, const SweepProgram& p, ProgramDevMem& d, boo
         if ((rc = upload(h, d.pair_ptr, p.pair_ptr))) return rc;
         if ((rc = upload(h, d.pair_jk, p.pair_jk))) return rc;
         if ((rc = upload(h, d.pair_ik, p.pair_ik))) return rc;
+        if ((rc = upload(h, d.frow, p.frow))) return rc;
+        if ((rc = upload(h, d.fent, p.fent))) return rc;
     }
     if ((rc = upload(h, d.cta_step_ptr, p.cta_step_ptr))) return rc;
     if ((rc = upload(h, d.step_row_ptr, p.step_row_ptr))) return rc;
@@ -343,8 +347,8 @@ int set_pattern(opmgpu_handle h, int N, int nnzb, const int* rowptr, const int* 
         return OPMGPU_SINGULAR_BLOCK;
     }
     h->N = N; h->nnzb = nnzb;
-    CK(h->d_rowptr.ensure((size_t)N + 1));
-    CK(h->d_colidx.ensure(nnzb));
+    CK(h->d_rowptr.ensure((size_t)N + 1 + 8));      // + 8: the SpMV's bulk copies round sizes up to 16 bytes
+    CK(h->d_colidx.ensure((size_t)nnzb + 8));
     CK(cudaMemcpyAsync(h->d_rowptr.p, rowptr, sizeof(int) * ((size_t)N + 1), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_colidx.p, colidx, sizeof(int) * (size_t)nnzb, cudaMemcpyHostToDevice, h->stream));
     int rc;
@@ -425,6 +429,17 @@ int launch_spmv(opmgpu_handle h, int mode, const double* x, double* y, const dou
 {
     const int* rowptr = h->world > 1 ? h->d_rowptr_full.p : h->d_rowptr.p;
     const int* colidx = h->world > 1 ? h->d_colidx_full.p : h->d_colidx.p;
+    if (h->spmv_tma && (reinterpret_cast<uintptr_t>(h->d_vals) & 15) == 0) {
+        const int nnzb = h->world > 1 ? h->nnzb_full : h->nnzb;
+        const int ntiles = (h->N + kSpmvRows - 1) / kSpmvRows;
+        const unsigned grid = (unsigned)std::min(ntiles, h->sm_count);
+        if (mode == 0) spmv3_tma_kernel<0><<<grid, kSpmvThreads, kSpmvSmemBytes, h->stream>>>(h->N, nnzb, rowptr, colidx, h->d_vals, x, y, w1, h->d_S.p, h->ws());
+        else if (mode == 1) spmv3_tma_kernel<1><<<grid, kSpmvThreads, kSpmvSmemBytes, h->stream>>>(h->N, nnzb, rowptr, colidx, h->d_vals, x, y, w1, h->d_S.p, h->ws());
+        else spmv3_tma_kernel<2><<<grid, kSpmvThreads, kSpmvSmemBytes, h->stream>>>(h->N, nnzb, rowptr, colidx, h->d_vals, x, y, w1, h->d_S.p, h->ws());
+        h->launches++;
+        CK(cudaGetLastError());
+        return 0;
+    }
     const long long threads = 3LL * h->N;
     const unsigned grid = (unsigned)((threads + 255) / 256);
     if (mode != 0 && grid > kMaxRedBlocks) {
@@ -499,10 +514,10 @@ int factor(opmgpu_handle h, int* bad_row)
         }
     } else {
         FactorDev pg;
-        pg.cta_step_ptr = h->progL.cta_step_ptr.p; pg.step_row_ptr = h->progL.step_row_ptr.p; pg.prow = h->progL.prow.p;
-        pg.pblk_ptr = h->progL.pblk_ptr.p; pg.pcol = h->progL.pcol.p; pg.psrc = h->progL.psrc.p;
-        pg.pair_ptr = h->progL.pair_ptr.p; pg.pair_jk = h->progL.pair_jk.p; pg.pair_ik = h->progL.pair_ik.p;
-        pg.publish = h->progL.publish.p; pg.diag = h->d_diag.p;
+        pg.cta_step_ptr = h->progL.cta_step_ptr.p; pg.step_row_ptr = h->progL.step_row_ptr.p;
+        pg.frow = (const int4*)h->progL.frow.p; pg.fent = (const int4*)h->progL.fent.p;
+        pg.pair_jk = h->progL.pair_jk.p; pg.pair_ik = h->progL.pair_ik.p;
+        pg.publish = h->progL.publish.p;
         double* lu = h->d_lu.p; int* flags = h->d_flags.p; int epoch = ++h->epoch; int* bad = h->d_bad.p; int* err = h->d_err.p;
         void* args[] = {&pg, &lu, &flags, &epoch, &bad, &err};
         CK(cudaLaunchCooperativeKernel((void*)ilu0_factor_tile_kernel, dim3(h->progL.P), dim3(128), args, 0, h->stream));
@@ -793,6 +808,10 @@ int opmgpu_create(int device, opmgpu_handle* out)
     h->sweep_ctas = h->sm_count * per_sm;
     if (const char* s = getenv("OPMGPU_SIMPLE_SWEEP")) h->force_simple = atoi(s) != 0;
     if (const char* s = getenv("OPMGPU_FACTOR_BY_LEVELS")) h->factor_by_levels = atoi(s) != 0;
+    if (const char* s = getenv("OPMGPU_SPMV_SIMPLE")) h->spmv_tma = atoi(s) == 0;
+    cudaFuncSetAttribute(spmv3_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
+    cudaFuncSetAttribute(spmv3_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
+    cudaFuncSetAttribute(spmv3_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
     cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
     cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
@@ -1220,8 +1239,9 @@ int opmgpu_set_pattern_bcrs_distributed(opmgpu_handle h, int N_local, int nnzb_l
     int rc = set_pattern(h, N_local, (int)lp.colidx_diag.size(), lp.rowptr_diag.data(), lp.colidx_diag.data());
     if (rc) return rc;
     h->have_pattern = false;
-    CK(h->d_rowptr_full.ensure((size_t)N_local + 1));
+    CK(h->d_rowptr_full.ensure((size_t)N_local + 1 + 8));
     CK(cudaMemcpyAsync(h->d_rowptr_full.p, rowptr, sizeof(int) * ((size_t)N_local + 1), cudaMemcpyHostToDevice, h->stream));
+    lp.colidx_full.resize(lp.colidx_full.size() + 8, 0);      // padding for the SpMV's 16-byte bulk copies
     if ((rc = upload(h, h->d_colidx_full, lp.colidx_full))) return rc;
     if ((rc = upload(h, h->d_lu_src, lp.lu_src))) return rc;
     // halo plan: tell every owner which of its rows this rank needs

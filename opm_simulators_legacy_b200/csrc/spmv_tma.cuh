@@ -1,0 +1,153 @@
+// K2 (fast path)  BCRS 3x3 SpMV  y = A x  as a persistent TMA-pipelined stream (sm_100a).
+//
+// (Dune::MatrixAdapter::apply -> BCRSMatrix::mv -> umv; call site opm/autodiff/ISTLSolver.hpp:303)
+//
+// The values of consecutive block rows are one contiguous byte range, so a CTA walks tiles of
+// 64 rows: one elected lane fetches the tile's values, column indices and row pointers with
+// bulk async copies (cp.async.bulk + mbarrier complete_tx) into a 6-stage shared-memory ring;
+// three groups of 192 compute threads, one thread per (row, component), read the blocks from shared memory in
+// ascending column order (the reference's order: bit parity) and gather x through L1/L2
+// (x is 24 MB at 1M cells, L2 resident).  The BiCGStab dot products that follow the SpMV are
+// fused as an epilogue: MODE 1: S[S_H] = w1.y; MODE 2: S[S_TR] = y.w1, S[S_TT] = y.y, reduced
+// deterministically over the (at most 148*k) CTAs.
+// Algorithmic bytes: 76 per block + 52 per row.
+#pragma once
+#include "kernels.cuh"
+#include "sweep_pipe.cuh"      // mbarrier / bulk-copy helpers
+
+namespace opmgpu {
+
+constexpr int kSpmvRows = 64;                   // rows per tile
+constexpr int kSpmvCapBlocks = 480;             // blocks a stage can hold (>= 64*7 + alignment slack)
+constexpr int kSpmvStages = 6;                  // a multiple of kSpmvGroups: a stage always serves the same
+                                                // group, so that group sees every phase of its mbarriers
+constexpr int kSpmvComputeWarps = 6;            // 192 threads = 64 rows x 3 components
+constexpr int kSpmvGroups = 3;                  // consumer groups working on different tiles at once
+constexpr int kSpmvThreads = 32 * (1 + kSpmvGroups * kSpmvComputeWarps);
+constexpr int kSpmvValBytes = kSpmvCapBlocks * 72;
+constexpr int kSpmvColBytes = ((kSpmvCapBlocks + 4) * 4 + 15) / 16 * 16;
+constexpr int kSpmvPtrBytes = ((kSpmvRows + 1 + 3) * 4 + 15) / 16 * 16;
+constexpr int kSpmvStageBytes = kSpmvValBytes + kSpmvColBytes + kSpmvPtrBytes;
+constexpr size_t kSpmvSmemBytes = 128 + (size_t)kSpmvStages * kSpmvStageBytes;
+static_assert(kSpmvStages % 3 == 0, "stages must be a multiple of the consumer groups");
+
+// rowptr / colidx must be readable up to 16 bytes past their end (the solver's own buffers are
+// padded); vals is never read past its end (a misaligned last tile takes the direct path).
+template <int MODE>
+__global__ void __launch_bounds__(kSpmvThreads, 1)
+spmv3_tma_kernel(int N, int nnzb, const int* __restrict__ rowptr, const int* __restrict__ colidx,
+                 const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
+                 const double* __restrict__ w1, double* S, ReduceWs ws)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(smem_raw);
+    unsigned long long* empty = full + kSpmvStages;
+    unsigned char* stages = smem_raw + 128;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ntiles = (N + kSpmvRows - 1) / kSpmvRows;
+
+    if (tid == 0) {
+        for (int i = 0; i < kSpmvStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kSpmvComputeWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    double d0 = 0.0, d1 = 0.0;                  // dot partials of this thread
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+                const int st = it % kSpmvStages, k = it / kSpmvStages;
+                const int r0 = t * kSpmvRows, r1 = min(N, r0 + kSpmvRows);
+                const int b0 = rowptr[r0], b1 = rowptr[r1];
+                const int b0a = b0 & ~1;                                  // 16-byte aligned start
+                int b1a = (b1 + 1) & ~1;
+                const bool direct = (b1a > nnzb) || (b1a - b0a > kSpmvCapBlocks);   // odd tail / oversized tile
+                if (k > 0) { while (!mbar_try_wait(&empty[st], (unsigned)((k - 1) & 1))) {} }
+                unsigned char* stage = stages + (size_t)st * kSpmvStageBytes;
+                int* hdr = reinterpret_cast<int*>(stage + kSpmvValBytes + kSpmvColBytes);
+                // the row pointers always travel; values and columns unless the tile is direct
+                const unsigned pbytes = (unsigned)(((r1 - r0 + 1) * 4 + 15) & ~15);
+                const int c0a = b0 & ~3;
+                const unsigned cbytes = direct ? 0u : (unsigned)((((b1 - c0a) * 4) + 15) & ~15);
+                const unsigned vbytes = direct ? 0u : (unsigned)((b1a - b0a) * 72);
+                mbar_arrive_expect_tx(&full[st], pbytes + cbytes + vbytes);
+                tma_bulk_g2s(hdr, rowptr + r0, pbytes, &full[st]);
+                if (!direct) {
+                    tma_bulk_g2s(stage, vals + (size_t)b0a * 9, vbytes, &full[st]);
+                    tma_bulk_g2s(stage + kSpmvValBytes, colidx + c0a, cbytes, &full[st]);
+                }
+            }
+        }
+    } else {
+        // consumer group g takes every kSpmvGroups-th tile of this CTA, so several tiles' x
+        // gathers (L2 latency) are in flight per SM
+        const int g = (warp - 1) / kSpmvComputeWarps;
+        const int ct = tid - 32 - g * kSpmvComputeWarps * 32;
+        const int rl = ct / 3, c = ct - rl * 3;
+        int it = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+            if (it % kSpmvGroups != g) continue;
+            const int st = it % kSpmvStages, k = it / kSpmvStages;
+            const int r0 = t * kSpmvRows, r1 = min(N, r0 + kSpmvRows);
+            while (!mbar_try_wait(&full[st], (unsigned)(k & 1))) {}
+            const unsigned char* stage = stages + (size_t)st * kSpmvStageBytes;
+            const int* rp = reinterpret_cast<const int*>(stage + kSpmvValBytes + kSpmvColBytes);
+            const int b0 = rp[0], b1 = rp[r1 - r0];
+            const int b0a = b0 & ~1, b1a = (b1 + 1) & ~1, c0a = b0 & ~3;
+            const bool direct = (b1a > nnzb) || (b1a - b0a > kSpmvCapBlocks);
+            const int r = r0 + rl;
+            if (r < r1) {
+                const int kb = rp[rl], ke = rp[rl + 1];
+                double acc = 0.0;
+                if (!direct) {
+                    const double* vs = reinterpret_cast<const double*>(stage) + c * 3;
+                    const int* cs = reinterpret_cast<const int*>(stage + kSpmvValBytes);
+                    // all x gathers of up to eight blocks are issued before the FMA chain
+                    for (int kk = kb; kk < ke; kk += 8) {
+                        double xv[8][3];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            if (kk + u < ke) {
+                                const double* xj = x + (size_t)cs[kk + u - c0a] * 3;
+                                xv[u][0] = xj[0]; xv[u][1] = xj[1]; xv[u][2] = xj[2];
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            if (kk + u < ke) {
+                                const double* a = vs + (size_t)(kk + u - b0a) * 9;
+                                acc = fma(a[0], xv[u][0], acc);
+                                acc = fma(a[1], xv[u][1], acc);
+                                acc = fma(a[2], xv[u][2], acc);
+                            }
+                        }
+                    }
+                } else {
+                    for (int kk = kb; kk < ke; ++kk) {
+                        const double* a = vals + (size_t)kk * 9 + c * 3;
+                        const double* xj = x + (size_t)colidx[kk] * 3;
+                        acc = fma(a[0], xj[0], acc);
+                        acc = fma(a[1], xj[1], acc);
+                        acc = fma(a[2], xj[2], acc);
+                    }
+                }
+                const size_t o = (size_t)r * 3 + c;
+                y[o] = acc;
+                if (MODE == 1) d0 = fma(w1[o], acc, d0);
+                if (MODE == 2) { d0 = fma(acc, w1[o], d0); d1 = fma(acc, acc, d1); }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[st]);
+        }
+    }
+    if (MODE == 1) {
+        double v[1] = {d0};
+        grid_reduce<1>(v, ws, [=](double (&u)[1]) { S[S_H] = u[0]; });
+    } else if (MODE == 2) {
+        double v[2] = {d0, d1};
+        grid_reduce<2>(v, ws, [=](double (&u)[2]) { S[S_TR] = u[0]; S[S_TT] = u[1]; });
+    }
+}
+
+}  // namespace opmgpu
