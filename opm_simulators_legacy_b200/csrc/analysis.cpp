@@ -181,6 +181,29 @@ void build_program(int N, const int* rowptr, const int* colidx, const std::vecto
             int* fr = &prog.frow[(size_t)q * 4];
             fr[0] = r; fr[1] = dslot; fr[2] = b0; fr[3] = (b1 - b0) | (simple ? kFactorSimple : 0);
         }
+        // push slots for the pivots: consumer entry (i <- j) gets one when i and j are both simple
+        std::vector<int> qof(N);
+        for (int q = 0; q < N; ++q) qof[order[q]] = q;
+        std::vector<std::vector<int>> pushes(N);
+        prog.needs_flag.assign(N, 0);
+        int nslots = 0;
+        for (int q = 0; q < N; ++q) {
+            const bool isimple = (prog.frow[(size_t)q * 4 + 3] & kFactorSimple) != 0;
+            for (int b = prog.pblk_ptr[q]; b < prog.pblk_ptr[q + 1]; ++b) {
+                int* e = &prog.fent[(size_t)b * 8];
+                e[7] = -1;
+                if (!(prog.pcol[b] & kExtBit)) continue;
+                const int j = prog.pcol[b] & ~kExtBit, qj = qof[j];
+                const bool jsimple = (prog.frow[(size_t)qj * 4 + 3] & kFactorSimple) != 0;
+                if (isimple && jsimple) { e[7] = nslots; pushes[qj].push_back(nslots); ++nslots; }
+                else prog.needs_flag[qj] = 1;
+            }
+        }
+        prog.n_fslots = nslots;
+        prog.fpush_ptr.assign(N + 1, 0);
+        for (int q = 0; q < N; ++q) prog.fpush_ptr[q + 1] = prog.fpush_ptr[q] + (int)pushes[q].size();
+        prog.fpush_slot.clear();
+        for (int q = 0; q < N; ++q) prog.fpush_slot.insert(prog.fpush_slot.end(), pushes[q].begin(), pushes[q].end());
     }
 }
 

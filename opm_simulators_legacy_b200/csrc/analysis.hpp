@@ -38,6 +38,13 @@ struct SweepProgram {
     // entry count | kFactorSimple}, fent[b] = {slot ij, diag slot of j, dep row | kExtBit,
     // pair count, first pair's jk, first pair's ik, pair_ptr, -}
     std::vector<int> frow, fent;
+    // inverted pivot blocks travel between CTAs through self-validating push slots (9 doubles,
+    // all-ones = empty) when both rows are "simple": fent[b][7] = slot or -1 (then the per-row
+    // flag is used), fpush_ptr/fpush_slot = slots a row's pivot is pushed to, needs_flag[q] = some
+    // consumer in another CTA still relies on the flag
+    std::vector<int> fpush_ptr, fpush_slot;
+    std::vector<unsigned char> needs_flag;
+    int n_fslots = 0;
 };
 constexpr int kFactorSimple = 1 << 30;       // <= 3 entries, each touching only the row's diagonal
 

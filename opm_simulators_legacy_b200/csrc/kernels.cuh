@@ -302,9 +302,32 @@ struct FactorDev {
     const int4* fent;         // two per entry: {ij, jd, dep | ext, npairs} {jk0, ik0, pair_ptr, -}
     const int* pair_jk;
     const int* pair_ik;
-    const unsigned char* publish;
+    const unsigned char* needs_flag;   // some consumer in another CTA waits on the row's flag
+    const int* fpush_ptr;              // slots the row's inverted pivot is pushed to
+    const int* fpush_slot;
+    double* fslots;                    // [n][9], all-ones = empty
 };
 constexpr int kFactorSimpleDev = 1 << 30;
+
+// self-validating 9-double slot written by another CTA (each double is one atomic 8-byte store)
+__device__ __forceinline__ bool factor_poll_slot(const double* slot, double (&d)[9], int* err)
+{
+    const volatile long long* s = reinterpret_cast<const volatile long long*>(slot);
+    unsigned spins = 0;
+    for (;;) {
+        long long v[9];
+        bool ok = true;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) { v[t] = s[t]; ok = ok && v[t] != -1; }
+        if (ok) {
+#pragma unroll
+            for (int t = 0; t < 9; ++t) d[t] = __longlong_as_double(v[t]);
+            return true;
+        }
+        if (++spins > (1u << 22)) { atomicExch(err, 6); return false; }
+        if ((spins & 255u) == 0 && *(volatile int*)err) return false;
+    }
+}
 
 __device__ __forceinline__ int ld_acquire_gpu_f(const int* p)
 {
@@ -327,10 +350,31 @@ __device__ __forceinline__ bool factor_wait_row(const int* flags, int j, int epo
     return true;
 }
 
-__global__ void __launch_bounds__(128)
+// row c of C = A * B where the thread holds row c of A (dune's accumulation order per entry)
+__device__ __forceinline__ void mat3_row_mul(const double (&Arow)[3], const double (&B)[9], double (&Crow)[3])
+{
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) s = fma(Arow[k], B[k * 3 + j], s);
+        Crow[j] = s;
+    }
+}
+
+// Three threads per block row (thread c owns row c of every 3x3 block of the row; ten rows per
+// warp, lanes 30/31 idle), one level of the CTA's tile per iteration.
+constexpr int kFactorThreads = 256;
+constexpr int kFactorRowsPerPass = (kFactorThreads / 32) * 10;
+
+__global__ void __launch_bounds__(kFactorThreads)
 ilu0_factor_tile_kernel(FactorDev pg, double* lu, int* flags, int epoch, int* bad_row, int* err)
 {
     const int s_begin = pg.cta_step_ptr[blockIdx.x], s_end = pg.cta_step_ptr[blockIdx.x + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rl = lane / 3, c = lane - rl * 3;
+    const bool lane_on = lane < 30;
+    const int base = rl * 3;
     for (int s = s_begin; s < s_end; ++s) {
         const int q0 = pg.step_row_ptr[s], q1 = pg.step_row_ptr[s + 1];
         // pull the coming levels towards L2 while this one computes: row records two levels
@@ -351,45 +395,68 @@ ilu0_factor_tile_kernel(FactorDev pg, double* lu, int* flags, int epoch, int* ba
                 for (int o = 0; o < (nn + 1) * 72 + 127; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(blk + o));
             }
         }
-        for (int q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
-            const int4 fr = pg.frow[q];
+        for (int qb = q0; qb < q1; qb += kFactorRowsPerPass) {              // warp-uniform trip count
+            const int q = qb + warp * 10 + rl;
+            const bool on = lane_on && q < q1;
+            int4 fr = make_int4(0, 0, 0, 0);
+            if (on) fr = pg.frow[q];
             const int i = fr.x, idiag = fr.y, e0 = fr.z, n = fr.w & ~kFactorSimpleDev;
-            double D[9];
-            if (fr.w & kFactorSimpleDev) {
+            const bool simple = on && (fr.w & kFactorSimpleDev);
+            double Drow[3] = {0.0, 0.0, 0.0};
+            int rearm[3] = {-1, -1, -1};
+            if (simple) {
                 // stencil rows: every address is known now, issue all loads before any arithmetic
-                int4 ea[3], eb[3];
-                double A[3][9], Dj[3][9], Ajk[3][9];
+                int4 ea[3];
+                int jk0[3];
+                double Arow[3][3], Dj[3][9], Ajk[3][9];
 #pragma unroll
                 for (int k = 0; k < 3; ++k)
-                    if (k < n) { ea[k] = pg.fent[2 * (e0 + k)]; eb[k] = pg.fent[2 * (e0 + k) + 1]; }
-                load9(D, lu + (size_t)idiag * 9, false);
+                    if (k < n) {
+                        ea[k] = pg.fent[2 * (e0 + k)];
+                        const int4 eb = pg.fent[2 * (e0 + k) + 1];
+                        jk0[k] = eb.x; rearm[k] = eb.w;
+                    }
+#pragma unroll
+                for (int t = 0; t < 3; ++t) Drow[t] = lu[(size_t)idiag * 9 + c * 3 + t];
 #pragma unroll
                 for (int k = 0; k < 3; ++k)
-                    if (k < n) load9(A[k], lu + (size_t)ea[k].x * 9, false);
+                    if (k < n) {
+#pragma unroll
+                        for (int t = 0; t < 3; ++t) Arow[k][t] = lu[(size_t)ea[k].x * 9 + c * 3 + t];
+                    }
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
                     if (k < n) {
                         const bool ext = (ea[k].z & kExtBitDev) != 0;
-                        if (ext) factor_wait_row(flags, ea[k].z & ~kExtBitDev, epoch, err);
-                        load9(Dj[k], lu + (size_t)ea[k].y * 9, ext);
-                        if (ea[k].w) load9(Ajk[k], lu + (size_t)eb[k].x * 9, ext);
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    if (k < n) {
-                        double L[9], B[9];
-                        mat3_mul(A[k], Dj[k], L);                     // L_ij = A_ij * inv(A_jj)
-#pragma unroll
-                        for (int t = 0; t < 9; ++t) lu[(size_t)ea[k].x * 9 + t] = L[t];
-                        if (ea[k].w) {
-                            mat3_mul(L, Ajk[k], B);                   // A_ii -= L_ij * A_ji
-#pragma unroll
-                            for (int t = 0; t < 9; ++t) D[t] -= B[t];
+                        // the coupling block A_ji of a simple row j is never modified: no wait
+                        if (ea[k].w && rearm[k] >= 0) load9(Ajk[k], lu + (size_t)jk0[k] * 9, true);
+                        if (ext && rearm[k] < 0) factor_wait_row(flags, ea[k].z & ~kExtBitDev, epoch, err);
+                        if (!(ext && rearm[k] >= 0)) {
+                            load9(Dj[k], lu + (size_t)ea[k].y * 9, ext);
+                            if (ea[k].w) load9(Ajk[k], lu + (size_t)jk0[k] * 9, ext);
                         }
                     }
                 }
-            } else {
+#pragma unroll
+                for (int k = 0; k < 3; ++k)                                  // pushed pivots last: they arrive latest
+                    if (k < n && rearm[k] >= 0) factor_poll_slot(pg.fslots + (size_t)rearm[k] * 9, Dj[k], err);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    if (k < n) {
+                        double Lrow[3], Brow[3];
+                        mat3_row_mul(Arow[k], Dj[k], Lrow);                 // L_ij = A_ij * inv(A_jj)
+#pragma unroll
+                        for (int t = 0; t < 3; ++t) lu[(size_t)ea[k].x * 9 + c * 3 + t] = Lrow[t];
+                        if (ea[k].w) {
+                            mat3_row_mul(Lrow, Ajk[k], Brow);               // A_ii -= L_ij * A_ji
+#pragma unroll
+                            for (int t = 0; t < 3; ++t) Drow[t] -= Brow[t];
+                        }
+                    }
+                }
+            } else if (on && c == 0) {
+                // general rows (more than three lower blocks, fill outside the diagonal): one thread
+                double D[9];
                 load9(D, lu + (size_t)idiag * 9, false);
                 for (int b = e0; b < e0 + n; ++b) {
                     const int4 ea = pg.fent[2 * b], eb = pg.fent[2 * b + 1];
@@ -416,12 +483,41 @@ ilu0_factor_tile_kernel(FactorDev pg, double* lu, int* flags, int epoch, int* ba
                         }
                     }
                 }
-            }
-            const double det = mat3_invert(D);
+                const double det = mat3_invert(D);
 #pragma unroll
-            for (int t = 0; t < 9; ++t) lu[(size_t)idiag * 9 + t] = D[t];
-            if (!(det != 0.0) || isinf(det) || isnan(det)) atomicMin(bad_row, i);
-            if (pg.publish[q]) {
+                for (int t = 0; t < 9; ++t) lu[(size_t)idiag * 9 + t] = D[t];
+                if (!(det != 0.0) || isinf(det) || isnan(det)) atomicMin(bad_row, i);
+            }
+            // simple rows: gather the whole pivot block inside the warp, invert, store own row
+            double D[9];
+#pragma unroll
+            for (int m = 0; m < 3; ++m)
+#pragma unroll
+                for (int t = 0; t < 3; ++t) D[m * 3 + t] = __shfl_sync(0xffffffffu, Drow[t], base + m);
+            if (simple) {
+                const double det = mat3_invert(D);
+                const double o0 = c == 0 ? D[0] : (c == 1 ? D[3] : D[6]);
+                const double o1 = c == 0 ? D[1] : (c == 1 ? D[4] : D[7]);
+                const double o2 = c == 0 ? D[2] : (c == 1 ? D[5] : D[8]);
+                double* dst = lu + (size_t)idiag * 9 + c * 3;
+                dst[0] = o0; dst[1] = o1; dst[2] = o2;
+                for (int t = pg.fpush_ptr[q]; t < pg.fpush_ptr[q + 1]; ++t) {      // push the pivot to other CTAs
+                    double* sl = pg.fslots + (size_t)pg.fpush_slot[t] * 9 + c * 3;
+                    __stcg(sl, o0); __stcg(sl + 1, o1); __stcg(sl + 2, o2);
+                }
+                if (c == 0 && (!(det != 0.0) || isinf(det) || isnan(det))) atomicMin(bad_row, i);
+            }
+            __syncwarp();
+            if (simple && c == 0) {                                          // re-arm the slots this row consumed
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    if (rearm[k] >= 0) {
+                        long long* sl = reinterpret_cast<long long*>(pg.fslots + (size_t)rearm[k] * 9);
+#pragma unroll
+                        for (int t = 0; t < 9; ++t) __stcg(sl + t, -1LL);
+                    }
+            }
+            if (on && c == 0 && pg.needs_flag[q]) {
                 __threadfence();
                 asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flags + i), "r"(epoch) : "memory");
             }

@@ -86,8 +86,10 @@ struct DevArr {
 struct ProgramDevMem {
     DevArr<int> cta_step_ptr, step_row_ptr, prow, pblk_ptr, pcol, psrc;
     DevArr<unsigned char> publish;
-    DevArr<int> pair_ptr, pair_jk, pair_ik, frow, fent;
-    DevArr<double> pval, pdinv;
+    DevArr<int> pair_ptr, pair_jk, pair_ik, frow, fent, fpush_ptr, fpush_slot;
+    DevArr<unsigned char> needs_flag;
+    DevArr<double> pval, pdinv, fslots;
+    size_t n_fslots = 0;
     size_t nblk = 0;
     int P = 0;
     void release()
@@ -95,6 +97,7 @@ struct ProgramDevMem {
         cta_step_ptr.release(); step_row_ptr.release(); prow.release(); pblk_ptr.release();
         pcol.release(); psrc.release(); publish.release(); pval.release(); pdinv.release();
         pair_ptr.release(); pair_jk.release(); pair_ik.release(); frow.release(); fent.release();
+        fpush_ptr.release(); fpush_slot.release(); needs_flag.release(); fslots.release();
     }
 };
 
@@ -253,6 +256,12 @@ int upload_program(opmgpu_handle h, const SweepProgram& p, ProgramDevMem& d, boo
         if ((rc = upload(h, d.pair_ik, p.pair_ik))) return rc;
         if ((rc = upload(h, d.frow, p.frow))) return rc;
         if ((rc = upload(h, d.fent, p.fent))) return rc;
+        if ((rc = upload(h, d.fpush_ptr, p.fpush_ptr))) return rc;
+        if ((rc = upload(h, d.fpush_slot, p.fpush_slot))) return rc;
+        if ((rc = upload(h, d.needs_flag, p.needs_flag))) return rc;
+        d.n_fslots = (size_t)p.n_fslots;
+        CK(d.fslots.ensure(std::max<size_t>(d.n_fslots, 1) * 9));
+        CK(cudaMemsetAsync(d.fslots.p, 0xff, std::max<size_t>(d.n_fslots, 1) * 9 * sizeof(double), h->stream));
     }
     if ((rc = upload(h, d.cta_step_ptr, p.cta_step_ptr))) return rc;
     if ((rc = upload(h, d.step_row_ptr, p.step_row_ptr))) return rc;
@@ -517,10 +526,11 @@ int factor(opmgpu_handle h, int* bad_row)
         pg.cta_step_ptr = h->progL.cta_step_ptr.p; pg.step_row_ptr = h->progL.step_row_ptr.p;
         pg.frow = (const int4*)h->progL.frow.p; pg.fent = (const int4*)h->progL.fent.p;
         pg.pair_jk = h->progL.pair_jk.p; pg.pair_ik = h->progL.pair_ik.p;
-        pg.publish = h->progL.publish.p;
+        pg.needs_flag = h->progL.needs_flag.p; pg.fpush_ptr = h->progL.fpush_ptr.p; pg.fpush_slot = h->progL.fpush_slot.p;
+        pg.fslots = h->progL.fslots.p;
         double* lu = h->d_lu.p; int* flags = h->d_flags.p; int epoch = ++h->epoch; int* bad = h->d_bad.p; int* err = h->d_err.p;
         void* args[] = {&pg, &lu, &flags, &epoch, &bad, &err};
-        CK(cudaLaunchCooperativeKernel((void*)ilu0_factor_tile_kernel, dim3(h->progL.P), dim3(128), args, 0, h->stream));
+        CK(cudaLaunchCooperativeKernel((void*)ilu0_factor_tile_kernel, dim3(h->progL.P), dim3(kFactorThreads), args, 0, h->stream));
         h->launches++;
     }
     CK(cudaGetLastError());
@@ -620,6 +630,7 @@ int sweep_watchdog(opmgpu_handle h)
     cudaMemsetAsync(h->d_err.p, 0, sizeof(int), h->stream);
     for (PipeDevMem* d : {&h->pipeL, &h->pipeU})
         if (d->ext.p) cudaMemsetAsync(d->ext.p, 0xff, std::max<size_t>(d->next, 1) * 3 * sizeof(double), h->stream);
+    if (h->progL.fslots.p) cudaMemsetAsync(h->progL.fslots.p, 0xff, std::max<size_t>(h->progL.n_fslots, 1) * 9 * sizeof(double), h->stream);
     cudaStreamSynchronize(h->stream);
     return OPMGPU_CUDA_ERROR;
 }
