@@ -312,13 +312,16 @@ constexpr int kFactorSimpleDev = 1 << 30;
 // self-validating 9-double slot written by another CTA (each double is one atomic 8-byte store)
 __device__ __forceinline__ bool factor_poll_slot(const double* slot, double (&d)[9], int* err)
 {
-    const volatile long long* s = reinterpret_cast<const volatile long long*>(slot);
+    const long long* s = reinterpret_cast<const long long*>(slot);
     unsigned spins = 0;
     for (;;) {
         long long v[9];
         bool ok = true;
 #pragma unroll
-        for (int t = 0; t < 9; ++t) { v[t] = s[t]; ok = ok && v[t] != -1; }
+        for (int t = 0; t < 9; ++t) {
+            asm volatile("ld.relaxed.gpu.global.s64 %0, [%1];" : "=l"(v[t]) : "l"(s + t) : "memory");
+            ok = ok && v[t] != -1;
+        }
         if (ok) {
 #pragma unroll
             for (int t = 0; t < 9; ++t) d[t] = __longlong_as_double(v[t]);

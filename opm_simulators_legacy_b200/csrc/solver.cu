@@ -20,6 +20,7 @@
 #include <cstdint>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace opmgpu;
@@ -754,15 +755,35 @@ int solve_resident(opmgpu_handle h, const opmgpu_params* prm, opmgpu_result* res
     return rc;
 }
 
+// memcmp of two large buffers on several host threads (the nine CSC index arrays are ~290 MB at
+// 1M cells; a single-threaded compare would cost more than the whole GPU solve)
+bool equal_parallel(const void* a, const void* b, size_t bytes)
+{
+    const size_t kMin = 4u << 20;
+    unsigned nt = std::min<unsigned>(8, std::max(1u, std::thread::hardware_concurrency()));
+    if (bytes < 2 * kMin) nt = 1;
+    if (nt == 1) return std::memcmp(a, b, bytes) == 0;
+    std::vector<std::thread> th;
+    std::vector<int> diff(nt, 0);
+    const size_t chunk = (bytes + nt - 1) / nt;
+    for (unsigned t = 0; t < nt; ++t) {
+        const size_t lo = std::min(bytes, t * chunk), hi = std::min(bytes, lo + chunk);
+        th.emplace_back([=, &diff]() { diff[t] = std::memcmp((const char*)a + lo, (const char*)b + lo, hi - lo) != 0; });
+    }
+    for (auto& x : th) x.join();
+    for (int d : diff) if (d) return false;
+    return true;
+}
+
 bool same_csc_pattern(opmgpu_handle h, int N, const opmgpu_csc* b, bool full)
 {
     if (!h->have_pattern || h->csc_colptr.size() != 9 || h->N != N || h->csc_full_pattern != full) return false;
     for (int q = 0; q < 9; ++q) {
         if ((int)h->csc_colptr[q].size() != N + 1) return false;
-        if (std::memcmp(h->csc_colptr[q].data(), b[q].colptr, sizeof(int) * ((size_t)N + 1))) return false;
+        if (!equal_parallel(h->csc_colptr[q].data(), b[q].colptr, sizeof(int) * ((size_t)N + 1))) return false;
         const size_t nnz = (size_t)b[q].colptr[N];
         if (h->csc_rowidx[q].size() != nnz) return false;
-        if (nnz && std::memcmp(h->csc_rowidx[q].data(), b[q].rowidx, sizeof(int) * nnz)) return false;
+        if (nnz && !equal_parallel(h->csc_rowidx[q].data(), b[q].rowidx, sizeof(int) * nnz)) return false;
     }
     return true;
 }

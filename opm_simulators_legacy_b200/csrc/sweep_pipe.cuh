@@ -339,7 +339,11 @@ ilu0_sweep_pipe_kernel(PipeDev pg, const double* __restrict__ rhs_perm, double* 
         double* ring = dep + kWindowRows * 3;
         int e = 0;
         unsigned spins = 0;
+        long long polls = 0;
+        const bool htr = pg.trace && blockIdx.x == pg.trace_cta && lane == 0;
+        if (htr) pg.trace[509 * 16 + 8] = clock64();
         while (e < total) {
+            ++polls;
             const int limit = min(total, ctl->ext_consumed + kExtRing);
             long long a[3][3];
             unsigned m[3];
@@ -373,6 +377,7 @@ ilu0_sweep_pipe_kernel(PipeDev pg, const double* __restrict__ rhs_perm, double* 
                 }
                 __syncwarp();
                 __threadfence_block();
+                if (htr && e == 0) { pg.trace[509 * 16 + 9] = clock64(); pg.trace[509 * 16 + 10] = polls; pg.trace[509 * 16 + 11] = n; }
                 e += n;
                 if (lane == 0) ctl->ext_ready = e;
                 spins = 0;
