@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <map>
 #include <numeric>
@@ -56,20 +57,23 @@ void infer_grid(int N, const int* rowptr, const int* colidx, int& nx, int& ny, i
     nx = gx; ny = gy; nz = gz;
 }
 
-void choose_tiling(int nx, int ny, int P, int& pa, int& pb)
+void choose_tiling(int nx, int ny, int nz, int P, int& pa, int& pb)
 {
-    long long best = -(1LL << 60);
-    double best_sq = 0;
+    // Cost model of one sweep (measured on B200, profiles/r01_summary.md): the critical path
+    // runs through nx+ny+nz-2 levels and crosses pa+pb-2 tile boundaries, each a store -> poll
+    // round trip through L2; every CTA also has to stream its own tile from HBM at 1/P of the
+    // bandwidth.  A tile level wider than one pass (kLeanStepRows rows) costs extra passes.
+    constexpr double kCrossUs = 2.5, kLevelUs = 0.4, kRowUs = 0.007;
+    double best = 1e300;
     pa = pb = 1;
-    for (int a = 1; a <= std::min(nx, P); ++a) {
-        const int b = std::min(ny, P / a);
-        if (b < 1) break;
-        long long cnt = (long long)a * b;
-        // a level of a tile has at most ceil(nx/a)*ceil(ny/b) rows: keep it within one pass
-        if ((long long)((nx + a - 1) / a) * ((ny + b - 1) / b) > kLeanStepRows) cnt -= 1000000;
-        const double sq = std::fabs(std::log((double(nx) / a) / (double(ny) / b)));
-        if (cnt > best || (cnt == best && sq < best_sq)) { best = cnt; best_sq = sq; pa = a; pb = b; }
-    }
+    for (int a = 1; a <= std::min(nx, P); ++a)
+        for (int b = 1; b <= std::min(ny, P / a); ++b) {
+            const int wa = (nx + a - 1) / a, wb = (ny + b - 1) / b;
+            const int passes = (wa * wb + kLeanStepRows - 1) / kLeanStepRows;
+            double t = (a + b - 2) * kCrossUs + (double)(nx + ny + nz - 2) * kLevelUs * passes + (double)wa * wb * nz * kRowUs;
+            if (passes > 1) t *= 1.25;          // the general kernel variant is slower than the lean one
+            if (t < best) { best = t; pa = a; pb = b; }
+        }
 }
 
 void build_program(int N, const int* rowptr, const int* colidx, const std::vector<int>& level,
@@ -488,7 +492,12 @@ void analyse_pattern(int N, const int* rowptr, const int* colidx, int P, Pattern
     if (P < 1) P = 1;
     if (nx > 0 && (long long)nx * ny >= 4) {
         int pa, pb;
-        choose_tiling(nx, ny, P, pa, pb);
+        choose_tiling(nx, ny, nz, P, pa, pb);
+        if (const char* e = std::getenv("OPMGPU_TILING")) {       // experiments: "AxB"
+            int a = 0, b = 0;
+            if (std::sscanf(e, "%dx%d", &a, &b) == 2 && a >= 1 && b >= 1 && a * b <= P && a <= nx && b <= ny) { pa = a; pb = b; }
+        }
+        if (std::getenv("OPMGPU_DEBUG")) std::fprintf(stderr, "[opmgpu] sweep tiling %d x %d column tiles\n", pa, pb);
         for (int r = 0; r < N; ++r) {
             const int i = r % nx, j = (r / nx) % ny;
             const int a = (int)((long long)i * pa / nx), b = (int)((long long)j * pb / ny);

@@ -82,7 +82,7 @@ constexpr int kDepZeroSlot = kWindowRows + kExtRing;
 constexpr int kMaxStepRows = 240;
 constexpr int kMaxStepBytes = 64 * 1024;
 constexpr int kMaxStepExt = kExtRing - 96;
-constexpr int kLeanStepRows = 80;         // rows one pass of the compute warps covers
+constexpr int kLeanStepRows = 96;         // rows one pass of the compute warps covers (sweep_pipe.cuh: kPipeRowsPerPass)
 
 struct PipeProgram {
     bool valid = false;

@@ -140,6 +140,8 @@ struct opmgpu_solver {
     bool use_pipe = false, force_simple = false, factor_by_levels = false, spmv_tma = true;
     int trace_cta = -1;
     DevArr<long long> d_trace;
+    int gtrace_steps = 0;          // > 0: all-CTA %globaltimer trace of the next apply (debug)
+    DevArr<long long> d_gtrace;
     int max_smem_optin = 0;
 
     // values and factors
@@ -307,6 +309,7 @@ int upload_pipe(opmgpu_handle h, const PipeProgram& p, PipeDevMem& d)
     const size_t per_stage = (size_t)d.stage_bytes + d.rhs_bytes;
     int S = (int)(((size_t)h->max_smem_optin - fixed) / per_stage);
     d.nstages = std::min(S, kPipeMaxStages);
+    if (const char* e = std::getenv("OPMGPU_PIPE_STAGES")) d.nstages = std::max(kPipeGroups, std::min(d.nstages, std::atoi(e)));
     d.smem = pipe_smem_bytes(d.nstages, d.stage_bytes, d.rhs_bytes);
     return 0;
 }
@@ -318,7 +321,7 @@ PipeDev pipe_dev(const PipeDevMem& d)
     p.step_rhs_row = d.step_rhs_row.p; p.step_rhs_bytes = d.step_rhs_bytes.p;
     p.cta_ext_base = d.cta_ext_base.p; p.ext = d.ext.p;
     p.stage_bytes = d.stage_bytes; p.rhs_bytes = d.rhs_bytes; p.nstages = d.nstages;
-    p.trace = nullptr; p.trace_cta = -1;
+    p.trace = nullptr; p.trace_cta = -1; p.gtrace = nullptr; p.gtrace_steps = 0;
     return p;
 }
 
@@ -589,6 +592,7 @@ int apply_precond(opmgpu_handle h, double w, const double* d, double* v)
         {
             PipeDev pg = pipe_dev(h->pipeL);
             if (h->trace_cta >= 0 && h->d_trace.p) { pg.trace = h->d_trace.p; pg.trace_cta = h->trace_cta; }
+            if (h->gtrace_steps > 0) { pg.gtrace = h->d_gtrace.p; pg.gtrace_steps = h->gtrace_steps; }
             const double* rhs = h->pipeL.rhs_perm.p; double* work = h->d_yL.p; double* hand = h->pipeU.rhs_perm.p;
             double* out = nullptr; int* err = h->d_err.p;
             void* args[] = {&pg, &rhs, &work, &hand, &out, &w, (void*)&scale, &err};
@@ -597,6 +601,7 @@ int apply_precond(opmgpu_handle h, double w, const double* d, double* v)
         {
             PipeDev pg = pipe_dev(h->pipeU);
             if (h->trace_cta >= 0 && h->d_trace.p) { pg.trace = h->d_trace.p + 512 * 16; pg.trace_cta = h->trace_cta; }
+            if (h->gtrace_steps > 0) { pg.gtrace = h->d_gtrace.p + (size_t)h->pipeL.P * (h->gtrace_steps * 8 + 2048); pg.gtrace_steps = h->gtrace_steps; }
             const double* rhs = h->pipeU.rhs_perm.p; double* work = h->d_vU.p; double* hand = nullptr;
             double* out = v; int* err = h->d_err.p;
             void* args[] = {&pg, &rhs, &work, &hand, &out, &w, (void*)&scale, &err};
@@ -1218,6 +1223,28 @@ int opmgpu_debug_trace_apply(opmgpu_handle h, int cta, double w, const double* d
     h->trace_cta = -1;
     if (rc) return rc;
     CK(cudaMemcpyAsync(out, h->d_trace.p, sizeof(long long) * 2 * 512 * 16, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return OPMGPU_OK;
+}
+
+// Debug (not in the public header): %globaltimer stamps (ns) of every CTA of the next pipelined
+// apply.  Per sweep: out[P][steps][8], per step {record landed, bar.sync passed, pushed inputs
+// ready, chain done, ext_end, rows}; the last step slot holds {kernel entry, helper's first
+// delivery, its polls}; then the helper's deliveries [P][1024][2] = {time, polls<<32 | ext_ready}.
+int opmgpu_debug_gtrace_apply(opmgpu_handle h, int steps, double w, const double* d_dev, double* v_dev, long long* out, int* P_out)
+{
+    if (!h || !h->have_factors || !h->use_pipe || steps < 2) return OPMGPU_BAD_ARGUMENT;
+    CK(cudaSetDevice(h->device));
+    const size_t n = (size_t)(h->pipeL.P + h->pipeU.P) * (steps * 8 + 2048);
+    if (P_out) { P_out[0] = h->pipeL.P; P_out[1] = h->pipeU.P; }
+    if (!out) return OPMGPU_OK;
+    CK(h->d_gtrace.ensure(n));
+    CK(cudaMemsetAsync(h->d_gtrace.p, 0, sizeof(long long) * n, h->stream));
+    h->gtrace_steps = steps;
+    int rc = apply_precond(h, w, d_dev, v_dev);
+    h->gtrace_steps = 0;
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out, h->d_gtrace.p, sizeof(long long) * n, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return OPMGPU_OK;
 }

@@ -29,8 +29,8 @@
 // step s, the other has already pulled the static data of step s+1 into registers and waits
 // on a named barrier; the global stores of step s are issued after the hand-over.
 //
-// Warp roles: warp 0 = TMA producer, warp 1 = pushed-result helper, warps 2..9 and 10..17 =
-// the two compute groups (one thread per block row and component).  Every wait is bounded;
+// Warp roles: warp 0 = TMA producer, warps 1..kPipeHelpers = pushed-result helpers, then kPipeGroups compute
+// groups of kPipeComputeWarps warps (one thread per block row).  Every wait is bounded;
 // on expiry the kernel raises *err and all roles drain (barrier hand-shakes keep running).
 #pragma once
 #include <cuda_runtime.h>
@@ -40,9 +40,12 @@
 
 namespace opmgpu {
 
-constexpr int kPipeComputeWarps = 8;
-constexpr int kPipeThreads = 32 * (2 + 2 * kPipeComputeWarps);     // two ping-pong compute groups
-constexpr int kPipeRowsPerPass = kPipeComputeWarps * 10;
+constexpr int kPipeGroups = 3;                                     // compute groups taking turns
+constexpr int kPipeComputeWarps = 3;                               // warps per group, one thread per block row
+constexpr int kPipeHelpers = 1;                                    // warps polling for pushed results
+constexpr int kPipeThreads = 32 * (1 + kPipeHelpers + kPipeGroups * kPipeComputeWarps);
+constexpr int kPipeRowsPerPass = kPipeComputeWarps * 32;
+static_assert(kPipeRowsPerPass == kLeanStepRows, "analysis.hpp sizes lean steps for one pass");
 constexpr int kPipeMaxStages = 8;
 constexpr unsigned kPipeSpinLimit = 1u << 21;
 constexpr int kPipeDepBytes = ((kDepZeroSlot + 1) * 24 + 15) / 16 * 16;
@@ -61,7 +64,13 @@ struct PipeDev {
     int nstages;
     long long* trace;            // optional (debug): per-step clock64 stamps of CTA trace_cta
     int trace_cta;
+    long long* gtrace;           // optional (debug): %globaltimer stamps of every CTA, [cta][gtrace_steps][8], then helper deliveries [cta][512][4]
+    int gtrace_steps;
 };
+__device__ __forceinline__ long long pipe_gtime() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+// timer read that cannot issue before `dep` is available (stamps after barriers / loads / chains)
+__device__ __forceinline__ long long pipe_gtime_after(int dep) { long long t; asm volatile("mov.u64 %0, %globaltimer; // %1" : "=l"(t) : "r"(dep)); return t; }
+__device__ __forceinline__ long long pipe_clock_after(int dep) { long long t; asm volatile("mov.u64 %0, %clock64; // %1" : "=l"(t) : "r"(dep)); return t; }
 
 struct PipeCtl {
     unsigned long long full[kPipeMaxStages];    // record + rhs landed (TMA complete_tx)
@@ -149,38 +158,59 @@ __device__ __forceinline__ bool pipe_wait_ext(PipeCtl* ctl, int ext_end, int* er
 }
 
 // ---- compute-warp helpers --------------------------------------------------------------------
-// Everything about a thread's (row r, component c; slot j = 3r + c) in a step that does not
-// depend on earlier results; loaded from the landed stage one step ahead.
+__device__ __forceinline__ double lds_f64(uint32_t a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+
+#ifndef OPMGPU_PUSH_MODE
+#define OPMGPU_PUSH_MODE 0
+#endif
+__device__ __forceinline__ void push_f64(double* p, double v)
+{
+#if OPMGPU_PUSH_MODE == 0
+    __stcg(p, v);
+#elif OPMGPU_PUSH_MODE == 1
+    atomicExch(reinterpret_cast<unsigned long long*>(p), (unsigned long long)__double_as_longlong(v));
+#else
+    asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+#endif
+}
+
+// Everything about a thread's block row r of a step that does not depend on earlier results;
+// loaded from the landed stage into registers one step ahead.  One thread owns the whole row
+// (all three components), so the chain needs no shuffles and its nine dependency loads are
+// issued once per row, not once per component.
 template <bool UPPER>
 struct StepPre {
     int n, qbase, ext_end, ext_cnt;
-    int4 ri0, ri1;              // rowinfo, dep0, dep1, dep2 | upos, push0, push1, -
+    int4 ri0, ri1;              // rowinfo, dep0, dep1, dep2 | upos, push0, push1, own window slot
     bool on;
-    double rhs;
-    double cf[9];
-    double dv[3];
+    double rhs[3];
+    double cf[27];              // cf[c*9 + k*3 + e]
+    double dv[9];               // dv[c*3 + e] (upper)
 
     // stage = rhs area followed by the record
-    __device__ __forceinline__ void load(const unsigned char* stage, int rhs_bytes, int r, int j, bool lane_on)
+    __device__ __forceinline__ void load(const unsigned char* stage, int rhs_bytes, int r, bool lane_on)
     {
         const unsigned char* rec = stage + rhs_bytes;
         const int4 h0 = *reinterpret_cast<const int4*>(rec);
         n = h0.x; qbase = h0.y; ext_end = h0.z; ext_cnt = h0.w;
         on = lane_on && r < n;
         if (on) {
-            const double* cfp = reinterpret_cast<const double*>(rec + 32) + j * 9;
+            const double* cfp = reinterpret_cast<const double*>(rec + 32) + r * 27;
 #pragma unroll
-            for (int q = 0; q < 9; ++q) cf[q] = cfp[q];
+            for (int q = 0; q < 27; ++q) cf[q] = cfp[q];
             const int T = 3 * n;
             size_t off = 32 + (size_t)T * 72;
             if (UPPER) {
-                const double* dp = reinterpret_cast<const double*>(rec + off) + j * 3;
-                dv[0] = dp[0]; dv[1] = dp[1]; dv[2] = dp[2];
+                const double* dp = reinterpret_cast<const double*>(rec + off) + r * 9;
+#pragma unroll
+                for (int q = 0; q < 9; ++q) dv[q] = dp[q];
                 off += (size_t)T * 24;
             }
             const int4* rip = reinterpret_cast<const int4*>(rec + ((off + 15) & ~(size_t)15)) + 2 * r;
             ri0 = rip[0]; ri1 = rip[1];
-            rhs = reinterpret_cast<const double*>(stage)[j];
+            const double* rp = reinterpret_cast<const double*>(stage) + 3 * r;
+            rhs[0] = rp[0]; rhs[1] = rp[1]; rhs[2] = rp[2];
         }
     }
 };
@@ -191,8 +221,8 @@ __device__ __forceinline__ const double* dep_ptr(int code, const double* dep, co
 }
 
 // blocks beyond the three held in registers (rows with many couplings, e.g. well cells)
-__device__ __noinline__ double sweep_tail_blocks(const unsigned char* rec, int r, int c, const double* dep,
-                                                 const double* work, double acc)
+__device__ __noinline__ void sweep_tail_blocks(const unsigned char* rec, int r, const double* dep,
+                                               const double* work, double (&acc)[3])
 {
     const int* hdr = reinterpret_cast<const int*>(rec);
     const int n = hdr[0];
@@ -202,38 +232,44 @@ __device__ __noinline__ double sweep_tail_blocks(const unsigned char* rec, int r
     const double* tail_vals = reinterpret_cast<const double*>(rec + (size_t)hdr[6] * 8);
     for (int t = r ? tail_end[r - 1] : 0; t < tail_end[r]; ++t) {
         const double* yp = dep_ptr(tail_dep[t], dep, work);
-        const double* ap = tail_vals + (size_t)t * 9 + c * 3;
-        acc = fma(-ap[0], yp[0], acc);
-        acc = fma(-ap[1], yp[1], acc);
-        acc = fma(-ap[2], yp[2], acc);
+        const double y0 = yp[0], y1 = yp[1], y2 = yp[2];
+        const double* ap = tail_vals + (size_t)t * 9;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            acc[c] = fma(-ap[c * 3 + 0], y0, acc[c]);
+            acc[c] = fma(-ap[c * 3 + 1], y1, acc[c]);
+            acc[c] = fma(-ap[c * 3 + 2], y2, acc[c]);
+        }
     }
-    return acc;
 }
 // pushes beyond the two held in registers
-__device__ __noinline__ void sweep_extra_pushes(const unsigned char* rec, int r, int c, double* ext, double acc)
+__device__ __noinline__ void sweep_extra_pushes(const unsigned char* rec, int r, double* ext, const double (&acc)[3])
 {
     const int* hdr = reinterpret_cast<const int*>(rec);
     const int n = hdr[0];
     const int* lists = reinterpret_cast<const int*>(rec + (size_t)hdr[5] * 8);
     const int* xpush_end = lists + n;
     const int* xpush_slot = lists + 2 * n + hdr[4];
-    for (int t = r ? xpush_end[r - 1] : 0; t < xpush_end[r]; ++t) __stcg(ext + (size_t)xpush_slot[t] * 3 + c, acc);
+    for (int t = r ? xpush_end[r - 1] : 0; t < xpush_end[r]; ++t) {
+        double* sl = ext + (size_t)xpush_slot[t] * 3;
+        __stcg(sl, acc[0]); __stcg(sl + 1, acc[1]); __stcg(sl + 2, acc[2]);
+    }
 }
 
-// one (row, component), critical part: dependency loads, FMA chain, Dinv (upper), window store
+// one block row, critical part: dependency loads, three 9-FMA chains in the reference's order
+// (bit parity), Dinv (upper), window store, pushes to other CTAs
 template <bool UPPER, bool LEAN>
-__device__ __forceinline__ double sweep_row_chain(const StepPre<UPPER>& p, const unsigned char* rec, int r, int c, int rl,
-                                                  double* dep, const double* work)
+__device__ __forceinline__ void sweep_row_chain(const StepPre<UPPER>& p, const unsigned char* rec, int r,
+                                                double* dep, uint32_t dep_s, const double* work, double* ext, double (&acc)[3])
 {
-    double acc = 0.0;
+    acc[0] = acc[1] = acc[2] = 0.0;
     if (p.on) {
-        acc = p.rhs;
         double y[9];
         if (LEAN || (p.ri0.y | p.ri0.z | p.ri0.w) >= 0) {    // all three in shared memory (the common case)
-            const double* y0 = dep + p.ri0.y; const double* y1 = dep + p.ri0.z; const double* y2 = dep + p.ri0.w;
-            y[0] = y0[0]; y[1] = y0[1]; y[2] = y0[2];
-            y[3] = y1[0]; y[4] = y1[1]; y[5] = y1[2];
-            y[6] = y2[0]; y[7] = y2[1]; y[8] = y2[2];
+            const uint32_t a0 = dep_s + 8u * (uint32_t)p.ri0.y, a1 = dep_s + 8u * (uint32_t)p.ri0.z, a2 = dep_s + 8u * (uint32_t)p.ri0.w;
+            y[0] = lds_f64(a0); y[1] = lds_f64(a0 + 8); y[2] = lds_f64(a0 + 16);
+            y[3] = lds_f64(a1); y[4] = lds_f64(a1 + 8); y[5] = lds_f64(a1 + 16);
+            y[6] = lds_f64(a2); y[7] = lds_f64(a2 + 8); y[8] = lds_f64(a2 + 16);
         } else {
             const double* y0 = dep_ptr(p.ri0.y, dep, work); const double* y1 = dep_ptr(p.ri0.z, dep, work);
             const double* y2 = dep_ptr(p.ri0.w, dep, work);
@@ -241,53 +277,66 @@ __device__ __forceinline__ double sweep_row_chain(const StepPre<UPPER>& p, const
             y[3] = y1[0]; y[4] = y1[1]; y[5] = y1[2];
             y[6] = y2[0]; y[7] = y2[1]; y[8] = y2[2];
         }
+        acc[0] = p.rhs[0]; acc[1] = p.rhs[1]; acc[2] = p.rhs[2];
 #pragma unroll
-        for (int q = 0; q < 9; ++q) acc = fma(-p.cf[q], y[q], acc);
-        if (!LEAN && (p.ri0.x & kRowSlow)) acc = sweep_tail_blocks(rec, r, c, dep, work, acc);
-    }
-    if (UPPER) {
-        // v = Dinv * r needs the whole row vector: exchange inside the warp
-        const int base = rl * 3;
-        const double r0 = __shfl_sync(0xffffffffu, acc, base);
-        const double r1 = __shfl_sync(0xffffffffu, acc, base + 1);
-        const double r2 = __shfl_sync(0xffffffffu, acc, base + 2);
-        if (p.on) {
-            double v = 0.0;
-            v = fma(p.dv[0], r0, v); v = fma(p.dv[1], r1, v); v = fma(p.dv[2], r2, v);
-            acc = v;
+        for (int q = 0; q < 9; ++q) {
+            acc[0] = fma(-p.cf[q], y[q], acc[0]);
+            acc[1] = fma(-p.cf[9 + q], y[q], acc[1]);
+            acc[2] = fma(-p.cf[18 + q], y[q], acc[2]);
         }
+        if (!LEAN && (p.ri0.x & kRowSlow)) sweep_tail_blocks(rec, r, dep, work, acc);
+        if (UPPER) {
+            double v[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                double t = 0.0;
+                t = fma(p.dv[c * 3 + 0], acc[0], t); t = fma(p.dv[c * 3 + 1], acc[1], t); t = fma(p.dv[c * 3 + 2], acc[2], t);
+                v[c] = t;
+            }
+            acc[0] = v[0]; acc[1] = v[1]; acc[2] = v[2];
+        }
+        const uint32_t w = dep_s + 8u * (uint32_t)p.ri1.w;
+        sts_f64(w, acc[0]); sts_f64(w + 8, acc[1]); sts_f64(w + 16, acc[2]);
+        // other CTAs wait for these: push before anything else
+        if (p.ri1.y >= 0) { double* sl = ext + (size_t)p.ri1.y * 3; push_f64(sl, acc[0]); push_f64(sl + 1, acc[1]); push_f64(sl + 2, acc[2]); }
+        if (p.ri1.z >= 0) { double* sl = ext + (size_t)p.ri1.z * 3; push_f64(sl, acc[0]); push_f64(sl + 1, acc[1]); push_f64(sl + 2, acc[2]); }
+        if (!LEAN && (p.ri0.x & kRowSlow)) sweep_extra_pushes(rec, r, ext, acc);
     }
-    if (p.on) dep[p.ri1.w + c] = acc;
-    return acc;
 }
-// ... and the part nobody inside the CTA waits for: results to HBM, pushes to other CTAs
+// ... and the part nobody waits for: results to HBM
 template <bool UPPER, bool LEAN>
-__device__ __forceinline__ void sweep_row_stores(const StepPre<UPPER>& p, const unsigned char* rec, int r, int c, double acc,
-                                                 double* work, double* hand_off, double* out, double* ext, double w, int scale)
+__device__ __forceinline__ void sweep_row_stores(const StepPre<UPPER>& p, const double (&acc)[3],
+                                                 double* work, double* hand_off, double* out, double w, int scale)
 {
     if (p.on) {
         const int row = p.ri0.x & kRowMask;
-        if (p.ri1.y >= 0) __stcg(ext + (size_t)p.ri1.y * 3 + c, acc);
-        if (p.ri1.z >= 0) __stcg(ext + (size_t)p.ri1.z * 3 + c, acc);
-        if (!LEAN && (p.ri0.x & kRowSlow)) sweep_extra_pushes(rec, r, c, ext, acc);
-        if (UPPER) out[(size_t)row * 3 + c] = scale ? acc * w : acc;
-        else hand_off[(size_t)p.ri1.x * 3 + c] = acc;
-        if (!LEAN && (p.ri0.x & kRowWriteGlobal)) work[(size_t)row * 3 + c] = acc;
+        if (UPPER) {
+            double* o = out + (size_t)row * 3;
+            o[0] = scale ? acc[0] * w : acc[0]; o[1] = scale ? acc[1] * w : acc[1]; o[2] = scale ? acc[2] * w : acc[2];
+        } else {
+            double* o = hand_off + (size_t)p.ri1.x * 3;
+            o[0] = acc[0]; o[1] = acc[1]; o[2] = acc[2];
+        }
+        if (!LEAN && (p.ri0.x & kRowWriteGlobal)) {
+            double* o = work + (size_t)row * 3;
+            o[0] = acc[0]; o[1] = acc[1]; o[2] = acc[2];
+        }
     }
 }
 
-// rows [80, n) of a step wider than one pass over the compute warps
+// rows [kPipeRowsPerPass, n) of a step wider than one pass over the compute warps
 template <bool UPPER>
-__device__ __noinline__ void sweep_extra_rows(const unsigned char* stage, int rhs_bytes, int n, int r_first, int c, int rl,
-                                              bool lane_on, double* dep, double* work, double* hand_off,
+__device__ __noinline__ void sweep_extra_rows(const unsigned char* stage, int rhs_bytes, int n, int r_first,
+                                              double* dep, uint32_t dep_s, double* work, double* hand_off,
                                               double* out, double* ext, double w, int scale)
 {
     for (int rbase = kPipeRowsPerPass; rbase < n; rbase += kPipeRowsPerPass) {
         const int r = rbase + r_first;
         StepPre<UPPER> p;
-        p.load(stage, rhs_bytes, r, 3 * r + c, lane_on);
-        const double acc = sweep_row_chain<UPPER, false>(p, stage + rhs_bytes, r, c, rl, dep, work);
-        sweep_row_stores<UPPER, false>(p, stage + rhs_bytes, r, c, acc, work, hand_off, out, ext, w, scale);
+        p.load(stage, rhs_bytes, r, true);
+        double acc[3];
+        sweep_row_chain<UPPER, false>(p, stage + rhs_bytes, r, dep, dep_s, work, ext, acc);
+        sweep_row_stores<UPPER, false>(p, acc, work, hand_off, out, w, scale);
     }
 }
 
@@ -307,9 +356,12 @@ ilu0_sweep_pipe_kernel(PipeDev pg, const double* __restrict__ rhs_perm, double* 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int s0 = pg.cta_step_ptr[blockIdx.x];
     const int nsteps = pg.cta_step_ptr[blockIdx.x + 1] - s0;
+    long long* gtr = pg.gtrace ? pg.gtrace + (size_t)blockIdx.x * pg.gtrace_steps * 8 : nullptr;
+    long long* hlog = pg.gtrace ? pg.gtrace + (size_t)gridDim.x * pg.gtrace_steps * 8 + (size_t)blockIdx.x * 2048 : nullptr;
+    if (gtr && tid == 0) gtr[(pg.gtrace_steps - 1) * 8 + 0] = pipe_gtime();
 
     if (tid == 0) {
-        for (int i = 0; i < S; ++i) { mbar_init(&ctl->full[i], 1); mbar_init(&ctl->empty[i], 1); }
+        for (int i = 0; i < S; ++i) { mbar_init(&ctl->full[i], 1); mbar_init(&ctl->empty[i], kPipeComputeWarps); }
         ctl->ext_consumed = 0; ctl->ext_ready = 0; ctl->abort_flag = 0;
         dep[kDepZeroSlot * 3] = 0.0; dep[kDepZeroSlot * 3 + 1] = 0.0; dep[kDepZeroSlot * 3 + 2] = 0.0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -331,19 +383,40 @@ ilu0_sweep_pipe_kernel(PipeDev pg, const double* __restrict__ rhs_perm, double* 
                 tma_bulk_g2s(stage, rhs_perm + (size_t)rrow * 3, rbytes, &ctl->full[st]);
             }
         }
-    } else if (warp == 1) {
-        // ------------------------------------------------ pushed-result helper
-        // Polls up to 96 slots per round trip, in consumption order; delivers the valid prefix.
+    } else if (warp <= kPipeHelpers) {
+        // ------------------------------------------------ pushed-result helpers
+        // A poll reads the next 96 slots in consumption order and delivers the valid prefix:
+        // values into the shared-memory ring, then ext_ready, then the slots are re-armed.  One
+        // poll is a full L2 round trip (1300+ cycles while the record stream is running), so
+        // kPipeHelpers warps poll the same window out of phase.  They do not coordinate beyond
+        // ext_ready (atomicMax): two helpers may deliver the same entry, which writes the same
+        // value to the same ring position twice.
+        const int hid = warp - 1;
         const long long base = pg.cta_ext_base[blockIdx.x];
         const int total = (int)(pg.cta_ext_base[blockIdx.x + 1] - base);
+        const long long* slots = reinterpret_cast<const long long*>(pg.ext) + (size_t)base * 3;
         double* ring = dep + kWindowRows * 3;
-        int e = 0;
+        int* ext_ready = const_cast<int*>(&ctl->ext_ready);
         unsigned spins = 0;
         long long polls = 0;
-        const bool htr = pg.trace && blockIdx.x == pg.trace_cta && lane == 0;
-        if (htr) pg.trace[509 * 16 + 8] = clock64();
-        while (e < total) {
+        int ndeliv = 0;
+        // The slots were last touched a whole sweep ago and may have left L2: keep the lines
+        // ahead of the poll window warm (helper 0).
+        constexpr int kPfAhead = 768;
+        int pf = 0;                            // slots [0, pf) have been prefetched
+        if (hid > 0) __nanosleep(300 * hid);
+        for (;;) {
+            const int e = ctl->ext_ready;
+            if (e >= total) break;
             ++polls;
+            if (hid == 0 && pf < min(total, e + kPfAhead)) {               // one 128-byte line per lane
+                const int want = min(total, e + kPfAhead);
+                const char* p0 = reinterpret_cast<const char*>(slots + (size_t)pf * 3);
+                const char* p1 = reinterpret_cast<const char*>(slots + (size_t)want * 3);
+                const char* line = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(p0) & ~(uintptr_t)127) + (size_t)lane * 128;
+                if (line < p1) asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
+                pf = min(want, pf + (32 * 128) / 24);
+            }
             const int limit = min(total, ctl->ext_consumed + kExtRing);
             long long a[3][3];
             unsigned m[3];
@@ -352,8 +425,10 @@ ilu0_sweep_pipe_kernel(PipeDev pg, const double* __restrict__ rhs_perm, double* 
                 const int idx = e + u * 32 + lane;
                 a[u][0] = a[u][1] = a[u][2] = -1;
                 if (idx < limit) {
-                    const volatile long long* sl = reinterpret_cast<const volatile long long*>(pg.ext) + (size_t)(base + idx) * 3;
-                    a[u][0] = sl[0]; a[u][1] = sl[1]; a[u][2] = sl[2];
+                    const long long* sl = slots + (size_t)idx * 3;
+                    asm volatile("ld.relaxed.gpu.global.s64 %0, [%1];" : "=l"(a[u][0]) : "l"(sl) : "memory");
+                    asm volatile("ld.relaxed.gpu.global.s64 %0, [%1];" : "=l"(a[u][1]) : "l"(sl + 1) : "memory");
+                    asm volatile("ld.relaxed.gpu.global.s64 %0, [%1];" : "=l"(a[u][2]) : "l"(sl + 2) : "memory");
                 }
             }
 #pragma unroll
@@ -364,22 +439,37 @@ ilu0_sweep_pipe_kernel(PipeDev pg, const double* __restrict__ rhs_perm, double* 
             else if (m[1] != 0xffffffffu) n = 32 + __ffs(~m[1]) - 1;
             else if (m[2] != 0xffffffffu) n = 64 + __ffs(~m[2]) - 1;
             else n = 96;
-            if (n > 0) {
+            // another helper may have delivered part of the prefix meanwhile
+            const int e_now = __shfl_sync(0xffffffffu, (int)ctl->ext_ready, 0);
+            if (e + n > e_now) {
 #pragma unroll
                 for (int u = 0; u < 3; ++u) {
                     const int idx = e + u * 32 + lane;
-                    if (u * 32 + lane < n) {
+                    if (idx >= e_now && u * 32 + lane < n) {
                         double* dst = ring + (idx & (kExtRing - 1)) * 3;
                         dst[0] = __longlong_as_double(a[u][0]); dst[1] = __longlong_as_double(a[u][1]); dst[2] = __longlong_as_double(a[u][2]);
-                        long long* sl = reinterpret_cast<long long*>(pg.ext) + (size_t)(base + idx) * 3;
-                        __stcg(sl + 0, -1LL); __stcg(sl + 1, -1LL); __stcg(sl + 2, -1LL);      // re-arm
                     }
                 }
+                // ring data before ext_ready: shared-memory stores of one warp are performed in order
                 __syncwarp();
-                __threadfence_block();
-                if (htr && e == 0) { pg.trace[509 * 16 + 9] = clock64(); pg.trace[509 * 16 + 10] = polls; pg.trace[509 * 16 + 11] = n; }
-                e += n;
-                if (lane == 0) ctl->ext_ready = e;
+                if (lane == 0) atomicMax(ext_ready, e + n);
+                // re-arm the consumed slots (nobody waits for these stores)
+#pragma unroll
+                for (int u = 0; u < 3; ++u) {
+                    const int idx = e + u * 32 + lane;
+                    if (idx >= e_now && u * 32 + lane < n) {
+                        long long* sl = const_cast<long long*>(slots) + (size_t)idx * 3;
+                        __stcg(sl + 0, -1LL); __stcg(sl + 1, -1LL); __stcg(sl + 2, -1LL);
+                    }
+                }
+                if (gtr && lane == 0 && hid == 0) {
+                    if (e_now == 0) { gtr[(pg.gtrace_steps - 1) * 8 + 1] = pipe_gtime(); gtr[(pg.gtrace_steps - 1) * 8 + 2] = polls; }
+                    if (ndeliv < 512) {
+                        hlog[4 * ndeliv] = pipe_gtime(); hlog[4 * ndeliv + 1] = ((long long)polls << 32) | (unsigned)(e + n);
+                        hlog[4 * ndeliv + 2] = 0; hlog[4 * ndeliv + 3] = e + n - e_now;
+                        ++ndeliv;
+                    }
+                }
                 spins = 0;
             } else {
                 ++spins;                                              // n is warp-uniform, so is spins
@@ -389,60 +479,75 @@ ilu0_sweep_pipe_kernel(PipeDev pg, const double* __restrict__ rhs_perm, double* 
             }
         }
     } else {
-        // ------------------------------------------------ compute warps (two ping-pong groups)
-        // lane = 3 * (row % 10) + c, ten rows per warp (lanes 30, 31 idle) so the three
-        // components of a row sit in one warp (shuffles in the upper sweep).  Group g owns the
-        // steps s = g, g+2, ...; it signals "step s done" on named barrier 1+g (bar.arrive)
-        // and waits for "step s-1 done" on barrier 2-g (bar.sync).
+        // ------------------------------------------------ compute warps (kPipeGroups groups in turn)
+        // lane = row of the step (kPipeRowsPerPass rows per pass).  Group g owns the steps
+        // s = g, g+G, ...; it signals "step s done" on named barrier 1+g (bar.arrive) and waits
+        // for "step s-1 done" on the barrier of the group before it (bar.sync).
+        constexpr int G = kPipeGroups;
         constexpr int NPP = 2 * kPipeComputeWarps * 32;
-        const int g = (warp - 2) / kPipeComputeWarps;
-        const int cw = (warp - 2) - g * kPipeComputeWarps;
-        const int rl = lane / 3, c = lane - rl * 3;
-        const bool lane_on = lane < 30;
-        const int r_first = cw * 10 + rl;
-        const int j_first = 3 * r_first + c;
+        const int g = (warp - 1 - kPipeHelpers) / kPipeComputeWarps;
+        const int cw = (warp - 1 - kPipeHelpers) - g * kPipeComputeWarps;
+        const int r_first = cw * 32 + lane;
         const bool elected = cw == 0 && lane == 0;
+        const int bar_prev = 1 + (g + G - 1) % G, bar_own = 1 + g;
+        const uint32_t dep_s = smem_u32(dep);
         bool dead = false;
         int st = g % S;
         unsigned par = (unsigned)((g / S) & 1);
         int st_prev = -1, ext_prev_end = 0;
-        for (int s = g; s < nsteps; s += 2) {
+        for (int s = g; s < nsteps; s += G) {
             const bool tr = pg.trace && blockIdx.x == pg.trace_cta && elected && s < 512;
             const unsigned char* stage = stages + st * stage_stride;
             StepPre<UPPER> p;
             p.n = 0; p.qbase = 0; p.ext_end = 0; p.ext_cnt = 0; p.on = false;
             if (!dead) {
-                if (pipe_wait(&ctl->full[st], par, ctl, err)) p.load(stage, pg.rhs_bytes, r_first, j_first, lane_on);
+                if (pipe_wait(&ctl->full[st], par, ctl, err)) p.load(stage, pg.rhs_bytes, r_first, true);
                 else dead = true;
             }
+            if (LEAN) {             // everything the step needs is in registers now: hand the stage back
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ctl->empty[st]);
+            }
             if (tr) pg.trace[s * 16 + 0] = clock64();
-            if (s > 0) asm volatile("bar.sync %0, %1;" ::"r"(2 - g), "n"(NPP) : "memory");     // step s-1 done
-            if (tr) pg.trace[s * 16 + 1] = clock64() + (ctl->abort_flag == 12345);
+            const bool gt = gtr && elected && s < pg.gtrace_steps - 1;
+            if (gt) gtr[s * 8 + 0] = pipe_gtime();
+            if (s > 0) asm volatile("bar.sync %0, %1;" ::"r"(bar_prev), "n"(NPP) : "memory");     // step s-1 done
+            if (tr) pg.trace[s * 16 + 1] = pipe_clock_after(ctl->abort_flag);
+            if (gt) gtr[s * 8 + 1] = pipe_gtime_after(ctl->abort_flag);
             // pushed inputs of this step staged by the helper warp?  (ring data is written
             // before ext_ready, and shared-memory accesses of a thread are not reordered)
             if (!dead && p.ext_cnt > 0) {
                 if (ctl->ext_ready < p.ext_end && !pipe_wait_ext(ctl, p.ext_end, err)) { dead = true; p.on = false; }
                 asm volatile("" ::: "memory");
             }
-            const double acc = sweep_row_chain<UPPER, LEAN>(p, stage + pg.rhs_bytes, r_first, c, rl, dep, work);
+            if (gt) { gtr[s * 8 + 2] = pipe_gtime_after(ctl->ext_ready); gtr[s * 8 + 4] = p.ext_end; gtr[s * 8 + 5] = p.n; }
+            if (tr) pg.trace[s * 16 + 5] = pipe_clock_after(ctl->ext_ready);
+            double acc[3];
+            sweep_row_chain<UPPER, LEAN>(p, stage + pg.rhs_bytes, r_first, dep, dep_s, work, pg.ext, acc);
             if (!LEAN && p.n > kPipeRowsPerPass)
-                sweep_extra_rows<UPPER>(stage, pg.rhs_bytes, p.n, r_first, c, rl, lane_on, dep, work, hand_off, out, pg.ext, w, scale);
-            if (tr) { pg.trace[s * 16 + 2] = clock64(); pg.trace[s * 16 + 4] = p.n; }
-            asm volatile("bar.arrive %0, %1;" ::"r"(1 + g), "n"(NPP) : "memory");             // step s done
-            // every warp of this group passed the bar.sync of this step, i.e. is done with its
-            // step s-2: release that stage and its pushed-result ring entries
-            if (elected && st_prev >= 0) {
-                ctl->ext_consumed = ext_prev_end;
-                mbar_arrive(&ctl->empty[st_prev]);
+                sweep_extra_rows<UPPER>(stage, pg.rhs_bytes, p.n, r_first, dep, dep_s, work, hand_off, out, pg.ext, w, scale);
+            if (tr) { pg.trace[s * 16 + 2] = pipe_clock_after(__double2hiint(acc[0])); pg.trace[s * 16 + 4] = p.n; }
+            if (gt) gtr[s * 8 + 3] = pipe_gtime_after(__double2hiint(acc[0]));
+            long long rb = 0;           // trace: read the first pushed value back through L2
+            const bool gt_rb = gt && p.on && p.ri1.y >= 0;
+            if (gt_rb) asm volatile("ld.relaxed.gpu.global.s64 %0, [%1];" : "=l"(rb) : "l"(pg.ext + (size_t)p.ri1.y * 3) : "memory");
+            asm volatile("bar.arrive %0, %1;" ::"r"(bar_own), "n"(NPP) : "memory");                // step s done
+            if (!LEAN) {            // tail lists of slow rows are read from the stage during the chain
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ctl->empty[st]);
             }
-            sweep_row_stores<UPPER, LEAN>(p, stage + pg.rhs_bytes, r_first, c, acc, work, hand_off, out, pg.ext, w, scale);
+            // every warp of this group passed the bar.sync of this step, i.e. is done with its
+            // step s-G: release the pushed-result ring entries of that step
+            if (elected && st_prev >= 0) ctl->ext_consumed = ext_prev_end;
+            sweep_row_stores<UPPER, LEAN>(p, acc, work, hand_off, out, w, scale);
+            if (gt_rb) gtr[s * 8 + 6] = pipe_gtime_after((int)rb);
             if (tr) pg.trace[s * 16 + 3] = clock64();
             st_prev = st; ext_prev_end = p.ext_end;
-            st += 2;
+            st += G;
             if (st >= S) { st -= S; par ^= 1u; }
         }
-        // consume the other group's last hand-over so no barrier is left half-arrived
-        if (((nsteps - 1) & 1) != g) asm volatile("bar.sync %0, %1;" ::"r"(2 - g), "n"(NPP) : "memory");
+        // consume the last hand-over addressed to this group so no barrier is left half-arrived
+        if (nsteps > 0 && (nsteps % G) == g) asm volatile("bar.sync %0, %1;" ::"r"(bar_prev), "n"(NPP) : "memory");
     }
 }
 

@@ -1,4 +1,6 @@
-"""Debug: per-step clock64 trace of one CTA of the pipelined ILU0 sweeps."""
+"""Debug: per-step clock64 trace of one CTA of the pipelined ILU0 sweeps.
+Stamps per step: [0] static data in registers, [1] turn barrier passed, [5] pushed inputs ready,
+[2] chain done, [3] stores issued, [4] rows."""
 import ctypes as C
 import os
 import sys
@@ -10,8 +12,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from opm_simulators_legacy_b200.jacobian import synth_blackoil_jacobian  # noqa: E402
 from opm_simulators_legacy_b200.solver import GpuLinearSolver  # noqa: E402
 
+G = 3
 nx, ny, nz = (int(a) for a in sys.argv[1:4])
-ctas = [int(a) for a in sys.argv[4:]] or [0, 70, 143]
+ctas = [int(a) for a in sys.argv[4:]] or [0, 70, 142]
 s = synth_blackoil_jacobian(nx, ny, nz, perm="lognormal")
 g = GpuLinearSolver(0)
 g.set_pattern(s.rowptr.numpy(), s.colidx.numpy())
@@ -31,24 +34,14 @@ for cta in ctas:
     for sw, name in ((0, "L"), (1, "U")):
         t = out[sw]
         n = int((t[:500, 0] > 0).sum())
-        if n < 3:
+        if n < 8:
             print(f"cta {cta} {name}: {n} steps"); continue
-        t0 = t[0, 0]
-        kentry = t[511, 15]
-        print(f"cta {cta} {name}: first step chain done {t[0,2]-kentry} cyc after kernel entry; step 8 done {t[8,2]-kentry}; step 16 done {t[16,2]-kentry}; last {t[n-1,2]-kentry}")
-        wait = (t[:n, 1] - t[:n, 0]); comp = (t[:n, 2] - t[:n, 1]); bar = (t[:n, 3] - t[:n, 2])
-        step = np.diff(t[:n, 0])
-        print(f"cta {cta} {name}: steps {n} total {t[n-1,3]-t0} cyc; per-step median: period {np.median(step):.0f} "
-              f"wait {np.median(wait):.0f} compute {np.median(comp):.0f} barrier {np.median(bar):.0f}; "
-              f"mean wait {wait.mean():.0f} comp {comp.mean():.0f} bar {bar.mean():.0f}")
-        own = t[2:n, 5] - t[:n-2, 3]     # this group's: end of stores (step s-2) -> start of step s
-        print("   ping-pong (median cycles): own loop overhead %d | full-wait+static load %d | barrier wait %d | chain %d | stores %d | step-to-step (same group) %d"
-              % (np.median(own), np.median(t[:n,0]-t[:n,5]), np.median(t[:n,1]-t[:n,0]), np.median(t[:n,2]-t[:n,1]), np.median(t[:n,3]-t[:n,2]), np.median(t[2:n,5]-t[:n-2,5])))
+        med = lambda v: float(np.median(v))
+        print(f"cta {cta} {name}: {n} steps, total {t[n-1,2]-t[0,0]} cycles; median cycles per step: "
+              f"prev chain done -> turn barrier passed {med(t[1:n,1]-t[:n-1,2]):.0f} | barrier -> pushed inputs ok {med(t[1:n,5]-t[1:n,1]):.0f} | "
+              f"chain {med(t[1:n,2]-t[1:n,5]):.0f} | chain done -> chain done {med(np.diff(t[:n,2])):.0f} || off path: stores {med(t[:n,3]-t[:n,2]):.0f} | "
+              f"stores -> next static loaded {med(t[G:n,0]-t[:n-G,3]):.0f} | static loaded -> barrier passed (idle) {med(t[1:n,1]-t[1:n,0]):.0f}")
         idx = list(range(0, n, max(1, n // 12)))
-        print("   step  nrows  enter   wait  comp  bar | bulk_issue-enter  gather_issue-enter")
-        for i in idx:
-            print(f"   {i:4d} {t[i,4]:5d} {t[i,0]-t0:8d} {wait[i]:6d} {comp[i]:5d} {bar[i]:4d} | {t[i,5]-t[i,0]:8d} {t[i,6]-t[i,0]:8d}")
-        print(f"   helper: loop start {t[509,8]-kentry}, first delivery at {t[509,9]-kentry} after {t[509,10]} polls, n={t[509,11]}; kentry {kentry}")
-        print("   raw (rel. kernel entry): step: looptop static_done bar_issued chain_done stores_done")
-        for i in range(0, min(n, 6)):
-            print(f"      {i}: {t[i,5]-kentry} {t[i,0]-kentry} {t[i,1]-kentry} {t[i,2]-kentry} {t[i,3]-kentry}")
+        print("   step rows | prev-done->bar  bar->ext  chain  stores")
+        for i in idx[1:]:
+            print(f"   {i:4d} {t[i,4]:4d} | {t[i,1]-t[i-1,2]:6d} {t[i,5]-t[i,1]:6d} {t[i,2]-t[i,5]:6d} {t[i,3]-t[i,2]:6d}")
