@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <cstdint>
 #include <cstring>
+#include <future>
 #include <string>
 #include <thread>
 #include <vector>
@@ -140,6 +141,7 @@ struct opmgpu_solver {
     bool use_pipe = false, force_simple = false, factor_by_levels = false, spmv_tma = true;
     int trace_cta = -1;
     DevArr<long long> d_trace;
+    std::future<bool> pattern_check;   // CSC front end: full index compare running beside the upload
     int gtrace_steps = 0;          // > 0: all-CTA %globaltimer trace of the next apply (debug)
     DevArr<long long> d_gtrace;
     int max_smem_optin = 0;
@@ -741,6 +743,8 @@ float ev_ms(cudaEvent_t a, cudaEvent_t b)
 }
 
 // factor + BiCGStab on the values/rhs already in place (d_vals, d_r); leaves the result in d_x
+constexpr int kPatternChanged = -1000;     // internal: solve_resident -> CSC front end
+
 int solve_resident(opmgpu_handle h, const opmgpu_params* prm, opmgpu_result* res)
 {
     cudaEventRecord(h->ev[0], h->stream);
@@ -749,6 +753,9 @@ int solve_resident(opmgpu_handle h, const opmgpu_params* prm, opmgpu_result* res
     int rc = factor(h, &badrow);
     h->prof_end();
     cudaEventRecord(h->ev[1], h->stream);
+    // the CSC front end compares the caller's sparsity pattern with the cached one on host
+    // threads while values are uploaded and factorised; the verdict is due before the solve
+    if (h->pattern_check.valid() && !h->pattern_check.get()) return kPatternChanged;
     if (rc) { res->bad_row = badrow; return rc; }
     rc = bicgstab(h, prm, res);
     cudaEventRecord(h->ev[2], h->stream);
@@ -765,7 +772,7 @@ int solve_resident(opmgpu_handle h, const opmgpu_params* prm, opmgpu_result* res
 bool equal_parallel(const void* a, const void* b, size_t bytes)
 {
     const size_t kMin = 4u << 20;
-    unsigned nt = std::min<unsigned>(8, std::max(1u, std::thread::hardware_concurrency()));
+    unsigned nt = std::min<unsigned>(16, std::max(1u, std::thread::hardware_concurrency()));
     if (bytes < 2 * kMin) nt = 1;
     if (nt == 1) return std::memcmp(a, b, bytes) == 0;
     std::vector<std::thread> th;
@@ -777,6 +784,15 @@ bool equal_parallel(const void* a, const void* b, size_t bytes)
     }
     for (auto& x : th) x.join();
     for (int d : diff) if (d) return false;
+    return true;
+}
+
+// O(1) part of the comparison: same sizes, so the cached upload plan cannot overrun the caller's arrays
+bool same_csc_sizes(opmgpu_handle h, int N, const opmgpu_csc* b, bool full)
+{
+    if (!h->have_pattern || h->csc_colptr.size() != 9 || h->N != N || h->csc_full_pattern != full) return false;
+    for (int q = 0; q < 9; ++q)
+        if ((int)h->csc_colptr[q].size() != N + 1 || h->csc_rowidx[q].size() != (size_t)b[q].colptr[N] || b[q].colptr[0] != 0) return false;
     return true;
 }
 
@@ -1092,7 +1108,17 @@ int opmgpu_solve_from_csc_blocks(opmgpu_handle h, int N, const opmgpu_csc blocks
     result->bad_row = -1;
     CK(cudaSetDevice(h->device));
     const bool full = params->require_full_sparsity_pattern != 0;
-    if (!same_csc_pattern(h, N, blocks, full)) {
+    if (h->pattern_check.valid()) h->pattern_check.get();
+    // the compare threads read the caller's arrays: never return while they run
+    struct WaitForCheck { opmgpu_handle h; ~WaitForCheck() { if (h->pattern_check.valid()) h->pattern_check.wait(); } } wait_for_check{h};
+    // Same sizes as last time: assume the pattern is unchanged, start uploading and factorising,
+    // and verify the ~290 MB of index arrays on host threads meanwhile (the reference rebuilds
+    // the pattern on every call, NewtonIterationBlackoilInterleaved.cpp:110-194).
+    bool speculative = same_csc_sizes(h, N, blocks, full);
+    if (speculative)
+        h->pattern_check = std::async(std::launch::async, [h, N, blocks, full]() { return same_csc_pattern(h, N, blocks, full); });
+    for (int attempt = 0; attempt < 2; ++attempt) {
+    if (!speculative) {
         cudaEventRecord(h->ev[3], h->stream);
         // pattern = union of the pressure-derivative patterns (all nine when required)
         std::vector<CscView> sel;
@@ -1162,6 +1188,16 @@ int opmgpu_solve_from_csc_blocks(opmgpu_handle h, int N, const opmgpu_csc blocks
     h->d_vals = h->d_vals_own.p;
     h->have_values = true; h->have_factors = false;
     int rc = solve_resident(h, params, result);
+    if (rc == kPatternChanged) {                  // the speculation failed: analyse the new pattern, start over
+        CK(cudaStreamSynchronize(h->stream));
+        speculative = false;
+        continue;
+    }
+    if (h->pattern_check.valid() && !h->pattern_check.get() && speculative) {   // factor() failed before the verdict
+        CK(cudaStreamSynchronize(h->stream));
+        speculative = false;
+        continue;
+    }
     result->ms_h2d = ev_ms(h->ev[3], h->ev[4]);
     result->ms_interleave = ev_ms(h->ev[4], h->ev[5]);
     if (rc == OPMGPU_OK || rc == OPMGPU_NOT_CONVERGED) {
@@ -1174,6 +1210,8 @@ int opmgpu_solve_from_csc_blocks(opmgpu_handle h, int N, const opmgpu_csc blocks
         result->ms_d2h = ev_ms(h->ev[5], h->ev[6]);
     }
     return rc;
+    }
+    return h->bad("sparsity pattern changed during the call");
 }
 
 int opmgpu_num_levels(opmgpu_handle h, int* lower_levels, int* upper_levels)

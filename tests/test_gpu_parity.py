@@ -103,6 +103,22 @@ def test_csc_blocks_path_matches_oracle(gpu_solver, oracle, case):
     assert res2["ms_analysis"] == 0.0 and np.array_equal(dx, dx2)
 
 
+def test_csc_pattern_change_with_equal_sizes_is_detected(gpu_solver, oracle):
+    # 6x5x4 and 5x6x4 grids: same N and the same number of entries in every block, different
+    # pattern.  The front end starts uploading on the cached plan and compares the index arrays
+    # meanwhile; the mismatch must throw that work away and re-analyse.
+    a = synth_blackoil_jacobian(6, 5, 4, perm="lognormal", seed=1)
+    b = synth_blackoil_jacobian(5, 6, 4, perm="lognormal", seed=2)
+    assert a.N == b.N and all(x[2].size == y[2].size for x, y in zip(a.csc_blocks(), b.csc_blocks()))
+    for s in (a, b, a, b):
+        rhs = s.rhs_eqmajor_unscaled.numpy()
+        dx, res = gpu_solver.solve_from_csc_blocks(s.N, s.csc_blocks(), s.matbalscale, rhs)
+        dx_ref, ref = oracle.solve_from_csc_blocks(s.N, s.csc_blocks(), s.matbalscale, rhs)
+        assert res["iterations"] == ref["iterations"] and res["ms_analysis"] > 0.0
+        sc = np.abs(dx_ref.reshape(3, -1)).max(1).repeat(s.N)
+        assert (np.abs(dx - dx_ref) <= 1e-8 * sc).all()
+
+
 def test_general_pattern_with_dense_well_coupling(gpu_solver, oracle):
     rp, ci, v = random_bcrs(700, extra_per_row=3, seed=7, dense_group=12)
     rng = np.random.default_rng(3)
