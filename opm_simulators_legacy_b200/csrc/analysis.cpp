@@ -443,6 +443,158 @@ void build_pipe_program(int N, const int* rowptr, const int* colidx, const std::
     pg.valid = true;
 }
 
+
+// ---- pipelined factorisation program ---------------------------------------------------------
+inline size_t factor_rec_bytes(int n) { return align_up(32 + (size_t)n * (kFRowInts * 4 + kFRowVals * 8), 16); }
+
+void build_factor_pipe_program(int N, const int* rowptr, const int* colidx, const std::vector<int>& diag,
+                               const std::vector<int>& level, const std::vector<int>& owner, int P,
+                               FactorPipeProgram& pg)
+{
+    pg = FactorPipeProgram();
+    pg.P = P;
+    std::vector<int> order(N);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        if (owner[a] != owner[b]) return owner[a] < owner[b];
+        return level[a] < level[b];
+    });
+    // every row simple?  slot of A_ji for every lower block (i,j), -1 when absent
+    std::vector<int> ji_slot(rowptr[N], -1), next(N, 0), npush(N, 0);
+    for (int r = 0; r < N; ++r) {
+        if (diag[r] - rowptr[r] > kFastBlocks) return;
+        for (int k = rowptr[r]; k < diag[r]; ++k) {
+            const int j = colidx[k];
+            for (int kk = diag[j] + 1; kk < rowptr[j + 1]; ++kk) {
+                const int c2 = colidx[kk];
+                if (c2 == r) { ji_slot[k] = kk; continue; }
+                if (std::binary_search(colidx + rowptr[r], colidx + rowptr[r + 1], c2)) return;   // fill off the diagonal
+            }
+            if (owner[j] != owner[r]) { ++next[r]; ++npush[j]; }
+        }
+    }
+    for (int r = 0; r < N; ++r) if (npush[r] > 2) return;
+    // steps = levels of the CTA's tile
+    struct Step { int q0, q1; };
+    std::vector<Step> steps;
+    std::vector<int> qlocal(N, 0), step_end_q(N, 0);
+    pg.cta_step_ptr.assign(P + 1, 0);
+    pg.cta_row_base.assign(P + 1, N);
+    pg.fpos.assign(N, 0);
+    for (int q = 0; q < N; ++q) pg.fpos[order[q]] = q;
+    {
+        int q = 0;
+        for (int c = 0; c < P; ++c) {
+            pg.cta_step_ptr[c] = (int)steps.size();
+            pg.cta_row_base[c] = q;
+            const int cbeg = q;
+            int cur_level = -1, rows = 0, ext = 0;
+            while (q < N && owner[order[q]] == c) {
+                const int r = order[q];
+                if (rows == 0 || level[r] != cur_level) {
+                    if (rows > 0) steps.back().q1 = q;
+                    steps.push_back({q, q});
+                    cur_level = level[r]; rows = ext = 0;
+                }
+                ++rows; ext += next[r];
+                if (rows > kLeanStepRows || ext > kFMaxStepExt) return;
+                qlocal[r] = q - cbeg;
+                ++q;
+            }
+            if (rows > 0) steps.back().q1 = q;
+            for (int sidx = pg.cta_step_ptr[c]; sidx < (int)steps.size(); ++sidx)
+                for (int qq = steps[sidx].q0; qq < steps[sidx].q1; ++qq) step_end_q[order[qq]] = steps[sidx].q1 - cbeg;
+        }
+        pg.cta_step_ptr[P] = (int)steps.size();
+    }
+    for (int r = 0; r < N; ++r)
+        for (int k = rowptr[r]; k < diag[r]; ++k) {
+            const int j = colidx[k];
+            if (owner[j] == owner[r] && qlocal[j] + kFWindow < step_end_q[r]) return;      // pivot left the window
+        }
+    // push slots: ordinals in consumption order per CTA
+    pg.cta_ext_base.assign(P + 1, 0);
+    std::vector<int> push_ptr(N + 1, 0);
+    for (int r = 0; r < N; ++r) push_ptr[r + 1] = push_ptr[r] + npush[r];
+    std::vector<long long> push_slot(push_ptr[N]);
+    std::vector<int> push_fill(push_ptr.begin(), push_ptr.end() - 1);
+    {
+        long long base = 0;
+        int q = 0;
+        for (int c = 0; c < P; ++c) {
+            pg.cta_ext_base[c] = base;
+            long long e = 0;
+            while (q < N && owner[order[q]] == c) {
+                const int r = order[q];
+                for (int k = rowptr[r]; k < diag[r]; ++k) {
+                    const int j = colidx[k];
+                    if (owner[j] != c) { push_slot[push_fill[j]++] = base + e; ++e; }
+                }
+                ++q;
+            }
+            base += e;
+        }
+        pg.cta_ext_base[P] = base;
+        pg.total_ext = base;
+        if (base >= (1LL << 31)) return;
+    }
+    size_t total_bytes = 0;
+    pg.step_off16.resize(steps.size());
+    pg.step_bytes.resize(steps.size());
+    for (size_t sidx = 0; sidx < steps.size(); ++sidx) {
+        const int n = steps[sidx].q1 - steps[sidx].q0;
+        const size_t b = factor_rec_bytes(n);
+        pg.step_off16[sidx] = (unsigned)(total_bytes / 16);
+        pg.step_bytes[sidx] = (unsigned)b;
+        total_bytes += b;
+        pg.max_step_bytes = std::max(pg.max_step_bytes, (int)b);
+        pg.max_step_rows = std::max(pg.max_step_rows, n);
+    }
+    if (total_bytes / 8 >= (1ull << 32)) return;
+    pg.buf.assign(total_bytes + 16, 0);
+    for (int c = 0; c < P; ++c) {
+        long long e = 0;
+        if (pg.cta_step_ptr[c] == pg.cta_step_ptr[c + 1]) continue;
+        const int cta_q0 = steps[pg.cta_step_ptr[c]].q0;
+        for (int sidx = pg.cta_step_ptr[c]; sidx < pg.cta_step_ptr[c + 1]; ++sidx) {
+            const size_t rec_off = (size_t)pg.step_off16[sidx] * 16;
+            unsigned char* rec = pg.buf.data() + rec_off;
+            const int n = steps[sidx].q1 - steps[sidx].q0;
+            const long long e_before = e;
+            int* hdr = (int*)rec;
+            int* rowints = (int*)(rec + 32);
+            const size_t vals_off = rec_off + 32 + (size_t)n * kFRowInts * 4;
+            int rr = 0;
+            for (int q = steps[sidx].q0; q < steps[sidx].q1; ++q, ++rr) {
+                const int r = order[q];
+                int* ri = rowints + kFRowInts * rr;
+                const size_t v8 = vals_off / 8 + (size_t)rr * kFRowVals;
+                ri[0] = r; ri[1] = ri[2] = ri[3] = 0; ri[4] = 0; ri[5] = ri[6] = -1;
+                ri[7] = (steps[sidx].q0 - cta_q0 + rr) % kFWindow;
+                ri[8] = ri[9] = ri[10] = -1; ri[11] = diag[r];
+                pg.val_src.push_back(diag[r]); pg.val_dst8.push_back((unsigned)v8);
+                int kb = 0;
+                for (int k = rowptr[r]; k < diag[r]; ++k, ++kb) {
+                    const int j = colidx[k];
+                    ri[1 + kb] = owner[j] != c ? kFWindow + (int)((e++) % kFRing) : qlocal[j] % kFWindow;
+                    ri[4] |= 1 << kb;
+                    ri[8 + kb] = k;
+                    pg.val_src.push_back(k); pg.val_dst8.push_back((unsigned)(v8 + 9 + kb * 18));
+                    if (ji_slot[k] >= 0) {
+                        ri[4] |= 1 << (4 + kb);
+                        pg.val_src.push_back(ji_slot[k]); pg.val_dst8.push_back((unsigned)(v8 + 18 + kb * 18));
+                    }
+                }
+                int np = 0;
+                for (int t = push_ptr[r]; t < push_ptr[r + 1]; ++t, ++np) ri[5 + np] = (int)push_slot[t];
+            }
+            hdr[0] = n; hdr[1] = steps[sidx].q0 - cta_q0; hdr[2] = (int)e; hdr[3] = (int)(e - e_before);
+            hdr[4] = sidx > pg.cta_step_ptr[c] ? steps[sidx - 1].q1 - steps[sidx - 1].q0 : 0;      // rows of the previous step
+        }
+    }
+    pg.valid = true;
+}
+
 }  // namespace
 
 void analyse_pattern(int N, const int* rowptr, const int* colidx, int P, PatternAnalysis& out,
@@ -517,6 +669,8 @@ void analyse_pattern(int N, const int* rowptr, const int* colidx, int P, Pattern
             if (out.pipeU.perm_row[q] >= 0) upos[out.pipeU.perm_row[q]] = (int)q;
         build_pipe_program(N, rowptr, colidx, out.diag, lvlL, nL, owner, P, true, &upos, out.pipeL);
     }
+    if (out.pipeL.valid && out.pipeU.valid && !force_simple)
+        build_factor_pipe_program(N, rowptr, colidx, out.diag, lvlL, owner, P, out.pipeF);
     out.nlevL = nL; out.nlevU = nU;
     build_program(N, rowptr, colidx, lvlL, nL, owner, P, true, out.lower);       // also drives the factorisation
     if (force_simple || !out.pipeL.valid || !out.pipeU.valid) {
@@ -631,6 +785,119 @@ bool interpret_pipe_program(const PipeProgram& pg, bool upper, const double* rhs
         }
     }
     return done;
+}
+
+
+namespace {
+inline double host_mat3_invert(double* M)
+{
+    double A[9];
+    for (int q = 0; q < 9; ++q) A[q] = M[q];
+    const double t4 = A[0] * A[4], t6 = A[0] * A[5], t8 = A[1] * A[3];
+    const double t10 = A[2] * A[3], t12 = A[1] * A[6], t14 = A[2] * A[6];
+    const double det = (t4 * A[8] - t6 * A[7] - t8 * A[8] + t10 * A[7] + t12 * A[5] - t14 * A[4]);
+    const double t17 = 1.0 / det;
+    M[0] = (A[4] * A[8] - A[5] * A[7]) * t17;
+    M[1] = -(A[1] * A[8] - A[2] * A[7]) * t17;
+    M[2] = (A[1] * A[5] - A[2] * A[4]) * t17;
+    M[3] = -(A[3] * A[8] - A[5] * A[6]) * t17;
+    M[4] = (A[0] * A[8] - t14) * t17;
+    M[5] = -(t6 - t10) * t17;
+    M[6] = (A[3] * A[7] - A[4] * A[6]) * t17;
+    M[7] = -(A[0] * A[7] - t12) * t17;
+    M[8] = (t4 - t8) * t17;
+    return det;
+}
+}  // namespace
+
+// Executes the records exactly as ilu0_factor_pipe_kernel does (window entries, pushed pivots,
+// arithmetic order of Dune::bilu0_decomposition), advancing each CTA as far as its inputs allow.
+int interpret_factor_program(const FactorPipeProgram& pg, const double* vals, double* lu)
+{
+    std::vector<double> fout((size_t)pg.fpos.size() * kFEntry, 0.0);      // what the kernel writes
+    const int P = pg.P;
+    std::vector<unsigned char> buf(pg.buf);
+    double* bufd = (double*)buf.data();
+    for (size_t b = 0; b < pg.val_src.size(); ++b)
+        for (int t = 0; t < 9; ++t) bufd[(size_t)pg.val_dst8[b] + t] = vals[(size_t)pg.val_src[b] * 9 + t];
+    std::vector<double> ext((size_t)std::max<long long>(pg.total_ext, 1) * 9);
+    std::vector<unsigned char> ext_valid((size_t)std::max<long long>(pg.total_ext, 1), 0);
+    std::vector<std::vector<double>> dep(P, std::vector<double>((size_t)(kFWindow + kFRing) * 9, 0.0));
+    std::vector<int> cur(P);
+    std::vector<long long> ext_seen(P, 0);
+    for (int c = 0; c < P; ++c) cur[c] = pg.cta_step_ptr[c];
+    int bad = 0x7fffffff;
+    bool progress = true, done = false;
+    while (progress && !done) {
+        progress = false; done = true;
+        for (int c = 0; c < P; ++c) {
+            while (cur[c] < pg.cta_step_ptr[c + 1]) {
+                done = false;
+                const int sidx = cur[c];
+                const unsigned char* rec = buf.data() + (size_t)pg.step_off16[sidx] * 16;
+                const int* hdr = (const int*)rec;
+                const int n = hdr[0];
+                const int* rowints = (const int*)(rec + 32);
+                const double* rv = (const double*)(rec + 32 + (size_t)n * kFRowInts * 4);
+                const long long ext_begin = ext_seen[c], ext_end = hdr[2];
+                bool ready = true;
+                for (long long e = ext_begin; e < ext_end && ready; ++e)
+                    if (!ext_valid[pg.cta_ext_base[c] + e]) ready = false;
+                if (!ready) break;
+                for (long long e = ext_begin; e < ext_end; ++e)
+                    for (int t = 0; t < 9; ++t)
+                        dep[c][(size_t)(kFWindow + e % kFRing) * 9 + t] = ext[(size_t)(pg.cta_ext_base[c] + e) * 9 + t];
+                std::vector<double> res((size_t)n * 9);
+                for (int rr = 0; rr < n; ++rr) {
+                    const int* ri = rowints + kFRowInts * rr;
+                    const double* v = rv + (size_t)rr * kFRowVals;
+                    double D[9];
+                    for (int t = 0; t < 9; ++t) D[t] = v[t];
+                    for (int kb = 0; kb < kFastBlocks; ++kb) {
+                        if (!(ri[4] & (1 << kb))) continue;
+                        const double* Aij = v + 9 + kb * 18;
+                        const double* Aji = v + 18 + kb * 18;
+                        const double* Dj = &dep[c][(size_t)ri[1 + kb] * 9];
+                        double L[9];
+                        for (int cc = 0; cc < 3; ++cc)
+                            for (int j = 0; j < 3; ++j) {
+                                double sacc = 0.0;
+                                for (int k = 0; k < 3; ++k) sacc = std::fma(Aij[cc * 3 + k], Dj[k * 3 + j], sacc);
+                                L[cc * 3 + j] = sacc;
+                            }
+                        for (int t = 0; t < 9; ++t) lu[(size_t)ri[8 + kb] * 9 + t] = L[t];
+                        if (ri[4] & (1 << (4 + kb)))
+                            for (int cc = 0; cc < 3; ++cc)
+                                for (int j = 0; j < 3; ++j) {
+                                    double sacc = 0.0;
+                                    for (int k = 0; k < 3; ++k) sacc = std::fma(L[cc * 3 + k], Aji[k * 3 + j], sacc);
+                                    D[cc * 3 + j] -= sacc;
+                                }
+                    }
+                    const double det = host_mat3_invert(D);
+                    if (!(det != 0.0) || std::isinf(det) || std::isnan(det)) bad = std::min(bad, ri[0]);
+                    for (int t = 0; t < 9; ++t) { lu[(size_t)ri[11] * 9 + t] = D[t]; res[(size_t)rr * 9 + t] = D[t]; }
+                }
+                for (int rr = 0; rr < n; ++rr) {
+                    const int* ri = rowints + kFRowInts * rr;
+                    for (int t = 0; t < 9; ++t) dep[c][(size_t)ri[7] * 9 + t] = res[(size_t)rr * 9 + t];
+                    // the kernel stores the step's window entries to program position cta_row_base + qbase + rr
+                    for (int t = 0; t < 9; ++t) fout[(size_t)(pg.cta_row_base[c] + hdr[1] + rr) * kFEntry + t] = res[(size_t)rr * 9 + t];
+                    if (pg.fpos[ri[0]] != pg.cta_row_base[c] + hdr[1] + rr) return -2;      // consumers address pivots through fpos
+                    for (int u = 0; u < 2; ++u)
+                        if (ri[5 + u] >= 0) {
+                            for (int t = 0; t < 9; ++t) ext[(size_t)ri[5 + u] * 9 + t] = res[(size_t)rr * 9 + t];
+                            ext_valid[ri[5 + u]] = 1;
+                        }
+                }
+                ext_seen[c] = ext_end;
+                ++cur[c];
+                progress = true;
+            }
+        }
+    }
+    if (!done) return -2;
+    return bad == 0x7fffffff ? -1 : bad;
 }
 
 void partition_local_rows(int N_local, const int* rowptr, const long long* colidx_global,
@@ -764,4 +1031,26 @@ extern "C" int opmgpu_debug_partition(int N_local, const int* rowptr, const long
     std::copy(lp.lu_src.begin(), lp.lu_src.end(), lu_src);
     *nnzb_diag_out = (int)lp.colidx_diag.size();
     return lp.n_ghost;
+}
+
+// Debug entry (CPU tests): builds the pipelined factorisation program for P CTAs and runs it
+// through the sequential interpreter.  lu receives the factors in BCRS layout.  Returns 0 and
+// the first singular row (or -1) in *bad_row; -2 when the pattern has no pipelined program.
+extern "C" int opmgpu_debug_host_factor_program(int N, const int* rowptr, const int* colidx,
+                                                const double* vals, int P, double* lu, int* bad_row, int* info /*[4]*/)
+{
+    using namespace opmgpu;
+    PatternAnalysis an;
+    analyse_pattern(N, rowptr, colidx, P, an, false);
+    if (an.missing_diag_row >= 0) return -1;
+    if (!an.pipeF.valid) return -2;
+    std::copy(vals, vals + (size_t)rowptr[N] * 9, lu);
+    const int rc = interpret_factor_program(an.pipeF, vals, lu);
+    if (rc == -2) return -3;
+    if (bad_row) *bad_row = rc;
+    if (info) {
+        info[0] = an.pipeF.max_step_rows; info[1] = an.pipeF.max_step_bytes;
+        info[2] = (int)std::min<long long>(an.pipeF.total_ext, 0x7fffffff); info[3] = an.pipeF.cta_step_ptr[P];
+    }
+    return 0;
 }

@@ -105,6 +105,48 @@ struct PipeProgram {
     std::vector<int> val_stride;              // [nval] element [c][e] goes to dst8 + c*stride + e
 };
 
+// ---- pipelined factorisation program (stencil-like patterns) -----------------------------------
+// Same tiles, steps (= dependency levels) and push-slot discipline as the lower sweep program,
+// but the value that travels between rows is the inverted 3x3 pivot block (9 doubles), and a
+// row's record carries the original A blocks it needs: A_ii, and per lower block k the pair
+// A_ij (row i) and A_ji (row j; the only entry of row j that A_ij touches in row i -- every row
+// must be "simple": at most kFastBlocks lower blocks, each updating only the diagonal).
+// Record layout:
+//   int hdr[8]:        nrows, qbase, ext_end, ext entries of this step, rows of the previous step, 0, 0, 0
+//   int rowints[n][12] row, dep[3] (entry index in the CTA's shared dependency array), mask
+//                      (bit k: lower block k present, bit 4+k: A_ji present), push[2] (global
+//                      push slot ids, -1: none), own window entry, BCRS slot of L_ij [3], BCRS
+//                      slot of the diagonal
+//   double vals[n][63] A_ii | k = 0..2: A_ij, A_ji   (row-major blocks, 0 when absent)
+// Shared dependency array: kFEntry-double entries, [0, kFWindow) own recent pivots (entry =
+// program row % kFWindow), [kFWindow, kFWindow + kFRing) pivots pushed by other CTAs (ordinal %
+// kFRing).  The kernel's only output is the inverted pivots in PROGRAM order (fpos[row] = the
+// row's position, kFEntry doubles per row), written with bulk stores straight from the window;
+// L_ij = A_ij * inv(D_j) is formed by the consumers (repack kernels) from A and the pivots.
+constexpr int kFWindow = 320;               // >= 3 steps of kLeanStepRows rows (see the store protocol in factor_pipe.cuh)
+constexpr int kFRing = 256;
+constexpr int kFEntry = 10;                 // doubles per entry: 9 values + 1 pad, so entries are 16-byte aligned
+constexpr int kFPoll = 64;                 // slots the helper warp examines per poll
+constexpr int kFMaxStepExt = 80;           // per step; the ring must hold the entries of the three steps in flight
+constexpr int kFRowInts = 12;
+constexpr int kFRowVals = 63;
+
+struct FactorPipeProgram {
+    bool valid = false;
+    int P = 0;
+    int max_step_bytes = 0, max_step_rows = 0;
+    long long total_ext = 0;
+    std::vector<unsigned char> buf;           // all records, CTA after CTA
+    std::vector<int> cta_step_ptr;            // [P+1]
+    std::vector<unsigned> step_off16;         // [nsteps] record offset / 16
+    std::vector<unsigned> step_bytes;         // [nsteps]
+    std::vector<long long> cta_ext_base;      // [P+1] first global push slot of the CTA
+    std::vector<int> cta_row_base;            // [P+1] program position of the CTA's first row
+    std::vector<int> fpos;                    // [N] program position of every natural row
+    std::vector<int> val_src;                 // [nval] BCRS slot of an A block ...
+    std::vector<unsigned> val_dst8;           // ... and the double index in buf of its 9 values
+};
+
 struct PatternAnalysis {
     int N = 0, nnzb = 0;
     std::vector<int> diag;                   // [N] BCRS slot of the diagonal block
@@ -113,6 +155,7 @@ struct PatternAnalysis {
     int grid_nx = 0, grid_ny = 0, grid_nz = 0;   // inferred Cartesian structure (0 = none)
     SweepProgram lower, upper;
     PipeProgram pipeL, pipeU;
+    FactorPipeProgram pipeF;
     int missing_diag_row = -1;
     int nlevL = 0, nlevU = 0;
 };
@@ -124,6 +167,11 @@ void analyse_pattern(int N, const int* rowptr, const int* colidx, int P, Pattern
 // Sequential interpreter of a pipelined program (debug / CPU tests of the host analysis).
 bool interpret_pipe_program(const PipeProgram& pg, bool upper, const double* rhs_perm, double* work,
                             double* hand_off, double* out, double w, int scale);
+
+// Sequential interpreter of the pipelined factorisation program (debug / CPU tests): vals and lu
+// in BCRS layout; lu must hold a copy of vals on entry (U blocks are not touched).  Returns the
+// first singular row or -1; -2 on a deadlock.
+int interpret_factor_program(const FactorPipeProgram& pg, const double* vals, double* lu);
 
 // Row-partitioned system: split a rank's local rows (global column ids) into the local
 // operator pattern (own columns first, then ghost columns in ascending global order, grouped

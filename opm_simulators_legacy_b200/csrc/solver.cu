@@ -8,6 +8,7 @@
 #include "analysis.hpp"
 #include "kernels.cuh"
 #include "sweep_pipe.cuh"
+#include "factor_pipe.cuh"
 #include "spmv_tma.cuh"
 
 #include <dlfcn.h>
@@ -121,6 +122,24 @@ struct PipeDevMem {
     }
 };
 
+struct FactorPipeDevMem {
+    DevArr<unsigned char> buf;
+    DevArr<int> cta_step_ptr, val_src, cta_row_base, fpos;
+    DevArr<unsigned> step_off16, step_bytes, val_dst8;
+    DevArr<long long> cta_ext_base;
+    DevArr<double> ext, fout;
+    size_t nval = 0, next = 0;
+    int P = 0, nstages = 0, stage_bytes = 0;
+    size_t smem = 0;
+    bool valid = false;
+    void release()
+    {
+        buf.release(); cta_step_ptr.release(); val_src.release(); step_off16.release(); step_bytes.release();
+        val_dst8.release(); cta_ext_base.release(); ext.release(); fout.release(); cta_row_base.release(); fpos.release();
+        valid = false;
+    }
+};
+
 }  // namespace
 
 struct opmgpu_solver {
@@ -138,6 +157,9 @@ struct opmgpu_solver {
     DevArr<int> d_rowptr, d_colidx, d_diag, d_lvl_rows;
     ProgramDevMem progL, progU;
     PipeDevMem pipeL, pipeU;
+    FactorPipeDevMem pipeF;
+    bool factor_tile = false;      // OPMGPU_FACTOR_TILE=1: keep the flag-synchronised tile kernel
+    bool lu_lazy = false;          // the pipelined factorisation left only pivots: d_lu is built on demand
     bool use_pipe = false, force_simple = false, factor_by_levels = false, spmv_tma = true;
     int trace_cta = -1;
     DevArr<long long> d_trace;
@@ -316,6 +338,34 @@ int upload_pipe(opmgpu_handle h, const PipeProgram& p, PipeDevMem& d)
     return 0;
 }
 
+int upload_factor_pipe(opmgpu_handle h, const FactorPipeProgram& p, FactorPipeDevMem& d)
+{
+    int rc;
+    d.valid = false;
+    if (!p.valid) return 0;
+    d.stage_bytes = (p.max_step_bytes + 15) / 16 * 16;
+    const size_t fixed = factor_pipe_smem_bytes(0, 0);
+    if ((size_t)h->max_smem_optin < fixed + 3 * (size_t)d.stage_bytes) return 0;
+    d.nstages = std::min((int)(((size_t)h->max_smem_optin - fixed) / (size_t)d.stage_bytes), kFMaxStages);
+    d.smem = factor_pipe_smem_bytes(d.nstages, d.stage_bytes);
+    CK(d.buf.ensure(p.buf.size()));
+    CK(cudaMemcpyAsync(d.buf.p, p.buf.data(), p.buf.size(), cudaMemcpyHostToDevice, h->stream));
+    if ((rc = upload(h, d.cta_step_ptr, p.cta_step_ptr))) return rc;
+    if ((rc = upload(h, d.step_off16, p.step_off16))) return rc;
+    if ((rc = upload(h, d.step_bytes, p.step_bytes))) return rc;
+    if ((rc = upload(h, d.cta_ext_base, p.cta_ext_base))) return rc;
+    if ((rc = upload(h, d.val_src, p.val_src))) return rc;
+    if ((rc = upload(h, d.val_dst8, p.val_dst8))) return rc;
+    if ((rc = upload(h, d.cta_row_base, p.cta_row_base))) return rc;
+    if ((rc = upload(h, d.fpos, p.fpos))) return rc;
+    CK(d.fout.ensure((p.fpos.size() + 2) * kFEntry));
+    d.nval = p.val_src.size(); d.next = (size_t)p.total_ext; d.P = p.P;
+    CK(d.ext.ensure(std::max<size_t>(d.next, 1) * 9));
+    CK(cudaMemsetAsync(d.ext.p, 0xff, std::max<size_t>(d.next, 1) * 9 * sizeof(double), h->stream));
+    d.valid = true;
+    return 0;
+}
+
 PipeDev pipe_dev(const PipeDevMem& d)
 {
     PipeDev p;
@@ -375,6 +425,11 @@ int set_pattern(opmgpu_handle h, int N, int nnzb, const int* rowptr, const int* 
         if ((rc = upload_pipe(h, h->an.pipeU, h->pipeU))) return rc;
         if (h->pipeL.nstages < 3 || h->pipeU.nstages < 3) h->use_pipe = false;
     }
+    h->pipeF.valid = false;
+    if (h->use_pipe && !h->factor_tile && !h->factor_by_levels) {
+        if ((rc = upload_factor_pipe(h, h->an.pipeF, h->pipeF))) return rc;
+    }
+    if (!h->pipeF.valid) h->pipeF.release();
     if (!h->use_pipe) {
         if (h->an.upper.prow.empty()) analyse_pattern(N, rowptr, colidx, h->sweep_ctas, h->an, true);
         if ((rc = upload_program(h, h->an.lower, h->progL, false))) return rc;
@@ -393,7 +448,7 @@ int set_pattern(opmgpu_handle h, int N, int nnzb, const int* rowptr, const int* 
     // keep only what the host still needs
     h->nlevL = h->an.nlevL; h->nlevU = h->an.nlevU;
     h->an.lower = SweepProgram(); h->an.upper = SweepProgram();
-    h->an.pipeL = PipeProgram(); h->an.pipeU = PipeProgram();
+    h->an.pipeL = PipeProgram(); h->an.pipeU = PipeProgram(); h->an.pipeF = FactorPipeProgram();
     h->have_pattern = true;
     return OPMGPU_OK;
 }
@@ -510,12 +565,16 @@ int factor(opmgpu_handle h, int* bad_row)
 {
     if (!h->have_values) return h->bad("no matrix values set");
     const size_t nv = (size_t)h->nnzb * 9;
+    const bool pipe_factor = h->pipeF.valid && !h->factor_by_levels;
+    h->lu_lazy = false;
     if (h->world > 1) {
         gather_blocks_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, h->stream>>>((size_t)h->nnzb, h->d_lu_src.p, h->d_vals, h->d_lu.p);
         h->launches++;
-    } else {
+    } else if (!pipe_factor) {
         CK(cudaMemcpyAsync(h->d_lu.p, h->d_vals, nv * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     }
+    // the blocks of A the ILU0 is built on (the rank's diagonal block when partitioned)
+    const double* ilu_A = h->world > 1 ? h->d_lu.p : h->d_vals;
     const int big = 0x7fffffff;
     CK(cudaMemcpyAsync(h->d_bad.p, &big, sizeof(int), cudaMemcpyHostToDevice, h->stream));
     if (h->factor_by_levels) {
@@ -527,6 +586,19 @@ int factor(opmgpu_handle h, int* bad_row)
                 h->d_lvl_rows.p, lp[l], lp[l + 1], h->d_rowptr.p, h->d_colidx.p, h->d_diag.p, h->d_lu.p, h->d_bad.p);
             h->launches++;
         }
+    } else if (pipe_factor) {
+        FactorPipeDevMem& d = h->pipeF;
+        const size_t e = d.nval * 9;
+        pack_factor_records_kernel<<<(unsigned)((e + 255) / 256), 256, 0, h->stream>>>(d.nval, d.val_src.p, d.val_dst8.p, ilu_A, (double*)d.buf.p);
+        FactorPipeDev pg;
+        pg.buf = d.buf.p; pg.cta_step_ptr = d.cta_step_ptr.p; pg.step_off16 = d.step_off16.p; pg.step_bytes = d.step_bytes.p;
+        pg.cta_ext_base = d.cta_ext_base.p; pg.cta_row_base = d.cta_row_base.p; pg.ext = d.ext.p; pg.fout = d.fout.p;
+        pg.stage_bytes = d.stage_bytes; pg.nstages = d.nstages;
+        int* bad = h->d_bad.p; int* err = h->d_err.p;
+        void* args[] = {&pg, &bad, &err};
+        CK(cudaLaunchCooperativeKernel((void*)ilu0_factor_pipe_kernel, dim3(d.P), dim3(kFThreads), args, d.smem, h->stream));
+        h->launches += 2;
+        h->lu_lazy = true;
     } else {
         FactorDev pg;
         pg.cta_step_ptr = h->progL.cta_step_ptr.p; pg.step_row_ptr = h->progL.step_row_ptr.p;
@@ -541,7 +613,22 @@ int factor(opmgpu_handle h, int* bad_row)
     }
     CK(cudaGetLastError());
     // stream the factors into the sweep programs' layout
-    if (h->use_pipe) {
+    if (h->use_pipe && pipe_factor) {
+        // L_ij = A_ij * inv(D_j) is formed here, from A and the program-ordered pivots
+        const FactorPipeDevMem& f = h->pipeF;
+        if (h->pipeL.nval) {
+            const size_t e = h->pipeL.nval * 3;
+            repack_pipe2_kernel<true><<<(unsigned)((e + 255) / 256), 256, 0, h->stream>>>(h->pipeL.nval, h->pipeL.val_src.p, h->pipeL.val_dst8.p,
+                h->pipeL.val_stride.p, h->d_colidx.p, h->d_diag.p, f.fpos.p, ilu_A, f.fout.p, (double*)h->pipeL.buf.p);
+            h->launches++;
+        }
+        if (h->pipeU.nval) {
+            const size_t e = h->pipeU.nval * 3;
+            repack_pipe2_kernel<false><<<(unsigned)((e + 255) / 256), 256, 0, h->stream>>>(h->pipeU.nval, h->pipeU.val_src.p, h->pipeU.val_dst8.p,
+                h->pipeU.val_stride.p, h->d_colidx.p, h->d_diag.p, f.fpos.p, ilu_A, f.fout.p, (double*)h->pipeU.buf.p);
+            h->launches++;
+        }
+    } else if (h->use_pipe) {
         for (PipeDevMem* d : {&h->pipeL, &h->pipeU}) {
             if (d->nval) {
                 const size_t e = d->nval * 9;
@@ -638,6 +725,7 @@ int sweep_watchdog(opmgpu_handle h)
     cudaMemsetAsync(h->d_err.p, 0, sizeof(int), h->stream);
     for (PipeDevMem* d : {&h->pipeL, &h->pipeU})
         if (d->ext.p) cudaMemsetAsync(d->ext.p, 0xff, std::max<size_t>(d->next, 1) * 3 * sizeof(double), h->stream);
+    if (h->pipeF.ext.p) cudaMemsetAsync(h->pipeF.ext.p, 0xff, std::max<size_t>(h->pipeF.next, 1) * 9 * sizeof(double), h->stream);
     if (h->progL.fslots.p) cudaMemsetAsync(h->progL.fslots.p, 0xff, std::max<size_t>(h->progL.n_fslots, 1) * 9 * sizeof(double), h->stream);
     cudaStreamSynchronize(h->stream);
     return OPMGPU_CUDA_ERROR;
@@ -861,11 +949,13 @@ int opmgpu_create(int device, opmgpu_handle* out)
     h->sweep_ctas = h->sm_count * per_sm;
     if (const char* s = getenv("OPMGPU_SIMPLE_SWEEP")) h->force_simple = atoi(s) != 0;
     if (const char* s = getenv("OPMGPU_FACTOR_BY_LEVELS")) h->factor_by_levels = atoi(s) != 0;
+    if (const char* s = getenv("OPMGPU_FACTOR_TILE")) h->factor_tile = atoi(s) != 0;
     if (const char* s = getenv("OPMGPU_SPMV_SIMPLE")) h->spmv_tma = atoi(s) == 0;
     cudaFuncSetAttribute(spmv3_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
     cudaFuncSetAttribute(spmv3_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
     cudaFuncSetAttribute(spmv3_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
     cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    cudaFuncSetAttribute(ilu0_factor_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
     cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
     cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
     cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
@@ -1006,6 +1096,17 @@ int opmgpu_ilu0_get_factors(opmgpu_handle h, double* lu)
 {
     if (!h || !h->have_factors) return OPMGPU_BAD_ARGUMENT;
     CK(cudaSetDevice(h->device));
+    if (h->lu_lazy) {
+        // the pipelined factorisation keeps only the pivots: build the BCRS factor array now
+        // (in place on a copy of A; the matrix values must still be the ones that were factorised)
+        if (h->world == 1)
+            CK(cudaMemcpyAsync(h->d_lu.p, h->d_vals, (size_t)h->nnzb * 9 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        const size_t e = (size_t)h->N * 3;
+        materialise_lu_kernel<<<(unsigned)((e + 255) / 256), 256, 0, h->stream>>>(h->N, h->d_rowptr.p, h->d_colidx.p, h->pipeF.fpos.p, h->pipeF.fout.p, h->d_lu.p);
+        h->launches++;
+        CK(cudaGetLastError());
+        h->lu_lazy = false;
+    }
     CK(cudaMemcpyAsync(lu, h->d_lu.p, (size_t)h->nnzb * 9 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return OPMGPU_OK;

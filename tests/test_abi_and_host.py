@@ -88,6 +88,46 @@ def test_sweep_programs_are_exact_on_general_patterns(oracle, N, extra, dense, P
     assert rc == 0 and np.array_equal(out, oracle.ilu0_apply(rp, ci, lu, 0.9, d))
 
 
+def _host_factor(rp, ci, v, P):
+    lib = _lib.load()
+    f = lib.opmgpu_debug_host_factor_program
+    ip, dp = C.POINTER(C.c_int), C.POINTER(C.c_double)
+    f.argtypes = [C.c_int, ip, ip, dp, C.c_int, dp, ip, ip]
+    f.restype = C.c_int
+    rp = np.ascontiguousarray(rp, dtype=np.int32); ci = np.ascontiguousarray(ci, dtype=np.int32)
+    v = np.ascontiguousarray(v)
+    lu = np.zeros_like(v); bad = C.c_int(0); info = np.zeros(4, dtype=np.int32)
+    rc = f(len(rp) - 1, rp.ctypes.data_as(ip), ci.ctypes.data_as(ip), v.ctypes.data_as(dp), P,
+           lu.ctypes.data_as(dp), C.byref(bad), info.ctypes.data_as(ip))
+    return rc, lu, bad.value, info
+
+
+@pytest.mark.parametrize("dims", [(10, 10, 3), (24, 20, 12), (64, 1, 1), (30, 17, 1), (7, 6, 40), (3, 3, 3)])
+@pytest.mark.parametrize("P", [1, 7, 148])
+def test_factor_program_is_exact_on_cartesian_grids(oracle, dims, P):
+    """The pipelined factorisation records (A_ii / A_ij / A_ji per row, pivot window, pushed
+    pivots) interpreted on the host must reproduce bilu0_decomposition bit for bit."""
+    s = synth_blackoil_jacobian(*dims, perm="lognormal")
+    rp, ci, v = s.rowptr.numpy(), s.colidx.numpy(), s.vals.numpy()
+    lu_ref, bad_ref = oracle.ilu0_factor(rp, ci, v)
+    rc, lu, bad, info = _host_factor(rp, ci, v, P)
+    if rc == -2:
+        pytest.skip("pattern has no pipelined factorisation program (falls back to the tile kernel)")
+    assert rc == 0 and bad == bad_ref == -1
+    assert np.array_equal(lu, lu_ref)
+
+
+def test_factor_program_reports_singular_row_and_rejects_fill(oracle):
+    s = synth_blackoil_jacobian(8, 7, 5, perm="lognormal")
+    rp, ci, v = s.rowptr.numpy(), s.colidx.numpy(), s.vals.numpy().copy()
+    v[rp[0]] = 0.0                       # row 0 has no lower blocks: its pivot is A_00 itself
+    rc, lu, bad, info = _host_factor(rp, ci, v, 5)
+    assert rc == 0 and bad == oracle.ilu0_factor(rp, ci, v)[1] == 0
+    # general pattern (fill outside the diagonal): no pipelined program, the tile kernel is used
+    rp2, ci2, v2 = random_bcrs(300, 3, seed=5, dense_group=10)
+    assert _host_factor(rp2, ci2, v2, 7)[0] == -2
+
+
 def test_well_elimination_and_recovery_match_dense_solve():
     """eliminateVariable / recoverVariable (NewtonIterationUtilities.cpp:45-184): solving the
     Schur-reduced system and recovering must equal solving the full system."""
