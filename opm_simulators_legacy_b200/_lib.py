@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libopmgpu.so")
+# OPMGPU_LIB: alternative build of the same library (kernel experiments), else the in-tree one
+LIB_PATH = os.environ.get("OPMGPU_LIB") or os.path.join(_HERE, "libopmgpu.so")
 
 # every symbol include/opm_gpu_solver.h declares (tests check the export list against this)
 EXPORTS = [

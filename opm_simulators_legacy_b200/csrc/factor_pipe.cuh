@@ -61,16 +61,19 @@ __host__ __device__ inline size_t factor_pipe_smem_bytes(int nstages, int stage_
     return 512 + (size_t)kFDepBytes + (size_t)nstages * (size_t)stage_bytes;
 }
 
-// A blocks (BCRS) -> step records: one thread per double
+// A blocks (BCRS) -> step records: one thread per block row (3 doubles)
 __global__ void __launch_bounds__(256)
 pack_factor_records_kernel(size_t nval, const int* __restrict__ src, const unsigned* __restrict__ dst8,
                            const double* __restrict__ vals, double* __restrict__ bufd)
 {
-    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= nval * 9) return;
-    const size_t b = e / 9;
-    const int t = (int)(e - b * 9);
-    bufd[(size_t)dst8[b] + t] = vals[(size_t)src[b] * 9 + t];
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nval * 3) return;
+    const size_t b = t / 3;
+    const int c = (int)(t - b * 3);
+    const double* a = vals + (size_t)src[b] * 9 + c * 3;
+    double* d = bufd + (size_t)dst8[b] + c * 3;
+    const double a0 = a[0], a1 = a[1], a2 = a[2];
+    d[0] = a0; d[1] = a1; d[2] = a2;
 }
 
 __device__ __forceinline__ double factor_invert3(double (&M)[9])

@@ -374,6 +374,7 @@ PipeDev pipe_dev(const PipeDevMem& d)
     p.cta_ext_base = d.cta_ext_base.p; p.ext = d.ext.p;
     p.stage_bytes = d.stage_bytes; p.rhs_bytes = d.rhs_bytes; p.nstages = d.nstages;
     p.trace = nullptr; p.trace_cta = -1; p.gtrace = nullptr; p.gtrace_steps = 0;
+    p.dbg = getenv("OPMGPU_SDEBUG") ? atoi(getenv("OPMGPU_SDEBUG")) : 0;
     return p;
 }
 
@@ -588,7 +589,7 @@ int factor(opmgpu_handle h, int* bad_row)
         }
     } else if (pipe_factor) {
         FactorPipeDevMem& d = h->pipeF;
-        const size_t e = d.nval * 9;
+        const size_t e = d.nval * 3;
         pack_factor_records_kernel<<<(unsigned)((e + 255) / 256), 256, 0, h->stream>>>(d.nval, d.val_src.p, d.val_dst8.p, ilu_A, (double*)d.buf.p);
         FactorPipeDev pg;
         pg.buf = d.buf.p; pg.cta_step_ptr = d.cta_step_ptr.p; pg.step_off16 = d.step_off16.p; pg.step_bytes = d.step_bytes.p;

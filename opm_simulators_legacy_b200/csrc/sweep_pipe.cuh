@@ -43,6 +43,10 @@ namespace opmgpu {
 constexpr int kPipeGroups = 3;                                     // compute groups taking turns
 constexpr int kPipeComputeWarps = 3;                               // warps per group, one thread per block row
 constexpr int kPipeHelpers = 1;                                    // warps polling for pushed results
+#ifndef OPMGPU_POLL_PER_LANE
+#define OPMGPU_POLL_PER_LANE 1
+#endif
+constexpr int kPipePollPerLane = OPMGPU_POLL_PER_LANE;             // slots a helper lane examines per poll (a short poll = a short crossing)
 constexpr int kPipeThreads = 32 * (1 + kPipeHelpers + kPipeGroups * kPipeComputeWarps);
 constexpr int kPipeRowsPerPass = kPipeComputeWarps * 32;
 static_assert(kPipeRowsPerPass == kLeanStepRows, "analysis.hpp sizes lean steps for one pass");
@@ -66,6 +70,7 @@ struct PipeDev {
     int trace_cta;
     long long* gtrace;           // optional (debug): %globaltimer stamps of every CTA, [cta][gtrace_steps][8], then helper deliveries [cta][512][4]
     int gtrace_steps;
+    int dbg;                     // experiments: bit 0 = skip the result stores to HBM
 };
 __device__ __forceinline__ long long pipe_gtime() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 // timer read that cannot issue before `dep` is available (stamps after barriers / loads / chains)
@@ -404,6 +409,7 @@ ilu0_sweep_pipe_kernel(PipeDev pg, const double* __restrict__ rhs_perm, double* 
         // ahead of the poll window warm (helper 0).
         constexpr int kPfAhead = 768;
         int pf = 0;                            // slots [0, pf) have been prefetched
+        int rearm_from = 0, rearm_n = 0;       // delivered, not yet re-armed
         if (hid > 0) __nanosleep(300 * hid);
         for (;;) {
             const int e = ctl->ext_ready;
@@ -418,10 +424,10 @@ ilu0_sweep_pipe_kernel(PipeDev pg, const double* __restrict__ rhs_perm, double* 
                 pf = min(want, pf + (32 * 128) / 24);
             }
             const int limit = min(total, ctl->ext_consumed + kExtRing);
-            long long a[3][3];
-            unsigned m[3];
+            long long a[kPipePollPerLane][3];
+            unsigned m[kPipePollPerLane];
 #pragma unroll
-            for (int u = 0; u < 3; ++u) {
+            for (int u = 0; u < kPipePollPerLane; ++u) {
                 const int idx = e + u * 32 + lane;
                 a[u][0] = a[u][1] = a[u][2] = -1;
                 if (idx < limit) {
@@ -431,19 +437,31 @@ ilu0_sweep_pipe_kernel(PipeDev pg, const double* __restrict__ rhs_perm, double* 
                     asm volatile("ld.relaxed.gpu.global.s64 %0, [%1];" : "=l"(a[u][2]) : "l"(sl + 2) : "memory");
                 }
             }
+            // re-arm the slots of the previous delivery while this poll's loads are in flight
+            // (nobody waits for these stores; the producer writes them again one sweep later)
+            if (rearm_n > 0) {
 #pragma unroll
-            for (int u = 0; u < 3; ++u)
+                for (int u = 0; u < kPipePollPerLane; ++u) {
+                    const int idx = rearm_from + u * 32 + lane;
+                    if (u * 32 + lane < rearm_n) {
+                        long long* sl = const_cast<long long*>(slots) + (size_t)idx * 3;
+                        __stcg(sl + 0, -1LL); __stcg(sl + 1, -1LL); __stcg(sl + 2, -1LL);
+                    }
+                }
+                rearm_n = 0;
+            }
+#pragma unroll
+            for (int u = 0; u < kPipePollPerLane; ++u)
                 m[u] = __ballot_sync(0xffffffffu, a[u][0] != -1 && a[u][1] != -1 && a[u][2] != -1);
-            int n = 0;
-            if (m[0] != 0xffffffffu) n = __ffs(~m[0]) - 1;
-            else if (m[1] != 0xffffffffu) n = 32 + __ffs(~m[1]) - 1;
-            else if (m[2] != 0xffffffffu) n = 64 + __ffs(~m[2]) - 1;
-            else n = 96;
+            int n = 32 * kPipePollPerLane;
+#pragma unroll
+            for (int u = kPipePollPerLane - 1; u >= 0; --u)
+                if (m[u] != 0xffffffffu) n = 32 * u + __ffs(~m[u]) - 1;
             // another helper may have delivered part of the prefix meanwhile
-            const int e_now = __shfl_sync(0xffffffffu, (int)ctl->ext_ready, 0);
+            const int e_now = kPipeHelpers > 1 ? __shfl_sync(0xffffffffu, (int)ctl->ext_ready, 0) : e;
             if (e + n > e_now) {
 #pragma unroll
-                for (int u = 0; u < 3; ++u) {
+                for (int u = 0; u < kPipePollPerLane; ++u) {
                     const int idx = e + u * 32 + lane;
                     if (idx >= e_now && u * 32 + lane < n) {
                         double* dst = ring + (idx & (kExtRing - 1)) * 3;
@@ -452,16 +470,8 @@ ilu0_sweep_pipe_kernel(PipeDev pg, const double* __restrict__ rhs_perm, double* 
                 }
                 // ring data before ext_ready: shared-memory stores of one warp are performed in order
                 __syncwarp();
-                if (lane == 0) atomicMax(ext_ready, e + n);
-                // re-arm the consumed slots (nobody waits for these stores)
-#pragma unroll
-                for (int u = 0; u < 3; ++u) {
-                    const int idx = e + u * 32 + lane;
-                    if (idx >= e_now && u * 32 + lane < n) {
-                        long long* sl = const_cast<long long*>(slots) + (size_t)idx * 3;
-                        __stcg(sl + 0, -1LL); __stcg(sl + 1, -1LL); __stcg(sl + 2, -1LL);
-                    }
-                }
+                if (lane == 0) { if (kPipeHelpers > 1) atomicMax(ext_ready, e + n); else *reinterpret_cast<volatile int*>(ext_ready) = e + n; }
+                rearm_from = e_now; rearm_n = e + n - e_now;
                 if (gtr && lane == 0 && hid == 0) {
                     if (e_now == 0) { gtr[(pg.gtrace_steps - 1) * 8 + 1] = pipe_gtime(); gtr[(pg.gtrace_steps - 1) * 8 + 2] = polls; }
                     if (ndeliv < 512) {
@@ -476,6 +486,16 @@ ilu0_sweep_pipe_kernel(PipeDev pg, const double* __restrict__ rhs_perm, double* 
                 const int ab = __shfl_sync(0xffffffffu, (int)ctl->abort_flag, 0);
                 if (ab) break;
                 if (spins > kPipeSpinLimit) { if (lane == 0) { ctl->abort_flag = 1; atomicExch(err, 3); } break; }
+            }
+        }
+        if (rearm_n > 0) {
+#pragma unroll
+            for (int u = 0; u < kPipePollPerLane; ++u) {
+                const int idx = rearm_from + u * 32 + lane;
+                if (u * 32 + lane < rearm_n) {
+                    long long* sl = const_cast<long long*>(slots) + (size_t)idx * 3;
+                    __stcg(sl + 0, -1LL); __stcg(sl + 1, -1LL); __stcg(sl + 2, -1LL);
+                }
             }
         }
     } else {
@@ -539,7 +559,7 @@ ilu0_sweep_pipe_kernel(PipeDev pg, const double* __restrict__ rhs_perm, double* 
             // every warp of this group passed the bar.sync of this step, i.e. is done with its
             // step s-G: release the pushed-result ring entries of that step
             if (elected && st_prev >= 0) ctl->ext_consumed = ext_prev_end;
-            sweep_row_stores<UPPER, LEAN>(p, acc, work, hand_off, out, w, scale);
+            if (!(pg.dbg & 1)) sweep_row_stores<UPPER, LEAN>(p, acc, work, hand_off, out, w, scale);
             if (gt_rb) gtr[s * 8 + 6] = pipe_gtime_after((int)rb);
             if (tr) pg.trace[s * 16 + 3] = clock64();
             st_prev = st; ext_prev_end = p.ext_end;

@@ -234,8 +234,10 @@ class GpuLinearSolver:
         return self.last
 
     def solve_from_csc_blocks(self, N, blocks9, matbalscale, rhs_eqmajor, params: Optional[L.Params] = None,
-                              raise_on_failure=True, **kw):
-        """...Interleaved.cpp:234-283 in one call; blocks9[p1*3+p2] = (colptr, rowidx, val)."""
+                              raise_on_failure=True, out=None, **kw):
+        """...Interleaved.cpp:234-283 in one call; blocks9[p1*3+p2] = (colptr, rowidx, val).
+        out: optional float64 array of 3N entries that receives the increment (page-locked memory
+        makes the device-to-host copy asynchronous and ~3x faster than into a fresh pageable array)."""
         p = params if params is not None else make_params(**kw)
         arr = (L.Csc * 9)()
         keep = []
@@ -247,7 +249,11 @@ class GpuLinearSolver:
             arr[q].colptr, arr[q].rowidx, arr[q].val = _ip(cp), _ip(ri), _dp(v)
         sc = np.ascontiguousarray(matbalscale, dtype=np.float64)
         rhs = np.ascontiguousarray(rhs_eqmajor, dtype=np.float64)
-        dx = np.zeros(3 * N)
+        if out is not None:
+            dx = out
+            assert dx.dtype == np.float64 and dx.size == 3 * N and dx.flags["C_CONTIGUOUS"]
+        else:
+            dx = np.zeros(3 * N)
         res = L.Result()
         rc = self.lib.opmgpu_solve_from_csc_blocks(self.h, int(N), arr, _dp(sc), _dp(rhs), _dp(dx),
                                                    C.byref(p), C.byref(res))
