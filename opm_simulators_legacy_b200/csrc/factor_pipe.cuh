@@ -249,10 +249,11 @@ ilu0_factor_pipe_kernel(FactorPipeDev pg, int* bad_row, int* err)
             if (lane == 0) mbar_arrive(&ctl->empty[st]);
             // the bulk store this thread issued two steps ago has read its window entries
             if (elected) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            // ext_ready only grows: the usual answer is fetched while the group waits for its turn
+            const bool ext_ok = dead || ext_cnt <= 0 || ctl->ext_ready >= ext_end;
             if (s > 0) asm volatile("bar.sync %0, %1;" ::"r"(bar_prev), "n"(NPP) : "memory");     // step s-1 done
-            if (elected && s > 0) factor_store_step(pg, dep, row_base, prev_q0, prev_n);
-            if (!dead && ext_cnt > 0) {
-                if (ctl->ext_ready < ext_end && !pipe_wait_ext(ctl, ext_end, err)) { dead = true; on = false; }
+            if (!ext_ok) {
+                if (!pipe_wait_ext(ctl, ext_end, err)) { dead = true; on = false; }
                 asm volatile("" ::: "memory");
             }
             double D[9];
@@ -296,7 +297,10 @@ ilu0_factor_pipe_kernel(FactorPipeDev pg, int* bad_row, int* err)
 #pragma unroll
                 for (int t = 0; t < 9; ++t) w[t] = D[t];
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // window -> bulk store
-                // other CTAs wait for these: push before anything else
+            }
+            asm volatile("bar.arrive %0, %1;" ::"r"(bar_own), "n"(NPP) : "memory");                // step s done
+            // off the in-tile critical path: pivots other CTAs wait for, pivots of step s-1 -> HBM
+            if (on) {
                 if (ri1.y >= 0) {
                     double* sl = pg.ext + (size_t)ri1.y * 9;
 #pragma unroll
@@ -308,7 +312,7 @@ ilu0_factor_pipe_kernel(FactorPipeDev pg, int* bad_row, int* err)
                     for (int t = 0; t < 9; ++t) push_f64(sl + t, D[t]);
                 }
             }
-            asm volatile("bar.arrive %0, %1;" ::"r"(bar_own), "n"(NPP) : "memory");                // step s done
+            if (elected && s > 0) factor_store_step(pg, dep, row_base, prev_q0, prev_n);
             // every warp of this group passed the bar.sync of this step, i.e. is done with its
             // step s-G: release the pushed-pivot ring entries of that step
             if (elected && ext_prev_end >= 0) ctl->ext_consumed = ext_prev_end;

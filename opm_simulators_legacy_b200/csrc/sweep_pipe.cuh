@@ -35,6 +35,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cstddef>
 
 #include "analysis.hpp"
 
@@ -164,6 +165,7 @@ __device__ __forceinline__ bool pipe_wait_ext(PipeCtl* ctl, int ext_end, int* er
 
 // ---- compute-warp helpers --------------------------------------------------------------------
 __device__ __forceinline__ double lds_f64(uint32_t a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
+__device__ __forceinline__ int lds_s32_volatile(uint32_t a) { int v; asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
 
 #ifndef OPMGPU_PUSH_MODE
@@ -302,7 +304,15 @@ __device__ __forceinline__ void sweep_row_chain(const StepPre<UPPER>& p, const u
         }
         const uint32_t w = dep_s + 8u * (uint32_t)p.ri1.w;
         sts_f64(w, acc[0]); sts_f64(w + 8, acc[1]); sts_f64(w + 16, acc[2]);
-        // other CTAs wait for these: push before anything else
+    }
+}
+// results other CTAs wait for.  Issued right after the hand-over to the next group: the
+// in-tile hand-over is on the critical path of every step, a tile crossing only once per tile.
+template <bool UPPER, bool LEAN>
+__device__ __forceinline__ void sweep_row_pushes(const StepPre<UPPER>& p, const unsigned char* rec, int r,
+                                                 double* ext, const double (&acc)[3])
+{
+    if (p.on) {
         if (p.ri1.y >= 0) { double* sl = ext + (size_t)p.ri1.y * 3; push_f64(sl, acc[0]); push_f64(sl + 1, acc[1]); push_f64(sl + 2, acc[2]); }
         if (p.ri1.z >= 0) { double* sl = ext + (size_t)p.ri1.z * 3; push_f64(sl, acc[0]); push_f64(sl + 1, acc[1]); push_f64(sl + 2, acc[2]); }
         if (!LEAN && (p.ri0.x & kRowSlow)) sweep_extra_pushes(rec, r, ext, acc);
@@ -341,6 +351,7 @@ __device__ __noinline__ void sweep_extra_rows(const unsigned char* stage, int rh
         p.load(stage, rhs_bytes, r, true);
         double acc[3];
         sweep_row_chain<UPPER, false>(p, stage + rhs_bytes, r, dep, dep_s, work, ext, acc);
+        sweep_row_pushes<UPPER, false>(p, stage + rhs_bytes, r, ext, acc);
         sweep_row_stores<UPPER, false>(p, acc, work, hand_off, out, w, scale);
     }
 }
@@ -510,7 +521,10 @@ ilu0_sweep_pipe_kernel(PipeDev pg, const double* __restrict__ rhs_perm, double* 
         const int r_first = cw * 32 + lane;
         const bool elected = cw == 0 && lane == 0;
         const int bar_prev = 1 + (g + G - 1) % G, bar_own = 1 + g;
-        const uint32_t dep_s = smem_u32(dep);
+        // 32-bit shared addresses held in registers (opaque to the compiler, which otherwise
+        // rebuilds them from SR_CgaCtaId on the critical path of every step)
+        uint32_t dep_s = smem_u32(dep), ctl_s = smem_u32(ctl);
+        asm volatile("" : "+r"(dep_s), "+r"(ctl_s));
         bool dead = false;
         int st = g % S;
         unsigned par = (unsigned)((g / S) & 1);
@@ -531,13 +545,15 @@ ilu0_sweep_pipe_kernel(PipeDev pg, const double* __restrict__ rhs_perm, double* 
             if (tr) pg.trace[s * 16 + 0] = clock64();
             const bool gt = gtr && elected && s < pg.gtrace_steps - 1;
             if (gt) gtr[s * 8 + 0] = pipe_gtime();
+            // pushed inputs of this step staged by the helper warp?  ext_ready only grows, so the
+            // usual answer (yes) is fetched while the group still waits for its turn.  (Ring data
+            // is written before ext_ready, and shared-memory accesses of a thread are not reordered.)
+            const bool ext_ok = dead || p.ext_cnt <= 0 || lds_s32_volatile(ctl_s + (uint32_t)offsetof(PipeCtl, ext_ready)) >= p.ext_end;
             if (s > 0) asm volatile("bar.sync %0, %1;" ::"r"(bar_prev), "n"(NPP) : "memory");     // step s-1 done
             if (tr) pg.trace[s * 16 + 1] = pipe_clock_after(ctl->abort_flag);
             if (gt) gtr[s * 8 + 1] = pipe_gtime_after(ctl->abort_flag);
-            // pushed inputs of this step staged by the helper warp?  (ring data is written
-            // before ext_ready, and shared-memory accesses of a thread are not reordered)
-            if (!dead && p.ext_cnt > 0) {
-                if (ctl->ext_ready < p.ext_end && !pipe_wait_ext(ctl, p.ext_end, err)) { dead = true; p.on = false; }
+            if (!ext_ok) {
+                if (!pipe_wait_ext(ctl, p.ext_end, err)) { dead = true; p.on = false; }
                 asm volatile("" ::: "memory");
             }
             if (gt) { gtr[s * 8 + 2] = pipe_gtime_after(ctl->ext_ready); gtr[s * 8 + 4] = p.ext_end; gtr[s * 8 + 5] = p.n; }
@@ -552,6 +568,7 @@ ilu0_sweep_pipe_kernel(PipeDev pg, const double* __restrict__ rhs_perm, double* 
             const bool gt_rb = gt && p.on && p.ri1.y >= 0;
             if (gt_rb) asm volatile("ld.relaxed.gpu.global.s64 %0, [%1];" : "=l"(rb) : "l"(pg.ext + (size_t)p.ri1.y * 3) : "memory");
             asm volatile("bar.arrive %0, %1;" ::"r"(bar_own), "n"(NPP) : "memory");                // step s done
+            sweep_row_pushes<UPPER, LEAN>(p, stage + pg.rhs_bytes, r_first, pg.ext, acc);
             if (!LEAN) {            // tail lists of slow rows are read from the stage during the chain
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&ctl->empty[st]);
