@@ -21,6 +21,26 @@ enum ScalarSlot {
     S_NRM2 = 6, S_RHO_NEW = 7, S_DOT = 8, S_COUNT = 16
 };
 
+// Host mailbox (page-locked, device-mapped): the kernel that finishes a BiCGStab half-step
+// writes the scalars the host's convergence logic needs, the sweep watchdog word and then a
+// sequence number straight into host memory, so the host polls a cache line instead of paying
+// a copy + stream synchronisation per half-step.  hS == nullptr: disabled (partitioned runs
+// reduce the scalars with NCCL after the kernel).
+struct HostBox {
+    double* hS;                        // [S_COUNT]
+    int* herr;
+    unsigned long long* hseq;
+    const int* derr;                   // device watchdog word of the sweeps
+    unsigned long long seq;
+};
+__device__ __forceinline__ void hostbox_publish(const HostBox& hb)
+{
+    if (!hb.hS) return;
+    *hb.herr = *reinterpret_cast<const volatile int*>(hb.derr);
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long*>(hb.hseq) = hb.seq;
+}
+
 // ------------------------------------------------------------------------------------------
 // Deterministic grid reduction: fixed-shape shuffle tree per block, per-block partials in
 // HBM, the last block to arrive (ticket) folds the partials in a fixed order.  No floating
@@ -129,7 +149,7 @@ spmv3_kernel(int N, const int* __restrict__ rowptr, const int* __restrict__ coli
 // ------------------------------------------------------------------------------------------
 // S[S_NRM2] = S[S_RHO_NEW] = r.r ; recurrences reset (rho = alpha = omega = 1)
 __global__ void __launch_bounds__(256)
-bicg_init_kernel(size_t n, const double* __restrict__ r, double* S, ReduceWs ws)
+bicg_init_kernel(size_t n, const double* __restrict__ r, double* S, ReduceWs ws, HostBox hb)
 {
     double v[1] = {0.0};
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
@@ -137,6 +157,7 @@ bicg_init_kernel(size_t n, const double* __restrict__ r, double* S, ReduceWs ws)
     grid_reduce<1>(v, ws, [=](double (&t)[1]) {
         S[S_NRM2] = t[0]; S[S_RHO_NEW] = t[0];
         S[S_RHO_OLD] = 1.0; S[S_ALPHA] = 1.0; S[S_OMEGA] = 1.0;
+        if (hb.hS) { hb.hS[S_NRM2] = t[0]; hostbox_publish(hb); }
     });
 }
 
@@ -157,9 +178,10 @@ bicg_update_p_kernel(size_t n, double* __restrict__ p, const double* __restrict_
 // alpha = rho_new / h ; x += alpha y ; r -= alpha v ; S[S_NRM2] = r.r
 __global__ void __launch_bounds__(256)
 bicg_update1_kernel(size_t n, double* __restrict__ x, double* __restrict__ r,
-                    const double* __restrict__ y, const double* __restrict__ v, double* S, ReduceWs ws)
+                    const double* __restrict__ y, const double* __restrict__ v, double* S, ReduceWs ws, HostBox hb)
 {
-    const double alpha = S[S_RHO_NEW] / S[S_H];
+    const double hdot = S[S_H];
+    const double alpha = S[S_RHO_NEW] / hdot;
     double s[1] = {0.0};
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         x[i] = fma(alpha, y[i], x[i]);
@@ -167,14 +189,17 @@ bicg_update1_kernel(size_t n, double* __restrict__ x, double* __restrict__ r,
         r[i] = ri;
         s[0] = fma(ri, ri, s[0]);
     }
-    grid_reduce<1>(s, ws, [=](double (&t)[1]) { S[S_NRM2] = t[0]; S[S_ALPHA] = alpha; });
+    grid_reduce<1>(s, ws, [=](double (&t)[1]) {
+        S[S_NRM2] = t[0]; S[S_ALPHA] = alpha;
+        if (hb.hS) { hb.hS[S_NRM2] = t[0]; hb.hS[S_H] = hdot; hostbox_publish(hb); }
+    });
 }
 
 // omega = (t.r)/(t.t) ; x += omega y ; r -= omega t ; S[S_NRM2] = r.r ; rho <- rho_new ; rho_new = rt.r
 __global__ void __launch_bounds__(256)
 bicg_update2_kernel(size_t n, double* __restrict__ x, double* __restrict__ r,
                     const double* __restrict__ y, const double* __restrict__ t,
-                    const double* __restrict__ rt, double* S, ReduceWs ws)
+                    const double* __restrict__ rt, double* S, ReduceWs ws, HostBox hb)
 {
     const double omega = S[S_TR] / S[S_TT];
     double s[2] = {0.0, 0.0};
@@ -186,10 +211,12 @@ bicg_update2_kernel(size_t n, double* __restrict__ x, double* __restrict__ r,
         s[1] = fma(rt[i], ri, s[1]);
     }
     grid_reduce<2>(s, ws, [=](double (&u)[2]) {
+        const double rho_old = S[S_RHO_NEW];
         S[S_OMEGA] = omega;
-        S[S_RHO_OLD] = S[S_RHO_NEW];
+        S[S_RHO_OLD] = rho_old;
         S[S_NRM2] = u[0];
         S[S_RHO_NEW] = u[1];
+        if (hb.hS) { hb.hS[S_OMEGA] = omega; hb.hS[S_RHO_OLD] = rho_old; hb.hS[S_NRM2] = u[0]; hostbox_publish(hb); }
     });
 }
 

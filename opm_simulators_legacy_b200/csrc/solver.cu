@@ -15,6 +15,7 @@
 #include <nccl.h>      // types only: the library is resolved at run time with dlopen
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -180,6 +181,9 @@ struct opmgpu_solver {
     int epoch = 0;
     double* h_S = nullptr;       // pinned
     int* h_flags2 = nullptr;     // pinned: [0] sweep watchdog, [1] bad row / bad pattern
+    unsigned long long* h_seq = nullptr;   // pinned: host mailbox sequence number (kernels.cuh: HostBox)
+    unsigned long long seq = 0;
+    bool use_hostbox = true;     // OPMGPU_HOSTBOX=0: copy + stream synchronisation per half-step instead
     cudaEvent_t ev[8] = {};
 
     // distributed (one process per GPU): row partition, halo plan, NCCL communicator
@@ -732,6 +736,37 @@ int sweep_watchdog(opmgpu_handle h)
     return OPMGPU_CUDA_ERROR;
 }
 
+// mailbox of the next half-step-ending kernel (single-GPU handles only)
+HostBox next_hostbox(opmgpu_handle h)
+{
+    HostBox hb;
+    hb.hS = nullptr; hb.herr = nullptr; hb.hseq = nullptr; hb.derr = h->d_err.p; hb.seq = 0;
+    if (h->world == 1 && h->use_hostbox) {
+        hb.hS = h->h_S; hb.herr = &h->h_flags2[0]; hb.hseq = h->h_seq; hb.seq = ++h->seq;
+    }
+    return hb;
+}
+
+int read_scalars(opmgpu_handle h);
+
+// wait for the mailbox of `hb` (or fall back to copy + synchronise when it is disabled)
+int wait_scalars(opmgpu_handle h, const HostBox& hb)
+{
+    if (!hb.hS) return read_scalars(h);
+    volatile unsigned long long* seq = h->h_seq;
+    for (unsigned spin = 1;; ++spin) {
+        if (*seq == hb.seq) break;
+        if ((spin & 0x3fffu) == 0) {                       // the kernel may have failed to run at all
+            const cudaError_t q = cudaStreamQuery(h->stream);
+            if (q == cudaSuccess) { if (*seq == hb.seq) break; return h->fail(cudaErrorUnknown, "host mailbox never written"); }
+            if (q != cudaErrorNotReady) return h->fail(q, "BiCGStab half-step");
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    if (h->h_flags2[0]) { CK(cudaStreamSynchronize(h->stream)); return sweep_watchdog(h); }
+    return 0;
+}
+
 int read_scalars(opmgpu_handle h)
 {
     CK(cudaMemcpyAsync(h->h_S, h->d_S.p, sizeof(double) * S_COUNT, cudaMemcpyDeviceToHost, h->stream));
@@ -752,10 +787,11 @@ int bicgstab(opmgpu_handle h, const opmgpu_params* prm, opmgpu_result* res)
     h->history.clear();
     CK(cudaMemsetAsync(h->d_x.p, 0, n * sizeof(double), h->stream));
     CK(cudaMemcpyAsync(h->d_rt.p, h->d_r.p, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-    bicg_init_kernel<<<kVecBlocks, 256, 0, h->stream>>>(n, h->d_r.p, h->d_S.p, h->ws());
+    HostBox hb = next_hostbox(h);
+    bicg_init_kernel<<<kVecBlocks, 256, 0, h->stream>>>(n, h->d_r.p, h->d_S.p, h->ws(), hb);
     h->launches++;
     if ((rc = allreduce_slots(h, S_NRM2, 2))) return rc;
-    if ((rc = read_scalars(h))) return rc;
+    if ((rc = wait_scalars(h, hb))) return rc;
     const double norm0 = std::sqrt(h->h_S[S_NRM2]);
     double norm = norm0, rho = 1.0, omega = 1.0, it = 0.0;
     int half = 0, status = OPMGPU_OK, converged = 0;
@@ -782,11 +818,12 @@ int bicgstab(opmgpu_handle h, const opmgpu_params* prm, opmgpu_result* res)
         if ((rc = spmv_with_dots(h, 1, h->d_y.p, h->d_v.p, h->d_rt.p))) return rc;
         h->prof_end();
         h->prof_begin(2);
-        bicg_update1_kernel<<<kVecBlocks, 256, 0, h->stream>>>(n, h->d_x.p, h->d_r.p, h->d_y.p, h->d_v.p, h->d_S.p, h->ws());
+        hb = next_hostbox(h);
+        bicg_update1_kernel<<<kVecBlocks, 256, 0, h->stream>>>(n, h->d_x.p, h->d_r.p, h->d_y.p, h->d_v.p, h->d_S.p, h->ws(), hb);
         h->prof_end();
         h->launches++;
         if ((rc = allreduce_slots(h, S_NRM2, 1))) return rc;
-        if ((rc = read_scalars(h))) return rc;
+        if ((rc = wait_scalars(h, hb))) return rc;
         if (std::fabs(h->h_S[S_H]) < EPSILON) { status = OPMGPU_BREAKDOWN; break; }
         norm = std::sqrt(h->h_S[S_NRM2]);
         h->history.push_back(norm);
@@ -802,11 +839,12 @@ int bicgstab(opmgpu_handle h, const opmgpu_params* prm, opmgpu_result* res)
         if ((rc = spmv_with_dots(h, 2, h->d_y.p, h->d_t.p, h->d_r.p))) return rc;
         h->prof_end();
         h->prof_begin(2);
-        bicg_update2_kernel<<<kVecBlocks, 256, 0, h->stream>>>(n, h->d_x.p, h->d_r.p, h->d_y.p, h->d_t.p, h->d_rt.p, h->d_S.p, h->ws());
+        hb = next_hostbox(h);
+        bicg_update2_kernel<<<kVecBlocks, 256, 0, h->stream>>>(n, h->d_x.p, h->d_r.p, h->d_y.p, h->d_t.p, h->d_rt.p, h->d_S.p, h->ws(), hb);
         h->prof_end();
         h->launches++;
         if ((rc = allreduce_slots(h, S_NRM2, 2))) return rc;
-        if ((rc = read_scalars(h))) return rc;
+        if ((rc = wait_scalars(h, hb))) return rc;
         omega = h->h_S[S_OMEGA];
         rho = h->h_S[S_RHO_OLD];
         norm = std::sqrt(h->h_S[S_NRM2]);
@@ -951,6 +989,7 @@ int opmgpu_create(int device, opmgpu_handle* out)
     if (const char* s = getenv("OPMGPU_SIMPLE_SWEEP")) h->force_simple = atoi(s) != 0;
     if (const char* s = getenv("OPMGPU_FACTOR_BY_LEVELS")) h->factor_by_levels = atoi(s) != 0;
     if (const char* s = getenv("OPMGPU_FACTOR_TILE")) h->factor_tile = atoi(s) != 0;
+    if (const char* s = getenv("OPMGPU_HOSTBOX")) h->use_hostbox = atoi(s) != 0;
     if (const char* s = getenv("OPMGPU_SPMV_SIMPLE")) h->spmv_tma = atoi(s) == 0;
     cudaFuncSetAttribute(spmv3_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
     cudaFuncSetAttribute(spmv3_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
@@ -980,10 +1019,12 @@ int opmgpu_create(int device, opmgpu_handle* out)
     h->stream = h->own_stream;
     bool ok = cudaMallocHost((void**)&h->h_S, sizeof(double) * S_COUNT) == cudaSuccess &&
               cudaMallocHost((void**)&h->h_flags2, sizeof(int) * 4) == cudaSuccess &&
+              cudaMallocHost((void**)&h->h_seq, sizeof(unsigned long long) * 8) == cudaSuccess &&
               h->d_S.ensure(S_COUNT) == cudaSuccess && h->d_partials.ensure((size_t)4 * kMaxRedBlocks) == cudaSuccess &&
               h->d_ticket.ensure(1) == cudaSuccess && h->d_err.ensure(1) == cudaSuccess && h->d_bad.ensure(1) == cudaSuccess;
     for (int i = 0; i < 8 && ok; ++i) ok = cudaEventCreate(&h->ev[i]) == cudaSuccess;
     if (ok) {
+        h->h_seq[0] = 0; h->h_flags2[0] = 0;
         cudaMemset(h->d_S.p, 0, sizeof(double) * S_COUNT);
         cudaMemset(h->d_ticket.p, 0, sizeof(unsigned));
         cudaMemset(h->d_err.p, 0, sizeof(int));
@@ -1012,6 +1053,7 @@ int opmgpu_destroy(opmgpu_handle h)
     h->d_err.release(); h->d_bad.release(); h->d_map9.release(); h->d_cscval.release(); h->d_rhs_stage.release();
     if (h->h_S) cudaFreeHost(h->h_S);
     if (h->h_flags2) cudaFreeHost(h->h_flags2);
+    if (h->h_seq) cudaFreeHost(h->h_seq);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
