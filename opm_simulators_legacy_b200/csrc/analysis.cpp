@@ -57,23 +57,35 @@ void infer_grid(int N, const int* rowptr, const int* colidx, int& nx, int& ny, i
     nx = gx; ny = gy; nz = gz;
 }
 
-void choose_tiling(int nx, int ny, int nz, int P, int& pa, int& pb)
+// Cost model of one sweep (measured on B200, profiles/r01_summary.md): the critical path runs
+// through nx+ny+nz-2 levels and crosses pa+pb-2 tile boundaries -- a store -> poll round trip
+// through L2 between clusters, a distributed-shared-memory store inside one; every CTA also has
+// to stream its own tile from HBM.  A tile level wider than one pass (kLeanStepRows rows) costs
+// extra passes.  caps.max_ctas[log2 cs] = CTAs that can be co-resident at cluster size cs.
+void choose_tiling(int nx, int ny, int nz, const ClusterCaps& caps, int& pa, int& pb, int& ca, int& cb)
 {
-    // Cost model of one sweep (measured on B200, profiles/r01_summary.md): the critical path
-    // runs through nx+ny+nz-2 levels and crosses pa+pb-2 tile boundaries, each a store -> poll
-    // round trip through L2; every CTA also has to stream its own tile from HBM at 1/P of the
-    // bandwidth.  A tile level wider than one pass (kLeanStepRows rows) costs extra passes.
-    constexpr double kCrossUs = 2.5, kLevelUs = 0.4, kRowUs = 0.007;
+    constexpr double kCrossUs = 1.7, kCrossClusterUs = 0.25, kLevelUs = 0.37, kRowUs = 0.007;
+    static const int shapes[][2] = {{1, 1}, {1, 2}, {2, 1}, {2, 2}, {1, 4}, {4, 1}, {2, 4}, {4, 2}};
     double best = 1e300;
-    pa = pb = 1;
-    for (int a = 1; a <= std::min(nx, P); ++a)
-        for (int b = 1; b <= std::min(ny, P / a); ++b) {
-            const int wa = (nx + a - 1) / a, wb = (ny + b - 1) / b;
-            const int passes = (wa * wb + kLeanStepRows - 1) / kLeanStepRows;
-            double t = (a + b - 2) * kCrossUs + (double)(nx + ny + nz - 2) * kLevelUs * passes + (double)wa * wb * nz * kRowUs;
-            if (passes > 1) t *= 1.25;          // the general kernel variant is slower than the lean one
-            if (t < best) { best = t; pa = a; pb = b; }
-        }
+    pa = pb = ca = cb = 1;
+    for (const auto& sh : shapes) {
+        const int sa = sh[0], sb = sh[1], cs = sa * sb;
+        const int lg = cs == 1 ? 0 : (cs == 2 ? 1 : (cs == 4 ? 2 : 3));
+        const int P = caps.max_ctas[lg];
+        if (P < cs) continue;
+        for (int a = sa; a <= std::min(nx, P); a += sa)
+            for (int b = sb; b <= std::min(ny, P / a); b += sb) {
+                const int wa = (nx + a - 1) / a, wb = (ny + b - 1) / b;
+                const int passes = (wa * wb + kLeanStepRows - 1) / kLeanStepRows;
+                if (cs > 1 && passes > 1) continue;            // clusters only with lean programs
+                const int cross_a = a - 1, cross_b = b - 1;
+                const int glob = (a / sa - 1) + (b / sb - 1), intra = cross_a + cross_b - glob;
+                double t = glob * kCrossUs + intra * kCrossClusterUs + (double)(nx + ny + nz - 2) * kLevelUs * passes +
+                           (double)wa * wb * nz * kRowUs;
+                if (passes > 1) t *= 1.25;          // the general kernel variant is slower than the lean one
+                if (t < best) { best = t; pa = a; pb = b; ca = sa; cb = sb; }
+            }
+    }
 }
 
 void build_program(int N, const int* rowptr, const int* colidx, const std::vector<int>& level,
@@ -239,18 +251,26 @@ RecLayout rec_layout(int n, int ntail, int npushx, bool upper, bool has_lists)
 
 // upos_of_row: for the lower program, position of every natural row in the upper program's
 // order (the lower sweep hands its result to the upper sweep in that order); null for upper.
+// owner[r]: CTA of row r; tile[r]: its tile.  A CTA may own several tiles (large grids), which it
+// walks one after the other in ascending tile id; a dependency on another TILE travels through
+// a push slot even when the same CTA owns both.
 void build_pipe_program(int N, const int* rowptr, const int* colidx, const std::vector<int>& diag,
                         const std::vector<int>& level, int nlevels, const std::vector<int>& owner,
-                        int P, bool lower, const std::vector<int>* upos_of_row, PipeProgram& pg)
+                        const std::vector<int>& tile,
+                        int P, bool lower, const std::vector<int>* upos_of_row, PipeProgram& pg, int cs = 1)
 {
     pg = PipeProgram();
     pg.P = P;
+    pg.cluster_size = cs;
+    // a dependency on another CTA of the same cluster travels through distributed shared memory
+    auto same_cluster = [&](int ca_, int cb_) { return cs > 1 && ca_ != cb_ && ca_ / cs == cb_ / cs; };
     pg.nlevels = nlevels;
     const bool upper = !lower;
     std::vector<int> order(N);
     std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
         if (owner[a] != owner[b]) return owner[a] < owner[b];
+        if (tile[a] != tile[b]) return lower ? tile[a] < tile[b] : tile[a] > tile[b];      // tile ids ascend with the L wavefront
         return level[a] < level[b];
     });
     std::vector<int> nblk(N, 0), next(N, 0), npush(N, 0);
@@ -261,7 +281,7 @@ void build_pipe_program(int N, const int* rowptr, const int* colidx, const std::
     for (int r = 0; r < N; ++r)
         for_deps(r, [&](int k) {
             ++nblk[r];
-            if (owner[colidx[k]] != owner[r]) { ++next[r]; ++npush[colidx[k]]; }
+            if (tile[colidx[k]] != tile[r]) { if (!same_cluster(owner[colidx[k]], owner[r])) ++next[r]; ++npush[colidx[k]]; }
         });
     auto tail_of = [&](int r) { return std::max(0, nblk[r] - kFastBlocks); };
     auto pushx_of = [&](int r) { return std::max(0, npush[r] - 2); };
@@ -275,16 +295,16 @@ void build_pipe_program(int N, const int* rowptr, const int* colidx, const std::
         for (int c = 0; c < P; ++c) {
             pg.cta_step_ptr[c] = (int)steps.size();
             const int cbeg = q;
-            int cur_level = -1, rows = 0, tail = 0, ext = 0, pushx = 0;
+            int cur_level = -1, cur_tile = -1, rows = 0, tail = 0, ext = 0, pushx = 0;
             while (q < N && owner[order[q]] == c) {
                 const int r = order[q];
-                const bool fits = rows > 0 && level[r] == cur_level && rows + 1 <= kMaxStepRows &&
+                const bool fits = rows > 0 && level[r] == cur_level && tile[r] == cur_tile && rows + 1 <= kMaxStepRows &&
                                   ext + next[r] <= kMaxStepExt &&
                                   rec_layout(rows + 1, tail + tail_of(r), pushx + pushx_of(r), upper, true).total <= (size_t)kMaxStepBytes;
                 if (!fits) {
                     if (rows > 0) steps.back().q1 = q;
                     steps.push_back({q, q});
-                    cur_level = level[r]; rows = tail = ext = pushx = 0;
+                    cur_level = level[r]; cur_tile = tile[r]; rows = tail = ext = pushx = 0;
                     if (rec_layout(1, tail_of(r), pushx_of(r), upper, true).total > (size_t)kMaxStepBytes || next[r] > kMaxStepExt)
                         return;                           // a single row exceeds a record: not pipelinable
                 }
@@ -308,19 +328,23 @@ void build_pipe_program(int N, const int* rowptr, const int* colidx, const std::
         for (int c = 0; c < P; ++c) {
             pg.cta_ext_base[c] = base;
             long long e = 0;
+            int cx = 0;
             while (q < N && owner[order[q]] == c) {
                 const int r = order[q];
                 for_deps(r, [&](int k) {
                     const int j = colidx[k];
-                    if (owner[j] != c) { push_slot[push_fill[j]++] = base + e; ++e; }
+                    if (tile[j] == tile[r]) return;
+                    if (same_cluster(owner[j], c)) { push_slot[push_fill[j]++] = kPushDsmem | ((c % cs) << 20) | cx; ++cx; }
+                    else { push_slot[push_fill[j]++] = base + e; ++e; }
                 });
                 ++q;
             }
             base += e;
+            pg.max_cx = std::max(pg.max_cx, cx);
         }
         pg.cta_ext_base[P] = base;
         pg.total_ext = base;
-        if (base >= (1LL << 31)) return;
+        if (base >= (1LL << 30) || pg.max_cx > kMaxCxEntries) return;
     }
     // program-order positions (rhs segments are fetched by bulk copies: even row counts)
     pg.step_rhs_row.resize(steps.size());
@@ -354,7 +378,7 @@ void build_pipe_program(int N, const int* rowptr, const int* colidx, const std::
     for (int r = 0; r < N; ++r)
         for_deps(r, [&](int k) {
             const int j = colidx[k];
-            if (owner[j] == owner[r] && qlocal[j] + kWindowRows < step_end_q[r]) write_global[j] = 1;
+            if (tile[j] == tile[r] && qlocal[j] + kWindowRows < step_end_q[r]) write_global[j] = 1;
         });
     // record sizes
     size_t total_bytes = 0;
@@ -376,6 +400,7 @@ void build_pipe_program(int N, const int* rowptr, const int* colidx, const std::
     // emit
     for (int c = 0; c < P; ++c) {
         long long e = 0;
+        int cx = 0;
         for (int sidx = pg.cta_step_ptr[c]; sidx < pg.cta_step_ptr[c + 1]; ++sidx) {
             const size_t rec_off = (size_t)pg.step_off16[sidx] * 16;
             unsigned char* rec = pg.buf.data() + rec_off;
@@ -399,7 +424,8 @@ void build_pipe_program(int N, const int* rowptr, const int* colidx, const std::
                 for_deps(r, [&](int k) {
                     const int j = colidx[k];
                     int code;
-                    if (owner[j] != c) code = (kWindowRows + (int)((e++) % kExtRing)) * 3;
+                    if (tile[j] != tile[r] && same_cluster(owner[j], c)) code = (kCxBase + cx++) * 3;
+                    else if (tile[j] != tile[r]) code = (kWindowRows + (int)((e++) % kExtRing)) * 3;
                     else if (qlocal[j] + kWindowRows >= step_end_q[r]) code = (qlocal[j] % kWindowRows) * 3;
                     else code = kDepGlobalBit | j;
                     if (kb < kFastBlocks) {
@@ -448,8 +474,8 @@ void build_pipe_program(int N, const int* rowptr, const int* colidx, const std::
 inline size_t factor_rec_bytes(int n) { return align_up(32 + (size_t)n * (kFRowInts * 4 + kFRowVals * 8), 16); }
 
 void build_factor_pipe_program(int N, const int* rowptr, const int* colidx, const std::vector<int>& diag,
-                               const std::vector<int>& level, const std::vector<int>& owner, int P,
-                               FactorPipeProgram& pg)
+                               const std::vector<int>& level, const std::vector<int>& owner,
+                               const std::vector<int>& tile, int P, FactorPipeProgram& pg)
 {
     pg = FactorPipeProgram();
     pg.P = P;
@@ -457,6 +483,7 @@ void build_factor_pipe_program(int N, const int* rowptr, const int* colidx, cons
     std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
         if (owner[a] != owner[b]) return owner[a] < owner[b];
+        if (tile[a] != tile[b]) return tile[a] < tile[b];
         return level[a] < level[b];
     });
     // every row simple?  slot of A_ji for every lower block (i,j), -1 when absent
@@ -470,7 +497,7 @@ void build_factor_pipe_program(int N, const int* rowptr, const int* colidx, cons
                 if (c2 == r) { ji_slot[k] = kk; continue; }
                 if (std::binary_search(colidx + rowptr[r], colidx + rowptr[r + 1], c2)) return;   // fill off the diagonal
             }
-            if (owner[j] != owner[r]) { ++next[r]; ++npush[j]; }
+            if (tile[j] != tile[r]) { ++next[r]; ++npush[j]; }
         }
     }
     for (int r = 0; r < N; ++r) if (npush[r] > 2) return;
@@ -488,13 +515,13 @@ void build_factor_pipe_program(int N, const int* rowptr, const int* colidx, cons
             pg.cta_step_ptr[c] = (int)steps.size();
             pg.cta_row_base[c] = q;
             const int cbeg = q;
-            int cur_level = -1, rows = 0, ext = 0;
+            int cur_level = -1, cur_tile = -1, rows = 0, ext = 0;
             while (q < N && owner[order[q]] == c) {
                 const int r = order[q];
-                if (rows == 0 || level[r] != cur_level) {
+                if (rows == 0 || level[r] != cur_level || tile[r] != cur_tile) {
                     if (rows > 0) steps.back().q1 = q;
                     steps.push_back({q, q});
-                    cur_level = level[r]; rows = ext = 0;
+                    cur_level = level[r]; cur_tile = tile[r]; rows = ext = 0;
                 }
                 ++rows; ext += next[r];
                 if (rows > kLeanStepRows || ext > kFMaxStepExt) return;
@@ -510,7 +537,7 @@ void build_factor_pipe_program(int N, const int* rowptr, const int* colidx, cons
     for (int r = 0; r < N; ++r)
         for (int k = rowptr[r]; k < diag[r]; ++k) {
             const int j = colidx[k];
-            if (owner[j] == owner[r] && qlocal[j] + kFWindow < step_end_q[r]) return;      // pivot left the window
+            if (tile[j] == tile[r] && qlocal[j] + kFWindow < step_end_q[r]) return;      // pivot left the window
         }
     // push slots: ordinals in consumption order per CTA
     pg.cta_ext_base.assign(P + 1, 0);
@@ -528,7 +555,7 @@ void build_factor_pipe_program(int N, const int* rowptr, const int* colidx, cons
                 const int r = order[q];
                 for (int k = rowptr[r]; k < diag[r]; ++k) {
                     const int j = colidx[k];
-                    if (owner[j] != c) { push_slot[push_fill[j]++] = base + e; ++e; }
+                    if (tile[j] != tile[r]) { push_slot[push_fill[j]++] = base + e; ++e; }
                 }
                 ++q;
             }
@@ -576,7 +603,7 @@ void build_factor_pipe_program(int N, const int* rowptr, const int* colidx, cons
                 int kb = 0;
                 for (int k = rowptr[r]; k < diag[r]; ++k, ++kb) {
                     const int j = colidx[k];
-                    ri[1 + kb] = owner[j] != c ? kFWindow + (int)((e++) % kFRing) : qlocal[j] % kFWindow;
+                    ri[1 + kb] = tile[j] != tile[r] ? kFWindow + (int)((e++) % kFRing) : qlocal[j] % kFWindow;
                     ri[4] |= 1 << kb;
                     ri[8 + kb] = k;
                     pg.val_src.push_back(k); pg.val_dst8.push_back((unsigned)(v8 + 9 + kb * 18));
@@ -598,7 +625,7 @@ void build_factor_pipe_program(int N, const int* rowptr, const int* colidx, cons
 }  // namespace
 
 void analyse_pattern(int N, const int* rowptr, const int* colidx, int P, PatternAnalysis& out,
-                     bool force_simple)
+                     bool force_simple, const ClusterCaps* caps_in)
 {
     out = PatternAnalysis();
     out.N = N;
@@ -637,40 +664,99 @@ void analyse_pattern(int N, const int* rowptr, const int* colidx, int P, Pattern
         for (int i = 0; i < N; ++i) out.lvl_rows[fill[lvlL[i]]++] = i;
     }
     // partition
-    std::vector<int> owner(N, 0);
+    std::vector<int> owner(N, 0), tile(N, 0);
     int nx, ny, nz;
     infer_grid(N, rowptr, colidx, nx, ny, nz);
     out.grid_nx = nx; out.grid_ny = ny; out.grid_nz = nz;
     if (P < 1) P = 1;
-    if (nx > 0 && (long long)nx * ny >= 4) {
-        int pa, pb;
-        choose_tiling(nx, ny, nz, P, pa, pb);
-        if (const char* e = std::getenv("OPMGPU_TILING")) {       // experiments: "AxB"
-            int a = 0, b = 0;
-            if (std::sscanf(e, "%dx%d", &a, &b) == 2 && a >= 1 && b >= 1 && a * b <= P && a <= nx && b <= ny) { pa = a; pb = b; }
+    ClusterCaps caps;
+    if (caps_in) caps = *caps_in;
+    caps.max_ctas[0] = P;
+    if (force_simple) caps.max_ctas[1] = caps.max_ctas[2] = caps.max_ctas[3] = 0;
+    const bool cartesian = nx > 0 && (long long)nx * ny >= 4;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        int cs = 1, Pl = P;
+        if (cartesian) {
+            int pa, pb, ca, cb;
+            choose_tiling(nx, ny, nz, caps, pa, pb, ca, cb);
+            if (const char* e = std::getenv("OPMGPU_TILING")) {       // experiments: "AxB" or "AxB/CxD" (cluster shape)
+                int a = 0, b = 0, c = 1, d = 1;
+                const int got = std::sscanf(e, "%dx%d/%dx%d", &a, &b, &c, &d);
+                if (got < 4) { c = d = 1; }
+                const int lg = c * d == 1 ? 0 : (c * d == 2 ? 1 : (c * d == 4 ? 2 : (c * d == 8 ? 3 : -1)));
+                if (got >= 2 && a >= 1 && b >= 1 && a <= nx && b <= ny && lg >= 0 && a % c == 0 && b % d == 0 &&
+                    a * b <= caps.max_ctas[lg]) { pa = a; pb = b; ca = c; cb = d; }
+            }
+            cs = ca * cb;
+            // Large grids: no tiling with one tile per CTA keeps a tile level within one pass of the
+            // compute warps.  Then cut smaller tiles and give every CTA several, dealt out in
+            // wavefront order (ascending i0 + j0), so that a CTA walks its tiles one after the other
+            // while the wavefront moves on; tile-to-tile dependencies all go through push slots.
+            int rounds = 1;
+            if (cs == 1 && ((nx + pa - 1) / pa) * ((ny + pb - 1) / pb) > kLeanStepRows && !std::getenv("OPMGPU_TILING") &&
+                !std::getenv("OPMGPU_ONE_TILE_PER_CTA")) {
+                double best = 1e300;
+                for (int a = 1; a <= nx; ++a)
+                    for (int b = 1; b <= ny; ++b) {
+                        const int wa = (nx + a - 1) / a, wb = (ny + b - 1) / b;
+                        if (wa * wb > kLeanStepRows || (long long)a * b > 64LL * P) continue;
+                        const int rnd = (a * b + P - 1) / P;
+                        // per-CTA work (rows) first, then the length of the tile chain
+                        const double t = (double)rnd * wa * wb * nz * 0.007 + (double)rnd * (wa + wb + nz) * 0.37 * 0.25 + (a + b) * 0.05;
+                        if (t < best) { best = t; pa = a; pb = b; rounds = rnd; }
+                    }
+            }
+            const int ncx = pa / ca, ncy = pb / cb;
+            Pl = cs > 1 ? ncx * ncy * cs : P;
+            if (std::getenv("OPMGPU_DEBUG"))
+                std::fprintf(stderr, "[opmgpu] sweep tiling %d x %d column tiles, clusters of %d x %d, %d CTAs, %d tile(s) per CTA\n", pa, pb, ca, cb, Pl, rounds);
+            out.tiles_a = pa; out.tiles_b = pb;
+            std::vector<int> tile_id((size_t)pa * pb);
+            if (rounds > 1) {
+                // tile ids in wavefront order; CTA = id % P, so a CTA's tiles ascend with the wavefront
+                std::vector<int> tl((size_t)pa * pb);
+                std::iota(tl.begin(), tl.end(), 0);
+                auto first = [](int t, int parts, int n) { int i = (int)(((long long)t * n + parts - 1) / parts); return i; };
+                std::stable_sort(tl.begin(), tl.end(), [&](int x, int y) {
+                    const int lx = first(x % pa, pa, nx) + first(x / pa, pb, ny), ly = first(y % pa, pa, nx) + first(y / pa, pb, ny);
+                    return lx < ly;
+                });
+                for (size_t k = 0; k < tl.size(); ++k) tile_id[tl[k]] = (int)k;
+            }
+            for (int r = 0; r < N; ++r) {
+                const int i = r % nx, j = (r / nx) % ny;
+                const int a = (int)((long long)i * pa / nx), b = (int)((long long)j * pb / ny);
+                if (rounds > 1) { tile[r] = tile_id[a + pa * b]; owner[r] = tile[r] % P; continue; }
+                // cluster-major CTA numbering: the cs tiles of a ca x cb block are consecutive CTAs
+                owner[r] = cs > 1 ? ((a / ca) + ncx * (b / cb)) * cs + (a % ca) + ca * (b % cb) : a + pa * b;
+                tile[r] = owner[r];
+            }
+        } else {
+            // generic: contiguous share of every level per CTA
+            for (int l = 0; l < nL; ++l) {
+                const int b = out.lvl_ptr[l], sz = out.lvl_ptr[l + 1] - b;
+                for (int q = 0; q < sz; ++q) owner[out.lvl_rows[b + q]] = (int)((long long)q * P / sz);
+            }
+            tile = owner;
         }
-        if (std::getenv("OPMGPU_DEBUG")) std::fprintf(stderr, "[opmgpu] sweep tiling %d x %d column tiles\n", pa, pb);
-        for (int r = 0; r < N; ++r) {
-            const int i = r % nx, j = (r / nx) % ny;
-            const int a = (int)((long long)i * pa / nx), b = (int)((long long)j * pb / ny);
-            owner[r] = a + pa * b;
+        out.P = Pl; out.cluster_size = cs;
+        build_pipe_program(N, rowptr, colidx, out.diag, lvlU, nU, owner, tile, Pl, false, nullptr, out.pipeU, cs);
+        if (out.pipeU.valid) {
+            std::vector<int> upos(N, 0);
+            for (size_t q = 0; q < out.pipeU.perm_row.size(); ++q)
+                if (out.pipeU.perm_row[q] >= 0) upos[out.pipeU.perm_row[q]] = (int)q;
+            build_pipe_program(N, rowptr, colidx, out.diag, lvlL, nL, owner, tile, Pl, true, &upos, out.pipeL, cs);
         }
-    } else {
-        // generic: contiguous share of every level per CTA
-        for (int l = 0; l < nL; ++l) {
-            const int b = out.lvl_ptr[l], sz = out.lvl_ptr[l + 1] - b;
-            for (int q = 0; q < sz; ++q) owner[out.lvl_rows[b + q]] = (int)((long long)q * P / sz);
+        // clusters are only supported by the lean kernels: otherwise lay everything out again without
+        if (cs > 1 && !(out.pipeL.valid && out.pipeU.valid && out.pipeL.lean && out.pipeU.lean)) {
+            caps.max_ctas[1] = caps.max_ctas[2] = caps.max_ctas[3] = 0;
+            continue;
         }
-    }
-    build_pipe_program(N, rowptr, colidx, out.diag, lvlU, nU, owner, P, false, nullptr, out.pipeU);
-    if (out.pipeU.valid) {
-        std::vector<int> upos(N, 0);
-        for (size_t q = 0; q < out.pipeU.perm_row.size(); ++q)
-            if (out.pipeU.perm_row[q] >= 0) upos[out.pipeU.perm_row[q]] = (int)q;
-        build_pipe_program(N, rowptr, colidx, out.diag, lvlL, nL, owner, P, true, &upos, out.pipeL);
+        P = Pl;
+        break;
     }
     if (out.pipeL.valid && out.pipeU.valid && !force_simple)
-        build_factor_pipe_program(N, rowptr, colidx, out.diag, lvlL, owner, P, out.pipeF);
+        build_factor_pipe_program(N, rowptr, colidx, out.diag, lvlL, owner, tile, P, out.pipeF);
     out.nlevL = nL; out.nlevU = nU;
     build_program(N, rowptr, colidx, lvlL, nL, owner, P, true, out.lower);       // also drives the factorisation
     if (force_simple || !out.pipeL.valid || !out.pipeU.valid) {
@@ -691,7 +777,10 @@ bool interpret_pipe_program(const PipeProgram& pg, bool upper, const double* rhs
     std::vector<double> ext((size_t)std::max<long long>(pg.total_ext, 1) * 3);
     std::vector<unsigned char> ext_valid((size_t)std::max<long long>(pg.total_ext, 1), 0);
     std::vector<int> cur(P);
-    std::vector<std::vector<double>> dep(P, std::vector<double>((size_t)(kDepZeroSlot + 1) * 3, 0.0));
+    const int cs = pg.cluster_size;
+    const size_t ncx = (size_t)std::max(pg.max_cx, 1);
+    std::vector<std::vector<double>> dep(P, std::vector<double>((size_t)(kCxBase + ncx) * 3, 0.0));
+    std::vector<std::vector<unsigned char>> cx_valid(P, std::vector<unsigned char>(ncx, 0));
     std::vector<long long> qbase(P, 0), ext_seen(P, 0);
     for (int c = 0; c < P; ++c) cur[c] = pg.cta_step_ptr[c];
     bool progress = true, done = false;
@@ -718,6 +807,12 @@ bool interpret_pipe_program(const PipeProgram& pg, bool upper, const double* rhs
                 bool ready = true;
                 for (long long e = ext_begin; e < ext_end && ready; ++e)
                     if (!ext_valid[pg.cta_ext_base[c] + e]) ready = false;
+                // results delivered through distributed shared memory are validated entry by entry
+                for (int rr = 0; rr < n && ready; ++rr)
+                    for (int k = 0; k < kFastBlocks; ++k) {
+                        const int code = rowints[8 * rr + 1 + k];
+                        if (code >= kCxBase * 3 && !cx_valid[c][code / 3 - kCxBase]) ready = false;
+                    }
                 if (!ready) break;
                 // the helper stages pushed results into the ring part of the dependency array
                 for (long long e = ext_begin; e < ext_end; ++e)
@@ -769,6 +864,12 @@ bool interpret_pipe_program(const PipeProgram& pg, bool upper, const double* rhs
                     if (rowinfo_rr & kRowWriteGlobal)
                         for (int t = 0; t < 3; ++t) work[(size_t)row * 3 + t] = res[(size_t)rr * 3 + t];
                     auto push_to = [&](int slot_id) {
+                        if (slot_id & kPushDsmem) {      // into the shared memory of a CTA of the same cluster
+                            const int target = (c / cs) * cs + ((slot_id >> 20) & 0xf), idx = slot_id & 0xfffff;
+                            for (int u = 0; u < 3; ++u) dep[target][(size_t)(kCxBase + idx) * 3 + u] = res[(size_t)rr * 3 + u];
+                            cx_valid[target][idx] = 1;
+                            return;
+                        }
                         for (int u = 0; u < 3; ++u) ext[(size_t)slot_id * 3 + u] = res[(size_t)rr * 3 + u];
                         ext_valid[slot_id] = 1;
                     };
@@ -982,9 +1083,13 @@ extern "C" int opmgpu_debug_host_program_apply(int N, const int* rowptr, const i
 {
     using namespace opmgpu;
     PatternAnalysis an;
-    analyse_pattern(N, rowptr, colidx, P, an, false);
+    ClusterCaps caps;                     // OPMGPU_TEST_CLUSTER_CTAS="p2,p4,p8": co-resident CTAs per cluster size
+    if (const char* e = std::getenv("OPMGPU_TEST_CLUSTER_CTAS"))
+        std::sscanf(e, "%d,%d,%d", &caps.max_ctas[1], &caps.max_ctas[2], &caps.max_ctas[3]);
+    analyse_pattern(N, rowptr, colidx, P, an, false, &caps);
     if (an.missing_diag_row >= 0) return -1;
     if (!an.pipeL.valid || !an.pipeU.valid) return -2;
+    if (info) info[7] = 0;
     for (PipeProgram* pg : {&an.pipeL, &an.pipeU}) {
         double* base = (double*)pg->buf.data();
         for (size_t b = 0; b < pg->val_src.size(); ++b)
@@ -1006,7 +1111,7 @@ extern "C" int opmgpu_debug_host_program_apply(int N, const int* rowptr, const i
         info[0] = an.grid_nx; info[1] = an.grid_ny; info[2] = an.grid_nz;
         info[3] = an.pipeL.nlevels; info[4] = an.pipeL.max_step_rows; info[5] = an.pipeL.max_step_bytes;
         info[6] = (int)std::min<long long>(an.pipeL.total_ext, 0x7fffffff);
-        info[7] = (int)(an.pipeL.cta_step_ptr[P]);
+        info[7] = (int)(an.pipeL.cta_step_ptr[an.P]);
     }
     return 0;
 }

@@ -83,11 +83,22 @@ constexpr int kMaxStepRows = 240;
 constexpr int kMaxStepBytes = 64 * 1024;
 constexpr int kMaxStepExt = kExtRing - 96;
 constexpr int kLeanStepRows = 96;         // rows one pass of the compute warps covers (sweep_pipe.cuh: kPipeRowsPerPass)
+// Thread-block clusters (lean programs only): CTAs cs*c .. cs*c+cs-1 form a cluster; a result
+// needed by another CTA of the same cluster is written by its producer straight into that
+// CTA's shared memory (distributed shared memory), into a per-CTA array of 3-double entries that
+// follows the dependency array: dep code = (kCxBase + index) * 3.  Entries are written once per
+// sweep (no reuse), initialised to all-ones by the consumer before the cluster starts.
+// push ids: kPushDsmem | rank in cluster << 20 | entry index.
+constexpr int kCxBase = kDepZeroSlot + 2;
+constexpr int kPushDsmem = 0x40000000;
+constexpr int kMaxCxEntries = 3072;       // 72 KB of shared memory at most
+struct ClusterCaps { int max_ctas[4] = {0, 0, 0, 0}; };   // co-resident CTAs at cluster size 1, 2, 4, 8
 
 struct PipeProgram {
     bool valid = false;
     bool lean = false;                        // no slow rows, no own-global reads, steps <= one pass
     int P = 0, nlevels = 0;
+    int cluster_size = 1, max_cx = 0;            // CTAs per cluster; most intra-cluster entries of a CTA
     int max_step_bytes = 0, max_step_rows = 0;   // rows padded to even
     long long total_ext = 0;
     long long nperm = 0;                      // length (rows) of vectors in this program's order
@@ -153,6 +164,9 @@ struct PatternAnalysis {
     // natural-order level sets of the lower triangle (factorisation)
     std::vector<int> lvl_ptr, lvl_rows;
     int grid_nx = 0, grid_ny = 0, grid_nz = 0;   // inferred Cartesian structure (0 = none)
+    int P = 0;                                   // CTAs every program is laid out for (launch size)
+    int cluster_size = 1;                        // sweeps are launched in clusters of this many CTAs
+    int tiles_a = 0, tiles_b = 0;                // column tiling (Cartesian patterns)
     SweepProgram lower, upper;
     PipeProgram pipeL, pipeU;
     FactorPipeProgram pipeF;
@@ -162,7 +176,7 @@ struct PatternAnalysis {
 
 // P = number of persistent CTAs the sweeps will be launched with.
 void analyse_pattern(int N, const int* rowptr, const int* colidx, int P, PatternAnalysis& out,
-                     bool force_simple = false);
+                     bool force_simple = false, const ClusterCaps* caps = nullptr);
 
 // Sequential interpreter of a pipelined program (debug / CPU tests of the host analysis).
 bool interpret_pipe_program(const PipeProgram& pg, bool upper, const double* rhs_perm, double* work,
