@@ -64,7 +64,8 @@ void infer_grid(int N, const int* rowptr, const int* colidx, int& nx, int& ny, i
 // extra passes.  caps.max_ctas[log2 cs] = CTAs that can be co-resident at cluster size cs.
 void choose_tiling(int nx, int ny, int nz, const ClusterCaps& caps, int& pa, int& pb, int& ca, int& cb)
 {
-    constexpr double kCrossUs = 1.7, kCrossClusterUs = 0.25, kLevelUs = 0.37, kRowUs = 0.007;
+    // (constants reproduce the measured ranking of tilings at 100^3, profiles/r01_summary.md)
+    constexpr double kCrossUs = 1.7, kCrossClusterUs = 0.9, kLevelUs = 0.37, kRowUs = 0.004;
     static const int shapes[][2] = {{1, 1}, {1, 2}, {2, 1}, {2, 2}, {1, 4}, {4, 1}, {2, 4}, {4, 2}};
     double best = 1e300;
     pa = pb = ca = cb = 1;

@@ -112,7 +112,7 @@ struct PipeDevMem {
     DevArr<long long> cta_ext_base;
     DevArr<double> ext, rhs_perm;
     size_t nval = 0, next = 0, nperm = 0;
-    int P = 0, nstages = 0, stage_bytes = 0, rhs_bytes = 0;
+    int P = 0, nstages = 0, stage_bytes = 0, rhs_bytes = 0, cluster_size = 1, cx_bytes = 0;
     bool lean = false;
     size_t smem = 0;
     void release()
@@ -161,6 +161,8 @@ struct opmgpu_solver {
     FactorPipeDevMem pipeF;
     bool factor_tile = false;      // OPMGPU_FACTOR_TILE=1: keep the flag-synchronised tile kernel
     bool lu_lazy = false;          // the pipelined factorisation left only pivots: d_lu is built on demand
+    ClusterCaps caps;              // co-resident CTAs of the cluster variants of the sweep kernels
+    int cluster_size = 1;          // thread-block cluster size the sweeps are launched with
     bool use_pipe = false, force_simple = false, factor_by_levels = false, spmv_tma = true;
     int trace_cta = -1;
     DevArr<long long> d_trace;
@@ -333,12 +335,14 @@ int upload_pipe(opmgpu_handle h, const PipeProgram& p, PipeDevMem& d)
     // ring geometry: as many stages as fit next to the dependency array
     d.stage_bytes = (p.max_step_bytes + 15) / 16 * 16;
     d.rhs_bytes = (p.max_step_rows * 24 + 15) / 16 * 16;
-    const size_t fixed = pipe_smem_bytes(0, 0, 0);
+    d.cluster_size = p.cluster_size;
+    d.cx_bytes = p.cluster_size > 1 ? (std::max(p.max_cx, 1) * 24 + 15) / 16 * 16 : 0;
+    const size_t fixed = pipe_smem_bytes(0, 0, 0, d.cx_bytes);
     const size_t per_stage = (size_t)d.stage_bytes + d.rhs_bytes;
-    int S = (int)(((size_t)h->max_smem_optin - fixed) / per_stage);
+    int S = (size_t)h->max_smem_optin > fixed ? (int)(((size_t)h->max_smem_optin - fixed) / per_stage) : 0;
     d.nstages = std::min(S, kPipeMaxStages);
     if (const char* e = std::getenv("OPMGPU_PIPE_STAGES")) d.nstages = std::max(kPipeGroups, std::min(d.nstages, std::atoi(e)));
-    d.smem = pipe_smem_bytes(d.nstages, d.stage_bytes, d.rhs_bytes);
+    d.smem = pipe_smem_bytes(d.nstages, d.stage_bytes, d.rhs_bytes, d.cx_bytes);
     return 0;
 }
 
@@ -379,6 +383,7 @@ PipeDev pipe_dev(const PipeDevMem& d)
     p.stage_bytes = d.stage_bytes; p.rhs_bytes = d.rhs_bytes; p.nstages = d.nstages;
     p.trace = nullptr; p.trace_cta = -1; p.gtrace = nullptr; p.gtrace_steps = 0;
     p.dbg = getenv("OPMGPU_SDEBUG") ? atoi(getenv("OPMGPU_SDEBUG")) : 0;
+    p.cluster_size = d.cluster_size; p.cx_bytes = d.cx_bytes;
     return p;
 }
 
@@ -411,7 +416,8 @@ int set_pattern(opmgpu_handle h, int N, int nnzb, const int* rowptr, const int* 
         }
     }
     h->have_pattern = h->have_values = h->have_factors = false;
-    analyse_pattern(N, rowptr, colidx, h->sweep_ctas, h->an, h->force_simple);
+    analyse_pattern(N, rowptr, colidx, h->sweep_ctas, h->an, h->force_simple, &h->caps);
+    h->cluster_size = h->an.cluster_size;
     if (h->an.missing_diag_row >= 0) {
         h->err = "diagonal entry missing in block row " + std::to_string(h->an.missing_diag_row);
         return OPMGPU_SINGULAR_BLOCK;
@@ -428,6 +434,14 @@ int set_pattern(opmgpu_handle h, int N, int nnzb, const int* rowptr, const int* 
     if (h->use_pipe) {
         if ((rc = upload_pipe(h, h->an.pipeL, h->pipeL))) return rc;
         if ((rc = upload_pipe(h, h->an.pipeU, h->pipeU))) return rc;
+        if ((h->pipeL.nstages < 3 || h->pipeU.nstages < 3) && h->cluster_size > 1) {
+            // not enough shared memory left for the record ring next to the intra-cluster entries
+            ClusterCaps none;
+            analyse_pattern(N, rowptr, colidx, h->sweep_ctas, h->an, h->force_simple, &none);
+            h->cluster_size = 1;
+            if ((rc = upload_pipe(h, h->an.pipeL, h->pipeL))) return rc;
+            if ((rc = upload_pipe(h, h->an.pipeU, h->pipeU))) return rc;
+        }
         if (h->pipeL.nstages < 3 || h->pipeU.nstages < 3) h->use_pipe = false;
     }
     h->pipeF.valid = false;
@@ -437,6 +451,7 @@ int set_pattern(opmgpu_handle h, int N, int nnzb, const int* rowptr, const int* 
     if (!h->pipeF.valid) h->pipeF.release();
     if (!h->use_pipe) {
         if (h->an.upper.prow.empty()) analyse_pattern(N, rowptr, colidx, h->sweep_ctas, h->an, true);
+        h->cluster_size = 1;
         if ((rc = upload_program(h, h->an.lower, h->progL, false))) return rc;
         if ((rc = upload_program(h, h->an.upper, h->progU, true))) return rc;
         h->pipeL.release(); h->pipeU.release();
@@ -674,6 +689,27 @@ int factor(opmgpu_handle h, int* bad_row)
     return OPMGPU_OK;
 }
 
+// cooperative launch of a pipelined sweep, in thread-block clusters when the program asks for them
+int launch_sweep(opmgpu_handle h, bool upper, const PipeDevMem& d, void** args)
+{
+    if (d.cluster_size > 1) {
+        const void* fn = upper ? (const void*)ilu0_sweep_pipe_kernel<true, true, true> : (const void*)ilu0_sweep_pipe_kernel<false, true, true>;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(d.P); cfg.blockDim = dim3(kPipeThreads); cfg.dynamicSmemBytes = d.smem; cfg.stream = h->stream;
+        cudaLaunchAttribute at[2];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = d.cluster_size; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        at[1].id = cudaLaunchAttributeCooperative; at[1].val.cooperative = 1;
+        cfg.attrs = at; cfg.numAttrs = 2;
+        CK(cudaLaunchKernelExC(&cfg, fn, args));
+        return 0;
+    }
+    const void* fn = upper ? (d.lean ? (const void*)ilu0_sweep_pipe_kernel<true, true> : (const void*)ilu0_sweep_pipe_kernel<true, false>)
+                           : (d.lean ? (const void*)ilu0_sweep_pipe_kernel<false, true> : (const void*)ilu0_sweep_pipe_kernel<false, false>);
+    CK(cudaLaunchCooperativeKernel(fn, dim3(d.P), dim3(kPipeThreads), args, d.smem, h->stream));
+    return 0;
+}
+
 // v = w U^-1 L^-1 d, all device pointers; asynchronous
 int apply_precond(opmgpu_handle h, double w, const double* d, double* v)
 {
@@ -690,7 +726,7 @@ int apply_precond(opmgpu_handle h, double w, const double* d, double* v)
             const double* rhs = h->pipeL.rhs_perm.p; double* work = h->d_yL.p; double* hand = h->pipeU.rhs_perm.p;
             double* out = nullptr; int* err = h->d_err.p;
             void* args[] = {&pg, &rhs, &work, &hand, &out, &w, (void*)&scale, &err};
-            CK(cudaLaunchCooperativeKernel(h->pipeL.lean ? (void*)ilu0_sweep_pipe_kernel<false, true> : (void*)ilu0_sweep_pipe_kernel<false, false>, dim3(h->pipeL.P), dim3(kPipeThreads), args, h->pipeL.smem, h->stream));
+            if (int rc = launch_sweep(h, false, h->pipeL, args)) return rc;
         }
         {
             PipeDev pg = pipe_dev(h->pipeU);
@@ -699,7 +735,7 @@ int apply_precond(opmgpu_handle h, double w, const double* d, double* v)
             const double* rhs = h->pipeU.rhs_perm.p; double* work = h->d_vU.p; double* hand = nullptr;
             double* out = v; int* err = h->d_err.p;
             void* args[] = {&pg, &rhs, &work, &hand, &out, &w, (void*)&scale, &err};
-            CK(cudaLaunchCooperativeKernel(h->pipeU.lean ? (void*)ilu0_sweep_pipe_kernel<true, true> : (void*)ilu0_sweep_pipe_kernel<true, false>, dim3(h->pipeU.P), dim3(kPipeThreads), args, h->pipeU.smem, h->stream));
+            if (int rc = launch_sweep(h, true, h->pipeU, args)) return rc;
         }
         h->launches += 3;
         return 0;
@@ -996,6 +1032,32 @@ int opmgpu_create(int device, opmgpu_handle* out)
     cudaFuncSetAttribute(spmv3_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
     cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     cudaFuncSetAttribute(ilu0_factor_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
+    cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
+    cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
+    {
+        // how many CTAs of the cluster variants can be co-resident (one CTA per SM, all of its
+        // shared memory): GPCs do not divide evenly into clusters of 4 or 8
+        int want = 8;                                        // OPMGPU_CLUSTER=0: no clusters; 2/4/8: largest size tried
+        if (const char* s = getenv("OPMGPU_CLUSTER")) want = atoi(s);
+        if (h->world > 1) want = 0;
+        for (int lg = 1; lg <= 3; ++lg) {
+            const int cs = 1 << lg;
+            if (cs > want) break;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(cs * h->sm_count); cfg.blockDim = dim3(kPipeThreads); cfg.dynamicSmemBytes = (size_t)h->max_smem_optin;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            int ncl = 0;
+            if (cudaOccupancyMaxActiveClusters(&ncl, (const void*)ilu0_sweep_pipe_kernel<true, true, true>, &cfg) == cudaSuccess)
+                h->caps.max_ctas[lg] = std::min(ncl * cs, h->sm_count);
+            else
+                cudaGetLastError();
+        }
+        if (getenv("OPMGPU_DEBUG"))
+            fprintf(stderr, "[opmgpu] co-resident CTAs at cluster size 2/4/8: %d/%d/%d\n", h->caps.max_ctas[1], h->caps.max_ctas[2], h->caps.max_ctas[3]);
+    }
     cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
     cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
     cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);

@@ -72,6 +72,8 @@ struct PipeDev {
     long long* gtrace;           // optional (debug): %globaltimer stamps of every CTA, [cta][gtrace_steps][8], then helper deliveries [cta][512][4]
     int gtrace_steps;
     int dbg;                     // experiments: bit 0 = skip the result stores to HBM
+    int cluster_size;            // CTAs per thread-block cluster (1: none)
+    int cx_bytes;                // intra-cluster result entries of a CTA (analysis.hpp: kCxBase), bytes
 };
 __device__ __forceinline__ long long pipe_gtime() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 // timer read that cannot issue before `dep` is available (stamps after barriers / loads / chains)
@@ -86,9 +88,14 @@ struct PipeCtl {
     volatile int abort_flag;
 };
 
-__host__ __device__ inline size_t pipe_smem_bytes(int nstages, int stage_bytes, int rhs_bytes)
+// dependency array (window | pushed ring | zero entry) followed by the intra-cluster entries
+__host__ __device__ inline size_t pipe_dep_bytes(int cx_bytes)
 {
-    return 512 + (size_t)kPipeDepBytes + (size_t)nstages * ((size_t)stage_bytes + rhs_bytes);
+    return cx_bytes > 0 ? ((size_t)kCxBase * 24 + (size_t)cx_bytes + 127) / 128 * 128 : (size_t)kPipeDepBytes;
+}
+__host__ __device__ inline size_t pipe_smem_bytes(int nstages, int stage_bytes, int rhs_bytes, int cx_bytes = 0)
+{
+    return 512 + pipe_dep_bytes(cx_bytes) + (size_t)nstages * ((size_t)stage_bytes + rhs_bytes);
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -265,9 +272,21 @@ __device__ __noinline__ void sweep_extra_pushes(const unsigned char* rec, int r,
 
 // one block row, critical part: dependency loads, three 9-FMA chains in the reference's order
 // (bit parity), Dinv (upper), window store, pushes to other CTAs
-template <bool UPPER, bool LEAN>
+// an entry written by another CTA of the cluster (self-validating: all-ones = not there yet)
+__device__ __forceinline__ bool cx_wait(uint32_t a, double& y0, double& y1, double& y2, PipeCtl* ctl, int* err)
+{
+    unsigned spins = 0;
+    while (__double_as_longlong(y0) == -1LL || __double_as_longlong(y1) == -1LL || __double_as_longlong(y2) == -1LL) {
+        if (++spins > kPipeSpinLimit * 8u || ctl->abort_flag) { ctl->abort_flag = 1; atomicExch(err, 8); return false; }
+        y0 = lds_f64(a); y1 = lds_f64(a + 8); y2 = lds_f64(a + 16);
+    }
+    return true;
+}
+
+template <bool UPPER, bool LEAN, bool CX = false>
 __device__ __forceinline__ void sweep_row_chain(const StepPre<UPPER>& p, const unsigned char* rec, int r,
-                                                double* dep, uint32_t dep_s, const double* work, double* ext, double (&acc)[3])
+                                                double* dep, uint32_t dep_s, const double* work, double* ext, double (&acc)[3],
+                                                PipeCtl* ctl = nullptr, int* err = nullptr)
 {
     acc[0] = acc[1] = acc[2] = 0.0;
     if (p.on) {
@@ -277,6 +296,11 @@ __device__ __forceinline__ void sweep_row_chain(const StepPre<UPPER>& p, const u
             y[0] = lds_f64(a0); y[1] = lds_f64(a0 + 8); y[2] = lds_f64(a0 + 16);
             y[3] = lds_f64(a1); y[4] = lds_f64(a1 + 8); y[5] = lds_f64(a1 + 16);
             y[6] = lds_f64(a2); y[7] = lds_f64(a2 + 8); y[8] = lds_f64(a2 + 16);
+            if (CX && max(p.ri0.y, max(p.ri0.z, p.ri0.w)) >= kCxBase * 3) {      // delivered by a CTA of the cluster?
+                if (p.ri0.y >= kCxBase * 3) cx_wait(a0, y[0], y[1], y[2], ctl, err);
+                if (p.ri0.z >= kCxBase * 3) cx_wait(a1, y[3], y[4], y[5], ctl, err);
+                if (p.ri0.w >= kCxBase * 3) cx_wait(a2, y[6], y[7], y[8], ctl, err);
+            }
         } else {
             const double* y0 = dep_ptr(p.ri0.y, dep, work); const double* y1 = dep_ptr(p.ri0.z, dep, work);
             const double* y2 = dep_ptr(p.ri0.w, dep, work);
@@ -308,13 +332,26 @@ __device__ __forceinline__ void sweep_row_chain(const StepPre<UPPER>& p, const u
 }
 // results other CTAs wait for.  Issued right after the hand-over to the next group: the
 // in-tile hand-over is on the critical path of every step, a tile crossing only once per tile.
-template <bool UPPER, bool LEAN>
+// result -> entry `id & 0xfffff` of CTA `(id >> 20) & 15` of this cluster (distributed shared memory)
+__device__ __forceinline__ void push_dsmem(uint32_t cx_s, int id, const double (&acc)[3])
+{
+    const uint32_t la = cx_s + 24u * (uint32_t)(id & 0xfffff);
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"((id >> 20) & 0xf));
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra), "d"(acc[0]) : "memory");
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra + 8), "d"(acc[1]) : "memory");
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra + 16), "d"(acc[2]) : "memory");
+}
+
+template <bool UPPER, bool LEAN, bool CX = false>
 __device__ __forceinline__ void sweep_row_pushes(const StepPre<UPPER>& p, const unsigned char* rec, int r,
-                                                 double* ext, const double (&acc)[3])
+                                                 double* ext, const double (&acc)[3], uint32_t cx_s = 0)
 {
     if (p.on) {
-        if (p.ri1.y >= 0) { double* sl = ext + (size_t)p.ri1.y * 3; push_f64(sl, acc[0]); push_f64(sl + 1, acc[1]); push_f64(sl + 2, acc[2]); }
-        if (p.ri1.z >= 0) { double* sl = ext + (size_t)p.ri1.z * 3; push_f64(sl, acc[0]); push_f64(sl + 1, acc[1]); push_f64(sl + 2, acc[2]); }
+        if (CX && p.ri1.y >= 0 && (p.ri1.y & kPushDsmem)) push_dsmem(cx_s, p.ri1.y, acc);
+        else if (p.ri1.y >= 0) { double* sl = ext + (size_t)p.ri1.y * 3; push_f64(sl, acc[0]); push_f64(sl + 1, acc[1]); push_f64(sl + 2, acc[2]); }
+        if (CX && p.ri1.z >= 0 && (p.ri1.z & kPushDsmem)) push_dsmem(cx_s, p.ri1.z, acc);
+        else if (p.ri1.z >= 0) { double* sl = ext + (size_t)p.ri1.z * 3; push_f64(sl, acc[0]); push_f64(sl + 1, acc[1]); push_f64(sl + 2, acc[2]); }
         if (!LEAN && (p.ri0.x & kRowSlow)) sweep_extra_pushes(rec, r, ext, acc);
     }
 }
@@ -358,7 +395,9 @@ __device__ __noinline__ void sweep_extra_rows(const unsigned char* stage, int rh
 
 // LEAN: the program has no slow rows, no own-result reads from HBM and no step wider than one
 // pass (every Cartesian stencil case): those paths are compiled out.
-template <bool UPPER, bool LEAN>
+// CX: launched in thread-block clusters; results for CTAs of the same cluster are stored straight
+// into their shared memory (a tile crossing then costs a shared-memory round trip, not an L2 poll).
+template <bool UPPER, bool LEAN, bool CX = false>
 __global__ void __launch_bounds__(kPipeThreads, 1)
 ilu0_sweep_pipe_kernel(PipeDev pg, const double* __restrict__ rhs_perm, double* work, double* hand_off,
                        double* out, double w, int scale, int* err)
@@ -366,7 +405,7 @@ ilu0_sweep_pipe_kernel(PipeDev pg, const double* __restrict__ rhs_perm, double* 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     PipeCtl* ctl = reinterpret_cast<PipeCtl*>(smem_raw);
     double* dep = reinterpret_cast<double*>(smem_raw + 512);      // window | pushed ring | zero entry
-    unsigned char* stages = smem_raw + 512 + kPipeDepBytes;
+    unsigned char* stages = smem_raw + 512 + pipe_dep_bytes(CX ? pg.cx_bytes : 0);
     const int S = pg.nstages;
     const size_t stage_stride = (size_t)pg.stage_bytes + pg.rhs_bytes;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -382,10 +421,19 @@ ilu0_sweep_pipe_kernel(PipeDev pg, const double* __restrict__ rhs_perm, double* 
         dep[kDepZeroSlot * 3] = 0.0; dep[kDepZeroSlot * 3 + 1] = 0.0; dep[kDepZeroSlot * 3 + 2] = 0.0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (CX) {
+        // intra-cluster entries start out empty; nobody may write into them before that
+        long long* cx = reinterpret_cast<long long*>(dep + (size_t)kCxBase * 3);
+        for (int i = tid; i < pg.cx_bytes / 8; i += kPipeThreads) cx[i] = -1LL;
+        __syncthreads();
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
     __syncthreads();
-    if (nsteps == 0) return;
+    if (!CX && nsteps == 0) return;
 
-    if (warp == 0) {
+    if (nsteps == 0) {
+        // (cluster launch) nothing to do, but stay until the cluster is done
+    } else if (warp == 0) {
         // ------------------------------------------------ TMA producer (one elected lane)
         if (lane == 0) {
             for (int i = 0; i < nsteps; ++i) {
@@ -559,7 +607,7 @@ ilu0_sweep_pipe_kernel(PipeDev pg, const double* __restrict__ rhs_perm, double* 
             if (gt) { gtr[s * 8 + 2] = pipe_gtime_after(ctl->ext_ready); gtr[s * 8 + 4] = p.ext_end; gtr[s * 8 + 5] = p.n; }
             if (tr) pg.trace[s * 16 + 5] = pipe_clock_after(ctl->ext_ready);
             double acc[3];
-            sweep_row_chain<UPPER, LEAN>(p, stage + pg.rhs_bytes, r_first, dep, dep_s, work, pg.ext, acc);
+            sweep_row_chain<UPPER, LEAN, CX>(p, stage + pg.rhs_bytes, r_first, dep, dep_s, work, pg.ext, acc, ctl, err);
             if (!LEAN && p.n > kPipeRowsPerPass)
                 sweep_extra_rows<UPPER>(stage, pg.rhs_bytes, p.n, r_first, dep, dep_s, work, hand_off, out, pg.ext, w, scale);
             if (tr) { pg.trace[s * 16 + 2] = pipe_clock_after(__double2hiint(acc[0])); pg.trace[s * 16 + 4] = p.n; }
@@ -568,7 +616,7 @@ ilu0_sweep_pipe_kernel(PipeDev pg, const double* __restrict__ rhs_perm, double* 
             const bool gt_rb = gt && p.on && p.ri1.y >= 0;
             if (gt_rb) asm volatile("ld.relaxed.gpu.global.s64 %0, [%1];" : "=l"(rb) : "l"(pg.ext + (size_t)p.ri1.y * 3) : "memory");
             asm volatile("bar.arrive %0, %1;" ::"r"(bar_own), "n"(NPP) : "memory");                // step s done
-            sweep_row_pushes<UPPER, LEAN>(p, stage + pg.rhs_bytes, r_first, pg.ext, acc);
+            sweep_row_pushes<UPPER, LEAN, CX>(p, stage + pg.rhs_bytes, r_first, pg.ext, acc, dep_s + 24u * (uint32_t)kCxBase);
             if (!LEAN) {            // tail lists of slow rows are read from the stage during the chain
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&ctl->empty[st]);
@@ -585,6 +633,10 @@ ilu0_sweep_pipe_kernel(PipeDev pg, const double* __restrict__ rhs_perm, double* 
         }
         // consume the last hand-over addressed to this group so no barrier is left half-arrived
         if (nsteps > 0 && (nsteps % G) == g) asm volatile("bar.sync %0, %1;" ::"r"(bar_prev), "n"(NPP) : "memory");
+    }
+    if (CX) {
+        // other CTAs of the cluster may still be writing into this CTA's shared memory
+        asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
     }
 }
 

@@ -78,6 +78,31 @@ def test_sweep_programs_are_exact_on_cartesian_grids(oracle, dims, P):
         assert np.array_equal(out, oracle.ilu0_apply(rp, ci, lu, w, b))
 
 
+@pytest.mark.parametrize("dims,P", [((40, 40, 20), 148), ((100, 100, 4), 148), ((24, 20, 12), 16)])
+def test_sweep_programs_with_thread_block_clusters(oracle, dims, P, monkeypatch):
+    """Cluster-major tile numbering and results delivered through distributed shared memory
+    (dep codes >= kCxBase, push ids with kPushDsmem): interpreted programs stay bit-exact."""
+    monkeypatch.setenv("OPMGPU_TEST_CLUSTER_CTAS", f"{P},{P // 4 * 4 - 4 if P > 8 else 0},{P // 8 * 8 - 8 if P > 16 else 0}")
+    s = synth_blackoil_jacobian(*dims, perm="lognormal")
+    rp, ci, v, b = s.rowptr.numpy(), s.colidx.numpy(), s.vals.numpy(), s.rhs.numpy()
+    lu, bad = oracle.ilu0_factor(rp, ci, v)
+    rc, out, info = _host_apply(rp, ci, lu, P, 0.9, b)
+    assert rc == 0 and np.array_equal(out, oracle.ilu0_apply(rp, ci, lu, 0.9, b))
+
+
+@pytest.mark.parametrize("dims,P", [((40, 40, 12), 7), ((60, 50, 8), 16), ((33, 47, 5), 5)])
+def test_programs_with_several_tiles_per_cta(oracle, dims, P):
+    """More columns than one pass per CTA: tiles dealt out in wavefront order, several per CTA,
+    ascending in the lower sweep / factorisation and descending in the upper sweep."""
+    s = synth_blackoil_jacobian(*dims, perm="lognormal")
+    rp, ci, v, b = s.rowptr.numpy(), s.colidx.numpy(), s.vals.numpy(), s.rhs.numpy()
+    lu, bad = oracle.ilu0_factor(rp, ci, v)
+    rc, out, info = _host_apply(rp, ci, lu, P, 0.9, b)
+    assert rc == 0 and info[4] <= 96 and np.array_equal(out, oracle.ilu0_apply(rp, ci, lu, 0.9, b))
+    rc, lu2, bad2, info2 = _host_factor(rp, ci, v, P)
+    assert rc == 0 and bad2 == -1 and np.array_equal(lu2, lu)
+
+
 @pytest.mark.parametrize("N,extra,dense,P", [(700, 3, 12, 5), (700, 3, 12, 148), (3000, 2, 300, 3), (500, 6, 40, 64)])
 def test_sweep_programs_are_exact_on_general_patterns(oracle, N, extra, dense, P):
     rp, ci, v = random_bcrs(N, extra, seed=N + dense, dense_group=dense)

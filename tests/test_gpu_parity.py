@@ -21,6 +21,9 @@ CASES = {
     "slab_1d": dict(dims=(64, 1, 1), perm="homogeneous"),
     "plane_2d": dict(dims=(30, 17, 1), perm="lognormal"),
     "mid_lognormal": dict(dims=(40, 40, 20), perm="lognormal"),
+    # 15 000 columns over 148 CTAs: more than one pass per tile level, so every CTA gets several
+    # smaller tiles (analysis.cpp: wavefront-ordered tile rounds)
+    "wide_multi_tile": dict(dims=(120, 125, 6), perm="lognormal"),
 }
 
 
@@ -259,8 +262,9 @@ def test_newton_iteration_blackoil_gpu_with_wells(oracle):
 
 
 # ---- BASELINE.json's full sizes: size-independent properties -----------------------------------
-@pytest.mark.parametrize("dims,perm", [((100, 100, 50), "homogeneous"), ((100, 100, 100), "lognormal")],
-                         ids=["c2_500k", "c3_1M"])
+@pytest.mark.parametrize("dims,perm", [((100, 100, 50), "homogeneous"), ((100, 100, 100), "lognormal"),
+                                       ((144, 144, 144), "homogeneous")],
+                         ids=["c2_500k", "c3_1M", "c5_3M_two_tiles_per_cta"])
 def test_full_size_properties(dims, perm):
     import torch
     from opm_simulators_legacy_b200.jacobian import bcrs_matvec
