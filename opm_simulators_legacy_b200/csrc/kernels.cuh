@@ -162,23 +162,29 @@ bicg_init_kernel(size_t n, const double* __restrict__ r, double* S, ReduceWs ws,
 }
 
 // p = r + beta (p - omega v),  beta = (rho_new/rho)(alpha/omega)
+// lpos != nullptr: p is also written in the lower sweep's program order (row r -> position
+// lpos[r]), which is what the next preconditioner application streams as its right-hand side
 __global__ void __launch_bounds__(256)
 bicg_update_p_kernel(size_t n, double* __restrict__ p, const double* __restrict__ r,
-                     const double* __restrict__ v, const double* __restrict__ S)
+                     const double* __restrict__ v, const double* __restrict__ S,
+                     const int* __restrict__ lpos, double* __restrict__ pperm)
 {
     const double omega = S[S_OMEGA];
     const double beta = (S[S_RHO_NEW] / S[S_RHO_OLD]) * (S[S_ALPHA] / omega);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         double pq = fma(-omega, v[i], p[i]);
         pq *= beta;
-        p[i] = pq + r[i];
+        const double pn = pq + r[i];
+        p[i] = pn;
+        if (lpos) { const size_t row = i / 3; pperm[(size_t)lpos[row] * 3 + (i - row * 3)] = pn; }
     }
 }
 
 // alpha = rho_new / h ; x += alpha y ; r -= alpha v ; S[S_NRM2] = r.r
 __global__ void __launch_bounds__(256)
 bicg_update1_kernel(size_t n, double* __restrict__ x, double* __restrict__ r,
-                    const double* __restrict__ y, const double* __restrict__ v, double* S, ReduceWs ws, HostBox hb)
+                    const double* __restrict__ y, const double* __restrict__ v, double* S, ReduceWs ws, HostBox hb,
+                    const int* __restrict__ lpos, double* __restrict__ rperm)
 {
     const double hdot = S[S_H];
     const double alpha = S[S_RHO_NEW] / hdot;
@@ -187,6 +193,7 @@ bicg_update1_kernel(size_t n, double* __restrict__ x, double* __restrict__ r,
         x[i] = fma(alpha, y[i], x[i]);
         const double ri = fma(-alpha, v[i], r[i]);
         r[i] = ri;
+        if (lpos) { const size_t row = i / 3; rperm[(size_t)lpos[row] * 3 + (i - row * 3)] = ri; }     // see bicg_update_p_kernel
         s[0] = fma(ri, ri, s[0]);
     }
     grid_reduce<1>(s, ws, [=](double (&t)[1]) {

@@ -107,7 +107,7 @@ struct ProgramDevMem {
 
 struct PipeDevMem {
     DevArr<unsigned char> buf;
-    DevArr<int> cta_step_ptr, val_src, val_stride, perm_row;
+    DevArr<int> cta_step_ptr, val_src, val_stride, perm_row, pos_of_row;
     DevArr<unsigned> step_off16, step_bytes, step_rhs_row, step_rhs_bytes, val_dst8;
     DevArr<long long> cta_ext_base;
     DevArr<double> ext, rhs_perm;
@@ -117,7 +117,7 @@ struct PipeDevMem {
     size_t smem = 0;
     void release()
     {
-        buf.release(); cta_step_ptr.release(); val_src.release(); val_stride.release(); perm_row.release();
+        buf.release(); cta_step_ptr.release(); val_src.release(); val_stride.release(); perm_row.release(); pos_of_row.release();
         step_off16.release(); step_bytes.release(); step_rhs_row.release(); step_rhs_bytes.release();
         val_dst8.release(); cta_ext_base.release(); ext.release(); rhs_perm.release();
     }
@@ -163,6 +163,8 @@ struct opmgpu_solver {
     bool lu_lazy = false;          // the pipelined factorisation left only pivots: d_lu is built on demand
     ClusterCaps caps;              // co-resident CTAs of the cluster variants of the sweep kernels
     int cluster_size = 1;          // thread-block cluster size the sweeps are launched with
+    int N_for_upload = 0;          // rows of the pattern being uploaded (set_pattern)
+    bool fuse_permute = true;      // OPMGPU_FUSE_PERMUTE=0: separate permute kernel before every lower sweep
     bool use_pipe = false, force_simple = false, factor_by_levels = false, spmv_tma = true;
     int trace_cta = -1;
     DevArr<long long> d_trace;
@@ -327,6 +329,15 @@ int upload_pipe(opmgpu_handle h, const PipeProgram& p, PipeDevMem& d)
     if ((rc = upload(h, d.val_dst8, p.val_dst8))) return rc;
     if ((rc = upload(h, d.val_stride, p.val_stride))) return rc;
     if ((rc = upload(h, d.perm_row, p.perm_row))) return rc;
+    {
+        // natural row -> position in this program's order (vector kernels write the next
+        // right-hand side of the lower sweep in place, bicg_update_p_kernel)
+        std::vector<int> pos((size_t)h->N_for_upload, 0);
+        for (size_t q = 0; q < p.perm_row.size(); ++q)
+            if (p.perm_row[q] >= 0) pos[p.perm_row[q]] = (int)q;
+        if ((rc = upload(h, d.pos_of_row, pos))) return rc;
+        CK(cudaStreamSynchronize(h->stream));          // pos is a local
+    }
     d.nval = p.val_src.size(); d.next = (size_t)p.total_ext; d.P = p.P; d.nperm = (size_t)p.nperm; d.lean = p.lean;
     CK(d.ext.ensure(std::max<size_t>(d.next, 1) * 3));
     CK(cudaMemsetAsync(d.ext.p, 0xff, std::max<size_t>(d.next, 1) * 3 * sizeof(double), h->stream));
@@ -431,6 +442,7 @@ int set_pattern(opmgpu_handle h, int N, int nnzb, const int* rowptr, const int* 
     if ((rc = upload(h, h->d_diag, h->an.diag))) return rc;
     if ((rc = upload(h, h->d_lvl_rows, h->an.lvl_rows))) return rc;
     h->use_pipe = h->an.pipeL.valid && h->an.pipeU.valid;
+    h->N_for_upload = N;
     if (h->use_pipe) {
         if ((rc = upload_pipe(h, h->an.pipeL, h->pipeL))) return rc;
         if ((rc = upload_pipe(h, h->an.pipeU, h->pipeU))) return rc;
@@ -711,11 +723,12 @@ int launch_sweep(opmgpu_handle h, bool upper, const PipeDevMem& d, void** args)
 }
 
 // v = w U^-1 L^-1 d, all device pointers; asynchronous
-int apply_precond(opmgpu_handle h, double w, const double* d, double* v)
+// d_in_program_order: the producer of d already wrote it into pipeL.rhs_perm (fused permutation)
+int apply_precond(opmgpu_handle h, double w, const double* d, double* v, bool d_in_program_order = false)
 {
     const int scale = std::fabs(w - 1.0) > 1e-15 ? 1 : 0;      // relaxation_ flag of the reference
     if (h->use_pipe) {
-        {
+        if (!d_in_program_order) {
             const size_t e = h->pipeL.nperm * 3;
             permute_rows_kernel<<<(unsigned)((e + 255) / 256), 256, 0, h->stream>>>(h->pipeL.nperm, h->pipeL.perm_row.p, d, h->pipeL.rhs_perm.p);
         }
@@ -737,7 +750,7 @@ int apply_precond(opmgpu_handle h, double w, const double* d, double* v)
             void* args[] = {&pg, &rhs, &work, &hand, &out, &w, (void*)&scale, &err};
             if (int rc = launch_sweep(h, true, h->pipeU, args)) return rc;
         }
-        h->launches += 3;
+        h->launches += d_in_program_order ? 2 : 3;
         return 0;
     }
     {
@@ -823,6 +836,9 @@ int bicgstab(opmgpu_handle h, const opmgpu_params* prm, opmgpu_result* res)
     h->history.clear();
     CK(cudaMemsetAsync(h->d_x.p, 0, n * sizeof(double), h->stream));
     CK(cudaMemcpyAsync(h->d_rt.p, h->d_r.p, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    // the vector kernels write the next right-hand side of the lower sweep in program order
+    const int* lpos = h->use_pipe && h->fuse_permute ? h->pipeL.pos_of_row.p : nullptr;
+    double* lperm = h->use_pipe ? h->pipeL.rhs_perm.p : nullptr;
     HostBox hb = next_hostbox(h);
     bicg_init_kernel<<<kVecBlocks, 256, 0, h->stream>>>(n, h->d_r.p, h->d_S.p, h->ws(), hb);
     h->launches++;
@@ -843,19 +859,19 @@ int bicgstab(opmgpu_handle h, const opmgpu_params* prm, opmgpu_result* res)
             CK(cudaMemcpyAsync(h->d_p.p, h->d_r.p, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
         } else {
             h->prof_begin(2);
-            bicg_update_p_kernel<<<kVecBlocks, 256, 0, h->stream>>>(n, h->d_p.p, h->d_r.p, h->d_v.p, h->d_S.p);
+            bicg_update_p_kernel<<<kVecBlocks, 256, 0, h->stream>>>(n, h->d_p.p, h->d_r.p, h->d_v.p, h->d_S.p, lpos, lperm);
             h->prof_end();
             h->launches++;
         }
         h->prof_begin(0);
-        if ((rc = apply_precond(h, w, h->d_p.p, h->d_y.p))) return rc;
+        if ((rc = apply_precond(h, w, h->d_p.p, h->d_y.p, lpos != nullptr && it >= 1))) return rc;
         h->prof_end();
         h->prof_begin(1);
         if ((rc = spmv_with_dots(h, 1, h->d_y.p, h->d_v.p, h->d_rt.p))) return rc;
         h->prof_end();
         h->prof_begin(2);
         hb = next_hostbox(h);
-        bicg_update1_kernel<<<kVecBlocks, 256, 0, h->stream>>>(n, h->d_x.p, h->d_r.p, h->d_y.p, h->d_v.p, h->d_S.p, h->ws(), hb);
+        bicg_update1_kernel<<<kVecBlocks, 256, 0, h->stream>>>(n, h->d_x.p, h->d_r.p, h->d_y.p, h->d_v.p, h->d_S.p, h->ws(), hb, lpos, lperm);
         h->prof_end();
         h->launches++;
         if ((rc = allreduce_slots(h, S_NRM2, 1))) return rc;
@@ -869,7 +885,7 @@ int bicgstab(opmgpu_handle h, const opmgpu_params* prm, opmgpu_result* res)
         if (half_limit >= 0 && half >= half_limit) break;
 
         h->prof_begin(0);
-        if ((rc = apply_precond(h, w, h->d_r.p, h->d_y.p))) return rc;
+        if ((rc = apply_precond(h, w, h->d_r.p, h->d_y.p, lpos != nullptr))) return rc;
         h->prof_end();
         h->prof_begin(1);
         if ((rc = spmv_with_dots(h, 2, h->d_y.p, h->d_t.p, h->d_r.p))) return rc;
@@ -1026,6 +1042,7 @@ int opmgpu_create(int device, opmgpu_handle* out)
     if (const char* s = getenv("OPMGPU_FACTOR_BY_LEVELS")) h->factor_by_levels = atoi(s) != 0;
     if (const char* s = getenv("OPMGPU_FACTOR_TILE")) h->factor_tile = atoi(s) != 0;
     if (const char* s = getenv("OPMGPU_HOSTBOX")) h->use_hostbox = atoi(s) != 0;
+    if (const char* s = getenv("OPMGPU_FUSE_PERMUTE")) h->fuse_permute = atoi(s) != 0;
     if (const char* s = getenv("OPMGPU_SPMV_SIMPLE")) h->spmv_tma = atoi(s) == 0;
     cudaFuncSetAttribute(spmv3_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
     cudaFuncSetAttribute(spmv3_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
