@@ -15,6 +15,7 @@
 #include <nccl.h>      // types only: the library is resolved at run time with dlopen
 
 #include <algorithm>
+#include <chrono>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -712,7 +713,12 @@ int launch_sweep(opmgpu_handle h, bool upper, const PipeDevMem& d, void** args)
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = d.cluster_size; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         at[1].id = cudaLaunchAttributeCooperative; at[1].val.cooperative = 1;
-        cfg.attrs = at; cfg.numAttrs = 2;
+        // Co-residency: the grid was sized from cudaOccupancyMaxActiveClusters and the solver's
+        // stream runs one kernel at a time.  The cooperative attribute would make the driver
+        // verify that, but profilers (Nsight Compute 2025.2) cannot replay launches that carry both
+        // the cluster and the cooperative attribute, so it is opt-in: OPMGPU_CLUSTER_COOP=1.
+        static const bool coop = getenv("OPMGPU_CLUSTER_COOP") && atoi(getenv("OPMGPU_CLUSTER_COOP")) != 0;
+        cfg.attrs = at; cfg.numAttrs = coop ? 2 : 1;
         CK(cudaLaunchKernelExC(&cfg, fn, args));
         return 0;
     }
@@ -933,8 +939,11 @@ int solve_resident(opmgpu_handle h, const opmgpu_params* prm, opmgpu_result* res
     h->prof_end();
     cudaEventRecord(h->ev[1], h->stream);
     // the CSC front end compares the caller's sparsity pattern with the cached one on host
-    // threads while values are uploaded and factorised; the verdict is due before the solve
-    if (h->pattern_check.valid() && !h->pattern_check.get()) return kPatternChanged;
+    // threads while values are uploaded and factorised; a negative verdict that is already in
+    // stops here (not waited for: a verdict that is still out is collected by the caller after the solve,
+    // which is then repeated on the new pattern -- rare, patterns change at report steps)
+    if (h->pattern_check.valid() && h->pattern_check.wait_for(std::chrono::seconds(0)) == std::future_status::ready &&
+        !h->pattern_check.get()) return kPatternChanged;
     if (rc) { res->bad_row = badrow; return rc; }
     rc = bicgstab(h, prm, res);
     cudaEventRecord(h->ev[2], h->stream);
