@@ -122,7 +122,7 @@ def config_of(workload, s, n_gpus):
     return {"workload": f"{workload}: synthetic 3-phase black-oil Jacobian, {dims[0]}x{dims[1]}x{dims[2]} "
                         f"Cartesian 7-point stencil, {perm} permeability, 3x3 BCRS",
             "cells": s.N, "nnzb": s.nnzb, "linear_solver_reduction": 1e-2, "linear_solver_maxiter": 150,
-            "ilu_relaxation": 0.9, "partition": "single GPU" if n_gpus == 1 else f"{n_gpus} k-slabs, block-Jacobi ILU0",
+            "ilu_relaxation": 0.9, "partition": "single GPU" if n_gpus == 1 else f"{n_gpus} slabs along the weakest-coupling axis, block-Jacobi ILU0",
             "l2": "inputs (>= 0.5 GB matrix) larger than the 126 MB L2; no explicit flush"}
 
 
@@ -267,8 +267,7 @@ def run_gpu(args, rank, world):
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     # per launch = per rank: rank 0's rows (its diagonal block for the block-Jacobi ILU0)
     N, nnzb = (s.N, s.nnzb) if world == 1 else (g.N, g.nnzb)
-    plane = s.dims[0] * s.dims[1]
-    nnzb_ilu = nnzb if world == 1 else nnzb - plane * (1 if world == 2 else 1)      # rank 0 has one neighbour slab
+    nnzb_ilu = nnzb if world == 1 else g.nnzb_diag      # blocks of the rank's diagonal block (block-Jacobi ILU0)
     b_ilu = 76 * (nnzb_ilu - N) + 176 * N       # SURVEY.md §8d, bytes per apply
     b_spmv = 76 * nnzb + 52 * N
     ap_ms, ap_n = prof["ilu_apply"]

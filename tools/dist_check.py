@@ -25,13 +25,13 @@ g = DistributedSolver(s, local)
 # distributed SpMV against the global one
 xs = s.xstar.numpy()
 g.set_values_dev(g.vals)
-y_loc = g.spmv(xs[g.lo:g.hi])
+y_loc = g.spmv(xs[g.perm[g.lo:g.hi]])
 out = {}
 for red in (1e-2, 1e-8):
     res = g.solve(make_params(linear_solver_reduction=red, linear_solver_maxiter=400))
     parts = [torch.zeros((int(g.offsets[r + 1] - g.offsets[r]), 3), dtype=torch.float64, device="cuda") for r in range(world)]
     dist.all_gather(parts, g.x)
-    x = torch.cat(parts).cpu().numpy()
+    x = g.to_natural(torch.cat(parts).cpu().numpy())
     out[red] = (res, x)
 ys = [torch.zeros((int(g.offsets[r + 1] - g.offsets[r]), 3), dtype=torch.float64, device="cuda") for r in range(world)]
 dist.all_gather(ys, torch.from_numpy(y_loc).cuda())
@@ -39,8 +39,8 @@ if rank == 0:
     from oracle import oracle_py as O
     rp, ci, v, b = s.rowptr.numpy(), s.colidx.numpy(), s.vals.numpy(), s.rhs.numpy()
     y_ref = O.spmv(rp, ci, v, xs)
-    y = torch.cat(ys).cpu().numpy()
-    report = {"dims": dims, "world": world, "spmv_bit_exact": bool(np.array_equal(y, y_ref))}
+    y = g.to_natural(torch.cat(ys).cpu().numpy())
+    report = {"dims": dims, "world": world, "slab_axis": "ijk"[g.axis], "spmv_bit_exact": bool(np.array_equal(y, y_ref))}
     for red, (res, x) in out.items():
         r = b - O.spmv(rp, ci, v, x)
         x_ref, ref = O.solve_bcrs(rp, ci, v, b, reduction=red, maxiter=400)
