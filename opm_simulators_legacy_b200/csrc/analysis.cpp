@@ -2,9 +2,11 @@
 #include "analysis.hpp"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <future>
 #include <map>
 #include <numeric>
 
@@ -397,6 +399,7 @@ void build_pipe_program(int N, const int* rowptr, const int* colidx, const std::
     }
     if (total_bytes / 16 >= (1ull << 32) || total_bytes / 8 >= (1ull << 32)) return;
     pg.buf.assign(total_bytes + 16, 0);
+    pg.val_src.reserve((size_t)rowptr[N] / 2 + N); pg.val_dst8.reserve((size_t)rowptr[N] / 2 + N); pg.val_stride.reserve((size_t)rowptr[N] / 2 + N);
     bool any_slow = false, any_global = false;
     // emit
     for (int c = 0; c < P; ++c) {
@@ -580,6 +583,7 @@ void build_factor_pipe_program(int N, const int* rowptr, const int* colidx, cons
     }
     if (total_bytes / 8 >= (1ull << 32)) return;
     pg.buf.assign(total_bytes + 16, 0);
+    pg.val_src.reserve((size_t)rowptr[N]); pg.val_dst8.reserve((size_t)rowptr[N]);
     for (int c = 0; c < P; ++c) {
         long long e = 0;
         if (pg.cta_step_ptr[c] == pg.cta_step_ptr[c + 1]) continue;
@@ -632,6 +636,14 @@ void analyse_pattern(int N, const int* rowptr, const int* colidx, int P, Pattern
     out.N = N;
     out.nnzb = rowptr[N];
     out.diag.assign(N, -1);
+    const bool timing = std::getenv("OPMGPU_DEBUG") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto tick = [&](const char* what) {
+        if (!timing) return;
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[opmgpu] analysis: %-34s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
     for (int i = 0; i < N; ++i) {
         const int* b = colidx + rowptr[i];
         const int* e = colidx + rowptr[i + 1];
@@ -741,13 +753,24 @@ void analyse_pattern(int N, const int* rowptr, const int* colidx, int P, Pattern
             tile = owner;
         }
         out.P = Pl; out.cluster_size = cs;
+        tick("levels + tiling");
+        // the factorisation program only depends on the partition: build it beside the sweep programs
+        std::future<void> fjob;
+        if (!force_simple)
+            fjob = std::async(std::launch::async, [&, Pl]() {
+                build_factor_pipe_program(N, rowptr, colidx, out.diag, lvlL, owner, tile, Pl, out.pipeF);
+            });
         build_pipe_program(N, rowptr, colidx, out.diag, lvlU, nU, owner, tile, Pl, false, nullptr, out.pipeU, cs);
+        tick("upper sweep program");
         if (out.pipeU.valid) {
             std::vector<int> upos(N, 0);
             for (size_t q = 0; q < out.pipeU.perm_row.size(); ++q)
                 if (out.pipeU.perm_row[q] >= 0) upos[out.pipeU.perm_row[q]] = (int)q;
             build_pipe_program(N, rowptr, colidx, out.diag, lvlL, nL, owner, tile, Pl, true, &upos, out.pipeL, cs);
+            tick("lower sweep program");
         }
+        if (fjob.valid()) fjob.get();
+        tick("factorisation program (concurrent)");
         // clusters are only supported by the lean kernels: otherwise lay everything out again without
         if (cs > 1 && !(out.pipeL.valid && out.pipeU.valid && out.pipeL.lean && out.pipeU.lean)) {
             caps.max_ctas[1] = caps.max_ctas[2] = caps.max_ctas[3] = 0;
@@ -756,14 +779,25 @@ void analyse_pattern(int N, const int* rowptr, const int* colidx, int P, Pattern
         P = Pl;
         break;
     }
-    if (out.pipeL.valid && out.pipeU.valid && !force_simple)
-        build_factor_pipe_program(N, rowptr, colidx, out.diag, lvlL, owner, tile, P, out.pipeF);
+    if (!(out.pipeL.valid && out.pipeU.valid)) out.pipeF = FactorPipeProgram();
     out.nlevL = nL; out.nlevU = nU;
-    build_program(N, rowptr, colidx, lvlL, nL, owner, P, true, out.lower);       // also drives the factorisation
+    // the flag-synchronised tile kernel's program is only needed when the pipelined factorisation
+    // is not available (or switched off): built on demand from the partition kept here
+    out.owner_ = owner; out.level_lower_ = lvlL;
+    if (force_simple || !out.pipeF.valid || std::getenv("OPMGPU_FACTOR_TILE") || std::getenv("OPMGPU_FACTOR_BY_LEVELS")) {
+        build_tile_factor_program(rowptr, colidx, out);
+        tick("tile-kernel factorisation program");
+    }
     if (force_simple || !out.pipeL.valid || !out.pipeU.valid) {
         out.pipeL = PipeProgram(); out.pipeU = PipeProgram();
         build_program(N, rowptr, colidx, lvlU, nU, owner, P, false, out.upper);
     }
+}
+
+void build_tile_factor_program(const int* rowptr, const int* colidx, PatternAnalysis& an)
+{
+    if (!an.lower.prow.empty() || an.owner_.empty()) return;
+    build_program(an.N, rowptr, colidx, an.level_lower_, an.nlevL, an.owner_, an.P, true, an.lower);
 }
 
 // Sequential interpreter of the pipelined programs (debug / CPU tests): executes the records

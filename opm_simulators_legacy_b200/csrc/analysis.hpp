@@ -167,6 +167,7 @@ struct PatternAnalysis {
     int P = 0;                                   // CTAs every program is laid out for (launch size)
     int cluster_size = 1;                        // sweeps are launched in clusters of this many CTAs
     int tiles_a = 0, tiles_b = 0;                // column tiling (Cartesian patterns)
+    std::vector<int> owner_, level_lower_;       // partition and L levels (build_tile_factor_program)
     SweepProgram lower, upper;
     PipeProgram pipeL, pipeU;
     FactorPipeProgram pipeF;
@@ -177,6 +178,9 @@ struct PatternAnalysis {
 // P = number of persistent CTAs the sweeps will be launched with.
 void analyse_pattern(int N, const int* rowptr, const int* colidx, int P, PatternAnalysis& out,
                      bool force_simple = false, const ClusterCaps* caps = nullptr);
+
+// SweepProgram `lower` (the flag-synchronised tile factorisation kernel's program) on demand.
+void build_tile_factor_program(const int* rowptr, const int* colidx, PatternAnalysis& an);
 
 // Sequential interpreter of a pipelined program (debug / CPU tests of the host analysis).
 bool interpret_pipe_program(const PipeProgram& pg, bool upper, const double* rhs_perm, double* work,

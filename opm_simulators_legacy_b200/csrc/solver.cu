@@ -469,7 +469,12 @@ int set_pattern(opmgpu_handle h, int N, int nnzb, const int* rowptr, const int* 
         if ((rc = upload_program(h, h->an.upper, h->progU, true))) return rc;
         h->pipeL.release(); h->pipeU.release();
     } else {
-        if ((rc = upload_program(h, h->an.lower, h->progL, false, false))) return rc;   // factorisation program only
+        if (!h->pipeF.valid) {          // the tile kernel factorises: its program is built on demand
+            build_tile_factor_program(rowptr, colidx, h->an);
+            if ((rc = upload_program(h, h->an.lower, h->progL, false, false))) return rc;
+        } else {
+            h->progL.release();
+        }
         h->progU.release();
     }
     CK(h->d_lu.ensure((size_t)nnzb * 9));
@@ -481,6 +486,7 @@ int set_pattern(opmgpu_handle h, int N, int nnzb, const int* rowptr, const int* 
     // keep only what the host still needs
     h->nlevL = h->an.nlevL; h->nlevU = h->an.nlevU;
     h->an.lower = SweepProgram(); h->an.upper = SweepProgram();
+    h->an.owner_ = std::vector<int>(); h->an.level_lower_ = std::vector<int>();
     h->an.pipeL = PipeProgram(); h->an.pipeU = PipeProgram(); h->an.pipeF = FactorPipeProgram();
     h->have_pattern = true;
     return OPMGPU_OK;

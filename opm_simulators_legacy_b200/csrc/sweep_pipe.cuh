@@ -41,7 +41,10 @@
 
 namespace opmgpu {
 
-constexpr int kPipeGroups = 3;                                     // compute groups taking turns
+#ifndef OPMGPU_PIPE_GROUPS
+#define OPMGPU_PIPE_GROUPS 3
+#endif
+constexpr int kPipeGroups = OPMGPU_PIPE_GROUPS;                    // compute groups taking turns
 constexpr int kPipeComputeWarps = 3;                               // warps per group, one thread per block row
 constexpr int kPipeHelpers = 1;                                    // warps polling for pushed results
 #ifndef OPMGPU_POLL_PER_LANE
