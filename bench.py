@@ -278,7 +278,7 @@ def run_gpu(args, rank, world):
     if os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f).get(args.workload, {}).get("ilu_apply_dram_bytes")
-    roofline = {"kernel": "ILU0 apply = ilu0_sweep_pipe_kernel<lower> + <upper> (+ permute_rows)", "bound": "hbm",
+    roofline = {"kernel": "ILU0 apply = ilu0_sweep_pipe_kernel<lower> + <upper> (right-hand side permuted by the producing vector kernel)", "bound": "hbm",
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
                 "traffic": traffic, "algorithmic_bytes_per_launch": b_ilu, "launches_timed": ap_n,
                 "avg_launch_us": ap_ms * 1e3 / max(ap_n, 1),
