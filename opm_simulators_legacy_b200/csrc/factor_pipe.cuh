@@ -339,38 +339,42 @@ ilu0_factor_pipe_kernel(FactorPipeDev pg, int* bad_row, int* err)
 // thread per (record block b, block row c): a lower block becomes row c of L_ij = A_ij *
 // inv(D_j) (the factorisation's own three fused multiply-adds per element), a diagonal block
 // becomes row c of inv(D_j), an upper block is A's.  Element [c][e] goes to dst8[b] + c*stride[b] + e.
-template <bool LOWER>
+// PART 0: everything, 1: only the blocks copied from A, 2: only the pivots
+template <bool LOWER, int PART>
 __global__ void __launch_bounds__(256)
 repack_pipe2_kernel(size_t nval, const int* __restrict__ src, const unsigned* __restrict__ dst8,
                     const int* __restrict__ stride, const int* __restrict__ colidx, const int* __restrict__ diag,
                     const int* __restrict__ fpos, const double* __restrict__ A, const double* __restrict__ fout,
                     double* __restrict__ bufd)
 {
-    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nval * 3) return;
-    const size_t b = t / 3;
-    const int c = (int)(t - b * 3);
-    const int k = src[b];
-    const int j = colidx[k];
-    double o[3];
-    if (k == diag[j]) {
-        const double* d = fout + (size_t)fpos[j] * kFEntry + c * 3;
-        o[0] = d[0]; o[1] = d[1]; o[2] = d[2];
-    } else {
-        const double* a = A + (size_t)k * 9 + c * 3;
-        if (LOWER) {
-            const double* d = fout + (size_t)fpos[j] * kFEntry;
-            const double a0 = a[0], a1 = a[1], a2 = a[2];
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < nval * 3; t += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = t / 3;
+        const int c = (int)(t - b * 3);
+        const int k = src[b];
+        const int j = colidx[k];
+        double o[3];
+        const bool pivot = k == diag[j];
+        if (PART == 1 && pivot) continue;
+        if (PART == 2 && !pivot) continue;
+        if (pivot) {
+            const double* d = fout + (size_t)fpos[j] * kFEntry + c * 3;
+            o[0] = d[0]; o[1] = d[1]; o[2] = d[2];
+        } else {
+            const double* a = A + (size_t)k * 9 + c * 3;
+            if (LOWER) {
+                const double* d = fout + (size_t)fpos[j] * kFEntry;
+                const double a0 = a[0], a1 = a[1], a2 = a[2];
 #pragma unroll
-            for (int e = 0; e < 3; ++e) {
-                double sacc = 0.0;
-                sacc = fma(a0, d[e], sacc); sacc = fma(a1, d[3 + e], sacc); sacc = fma(a2, d[6 + e], sacc);
-                o[e] = sacc;
-            }
-        } else { o[0] = a[0]; o[1] = a[1]; o[2] = a[2]; }
+                for (int e = 0; e < 3; ++e) {
+                    double sacc = 0.0;
+                    sacc = fma(a0, d[e], sacc); sacc = fma(a1, d[3 + e], sacc); sacc = fma(a2, d[6 + e], sacc);
+                    o[e] = sacc;
+                }
+            } else { o[0] = a[0]; o[1] = a[1]; o[2] = a[2]; }
+        }
+        double* dst = bufd + (size_t)dst8[b] + (size_t)c * stride[b];
+        dst[0] = o[0]; dst[1] = o[1]; dst[2] = o[2];
     }
-    double* dst = bufd + (size_t)dst8[b] + (size_t)c * stride[b];
-    dst[0] = o[0]; dst[1] = o[1]; dst[2] = o[2];
 }
 
 // BCRS factor array on demand (opmgpu_ilu0_get_factors): in place on a copy of A.  One thread

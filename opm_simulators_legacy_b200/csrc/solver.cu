@@ -273,7 +273,11 @@ struct opmgpu_solver {
 
 namespace {
 
-constexpr int kVecBlocks = 148 * 4;      // fixed launch shape of the vector kernels (determinism)
+#ifndef OPMGPU_VEC_BLOCKS_PER_SM
+#define OPMGPU_VEC_BLOCKS_PER_SM 8
+#endif
+constexpr int kVecBlocks = 148 * OPMGPU_VEC_BLOCKS_PER_SM;      // fixed launch shape of the vector kernels (determinism)
+static_assert(kVecBlocks <= kMaxRedBlocks, "per-block partials of the grid reduction");
 
 template <class T>
 int upload(opmgpu_handle h, DevArr<T>& d, const std::vector<T>& v)
@@ -653,17 +657,19 @@ int factor(opmgpu_handle h, int* bad_row)
     CK(cudaGetLastError());
     // stream the factors into the sweep programs' layout
     if (h->use_pipe && pipe_factor) {
-        // L_ij = A_ij * inv(D_j) is formed here, from A and the program-ordered pivots
+        // L_ij = A_ij * inv(D_j) is formed here, from A and the program-ordered pivots.  (Copying the
+        // U blocks on a second stream beside the factorisation kernel was measured: it slows that
+        // latency-bound kernel down by more than the copy costs, 0.84 -> 0.99 ms per factorisation.)
         const FactorPipeDevMem& f = h->pipeF;
         if (h->pipeL.nval) {
             const size_t e = h->pipeL.nval * 3;
-            repack_pipe2_kernel<true><<<(unsigned)((e + 255) / 256), 256, 0, h->stream>>>(h->pipeL.nval, h->pipeL.val_src.p, h->pipeL.val_dst8.p,
+            repack_pipe2_kernel<true, 0><<<(unsigned)((e + 255) / 256), 256, 0, h->stream>>>(h->pipeL.nval, h->pipeL.val_src.p, h->pipeL.val_dst8.p,
                 h->pipeL.val_stride.p, h->d_colidx.p, h->d_diag.p, f.fpos.p, ilu_A, f.fout.p, (double*)h->pipeL.buf.p);
             h->launches++;
         }
         if (h->pipeU.nval) {
             const size_t e = h->pipeU.nval * 3;
-            repack_pipe2_kernel<false><<<(unsigned)((e + 255) / 256), 256, 0, h->stream>>>(h->pipeU.nval, h->pipeU.val_src.p, h->pipeU.val_dst8.p,
+            repack_pipe2_kernel<false, 0><<<(unsigned)((e + 255) / 256), 256, 0, h->stream>>>(h->pipeU.nval, h->pipeU.val_src.p, h->pipeU.val_dst8.p,
                 h->pipeU.val_stride.p, h->d_colidx.p, h->d_diag.p, f.fpos.p, ilu_A, f.fout.p, (double*)h->pipeU.buf.p);
             h->launches++;
         }
