@@ -734,8 +734,12 @@ int launch_sweep(opmgpu_handle h, bool upper, const PipeDevMem& d, void** args)
         CK(cudaLaunchKernelExC(&cfg, fn, args));
         return 0;
     }
+    const bool trace = (h->trace_cta >= 0 && h->d_trace.p) || h->gtrace_steps > 0;       // debug tools only
     const void* fn = upper ? (d.lean ? (const void*)ilu0_sweep_pipe_kernel<true, true> : (const void*)ilu0_sweep_pipe_kernel<true, false>)
                            : (d.lean ? (const void*)ilu0_sweep_pipe_kernel<false, true> : (const void*)ilu0_sweep_pipe_kernel<false, false>);
+    if (trace)
+        fn = upper ? (d.lean ? (const void*)ilu0_sweep_pipe_kernel<true, true, false, true> : (const void*)ilu0_sweep_pipe_kernel<true, false, false, true>)
+                   : (d.lean ? (const void*)ilu0_sweep_pipe_kernel<false, true, false, true> : (const void*)ilu0_sweep_pipe_kernel<false, false, false, true>);
     CK(cudaLaunchCooperativeKernel(fn, dim3(d.P), dim3(kPipeThreads), args, d.smem, h->stream));
     return 0;
 }
@@ -1070,6 +1074,10 @@ int opmgpu_create(int device, opmgpu_handle* out)
     cudaFuncSetAttribute(spmv3_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
     cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     cudaFuncSetAttribute(ilu0_factor_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
+    cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
+    cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
+    cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
+    cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<true, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
     cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
     cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
     {

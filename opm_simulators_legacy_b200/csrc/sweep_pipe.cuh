@@ -200,14 +200,16 @@ template <bool UPPER>
 struct StepPre {
     int n, qbase, ext_end, ext_cnt;
     int4 ri0, ri1;              // rowinfo, dep0, dep1, dep2 | upos, push0, push1, own window slot
-    bool on;
+    uint32_t a0, a1, a2, aw;    // shared addresses of the three dependencies and of the own window slot
+    bool on, has_cx;            // has_cx: some dependency arrives through distributed shared memory
     double rhs[3];
     double cf[27];              // cf[c*9 + k*3 + e]
     double dv[9];               // dv[c*3 + e] (upper)
 
     // stage = rhs area followed by the record
-    __device__ __forceinline__ void load(const unsigned char* stage, int rhs_bytes, int r, bool lane_on)
+    __device__ __forceinline__ void load(const unsigned char* stage, int rhs_bytes, int r, bool lane_on, uint32_t dep_s = 0)
     {
+        a0 = a1 = a2 = aw = dep_s; has_cx = false;
         const unsigned char* rec = stage + rhs_bytes;
         const int4 h0 = *reinterpret_cast<const int4*>(rec);
         n = h0.x; qbase = h0.y; ext_end = h0.z; ext_cnt = h0.w;
@@ -226,6 +228,10 @@ struct StepPre {
             }
             const int4* rip = reinterpret_cast<const int4*>(rec + ((off + 15) & ~(size_t)15)) + 2 * r;
             ri0 = rip[0]; ri1 = rip[1];
+            // (off the critical path: the step's addresses are ready before its turn comes)
+            a0 = dep_s + 8u * (uint32_t)ri0.y; a1 = dep_s + 8u * (uint32_t)ri0.z; a2 = dep_s + 8u * (uint32_t)ri0.w;
+            aw = dep_s + 8u * (uint32_t)ri1.w;
+            has_cx = max(ri0.y, max(ri0.z, ri0.w)) >= kCxBase * 3;
             const double* rp = reinterpret_cast<const double*>(stage) + 3 * r;
             rhs[0] = rp[0]; rhs[1] = rp[1]; rhs[2] = rp[2];
         }
@@ -291,15 +297,16 @@ __device__ __forceinline__ void sweep_row_chain(const StepPre<UPPER>& p, const u
                                                 double* dep, uint32_t dep_s, const double* work, double* ext, double (&acc)[3],
                                                 PipeCtl* ctl = nullptr, int* err = nullptr)
 {
-    acc[0] = acc[1] = acc[2] = 0.0;
+    if (!p.on) { acc[0] = acc[1] = acc[2] = 0.0; }
     if (p.on) {
         double y[9];
         if (LEAN || (p.ri0.y | p.ri0.z | p.ri0.w) >= 0) {    // all three in shared memory (the common case)
-            const uint32_t a0 = dep_s + 8u * (uint32_t)p.ri0.y, a1 = dep_s + 8u * (uint32_t)p.ri0.z, a2 = dep_s + 8u * (uint32_t)p.ri0.w;
+            const uint32_t a0 = LEAN ? p.a0 : dep_s + 8u * (uint32_t)p.ri0.y, a1 = LEAN ? p.a1 : dep_s + 8u * (uint32_t)p.ri0.z,
+                           a2 = LEAN ? p.a2 : dep_s + 8u * (uint32_t)p.ri0.w;
             y[0] = lds_f64(a0); y[1] = lds_f64(a0 + 8); y[2] = lds_f64(a0 + 16);
             y[3] = lds_f64(a1); y[4] = lds_f64(a1 + 8); y[5] = lds_f64(a1 + 16);
             y[6] = lds_f64(a2); y[7] = lds_f64(a2 + 8); y[8] = lds_f64(a2 + 16);
-            if (CX && max(p.ri0.y, max(p.ri0.z, p.ri0.w)) >= kCxBase * 3) {      // delivered by a CTA of the cluster?
+            if (CX && p.has_cx) {      // delivered by a CTA of the cluster?
                 if (p.ri0.y >= kCxBase * 3) cx_wait(a0, y[0], y[1], y[2], ctl, err);
                 if (p.ri0.z >= kCxBase * 3) cx_wait(a1, y[3], y[4], y[5], ctl, err);
                 if (p.ri0.w >= kCxBase * 3) cx_wait(a2, y[6], y[7], y[8], ctl, err);
@@ -329,7 +336,7 @@ __device__ __forceinline__ void sweep_row_chain(const StepPre<UPPER>& p, const u
             }
             acc[0] = v[0]; acc[1] = v[1]; acc[2] = v[2];
         }
-        const uint32_t w = dep_s + 8u * (uint32_t)p.ri1.w;
+        const uint32_t w = LEAN ? p.aw : dep_s + 8u * (uint32_t)p.ri1.w;
         sts_f64(w, acc[0]); sts_f64(w + 8, acc[1]); sts_f64(w + 16, acc[2]);
     }
 }
@@ -400,7 +407,9 @@ __device__ __noinline__ void sweep_extra_rows(const unsigned char* stage, int rh
 // pass (every Cartesian stencil case): those paths are compiled out.
 // CX: launched in thread-block clusters; results for CTAs of the same cluster are stored straight
 // into their shared memory (a tile crossing then costs a shared-memory round trip, not an L2 poll).
-template <bool UPPER, bool LEAN, bool CX = false>
+// TRACE: the per-step time stamps of the debug tools (tools/trace_sweep.py, gtrace_sweep.py) are
+// compiled in; the production variants carry none of that code on the critical path.
+template <bool UPPER, bool LEAN, bool CX = false, bool TRACE = false>
 __global__ void __launch_bounds__(kPipeThreads, 1)
 ilu0_sweep_pipe_kernel(PipeDev pg, const double* __restrict__ rhs_perm, double* work, double* hand_off,
                        double* out, double w, int scale, int* err)
@@ -414,9 +423,9 @@ ilu0_sweep_pipe_kernel(PipeDev pg, const double* __restrict__ rhs_perm, double* 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int s0 = pg.cta_step_ptr[blockIdx.x];
     const int nsteps = pg.cta_step_ptr[blockIdx.x + 1] - s0;
-    long long* gtr = pg.gtrace ? pg.gtrace + (size_t)blockIdx.x * pg.gtrace_steps * 8 : nullptr;
-    long long* hlog = pg.gtrace ? pg.gtrace + (size_t)gridDim.x * pg.gtrace_steps * 8 + (size_t)blockIdx.x * 2048 : nullptr;
-    if (gtr && tid == 0) gtr[(pg.gtrace_steps - 1) * 8 + 0] = pipe_gtime();
+    long long* gtr = TRACE && pg.gtrace ? pg.gtrace + (size_t)blockIdx.x * pg.gtrace_steps * 8 : nullptr;
+    long long* hlog = TRACE && pg.gtrace ? pg.gtrace + (size_t)gridDim.x * pg.gtrace_steps * 8 + (size_t)blockIdx.x * 2048 : nullptr;
+    if (TRACE && gtr && tid == 0) gtr[(pg.gtrace_steps - 1) * 8 + 0] = pipe_gtime();
 
     if (tid == 0) {
         for (int i = 0; i < S; ++i) { mbar_init(&ctl->full[i], 1); mbar_init(&ctl->empty[i], kPipeComputeWarps); }
@@ -534,7 +543,7 @@ ilu0_sweep_pipe_kernel(PipeDev pg, const double* __restrict__ rhs_perm, double* 
                 __syncwarp();
                 if (lane == 0) { if (kPipeHelpers > 1) atomicMax(ext_ready, e + n); else *reinterpret_cast<volatile int*>(ext_ready) = e + n; }
                 rearm_from = e_now; rearm_n = e + n - e_now;
-                if (gtr && lane == 0 && hid == 0) {
+                if (TRACE && gtr && lane == 0 && hid == 0) {
                     if (e_now == 0) { gtr[(pg.gtrace_steps - 1) * 8 + 1] = pipe_gtime(); gtr[(pg.gtrace_steps - 1) * 8 + 2] = polls; }
                     if (ndeliv < 512) {
                         hlog[4 * ndeliv] = pipe_gtime(); hlog[4 * ndeliv + 1] = ((long long)polls << 32) | (unsigned)(e + n);
@@ -581,12 +590,12 @@ ilu0_sweep_pipe_kernel(PipeDev pg, const double* __restrict__ rhs_perm, double* 
         unsigned par = (unsigned)((g / S) & 1);
         int st_prev = -1, ext_prev_end = 0;
         for (int s = g; s < nsteps; s += G) {
-            const bool tr = pg.trace && blockIdx.x == pg.trace_cta && elected && s < 512;
+            const bool tr = TRACE && pg.trace && blockIdx.x == pg.trace_cta && elected && s < 512;
             const unsigned char* stage = stages + st * stage_stride;
             StepPre<UPPER> p;
-            p.n = 0; p.qbase = 0; p.ext_end = 0; p.ext_cnt = 0; p.on = false;
+            p.n = 0; p.qbase = 0; p.ext_end = 0; p.ext_cnt = 0; p.on = false; p.has_cx = false; p.a0 = p.a1 = p.a2 = p.aw = dep_s;
             if (!dead) {
-                if (pipe_wait(&ctl->full[st], par, ctl, err)) p.load(stage, pg.rhs_bytes, r_first, true);
+                if (pipe_wait(&ctl->full[st], par, ctl, err)) p.load(stage, pg.rhs_bytes, r_first, true, dep_s);
                 else dead = true;
             }
             if (LEAN) {             // everything the step needs is in registers now: hand the stage back
@@ -594,7 +603,7 @@ ilu0_sweep_pipe_kernel(PipeDev pg, const double* __restrict__ rhs_perm, double* 
                 if (lane == 0) mbar_arrive(&ctl->empty[st]);
             }
             if (tr) pg.trace[s * 16 + 0] = clock64();
-            const bool gt = gtr && elected && s < pg.gtrace_steps - 1;
+            const bool gt = TRACE && gtr && elected && s < pg.gtrace_steps - 1;
             if (gt) gtr[s * 8 + 0] = pipe_gtime();
             // pushed inputs of this step staged by the helper warp?  ext_ready only grows, so the
             // usual answer (yes) is fetched while the group still waits for its turn.  (Ring data

@@ -6,6 +6,8 @@ import os
 import sys
 
 import numpy as np
+
+os.environ.setdefault("OPMGPU_CLUSTER", "0")      # the traced kernel variants exist without clusters only
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
