@@ -50,6 +50,12 @@ constexpr int kPipeHelpers = 1;                                    // warps poll
 #ifndef OPMGPU_POLL_PER_LANE
 #define OPMGPU_POLL_PER_LANE 1
 #endif
+#ifndef OPMGPU_SPIN_HANDOVER
+#define OPMGPU_SPIN_HANDOVER 0
+#endif
+// 1: the groups hand the turn over through a shared-memory counter the waiting warps poll,
+// instead of named barriers (experiment)
+constexpr bool kPipeSpinHandover = OPMGPU_SPIN_HANDOVER != 0;
 constexpr int kPipePollPerLane = OPMGPU_POLL_PER_LANE;             // slots a helper lane examines per poll (a short poll = a short crossing)
 constexpr int kPipeThreads = 32 * (1 + kPipeHelpers + kPipeGroups * kPipeComputeWarps);
 constexpr int kPipeRowsPerPass = kPipeComputeWarps * 32;
@@ -89,6 +95,7 @@ struct PipeCtl {
     volatile int ext_consumed;
     volatile int ext_ready;
     volatile int abort_flag;
+    volatile int steps_done;                    // OPMGPU_SPIN_HANDOVER: compute warps that finished a step, all steps
 };
 
 // dependency array (window | pushed ring | zero entry) followed by the intra-cluster entries
@@ -429,7 +436,7 @@ ilu0_sweep_pipe_kernel(PipeDev pg, const double* __restrict__ rhs_perm, double* 
 
     if (tid == 0) {
         for (int i = 0; i < S; ++i) { mbar_init(&ctl->full[i], 1); mbar_init(&ctl->empty[i], kPipeComputeWarps); }
-        ctl->ext_consumed = 0; ctl->ext_ready = 0; ctl->abort_flag = 0;
+        ctl->ext_consumed = 0; ctl->ext_ready = 0; ctl->abort_flag = 0; ctl->steps_done = 0;
         dep[kDepZeroSlot * 3] = 0.0; dep[kDepZeroSlot * 3 + 1] = 0.0; dep[kDepZeroSlot * 3 + 2] = 0.0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -609,7 +616,10 @@ ilu0_sweep_pipe_kernel(PipeDev pg, const double* __restrict__ rhs_perm, double* 
             // usual answer (yes) is fetched while the group still waits for its turn.  (Ring data
             // is written before ext_ready, and shared-memory accesses of a thread are not reordered.)
             const bool ext_ok = dead || p.ext_cnt <= 0 || lds_s32_volatile(ctl_s + (uint32_t)offsetof(PipeCtl, ext_ready)) >= p.ext_end;
-            if (s > 0) asm volatile("bar.sync %0, %1;" ::"r"(bar_prev), "n"(NPP) : "memory");     // step s-1 done
+            if (kPipeSpinHandover) {                                                             // step s-1 done
+                const int need = kPipeComputeWarps * s;
+                while (lds_s32_volatile(ctl_s + (uint32_t)offsetof(PipeCtl, steps_done)) < need) { }
+            } else if (s > 0) asm volatile("bar.sync %0, %1;" ::"r"(bar_prev), "n"(NPP) : "memory");
             if (tr) pg.trace[s * 16 + 1] = pipe_clock_after(ctl->abort_flag);
             if (gt) gtr[s * 8 + 1] = pipe_gtime_after(ctl->abort_flag);
             if (!ext_ok) {
@@ -627,7 +637,10 @@ ilu0_sweep_pipe_kernel(PipeDev pg, const double* __restrict__ rhs_perm, double* 
             long long rb = 0;           // trace: read the first pushed value back through L2
             const bool gt_rb = gt && p.on && p.ri1.y >= 0;
             if (gt_rb) asm volatile("ld.relaxed.gpu.global.s64 %0, [%1];" : "=l"(rb) : "l"(pg.ext + (size_t)p.ri1.y * 3) : "memory");
-            asm volatile("bar.arrive %0, %1;" ::"r"(bar_own), "n"(NPP) : "memory");                // step s done
+            if (kPipeSpinHandover) {                                                               // step s done
+                __syncwarp();
+                if (lane == 0) asm volatile("red.shared.add.s32 [%0], 1;" ::"r"(ctl_s + (uint32_t)offsetof(PipeCtl, steps_done)) : "memory");
+            } else asm volatile("bar.arrive %0, %1;" ::"r"(bar_own), "n"(NPP) : "memory");
             sweep_row_pushes<UPPER, LEAN, CX>(p, stage + pg.rhs_bytes, r_first, pg.ext, acc, dep_s + 24u * (uint32_t)kCxBase);
             if (!LEAN) {            // tail lists of slow rows are read from the stage during the chain
                 __syncwarp();
@@ -644,7 +657,7 @@ ilu0_sweep_pipe_kernel(PipeDev pg, const double* __restrict__ rhs_perm, double* 
             if (st >= S) { st -= S; par ^= 1u; }
         }
         // consume the last hand-over addressed to this group so no barrier is left half-arrived
-        if (nsteps > 0 && (nsteps % G) == g) asm volatile("bar.sync %0, %1;" ::"r"(bar_prev), "n"(NPP) : "memory");
+        if (!kPipeSpinHandover && nsteps > 0 && (nsteps % G) == g) asm volatile("bar.sync %0, %1;" ::"r"(bar_prev), "n"(NPP) : "memory");
     }
     if (CX) {
         // other CTAs of the cluster may still be writing into this CTA's shared memory
