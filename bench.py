@@ -111,18 +111,44 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "how": "NVML, every 2 ms during the timed region"}
 
 
-def build_system(workload):
-    from opm_simulators_legacy_b200.jacobian import synth_blackoil_jacobian
+def build_system(workload, rank=0, world=1):
+    """The synthetic system of a workload.  Multi-GPU runs build it once, on rank 0 (CPU, so every
+    rank sees bit-identical inputs), and broadcast the arrays through NCCL: a rank never holds the
+    generator's temporaries (15 GB at 8M cells)."""
+    from opm_simulators_legacy_b200.jacobian import synth_blackoil_jacobian, SynthSystem
     dims, perm = WORKLOADS[workload]
-    return synth_blackoil_jacobian(*dims, perm=perm)
+    if world == 1:
+        return synth_blackoil_jacobian(*dims, perm=perm)
+    import torch
+    import torch.distributed as dist
+    s = synth_blackoil_jacobian(*dims, perm=perm) if rank == 0 else None
+    N = dims[0] * dims[1] * dims[2]
+    nnzb = 7 * N - 2 * (dims[0] * dims[1] + dims[1] * dims[2] + dims[0] * dims[2])
+    spec = [("rowptr", (N + 1,), torch.int32), ("colidx", (nnzb,), torch.int32), ("vals_unscaled", (nnzb, 9), torch.float64),
+            ("sat_present", (nnzb,), torch.bool), ("rhs_unscaled", (N, 3), torch.float64), ("xstar", (N, 3), torch.float64)]
+    got = {}
+    for name, shape, dt in spec:
+        t = getattr(s, name).cuda() if rank == 0 else torch.empty(shape, dtype=dt, device="cuda")
+        if dt == torch.bool:
+            t = t.to(torch.uint8)
+        dist.broadcast(t, 0)
+        got[name] = (t.to(torch.bool) if dt == torch.bool else t).cpu()
+        del t
+    torch.cuda.empty_cache()
+    if rank == 0:
+        return s
+    return SynthSystem(dims, N, nnzb, got["rowptr"], got["colidx"], got["vals_unscaled"], got["sat_present"],
+                       got["rhs_unscaled"], got["xstar"])
 
 
-def config_of(workload, s, n_gpus):
+def config_of(workload, s, n_gpus, axis=None):
     dims, perm = WORKLOADS[workload]
+    part = "single GPU" if n_gpus == 1 else (f"{n_gpus} slabs along grid axis {'ijk'[axis] if axis is not None else '?'} "
+                                              "(the weakest coupling), block-Jacobi ILU0")
     return {"workload": f"{workload}: synthetic 3-phase black-oil Jacobian, {dims[0]}x{dims[1]}x{dims[2]} "
                         f"Cartesian 7-point stencil, {perm} permeability, 3x3 BCRS",
             "cells": s.N, "nnzb": s.nnzb, "linear_solver_reduction": 1e-2, "linear_solver_maxiter": 150,
-            "ilu_relaxation": 0.9, "partition": "single GPU" if n_gpus == 1 else f"{n_gpus} slabs along the weakest-coupling axis, block-Jacobi ILU0",
+            "ilu_relaxation": 0.9, "partition": part,
             "l2": "inputs (>= 0.5 GB matrix) larger than the 126 MB L2; no explicit flush"}
 
 
@@ -153,21 +179,16 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
-def run_gpu(args, rank, world):
+def measure(workload, steps, warmup, rank, world, local, sample_clocks=True):
+    """One workload on `world` GPUs: device-timed solve, end-to-end solve, roofline of the ILU0
+    apply, parity against the CPU oracle.  Returns the pieces of the JSON line (rank 0) or None."""
     import numpy as np
     import torch
     import torch.distributed as dist
     from opm_simulators_legacy_b200.solver import GpuLinearSolver, make_params
 
-    local = int(os.environ.get("LOCAL_RANK", rank))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        from opm_simulators_legacy_b200.distributed import DistributedSolver
-    s = build_system(args.workload)
+    s = build_system(workload, rank, world)
     params = make_params()
-    stream = torch.cuda.Stream()
-    torch.cuda.set_stream(stream)
 
     if world == 1:
         g = GpuLinearSolver(local)
@@ -179,42 +200,66 @@ def run_gpu(args, rank, world):
         rhs = s.rhs.cuda()
         x = torch.zeros_like(rhs)
         solve = lambda: g.solve_bcrs_dev(vals, rhs, x, params=params)          # noqa: E731
+        axis = None
     else:
+        from opm_simulators_legacy_b200.distributed import DistributedSolver
         g = DistributedSolver(s, local)
         analysis_ms = g.analysis_ms
-        x = None
+        x = g.x
         solve = lambda: g.solve(params)                                          # noqa: E731
+        axis = g.axis
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # distributed SpMV against the oracle's global one (bit-exact: entries keep their natural order)
+    y_nat = None
+    if world > 1:
+        xs = s.xstar.numpy()
+        g.set_values_dev(g.vals)
+        y_loc = torch.from_numpy(g.spmv(xs[g.perm[g.lo:g.hi]])).cuda()
+        parts = [torch.zeros((int(g.offsets[r + 1] - g.offsets[r]), 3), dtype=torch.float64, device="cuda") for r in range(world)]
+        dist.all_gather(parts, y_loc)
+        if rank == 0:
+            y_nat = g.to_natural(torch.cat(parts).cpu().numpy())
+        del parts
+
     res = None
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         res = solve()
     g.set_profiling(True)
     l0 = g.launch_count()
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and sample_clocks:
         sampler.start()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         res = solve()
     ev1.record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if rank == 0 and sample_clocks else None
     ms_total = torch.tensor([ev0.elapsed_time(ev1)], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
-    ms = float(ms_total) / args.steps
+    ms = float(ms_total) / steps
     launches = g.launch_count() - l0
     prof = g.profile()
     g.set_profiling(False)
 
-    # ---- end to end through the C-ABI call with host buffers (rank-local system)
+    # the increment in natural cell order on rank 0
+    if world > 1:
+        parts = [torch.zeros((int(g.offsets[r + 1] - g.offsets[r]), 3), dtype=torch.float64, device="cuda") for r in range(world)]
+        dist.all_gather(parts, g.x)
+        x_nat = g.to_natural(torch.cat(parts).cpu().numpy()) if rank == 0 else None
+        del parts
+    else:
+        x_nat = x.cpu().numpy()
+
+    # ---- end to end through the C-ABI call with host buffers
     e2e = None
     if world > 1:
         vals_h = g.vals.cpu().pin_memory().numpy()
@@ -224,15 +269,15 @@ def run_gpu(args, rank, world):
         barrier()
         ev0.record()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
+        for _ in range(steps):
             g.solve_bcrs(vals_h, rhs_h, params=params)
         ev1.record()
         barrier()
-        t = torch.tensor([max((time.perf_counter() - t0) * 1e3, ev0.elapsed_time(ev1)) / args.steps], device="cuda", dtype=torch.float64)
+        t = torch.tensor([max((time.perf_counter() - t0) * 1e3, ev0.elapsed_time(ev1)) / steps], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": float(t), "unit": "ms", "h2d_bytes_per_step": int(vals_h.nbytes + rhs_h.nbytes),
                "d2h_bytes_per_step": int(rhs_h.nbytes), "call": "opmgpu_solve_bcrs3 (pinned host buffers, this rank's rows; bytes are per rank)"}
-    if world == 1:
+    else:
         blocks = s.csc_blocks()
         pinned = []
         for cp, ri, v in blocks:
@@ -243,26 +288,29 @@ def run_gpu(args, rank, world):
         h2d = sum(b[2].nbytes for b in pinned) + rhs_h.nbytes
         d2h = rhs_h.nbytes
         g.solve_from_csc_blocks(s.N, pinned, s.matbalscale, rhs_h, params=params, out=dx_h)       # pattern analysis, untimed
-        for _ in range(max(1, args.warmup // 2)):
+        for _ in range(max(1, warmup // 2)):
             g.solve_from_csc_blocks(s.N, pinned, s.matbalscale, rhs_h, params=params, out=dx_h)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         ev0.record()
-        for _ in range(args.steps):
+        for _ in range(steps):
             dx, r2 = g.solve_from_csc_blocks(s.N, pinned, s.matbalscale, rhs_h, params=params, out=dx_h)
         ev1.record()
         torch.cuda.synchronize()
-        wall = (time.perf_counter() - t0) * 1e3 / args.steps
-        e2e = {"value": max(wall, ev0.elapsed_time(ev1) / args.steps), "unit": "ms", "h2d_bytes_per_step": h2d,
+        wall = (time.perf_counter() - t0) * 1e3 / steps
+        e2e = {"value": max(wall, ev0.elapsed_time(ev1) / steps), "unit": "ms", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "call": "opmgpu_solve_from_csc_blocks (pinned host buffers)",
                "breakdown_ms": {k: r2[k] for k in ("ms_h2d", "ms_interleave", "ms_factor", "ms_solve", "ms_d2h")}}
+        del pinned, blocks
 
     if rank != 0:
-        return
+        g.close()
+        return None
     # ---- roofline of the dominant kernel class: ILU0 apply (lower + upper sweep)
-    with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-        peak = json.load(f).get("hbm_gbs") if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else None
-    peak_src = "measured (MEASURED_PEAKS.json)"
+    peak, peak_src = None, "measured (MEASURED_PEAKS.json)"
+    if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak = json.load(f).get("hbm_gbs")
     if not peak:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     # per launch = per rank: rank 0's rows (its diagonal block for the block-Jacobi ILU0)
@@ -273,43 +321,91 @@ def run_gpu(args, rank, world):
     ap_ms, ap_n = prof["ilu_apply"]
     sp_ms, sp_n = prof["spmv"]
     ach = b_ilu * ap_n / (ap_ms * 1e-3) / 1e9 if ap_ms > 0 else 0.0
+    # DRAM traffic of one apply from an `ncu --set full` capture: only quoted for the workload and
+    # GPU count it was captured on (profiles/r02_ncu_traffic.json), null otherwise
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get(args.workload, {}).get("ilu_apply_dram_bytes")
-    roofline = {"kernel": "ILU0 apply = ilu0_sweep_pipe_kernel<lower> + <upper> (right-hand side permuted by the producing vector kernel)", "bound": "hbm",
+            traffic = json.load(f).get(f"{workload}_n{world}", {}).get("ilu_apply_dram_bytes")
+    roofline = {"kernel": "ILU0 apply = lower + upper sweep kernel (right-hand side permuted by the producing vector kernel)", "bound": "hbm",
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
                 "traffic": traffic, "algorithmic_bytes_per_launch": b_ilu, "launches_timed": ap_n,
                 "avg_launch_us": ap_ms * 1e3 / max(ap_n, 1),
-                "share_of_step": ap_ms / (ms * args.steps),
+                "share_of_step": ap_ms / (ms * steps),
                 "spmv": {"achieved": b_spmv * sp_n / (sp_ms * 1e-3) / 1e9 if sp_ms > 0 else 0.0,
                          "avg_launch_us": sp_ms * 1e3 / max(sp_n, 1), "algorithmic_bytes_per_launch": b_spmv,
-                         "share_of_step": sp_ms / (ms * args.steps)},
-                "factor_share_of_step": prof["factor"][0] / (ms * args.steps),
-                "vector_share_of_step": prof["vector"][0] / (ms * args.steps)}
+                         "share_of_step": sp_ms / (ms * steps)},
+                "factor_share_of_step": prof["factor"][0] / (ms * steps),
+                "vector_share_of_step": prof["vector"][0] / (ms * steps)}
 
-    # ---- CPU baseline on this box's host cores (bounded sample: full solves of the same system)
+    # ---- CPU baseline on this box's host cores (bounded sample: one full solve of the same system)
     from oracle import oracle_py as O
     rp, ci, v, b = s.rowptr.numpy(), s.colidx.numpy(), s.vals.numpy(), s.rhs.numpy()
     t0 = time.perf_counter()
     x_ref, ref = O.solve_bcrs(rp, ci, v, b)
     cpu_ms = (time.perf_counter() - t0) * 1e3
-    parity = None
-    if x is not None:
-        xg = x.cpu().numpy()
+    true_red = float(np.linalg.norm(b - O.spmv(rp, ci, v, x_nat)) / np.linalg.norm(b))
+    if world == 1:
         parity = {"iterations_gpu": res["iterations"], "iterations_cpu_oracle": ref["iterations"],
-                  "max_rel_diff_increment": float((np.abs(xg - x_ref).max(0) / np.abs(x_ref).max(0)).max())}
-    line = {"metric": METRIC, "value": ms, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": config_of(args.workload, s, world), "clocks": clocks,
-            "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
-            "cpu_baseline": {"value": cpu_ms, "unit": "ms", "cores": 1, "kind": "port",
-                             "sample": "1 full solve of the same system (ILU0 factor + BiCGStab to 1e-2), "
-                                       "single thread like the reference's sequential dune-istl solver",
-                             "host_cpus": os.cpu_count()},
-            "iterations": res["iterations"], "reduction": res["reduction"], "analysis_ms_once_per_pattern": analysis_ms,
-            "solve_breakdown_ms": {"factor": res["ms_factor"], "bicgstab": res["ms_solve"]}, "parity": parity}
+                  "max_rel_diff_increment": float((np.abs(x_nat - x_ref).max(0) / np.abs(x_ref).max(0)).max()),
+                  "true_residual_reduction": true_red}
+    else:
+        # partitioned parity (BASELINE.json north_star): the true residual of the gathered increment
+        # is reduced by linear_solver_reduction; iteration counts side by side
+        parity = {"iterations_partitioned": res["iterations"], "iterations_oracle_unpartitioned": ref["iterations"],
+                  "true_residual_reduction": true_red, "tolerance": 1e-2, "within_tolerance": bool(true_red <= 1e-2 * 1.0001),
+                  "spmv_bit_exact": bool(np.array_equal(y_nat, O.spmv(rp, ci, v, s.xstar.numpy()))),
+                  "max_rel_diff_vs_unpartitioned": float((np.abs(x_nat - x_ref).max(0) / np.abs(x_ref).max(0)).max())}
+    out = {"ms": ms, "clocks": clocks, "e2e": e2e, "launches": launches, "roofline": roofline,
+           "cpu_baseline": {"value": cpu_ms, "unit": "ms", "cores": 1, "kind": "port",
+                            "sample": "1 full solve of the same system (ILU0 factor + BiCGStab to 1e-2), "
+                                      "single thread like the reference's sequential dune-istl solver",
+                            "host_cpus": os.cpu_count()},
+           "iterations": res["iterations"], "reduction": res["reduction"], "analysis_ms": analysis_ms,
+           "breakdown": {"factor": res["ms_factor"], "bicgstab": res["ms_solve"]}, "parity": parity,
+           "config": config_of(workload, s, world, axis)}
+    g.close()
+    return out
+
+
+def run_gpu(args, rank, world):
+    import torch
+    import torch.distributed as dist
+
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    m = measure(args.workload, args.steps, args.warmup, rank, world, local)
+    # the strong-scaling configuration (BASELINE.json config 4: 8M cells) beside the headline
+    c4 = None
+    if args.workload == "c3" and not args.no_c4:
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        k4 = max(2, min(args.steps, 3))
+        m4 = measure("c4", k4, 3, rank, world, local, sample_clocks=False)
+        if m4 is not None:
+            c4 = {"value": m4["ms"], "unit": "ms", "steps": k4, "warmup": 3, "iterations": m4["iterations"],
+                  "e2e": m4["e2e"], "ilu_apply_frac": m4["roofline"]["frac"], "ilu_apply_us": m4["roofline"]["avg_launch_us"],
+                  "spmv_gbs": m4["roofline"]["spmv"]["achieved"], "cpu_baseline_ms": m4["cpu_baseline"]["value"],
+                  "analysis_ms_once_per_pattern": m4["analysis_ms"], "parity": m4["parity"],
+                  "config": m4["config"]}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    line = {"metric": METRIC, "value": m["ms"], "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": m["ms"], "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": m["config"], "clocks": m["clocks"],
+            "e2e": m["e2e"], "gpu_launches": m["launches"], "roofline": m["roofline"],
+            "cpu_baseline": m["cpu_baseline"],
+            "iterations": m["iterations"], "reduction": m["reduction"], "analysis_ms_once_per_pattern": m["analysis_ms"],
+            "solve_breakdown_ms": m["breakdown"], "parity": m["parity"], "c4": c4}
     print(json.dumps(line), flush=True)
 
 
@@ -320,6 +416,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-c4", action="store_true", help="skip the 8M-cell sub-measurement of the default (c3) run")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", 0))

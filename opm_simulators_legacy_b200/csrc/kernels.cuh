@@ -18,7 +18,9 @@ constexpr int kExtBitDev = 0x40000000;
 // ---- device scalar block of the BiCGStab recurrences (lives in HBM, read by every kernel)
 enum ScalarSlot {
     S_RHO_OLD = 0, S_ALPHA = 1, S_OMEGA = 2, S_H = 3, S_TR = 4, S_TT = 5,
-    S_NRM2 = 6, S_RHO_NEW = 7, S_DOT = 8, S_COUNT = 16
+    S_NRM2 = 6,
+    S_ERRW = 7,       // != 0: the sweep watchdog word was set when the half-step ended (summed over ranks with S_NRM2)
+    S_RHO_NEW = 8, S_DOT = 9, S_COUNT = 16
 };
 
 // Host mailbox (page-locked, device-mapped): the kernel that finishes a BiCGStab half-step
@@ -39,6 +41,20 @@ __device__ __forceinline__ void hostbox_publish(const HostBox& hb)
     *hb.herr = *reinterpret_cast<const volatile int*>(hb.derr);
     __threadfence_system();
     *reinterpret_cast<volatile unsigned long long*>(hb.hseq) = hb.seq;
+}
+// Partitioned runs: the scalars are summed over the ranks (ncclAllReduce) after the kernel that
+// produced them, so the mailbox is written by this one-warp kernel that follows the reduction.
+// S[S_ERRW] then holds the number of ranks whose sweep watchdog fired: every rank sees the same
+// verdict and leaves the solve with the same status.
+__global__ void publish_scalars_kernel(const double* __restrict__ S, HostBox hb)
+{
+    if (threadIdx.x < S_COUNT) hb.hS[threadIdx.x] = S[threadIdx.x];
+    __syncwarp();
+    if (threadIdx.x == 0) {
+        *hb.herr = S[S_ERRW] != 0.0 ? 9 : 0;
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long*>(hb.hseq) = hb.seq;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -157,6 +173,7 @@ bicg_init_kernel(size_t n, const double* __restrict__ r, double* S, ReduceWs ws,
     grid_reduce<1>(v, ws, [=](double (&t)[1]) {
         S[S_NRM2] = t[0]; S[S_RHO_NEW] = t[0];
         S[S_RHO_OLD] = 1.0; S[S_ALPHA] = 1.0; S[S_OMEGA] = 1.0;
+        S[S_ERRW] = *reinterpret_cast<const volatile int*>(hb.derr) != 0 ? 1.0 : 0.0;
         if (hb.hS) { hb.hS[S_NRM2] = t[0]; hostbox_publish(hb); }
     });
 }
@@ -198,6 +215,7 @@ bicg_update1_kernel(size_t n, double* __restrict__ x, double* __restrict__ r,
     }
     grid_reduce<1>(s, ws, [=](double (&t)[1]) {
         S[S_NRM2] = t[0]; S[S_ALPHA] = alpha;
+        S[S_ERRW] = *reinterpret_cast<const volatile int*>(hb.derr) != 0 ? 1.0 : 0.0;
         if (hb.hS) { hb.hS[S_NRM2] = t[0]; hb.hS[S_H] = hdot; hostbox_publish(hb); }
     });
 }
@@ -223,6 +241,7 @@ bicg_update2_kernel(size_t n, double* __restrict__ x, double* __restrict__ r,
         S[S_RHO_OLD] = rho_old;
         S[S_NRM2] = u[0];
         S[S_RHO_NEW] = u[1];
+        S[S_ERRW] = *reinterpret_cast<const volatile int*>(hb.derr) != 0 ? 1.0 : 0.0;
         if (hb.hS) { hb.hS[S_OMEGA] = omega; hb.hS[S_RHO_OLD] = rho_old; hb.hS[S_NRM2] = u[0]; hostbox_publish(hb); }
     });
 }

@@ -699,6 +699,12 @@ int factor(opmgpu_handle h, int* bad_row)
     }
     }
     CK(cudaGetLastError());
+    if (h->world > 1) {
+        // a singular pivot or a watchdog trip on one rank must end the solve on every rank (the others
+        // would otherwise wait for it in the next collective): agree on the verdict
+        NK(g_nccl.AllReduce(h->d_bad.p, h->d_bad.p, 1, ncclInt32, ncclMin, h->comm, h->stream));
+        NK(g_nccl.AllReduce(h->d_err.p, h->d_err.p, 1, ncclInt32, ncclMax, h->comm, h->stream));
+    }
     CK(cudaMemcpyAsync(&h->h_flags2[1], h->d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(&h->h_flags2[0], h->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -807,7 +813,9 @@ int sweep_watchdog(opmgpu_handle h)
     return OPMGPU_CUDA_ERROR;
 }
 
-// mailbox of the next half-step-ending kernel (single-GPU handles only)
+// mailbox of the next half-step-ending kernel.  Partitioned handles: the kernel itself gets no
+// mailbox (its scalars are rank-local partial sums); publish_scalars_kernel writes it after the
+// all-reduce (reduce_and_publish).
 HostBox next_hostbox(opmgpu_handle h)
 {
     HostBox hb;
@@ -816,6 +824,19 @@ HostBox next_hostbox(opmgpu_handle h)
         hb.hS = h->h_S; hb.herr = &h->h_flags2[0]; hb.hseq = h->h_seq; hb.seq = ++h->seq;
     }
     return hb;
+}
+
+// partitioned handles: sum `count` scalars from S_NRM2 on over the ranks, then publish the whole
+// scalar block into the host mailbox (returned in hb for wait_scalars)
+int reduce_and_publish(opmgpu_handle h, int count, HostBox& hb)
+{
+    if (h->world == 1) return 0;
+    if (int rc = allreduce_slots(h, S_NRM2, count)) return rc;
+    if (!h->use_hostbox) return 0;
+    hb.hS = h->h_S; hb.herr = &h->h_flags2[0]; hb.hseq = h->h_seq; hb.seq = ++h->seq;
+    publish_scalars_kernel<<<1, 32, 0, h->stream>>>(h->d_S.p, hb);
+    h->launches++;
+    return 0;
 }
 
 int read_scalars(opmgpu_handle h);
@@ -843,6 +864,7 @@ int read_scalars(opmgpu_handle h)
     CK(cudaMemcpyAsync(h->h_S, h->d_S.p, sizeof(double) * S_COUNT, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(&h->h_flags2[0], h->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    if (h->world > 1) h->h_flags2[0] = h->h_S[S_ERRW] != 0.0 ? 9 : 0;      // the all-reduced verdict: the same on every rank
     if (h->h_flags2[0]) return sweep_watchdog(h);
     return 0;
 }
@@ -864,7 +886,7 @@ int bicgstab(opmgpu_handle h, const opmgpu_params* prm, opmgpu_result* res)
     HostBox hb = next_hostbox(h);
     bicg_init_kernel<<<kVecBlocks, 256, 0, h->stream>>>(n, h->d_r.p, h->d_S.p, h->ws(), hb);
     h->launches++;
-    if ((rc = allreduce_slots(h, S_NRM2, 2))) return rc;
+    if ((rc = reduce_and_publish(h, 3, hb))) return rc;
     if ((rc = wait_scalars(h, hb))) return rc;
     const double norm0 = std::sqrt(h->h_S[S_NRM2]);
     double norm = norm0, rho = 1.0, omega = 1.0, it = 0.0;
@@ -896,7 +918,7 @@ int bicgstab(opmgpu_handle h, const opmgpu_params* prm, opmgpu_result* res)
         bicg_update1_kernel<<<kVecBlocks, 256, 0, h->stream>>>(n, h->d_x.p, h->d_r.p, h->d_y.p, h->d_v.p, h->d_S.p, h->ws(), hb, lpos, lperm);
         h->prof_end();
         h->launches++;
-        if ((rc = allreduce_slots(h, S_NRM2, 1))) return rc;
+        if ((rc = reduce_and_publish(h, 2, hb))) return rc;
         if ((rc = wait_scalars(h, hb))) return rc;
         if (std::fabs(h->h_S[S_H]) < EPSILON) { status = OPMGPU_BREAKDOWN; break; }
         norm = std::sqrt(h->h_S[S_NRM2]);
@@ -917,7 +939,7 @@ int bicgstab(opmgpu_handle h, const opmgpu_params* prm, opmgpu_result* res)
         bicg_update2_kernel<<<kVecBlocks, 256, 0, h->stream>>>(n, h->d_x.p, h->d_r.p, h->d_y.p, h->d_t.p, h->d_rt.p, h->d_S.p, h->ws(), hb);
         h->prof_end();
         h->launches++;
-        if ((rc = allreduce_slots(h, S_NRM2, 2))) return rc;
+        if ((rc = reduce_and_publish(h, 3, hb))) return rc;
         if ((rc = wait_scalars(h, hb))) return rc;
         omega = h->h_S[S_OMEGA];
         rho = h->h_S[S_RHO_OLD];

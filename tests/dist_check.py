@@ -16,12 +16,41 @@ from opm_simulators_legacy_b200.distributed import DistributedSolver  # noqa: E4
 from opm_simulators_legacy_b200.solver import make_params  # noqa: E402
 
 dims = tuple(int(a) for a in sys.argv[1:4]) if len(sys.argv) > 3 else (24, 20, 16)
+singular = "--singular" in sys.argv        # one rank's slab holds a singular pivot: every rank must return, none may hang
 local = int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 rank, world = dist.get_rank(), dist.get_world_size()
 s = synth_blackoil_jacobian(*dims, perm="lognormal")
 g = DistributedSolver(s, local)
+if singular:
+    # zero the diagonal block of the first row of the LAST rank's slab (row 0 of a slab has no lower
+    # blocks inside the slab, so its pivot is the block itself)
+    from opm_simulators_legacy_b200.solver import NumericalIssue
+    if rank == world - 1:
+        # local pattern: the diagonal of local row 0 is the entry whose global column equals the slab's first row
+        import numpy as _np
+        from opm_simulators_legacy_b200.distributed import local_rows_permuted, local_rows
+        g_rp, g_ci, g_v, g_b = s.rowptr.numpy(), s.colidx.numpy(), s.vals.numpy(), s.rhs.numpy()
+        rp_l, cg_l, _, _ = (local_rows(g_rp, g_ci, g_v, g_b, g.lo, g.hi) if g.axis == 2
+                            else local_rows_permuted(g_rp, g_ci, g_v, g_b, g.perm, g.lo, g.hi))
+        k = int(_np.nonzero(cg_l[rp_l[0]:rp_l[1]] == g.lo)[0][0])
+        g.vals[k] = 0.0
+    status = "no exception"
+    try:
+        g.solve(make_params())
+    except NumericalIssue as e:
+        status = "NumericalIssue"
+    codes = [None] * world
+    dist.all_gather_object(codes, status)
+    if rank == 0:
+        ok = all(c == "NumericalIssue" for c in codes)
+        print(json.dumps({"singular_slab": codes, "ok": ok}))
+        if not ok:
+            sys.exit(1)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0)
 # distributed SpMV against the global one
 xs = s.xstar.numpy()
 g.set_values_dev(g.vals)
