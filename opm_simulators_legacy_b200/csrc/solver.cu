@@ -9,6 +9,8 @@
 #include "kernels.cuh"
 #include "sweep_pipe.cuh"
 #include "factor_pipe.cuh"
+#include "colprog.hpp"
+#include "sweep_col.cuh"
 #include "spmv_tma.cuh"
 
 #include <dlfcn.h>
@@ -124,6 +126,24 @@ struct PipeDevMem {
     }
 };
 
+// column-owned sweep program (exact Cartesian stencils, colprog.hpp)
+struct ColDevMem {
+    bool valid = false;
+    ColGeom g = {};
+    int P = 0, nstagesL = 0, nstagesU = 0;
+    size_t smemL = 0, smemU = 0, nperm = 0, next = 0, nvalL = 0, nvalU = 0;
+    DevArr<double> recL, recU, extL, extU, rhsL, rhsU;
+    DevArr<int> tile_ptr, tilesL, tilesU, valL_src, valU_src, perm_row, pos_of_row;
+    DevArr<unsigned long long> valL_dst, valU_dst;
+    void release()
+    {
+        recL.release(); recU.release(); extL.release(); extU.release(); rhsL.release(); rhsU.release();
+        tile_ptr.release(); tilesL.release(); tilesU.release(); valL_src.release(); valU_src.release();
+        perm_row.release(); pos_of_row.release(); valL_dst.release(); valU_dst.release();
+        valid = false;
+    }
+};
+
 struct FactorPipeDevMem {
     DevArr<unsigned char> buf;
     DevArr<int> cta_step_ptr, val_src, cta_row_base, fpos;
@@ -160,6 +180,8 @@ struct opmgpu_solver {
     ProgramDevMem progL, progU;
     PipeDevMem pipeL, pipeU;
     FactorPipeDevMem pipeF;
+    ColDevMem col;                 // column-owned sweeps (exact Cartesian stencils); replaces pipeL / pipeU when valid
+    bool use_col = false, allow_col = false;     // OPMGPU_COL=1: column-owned sweeps on exact Cartesian stencils (experimental, slower so far: profiles/r02_column_sweeps.md)
     bool factor_tile = false;      // OPMGPU_FACTOR_TILE=1: keep the flag-synchronised tile kernel
     bool lu_lazy = false;          // the pipelined factorisation left only pivots: d_lu is built on demand
     ClusterCaps caps;              // co-resident CTAs of the cluster variants of the sweep kernels
@@ -390,6 +412,50 @@ int upload_factor_pipe(opmgpu_handle h, const FactorPipeProgram& p, FactorPipeDe
     return 0;
 }
 
+int upload_col(opmgpu_handle h, const ColProgram& p, ColDevMem& d)
+{
+    int rc;
+    d.valid = false;
+    d.g = p.g; d.P = p.P; d.nperm = (size_t)p.nperm; d.next = (size_t)p.next;
+    d.nvalL = p.valL_src.size(); d.nvalU = p.valU_src.size();
+    d.nstagesL = col_stage_count(p.g, false, (size_t)h->max_smem_optin);
+    d.nstagesU = col_stage_count(p.g, true, (size_t)h->max_smem_optin);
+    if (const char* e = std::getenv("OPMGPU_COL_STAGES")) {
+        d.nstagesL = std::max(2, std::min(d.nstagesL, std::atoi(e))); d.nstagesU = std::max(2, std::min(d.nstagesU, std::atoi(e)));
+    }
+    if (d.nstagesL < 2 || d.nstagesU < 2) return 0;
+    d.smemL = col_smem_fixed(p.g) + (size_t)p.g.W * d.nstagesL * col_stage_bytes(false);
+    d.smemU = col_smem_fixed(p.g) + (size_t)p.g.W * d.nstagesU * col_stage_bytes(true);
+    if ((rc = upload(h, d.tile_ptr, p.cta_tile_ptr))) return rc;
+    if ((rc = upload(h, d.tilesL, p.cta_tilesL))) return rc;
+    if ((rc = upload(h, d.tilesU, p.cta_tilesU))) return rc;
+    if ((rc = upload(h, d.valL_src, p.valL_src))) return rc;
+    if ((rc = upload(h, d.valU_src, p.valU_src))) return rc;
+    if ((rc = upload(h, d.valL_dst, p.valL_dst))) return rc;
+    if ((rc = upload(h, d.valU_dst, p.valU_dst))) return rc;
+    if ((rc = upload(h, d.perm_row, p.perm_rowL))) return rc;
+    {
+        // natural row -> lane-step of the lower sweep (the vector kernels write its right-hand side in place)
+        std::vector<int> pos((size_t)h->N_for_upload, 0);
+        for (size_t q = 0; q < p.perm_rowL.size(); ++q)
+            if (p.perm_rowL[q] >= 0) pos[p.perm_rowL[q]] = (int)q;
+        if ((rc = upload(h, d.pos_of_row, pos))) return rc;
+        CK(cudaStreamSynchronize(h->stream));          // pos is a local
+    }
+    // records: zero wherever a block (or a whole lane-step) does not exist; values arrive per factorisation
+    CK(d.recL.ensure(d.nperm * kColNCL)); CK(d.recU.ensure(d.nperm * kColNCU));
+    CK(cudaMemsetAsync(d.recL.p, 0, d.nperm * kColNCL * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(d.recU.p, 0, d.nperm * kColNCU * sizeof(double), h->stream));
+    CK(d.rhsL.ensure(d.nperm * 3)); CK(d.rhsU.ensure(d.nperm * 3));
+    CK(cudaMemsetAsync(d.rhsL.p, 0, d.nperm * 3 * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(d.rhsU.p, 0, d.nperm * 3 * sizeof(double), h->stream));
+    CK(d.extL.ensure(std::max<size_t>(d.next, 1) * 3)); CK(d.extU.ensure(std::max<size_t>(d.next, 1) * 3));
+    CK(cudaMemsetAsync(d.extL.p, 0xff, std::max<size_t>(d.next, 1) * 3 * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(d.extU.p, 0xff, std::max<size_t>(d.next, 1) * 3 * sizeof(double), h->stream));
+    d.valid = true;
+    return 0;
+}
+
 PipeDev pipe_dev(const PipeDevMem& d)
 {
     PipeDev p;
@@ -448,7 +514,19 @@ int set_pattern(opmgpu_handle h, int N, int nnzb, const int* rowptr, const int* 
     if ((rc = upload(h, h->d_lvl_rows, h->an.lvl_rows))) return rc;
     h->use_pipe = h->an.pipeL.valid && h->an.pipeU.valid;
     h->N_for_upload = N;
-    if (h->use_pipe) {
+    h->use_col = false;
+    if (h->use_pipe && h->allow_col && h->an.grid_nx > 0) {
+        // exact Cartesian stencil: column-owned sweeps (colprog.hpp) instead of the general pipelined ones
+        ColProgram cp;
+        build_col_program(N, rowptr, colidx, h->an.diag, h->an.grid_nx, h->an.grid_ny, h->an.grid_nz, h->sm_count,
+                          (size_t)h->max_smem_optin, cp);
+        if (cp.valid) {
+            if ((rc = upload_col(h, cp, h->col))) return rc;
+            h->use_col = h->col.valid;
+        }
+    }
+    if (!h->use_col) h->col.release();
+    if (h->use_pipe && !h->use_col) {
         if ((rc = upload_pipe(h, h->an.pipeL, h->pipeL))) return rc;
         if ((rc = upload_pipe(h, h->an.pipeU, h->pipeU))) return rc;
         if ((h->pipeL.nstages < 3 || h->pipeU.nstages < 3) && h->cluster_size > 1) {
@@ -461,6 +539,7 @@ int set_pattern(opmgpu_handle h, int N, int nnzb, const int* rowptr, const int* 
         }
         if (h->pipeL.nstages < 3 || h->pipeU.nstages < 3) h->use_pipe = false;
     }
+    if (h->use_col) { h->pipeL.release(); h->pipeU.release(); h->cluster_size = 1; }
     h->pipeF.valid = false;
     if (h->use_pipe && !h->factor_tile && !h->factor_by_levels) {
         if ((rc = upload_factor_pipe(h, h->an.pipeF, h->pipeF))) return rc;
@@ -656,7 +735,20 @@ int factor(opmgpu_handle h, int* bad_row)
     }
     CK(cudaGetLastError());
     // stream the factors into the sweep programs' layout
-    if (h->use_pipe && pipe_factor) {
+    if (h->use_col) {
+        ColDevMem& c = h->col;
+        const unsigned gridL = (unsigned)std::min<size_t>((c.nvalL * 3 + 255) / 256, (size_t)h->sm_count * 16);
+        const unsigned gridU = (unsigned)std::min<size_t>((c.nvalU * 3 + 255) / 256, (size_t)h->sm_count * 16);
+        if (pipe_factor) {
+            const FactorPipeDevMem& f = h->pipeF;
+            if (c.nvalL) repack_col_kernel<true><<<gridL, 256, 0, h->stream>>>(c.nvalL, c.valL_src.p, c.valL_dst.p, h->d_colidx.p, f.fpos.p, ilu_A, f.fout.p, c.recL.p);
+            repack_col_kernel<false><<<gridU, 256, 0, h->stream>>>(c.nvalU, c.valU_src.p, c.valU_dst.p, h->d_colidx.p, f.fpos.p, ilu_A, f.fout.p, c.recU.p);
+        } else {
+            if (c.nvalL) repack_col_from_lu_kernel<true><<<gridL, 256, 0, h->stream>>>(c.nvalL, c.valL_src.p, c.valL_dst.p, h->d_lu.p, c.recL.p);
+            repack_col_from_lu_kernel<false><<<gridU, 256, 0, h->stream>>>(c.nvalU, c.valU_src.p, c.valU_dst.p, h->d_lu.p, c.recU.p);
+        }
+        h->launches += c.nvalL ? 2 : 1;
+    } else if (h->use_pipe && pipe_factor) {
         // L_ij = A_ij * inv(D_j) is formed here, from A and the program-ordered pivots.  (Copying the
         // U blocks on a second stream beside the factorisation kernel was measured: it slows that
         // latency-bound kernel down by more than the copy costs, 0.84 -> 0.99 ms per factorisation.)
@@ -755,6 +847,66 @@ int launch_sweep(opmgpu_handle h, bool upper, const PipeDevMem& d, void** args)
 int apply_precond(opmgpu_handle h, double w, const double* d, double* v, bool d_in_program_order = false)
 {
     const int scale = std::fabs(w - 1.0) > 1e-15 ? 1 : 0;      // relaxation_ flag of the reference
+    if (h->use_col) {
+        ColDevMem& c = h->col;
+        if (!d_in_program_order) {
+            const size_t e = c.nperm * 3;
+            permute_rows_kernel<<<(unsigned)((e + 255) / 256), 256, 0, h->stream>>>(c.nperm, c.perm_row.p, d, c.rhsL.p);
+        }
+        for (int upper = 0; upper < 2; ++upper) {
+            ColDev pg;
+            pg.g = c.g; pg.rec = upper ? c.recU.p : c.recL.p; pg.cta_tile_ptr = c.tile_ptr.p;
+            pg.cta_tiles = upper ? c.tilesU.p : c.tilesL.p; pg.ext = upper ? c.extU.p : c.extL.p;
+            pg.nstages = upper ? c.nstagesU : c.nstagesL;
+            static const int pf = getenv("OPMGPU_COL_PF") ? atoi(getenv("OPMGPU_COL_PF")) : 12;
+            pg.pf_ahead = pf;
+            // service warps: with W <= 3 every compute warp keeps a scheduler (SM sub-partition) to
+            // itself and the producer (mostly asleep) shares one with the helper
+            static const int roles = getenv("OPMGPU_COL_ROLES") ? atoi(getenv("OPMGPU_COL_ROLES")) : 1;
+            int nwarps = c.g.W + 2;
+            pg.producer_warp = c.g.W; pg.helper_warp = c.g.W + 1;
+            if (roles == 1 && c.g.W <= 3) { nwarps = 8; pg.producer_warp = 3; pg.helper_warp = 7; }
+            pg.prof = nullptr; pg.trace = nullptr; pg.trace_cta = -1;
+            static const int trace_cta = getenv("OPMGPU_COL_TRACE") ? atoi(getenv("OPMGPU_COL_TRACE")) : -1;
+            static const bool prof = getenv("OPMGPU_COL_PROF") != nullptr;
+            if (prof) {
+                CK(h->d_trace.ensure((size_t)c.P * 8 * 4));
+                CK(cudaMemsetAsync(h->d_trace.p, 0, sizeof(long long) * (size_t)c.P * 8 * 4, h->stream));
+                pg.prof = h->d_trace.p;
+                if (trace_cta >= 0) {
+                    CK(h->d_gtrace.ensure((size_t)c.g.T * 8));
+                    CK(cudaMemsetAsync(h->d_gtrace.p, 0, sizeof(long long) * (size_t)c.g.T * 8, h->stream));
+                    pg.trace = h->d_gtrace.p; pg.trace_cta = trace_cta;
+                }
+            }
+            const double* rhs = upper ? c.rhsU.p : c.rhsL.p; double* hand = upper ? nullptr : c.rhsU.p;
+            double* out = upper ? v : nullptr; int* err = h->d_err.p;
+            void* args[] = {&pg, &rhs, &hand, &out, &w, (void*)&scale, &err};
+            const void* fn = upper ? (prof ? (const void*)ilu0_sweep_col_kernel<true, true> : (const void*)ilu0_sweep_col_kernel<true, false>)
+                                   : (prof ? (const void*)ilu0_sweep_col_kernel<false, true> : (const void*)ilu0_sweep_col_kernel<false, false>);
+            CK(cudaLaunchCooperativeKernel(fn, dim3(c.P), dim3(32 * nwarps), args, upper ? c.smemU : c.smemL, h->stream));
+            if (prof) {
+                std::vector<long long> pr((size_t)c.P * 8 * 4);
+                CK(cudaMemcpyAsync(pr.data(), h->d_trace.p, sizeof(long long) * pr.size(), cudaMemcpyDeviceToHost, h->stream));
+                CK(cudaStreamSynchronize(h->stream));
+                double rec = 0, ring = 0, all = 0, steps = 0, worst = 0;
+                for (size_t i = 0; i < pr.size(); i += 4) { rec += pr[i]; ring += pr[i + 1]; all += pr[i + 2]; steps += pr[i + 3]; worst = std::max(worst, (double)pr[i + 2]); }
+                if (trace_cta >= 0) {
+                    std::vector<long long> tr((size_t)c.g.T * 8);
+                    CK(cudaMemcpy(tr.data(), h->d_gtrace.p, sizeof(long long) * tr.size(), cudaMemcpyDeviceToHost));
+                    fprintf(stderr, "[opmgpu] col %s sweep, CTA %d warp 0: step: start(rel) | waits | loads+shuffles+chain | release+stores\n", upper ? "upper" : "lower", trace_cta);
+                    for (int t = 0; t < c.g.T; ++t) {
+                        const long long* q = &tr[(size_t)t * 8];
+                        fprintf(stderr, "  %3d: %8lld | %5lld | %6lld | %5lld\n", t, q[0] - tr[0], q[1] - q[0], q[2] - q[1], q[3] - q[2]);
+                    }
+                }
+                fprintf(stderr, "[opmgpu] col %s sweep: per step %.0f cycles (waits %.0f, loads+chain %.0f, rest %.0f); longest warp %.0f cycles\n",
+                        upper ? "upper" : "lower", all / steps, rec / steps, ring / steps, (all - rec - ring) / steps, worst);
+            }
+        }
+        h->launches += d_in_program_order ? 2 : 3;
+        return 0;
+    }
     if (h->use_pipe) {
         if (!d_in_program_order) {
             const size_t e = h->pipeL.nperm * 3;
@@ -807,6 +959,10 @@ int sweep_watchdog(opmgpu_handle h)
     cudaMemsetAsync(h->d_err.p, 0, sizeof(int), h->stream);
     for (PipeDevMem* d : {&h->pipeL, &h->pipeU})
         if (d->ext.p) cudaMemsetAsync(d->ext.p, 0xff, std::max<size_t>(d->next, 1) * 3 * sizeof(double), h->stream);
+    if (h->col.valid) {
+        cudaMemsetAsync(h->col.extL.p, 0xff, std::max<size_t>(h->col.next, 1) * 3 * sizeof(double), h->stream);
+        cudaMemsetAsync(h->col.extU.p, 0xff, std::max<size_t>(h->col.next, 1) * 3 * sizeof(double), h->stream);
+    }
     if (h->pipeF.ext.p) cudaMemsetAsync(h->pipeF.ext.p, 0xff, std::max<size_t>(h->pipeF.next, 1) * 9 * sizeof(double), h->stream);
     if (h->progL.fslots.p) cudaMemsetAsync(h->progL.fslots.p, 0xff, std::max<size_t>(h->progL.n_fslots, 1) * 9 * sizeof(double), h->stream);
     cudaStreamSynchronize(h->stream);
@@ -881,8 +1037,8 @@ int bicgstab(opmgpu_handle h, const opmgpu_params* prm, opmgpu_result* res)
     CK(cudaMemsetAsync(h->d_x.p, 0, n * sizeof(double), h->stream));
     CK(cudaMemcpyAsync(h->d_rt.p, h->d_r.p, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     // the vector kernels write the next right-hand side of the lower sweep in program order
-    const int* lpos = h->use_pipe && h->fuse_permute ? h->pipeL.pos_of_row.p : nullptr;
-    double* lperm = h->use_pipe ? h->pipeL.rhs_perm.p : nullptr;
+    const int* lpos = h->use_pipe && h->fuse_permute ? (h->use_col ? h->col.pos_of_row.p : h->pipeL.pos_of_row.p) : nullptr;
+    double* lperm = h->use_pipe ? (h->use_col ? h->col.rhsL.p : h->pipeL.rhs_perm.p) : nullptr;
     HostBox hb = next_hostbox(h);
     bicg_init_kernel<<<kVecBlocks, 256, 0, h->stream>>>(n, h->d_r.p, h->d_S.p, h->ws(), hb);
     h->launches++;
@@ -1096,6 +1252,11 @@ int opmgpu_create(int device, opmgpu_handle* out)
     cudaFuncSetAttribute(spmv3_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
     cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     cudaFuncSetAttribute(ilu0_factor_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
+    cudaFuncSetAttribute(ilu0_sweep_col_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
+    cudaFuncSetAttribute(ilu0_sweep_col_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
+    cudaFuncSetAttribute(ilu0_sweep_col_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
+    cudaFuncSetAttribute(ilu0_sweep_col_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
+    if (const char* s = getenv("OPMGPU_COL")) h->allow_col = atoi(s) != 0;
     cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
     cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
     cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
@@ -1173,7 +1334,7 @@ int opmgpu_destroy(opmgpu_handle h)
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     h->d_rowptr.release(); h->d_colidx.release(); h->d_diag.release(); h->d_lvl_rows.release();
-    h->progL.release(); h->progU.release(); h->pipeL.release(); h->pipeU.release();
+    h->progL.release(); h->progU.release(); h->pipeL.release(); h->pipeU.release(); h->pipeF.release(); h->col.release();
     h->d_vals_own.release(); h->d_lu.release();
     h->d_x.release(); h->d_r.release(); h->d_rt.release(); h->d_p.release(); h->d_v.release();
     h->d_t.release(); h->d_y.release(); h->d_yL.release(); h->d_vU.release(); h->d_tmp.release(); h->d_tmp2.release();
@@ -1526,7 +1687,7 @@ int opmgpu_get_profile(opmgpu_handle h, double ms[4], long long count[4])
 // nrows, bulk issued, rhs gather issued, -}.
 int opmgpu_debug_trace_apply(opmgpu_handle h, int cta, double w, const double* d_dev, double* v_dev, long long* out)
 {
-    if (!h || !h->have_factors || !h->use_pipe) return OPMGPU_BAD_ARGUMENT;
+    if (!h || !h->have_factors || !h->use_pipe || h->use_col) return OPMGPU_BAD_ARGUMENT;
     CK(cudaSetDevice(h->device));
     CK(h->d_trace.ensure(2 * 512 * 16));
     CK(cudaMemsetAsync(h->d_trace.p, 0, sizeof(long long) * 2 * 512 * 16, h->stream));
@@ -1545,7 +1706,7 @@ int opmgpu_debug_trace_apply(opmgpu_handle h, int cta, double w, const double* d
 // delivery, its polls}; then the helper's deliveries [P][1024][2] = {time, polls<<32 | ext_ready}.
 int opmgpu_debug_gtrace_apply(opmgpu_handle h, int steps, double w, const double* d_dev, double* v_dev, long long* out, int* P_out)
 {
-    if (!h || !h->have_factors || !h->use_pipe || steps < 2) return OPMGPU_BAD_ARGUMENT;
+    if (!h || !h->have_factors || !h->use_pipe || h->use_col || steps < 2) return OPMGPU_BAD_ARGUMENT;
     CK(cudaSetDevice(h->device));
     const size_t n = (size_t)(h->pipeL.P + h->pipeU.P) * (steps * 8 + 2048);
     if (P_out) { P_out[0] = h->pipeL.P; P_out[1] = h->pipeU.P; }

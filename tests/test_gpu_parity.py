@@ -317,3 +317,27 @@ def test_cpp_host_mirror_selftest():
     assert os.path.exists(exe), "run __graft_entry__.build() first"
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
+
+
+@pytest.mark.parametrize("dims", [(24, 20, 12), (40, 40, 20), (120, 125, 6), (7, 6, 40), (64, 1, 1)])
+def test_column_owned_sweeps_bit_exact(oracle, dims, monkeypatch):
+    """The experimental column-owned sweep kernels (OPMGPU_COL=1, sweep_col.cuh): same bits as
+    ParallelOverlappingILU0::apply, same iteration counts."""
+    monkeypatch.setenv("OPMGPU_COL", "1")
+    s = synth_blackoil_jacobian(*dims, perm="lognormal")
+    rp, ci, v, b = _np(s)
+    g = GpuLinearSolver(0)
+    try:
+        g.set_pattern(rp, ci)
+        g.set_values(v)
+        assert g.ilu0_factor() == -1
+        lu_ref, bad = oracle.ilu0_factor(rp, ci, v)
+        for w in (0.9, 1.0):
+            for _ in range(2):
+                assert np.array_equal(g.ilu0_apply(w, b), oracle.ilu0_apply(rp, ci, lu_ref, w, b))
+        x, res = g.solve_bcrs(v, b)
+        x_ref, ref = oracle.solve_bcrs(rp, ci, v, b)
+        assert res["iterations"] == ref["iterations"]
+        assert (np.abs(x - x_ref).max(0) <= 1e-8 * np.abs(x_ref).max(0)).all()
+    finally:
+        g.close()
