@@ -53,6 +53,9 @@ typedef struct {
     int    require_full_sparsity_pattern;          /* 0    */
     int    max_half_steps;                         /* -1; >=0 stops after that many half iterations
                                                       (parity checks at equal half-step counts)      */
+    int    newton_use_gmres;                       /* 0; 1: Dune::RestartedGMResSolver instead of
+                                                      BiCGSTABSolver (ISTLSolver.hpp:257-265)        */
+    int    linear_solver_restart;                  /* 40   */
 } opmgpu_params;
 
 /* Dune::InverseOperatorResult plus what the benchmark reports. */

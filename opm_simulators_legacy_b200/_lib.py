@@ -36,7 +36,9 @@ class Params(C.Structure):
                 ("linear_solver_verbosity", C.c_int),
                 ("linear_solver_ignoreconvergencefailure", C.c_int),
                 ("require_full_sparsity_pattern", C.c_int),
-                ("max_half_steps", C.c_int)]
+                ("max_half_steps", C.c_int),
+                ("newton_use_gmres", C.c_int),
+                ("linear_solver_restart", C.c_int)]
 
 
 class Result(C.Structure):

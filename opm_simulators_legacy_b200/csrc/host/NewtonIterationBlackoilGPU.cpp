@@ -151,9 +151,12 @@ NewtonIterationBlackoilGPU::NewtonIterationBlackoilGPU(const ParameterGroup& par
     parameters_.linear_solver_verbosity = param.getDefault("linear_solver_verbosity", parameters_.linear_solver_verbosity);
     parameters_.linear_solver_ignoreconvergencefailure = param.getDefault("linear_solver_ignoreconvergencefailure", false) ? 1 : 0;
     parameters_.require_full_sparsity_pattern = param.getDefault("require_full_sparsity_pattern", false) ? 1 : 0;
-    if (param.getDefault("newton_use_gmres", false) || param.getDefault("linear_solver_use_amg", false) ||
-        param.getDefault("ilu_fillin_level", 0) != 0 || param.getDefault("ilu_redblack", false))
-        throw std::invalid_argument("solver_approach=gpu supports ILU0-preconditioned BiCGStab only");
+    parameters_.newton_use_gmres = param.getDefault("newton_use_gmres", false) ? 1 : 0;
+    parameters_.linear_solver_restart = param.getDefault("linear_solver_restart", parameters_.linear_solver_restart);
+    if (param.getDefault("linear_solver_use_amg", false) || param.getDefault("ilu_fillin_level", 0) != 0 ||
+        param.getDefault("ilu_redblack", false) || param.getDefault("ilu_milu", std::string("ILU")) != "ILU")
+        throw std::invalid_argument("solver_approach=gpu supports ILU0-preconditioned BiCGStab / restarted GMRes only "
+                                    "(no AMG/CPR, no fill-in, no red-black ordering, no MILU)");
     if (opmgpu_create(device, &handle_) != OPMGPU_OK)
         throw std::runtime_error(std::string("NewtonIterationBlackoilGPU: ") + opmgpu_last_error(nullptr));
 }

@@ -12,6 +12,7 @@
 #include "colprog.hpp"
 #include "sweep_col.cuh"
 #include "spmv_tma.cuh"
+#include "gmres.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>      // types only: the library is resolved at run time with dlopen
@@ -203,6 +204,7 @@ struct opmgpu_solver {
     // vectors (3N each)
     DevArr<double> d_x, d_r, d_rt, d_p, d_v, d_t, d_y, d_yL, d_vU, d_tmp, d_tmp2;
     DevArr<double> d_S, d_partials;
+    DevArr<double> d_gmres_V, d_gmres_H;      // restarted GMRES (newton_use_gmres): m+1 basis vectors, one Hessenberg column
     DevArr<unsigned> d_ticket;
     DevArr<int> d_flags, d_err, d_bad;
     int epoch = 0;
@@ -1046,6 +1048,17 @@ int bicgstab(opmgpu_handle h, const opmgpu_params* prm, opmgpu_result* res)
     if ((rc = wait_scalars(h, hb))) return rc;
     const double norm0 = std::sqrt(h->h_S[S_NRM2]);
     double norm = norm0, rho = 1.0, omega = 1.0, it = 0.0;
+    // linear_solver_verbosity as dune's solvers read it: > 0 header and summary, > 1 a line per (half) iteration
+    const int verbose = h->rank == 0 ? prm->linear_solver_verbosity : 0;
+    double norm_old = norm0;
+    if (verbose > 0) {
+        std::printf("=== opmgpu BiCGSTABSolver (ILU0, %d block rows)\n", h->N);
+        if (verbose > 1) std::printf(" Iter          Defect            Rate\n%5.1f %15.6e\n", 0.0, norm0);
+    }
+    auto report = [&](double itv) {
+        if (verbose > 1) std::printf("%5.1f %15.6e %15.6e\n", itv, norm, norm_old > 0 ? norm / norm_old : 0.0);
+        norm_old = norm;
+    };
     int half = 0, status = OPMGPU_OK, converged = 0;
     res->norm0 = norm0;
     if (norm < norm0 * red || norm < 1e-30) {
@@ -1079,6 +1092,7 @@ int bicgstab(opmgpu_handle h, const opmgpu_params* prm, opmgpu_result* res)
         if (std::fabs(h->h_S[S_H]) < EPSILON) { status = OPMGPU_BREAKDOWN; break; }
         norm = std::sqrt(h->h_S[S_NRM2]);
         h->history.push_back(norm);
+        report(it);
         ++half;
         if (norm < norm0 * red) { converged = 1; break; }
         it += 0.5;
@@ -1101,6 +1115,7 @@ int bicgstab(opmgpu_handle h, const opmgpu_params* prm, opmgpu_result* res)
         rho = h->h_S[S_RHO_OLD];
         norm = std::sqrt(h->h_S[S_NRM2]);
         h->history.push_back(norm);
+        report(it);
         ++half;
         if (norm < norm0 * red || norm < 1e-30) { converged = 1; break; }
     }
@@ -1109,8 +1124,142 @@ int bicgstab(opmgpu_handle h, const opmgpu_params* prm, opmgpu_result* res)
     res->converged = converged;
     res->half_steps = half;
     res->reduction = norm / norm0;
+    if (verbose > 0) std::printf("=== rate=%g, IT=%d, reduction=%g, %s\n", res->iterations > 0 ? std::pow(norm / norm0, 1.0 / res->iterations) : 0.0,
+                                 res->iterations, norm / norm0, converged ? "converged" : "NOT converged");
     if (status == OPMGPU_OK && !converged) status = OPMGPU_NOT_CONVERGED;
     if (status == OPMGPU_BREAKDOWN) h->err = "breakdown in BiCGSTAB (rho, omega or h below 1e-80)";
+    return status;
+}
+
+// Dune::RestartedGMResSolver::apply on device vectors (newton_use_gmres, ISTLSolver.hpp:257-265):
+// left preconditioned, modified Gram-Schmidt, Givens rotations on the host.  In: d_r = b (x0 = 0).
+// Out: d_x.  One host synchronisation per Arnoldi step (the new Hessenberg column).
+int gmres(opmgpu_handle h, const opmgpu_params* prm, opmgpu_result* res)
+{
+    const double EPSILON = 1e-80;
+    const size_t n = (size_t)h->N * 3;
+    const double red = prm->linear_solver_reduction, w = prm->ilu_relaxation;
+    const int maxit = prm->linear_solver_maxiter, m = std::max(1, prm->linear_solver_restart);
+    int rc;
+    h->history.clear();
+    CK(h->d_gmres_V.ensure((size_t)(m + 1) * n));
+    CK(h->d_gmres_H.ensure((size_t)m + 2));
+    double* V = h->d_gmres_V.p; double* Hd = h->d_gmres_H.p; double* wv = h->d_t.p; double* b = h->d_r.p; double* b2 = h->d_rt.p;
+    std::vector<double> s(m + 1, 0.0), sn(m, 0.0), cs(m, 0.0), H((size_t)(m + 1) * m, 0.0), y(m + 1, 0.0), col(m + 2, 0.0);
+    auto gen_rot = [](double dx, double dy, double& c, double& sv) {
+        const double ndx = std::fabs(dx), ndy = std::fabs(dy);
+        if (ndy < 1e-15) { c = 1.0; sv = 0.0; }
+        else if (ndx < 1e-15) { c = 0.0; sv = 1.0; }
+        else if (ndy > ndx) { const double t = ndx / ndy; c = 1.0 / std::sqrt(1.0 + t * t); sv = c; c *= t; sv *= dx / ndx; sv *= dy / ndy; }
+        else { const double t = ndy / ndx; c = 1.0 / std::sqrt(1.0 + t * t); sv = c; sv *= dy / dx; }
+    };
+    auto app_rot = [](double& dx, double& dy, double c, double sv) { const double t = c * dx + sv * dy; dy = -sv * dx + c * dy; dx = t; };
+    // H slots [lo, lo+cnt) hold rank-local partial sums: reduce them, then fetch [0, upto) to the host
+    auto reduce_slots = [&](int lo, int cnt) -> int {
+        if (h->world > 1) NK(g_nccl.AllReduce(Hd + lo, Hd + lo, (size_t)cnt, ncclDouble, ncclSum, h->comm, h->stream));
+        return 0;
+    };
+    auto fetch = [&](int upto) -> int {
+        CK(cudaMemcpyAsync(col.data(), Hd, sizeof(double) * upto, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(&h->h_flags2[0], h->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        if (h->h_flags2[0]) return sweep_watchdog(h);
+        return 0;
+    };
+    auto precond_norm = [&](double* v0, double& nrm) -> int {          // v0 = W^-1 b, nrm = |v0|
+        if ((rc = apply_precond(h, w, b, v0))) return rc;
+        gmres_dot_kernel<<<kVecBlocks, 256, 0, h->stream>>>(n, v0, v0, Hd, 0, h->ws());
+        h->launches++;
+        if ((rc = reduce_slots(0, 1))) return rc;
+        if ((rc = fetch(1))) return rc;
+        nrm = std::sqrt(col[0]);
+        return 0;
+    };
+    CK(cudaMemsetAsync(h->d_x.p, 0, n * sizeof(double), h->stream));
+    CK(cudaMemcpyAsync(b2, b, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    // b -= A x with x = 0 leaves b as it is
+    double norm = 0.0, norm_0 = 0.0;
+    if ((rc = precond_norm(V, norm_0))) return rc;
+    norm = norm_0;
+    res->norm0 = norm_0;
+    int j = 1, status = OPMGPU_OK, converged = 0;
+    if (norm_0 < EPSILON) { res->converged = 1; res->iterations = 0; res->reduction = 0.0; return OPMGPU_OK; }
+    while (j <= maxit && !converged && status == OPMGPU_OK) {
+        int i = 0;
+        gmres_scale_kernel<<<kVecBlocks, 256, 0, h->stream>>>(n, V, V, 1.0 / norm);
+        h->launches++;
+        s[0] = norm;
+        for (i = 1; i < m + 1; ++i) s[i] = 0.0;
+        for (i = 0; i < m && j <= maxit && !converged; ++i, ++j) {
+            double* vi = V + (size_t)i * n;
+            double* vn = V + (size_t)(i + 1) * n;
+            // v[i+1] = A v[i] (the operand needs room for the ghost rows when partitioned), w = W^-1 v[i+1]
+            double* xin = vi;
+            if (h->world > 1) { CK(cudaMemcpyAsync(h->d_tmp.p, vi, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream)); xin = h->d_tmp.p; }
+            if ((rc = spmv_with_dots(h, 0, xin, vn, nullptr))) return rc;
+            if ((rc = apply_precond(h, w, vn, wv))) return rc;
+            // modified Gram-Schmidt: H[k][i] = v[k].w ; w -= H[k][i] v[k]
+            gmres_dot_kernel<<<kVecBlocks, 256, 0, h->stream>>>(n, V, wv, Hd, 0, h->ws());
+            h->launches++;
+            if ((rc = reduce_slots(0, 1))) return rc;
+            for (int k = 0; k <= i; ++k) {
+                gmres_mgs_kernel<<<kVecBlocks, 256, 0, h->stream>>>(n, wv, V + (size_t)k * n, k < i ? V + (size_t)(k + 1) * n : nullptr, Hd, k, h->ws());
+                h->launches++;
+                if ((rc = reduce_slots(k + 1, 1))) return rc;
+            }
+            if ((rc = fetch(i + 2))) return rc;
+            for (int k = 0; k <= i; ++k) H[(size_t)k * m + i] = col[k];
+            const double hn = std::sqrt(col[i + 1]);
+            H[(size_t)(i + 1) * m + i] = hn;
+            if (std::fabs(hn) < EPSILON) { status = OPMGPU_BREAKDOWN; break; }
+            gmres_scale_kernel<<<kVecBlocks, 256, 0, h->stream>>>(n, vn, wv, 1.0 / hn);
+            h->launches++;
+            for (int k = 0; k < i; ++k) app_rot(H[(size_t)k * m + i], H[(size_t)(k + 1) * m + i], cs[k], sn[k]);
+            gen_rot(H[(size_t)i * m + i], H[(size_t)(i + 1) * m + i], cs[i], sn[i]);
+            app_rot(H[(size_t)i * m + i], H[(size_t)(i + 1) * m + i], cs[i], sn[i]);
+            app_rot(s[i], s[i + 1], cs[i], sn[i]);
+            norm = std::fabs(s[i + 1]);
+            h->history.push_back(norm);
+            if (h->rank == 0 && prm->linear_solver_verbosity > 1) std::printf("%5d %15.6e\n", j, norm);
+            if (norm < red * norm_0) converged = 1;
+        }
+        if (status != OPMGPU_OK) break;
+        // update: back substitution, x += sum y[a] v[a]
+        CK(cudaMemsetAsync(wv, 0, n * sizeof(double), h->stream));
+        for (int a = 0; a < m + 1; ++a) y[a] = s[a];
+        for (int a = i - 1; a >= 0; --a) {
+            double rhs = s[a];
+            for (int c = a + 1; c < i; ++c) rhs -= H[(size_t)a * m + c] * y[c];
+            y[a] = rhs / H[(size_t)a * m + a];
+            gmres_axpy_kernel<<<kVecBlocks, 256, 0, h->stream>>>(n, wv, y[a], V + (size_t)a * n);
+            h->launches++;
+        }
+        gmres_add_kernel<<<kVecBlocks, 256, 0, h->stream>>>(n, h->d_x.p, wv);
+        h->launches++;
+        if (!converged && j <= maxit) {
+            CK(cudaMemcpyAsync(b, b2, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+            const double* xin = h->d_x.p;
+            if (h->world > 1) {
+                CK(cudaMemcpyAsync(h->d_tmp.p, h->d_x.p, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+                if ((rc = halo_exchange(h, h->d_tmp.p))) return rc;
+                xin = h->d_tmp.p;
+            }
+            const int* rowptr = h->world > 1 ? h->d_rowptr_full.p : h->d_rowptr.p;
+            const int* colidx = h->world > 1 ? h->d_colidx_full.p : h->d_colidx.p;
+            residual3_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->N, rowptr, colidx, h->d_vals, xin, b);
+            h->launches++;
+            if ((rc = precond_norm(V, norm))) return rc;
+        }
+    }
+    CK(cudaGetLastError());
+    res->iterations = j - 1;
+    res->converged = converged;
+    if (h->rank == 0 && prm->linear_solver_verbosity > 0)
+        std::printf("=== opmgpu RestartedGMResSolver (ILU0, restart %d): IT=%d, reduction=%g, %s\n", m, j - 1, norm / norm_0, converged ? "converged" : "NOT converged");
+    res->half_steps = (int)h->history.size();
+    res->reduction = norm / norm_0;
+    if (status == OPMGPU_OK && !converged) status = OPMGPU_NOT_CONVERGED;
+    if (status == OPMGPU_BREAKDOWN) h->err = "breakdown in GMRes (new Krylov vector below 1e-80)";
     return status;
 }
 
@@ -1139,7 +1288,7 @@ int solve_resident(opmgpu_handle h, const opmgpu_params* prm, opmgpu_result* res
     if (h->pattern_check.valid() && h->pattern_check.wait_for(std::chrono::seconds(0)) == std::future_status::ready &&
         !h->pattern_check.get()) return kPatternChanged;
     if (rc) { res->bad_row = badrow; return rc; }
-    rc = bicgstab(h, prm, res);
+    rc = prm->newton_use_gmres ? gmres(h, prm, res) : bicgstab(h, prm, res);
     cudaEventRecord(h->ev[2], h->stream);
     cudaEventSynchronize(h->ev[2]);
     res->ms_factor = ev_ms(h->ev[0], h->ev[1]);
@@ -1207,6 +1356,8 @@ void opmgpu_default_params(opmgpu_params* p)
     p->linear_solver_ignoreconvergencefailure = 0;
     p->require_full_sparsity_pattern = 0;
     p->max_half_steps = -1;
+    p->newton_use_gmres = 0;
+    p->linear_solver_restart = 40;
 }
 
 const char* opmgpu_last_error(opmgpu_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -1750,6 +1901,25 @@ int opmgpu_create_distributed(int device, int rank, int world, const void* nccl_
         g_create_error = std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r);
         opmgpu_destroy(h);
         return OPMGPU_NCCL_ERROR;
+    }
+    // NCCL sets its channels up lazily, on the first collective / point-to-point call that uses them
+    // (seconds on an 8-GPU box): do that once here, not inside the first pattern analysis or solve.
+    {
+        DevArr<double> warm;
+        bool ok = warm.ensure((size_t)2 * world) == cudaSuccess && cudaMemsetAsync(warm.p, 0, sizeof(double) * 2 * world, h->stream) == cudaSuccess;
+        ok = ok && g_nccl.AllReduce(warm.p, warm.p, 1, ncclDouble, ncclSum, h->comm, h->stream) == ncclSuccess;
+        if (ok && world > 1) {
+            ok = g_nccl.GroupStart() == ncclSuccess;
+            for (int p = 0; p < world && ok; ++p) {
+                if (p == rank) continue;
+                ok = g_nccl.Send(warm.p + p, 1, ncclDouble, p, h->comm, h->stream) == ncclSuccess &&
+                     g_nccl.Recv(warm.p + world + p, 1, ncclDouble, p, h->comm, h->stream) == ncclSuccess;
+            }
+            ok = g_nccl.GroupEnd() == ncclSuccess && ok;
+        }
+        ok = ok && cudaStreamSynchronize(h->stream) == cudaSuccess;
+        warm.release();
+        if (!ok) { g_create_error = "NCCL warm-up (all-reduce + send/recv) failed"; opmgpu_destroy(h); return OPMGPU_NCCL_ERROR; }
     }
     *out = h;
     return OPMGPU_OK;

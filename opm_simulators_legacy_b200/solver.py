@@ -42,9 +42,11 @@ _PARAM_KEYS = {
     "linear_solver_verbosity": ("linear_solver_verbosity", 0, int),
     "linear_solver_ignoreconvergencefailure": ("linear_solver_ignoreconvergencefailure", False, bool),
     "require_full_sparsity_pattern": ("require_full_sparsity_pattern", False, bool),
+    "newton_use_gmres": ("newton_use_gmres", False, bool),
+    "linear_solver_restart": ("linear_solver_restart", 40, int),
 }
 # keys of FlowLinearSolverParameters this solver accepts only at their default value
-_UNSUPPORTED = {"newton_use_gmres": False, "linear_solver_use_amg": False, "ilu_fillin_level": 0,
+_UNSUPPORTED = {"linear_solver_use_amg": False, "ilu_fillin_level": 0,
                 "ilu_milu": "ILU", "ilu_redblack": False}
 
 

@@ -358,6 +358,162 @@ done:
     free(p); free(v); free(t); free(y); free(rt);
 }
 
+/* ------------------------------------------------------------------------------------
+ * f3  Dune::RestartedGMResSolver::apply  (call site opm/autodiff/ISTLSolver.hpp:257-265,
+ * selected by newton_use_gmres, restart = linear_solver_restart), dune-istl 2.6: LEFT
+ * preconditioned (the Krylov space is built on W^-1 A, the defect that is measured is the
+ * preconditioned one), modified Gram-Schmidt, Givens rotations, x updated at the end of
+ * every cycle.  Like the BiCGStab above this is a restatement of an external routine
+ * ("parity unpinned" at the dune level; pinned by scipy and known-answer tests).
+ * b is overwritten (defect of the last restart), x0 as given.
+ * ---------------------------------------------------------------------------------- */
+static void gen_rotation(double dx, double dy, double* cs, double* sn)
+{
+    const double ndx = fabs(dx), ndy = fabs(dy);
+    if (ndy < 1e-15) { *cs = 1.0; *sn = 0.0; }
+    else if (ndx < 1e-15) { *cs = 0.0; *sn = 1.0; }
+    else if (ndy > ndx) {
+        const double temp = ndx / ndy;
+        *cs = 1.0 / sqrt(1.0 + temp * temp);
+        *sn = *cs;
+        *cs *= temp;
+        *sn *= dx / ndx;
+        *sn *= dy / ndy;
+    } else {
+        const double temp = ndy / ndx;
+        *cs = 1.0 / sqrt(1.0 + temp * temp);
+        *sn = *cs;
+        *sn *= dy / dx;
+    }
+}
+static void apply_rotation(double* dx, double* dy, double cs, double sn)
+{
+    const double temp = cs * (*dx) + sn * (*dy);
+    *dy = -sn * (*dx) + cs * (*dy);
+    *dx = temp;
+}
+/* b -= A x  (MatrixAdapter::applyscaleadd(-1,x,b) -> BCRSMatrix::usmv: per block y -= a*x) */
+static void residual_update(int N, const int* rowptr, const int* colidx, const double* vals,
+                            const double* x, double* b)
+{
+    for (int i = 0; i < N; ++i) {
+        double r0 = b[(size_t)i * BS], r1 = b[(size_t)i * BS + 1], r2 = b[(size_t)i * BS + 2];
+        for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+            const double* a = vals + (size_t)k * BB;
+            const double* xj = x + (size_t)colidx[k] * BS;
+            r0 = fma(-a[0], xj[0], r0); r0 = fma(-a[1], xj[1], r0); r0 = fma(-a[2], xj[2], r0);
+            r1 = fma(-a[3], xj[0], r1); r1 = fma(-a[4], xj[1], r1); r1 = fma(-a[5], xj[2], r1);
+            r2 = fma(-a[6], xj[0], r2); r2 = fma(-a[7], xj[1], r2); r2 = fma(-a[8], xj[2], r2);
+        }
+        b[(size_t)i * BS] = r0; b[(size_t)i * BS + 1] = r1; b[(size_t)i * BS + 2] = r2;
+    }
+}
+
+void oracle_gmres3(int N, const int* rowptr, const int* colidx, const double* vals,
+                   const double* lu, double wrelax, double* b, double* x,
+                   double reduction, int maxiter, int restart,
+                   double* history, int history_cap, oracle_result* res)
+{
+    const double EPSILON = 1e-80;
+    const size_t n = (size_t)N * BS;
+    const int m = restart;
+    double* s = (double*)calloc((size_t)m + 1, sizeof(double));
+    double* sn = (double*)calloc((size_t)m, sizeof(double));
+    double* cs = (double*)calloc((size_t)m, sizeof(double));
+    double* H = (double*)calloc((size_t)(m + 1) * m, sizeof(double));      /* H[k][i] = H[k*m + i] */
+    double* V = (double*)calloc((size_t)(m + 1) * (n ? n : 1), sizeof(double));
+    double* w = (double*)calloc(n ? n : 1, sizeof(double));
+    double* b2 = (double*)malloc(sizeof(double) * (n ? n : 1));
+    double* yv = (double*)calloc((size_t)m + 1, sizeof(double));
+    double norm, norm_0;
+    int j = 1, nh = 0;
+
+    memset(res, 0, sizeof *res);
+    memcpy(b2, b, sizeof(double) * n);
+    residual_update(N, rowptr, colidx, vals, x, b);               /* b -= A x */
+    precond(N, rowptr, colidx, lu, wrelax, b, V);                 /* v[0] = W^-1 b */
+    norm_0 = vnorm(N, V);
+    norm = norm_0;
+    res->norm0 = norm_0;
+    if (norm_0 < EPSILON) { res->converged = 1; res->iterations = 0; goto done; }
+
+    while (j <= maxiter && !res->converged) {
+        int i = 0;
+        const double inv = 1.0 / norm;
+        for (size_t q = 0; q < n; ++q) V[q] *= inv;               /* v[0] *= 1/norm */
+        s[0] = norm;
+        for (i = 1; i < m + 1; ++i) s[i] = 0.0;
+        for (i = 0; i < m && j <= maxiter && !res->converged; ++i, ++j) {
+            double* vi = V + (size_t)i * n;
+            double* vn = V + (size_t)(i + 1) * n;
+            oracle_spmv3(N, rowptr, colidx, vals, vi, vn);        /* _A.apply(v[i], v[i+1]) */
+            precond(N, rowptr, colidx, lu, wrelax, vn, w);        /* _W.apply(w, v[i+1]) */
+            for (int k = 0; k < i + 1; ++k) {
+                const double* vk = V + (size_t)k * n;
+                const double hki = vdot(N, vk, w);
+                H[(size_t)k * m + i] = hki;
+                for (size_t q = 0; q < n; ++q) w[q] = fma(-hki, vk[q], w[q]);     /* w.axpy(-H[k][i], v[k]) */
+            }
+            const double hn = vnorm(N, w);
+            H[(size_t)(i + 1) * m + i] = hn;
+            if (fabs(hn) < EPSILON) { res->status = 3; goto finish; }             /* breakdown */
+            const double hinv = 1.0 / hn;
+            for (size_t q = 0; q < n; ++q) vn[q] = w[q] * hinv;                   /* v[i+1] = w; v[i+1] *= 1/H */
+            for (int k = 0; k < i; ++k)
+                apply_rotation(&H[(size_t)k * m + i], &H[(size_t)(k + 1) * m + i], cs[k], sn[k]);
+            gen_rotation(H[(size_t)i * m + i], H[(size_t)(i + 1) * m + i], &cs[i], &sn[i]);
+            apply_rotation(&H[(size_t)i * m + i], &H[(size_t)(i + 1) * m + i], cs[i], sn[i]);
+            apply_rotation(&s[i], &s[i + 1], cs[i], sn[i]);
+            norm = fabs(s[i + 1]);
+            if (history && nh < history_cap) history[nh] = norm;
+            ++nh;
+            if (norm < reduction * norm_0) res->converged = 1;
+        }
+        /* update(w, i, H, s, v): back substitution, x += sum y[a] v[a] accumulated in w */
+        memset(w, 0, sizeof(double) * n);
+        for (int a = 0; a < m + 1; ++a) yv[a] = s[a];
+        for (int a = i - 1; a >= 0; --a) {
+            double rhs = s[a];
+            for (int c = a + 1; c < i; ++c) rhs -= H[(size_t)a * m + c] * yv[c];
+            yv[a] = rhs / H[(size_t)a * m + a];
+            const double* va = V + (size_t)a * n;
+            for (size_t q = 0; q < n; ++q) w[q] = fma(yv[a], va[q], w[q]);
+        }
+        for (size_t q = 0; q < n; ++q) x[q] += w[q];
+        if (!res->converged && j <= maxiter) {
+            memcpy(b, b2, sizeof(double) * n);
+            residual_update(N, rowptr, colidx, vals, x, b);
+            precond(N, rowptr, colidx, lu, wrelax, b, V);
+            norm = vnorm(N, V);
+        }
+    }
+finish:
+    res->iterations = j - 1;
+    res->reduction = norm / norm_0;
+    if (!res->converged && res->status == 0) res->status = 1;
+done:
+    res->half_steps = nh;
+    free(s); free(sn); free(cs); free(H); free(V); free(w); free(b2); free(yv);
+}
+
+/* factor + GMRES on a BCRS system (vals untouched), x0 = 0 */
+void oracle_solve_gmres_bcrs3(int N, const int* rowptr, const int* colidx, const double* vals,
+                              const double* rhs_cellmajor, double* x_cellmajor,
+                              double reduction, int maxiter, double relax, int restart,
+                              oracle_result* res)
+{
+    const size_t nnzb = (size_t)rowptr[N];
+    double* lu = (double*)malloc(sizeof(double) * (nnzb ? nnzb : 1) * BB);
+    double* b = (double*)malloc(sizeof(double) * ((size_t)N * BS + 1));
+    memcpy(lu, vals, sizeof(double) * nnzb * BB);
+    memcpy(b, rhs_cellmajor, sizeof(double) * (size_t)N * BS);
+    memset(x_cellmajor, 0, sizeof(double) * (size_t)N * BS);
+    const int bad = oracle_ilu0_factor3(N, rowptr, colidx, lu);
+    if (bad) { memset(res, 0, sizeof *res); res->status = 2; res->bad_row = bad - 1; }
+    else oracle_gmres3(N, rowptr, colidx, vals, lu, relax, b, x_cellmajor, reduction, maxiter, restart, NULL, 0, res);
+    free(lu); free(b);
+}
+
 void oracle_solve_bcrs3(int N, const int* rowptr, const int* colidx, const double* vals,
                         const double* rhs_cellmajor, double* x_cellmajor,
                         double reduction, int maxiter, double relax, int max_half_steps,

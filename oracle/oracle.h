@@ -99,6 +99,18 @@ void oracle_solve_bcrs3(int N, const int* rowptr, const int* colidx, const doubl
                         double reduction, int maxiter, double relax, int max_half_steps,
                         oracle_result* res);
 
+/* Dune::RestartedGMResSolver::apply (dune-istl 2.6: left preconditioned, modified Gram-Schmidt,
+ * Givens rotations; ISTLSolver.hpp:257-265 with restart = linear_solver_restart).  iterations =
+ * Arnoldi steps; history receives the preconditioned defect norm after every step. */
+void oracle_gmres3(int N, const int* rowptr, const int* colidx, const double* vals,
+                   const double* lu, double w, double* b, double* x,
+                   double reduction, int maxiter, int restart,
+                   double* history, int history_cap, oracle_result* res);
+void oracle_solve_gmres_bcrs3(int N, const int* rowptr, const int* colidx, const double* vals,
+                              const double* rhs_cellmajor, double* x_cellmajor,
+                              double reduction, int maxiter, double relax, int restart,
+                              oracle_result* res);
+
 void oracle_free(void* p);
 
 #ifdef __cplusplus

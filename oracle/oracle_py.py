@@ -68,6 +68,12 @@ def lib():
                                                       C.c_double, C.c_int, C.c_double, C.c_int,
                                                       C.POINTER(OracleResult)]
         _lib.oracle_solve_from_csc_blocks.restype = None
+        _lib.oracle_gmres3.argtypes = [C.c_int, ip, ip, dp, dp, C.c_double, dp, dp, C.c_double, C.c_int, C.c_int,
+                                       dp, C.c_int, C.POINTER(OracleResult)]
+        _lib.oracle_gmres3.restype = None
+        _lib.oracle_solve_gmres_bcrs3.argtypes = [C.c_int, ip, ip, dp, dp, dp, C.c_double, C.c_int, C.c_double, C.c_int,
+                                                  C.POINTER(OracleResult)]
+        _lib.oracle_solve_gmres_bcrs3.restype = None
         _lib.oracle_free.argtypes = [C.c_void_p]
         _lib.oracle_free.restype = None
     return _lib
@@ -163,6 +169,34 @@ def bicgstab(rowptr, colidx, vals, lu, w, rhs, reduction=1e-2, maxiter=150, max_
                            x.ctypes.data_as(C.POINTER(C.c_double)), float(reduction), int(maxiter),
                            int(max_half_steps), hist.ctypes.data_as(C.POINTER(C.c_double)),
                            int(history_cap), C.byref(res))
+    return x.reshape(N, 3), res.as_dict(), hist[:min(history_cap, res.half_steps)]
+
+
+def solve_gmres_bcrs(rowptr, colidx, vals, rhs, reduction=1e-2, maxiter=150, relax=0.9, restart=40):
+    """ILU0 + Dune::RestartedGMResSolver (newton_use_gmres): x, result dict."""
+    rowptr, prp = _i(rowptr); colidx, pci = _i(colidx); vals, pv = _d(vals); rhs, pr = _d(rhs)
+    N = rowptr.size - 1
+    x = np.zeros(N * 3)
+    res = OracleResult()
+    lib().oracle_solve_gmres_bcrs3(N, prp, pci, pv, pr, x.ctypes.data_as(C.POINTER(C.c_double)),
+                                   float(reduction), int(maxiter), float(relax), int(restart), C.byref(res))
+    return x.reshape(N, 3), res.as_dict()
+
+
+def gmres(rowptr, colidx, vals, lu, w, rhs, reduction=1e-2, maxiter=150, restart=40, history_cap=0):
+    """lu=None -> identity preconditioner.  Returns x, result dict, preconditioned defect history."""
+    rowptr, prp = _i(rowptr); colidx, pci = _i(colidx); vals, pv = _d(vals)
+    N = rowptr.size - 1
+    b = np.array(rhs, dtype=np.float64, copy=True).reshape(-1)
+    x = np.zeros(N * 3)
+    hist = np.zeros(max(history_cap, 1))
+    plu = None
+    if lu is not None:
+        lu, plu = _d(lu)
+    res = OracleResult()
+    lib().oracle_gmres3(N, prp, pci, pv, plu, float(w), b.ctypes.data_as(C.POINTER(C.c_double)),
+                        x.ctypes.data_as(C.POINTER(C.c_double)), float(reduction), int(maxiter), int(restart),
+                        hist.ctypes.data_as(C.POINTER(C.c_double)), int(history_cap), C.byref(res))
     return x.reshape(N, 3), res.as_dict(), hist[:min(history_cap, res.half_steps)]
 
 

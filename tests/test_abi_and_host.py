@@ -33,8 +33,10 @@ def test_default_params_are_the_reference_defaults():
     assert p.ilu_relaxation == 0.9 and p.linear_solver_ignoreconvergencefailure == 0
     q = make_params({"linear_solver_reduction": "1e-3", "linear_solver_maxiter": 50, "unrelated_key": 1})
     assert q.linear_solver_reduction == 1e-3 and q.linear_solver_maxiter == 50
+    g = make_params({"newton_use_gmres": "true", "linear_solver_restart": 25})
+    assert g.newton_use_gmres == 1 and g.linear_solver_restart == 25 and p.newton_use_gmres == 0 and p.linear_solver_restart == 40
     with pytest.raises(ValueError):
-        make_params({"newton_use_gmres": True})
+        make_params({"linear_solver_use_amg": True})
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

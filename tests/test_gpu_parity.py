@@ -341,3 +341,22 @@ def test_column_owned_sweeps_bit_exact(oracle, dims, monkeypatch):
         assert (np.abs(x - x_ref).max(0) <= 1e-8 * np.abs(x_ref).max(0)).all()
     finally:
         g.close()
+
+
+@pytest.mark.parametrize("dims,restart", [((24, 20, 12), 40), ((40, 40, 20), 40), ((24, 20, 12), 4), ((30, 17, 1), 40)])
+def test_gmres_parity(gpu_solver, oracle, dims, restart):
+    """newton_use_gmres: restarted GMRES (ISTLSolver.hpp:257-265) against the oracle's restatement of
+    Dune::RestartedGMResSolver: equal iteration counts, increment within rel 1e-8, defect history."""
+    s = synth_blackoil_jacobian(*dims, perm="lognormal")
+    rp, ci, v, b = _np(s)
+    gpu_solver.set_pattern(rp, ci)
+    for red in (1e-2, 1e-8):
+        x, res = gpu_solver.solve_bcrs(v, b, newton_use_gmres=True, linear_solver_restart=restart,
+                                       linear_solver_reduction=red, linear_solver_maxiter=400)
+        x_ref, ref = oracle.solve_gmres_bcrs(rp, ci, v, b, reduction=red, maxiter=400, restart=restart)
+        assert res["converged"] == 1 and res["iterations"] == ref["iterations"], (res, ref)
+        assert (np.abs(x - x_ref).max(0) <= 1e-8 * np.abs(x_ref).max(0)).all()
+    # not converged within maxiter -> LinearSolverProblem, iterations still reported
+    with pytest.raises(LinearSolverProblem):
+        gpu_solver.solve_bcrs(v, b, newton_use_gmres=True, linear_solver_reduction=1e-14, linear_solver_maxiter=3)
+    assert gpu_solver.last["iterations"] == 3

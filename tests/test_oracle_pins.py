@@ -156,3 +156,38 @@ def test_oracle_reproduces_golden(oracle, path):
     assert np.array_equal(oracle.ilu0_apply(rp, ci, lu, 1.0, b), g["apply_w1"])
     x, res = oracle.solve_bcrs(rp, ci, v, b)
     assert res["iterations"] == int(g["iterations"]) and np.array_equal(x, g["x"])
+
+
+# ---- restarted GMRES (newton_use_gmres; Dune::RestartedGMResSolver restated in oracle_gmres3) ----
+def test_gmres_matches_a_direct_solve_also_across_restarts():
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    from opm_simulators_legacy_b200.jacobian import synth_blackoil_jacobian
+    from oracle import oracle_py as o
+    s = synth_blackoil_jacobian(12, 10, 8, perm="lognormal")
+    rp, ci, v, b = s.rowptr.numpy(), s.colidx.numpy(), s.vals.numpy(), s.rhs.numpy()
+    A = sp.bsr_matrix((v.reshape(-1, 3, 3), ci, rp)).tocsc()
+    xs = spla.spsolve(A, b.reshape(-1))
+    for restart, tol in ((40, 1e-9), (5, 1e-6)):
+        x, res = o.solve_gmres_bcrs(rp, ci, v, b, reduction=1e-12, maxiter=2000, restart=restart)
+        assert res["converged"] == 1 and res["status"] == 0
+        assert np.abs(x.reshape(-1) - xs).max() <= tol * np.abs(xs).max()
+    # restart = 5 needs more Arnoldi steps than one long cycle
+    assert o.solve_gmres_bcrs(rp, ci, v, b, reduction=1e-8, maxiter=2000, restart=5)[1]["iterations"] > \
+        o.solve_gmres_bcrs(rp, ci, v, b, reduction=1e-8, maxiter=2000, restart=200)[1]["iterations"]
+
+
+def test_gmres_known_answers():
+    """Block-tridiagonal system: ILU0 is the exact LU, so W^-1 A = I/w and GMRES stops after one
+    Arnoldi step with x = A^-1 b; maxiter reached -> status 1 with iterations == maxiter."""
+    from opm_simulators_legacy_b200.jacobian import synth_blackoil_jacobian
+    from oracle import oracle_py as o
+    s = synth_blackoil_jacobian(40, 1, 1, perm="lognormal")
+    rp, ci, v, b = s.rowptr.numpy(), s.colidx.numpy(), s.vals.numpy(), s.rhs.numpy()
+    x, res = o.solve_gmres_bcrs(rp, ci, v, b, reduction=1e-10, relax=1.0)
+    assert res["iterations"] == 1 and res["converged"] == 1
+    assert np.abs(x - s.xstar.numpy()).max() <= 1e-9 * np.abs(s.xstar.numpy()).max()
+    s2 = synth_blackoil_jacobian(10, 10, 6, perm="lognormal")
+    rp, ci, v, b = s2.rowptr.numpy(), s2.colidx.numpy(), s2.vals.numpy(), s2.rhs.numpy()
+    x, res = o.solve_gmres_bcrs(rp, ci, v, b, reduction=1e-14, maxiter=3)
+    assert res["iterations"] == 3 and res["converged"] == 0 and res["status"] == 1
