@@ -260,22 +260,54 @@ RecLayout rec_layout(int n, int ntail, int npushx, bool upper, bool has_lists)
 void build_pipe_program(int N, const int* rowptr, const int* colidx, const std::vector<int>& diag,
                         const std::vector<int>& level, int nlevels, const std::vector<int>& owner,
                         const std::vector<int>& tile,
-                        int P, bool lower, const std::vector<int>* upos_of_row, PipeProgram& pg, int cs = 1)
+                        int P, bool lower, const std::vector<int>* upos_of_row, PipeProgram& pg, int cs = 1,
+                        std::vector<unsigned>* ri4_index = nullptr)
 {
+    // ri4_index (lower program built beside the upper one): where each row's "position in the upper
+    // sweep's order" lives in ibuf (int index), to be filled in once the upper program is known
+    if (ri4_index) ri4_index->assign(N, 0);
     pg = PipeProgram();
     pg.P = P;
     pg.cluster_size = cs;
+    const bool timing__ = std::getenv("OPMGPU_DEBUG2") != nullptr;
+    auto t_last__ = std::chrono::steady_clock::now();
+    auto tick__ = [&](const char* what) {
+        if (!timing__) return;
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[opmgpu]   pipe %s: %-28s %8.1f ms\n", lower ? "L" : "U", what, std::chrono::duration<double, std::milli>(now - t_last__).count());
+        t_last__ = now;
+    };
     // a dependency on another CTA of the same cluster travels through distributed shared memory
     auto same_cluster = [&](int ca_, int cb_) { return cs > 1 && ca_ != cb_ && ca_ / cs == cb_ / cs; };
     pg.nlevels = nlevels;
     const bool upper = !lower;
+    // rows by (CTA, tile in walking order, level, row): one 64-bit key per row, so the sort runs
+    // over a contiguous array (tile ids ascend with the L wavefront, the upper sweep walks them backwards)
     std::vector<int> order(N);
-    std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-        if (owner[a] != owner[b]) return owner[a] < owner[b];
-        if (tile[a] != tile[b]) return lower ? tile[a] < tile[b] : tile[a] > tile[b];      // tile ids ascend with the L wavefront
-        return level[a] < level[b];
-    });
+    {
+        int max_tile = 0, max_level = 0, max_owner = 0;
+        for (int r = 0; r < N; ++r) { max_tile = std::max(max_tile, tile[r]); max_level = std::max(max_level, level[r]); max_owner = std::max(max_owner, owner[r]); }
+        auto bits = [](long long v) { int b = 1; while ((1LL << b) <= v) ++b; return b; };
+        const int br = bits(N), bl = bits(max_level), bt = bits(max_tile), bo = bits(max_owner);
+        if (br + bl + bt + bo <= 64) {
+            std::vector<unsigned long long> key(N);
+            for (int r = 0; r < N; ++r) {
+                const unsigned long long t = lower ? (unsigned long long)tile[r] : (unsigned long long)(max_tile - tile[r]);
+                key[r] = ((((unsigned long long)owner[r] << bt | t) << bl | (unsigned long long)level[r]) << br) | (unsigned long long)r;
+            }
+            std::sort(key.begin(), key.end());
+            const unsigned long long mask = (1ULL << br) - 1;
+            for (int q = 0; q < N; ++q) order[q] = (int)(key[q] & mask);
+        } else {
+            std::iota(order.begin(), order.end(), 0);
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+                if (owner[a] != owner[b]) return owner[a] < owner[b];
+                if (tile[a] != tile[b]) return lower ? tile[a] < tile[b] : tile[a] > tile[b];
+                return level[a] < level[b];
+            });
+        }
+    }
+    tick__("sort");
     std::vector<int> nblk(N, 0), next(N, 0), npush(N, 0);
     auto for_deps = [&](int r, auto&& fn) {
         if (lower) { for (int k = rowptr[r]; k < diag[r]; ++k) fn(k); }
@@ -319,6 +351,7 @@ void build_pipe_program(int N, const int* rowptr, const int* colidx, const std::
         }
         pg.cta_step_ptr[P] = (int)steps.size();
     }
+    tick__("counts + steps");
     // push slots: ordinals in consumption order per CTA
     pg.cta_ext_base.assign(P + 1, 0);
     std::vector<int> push_ptr(N + 1, 0);
@@ -349,6 +382,7 @@ void build_pipe_program(int N, const int* rowptr, const int* colidx, const std::
         pg.total_ext = base;
         if (base >= (1LL << 30) || pg.max_cx > kMaxCxEntries) return;
     }
+    tick__("push slots");
     // program-order positions (rhs segments are fetched by bulk copies: even row counts)
     pg.step_rhs_row.resize(steps.size());
     pg.step_rhs_bytes.resize(steps.size());
@@ -383,10 +417,12 @@ void build_pipe_program(int N, const int* rowptr, const int* colidx, const std::
             const int j = colidx[k];
             if (tile[j] == tile[r] && qlocal[j] + kWindowRows < step_end_q[r]) write_global[j] = 1;
         });
+    tick__("positions + write_global");
     // record sizes
-    size_t total_bytes = 0;
+    size_t total_bytes = 0, total_ibytes = 0;
     pg.step_off16.resize(steps.size());
     pg.step_bytes.resize(steps.size());
+    pg.step_ioff16.resize(steps.size()); pg.step_ilen.resize(steps.size()); pg.step_roff.resize(steps.size());
     std::vector<RecLayout> lay(steps.size());
     for (size_t sidx = 0; sidx < steps.size(); ++sidx) {
         int rows = steps[sidx].q1 - steps[sidx].q0, tail = 0, pushx = 0;
@@ -396,29 +432,37 @@ void build_pipe_program(int N, const int* rowptr, const int* colidx, const std::
         pg.step_bytes[sidx] = (unsigned)lay[sidx].total;
         total_bytes += lay[sidx].total;
         pg.max_step_bytes = std::max(pg.max_step_bytes, (int)lay[sidx].total);
+        // compact stream: header | [rowints, tail_vals) of the record
+        pg.step_ioff16[sidx] = (unsigned)(total_ibytes / 16);
+        pg.step_ilen[sidx] = (unsigned)(32 + (lay[sidx].tail_vals - lay[sidx].rowints));
+        pg.step_roff[sidx] = (unsigned)lay[sidx].rowints;
+        total_ibytes += pg.step_ilen[sidx];
     }
-    if (total_bytes / 16 >= (1ull << 32) || total_bytes / 8 >= (1ull << 32)) return;
-    pg.buf.assign(total_bytes + 16, 0);
+    if (total_bytes / 16 >= (1ull << 32) || total_bytes / 8 >= (1ull << 32) || total_ibytes / 16 >= (1ull << 32)) return;
+    pg.total_bytes = total_bytes + 16;
+    pg.ibuf.assign(total_ibytes + 16, 0);
     pg.val_src.reserve((size_t)rowptr[N] / 2 + N); pg.val_dst8.reserve((size_t)rowptr[N] / 2 + N); pg.val_stride.reserve((size_t)rowptr[N] / 2 + N);
     bool any_slow = false, any_global = false;
+    tick__("sizes + buffer");
     // emit
     for (int c = 0; c < P; ++c) {
         long long e = 0;
         int cx = 0;
         for (int sidx = pg.cta_step_ptr[c]; sidx < pg.cta_step_ptr[c + 1]; ++sidx) {
             const size_t rec_off = (size_t)pg.step_off16[sidx] * 16;
-            unsigned char* rec = pg.buf.data() + rec_off;
+            unsigned char* irec = pg.ibuf.data() + (size_t)pg.step_ioff16[sidx] * 16;     // header | integer region
             const long long e_before = e;
             const int cta_q0 = steps[pg.cta_step_ptr[c]].q0;
             const RecLayout& L = lay[sidx];
             const int n = steps[sidx].q1 - steps[sidx].q0;
             const bool has_lists = L.tail_dep > L.lists;      // the cumulative arrays are present
-            int* hdr = (int*)rec;
-            int* rowints = (int*)(rec + L.rowints);
-            int* tail_end = (int*)(rec + L.tail_end);
-            int* xpush_end = (int*)(rec + L.xpush_end);
-            int* tail_dep = (int*)(rec + L.tail_dep);
-            int* xpush_slot = (int*)(rec + L.xpush_slot);
+            int* hdr = (int*)irec;
+            unsigned char* ireg = irec + 32 - L.rowints;          // record offsets >= L.rowints map into the region
+            int* rowints = (int*)(ireg + L.rowints);
+            int* tail_end = (int*)(ireg + L.tail_end);
+            int* xpush_end = (int*)(ireg + L.xpush_end);
+            int* tail_dep = (int*)(ireg + L.tail_dep);
+            int* xpush_slot = (int*)(ireg + L.xpush_slot);
             int nt = 0, npx = 0, rr = 0;
             for (int q = steps[sidx].q0; q < steps[sidx].q1; ++q, ++rr) {
                 const int r = order[q];
@@ -458,6 +502,7 @@ void build_pipe_program(int N, const int* rowptr, const int* colidx, const std::
                 any_slow |= slow; any_global |= write_global[r] != 0;
                 ri[0] = r | (write_global[r] ? kRowWriteGlobal : 0) | (slow ? kRowSlow : 0);
                 ri[4] = (lower && upos_of_row) ? (*upos_of_row)[r] : 0;
+                if (ri4_index) (*ri4_index)[r] = (unsigned)((ri + 4) - (int*)pg.ibuf.data());
                 if (upper) {
                     pg.val_src.push_back(diag[r]);
                     pg.val_dst8.push_back((unsigned)((rec_off + L.dinv) / 8 + (size_t)(3 * rr) * 3));
@@ -469,6 +514,7 @@ void build_pipe_program(int N, const int* rowptr, const int* colidx, const std::
             hdr[7] = has_lists ? 1 : 0;
         }
     }
+    tick__("emit");
     pg.lean = !any_slow && !any_global && pg.max_step_rows <= kLeanStepRows;
     pg.valid = true;
 }
@@ -484,12 +530,27 @@ void build_factor_pipe_program(int N, const int* rowptr, const int* colidx, cons
     pg = FactorPipeProgram();
     pg.P = P;
     std::vector<int> order(N);
-    std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-        if (owner[a] != owner[b]) return owner[a] < owner[b];
-        if (tile[a] != tile[b]) return tile[a] < tile[b];
-        return level[a] < level[b];
-    });
+    {
+        int max_tile = 0, max_level = 0, max_owner = 0;
+        for (int r = 0; r < N; ++r) { max_tile = std::max(max_tile, tile[r]); max_level = std::max(max_level, level[r]); max_owner = std::max(max_owner, owner[r]); }
+        auto bits = [](long long v) { int b = 1; while ((1LL << b) <= v) ++b; return b; };
+        const int br = bits(N), bl = bits(max_level), bt = bits(max_tile), bo = bits(max_owner);
+        if (br + bl + bt + bo <= 64) {
+            std::vector<unsigned long long> key(N);
+            for (int r = 0; r < N; ++r)
+                key[r] = ((((unsigned long long)owner[r] << bt | (unsigned long long)tile[r]) << bl | (unsigned long long)level[r]) << br) | (unsigned long long)r;
+            std::sort(key.begin(), key.end());
+            const unsigned long long mask = (1ULL << br) - 1;
+            for (int q = 0; q < N; ++q) order[q] = (int)(key[q] & mask);
+        } else {
+            std::iota(order.begin(), order.end(), 0);
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+                if (owner[a] != owner[b]) return owner[a] < owner[b];
+                if (tile[a] != tile[b]) return tile[a] < tile[b];
+                return level[a] < level[b];
+            });
+        }
+    }
     // every row simple?  slot of A_ji for every lower block (i,j), -1 when absent
     std::vector<int> ji_slot(rowptr[N], -1), next(N, 0), npush(N, 0);
     for (int r = 0; r < N; ++r) {
@@ -582,7 +643,18 @@ void build_factor_pipe_program(int N, const int* rowptr, const int* colidx, cons
         pg.max_step_rows = std::max(pg.max_step_rows, n);
     }
     if (total_bytes / 8 >= (1ull << 32)) return;
-    pg.buf.assign(total_bytes + 16, 0);
+    pg.total_bytes = total_bytes + 16;
+    {
+        size_t total_ibytes = 0;
+        pg.step_ioff16.resize(steps.size()); pg.step_ilen.resize(steps.size()); pg.step_roff.assign(steps.size(), 32u);
+        for (size_t sidx = 0; sidx < steps.size(); ++sidx) {
+            const int n = steps[sidx].q1 - steps[sidx].q0;
+            pg.step_ioff16[sidx] = (unsigned)(total_ibytes / 16);
+            pg.step_ilen[sidx] = (unsigned)(32 + (size_t)n * kFRowInts * 4);
+            total_ibytes += pg.step_ilen[sidx];
+        }
+        pg.ibuf.assign(total_ibytes + 16, 0);
+    }
     pg.val_src.reserve((size_t)rowptr[N]); pg.val_dst8.reserve((size_t)rowptr[N]);
     for (int c = 0; c < P; ++c) {
         long long e = 0;
@@ -590,7 +662,7 @@ void build_factor_pipe_program(int N, const int* rowptr, const int* colidx, cons
         const int cta_q0 = steps[pg.cta_step_ptr[c]].q0;
         for (int sidx = pg.cta_step_ptr[c]; sidx < pg.cta_step_ptr[c + 1]; ++sidx) {
             const size_t rec_off = (size_t)pg.step_off16[sidx] * 16;
-            unsigned char* rec = pg.buf.data() + rec_off;
+            unsigned char* rec = pg.ibuf.data() + (size_t)pg.step_ioff16[sidx] * 16;      // header | rowints
             const int n = steps[sidx].q1 - steps[sidx].q0;
             const long long e_before = e;
             int* hdr = (int*)rec;
@@ -628,6 +700,23 @@ void build_factor_pipe_program(int N, const int* rowptr, const int* colidx, cons
 }
 
 }  // namespace
+
+namespace {
+void materialise(std::vector<unsigned char>& buf, size_t total_bytes, const std::vector<unsigned char>& ibuf,
+                 const std::vector<unsigned>& off16, const std::vector<unsigned>& ioff16,
+                 const std::vector<unsigned>& ilen, const std::vector<unsigned>& roff)
+{
+    buf.assign(total_bytes, 0);
+    for (size_t s = 0; s < off16.size(); ++s) {
+        unsigned char* rec = buf.data() + (size_t)off16[s] * 16;
+        const unsigned char* src = ibuf.data() + (size_t)ioff16[s] * 16;
+        std::copy(src, src + 32, rec);
+        std::copy(src + 32, src + ilen[s], rec + roff[s]);
+    }
+}
+}  // namespace
+void materialise_records(PipeProgram& pg) { materialise(pg.buf, pg.total_bytes, pg.ibuf, pg.step_off16, pg.step_ioff16, pg.step_ilen, pg.step_roff); }
+void materialise_records(FactorPipeProgram& pg) { materialise(pg.buf, pg.total_bytes, pg.ibuf, pg.step_off16, pg.step_ioff16, pg.step_ilen, pg.step_roff); }
 
 void analyse_pattern(int N, const int* rowptr, const int* colidx, int P, PatternAnalysis& out,
                      bool force_simple, const ClusterCaps* caps_in)
@@ -760,15 +849,23 @@ void analyse_pattern(int N, const int* rowptr, const int* colidx, int P, Pattern
             fjob = std::async(std::launch::async, [&, Pl]() {
                 build_factor_pipe_program(N, rowptr, colidx, out.diag, lvlL, owner, tile, Pl, out.pipeF);
             });
+        // the two sweep programs are built side by side; the lower one needs every row's position in
+        // the upper sweep's order, which is patched in afterwards
+        std::vector<unsigned> ri4;
+        std::future<void> ljob = std::async(std::launch::async, [&, Pl, cs]() {
+            build_pipe_program(N, rowptr, colidx, out.diag, lvlL, nL, owner, tile, Pl, true, nullptr, out.pipeL, cs, &ri4);
+        });
         build_pipe_program(N, rowptr, colidx, out.diag, lvlU, nU, owner, tile, Pl, false, nullptr, out.pipeU, cs);
         tick("upper sweep program");
-        if (out.pipeU.valid) {
-            std::vector<int> upos(N, 0);
+        ljob.get();
+        if (out.pipeU.valid && out.pipeL.valid) {
+            int* li = (int*)out.pipeL.ibuf.data();
             for (size_t q = 0; q < out.pipeU.perm_row.size(); ++q)
-                if (out.pipeU.perm_row[q] >= 0) upos[out.pipeU.perm_row[q]] = (int)q;
-            build_pipe_program(N, rowptr, colidx, out.diag, lvlL, nL, owner, tile, Pl, true, &upos, out.pipeL, cs);
-            tick("lower sweep program");
+                if (out.pipeU.perm_row[q] >= 0) li[ri4[out.pipeU.perm_row[q]]] = (int)q;
+        } else {
+            out.pipeL = PipeProgram();
         }
+        tick("lower sweep program (concurrent)");
         if (fjob.valid()) fjob.get();
         tick("factorisation program (concurrent)");
         // clusters are only supported by the lean kernels: otherwise lay everything out again without
@@ -1126,6 +1223,7 @@ extern "C" int opmgpu_debug_host_program_apply(int N, const int* rowptr, const i
     if (!an.pipeL.valid || !an.pipeU.valid) return -2;
     if (info) info[7] = 0;
     for (PipeProgram* pg : {&an.pipeL, &an.pipeU}) {
+        materialise_records(*pg);
         double* base = (double*)pg->buf.data();
         for (size_t b = 0; b < pg->val_src.size(); ++b)
             for (int c = 0; c < 3; ++c)
@@ -1185,6 +1283,7 @@ extern "C" int opmgpu_debug_host_factor_program(int N, const int* rowptr, const 
     if (an.missing_diag_row >= 0) return -1;
     if (!an.pipeF.valid) return -2;
     std::copy(vals, vals + (size_t)rowptr[N] * 9, lu);
+    materialise_records(an.pipeF);
     const int rc = interpret_factor_program(an.pipeF, vals, lu);
     if (rc == -2) return -3;
     if (bad_row) *bad_row = rc;

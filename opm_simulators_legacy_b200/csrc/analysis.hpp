@@ -102,7 +102,16 @@ struct PipeProgram {
     int max_step_bytes = 0, max_step_rows = 0;   // rows padded to even
     long long total_ext = 0;
     long long nperm = 0;                      // length (rows) of vectors in this program's order
-    std::vector<unsigned char> buf;           // all records, CTA after CTA
+    // The records are mostly factor VALUES, which arrive on the device with every factorisation;
+    // the host only produces their integer parts (header, rowints, lists: ~11 % of the bytes) as a
+    // compact stream, which a device kernel spreads into the zero-filled record buffer
+    // (expand_records_kernel).  buf = the full records, only materialised for the host interpreter.
+    std::vector<unsigned char> buf;           // all records, CTA after CTA (materialise_records)
+    std::vector<unsigned char> ibuf;          // per step: header (32 bytes) | integer region of the record
+    std::vector<unsigned> step_ioff16;        // [nsteps] offset of the step in ibuf / 16
+    std::vector<unsigned> step_ilen;          // [nsteps] bytes of the step in ibuf (header included)
+    std::vector<unsigned> step_roff;          // [nsteps] offset of the integer region inside the record
+    size_t total_bytes = 0;                   // size of the record buffer
     std::vector<int> cta_step_ptr;            // [P+1]
     std::vector<unsigned> step_off16;         // [nsteps] record offset / 16
     std::vector<unsigned> step_bytes;         // [nsteps]
@@ -147,7 +156,10 @@ struct FactorPipeProgram {
     int P = 0;
     int max_step_bytes = 0, max_step_rows = 0;
     long long total_ext = 0;
-    std::vector<unsigned char> buf;           // all records, CTA after CTA
+    std::vector<unsigned char> buf;           // all records, CTA after CTA (materialise_records)
+    std::vector<unsigned char> ibuf;          // compact integer parts, as in PipeProgram
+    std::vector<unsigned> step_ioff16, step_ilen, step_roff;
+    size_t total_bytes = 0;
     std::vector<int> cta_step_ptr;            // [P+1]
     std::vector<unsigned> step_off16;         // [nsteps] record offset / 16
     std::vector<unsigned> step_bytes;         // [nsteps]
@@ -181,6 +193,10 @@ void analyse_pattern(int N, const int* rowptr, const int* colidx, int P, Pattern
 
 // SweepProgram `lower` (the flag-synchronised tile factorisation kernel's program) on demand.
 void build_tile_factor_program(const int* rowptr, const int* colidx, PatternAnalysis& an);
+
+// Full record buffer of a program from its compact integer stream (host interpreters / CPU tests).
+void materialise_records(PipeProgram& pg);
+void materialise_records(FactorPipeProgram& pg);
 
 // Sequential interpreter of a pipelined program (debug / CPU tests of the host analysis).
 bool interpret_pipe_program(const PipeProgram& pg, bool upper, const double* rhs_perm, double* work,

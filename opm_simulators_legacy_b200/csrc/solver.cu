@@ -343,13 +343,51 @@ int upload_program(opmgpu_handle h, const SweepProgram& p, ProgramDevMem& d, boo
     return 0;
 }
 
+// integer parts of the step records (compact host stream, analysis.hpp) -> their places in the
+// zero-filled record buffer; one block per step, 16-byte copies
+__global__ void __launch_bounds__(128)
+expand_records_kernel(int nsteps, const uint4* __restrict__ ibuf, const unsigned* __restrict__ ioff16,
+                      const unsigned* __restrict__ ilen, const unsigned* __restrict__ roff,
+                      const unsigned* __restrict__ off16, uint4* __restrict__ buf)
+{
+    for (int s = blockIdx.x; s < nsteps; s += gridDim.x) {
+        const uint4* src = ibuf + ioff16[s];
+        uint4* rec = buf + off16[s];
+        const unsigned n16 = ilen[s] / 16, r16 = roff[s] / 16;
+        for (unsigned q = threadIdx.x; q < n16; q += blockDim.x) rec[q < 2 ? q : r16 + (q - 2)] = src[q];
+    }
+}
+
+int expand_records(opmgpu_handle h, size_t total_bytes, const std::vector<unsigned char>& ibuf, const std::vector<unsigned>& ioff16,
+                   const std::vector<unsigned>& ilen, const std::vector<unsigned>& roff, const unsigned* d_off16,
+                   DevArr<unsigned char>& d_buf)
+{
+    int rc;
+    DevArr<unsigned char> d_ibuf;
+    DevArr<unsigned> d_ioff, d_ilen, d_roff;
+    CK(d_buf.ensure(total_bytes));
+    CK(cudaMemsetAsync(d_buf.p, 0, total_bytes, h->stream));
+    if ((rc = upload(h, d_ibuf, ibuf))) return rc;
+    if ((rc = upload(h, d_ioff, ioff16))) return rc;
+    if ((rc = upload(h, d_ilen, ilen))) return rc;
+    if ((rc = upload(h, d_roff, roff))) return rc;
+    const int nsteps = (int)ioff16.size();
+    if (nsteps > 0) {
+        expand_records_kernel<<<std::min(nsteps, h->sm_count * 16), 128, 0, h->stream>>>(
+            nsteps, (const uint4*)d_ibuf.p, d_ioff.p, d_ilen.p, d_roff.p, d_off16, (uint4*)d_buf.p);
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(h->stream));       // the temporaries go away
+    d_ibuf.release(); d_ioff.release(); d_ilen.release(); d_roff.release();
+    return 0;
+}
+
 int upload_pipe(opmgpu_handle h, const PipeProgram& p, PipeDevMem& d)
 {
     int rc;
-    CK(d.buf.ensure(p.buf.size()));
-    CK(cudaMemcpyAsync(d.buf.p, p.buf.data(), p.buf.size(), cudaMemcpyHostToDevice, h->stream));
     if ((rc = upload(h, d.cta_step_ptr, p.cta_step_ptr))) return rc;
     if ((rc = upload(h, d.step_off16, p.step_off16))) return rc;
+    if ((rc = expand_records(h, p.total_bytes, p.ibuf, p.step_ioff16, p.step_ilen, p.step_roff, d.step_off16.p, d.buf))) return rc;
     if ((rc = upload(h, d.step_bytes, p.step_bytes))) return rc;
     if ((rc = upload(h, d.step_rhs_row, p.step_rhs_row))) return rc;
     if ((rc = upload(h, d.step_rhs_bytes, p.step_rhs_bytes))) return rc;
@@ -396,10 +434,9 @@ int upload_factor_pipe(opmgpu_handle h, const FactorPipeProgram& p, FactorPipeDe
     if ((size_t)h->max_smem_optin < fixed + 3 * (size_t)d.stage_bytes) return 0;
     d.nstages = std::min((int)(((size_t)h->max_smem_optin - fixed) / (size_t)d.stage_bytes), kFMaxStages);
     d.smem = factor_pipe_smem_bytes(d.nstages, d.stage_bytes);
-    CK(d.buf.ensure(p.buf.size()));
-    CK(cudaMemcpyAsync(d.buf.p, p.buf.data(), p.buf.size(), cudaMemcpyHostToDevice, h->stream));
     if ((rc = upload(h, d.cta_step_ptr, p.cta_step_ptr))) return rc;
     if ((rc = upload(h, d.step_off16, p.step_off16))) return rc;
+    if ((rc = expand_records(h, p.total_bytes, p.ibuf, p.step_ioff16, p.step_ilen, p.step_roff, d.step_off16.p, d.buf))) return rc;
     if ((rc = upload(h, d.step_bytes, p.step_bytes))) return rc;
     if ((rc = upload(h, d.cta_ext_base, p.cta_ext_base))) return rc;
     if ((rc = upload(h, d.val_src, p.val_src))) return rc;

@@ -200,6 +200,32 @@ def gmres(rowptr, colidx, vals, lu, w, rhs, reduction=1e-2, maxiter=150, restart
     return x.reshape(N, 3), res.as_dict(), hist[:min(history_cap, res.half_steps)]
 
 
+_omp = None
+
+
+def solve_bcrs_openmp(rowptr, colidx, vals, rhs, reduction=1e-2, maxiter=150, relax=0.9, nthreads=0):
+    """Baseline B (oracle_omp.c): ILU0 + BiCGStab with OpenMP, level-scheduled.  Returns x, result
+    dict with ms_factor / ms_solve / threads."""
+    global _omp
+    if _omp is None:
+        build()
+        _omp = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "_build", "liboracle_omp.so"))
+        ip, dp = C.POINTER(C.c_int), C.POINTER(C.c_double)
+        _omp.oracle_omp_solve_bcrs3.argtypes = [C.c_int, ip, ip, dp, dp, dp, C.c_double, C.c_int, C.c_double, C.c_int,
+                                                C.POINTER(OracleResult), dp, dp, ip]
+        _omp.oracle_omp_solve_bcrs3.restype = C.c_int
+    rowptr, prp = _i(rowptr); colidx, pci = _i(colidx); vals, pv = _d(vals); rhs, pr = _d(rhs)
+    N = rowptr.size - 1
+    x = np.zeros(N * 3)
+    res = OracleResult()
+    msf, mss, nt = C.c_double(0), C.c_double(0), C.c_int(0)
+    _omp.oracle_omp_solve_bcrs3(N, prp, pci, pv, pr, x.ctypes.data_as(C.POINTER(C.c_double)), float(reduction),
+                                int(maxiter), float(relax), int(nthreads), C.byref(res), C.byref(msf), C.byref(mss), C.byref(nt))
+    d = res.as_dict()
+    d.update(ms_factor=msf.value, ms_solve=mss.value, threads=nt.value)
+    return x.reshape(N, 3), d
+
+
 def solve_from_csc_blocks(N, blocks9, matbalscale, rhs_eqmajor, reduction=1e-2, maxiter=150,
                           relax=0.9, require_full=False):
     arr, keep = _csc_array(blocks9)
