@@ -85,7 +85,20 @@ typedef struct {
 void opmgpu_default_params(opmgpu_params* p);
 
 /* Lifetime: created once where FlowMain::setupLinearSolver builds fis_solver_
- * (opm/autodiff/FlowMain.hpp:806-830) and kept for the whole run. */
+ * (opm/autodiff/FlowMain.hpp:806-830) and kept for the whole run.
+ *
+ * GPU exclusivity: the ILU0 sweep and factorisation kernels are persistent CTAs that wait for each
+ * other (push slots, distributed shared memory, cluster barriers), so every CTA of a launch must
+ * be resident at once.  They are launched cooperatively (the driver refuses a launch that cannot
+ * be co-resident) and the handle's stream runs one kernel at a time; do not share the device's
+ * SMs with other work (other streams, MPS clients) while a solve is in flight.  All waits are
+ * bounded: an undelivered dependency ends the solve with OPMGPU_CUDA_ERROR ("sweep watchdog"),
+ * after which the handle is usable again.
+ *
+ * Borrowed device pointers: opmgpu_set_values_bcrs3_dev keeps the caller's pointer until the next
+ * set_values / solve call -- the buffer must stay valid and unchanged that long (opmgpu_spmv*,
+ * opmgpu_ilu0_factor and opmgpu_ilu0_get_factors read it).  opmgpu_solve_bcrs3_dev borrows its
+ * pointers for the duration of the call only. */
 int  opmgpu_create(int device, opmgpu_handle* out);
 int  opmgpu_destroy(opmgpu_handle h);
 const char* opmgpu_last_error(opmgpu_handle h);          /* h may be NULL: creation errors */
@@ -100,6 +113,18 @@ const char* opmgpu_last_error(opmgpu_handle h);          /* h may be NULL: creat
  * solve / set_values / spmv entry points take the rank's LOCAL rows (values in the order of the
  * local pattern passed here) and the solves are collective. */
 int  opmgpu_nccl_unique_id(void* id128);
+
+/* Multi-GPU beneath this ABI: ONE host process, one worker thread per
+ * GPU, the caller unaware of ranks -- the counterpart of the MPI branch inside ISTLSolver::solve
+ * (ISTLSolver.hpp:283-306), which a caller of NewtonIterationBlackoilInterface does not see either.
+ * The handle accepts opmgpu_set_pattern_bcrs, opmgpu_solve_bcrs3, opmgpu_solve_from_csc_blocks,
+ * opmgpu_destroy and opmgpu_last_error with GLOBAL arrays; it partitions the rows itself (slabs along
+ * the weakest-coupling grid axis for Cartesian patterns, contiguous row blocks otherwise; the halo
+ * plan comes from the pattern), runs block-Jacobi ILU0 per GPU and the global operator with halo
+ * exchange, and returns the increment in the caller's ordering.  opmgpu_multi_partition reports
+ * the partition chosen at the first solve (axis 0/1/2 = i/j/k, -1 = contiguous row blocks). */
+int  opmgpu_create_multi(int ngpus, const int* device_ids, opmgpu_handle* out);
+int  opmgpu_multi_partition(opmgpu_handle h, int* axis, long long* row_offsets /* ngpus+1 */);
 int  opmgpu_create_distributed(int device, int rank, int world, const void* nccl_unique_id,
                                opmgpu_handle* out);
 

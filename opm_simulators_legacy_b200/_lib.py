@@ -17,6 +17,7 @@ LIB_PATH = os.environ.get("OPMGPU_LIB") or os.path.join(_HERE, "libopmgpu.so")
 EXPORTS = [
     "opmgpu_default_params", "opmgpu_create", "opmgpu_destroy", "opmgpu_last_error",
     "opmgpu_nccl_unique_id", "opmgpu_create_distributed", "opmgpu_set_stream",
+    "opmgpu_create_multi", "opmgpu_multi_partition",
     "opmgpu_set_pattern_bcrs", "opmgpu_set_pattern_bcrs_distributed",
     "opmgpu_solve_bcrs3", "opmgpu_solve_bcrs3_dev", "opmgpu_solve_from_csc_blocks",
     "opmgpu_set_values_bcrs3", "opmgpu_set_values_bcrs3_dev", "opmgpu_spmv", "opmgpu_spmv_dev",
@@ -78,6 +79,8 @@ def load():
         "opmgpu_last_error": (C.c_char_p, [H]),
         "opmgpu_nccl_unique_id": (C.c_int, [vp]),
         "opmgpu_create_distributed": (C.c_int, [C.c_int, C.c_int, C.c_int, vp, C.POINTER(H)]),
+        "opmgpu_create_multi": (C.c_int, [C.c_int, ip, C.POINTER(H)]),
+        "opmgpu_multi_partition": (C.c_int, [H, ip, C.POINTER(C.c_longlong)]),
         "opmgpu_set_stream": (C.c_int, [H, vp]),
         "opmgpu_set_pattern_bcrs": (C.c_int, [H, C.c_int, C.c_int, ip, ip]),
         "opmgpu_set_pattern_bcrs_distributed": (C.c_int, [H, C.c_int, C.c_int, ip, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),

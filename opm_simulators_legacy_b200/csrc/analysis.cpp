@@ -715,6 +715,7 @@ void materialise(std::vector<unsigned char>& buf, size_t total_bytes, const std:
     }
 }
 }  // namespace
+void infer_cartesian_grid(int N, const int* rowptr, const int* colidx, int& nx, int& ny, int& nz) { infer_grid(N, rowptr, colidx, nx, ny, nz); }
 void materialise_records(PipeProgram& pg) { materialise(pg.buf, pg.total_bytes, pg.ibuf, pg.step_off16, pg.step_ioff16, pg.step_ilen, pg.step_roff); }
 void materialise_records(FactorPipeProgram& pg) { materialise(pg.buf, pg.total_bytes, pg.ibuf, pg.step_off16, pg.step_ioff16, pg.step_ilen, pg.step_roff); }
 

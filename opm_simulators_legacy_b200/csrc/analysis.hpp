@@ -187,6 +187,9 @@ struct PatternAnalysis {
     int nlevL = 0, nlevU = 0;
 };
 
+// Cartesian structure of a pattern in natural ordering (0 0 0 when there is none): nx, ny, nz.
+void infer_cartesian_grid(int N, const int* rowptr, const int* colidx, int& nx, int& ny, int& nz);
+
 // P = number of persistent CTAs the sweeps will be launched with.
 void analyse_pattern(int N, const int* rowptr, const int* colidx, int P, PatternAnalysis& out,
                      bool force_simple = false, const ClusterCaps* caps = nullptr);

@@ -2,6 +2,8 @@
 // produced by libopmgpu.so on the GPU.
 #include "NewtonIterationBlackoilGPU.hpp"
 
+#include <sstream>
+
 #include <algorithm>
 #include <cmath>
 
@@ -157,7 +159,17 @@ NewtonIterationBlackoilGPU::NewtonIterationBlackoilGPU(const ParameterGroup& par
         param.getDefault("ilu_redblack", false) || param.getDefault("ilu_milu", std::string("ILU")) != "ILU")
         throw std::invalid_argument("solver_approach=gpu supports ILU0-preconditioned BiCGStab / restarted GMRes only "
                                     "(no AMG/CPR, no fill-in, no red-black ordering, no MILU)");
-    if (opmgpu_create(device, &handle_) != OPMGPU_OK)
+    // gpu_devices=0,1,...: several GPUs of this process behind the same interface (the caller stays
+    // unaware of the partition, like a caller of the reference's MPI-parallel ISTLSolver)
+    std::vector<int> devs;
+    {
+        std::istringstream is(param.getDefault("gpu_devices", std::string()));
+        std::string tok;
+        while (std::getline(is, tok, ',')) if (!tok.empty()) devs.push_back(std::stoi(tok));
+    }
+    const int rc = devs.size() > 1 ? opmgpu_create_multi((int)devs.size(), devs.data(), &handle_)
+                                   : opmgpu_create(devs.empty() ? device : devs[0], &handle_);
+    if (rc != OPMGPU_OK)
         throw std::runtime_error(std::string("NewtonIterationBlackoilGPU: ") + opmgpu_last_error(nullptr));
 }
 

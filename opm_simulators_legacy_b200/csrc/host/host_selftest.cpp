@@ -20,8 +20,10 @@ static SparseCSC fromDense(const std::vector<double>& d, int r, int c)
     return m;
 }
 
-int main()
+// usage: host_selftest [gpu_devices, e.g. 0,1]   (several devices: the multi-GPU handle beneath the same class)
+int main(int argc, char** argv)
 {
+    const std::string devices = argc > 1 ? argv[1] : "";
     const int N = 60, nw = 2, np = 3;
     const int sizes[5] = {N, N, N, nw * np, nw};
     int offs[6] = {0};
@@ -57,6 +59,7 @@ int main()
     res.well_eq = all[4];
     std::map<std::string, std::string> kv = {{"linear_solver_reduction", "1e-12"}, {"linear_solver_maxiter", "200"},
                                              {"require_full_sparsity_pattern", "true"}};
+    if (!devices.empty()) kv["gpu_devices"] = devices;
     NewtonIterationBlackoilGPU solver{ParameterGroup(kv)};
     const auto dx = solver.computeNewtonIncrement(res);
     // dense reference: Gaussian elimination on the full system
@@ -78,11 +81,12 @@ int main()
     }
     double err = 0.0, ref = 0.0;
     for (int i = 0; i < nt; ++i) { err = std::fmax(err, std::fabs(dx[i] - x[i])); ref = std::fmax(ref, std::fabs(x[i])); }
-    std::printf("host_selftest: size %zu iterations %d max_abs_err %.3e (ref %.3e)\n", dx.size(), solver.iterations(), err, ref);
+    std::printf("host_selftest[%s]: size %zu iterations %d max_abs_err %.3e (ref %.3e)\n", devices.empty() ? "1 GPU" : devices.c_str(), dx.size(), solver.iterations(), err, ref);
     // error contract: not converged -> LinearSolverProblem, iterations still reported
     bool threw = false;
     std::map<std::string, std::string> kv2 = {{"linear_solver_reduction", "1e-14"}, {"linear_solver_maxiter", "1"},
                                               {"require_full_sparsity_pattern", "true"}};
+    if (!devices.empty()) kv2["gpu_devices"] = devices;
     NewtonIterationBlackoilGPU s2{ParameterGroup(kv2)};
     try { s2.computeNewtonIncrement(res); } catch (const LinearSolverProblem&) { threw = true; }
     std::printf("host_selftest: LinearSolverProblem thrown %d, iterations() %d\n", (int)threw, s2.iterations());

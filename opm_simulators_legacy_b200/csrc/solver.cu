@@ -13,6 +13,7 @@
 #include "sweep_col.cuh"
 #include "spmv_tma.cuh"
 #include "gmres.cuh"
+#include "multi.hpp"
 
 #include <dlfcn.h>
 #include <nccl.h>      // types only: the library is resolved at run time with dlopen
@@ -166,6 +167,7 @@ struct FactorPipeDevMem {
 }  // namespace
 
 struct opmgpu_solver {
+    opmgpu::MultiSolver* multi = nullptr;      // opmgpu_create_multi: this handle only fronts one worker handle per GPU
     int device = 0;
     int sm_count = 0;
     int sweep_ctas = 0;
@@ -866,9 +868,21 @@ int launch_sweep(opmgpu_handle h, bool upper, const PipeDevMem& d, void** args)
         // stream runs one kernel at a time.  The cooperative attribute would make the driver
         // verify that, but profilers (Nsight Compute 2025.2) cannot replay launches that carry both
         // the cluster and the cooperative attribute, so it is opt-in: OPMGPU_CLUSTER_COOP=1.
-        static const bool coop = getenv("OPMGPU_CLUSTER_COOP") && atoi(getenv("OPMGPU_CLUSTER_COOP")) != 0;
-        cfg.attrs = at; cfg.numAttrs = coop ? 2 : 1;
-        CK(cudaLaunchKernelExC(&cfg, fn, args));
+        // default: with the cooperative attribute, so the driver refuses the launch instead of letting
+        // CTAs wait for peers that are not resident (shared stream, MPS neighbours).  OPMGPU_CLUSTER_COOP=0
+        // drops it (profilers cannot replay such launches).  A refused cooperative cluster launch
+        // is retried once without the attribute and remembered.
+        static const bool coop_env = !(getenv("OPMGPU_CLUSTER_COOP") && atoi(getenv("OPMGPU_CLUSTER_COOP")) == 0);
+        static bool coop_refused = false;
+        cfg.attrs = at; cfg.numAttrs = coop_env && !coop_refused ? 2 : 1;
+        cudaError_t le = cudaLaunchKernelExC(&cfg, fn, args);
+        if (le != cudaSuccess && cfg.numAttrs == 2) {
+            cudaGetLastError();
+            coop_refused = true;
+            cfg.numAttrs = 1;
+            le = cudaLaunchKernelExC(&cfg, fn, args);
+        }
+        CK(le);
         return 0;
     }
     const bool trace = (h->trace_cta >= 0 && h->d_trace.p) || h->gtrace_steps > 0;       // debug tools only
@@ -1519,6 +1533,7 @@ int opmgpu_create(int device, opmgpu_handle* out)
 int opmgpu_destroy(opmgpu_handle h)
 {
     if (!h) return OPMGPU_OK;
+    if (h->multi) { multi_destroy(h->multi); delete h; return OPMGPU_OK; }
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     h->d_rowptr.release(); h->d_colidx.release(); h->d_diag.release(); h->d_lvl_rows.release();
@@ -1550,6 +1565,7 @@ int opmgpu_set_stream(opmgpu_handle h, void* cuda_stream)
 int opmgpu_set_pattern_bcrs(opmgpu_handle h, int N, int nnzb, const int* rowptr, const int* colidx)
 {
     if (!h || !rowptr || !colidx) return OPMGPU_BAD_ARGUMENT;
+    if (h->multi) return multi_set_pattern(h->multi, N, nnzb, rowptr, colidx, h->err);
     if (h->world > 1) return h->bad("distributed handle: use opmgpu_set_pattern_bcrs_distributed");
     CK(cudaSetDevice(h->device));
     h->csc_colptr.clear(); h->csc_rowidx.clear();
@@ -1618,6 +1634,9 @@ int opmgpu_ilu0_get_factors(opmgpu_handle h, double* lu)
 {
     if (!h || !h->have_factors) return OPMGPU_BAD_ARGUMENT;
     CK(cudaSetDevice(h->device));
+    if (h->lu_lazy && !h->have_values)
+        return h->bad("the factorised matrix values were only borrowed for the solve call (opmgpu_solve_bcrs3_dev): "
+                      "set them again (opmgpu_set_values_bcrs3[_dev]) and factorise before asking for the factors");
     if (h->lu_lazy) {
         // the pipelined factorisation keeps only the pivots: build the BCRS factor array now
         // (in place on a copy of A; the matrix values must still be the ones that were factorised)
@@ -1690,6 +1709,10 @@ int opmgpu_solve_bcrs3_dev(opmgpu_handle h, const double* vals_dev, const double
         CK(cudaMemcpyAsync(x_dev, h->d_x.p, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
         CK(cudaStreamSynchronize(h->stream));
     }
+    // the caller's buffer was only borrowed for this call: nothing may read it later (the lazy path
+    // of opmgpu_ilu0_get_factors would); the factors in the sweep records stay usable
+    h->have_values = false;
+    h->d_vals = nullptr;
     return rc;
 }
 
@@ -1697,6 +1720,7 @@ int opmgpu_solve_bcrs3(opmgpu_handle h, const double* vals, const double* rhs, d
                        const opmgpu_params* params, opmgpu_result* result)
 {
     if (!h || !vals || !rhs || !x || !params || !result) return OPMGPU_BAD_ARGUMENT;
+    if (h->multi) return multi_solve_bcrs3(h->multi, vals, rhs, x, params, result, h->err);
     if (!h->have_pattern) return h->bad("set the pattern first");
     std::memset(result, 0, sizeof *result);
     result->bad_row = -1;
@@ -1727,6 +1751,7 @@ int opmgpu_solve_from_csc_blocks(opmgpu_handle h, int N, const opmgpu_csc blocks
 {
     if (!h || !blocks || !matbalscale || !rhs_eqmajor || !dx_varmajor || !params || !result || N < 1)
         return OPMGPU_BAD_ARGUMENT;
+    if (h->multi) return multi_solve_from_csc_blocks(h->multi, N, blocks, matbalscale, rhs_eqmajor, dx_varmajor, params, result, h->err);
     std::memset(result, 0, sizeof *result);
     result->bad_row = -1;
     CK(cudaSetDevice(h->device));
@@ -1749,6 +1774,19 @@ int opmgpu_solve_from_csc_blocks(opmgpu_handle h, int N, const opmgpu_csc blocks
         if (full)
             for (int p1 = 0; p1 < 3; ++p1)
                 for (int p2 = 1; p2 < 3; ++p2) sel.push_back({blocks[p1 * 3 + p2].colptr, blocks[p1 * 3 + p2].rowidx});
+        // the index arrays are about to be trusted by host and device code: validate them once per pattern
+        for (int q = 0; q < 9; ++q) {
+            const int* cp = blocks[q].colptr;
+            const int* ri = blocks[q].rowidx;
+            if (!cp || cp[0] != 0) return h->bad("CSC block: colptr[0] != 0");
+            for (int c = 0; c < N; ++c) {
+                if (cp[c + 1] < cp[c]) return h->bad("CSC block: colptr not monotone");
+                for (int k = cp[c]; k < cp[c + 1]; ++k) {
+                    if (ri[k] < 0 || ri[k] >= N) return h->bad("CSC block: row index out of range");
+                    if (k > cp[c] && ri[k] <= ri[k - 1]) return h->bad("CSC block: row indices not strictly ascending in a column");
+                }
+            }
+        }
         std::vector<int> rowptr, colidx;
         union_pattern_from_csc(N, sel.data(), (int)sel.size(), rowptr, colidx);
         int rc = set_pattern(h, N, rowptr[N], rowptr.data(), colidx.data());
@@ -1960,6 +1998,24 @@ int opmgpu_create_distributed(int device, int rank, int world, const void* nccl_
     }
     *out = h;
     return OPMGPU_OK;
+}
+
+int opmgpu_create_multi(int ngpus, const int* device_ids, opmgpu_handle* out)
+{
+    if (!out) return OPMGPU_BAD_ARGUMENT;
+    *out = nullptr;
+    MultiSolver* m = multi_create(ngpus, device_ids, g_create_error);
+    if (!m) return g_create_error.find("NCCL") != std::string::npos ? OPMGPU_NCCL_ERROR : OPMGPU_CUDA_ERROR;
+    opmgpu_handle h = new opmgpu_solver();
+    h->multi = m;
+    *out = h;
+    return OPMGPU_OK;
+}
+
+int opmgpu_multi_partition(opmgpu_handle h, int* axis, long long* row_offsets)
+{
+    if (!h || !h->multi) return OPMGPU_BAD_ARGUMENT;
+    return multi_partition_info(h->multi, axis, row_offsets);
 }
 
 int opmgpu_set_pattern_bcrs_distributed(opmgpu_handle h, int N_local, int nnzb_local, const int* rowptr,

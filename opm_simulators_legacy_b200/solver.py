@@ -94,6 +94,30 @@ class GpuLinearSolver:
         self.nnzb = 0
         self.last = None
 
+    @classmethod
+    def multi(cls, devices):
+        """One handle, several GPUs of this process (opmgpu_create_multi): the partition, the halo plan and
+        the per-GPU worker threads live beneath the C ABI; set_pattern / solve_bcrs /
+        solve_from_csc_blocks take and return GLOBAL arrays."""
+        self = cls.__new__(cls)
+        self.lib = L.load()
+        self.h = C.c_void_p()
+        dev = np.ascontiguousarray(list(devices), dtype=np.int32)
+        rc = self.lib.opmgpu_create_multi(int(dev.size), _ip(dev), C.byref(self.h))
+        if rc != L.OK:
+            raise RuntimeError("opmgpu_create_multi failed: " + self.lib.opmgpu_last_error(None).decode())
+        self.N = self.nnzb = 0
+        self.last = None
+        self.ngpus = int(dev.size)
+        return self
+
+    def multi_partition(self):
+        """(axis, row_offsets) of a multi-GPU handle after its first solve; axis -1 = contiguous row blocks."""
+        axis = C.c_int(0)
+        offs = (C.c_longlong * (self.ngpus + 1))()
+        self._check(self.lib.opmgpu_multi_partition(self.h, C.byref(axis), offs))
+        return axis.value, list(offs)
+
     def close(self):
         if self.h:
             self.lib.opmgpu_destroy(self.h)
