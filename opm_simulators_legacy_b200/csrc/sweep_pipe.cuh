@@ -299,11 +299,47 @@ __device__ __forceinline__ bool cx_wait(uint32_t a, double& y0, double& y1, doub
     return true;
 }
 
+#ifndef OPMGPU_CX_UNIFORM
+#define OPMGPU_CX_UNIFORM 0
+#endif
+// 1 (experiment): results delivered through distributed shared memory are awaited by the whole
+// warp (vote) before the dependency loads, not by the lanes that need them afterwards.  A lone
+// spinning lane costs ~1000 cycles per hand-over against 200-300 for a warp-uniform poll
+// (tools/ubench/xwarp*.cu), but in the sweeps the entries are usually there already and the extra
+// vote + nine 4-byte loads per step cost more: 100^3 apply 282 us (0) against 293 us (1), round 2.
+constexpr bool kCxUniformWait = OPMGPU_CX_UNIFORM != 0;
+
+__device__ __forceinline__ bool cx_entry_there(uint32_t a)
+{
+    int h0, h1, h2;
+    asm volatile("ld.volatile.shared.s32 %0, [%1+4];" : "=r"(h0) : "r"(a) : "memory");
+    asm volatile("ld.volatile.shared.s32 %0, [%1+12];" : "=r"(h1) : "r"(a) : "memory");
+    asm volatile("ld.volatile.shared.s32 %0, [%1+20];" : "=r"(h2) : "r"(a) : "memory");
+    return (h0 != -1) & (h1 != -1) & (h2 != -1);      // a result never has an all-ones upper half (that is a NaN no arithmetic produces)
+}
+
 template <bool UPPER, bool LEAN, bool CX = false>
 __device__ __forceinline__ void sweep_row_chain(const StepPre<UPPER>& p, const unsigned char* rec, int r,
                                                 double* dep, uint32_t dep_s, const double* work, double* ext, double (&acc)[3],
                                                 PipeCtl* ctl = nullptr, int* err = nullptr)
 {
+    if (CX && kCxUniformWait) {
+        // (all lanes of the warp are here: the turn barrier and the pushed-input check are warp-uniform)
+        const bool mine = p.on && p.has_cx;
+        if (__any_sync(0xffffffffu, mine)) {
+            unsigned spins = 0;
+            for (;;) {
+                bool missing = false;
+                if (mine) {
+                    if (p.ri0.y >= kCxBase * 3) missing |= !cx_entry_there(p.a0);
+                    if (p.ri0.z >= kCxBase * 3) missing |= !cx_entry_there(p.a1);
+                    if (p.ri0.w >= kCxBase * 3) missing |= !cx_entry_there(p.a2);
+                }
+                if (!__any_sync(0xffffffffu, missing)) break;
+                if (++spins > kPipeSpinLimit * 8u || ctl->abort_flag) { ctl->abort_flag = 1; atomicExch(err, 8); break; }
+            }
+        }
+    }
     if (!p.on) { acc[0] = acc[1] = acc[2] = 0.0; }
     if (p.on) {
         double y[9];
@@ -313,7 +349,7 @@ __device__ __forceinline__ void sweep_row_chain(const StepPre<UPPER>& p, const u
             y[0] = lds_f64(a0); y[1] = lds_f64(a0 + 8); y[2] = lds_f64(a0 + 16);
             y[3] = lds_f64(a1); y[4] = lds_f64(a1 + 8); y[5] = lds_f64(a1 + 16);
             y[6] = lds_f64(a2); y[7] = lds_f64(a2 + 8); y[8] = lds_f64(a2 + 16);
-            if (CX && p.has_cx) {      // delivered by a CTA of the cluster?
+            if (CX && !kCxUniformWait && p.has_cx) {      // delivered by a CTA of the cluster?
                 if (p.ri0.y >= kCxBase * 3) cx_wait(a0, y[0], y[1], y[2], ctl, err);
                 if (p.ri0.z >= kCxBase * 3) cx_wait(a1, y[3], y[4], y[5], ctl, err);
                 if (p.ri0.w >= kCxBase * 3) cx_wait(a2, y[6], y[7], y[8], ctl, err);
