@@ -1908,6 +1908,18 @@ int opmgpu_get_profile(opmgpu_handle h, double ms[4], long long count[4])
     return OPMGPU_OK;
 }
 
+// Debug (not in the public header; tests of the recovery path): sets the device watchdog word
+// as a sweep kernel does when a dependency is never delivered.  The next call that collects it
+// must fail with OPMGPU_CUDA_ERROR ("sweep watchdog"), re-arm the push slots and leave the handle usable.
+int opmgpu_debug_set_watchdog_word(opmgpu_handle h, int code)
+{
+    if (!h || h->multi) return OPMGPU_BAD_ARGUMENT;
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(h->d_err.p, &code, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return OPMGPU_OK;
+}
+
 // Debug (not in the public header): clock64 stamps of one CTA of the next pipelined apply.
 // out[2][512][8]: lower then upper sweep; per step {enter, landed, computed, after barrier,
 // nrows, bulk issued, rhs gather issued, -}.

@@ -263,8 +263,8 @@ def test_newton_iteration_blackoil_gpu_with_wells(oracle):
 
 # ---- BASELINE.json's full sizes: size-independent properties -----------------------------------
 @pytest.mark.parametrize("dims,perm", [((100, 100, 50), "homogeneous"), ((100, 100, 100), "lognormal"),
-                                       ((144, 144, 144), "homogeneous")],
-                         ids=["c2_500k", "c3_1M", "c5_3M_two_tiles_per_cta"])
+                                       ((144, 144, 144), "homogeneous"), ((200, 200, 200), "lognormal")],
+                         ids=["c2_500k", "c3_1M", "c5_3M_two_tiles_per_cta", "c4_8M"])
 def test_full_size_properties(dims, perm):
     import torch
     from opm_simulators_legacy_b200.jacobian import bcrs_matvec
@@ -360,3 +360,86 @@ def test_gmres_parity(gpu_solver, oracle, dims, restart):
     with pytest.raises(LinearSolverProblem):
         gpu_solver.solve_bcrs(v, b, newton_use_gmres=True, linear_solver_reduction=1e-14, linear_solver_maxiter=3)
     assert gpu_solver.last["iterations"] == 3
+
+
+def test_require_full_sparsity_pattern(gpu_solver, oracle):
+    """A saturation-derivative entry outside the union of the pressure patterns: dune throws in
+    istlA[row][col] unless require_full_sparsity_pattern builds the pattern from all nine blocks
+    (...Interleaved.cpp:127-134)."""
+    import scipy.sparse as sp
+    s = synth_blackoil_jacobian(8, 7, 5, perm="lognormal")
+    blocks = [tuple(t) for t in s.csc_blocks()]
+    N = s.N
+    cp, ri, val = blocks[1]                                   # d(water eq)/d(sw)
+    m = sp.csc_matrix((val, ri, cp), shape=(N, N)).tolil()
+    extra = [(5, 5 + 2), (40, 40 + 3 * 8), (N - 1, 0)]        # no stencil neighbours
+    for r, c in extra:
+        m[r, c] = 0.125 * (1 + r % 3)
+    m = m.tocsc(); m.sort_indices()
+    blocks[1] = (m.indptr.astype(np.int32), m.indices.astype(np.int32), m.data.copy())
+    rhs = s.rhs_eqmajor_unscaled.numpy()
+    with pytest.raises(ValueError):
+        gpu_solver.solve_from_csc_blocks(N, blocks, s.matbalscale, rhs)
+    dx, res = gpu_solver.solve_from_csc_blocks(N, blocks, s.matbalscale, rhs, require_full_sparsity_pattern=True)
+    dx_ref, ref = oracle.solve_from_csc_blocks(N, blocks, s.matbalscale, rhs, require_full=True)
+    assert res["converged"] == 1 and res["iterations"] == ref["iterations"]
+    sc = np.abs(dx_ref.reshape(3, -1)).max(1).repeat(N)
+    assert (np.abs(dx - dx_ref) <= 1e-8 * sc).all()
+    # the pattern (now with fill outside the stencil) is cached like any other
+    dx2, res2 = gpu_solver.solve_from_csc_blocks(N, blocks, s.matbalscale, rhs, require_full_sparsity_pattern=True)
+    assert res2["ms_analysis"] == 0.0 and np.array_equal(dx, dx2)
+
+
+def test_nan_and_inf_end_the_solve_like_the_reference(gpu_solver, oracle):
+    """NaN / Inf in the matrix or the right-hand side: the reference's solve ends with "not
+    converged" (-> LinearSolverProblem) or a MatrixBlockError (-> NumericalIssue).  Here it must
+    do the same, promptly (no watchdog trip: results are never all-ones, the push slots' empty
+    marker, because arithmetic only produces the canonical NaN), and leave the handle usable."""
+    import time
+    s = synth_blackoil_jacobian(24, 20, 12, perm="lognormal")
+    rp, ci, v, b = _np(s)
+    gpu_solver.set_pattern(rp, ci)
+    x_ok, res_ok = gpu_solver.solve_bcrs(v, b)
+    for what in ("rhs_nan", "rhs_inf", "val_nan_offdiag", "val_nan_diag"):
+        v2, b2 = v.copy(), b.copy()
+        if what == "rhs_nan":
+            b2[777, 1] = np.nan
+        elif what == "rhs_inf":
+            b2[777, 1] = np.inf
+        elif what == "val_nan_offdiag":
+            v2[rp[900] + 1, 5] = np.nan
+        else:
+            d = np.searchsorted(ci[rp[900]:rp[901]], 900) + rp[900]
+            v2[d, 0] = np.nan
+        t0 = time.time()
+        with pytest.raises((LinearSolverProblem, NumericalIssue)):
+            gpu_solver.solve_bcrs(v2, b2, linear_solver_maxiter=20)
+        assert time.time() - t0 < 5.0, what
+        assert "watchdog" not in gpu_solver.error(), (what, gpu_solver.error())
+        x, res = gpu_solver.solve_bcrs(v, b)                  # the handle is as good as before
+        assert res["iterations"] == res_ok["iterations"] and np.array_equal(x, x_ok), what
+
+
+def test_watchdog_trip_is_reported_and_recovered(gpu_solver, oracle):
+    """The sweep kernels raise a device word when a dependency is never delivered (bounded
+    spins).  The host must turn it into an error (std::runtime_error class), re-arm every push
+    slot and keep the handle usable."""
+    import ctypes as C
+    s = synth_blackoil_jacobian(40, 40, 20, perm="lognormal")          # several CTAs, clusters, push slots
+    rp, ci, v, b = _np(s)
+    gpu_solver.set_pattern(rp, ci)
+    x_ok, res_ok = gpu_solver.solve_bcrs(v, b)
+    f = gpu_solver.lib.opmgpu_debug_set_watchdog_word
+    f.argtypes = [C.c_void_p, C.c_int]; f.restype = C.c_int
+    assert f(gpu_solver.h, 4) == 0
+    with pytest.raises(RuntimeError, match="watchdog"):
+        gpu_solver.solve_bcrs(v, b)
+    x, res = gpu_solver.solve_bcrs(v, b)
+    assert res["iterations"] == res_ok["iterations"] and np.array_equal(x, x_ok)
+    gpu_solver.set_values(v)
+    assert gpu_solver.ilu0_factor() == -1
+    assert f(gpu_solver.h, 2) == 0
+    with pytest.raises(RuntimeError, match="watchdog"):
+        gpu_solver.ilu0_apply(0.9, b)
+    lu_ref, _ = oracle.ilu0_factor(rp, ci, v)
+    assert np.array_equal(gpu_solver.ilu0_apply(0.9, b), oracle.ilu0_apply(rp, ci, lu_ref, 0.9, b))
