@@ -858,6 +858,8 @@ int launch_sweep(opmgpu_handle h, bool upper, const PipeDevMem& d, void** args)
 {
     if (d.cluster_size > 1) {
         const void* fn = upper ? (const void*)ilu0_sweep_pipe_kernel<true, true, true> : (const void*)ilu0_sweep_pipe_kernel<false, true, true>;
+        if (h->gtrace_steps > 0 || (h->trace_cta >= 0 && h->d_trace.p))                     // debug tools only
+            fn = upper ? (const void*)ilu0_sweep_pipe_kernel<true, true, true, true> : (const void*)ilu0_sweep_pipe_kernel<false, true, true, true>;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(d.P); cfg.blockDim = dim3(kPipeThreads); cfg.dynamicSmemBytes = d.smem; cfg.stream = h->stream;
         cudaLaunchAttribute at[2];
@@ -1465,6 +1467,8 @@ int opmgpu_create(int device, opmgpu_handle* out)
     cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<true, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
     cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
     cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
+    cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<false, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
+    cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<true, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
     {
         // how many CTAs of the cluster variants can be co-resident (one CTA per SM, all of its
         // shared memory): GPCs do not divide evenly into clusters of 4 or 8
