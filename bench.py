@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the Newton-step linear solve (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c3|c2|c4|small]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c3|c2|c4|small] [--dtype f64|f32]
 
 One "step" = one pass of the hot path: ILU0 factorisation + ILU0/BiCGStab solve to
 linear_solver_reduction = 1e-2 of one synthetic three-phase black-oil Jacobian system
@@ -18,6 +18,9 @@ between formInterleavedSystem and the de-interleave.
 * `cpu_baseline`: the CPU oracle (a port of the reference's dune-istl path, 1 thread like the
   reference) on the same system, on rank 0.
 * `--impl reference`: the CPU oracle alone, same JSON line with "impl": "reference".
+* `--dtype f32`: the whole line for the single-precision instance (the reference's Impl<3,float>,
+  selected by LinearisedBlackoilResidual::singlePrecision), checked against the float build of the
+  oracle.  The default (f64) line carries a compact `f32` sub-measurement of the same workload.
 """
 from __future__ import annotations
 
@@ -157,7 +160,8 @@ def run_reference(args, rank):
     built here), single-threaded like the reference's solver."""
     if rank != 0:
         return
-    from oracle import oracle_py as O
+    from oracle import oracle_py
+    O = oracle_py.instance(args.dtype == "f32")
     s = build_system(args.workload)
     rp, ci, v, b = s.rowptr.numpy(), s.colidx.numpy(), s.vals.numpy(), s.rhs.numpy()
     res = None
@@ -171,7 +175,7 @@ def run_reference(args, rank):
     ms = sum(ts) / len(ts)
     line = {"impl": "reference", "metric": METRIC, "value": ms, "unit": "ms", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": config_of(args.workload, s, 1), "iterations": res["iterations"],
             "cpu_baseline": {"value": ms, "unit": "ms", "cores": 1, "kind": "port",
                              "sample": f"{args.steps} full solves of the same system (ILU0 factor + BiCGStab to 1e-2)"},
@@ -179,9 +183,10 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
-def measure(workload, steps, warmup, rank, world, local, sample_clocks=True):
+def measure(workload, steps, warmup, rank, world, local, sample_clocks=True, single=False, with_allcores=True):
     """One workload on `world` GPUs: device-timed solve, end-to-end solve, roofline of the ILU0
-    apply, parity against the CPU oracle.  Returns the pieces of the JSON line (rank 0) or None."""
+    apply, parity against the CPU oracle.  single: the float instance (Impl<3,float>) against the
+    float oracle.  Returns the pieces of the JSON line (rank 0) or None."""
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -199,14 +204,25 @@ def measure(workload, steps, warmup, rank, world, local, sample_clocks=True):
         vals = s.vals.cuda()
         rhs = s.rhs.cuda()
         x = torch.zeros_like(rhs)
-        solve = lambda: g.solve_bcrs_dev(vals, rhs, x, params=params)          # noqa: E731
+        if single:
+            # matrix resident in HBM as the instance stores it (float): rounded once, outside the timed region
+            g.set_precision(True)
+            g.set_values_dev(vals)
+            solve = lambda: g.solve_bcrs_dev(None, rhs, x, params=params)      # noqa: E731
+        else:
+            solve = lambda: g.solve_bcrs_dev(vals, rhs, x, params=params)      # noqa: E731
         axis = None
     else:
         from opm_simulators_legacy_b200.distributed import DistributedSolver
         g = DistributedSolver(s, local)
         analysis_ms = g.analysis_ms
         x = g.x
-        solve = lambda: g.solve(params)                                          # noqa: E731
+        if single:
+            g.set_precision(True)
+            g.set_values_dev(g.vals)
+            solve = lambda: g.solve_bcrs_dev(None, g.rhs, g.x, params=params)    # noqa: E731
+        else:
+            solve = lambda: g.solve(params)                                      # noqa: E731
         axis = g.axis
 
     def barrier():
@@ -316,8 +332,8 @@ def measure(workload, steps, warmup, rank, world, local, sample_clocks=True):
     # per launch = per rank: rank 0's rows (its diagonal block for the block-Jacobi ILU0)
     N, nnzb = (s.N, s.nnzb) if world == 1 else (g.N, g.nnzb)
     nnzb_ilu = nnzb if world == 1 else g.nnzb_diag      # blocks of the rank's diagonal block (block-Jacobi ILU0)
-    b_ilu = 76 * (nnzb_ilu - N) + 176 * N       # SURVEY.md §8d, bytes per apply
-    b_spmv = 76 * nnzb + 52 * N
+    b_ilu = 76 * (nnzb_ilu - N) + 176 * N       # SURVEY.md §8d, bytes per apply (the float instance keeps 8-byte factor containers)
+    b_spmv = (40 * nnzb + 28 * N) if single else (76 * nnzb + 52 * N)          # 36-byte blocks, 4-byte vector entries in float
     ap_ms, ap_n = prof["ilu_apply"]
     sp_ms, sp_n = prof["spmv"]
     ach = b_ilu * ap_n / (ap_ms * 1e-3) / 1e9 if ap_ms > 0 else 0.0
@@ -340,12 +356,14 @@ def measure(workload, steps, warmup, rank, world, local, sample_clocks=True):
                 "vector_share_of_step": prof["vector"][0] / (ms * steps)}
 
     # ---- CPU baseline on this box's host cores (bounded sample: one full solve of the same system)
-    from oracle import oracle_py as O
+    from oracle import oracle_py
+    O = oracle_py.instance(single)
     rp, ci, v, b = s.rowptr.numpy(), s.colidx.numpy(), s.vals.numpy(), s.rhs.numpy()
     t0 = time.perf_counter()
     x_ref, ref = O.solve_bcrs(rp, ci, v, b)
     cpu_ms = (time.perf_counter() - t0) * 1e3
-    true_red = float(np.linalg.norm(b - O.spmv(rp, ci, v, x_nat)) / np.linalg.norm(b))
+    x_ref = x_ref.astype(np.float64)
+    true_red = float(np.linalg.norm(b - oracle_py.spmv(rp, ci, v, x_nat)) / np.linalg.norm(b))
     if world == 1:
         parity = {"iterations_gpu": res["iterations"], "iterations_cpu_oracle": ref["iterations"],
                   "max_rel_diff_increment": float((np.abs(x_nat - x_ref).max(0) / np.abs(x_ref).max(0)).max()),
@@ -355,13 +373,15 @@ def measure(workload, steps, warmup, rank, world, local, sample_clocks=True):
         # is reduced by linear_solver_reduction; iteration counts side by side
         parity = {"iterations_partitioned": res["iterations"], "iterations_oracle_unpartitioned": ref["iterations"],
                   "true_residual_reduction": true_red, "tolerance": 1e-2, "within_tolerance": bool(true_red <= 1e-2 * 1.0001),
-                  "spmv_bit_exact": bool(np.array_equal(y_nat, O.spmv(rp, ci, v, s.xstar.numpy()))),
+                  "spmv_bit_exact": bool(np.array_equal(y_nat, O.spmv(rp, ci, v, s.xstar.numpy()).astype(np.float64))),
                   "max_rel_diff_vs_unpartitioned": float((np.abs(x_nat - x_ref).max(0) / np.abs(x_ref).max(0)).max())}
     # Baseline B: the same algorithm with OpenMP on every host core, level-scheduled
     # ILU0 -- labelled, because the reference's solver is sequential (rank 0 only; torchrun pins
     # OMP_NUM_THREADS to 1 per rank, so the thread count is set explicitly)
     allcores = None
     try:
+        if single or not with_allcores:
+            raise RuntimeError("not measured for this sub-line (the OpenMP baseline exists for the double instance)")
         ncpu = len(os.sched_getaffinity(0))
         x_b, rb = O.solve_bcrs_openmp(rp, ci, v, b, nthreads=ncpu)          # warm-up (page faults, thread pool)
         x_b, rb = O.solve_bcrs_openmp(rp, ci, v, b, nthreads=ncpu)
@@ -394,7 +414,25 @@ def run_gpu(args, rank, world):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
-    m = measure(args.workload, args.steps, args.warmup, rank, world, local)
+    single = args.dtype == "f32"
+    m = measure(args.workload, args.steps, args.warmup, rank, world, local, single=single)
+    # the float instance (the reference's default for time steps below 20 days,
+    # BlackoilModelBase_impl.hpp:284) beside the double headline
+    f32 = None
+    if not single and not args.no_f32:
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        mf = measure(args.workload, args.steps, 3, rank, world, local, sample_clocks=False, single=True, with_allcores=False)
+        if mf is not None:
+            f32 = {"value": mf["ms"], "unit": "ms", "dtype": "f32", "steps": args.steps, "iterations": mf["iterations"],
+                   "e2e": mf["e2e"], "solve_breakdown_ms": mf["breakdown"],
+                   "ilu_apply_us": mf["roofline"]["avg_launch_us"], "ilu_apply_frac_8byte_containers": mf["roofline"]["frac"],
+                   "spmv_us": mf["roofline"]["spmv"]["avg_launch_us"], "spmv_gbs": mf["roofline"]["spmv"]["achieved"],
+                   "spmv_algorithmic_bytes": mf["roofline"]["spmv"]["algorithmic_bytes_per_launch"],
+                   "cpu_baseline_float_oracle_ms": mf["cpu_baseline"]["value"], "parity_vs_float_oracle": mf["parity"],
+                   "note": "Impl<3,float>: matrix values and vectors in float (SpMV 40 B/block + 28 B/row), ILU0 factors and sweep "
+                           "records keep 8-byte containers (float arithmetic, bit-exact against the float oracle)"}
     # the strong-scaling configuration (BASELINE.json config 4: 8M cells) beside the headline
     c4 = None
     if args.workload == "c3" and not args.no_c4:
@@ -402,7 +440,7 @@ def run_gpu(args, rank, world):
         gc.collect()
         torch.cuda.empty_cache()
         k4 = max(2, min(args.steps, 3))
-        m4 = measure("c4", k4, 3, rank, world, local, sample_clocks=False)
+        m4 = measure("c4", k4, 3, rank, world, local, sample_clocks=False, single=single)
         if m4 is not None:
             c4 = {"value": m4["ms"], "unit": "ms", "steps": k4, "warmup": 3, "iterations": m4["iterations"],
                   "e2e": m4["e2e"], "ilu_apply_frac": m4["roofline"]["frac"], "ilu_apply_us": m4["roofline"]["avg_launch_us"],
@@ -416,12 +454,12 @@ def run_gpu(args, rank, world):
     if rank != 0:
         return
     line = {"metric": METRIC, "value": m["ms"], "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": m["ms"], "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": m["ms"], "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": args.dtype,
             "data": "synthetic", "config": m["config"], "clocks": m["clocks"],
             "e2e": m["e2e"], "gpu_launches": m["launches"], "roofline": m["roofline"],
             "cpu_baseline": m["cpu_baseline"], "cpu_baseline_allcores": m["cpu_baseline_allcores"],
             "iterations": m["iterations"], "reduction": m["reduction"], "analysis_ms_once_per_pattern": m["analysis_ms"],
-            "solve_breakdown_ms": m["breakdown"], "parity": m["parity"], "c4": c4}
+            "solve_breakdown_ms": m["breakdown"], "parity": m["parity"], "c4": c4, "f32": f32}
     print(json.dumps(line), flush=True)
 
 
@@ -433,6 +471,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-c4", action="store_true", help="skip the 8M-cell sub-measurement of the default (c3) run")
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"],
+                    help="instance measured on the headline: Impl<3,double> (default) or Impl<3,float> (singlePrecision)")
+    ap.add_argument("--no-f32", action="store_true", help="skip the float-instance sub-measurement of the default (f64) run")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", 0))

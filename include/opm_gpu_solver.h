@@ -101,6 +101,19 @@ void opmgpu_default_params(opmgpu_params* p);
  * pointers for the duration of the call only. */
 int  opmgpu_create(int device, opmgpu_handle* out);
 int  opmgpu_destroy(opmgpu_handle h);
+
+/* Scalar type of the instance the handle runs.  The reference keeps two instances of its solver,
+ * Impl<np,double> and Impl<np,float>, and picks one per call from
+ * LinearisedBlackoilResidual::singlePrecision (NewtonIterationBlackoilInterleaved.cpp:467-487;
+ * BlackoilModelBase_impl.hpp:284 sets it for time steps below 20 days).  single_precision != 0
+ * selects the float instance: the interleaved matrix, the right-hand side and every vector are
+ * rounded to float once (as the assignments at ...Interleaved.cpp:189, :266 do), SpMV, ILU0,
+ * sweeps, vector updates, scalar products and the convergence test run in float.  The ABI still
+ * exchanges doubles everywhere; device pointers passed to the *_dev entry points are copied and
+ * rounded, never borrowed, in this mode.  Switching invalidates values and factors, not the
+ * pattern analysis.  Restarted GMRES exists for the double instance only. */
+int  opmgpu_set_precision(opmgpu_handle h, int single_precision);
+int  opmgpu_get_precision(opmgpu_handle h);                 /* 1: float instance */
 const char* opmgpu_last_error(opmgpu_handle h);          /* h may be NULL: creation errors */
 
 /* Multi-GPU (one process per GPU): rank r of `world` owns the contiguous block rows
@@ -147,7 +160,9 @@ int  opmgpu_set_pattern_bcrs_distributed(opmgpu_handle h, int N_local, int nnzb_
  * blocks [eq][var], rhs/x cell-major [cell][3], x0 = 0 (...Interleaved.cpp:272-273). */
 int  opmgpu_solve_bcrs3(opmgpu_handle h, const double* vals, const double* rhs, double* x,
                         const opmgpu_params* params, opmgpu_result* result);
-/* Same with device-resident inputs/outputs (benchmarks; a caller that assembles on the GPU). */
+/* Same with device-resident inputs/outputs (benchmarks; a caller that assembles on the GPU).
+ * vals_dev == NULL: factorise and solve with the values already resident in the handle
+ * (opmgpu_set_values_bcrs3[_dev]). */
 int  opmgpu_solve_bcrs3_dev(opmgpu_handle h, const double* vals_dev, const double* rhs_dev,
                             double* x_dev, const opmgpu_params* params, opmgpu_result* result);
 

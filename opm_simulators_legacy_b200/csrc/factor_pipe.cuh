@@ -61,30 +61,32 @@ __host__ __device__ inline size_t factor_pipe_smem_bytes(int nstages, int stage_
     return 512 + (size_t)kFDepBytes + (size_t)nstages * (size_t)stage_bytes;
 }
 
-// A blocks (BCRS) -> step records: one thread per block row (3 doubles)
+// A blocks (BCRS) -> step records: one thread per block row (3 values; TA = type the blocks are stored in)
+template <class TA>
 __global__ void __launch_bounds__(256)
 pack_factor_records_kernel(size_t nval, const int* __restrict__ src, const unsigned* __restrict__ dst8,
-                           const double* __restrict__ vals, double* __restrict__ bufd)
+                           const TA* __restrict__ vals, double* __restrict__ bufd)
 {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nval * 3) return;
     const size_t b = t / 3;
     const int c = (int)(t - b * 3);
-    const double* a = vals + (size_t)src[b] * 9 + c * 3;
+    const TA* a = vals + (size_t)src[b] * 9 + c * 3;
     double* d = bufd + (size_t)dst8[b] + c * 3;
-    const double a0 = a[0], a1 = a[1], a2 = a[2];
-    d[0] = a0; d[1] = a1; d[2] = a2;
+    const TA a0 = a[0], a1 = a[1], a2 = a[2];
+    d[0] = (double)a0; d[1] = (double)a1; d[2] = (double)a2;
 }
 
-__device__ __forceinline__ double factor_invert3(double (&M)[9])
+template <class AT>
+__device__ __forceinline__ AT factor_invert3(AT (&M)[9])
 {
-    double A[9];
+    AT A[9];
 #pragma unroll
     for (int q = 0; q < 9; ++q) A[q] = M[q];
-    const double t4 = A[0] * A[4], t6 = A[0] * A[5], t8 = A[1] * A[3];
-    const double t10 = A[2] * A[3], t12 = A[1] * A[6], t14 = A[2] * A[6];
-    const double det = (t4 * A[8] - t6 * A[7] - t8 * A[8] + t10 * A[7] + t12 * A[5] - t14 * A[4]);
-    const double t17 = 1.0 / det;
+    const AT t4 = A[0] * A[4], t6 = A[0] * A[5], t8 = A[1] * A[3];
+    const AT t10 = A[2] * A[3], t12 = A[1] * A[6], t14 = A[2] * A[6];
+    const AT det = (t4 * A[8] - t6 * A[7] - t8 * A[8] + t10 * A[7] + t12 * A[5] - t14 * A[4]);
+    const AT t17 = AT(1) / det;
     M[0] = (A[4] * A[8] - A[5] * A[7]) * t17;
     M[1] = -(A[1] * A[8] - A[2] * A[7]) * t17;
     M[2] = (A[1] * A[5] - A[2] * A[4]) * t17;
@@ -113,6 +115,8 @@ __device__ __forceinline__ void factor_store_step(const FactorPipeDev& pg, const
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 
+// AT: arithmetic type (double / float); records, window, push slots and fout are 8-byte containers
+template <class AT>
 __global__ void __launch_bounds__(kFThreads, 1)
 ilu0_factor_pipe_kernel(FactorPipeDev pg, int* bad_row, int* err)
 {
@@ -227,7 +231,7 @@ ilu0_factor_pipe_kernel(FactorPipeDev pg, int* bad_row, int* err)
             // ---- everything that does not depend on earlier rows: into registers, stage back
             int n = 0, ext_end = 0, ext_cnt = 0;
             int4 ri0 = make_int4(0, 0, 0, 0), ri1 = make_int4(0, -1, -1, 0), ri2 = make_int4(-1, -1, -1, 0);
-            double v[kFRowVals];
+            AT v[kFRowVals];
             bool on = false;
             if (!dead) {
                 if (pipe_wait(&ctl->full[st], par, ctl, err)) {
@@ -241,7 +245,7 @@ ilu0_factor_pipe_kernel(FactorPipeDev pg, int* bad_row, int* err)
                         ri0 = rip[0]; ri1 = rip[1]; ri2 = rip[2];
                         const double* vp = reinterpret_cast<const double*>(rec + 32 + (size_t)n * (kFRowInts * 4)) + (size_t)r * kFRowVals;
 #pragma unroll
-                        for (int q = 0; q < kFRowVals; ++q) v[q] = vp[q];
+                        for (int q = 0; q < kFRowVals; ++q) v[q] = (AT)vp[q];
                     }
                 } else dead = true;
             }
@@ -256,8 +260,8 @@ ilu0_factor_pipe_kernel(FactorPipeDev pg, int* bad_row, int* err)
                 if (!pipe_wait_ext(ctl, ext_end, err)) { dead = true; on = false; }
                 asm volatile("" ::: "memory");
             }
-            double D[9];
-            double det = 1.0;
+            AT D[9];
+            AT det = AT(1);
             if (on) {
                 const int mask = ri1.x;
 #pragma unroll
@@ -267,14 +271,14 @@ ilu0_factor_pipe_kernel(FactorPipeDev pg, int* bad_row, int* err)
                     if (mask & (1 << kb)) {
                         const int de = kb == 0 ? ri0.y : (kb == 1 ? ri0.z : ri0.w);
                         const double* dj = dep + (size_t)de * kFEntry;
-                        double Dj[9], L[9];
+                        AT Dj[9], L[9];
 #pragma unroll
-                        for (int t = 0; t < 9; ++t) Dj[t] = dj[t];
+                        for (int t = 0; t < 9; ++t) Dj[t] = (AT)dj[t];
 #pragma unroll
                         for (int c = 0; c < 3; ++c)
 #pragma unroll
                             for (int j = 0; j < 3; ++j) {
-                                double sacc = 0.0;
+                                AT sacc = AT(0);
 #pragma unroll
                                 for (int k = 0; k < 3; ++k) sacc = fma(v[9 + kb * 18 + c * 3 + k], Dj[k * 3 + j], sacc);
                                 L[c * 3 + j] = sacc;
@@ -284,7 +288,7 @@ ilu0_factor_pipe_kernel(FactorPipeDev pg, int* bad_row, int* err)
                             for (int c = 0; c < 3; ++c)
 #pragma unroll
                                 for (int j = 0; j < 3; ++j) {
-                                    double sacc = 0.0;
+                                    AT sacc = AT(0);
 #pragma unroll
                                     for (int k = 0; k < 3; ++k) sacc = fma(L[c * 3 + k], v[18 + kb * 18 + k * 3 + j], sacc);
                                     D[c * 3 + j] -= sacc;
@@ -295,7 +299,7 @@ ilu0_factor_pipe_kernel(FactorPipeDev pg, int* bad_row, int* err)
                 det = factor_invert3(D);
                 double* w = dep + (size_t)ri1.w * kFEntry;
 #pragma unroll
-                for (int t = 0; t < 9; ++t) w[t] = D[t];
+                for (int t = 0; t < 9; ++t) w[t] = (double)D[t];
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // window -> bulk store
             }
             asm volatile("bar.arrive %0, %1;" ::"r"(bar_own), "n"(NPP) : "memory");                // step s done
@@ -304,19 +308,19 @@ ilu0_factor_pipe_kernel(FactorPipeDev pg, int* bad_row, int* err)
                 if (ri1.y >= 0) {
                     double* sl = pg.ext + (size_t)ri1.y * 9;
 #pragma unroll
-                    for (int t = 0; t < 9; ++t) push_f64(sl + t, D[t]);
+                    for (int t = 0; t < 9; ++t) push_f64(sl + t, (double)D[t]);
                 }
                 if (ri1.z >= 0) {
                     double* sl = pg.ext + (size_t)ri1.z * 9;
 #pragma unroll
-                    for (int t = 0; t < 9; ++t) push_f64(sl + t, D[t]);
+                    for (int t = 0; t < 9; ++t) push_f64(sl + t, (double)D[t]);
                 }
             }
             if (elected && s > 0) factor_store_step(pg, dep, row_base, prev_q0, prev_n);
             // every warp of this group passed the bar.sync of this step, i.e. is done with its
             // step s-G: release the pushed-pivot ring entries of that step
             if (elected && ext_prev_end >= 0) ctl->ext_consumed = ext_prev_end;
-            if (on && (!(det != 0.0) || isinf(det) || isnan(det))) atomicMin(bad_row, ri0.x);
+            if (on && (!(det != AT(0)) || isinf(det) || isnan(det))) atomicMin(bad_row, ri0.x);
             ext_prev_end = ext_end;
             st += G;
             if (st >= S) { st -= S; par ^= 1u; }
@@ -340,11 +344,12 @@ ilu0_factor_pipe_kernel(FactorPipeDev pg, int* bad_row, int* err)
 // inv(D_j) (the factorisation's own three fused multiply-adds per element), a diagonal block
 // becomes row c of inv(D_j), an upper block is A's.  Element [c][e] goes to dst8[b] + c*stride[b] + e.
 // PART 0: everything, 1: only the blocks copied from A, 2: only the pivots
-template <bool LOWER, int PART>
+// TA: type A is stored in, AT: arithmetic type of the product.
+template <bool LOWER, int PART, class TA, class AT>
 __global__ void __launch_bounds__(256)
 repack_pipe2_kernel(size_t nval, const int* __restrict__ src, const unsigned* __restrict__ dst8,
                     const int* __restrict__ stride, const int* __restrict__ colidx, const int* __restrict__ diag,
-                    const int* __restrict__ fpos, const double* __restrict__ A, const double* __restrict__ fout,
+                    const int* __restrict__ fpos, const TA* __restrict__ A, const double* __restrict__ fout,
                     double* __restrict__ bufd)
 {
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < nval * 3; t += (size_t)gridDim.x * blockDim.x) {
@@ -360,17 +365,17 @@ repack_pipe2_kernel(size_t nval, const int* __restrict__ src, const unsigned* __
             const double* d = fout + (size_t)fpos[j] * kFEntry + c * 3;
             o[0] = d[0]; o[1] = d[1]; o[2] = d[2];
         } else {
-            const double* a = A + (size_t)k * 9 + c * 3;
+            const TA* a = A + (size_t)k * 9 + c * 3;
             if (LOWER) {
                 const double* d = fout + (size_t)fpos[j] * kFEntry;
-                const double a0 = a[0], a1 = a[1], a2 = a[2];
+                const AT a0 = (AT)a[0], a1 = (AT)a[1], a2 = (AT)a[2];
 #pragma unroll
                 for (int e = 0; e < 3; ++e) {
-                    double sacc = 0.0;
-                    sacc = fma(a0, d[e], sacc); sacc = fma(a1, d[3 + e], sacc); sacc = fma(a2, d[6 + e], sacc);
-                    o[e] = sacc;
+                    AT sacc = AT(0);
+                    sacc = fma(a0, (AT)d[e], sacc); sacc = fma(a1, (AT)d[3 + e], sacc); sacc = fma(a2, (AT)d[6 + e], sacc);
+                    o[e] = (double)sacc;
                 }
-            } else { o[0] = a[0]; o[1] = a[1]; o[2] = a[2]; }
+            } else { o[0] = (double)a[0]; o[1] = (double)a[1]; o[2] = (double)a[2]; }
         }
         double* dst = bufd + (size_t)dst8[b] + (size_t)c * stride[b];
         dst[0] = o[0]; dst[1] = o[1]; dst[2] = o[2];
@@ -379,6 +384,7 @@ repack_pipe2_kernel(size_t nval, const int* __restrict__ src, const unsigned* __
 
 // BCRS factor array on demand (opmgpu_ilu0_get_factors): in place on a copy of A.  One thread
 // per (row, block row c).
+template <class AT>
 __global__ void __launch_bounds__(256)
 materialise_lu_kernel(int N, const int* __restrict__ rowptr, const int* __restrict__ colidx,
                       const int* __restrict__ fpos, const double* __restrict__ fout, double* lu)
@@ -393,12 +399,12 @@ materialise_lu_kernel(int N, const int* __restrict__ rowptr, const int* __restri
         const double* d = fout + (size_t)fpos[j] * kFEntry;
         if (j == i) { a[0] = d[c * 3]; a[1] = d[c * 3 + 1]; a[2] = d[c * 3 + 2]; }
         else {
-            const double a0 = a[0], a1 = a[1], a2 = a[2];
+            const AT a0 = (AT)a[0], a1 = (AT)a[1], a2 = (AT)a[2];
 #pragma unroll
             for (int e = 0; e < 3; ++e) {
-                double sacc = 0.0;
-                sacc = fma(a0, d[e], sacc); sacc = fma(a1, d[3 + e], sacc); sacc = fma(a2, d[6 + e], sacc);
-                a[e] = sacc;
+                AT sacc = AT(0);
+                sacc = fma(a0, (AT)d[e], sacc); sacc = fma(a1, (AT)d[3 + e], sacc); sacc = fma(a2, (AT)d[6 + e], sacc);
+                a[e] = (double)sacc;
             }
         }
     }

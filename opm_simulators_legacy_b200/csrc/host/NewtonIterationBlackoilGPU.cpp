@@ -203,6 +203,10 @@ NewtonIterationBlackoilGPU::computeNewtonIncrement(const LinearisedBlackoilResid
     for (int p = 0; p < 3; ++p) b.insert(b.end(), eqs[p].val.begin(), eqs[p].val.end());
     SolutionVector dx((size_t)3 * N, 0.0);
     const double scale[3] = {residual.matbalscale[0], residual.matbalscale[1], residual.matbalscale[2]};
+    // the reference's dispatcher (...Interleaved.cpp:467-487): the float instance when the residual asks
+    // for it (restarted GMRES exists for the double instance only; that combination stays in double)
+    if (opmgpu_set_precision(handle_, residual.singlePrecision && !parameters_.newton_use_gmres) != OPMGPU_OK)
+        throw std::runtime_error(opmgpu_last_error(handle_));
     const int rc = opmgpu_solve_from_csc_blocks(handle_, N, blocks, scale, b.data(), dx.data(), &parameters_, &last_);
     iterations_ = last_.iterations;             // before any throw
     switch (rc) {

@@ -1,7 +1,13 @@
 // Device code of the B200-native Newton-step linear solver (sm_100a).
 //
-// All kernels are FP64 and HBM-bound (SpMV: 18 flop per 76 B); none uses tensor cores --
-// 3x3 blocks are not a dense contraction (BASELINE.json north_star).  Arithmetic order inside
+// All kernels are HBM-bound (SpMV: 18 flop per 76 B in FP64); none uses tensor cores --
+// 3x3 blocks are not a dense contraction (BASELINE.json north_star).  Every kernel that does
+// arithmetic is a template on the scalar type T: double is the reference's Impl<3,double>, float its
+// Impl<3,float> (NewtonIterationBlackoilInterleaved.cpp:478-480, selected by
+// LinearisedBlackoilResidual::singlePrecision).  In the float instance the matrix values and all
+// vectors are stored as float; the ILU0 factors, the sweep records and the scalar block keep
+// their 8-byte containers (every value in them is a float widened exactly), so the layouts the host
+// analysis produces are the same for both instances.  Arithmetic order inside
 // a block row follows the reference's dune-istl loops so that SpMV, the ILU0 factors and the
 // ILU0 sweeps are bit-identical to the CPU oracle: every `y +-= a*x` is one fma(), nothing
 // else is contracted (the file is compiled with -fmad=false).
@@ -68,15 +74,16 @@ struct ReduceWs {
 };
 constexpr int kMaxRedBlocks = 2048;
 
-__device__ __forceinline__ double warp_sum(double v)
+template <class T>
+__device__ __forceinline__ T warp_sum(T v)
 {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
     return v;
 }
 
-template <int NRED>
-__device__ __forceinline__ void block_sum(double (&v)[NRED], double* smem /*[NRED*32]*/)
+template <int NRED, class T>
+__device__ __forceinline__ void block_sum(T (&v)[NRED], T* smem /*[NRED*32]*/)
 {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
 #pragma unroll
@@ -88,23 +95,24 @@ __device__ __forceinline__ void block_sum(double (&v)[NRED], double* smem /*[NRE
     if (wid == 0) {
 #pragma unroll
         for (int r = 0; r < NRED; ++r) {
-            double t = (lane < nw) ? smem[r * 32 + lane] : 0.0;
+            T t = (lane < nw) ? smem[r * 32 + lane] : T(0);
             v[r] = warp_sum(t);
         }
     }
     __syncthreads();
 }
 
-// Finaliser hook: called by thread 0 of the last block with the NRED totals.
-template <int NRED, class Fin>
-__device__ __forceinline__ void grid_reduce(double (&v)[NRED], ReduceWs ws, Fin fin)
+// Finaliser hook: called by thread 0 of the last block with the NRED totals.  (The per-block
+// partials travel through 8-byte slots whatever T is.)
+template <int NRED, class T, class Fin>
+__device__ __forceinline__ void grid_reduce(T (&v)[NRED], ReduceWs ws, Fin fin)
 {
-    __shared__ double red_smem[NRED * 32];
+    __shared__ T red_smem[NRED * 32];
     __shared__ bool is_last;
-    block_sum<NRED>(v, red_smem);
+    block_sum<NRED, T>(v, red_smem);
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int r = 0; r < NRED; ++r) ws.partials[r * kMaxRedBlocks + blockIdx.x] = v[r];
+        for (int r = 0; r < NRED; ++r) ws.partials[r * kMaxRedBlocks + blockIdx.x] = (double)v[r];
         __threadfence();
         const unsigned t = atomicInc(ws.ticket, gridDim.x - 1);
         is_last = (t == gridDim.x - 1);
@@ -112,14 +120,14 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NRED], ReduceWs ws, Fin 
     __syncthreads();
     if (is_last) {
         __threadfence();
-        double acc[NRED];
+        T acc[NRED];
 #pragma unroll
         for (int r = 0; r < NRED; ++r) {
-            acc[r] = 0.0;
+            acc[r] = T(0);
             for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x)
-                acc[r] += __ldcg(&ws.partials[r * kMaxRedBlocks + b]);
+                acc[r] += (T)__ldcg(&ws.partials[r * kMaxRedBlocks + b]);
         }
-        block_sum<NRED>(acc, red_smem);
+        block_sum<NRED, T>(acc, red_smem);
         if (threadIdx.x == 0) fin(acc);
     }
 }
@@ -130,20 +138,20 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NRED], ReduceWs ws, Fin 
 // blocks visited in ascending column order.  MODE 0: plain.  MODE 1: also S[S_H] = w1.y.
 // MODE 2: also S[S_TR] = y.w1, S[S_TT] = y.y.  (fused dot epilogues of BiCGStab)
 // ------------------------------------------------------------------------------------------
-template <int MODE>
+template <int MODE, class T>
 __global__ void __launch_bounds__(256)
 spmv3_kernel(int N, const int* __restrict__ rowptr, const int* __restrict__ colidx,
-             const double* __restrict__ vals, const double* __restrict__ x,
-             double* __restrict__ y, const double* __restrict__ w1, double* S, ReduceWs ws)
+             const T* __restrict__ vals, const T* __restrict__ x,
+             T* __restrict__ y, const T* __restrict__ w1, double* S, ReduceWs ws)
 {
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int row = (int)(gid / 3), c = (int)(gid - 3LL * row);
-    double acc = 0.0;
+    T acc = T(0);
     if (row < N) {
         const int kb = __ldg(rowptr + row), ke = __ldg(rowptr + row + 1);
         for (int k = kb; k < ke; ++k) {
-            const double* a = vals + (size_t)k * kBB + c * kBS;
-            const double* xj = x + (size_t)__ldg(colidx + k) * kBS;
+            const T* a = vals + (size_t)k * kBB + c * kBS;
+            const T* xj = x + (size_t)__ldg(colidx + k) * kBS;
             acc = fma(__ldcs(a + 0), xj[0], acc);
             acc = fma(__ldcs(a + 1), xj[1], acc);
             acc = fma(__ldcs(a + 2), xj[2], acc);
@@ -151,11 +159,11 @@ spmv3_kernel(int N, const int* __restrict__ rowptr, const int* __restrict__ coli
         y[gid] = acc;
     }
     if (MODE == 1) {
-        double v[1] = { row < N ? w1[gid] * acc : 0.0 };
-        grid_reduce<1>(v, ws, [=](double (&t)[1]) { S[S_H] = t[0]; });
+        T v[1] = { row < N ? w1[gid] * acc : T(0) };
+        grid_reduce<1, T>(v, ws, [=](T (&t)[1]) { S[S_H] = t[0]; });
     } else if (MODE == 2) {
-        double v[2] = { row < N ? acc * w1[gid] : 0.0, row < N ? acc * acc : 0.0 };
-        grid_reduce<2>(v, ws, [=](double (&t)[2]) { S[S_TR] = t[0]; S[S_TT] = t[1]; });
+        T v[2] = { row < N ? acc * w1[gid] : T(0), row < N ? acc * acc : T(0) };
+        grid_reduce<2, T>(v, ws, [=](T (&t)[2]) { S[S_TR] = t[0]; S[S_TT] = t[1]; });
     }
 }
 
@@ -164,13 +172,14 @@ spmv3_kernel(int N, const int* __restrict__ rowptr, const int* __restrict__ coli
 // p.axpy(-omega,v); p*=beta; p+=r   /   x.axpy(alpha,y); r.axpy(-alpha,v)).
 // ------------------------------------------------------------------------------------------
 // S[S_NRM2] = S[S_RHO_NEW] = r.r ; recurrences reset (rho = alpha = omega = 1)
+template <class T>
 __global__ void __launch_bounds__(256)
-bicg_init_kernel(size_t n, const double* __restrict__ r, double* S, ReduceWs ws, HostBox hb)
+bicg_init_kernel(size_t n, const T* __restrict__ r, double* S, ReduceWs ws, HostBox hb)
 {
-    double v[1] = {0.0};
+    T v[1] = {T(0)};
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         v[0] = fma(r[i], r[i], v[0]);
-    grid_reduce<1>(v, ws, [=](double (&t)[1]) {
+    grid_reduce<1, T>(v, ws, [=](T (&t)[1]) {
         S[S_NRM2] = t[0]; S[S_RHO_NEW] = t[0];
         S[S_RHO_OLD] = 1.0; S[S_ALPHA] = 1.0; S[S_OMEGA] = 1.0;
         S[S_ERRW] = *reinterpret_cast<const volatile int*>(hb.derr) != 0 ? 1.0 : 0.0;
@@ -181,39 +190,41 @@ bicg_init_kernel(size_t n, const double* __restrict__ r, double* S, ReduceWs ws,
 // p = r + beta (p - omega v),  beta = (rho_new/rho)(alpha/omega)
 // lpos != nullptr: p is also written in the lower sweep's program order (row r -> position
 // lpos[r]), which is what the next preconditioner application streams as its right-hand side
+template <class T>
 __global__ void __launch_bounds__(256)
-bicg_update_p_kernel(size_t n, double* __restrict__ p, const double* __restrict__ r,
-                     const double* __restrict__ v, const double* __restrict__ S,
+bicg_update_p_kernel(size_t n, T* __restrict__ p, const T* __restrict__ r,
+                     const T* __restrict__ v, const double* __restrict__ S,
                      const int* __restrict__ lpos, double* __restrict__ pperm)
 {
-    const double omega = S[S_OMEGA];
-    const double beta = (S[S_RHO_NEW] / S[S_RHO_OLD]) * (S[S_ALPHA] / omega);
+    const T omega = (T)S[S_OMEGA];
+    const T beta = ((T)S[S_RHO_NEW] / (T)S[S_RHO_OLD]) * ((T)S[S_ALPHA] / omega);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        double pq = fma(-omega, v[i], p[i]);
+        T pq = fma(-omega, v[i], p[i]);
         pq *= beta;
-        const double pn = pq + r[i];
+        const T pn = pq + r[i];
         p[i] = pn;
-        if (lpos) { const size_t row = i / 3; pperm[(size_t)lpos[row] * 3 + (i - row * 3)] = pn; }
+        if (lpos) { const size_t row = i / 3; pperm[(size_t)lpos[row] * 3 + (i - row * 3)] = (double)pn; }
     }
 }
 
 // alpha = rho_new / h ; x += alpha y ; r -= alpha v ; S[S_NRM2] = r.r
+template <class T>
 __global__ void __launch_bounds__(256)
-bicg_update1_kernel(size_t n, double* __restrict__ x, double* __restrict__ r,
-                    const double* __restrict__ y, const double* __restrict__ v, double* S, ReduceWs ws, HostBox hb,
+bicg_update1_kernel(size_t n, T* __restrict__ x, T* __restrict__ r,
+                    const T* __restrict__ y, const T* __restrict__ v, double* S, ReduceWs ws, HostBox hb,
                     const int* __restrict__ lpos, double* __restrict__ rperm)
 {
-    const double hdot = S[S_H];
-    const double alpha = S[S_RHO_NEW] / hdot;
-    double s[1] = {0.0};
+    const T hdot = (T)S[S_H];
+    const T alpha = (T)S[S_RHO_NEW] / hdot;
+    T s[1] = {T(0)};
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         x[i] = fma(alpha, y[i], x[i]);
-        const double ri = fma(-alpha, v[i], r[i]);
+        const T ri = fma(-alpha, v[i], r[i]);
         r[i] = ri;
-        if (lpos) { const size_t row = i / 3; rperm[(size_t)lpos[row] * 3 + (i - row * 3)] = ri; }     // see bicg_update_p_kernel
+        if (lpos) { const size_t row = i / 3; rperm[(size_t)lpos[row] * 3 + (i - row * 3)] = (double)ri; }     // see bicg_update_p_kernel
         s[0] = fma(ri, ri, s[0]);
     }
-    grid_reduce<1>(s, ws, [=](double (&t)[1]) {
+    grid_reduce<1, T>(s, ws, [=](T (&t)[1]) {
         S[S_NRM2] = t[0]; S[S_ALPHA] = alpha;
         S[S_ERRW] = *reinterpret_cast<const volatile int*>(hb.derr) != 0 ? 1.0 : 0.0;
         if (hb.hS) { hb.hS[S_NRM2] = t[0]; hb.hS[S_H] = hdot; hostbox_publish(hb); }
@@ -221,21 +232,22 @@ bicg_update1_kernel(size_t n, double* __restrict__ x, double* __restrict__ r,
 }
 
 // omega = (t.r)/(t.t) ; x += omega y ; r -= omega t ; S[S_NRM2] = r.r ; rho <- rho_new ; rho_new = rt.r
+template <class T>
 __global__ void __launch_bounds__(256)
-bicg_update2_kernel(size_t n, double* __restrict__ x, double* __restrict__ r,
-                    const double* __restrict__ y, const double* __restrict__ t,
-                    const double* __restrict__ rt, double* S, ReduceWs ws, HostBox hb)
+bicg_update2_kernel(size_t n, T* __restrict__ x, T* __restrict__ r,
+                    const T* __restrict__ y, const T* __restrict__ t,
+                    const T* __restrict__ rt, double* S, ReduceWs ws, HostBox hb)
 {
-    const double omega = S[S_TR] / S[S_TT];
-    double s[2] = {0.0, 0.0};
+    const T omega = (T)S[S_TR] / (T)S[S_TT];
+    T s[2] = {T(0), T(0)};
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         x[i] = fma(omega, y[i], x[i]);
-        const double ri = fma(-omega, t[i], r[i]);
+        const T ri = fma(-omega, t[i], r[i]);
         r[i] = ri;
         s[0] = fma(ri, ri, s[0]);
         s[1] = fma(rt[i], ri, s[1]);
     }
-    grid_reduce<2>(s, ws, [=](double (&u)[2]) {
+    grid_reduce<2, T>(s, ws, [=](T (&u)[2]) {
         const double rho_old = S[S_RHO_NEW];
         S[S_OMEGA] = omega;
         S[S_RHO_OLD] = rho_old;
@@ -246,41 +258,44 @@ bicg_update2_kernel(size_t n, double* __restrict__ x, double* __restrict__ r,
     });
 }
 
+template <class T>
 __global__ void __launch_bounds__(256)
-dot_kernel(size_t n, const double* __restrict__ a, const double* __restrict__ b, double* S, ReduceWs ws)
+dot_kernel(size_t n, const T* __restrict__ a, const T* __restrict__ b, double* S, ReduceWs ws)
 {
-    double v[1] = {0.0};
+    T v[1] = {T(0)};
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         v[0] = fma(a[i], b[i], v[0]);
-    grid_reduce<1>(v, ws, [=](double (&t)[1]) { S[S_DOT] = t[0]; });
+    grid_reduce<1, T>(v, ws, [=](T (&t)[1]) { S[S_DOT] = t[0]; });
 }
 
 // ------------------------------------------------------------------------------------------
 // 3x3 helpers mirroring dune's DenseMatrix::{left,right}multiply and OPM's MatrixBlock inverse
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void mat3_mul(const double* A, const double* B, double* C)
+template <class T>
+__device__ __forceinline__ void mat3_mul(const T* A, const T* B, T* C)
 {
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-            double s = 0.0;
+            T s = T(0);
 #pragma unroll
             for (int k = 0; k < 3; ++k) s = fma(A[i * 3 + k], B[k * 3 + j], s);
             C[i * 3 + j] = s;
         }
 }
 
-// adjugate / determinant, same operation order as Opm::MatrixBlock<double,3,3>::invert
-__device__ __forceinline__ double mat3_invert(double* M)
+// adjugate / determinant, same operation order as Opm::MatrixBlock<T,3,3>::invert
+template <class T>
+__device__ __forceinline__ T mat3_invert(T* M)
 {
-    double A[9];
+    T A[9];
 #pragma unroll
     for (int q = 0; q < 9; ++q) A[q] = M[q];
-    const double t4 = A[0] * A[4], t6 = A[0] * A[5], t8 = A[1] * A[3];
-    const double t10 = A[2] * A[3], t12 = A[1] * A[6], t14 = A[2] * A[6];
-    const double det = (t4 * A[8] - t6 * A[7] - t8 * A[8] + t10 * A[7] + t12 * A[5] - t14 * A[4]);
-    const double t17 = 1.0 / det;
+    const T t4 = A[0] * A[4], t6 = A[0] * A[5], t8 = A[1] * A[3];
+    const T t10 = A[2] * A[3], t12 = A[1] * A[6], t14 = A[2] * A[6];
+    const T det = (t4 * A[8] - t6 * A[7] - t8 * A[8] + t10 * A[7] + t12 * A[5] - t14 * A[4]);
+    const T t17 = T(1) / det;
     M[0] = (A[4] * A[8] - A[5] * A[7]) * t17;
     M[1] = -(A[1] * A[8] - A[2] * A[7]) * t17;
     M[2] = (A[1] * A[5] - A[2] * A[4]) * t17;
@@ -298,6 +313,8 @@ __device__ __forceinline__ double mat3_invert(double* M)
 // (Opm::ParallelOverlappingILU0 ctor -> Dune::bilu0_decomposition; ISTLSolver.hpp:201-211).
 // One thread per row of the level; rows of a level are independent by construction.
 // ------------------------------------------------------------------------------------------
+// (lu: 8-byte containers; AT = arithmetic type, every stored value is an AT widened exactly)
+template <class AT>
 __global__ void __launch_bounds__(128)
 ilu0_factor_level_kernel(const int* __restrict__ lvl_rows, int begin, int end,
                          const int* __restrict__ rowptr, const int* __restrict__ colidx,
@@ -309,36 +326,36 @@ ilu0_factor_level_kernel(const int* __restrict__ lvl_rows, int begin, int end,
     const int iend = rowptr[i + 1], idiag = diag[i];
     for (int ij = rowptr[i]; ij < idiag; ++ij) {
         const int j = colidx[ij];
-        double Aij[9], Dj[9], L[9];
+        AT Aij[9], Dj[9], L[9];
         const int jd = diag[j];
 #pragma unroll
-        for (int t = 0; t < 9; ++t) { Aij[t] = lu[(size_t)ij * 9 + t]; Dj[t] = lu[(size_t)jd * 9 + t]; }
+        for (int t = 0; t < 9; ++t) { Aij[t] = (AT)lu[(size_t)ij * 9 + t]; Dj[t] = (AT)lu[(size_t)jd * 9 + t]; }
         mat3_mul(Aij, Dj, L);                                 // L_ij = A_ij * inv(A_jj)
 #pragma unroll
-        for (int t = 0; t < 9; ++t) lu[(size_t)ij * 9 + t] = L[t];
+        for (int t = 0; t < 9; ++t) lu[(size_t)ij * 9 + t] = (double)L[t];
         int jk = jd + 1, ik = ij + 1;
         const int jend = rowptr[j + 1];
         while (ik < iend && jk < jend) {
             const int ci = colidx[ik], cj = colidx[jk];
             if (ci == cj) {
-                double Ajk[9], B[9];
+                AT Ajk[9], B[9];
 #pragma unroll
-                for (int t = 0; t < 9; ++t) Ajk[t] = lu[(size_t)jk * 9 + t];
+                for (int t = 0; t < 9; ++t) Ajk[t] = (AT)lu[(size_t)jk * 9 + t];
                 mat3_mul(L, Ajk, B);                          // B = L_ij * A_jk
 #pragma unroll
-                for (int t = 0; t < 9; ++t) lu[(size_t)ik * 9 + t] -= B[t];
+                for (int t = 0; t < 9; ++t) lu[(size_t)ik * 9 + t] = (double)((AT)lu[(size_t)ik * 9 + t] - B[t]);
                 ++ik; ++jk;
             } else if (ci < cj) ++ik;
             else ++jk;
         }
     }
-    double D[9];
+    AT D[9];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) D[t] = lu[(size_t)idiag * 9 + t];
-    const double det = mat3_invert(D);
+    for (int t = 0; t < 9; ++t) D[t] = (AT)lu[(size_t)idiag * 9 + t];
+    const AT det = mat3_invert(D);
 #pragma unroll
-    for (int t = 0; t < 9; ++t) lu[(size_t)idiag * 9 + t] = D[t];
-    if (!(det != 0.0) || isinf(det) || isnan(det)) atomicMin(bad_row, i);
+    for (int t = 0; t < 9; ++t) lu[(size_t)idiag * 9 + t] = (double)D[t];
+    if (!(det != AT(0)) || isinf(det) || isnan(det)) atomicMin(bad_row, i);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -363,7 +380,8 @@ struct FactorDev {
 constexpr int kFactorSimpleDev = 1 << 30;
 
 // self-validating 9-double slot written by another CTA (each double is one atomic 8-byte store)
-__device__ __forceinline__ bool factor_poll_slot(const double* slot, double (&d)[9], int* err)
+template <class AT>
+__device__ __forceinline__ bool factor_poll_slot(const double* slot, AT (&d)[9], int* err)
 {
     const long long* s = reinterpret_cast<const long long*>(slot);
     unsigned spins = 0;
@@ -377,7 +395,7 @@ __device__ __forceinline__ bool factor_poll_slot(const double* slot, double (&d)
         }
         if (ok) {
 #pragma unroll
-            for (int t = 0; t < 9; ++t) d[t] = __longlong_as_double(v[t]);
+            for (int t = 0; t < 9; ++t) d[t] = (AT)__longlong_as_double(v[t]);
             return true;
         }
         if (++spins > (1u << 22)) { atomicExch(err, 6); return false; }
@@ -391,10 +409,11 @@ __device__ __forceinline__ int ld_acquire_gpu_f(const int* p)
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void load9(double (&d)[9], const double* p, bool bypass_l1)
+template <class AT>
+__device__ __forceinline__ void load9(AT (&d)[9], const double* p, bool bypass_l1)
 {
 #pragma unroll
-    for (int t = 0; t < 9; ++t) d[t] = bypass_l1 ? __ldcg(p + t) : p[t];
+    for (int t = 0; t < 9; ++t) d[t] = (AT)(bypass_l1 ? __ldcg(p + t) : p[t]);
 }
 __device__ __forceinline__ bool factor_wait_row(const int* flags, int j, int epoch, int* err)
 {
@@ -407,11 +426,12 @@ __device__ __forceinline__ bool factor_wait_row(const int* flags, int j, int epo
 }
 
 // row c of C = A * B where the thread holds row c of A (dune's accumulation order per entry)
-__device__ __forceinline__ void mat3_row_mul(const double (&Arow)[3], const double (&B)[9], double (&Crow)[3])
+template <class AT>
+__device__ __forceinline__ void mat3_row_mul(const AT (&Arow)[3], const AT (&B)[9], AT (&Crow)[3])
 {
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-        double s = 0.0;
+        AT s = AT(0);
 #pragma unroll
         for (int k = 0; k < 3; ++k) s = fma(Arow[k], B[k * 3 + j], s);
         Crow[j] = s;
@@ -423,6 +443,7 @@ __device__ __forceinline__ void mat3_row_mul(const double (&Arow)[3], const doub
 constexpr int kFactorThreads = 256;
 constexpr int kFactorRowsPerPass = (kFactorThreads / 32) * 10;
 
+template <class AT>
 __global__ void __launch_bounds__(kFactorThreads)
 ilu0_factor_tile_kernel(FactorDev pg, double* lu, int* flags, int epoch, int* bad_row, int* err)
 {
@@ -458,13 +479,13 @@ ilu0_factor_tile_kernel(FactorDev pg, double* lu, int* flags, int epoch, int* ba
             if (on) fr = pg.frow[q];
             const int i = fr.x, idiag = fr.y, e0 = fr.z, n = fr.w & ~kFactorSimpleDev;
             const bool simple = on && (fr.w & kFactorSimpleDev);
-            double Drow[3] = {0.0, 0.0, 0.0};
+            AT Drow[3] = {AT(0), AT(0), AT(0)};
             int rearm[3] = {-1, -1, -1};
             if (simple) {
                 // stencil rows: every address is known now, issue all loads before any arithmetic
                 int4 ea[3];
                 int jk0[3];
-                double Arow[3][3], Dj[3][9], Ajk[3][9];
+                AT Arow[3][3], Dj[3][9], Ajk[3][9];
 #pragma unroll
                 for (int k = 0; k < 3; ++k)
                     if (k < n) {
@@ -473,12 +494,12 @@ ilu0_factor_tile_kernel(FactorDev pg, double* lu, int* flags, int epoch, int* ba
                         jk0[k] = eb.x; rearm[k] = eb.w;
                     }
 #pragma unroll
-                for (int t = 0; t < 3; ++t) Drow[t] = lu[(size_t)idiag * 9 + c * 3 + t];
+                for (int t = 0; t < 3; ++t) Drow[t] = (AT)lu[(size_t)idiag * 9 + c * 3 + t];
 #pragma unroll
                 for (int k = 0; k < 3; ++k)
                     if (k < n) {
 #pragma unroll
-                        for (int t = 0; t < 3; ++t) Arow[k][t] = lu[(size_t)ea[k].x * 9 + c * 3 + t];
+                        for (int t = 0; t < 3; ++t) Arow[k][t] = (AT)lu[(size_t)ea[k].x * 9 + c * 3 + t];
                     }
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
@@ -499,10 +520,10 @@ ilu0_factor_tile_kernel(FactorDev pg, double* lu, int* flags, int epoch, int* ba
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
                     if (k < n) {
-                        double Lrow[3], Brow[3];
+                        AT Lrow[3], Brow[3];
                         mat3_row_mul(Arow[k], Dj[k], Lrow);                 // L_ij = A_ij * inv(A_jj)
 #pragma unroll
-                        for (int t = 0; t < 3; ++t) lu[(size_t)ea[k].x * 9 + c * 3 + t] = Lrow[t];
+                        for (int t = 0; t < 3; ++t) lu[(size_t)ea[k].x * 9 + c * 3 + t] = (double)Lrow[t];
                         if (ea[k].w) {
                             mat3_row_mul(Lrow, Ajk[k], Brow);               // A_ii -= L_ij * A_ji
 #pragma unroll
@@ -512,22 +533,22 @@ ilu0_factor_tile_kernel(FactorDev pg, double* lu, int* flags, int epoch, int* ba
                 }
             } else if (on && c == 0) {
                 // general rows (more than three lower blocks, fill outside the diagonal): one thread
-                double D[9];
+                AT D[9];
                 load9(D, lu + (size_t)idiag * 9, false);
                 for (int b = e0; b < e0 + n; ++b) {
                     const int4 ea = pg.fent[2 * b], eb = pg.fent[2 * b + 1];
                     const int ij = ea.x;
                     const bool ext = (ea.z & kExtBitDev) != 0;
                     if (ext) factor_wait_row(flags, ea.z & ~kExtBitDev, epoch, err);
-                    double Aij[9], Dj[9], L[9];
+                    AT Aij[9], Dj[9], L[9];
                     load9(Aij, lu + (size_t)ij * 9, false);
                     load9(Dj, lu + (size_t)ea.y * 9, ext);
                     mat3_mul(Aij, Dj, L);
 #pragma unroll
-                    for (int t = 0; t < 9; ++t) lu[(size_t)ij * 9 + t] = L[t];
+                    for (int t = 0; t < 9; ++t) lu[(size_t)ij * 9 + t] = (double)L[t];
                     for (int pp = eb.z; pp < eb.z + ea.w; ++pp) {
                         const int jk = pg.pair_jk[pp], ik = pg.pair_ik[pp];
-                        double Ajk[9], B[9];
+                        AT Ajk[9], B[9];
                         load9(Ajk, lu + (size_t)jk * 9, ext);
                         mat3_mul(L, Ajk, B);
                         if (ik == idiag) {
@@ -535,33 +556,33 @@ ilu0_factor_tile_kernel(FactorDev pg, double* lu, int* flags, int epoch, int* ba
                             for (int t = 0; t < 9; ++t) D[t] -= B[t];
                         } else {
 #pragma unroll
-                            for (int t = 0; t < 9; ++t) lu[(size_t)ik * 9 + t] -= B[t];
+                            for (int t = 0; t < 9; ++t) lu[(size_t)ik * 9 + t] = (double)((AT)lu[(size_t)ik * 9 + t] - B[t]);
                         }
                     }
                 }
-                const double det = mat3_invert(D);
+                const AT det = mat3_invert(D);
 #pragma unroll
-                for (int t = 0; t < 9; ++t) lu[(size_t)idiag * 9 + t] = D[t];
-                if (!(det != 0.0) || isinf(det) || isnan(det)) atomicMin(bad_row, i);
+                for (int t = 0; t < 9; ++t) lu[(size_t)idiag * 9 + t] = (double)D[t];
+                if (!(det != AT(0)) || isinf(det) || isnan(det)) atomicMin(bad_row, i);
             }
             // simple rows: gather the whole pivot block inside the warp, invert, store own row
-            double D[9];
+            AT D[9];
 #pragma unroll
             for (int m = 0; m < 3; ++m)
 #pragma unroll
                 for (int t = 0; t < 3; ++t) D[m * 3 + t] = __shfl_sync(0xffffffffu, Drow[t], base + m);
             if (simple) {
-                const double det = mat3_invert(D);
-                const double o0 = c == 0 ? D[0] : (c == 1 ? D[3] : D[6]);
-                const double o1 = c == 0 ? D[1] : (c == 1 ? D[4] : D[7]);
-                const double o2 = c == 0 ? D[2] : (c == 1 ? D[5] : D[8]);
+                const AT det = mat3_invert(D);
+                const double o0 = (double)(c == 0 ? D[0] : (c == 1 ? D[3] : D[6]));
+                const double o1 = (double)(c == 0 ? D[1] : (c == 1 ? D[4] : D[7]));
+                const double o2 = (double)(c == 0 ? D[2] : (c == 1 ? D[5] : D[8]));
                 double* dst = lu + (size_t)idiag * 9 + c * 3;
                 dst[0] = o0; dst[1] = o1; dst[2] = o2;
                 for (int t = pg.fpush_ptr[q]; t < pg.fpush_ptr[q + 1]; ++t) {      // push the pivot to other CTAs
                     double* sl = pg.fslots + (size_t)pg.fpush_slot[t] * 9 + c * 3;
                     __stcg(sl, o0); __stcg(sl + 1, o1); __stcg(sl + 2, o2);
                 }
-                if (c == 0 && (!(det != 0.0) || isinf(det) || isnan(det))) atomicMin(bad_row, i);
+                if (c == 0 && (!(det != AT(0)) || isinf(det) || isnan(det))) atomicMin(bad_row, i);
             }
             __syncwarp();
             if (simple && c == 0) {                                          // re-arm the slots this row consumed
@@ -647,11 +668,12 @@ __device__ __forceinline__ void st_release_gpu(int* p, int v)
 
 constexpr unsigned kSpinLimit = 1u << 22;
 
-template <bool LOWER>
+template <bool LOWER, class T>
 __global__ void __launch_bounds__(256)
-ilu0_sweep_kernel(SweepDev pg, const double* __restrict__ rhs, double* work, double* out,
-                  double w, int scale, int* flags, int epoch, int* err)
+ilu0_sweep_kernel(SweepDev pg, const T* __restrict__ rhs, T* work, T* out,
+                  double w_, int scale, int* flags, int epoch, int* err)
 {
+    const T w = (T)w_;
     // LOWER: rhs = d, work = yL (written), out unused.
     // UPPER: rhs = yL, work = vU (unscaled, written, read by dependants), out = w * vU.
     const int s_begin = pg.cta_step_ptr[blockIdx.x], s_end = pg.cta_step_ptr[blockIdx.x + 1];
@@ -659,12 +681,12 @@ ilu0_sweep_kernel(SweepDev pg, const double* __restrict__ rhs, double* work, dou
         const int q0 = pg.step_row_ptr[s], q1 = pg.step_row_ptr[s + 1];
         for (int q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
             const int row = pg.prow[q];
-            double r0 = rhs[(size_t)row * 3], r1 = rhs[(size_t)row * 3 + 1], r2 = rhs[(size_t)row * 3 + 2];
+            T r0 = rhs[(size_t)row * 3], r1 = rhs[(size_t)row * 3 + 1], r2 = rhs[(size_t)row * 3 + 2];
             const int b0 = pg.pblk_ptr[q], b1 = pg.pblk_ptr[q + 1];
             for (int b = b0; b < b1; ++b) {
                 const int c = pg.pcol[b];
                 const int j = c & ~kExtBitDev;
-                double y0, y1, y2;
+                T y0, y1, y2;
                 if (c & kExtBitDev) {
                     unsigned spins = 0;
                     while (ld_acquire_gpu(flags + j) != epoch) {
@@ -676,16 +698,16 @@ ilu0_sweep_kernel(SweepDev pg, const double* __restrict__ rhs, double* work, dou
                     y0 = work[(size_t)j * 3]; y1 = work[(size_t)j * 3 + 1]; y2 = work[(size_t)j * 3 + 2];
                 }
                 const double* a = pg.pval + (size_t)b * 9;
-                r0 = fma(-a[0], y0, r0); r0 = fma(-a[1], y1, r0); r0 = fma(-a[2], y2, r0);
-                r1 = fma(-a[3], y0, r1); r1 = fma(-a[4], y1, r1); r1 = fma(-a[5], y2, r1);
-                r2 = fma(-a[6], y0, r2); r2 = fma(-a[7], y1, r2); r2 = fma(-a[8], y2, r2);
+                r0 = fma(-(T)a[0], y0, r0); r0 = fma(-(T)a[1], y1, r0); r0 = fma(-(T)a[2], y2, r0);
+                r1 = fma(-(T)a[3], y0, r1); r1 = fma(-(T)a[4], y1, r1); r1 = fma(-(T)a[5], y2, r1);
+                r2 = fma(-(T)a[6], y0, r2); r2 = fma(-(T)a[7], y1, r2); r2 = fma(-(T)a[8], y2, r2);
             }
             if (!LOWER) {
                 const double* di = pg.pdinv + (size_t)q * 9;
-                double v0 = 0.0, v1 = 0.0, v2 = 0.0;
-                v0 = fma(di[0], r0, v0); v0 = fma(di[1], r1, v0); v0 = fma(di[2], r2, v0);
-                v1 = fma(di[3], r0, v1); v1 = fma(di[4], r1, v1); v1 = fma(di[5], r2, v1);
-                v2 = fma(di[6], r0, v2); v2 = fma(di[7], r1, v2); v2 = fma(di[8], r2, v2);
+                T v0 = T(0), v1 = T(0), v2 = T(0);
+                v0 = fma((T)di[0], r0, v0); v0 = fma((T)di[1], r1, v0); v0 = fma((T)di[2], r2, v0);
+                v1 = fma((T)di[3], r0, v1); v1 = fma((T)di[4], r1, v1); v1 = fma((T)di[5], r2, v1);
+                v2 = fma((T)di[6], r0, v2); v2 = fma((T)di[7], r1, v2); v2 = fma((T)di[8], r2, v2);
                 r0 = v0; r1 = v1; r2 = v2;
                 if (scale) { v0 *= w; v1 *= w; v2 *= w; }
                 out[(size_t)row * 3] = v0; out[(size_t)row * 3 + 1] = v1; out[(size_t)row * 3 + 2] = v2;
@@ -728,38 +750,50 @@ build_gather_map_kernel(int N, int q, const int* __restrict__ colptr, const int*
 }
 
 // one thread per output double: vals[slot][p1][p2] = cscval[map] * scale[p1]  (0 if absent)
+// (T = float: the scaled value is rounded once, as the assignment to the reference's float matrix does)
+template <class T>
 __global__ void __launch_bounds__(256)
 interleave_gather_kernel(size_t nvals, const long long* __restrict__ map9,
                          const double* __restrict__ cscval, double s0, double s1, double s2,
-                         double* __restrict__ vals)
+                         T* __restrict__ vals)
 {
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= nvals) return;
     const long long m = map9[e];
     const int p1 = (int)((e % 9) / 3);
     const double sc = p1 == 0 ? s0 : (p1 == 1 ? s1 : s2);
-    vals[e] = m >= 0 ? cscval[m] * sc : 0.0;
+    vals[e] = (T)(m >= 0 ? cscval[m] * sc : 0.0);
 }
 
 // a8  rhs interleave (+ scaling) and solution de-interleave (...Interleaved.cpp:263-269, 279-283)
+template <class T>
 __global__ void __launch_bounds__(256)
 interleave_rhs_kernel(int N, const double* __restrict__ b_eqmajor, double s0, double s1, double s2,
-                      double* __restrict__ b_cellmajor)
+                      T* __restrict__ b_cellmajor)
 {
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= (size_t)N * 3) return;
     const size_t i = e / 3;
     const int p = (int)(e - i * 3);
     const double sc = p == 0 ? s0 : (p == 1 ? s1 : s2);
-    b_cellmajor[e] = b_eqmajor[(size_t)p * N + i] * sc;
+    b_cellmajor[e] = (T)(b_eqmajor[(size_t)p * N + i] * sc);
 }
+template <class T>
 __global__ void __launch_bounds__(256)
-deinterleave_x_kernel(int N, const double* __restrict__ x_cellmajor, double* __restrict__ dx_varmajor)
+deinterleave_x_kernel(int N, const T* __restrict__ x_cellmajor, double* __restrict__ dx_varmajor)
 {
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= (size_t)N * 3) return;
     const size_t p = e / N, i = e - p * N;
-    dx_varmajor[e] = x_cellmajor[i * 3 + p];
+    dx_varmajor[e] = (double)x_cellmajor[i * 3 + p];
+}
+
+// plain conversions between the caller's doubles and the instance's scalar type
+template <class TI, class TO>
+__global__ void __launch_bounds__(256)
+convert_kernel(size_t n, const TI* __restrict__ in, TO* __restrict__ out)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = (TO)in[i];
 }
 
 }  // namespace opmgpu

@@ -102,6 +102,13 @@ void multi_destroy(MultiSolver* m)
     delete m;
 }
 
+int multi_set_precision(MultiSolver* m, int single_precision, std::string& err)
+{
+    for (int g = 0; g < m->G; ++g)
+        if (int rc = opmgpu_set_precision(m->child[g], single_precision)) { err = opmgpu_last_error(m->child[g]); return rc; }
+    return OPMGPU_OK;
+}
+
 int multi_set_pattern(MultiSolver* m, int N, int nnzb, const int* rowptr, const int* colidx, std::string& err)
 {
     if (N < m->G) { err = "fewer block rows than GPUs"; return OPMGPU_BAD_ARGUMENT; }

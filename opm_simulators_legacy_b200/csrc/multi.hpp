@@ -18,6 +18,8 @@ int multi_solve_bcrs3(MultiSolver* m, const double* vals, const double* rhs, dou
 int multi_solve_from_csc_blocks(MultiSolver* m, int N, const opmgpu_csc blocks[9], const double scale[3],
                                 const double* rhs_eqmajor, double* dx_varmajor, const opmgpu_params* prm,
                                 opmgpu_result* res, std::string& err);
+// single_precision != 0: every GPU runs the reference's float instance
+int multi_set_precision(MultiSolver* m, int single_precision, std::string& err);
 // partition facts for tests / reports: axis (0 = i, 1 = j, 2 = k, -1 = contiguous row blocks), rows per GPU
 int multi_partition_info(MultiSolver* m, int* axis, long long* offsets /*[ngpus+1]*/);
 

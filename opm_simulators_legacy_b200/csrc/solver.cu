@@ -200,8 +200,14 @@ struct opmgpu_solver {
     int max_smem_optin = 0;
 
     // values and factors
-    DevArr<double> d_vals_own, d_lu;
-    const double* d_vals = nullptr;
+    // f32: the handle runs the reference's float instance (Impl<3,float>, ...Interleaved.cpp:478-480):
+    // matrix values and vectors are float arrays (the vector buffers below are then used as float
+    // arrays), factors / sweep records / scalar block keep their 8-byte containers.  The C ABI
+    // exchanges doubles either way; d_stage holds them on their way in and out.
+    bool f32 = false;
+    DevArr<double> d_vals_own, d_lu, d_stage;
+    DevArr<float> d_vals32;
+    const void* d_vals = nullptr;
 
     // vectors (3N each)
     DevArr<double> d_x, d_r, d_rt, d_p, d_v, d_t, d_y, d_yL, d_vU, d_tmp, d_tmp2;
@@ -519,6 +525,21 @@ SweepDev sweep_dev(const ProgramDevMem& d)
     return s;
 }
 
+template <class T> inline T* vec(DevArr<double>& a) { return reinterpret_cast<T*>(a.p); }
+template <class T> inline ncclDataType_t nccl_type() { return sizeof(T) == 4 ? ncclFloat : ncclDouble; }
+
+// double <-> instance scalar type, device to device
+template <class TI, class TO>
+int convert(opmgpu_handle h, size_t n, const TI* in, TO* out)
+{
+    if (!n) return 0;
+    const unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)h->sm_count * 16);
+    convert_kernel<TI, TO><<<grid, 256, 0, h->stream>>>(n, in, out);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
 int ensure_vectors(opmgpu_handle h)
 {
     const size_t n = (size_t)h->N * 3;
@@ -617,35 +638,39 @@ int set_pattern(opmgpu_handle h, int N, int nnzb, const int* rowptr, const int* 
 }
 
 // gather kernels of the distributed path
+template <class T>
 __global__ void __launch_bounds__(256)
-pack_rows_kernel(int n, const int* __restrict__ rows, const double* __restrict__ x, double* __restrict__ buf)
+pack_rows_kernel(int n, const int* __restrict__ rows, const T* __restrict__ x, T* __restrict__ buf)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n * 3) return;
     const int k = e / 3;
     buf[e] = x[(size_t)rows[k] * 3 + (e - k * 3)];
 }
+template <class T>
 __global__ void __launch_bounds__(256)
-gather_blocks_kernel(size_t nblk, const int* __restrict__ src, const double* __restrict__ vals, double* __restrict__ lu)
+gather_blocks_kernel(size_t nblk, const int* __restrict__ src, const T* __restrict__ vals, double* __restrict__ lu)
 {
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= nblk * 9) return;
     const size_t b = e / 9;
-    lu[e] = vals[(size_t)src[b] * 9 + (e - b * 9)];
+    lu[e] = (double)vals[(size_t)src[b] * 9 + (e - b * 9)];
 }
 
 // x[N_local .. N_local + n_ghost) <- the owners' rows (ncclSend/ncclRecv over NVLink)
-int halo_exchange(opmgpu_handle h, double* x)
+template <class T>
+int halo_exchange(opmgpu_handle h, T* x)
 {
     if (h->world == 1) return 0;
+    T* sendbuf = vec<T>(h->d_sendbuf);
     if (h->n_send) {
-        pack_rows_kernel<<<(h->n_send * 3 + 255) / 256, 256, 0, h->stream>>>(h->n_send, h->d_send_rows.p, x, h->d_sendbuf.p);
+        pack_rows_kernel<T><<<(h->n_send * 3 + 255) / 256, 256, 0, h->stream>>>(h->n_send, h->d_send_rows.p, x, sendbuf);
         h->launches++;
     }
     NK(g_nccl.GroupStart());
     for (int p = 0; p < h->world; ++p) {
-        if (h->send_cnt[p]) NK(g_nccl.Send(h->d_sendbuf.p + (size_t)h->send_off[p] * 3, (size_t)h->send_cnt[p] * 3, ncclDouble, p, h->comm, h->stream));
-        if (h->recv_cnt[p]) NK(g_nccl.Recv(x + ((size_t)h->N + h->recv_off[p]) * 3, (size_t)h->recv_cnt[p] * 3, ncclDouble, p, h->comm, h->stream));
+        if (h->send_cnt[p]) NK(g_nccl.Send(sendbuf + (size_t)h->send_off[p] * 3, (size_t)h->send_cnt[p] * 3, nccl_type<T>(), p, h->comm, h->stream));
+        if (h->recv_cnt[p]) NK(g_nccl.Recv(x + ((size_t)h->N + h->recv_off[p]) * 3, (size_t)h->recv_cnt[p] * 3, nccl_type<T>(), p, h->comm, h->stream));
     }
     NK(g_nccl.GroupEnd());
     return 0;
@@ -658,17 +683,19 @@ int allreduce_slots(opmgpu_handle h, int slot, int count)
     return 0;
 }
 
-int launch_spmv(opmgpu_handle h, int mode, const double* x, double* y, const double* w1)
+template <class T>
+int launch_spmv(opmgpu_handle h, int mode, const T* x, T* y, const T* w1)
 {
+    const T* vals = static_cast<const T*>(h->d_vals);
     const int* rowptr = h->world > 1 ? h->d_rowptr_full.p : h->d_rowptr.p;
     const int* colidx = h->world > 1 ? h->d_colidx_full.p : h->d_colidx.p;
     if (h->spmv_tma && (reinterpret_cast<uintptr_t>(h->d_vals) & 15) == 0) {
         const int nnzb = h->world > 1 ? h->nnzb_full : h->nnzb;
         const int ntiles = (h->N + kSpmvRows - 1) / kSpmvRows;
         const unsigned grid = (unsigned)std::min(ntiles, h->sm_count);
-        if (mode == 0) spmv3_tma_kernel<0><<<grid, kSpmvThreads, kSpmvSmemBytes, h->stream>>>(h->N, nnzb, rowptr, colidx, h->d_vals, x, y, w1, h->d_S.p, h->ws());
-        else if (mode == 1) spmv3_tma_kernel<1><<<grid, kSpmvThreads, kSpmvSmemBytes, h->stream>>>(h->N, nnzb, rowptr, colidx, h->d_vals, x, y, w1, h->d_S.p, h->ws());
-        else spmv3_tma_kernel<2><<<grid, kSpmvThreads, kSpmvSmemBytes, h->stream>>>(h->N, nnzb, rowptr, colidx, h->d_vals, x, y, w1, h->d_S.p, h->ws());
+        if (mode == 0) spmv3_tma_kernel<0, T><<<grid, kSpmvThreads, kSpmvSmemBytes, h->stream>>>(h->N, nnzb, rowptr, colidx, vals, x, y, w1, h->d_S.p, h->ws());
+        else if (mode == 1) spmv3_tma_kernel<1, T><<<grid, kSpmvThreads, kSpmvSmemBytes, h->stream>>>(h->N, nnzb, rowptr, colidx, vals, x, y, w1, h->d_S.p, h->ws());
+        else spmv3_tma_kernel<2, T><<<grid, kSpmvThreads, kSpmvSmemBytes, h->stream>>>(h->N, nnzb, rowptr, colidx, vals, x, y, w1, h->d_S.p, h->ws());
         h->launches++;
         CK(cudaGetLastError());
         return 0;
@@ -677,41 +704,43 @@ int launch_spmv(opmgpu_handle h, int mode, const double* x, double* y, const dou
     const unsigned grid = (unsigned)((threads + 255) / 256);
     if (mode != 0 && grid > kMaxRedBlocks) {
         // fused reduction epilogue has a bounded partial array: fall back to SpMV + dot kernels
-        spmv3_kernel<0><<<grid, 256, 0, h->stream>>>(h->N, rowptr, colidx, h->d_vals, x, y, nullptr, h->d_S.p, h->ws());
+        spmv3_kernel<0, T><<<grid, 256, 0, h->stream>>>(h->N, rowptr, colidx, vals, x, y, (const T*)nullptr, h->d_S.p, h->ws());
         h->launches++;
         return -100;
     }
-    if (mode == 0) spmv3_kernel<0><<<grid, 256, 0, h->stream>>>(h->N, rowptr, colidx, h->d_vals, x, y, w1, h->d_S.p, h->ws());
-    else if (mode == 1) spmv3_kernel<1><<<grid, 256, 0, h->stream>>>(h->N, rowptr, colidx, h->d_vals, x, y, w1, h->d_S.p, h->ws());
-    else spmv3_kernel<2><<<grid, 256, 0, h->stream>>>(h->N, rowptr, colidx, h->d_vals, x, y, w1, h->d_S.p, h->ws());
+    if (mode == 0) spmv3_kernel<0, T><<<grid, 256, 0, h->stream>>>(h->N, rowptr, colidx, vals, x, y, w1, h->d_S.p, h->ws());
+    else if (mode == 1) spmv3_kernel<1, T><<<grid, 256, 0, h->stream>>>(h->N, rowptr, colidx, vals, x, y, w1, h->d_S.p, h->ws());
+    else spmv3_kernel<2, T><<<grid, 256, 0, h->stream>>>(h->N, rowptr, colidx, vals, x, y, w1, h->d_S.p, h->ws());
     h->launches++;
     CK(cudaGetLastError());
     return 0;
 }
 
 // separate (non-fused) dots for systems too large for the fused epilogue
-__global__ void dot_to_slot_kernel(size_t n, const double* __restrict__ a, const double* __restrict__ b,
+template <class T>
+__global__ void dot_to_slot_kernel(size_t n, const T* __restrict__ a, const T* __restrict__ b,
                                    double* S, int slot, ReduceWs ws)
 {
-    double v[1] = {0.0};
+    T v[1] = {T(0)};
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         v[0] = fma(a[i], b[i], v[0]);
-    grid_reduce<1>(v, ws, [=](double (&t)[1]) { S[slot] = t[0]; });
+    grid_reduce<1, T>(v, ws, [=](T (&t)[1]) { S[slot] = t[0]; });
 }
 
-int spmv_with_dots(opmgpu_handle h, int mode, double* x, double* y, const double* w1)
+template <class T>
+int spmv_with_dots(opmgpu_handle h, int mode, T* x, T* y, const T* w1)
 {
-    int rc = halo_exchange(h, x);
+    int rc = halo_exchange<T>(h, x);
     if (rc) return rc;
-    rc = launch_spmv(h, mode, x, y, w1);
+    rc = launch_spmv<T>(h, mode, x, y, w1);
     if (rc == -100) {
         const size_t n = (size_t)h->N * 3;
         if (mode == 1) {
-            dot_to_slot_kernel<<<kVecBlocks, 256, 0, h->stream>>>(n, w1, y, h->d_S.p, S_H, h->ws());
+            dot_to_slot_kernel<T><<<kVecBlocks, 256, 0, h->stream>>>(n, w1, (const T*)y, h->d_S.p, S_H, h->ws());
             h->launches++;
         } else {
-            dot_to_slot_kernel<<<kVecBlocks, 256, 0, h->stream>>>(n, y, w1, h->d_S.p, S_TR, h->ws());
-            dot_to_slot_kernel<<<kVecBlocks, 256, 0, h->stream>>>(n, y, y, h->d_S.p, S_TT, h->ws());
+            dot_to_slot_kernel<T><<<kVecBlocks, 256, 0, h->stream>>>(n, (const T*)y, w1, h->d_S.p, S_TR, h->ws());
+            dot_to_slot_kernel<T><<<kVecBlocks, 256, 0, h->stream>>>(n, (const T*)y, (const T*)y, h->d_S.p, S_TT, h->ws());
             h->launches += 2;
         }
         CK(cudaGetLastError());
@@ -724,20 +753,26 @@ int spmv_with_dots(opmgpu_handle h, int mode, double* x, double* y, const double
 
 int sweep_watchdog(opmgpu_handle h);
 
-int factor(opmgpu_handle h, int* bad_row)
+// T: scalar type of the instance (matrix values are stored as T, the arithmetic is T's; the factor
+// array, the records and the pivots are 8-byte containers)
+template <class T>
+int factor_t(opmgpu_handle h, int* bad_row)
 {
     if (!h->have_values) return h->bad("no matrix values set");
+    if (h->f32 && h->use_col) return h->bad("the column-owned sweeps (OPMGPU_COL=1) exist for the double instance only");
     const size_t nv = (size_t)h->nnzb * 9;
     const bool pipe_factor = h->pipeF.valid && !h->factor_by_levels;
+    const T* vals = static_cast<const T*>(h->d_vals);
     h->lu_lazy = false;
     if (h->world > 1) {
-        gather_blocks_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, h->stream>>>((size_t)h->nnzb, h->d_lu_src.p, h->d_vals, h->d_lu.p);
+        gather_blocks_kernel<T><<<(unsigned)((nv + 255) / 256), 256, 0, h->stream>>>((size_t)h->nnzb, h->d_lu_src.p, vals, h->d_lu.p);
         h->launches++;
     } else if (!pipe_factor) {
-        CK(cudaMemcpyAsync(h->d_lu.p, h->d_vals, nv * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        if (sizeof(T) == 8) CK(cudaMemcpyAsync(h->d_lu.p, h->d_vals, nv * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        else if (int rc = convert<T, double>(h, nv, vals, h->d_lu.p)) return rc;
     }
-    // the blocks of A the ILU0 is built on (the rank's diagonal block when partitioned)
-    const double* ilu_A = h->world > 1 ? h->d_lu.p : h->d_vals;
+    // the blocks of A the ILU0 is built on (the rank's diagonal block when partitioned: 8-byte containers)
+    const bool A_in_lu = h->world > 1;
     const int big = 0x7fffffff;
     CK(cudaMemcpyAsync(h->d_bad.p, &big, sizeof(int), cudaMemcpyHostToDevice, h->stream));
     if (h->factor_by_levels) {
@@ -745,21 +780,22 @@ int factor(opmgpu_handle h, int* bad_row)
         for (size_t l = 0; l + 1 < lp.size(); ++l) {
             const int n = lp[l + 1] - lp[l];
             if (n <= 0) continue;
-            ilu0_factor_level_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(
+            ilu0_factor_level_kernel<T><<<(n + 127) / 128, 128, 0, h->stream>>>(
                 h->d_lvl_rows.p, lp[l], lp[l + 1], h->d_rowptr.p, h->d_colidx.p, h->d_diag.p, h->d_lu.p, h->d_bad.p);
             h->launches++;
         }
     } else if (pipe_factor) {
         FactorPipeDevMem& d = h->pipeF;
         const size_t e = d.nval * 3;
-        pack_factor_records_kernel<<<(unsigned)((e + 255) / 256), 256, 0, h->stream>>>(d.nval, d.val_src.p, d.val_dst8.p, ilu_A, (double*)d.buf.p);
+        if (A_in_lu) pack_factor_records_kernel<double><<<(unsigned)((e + 255) / 256), 256, 0, h->stream>>>(d.nval, d.val_src.p, d.val_dst8.p, h->d_lu.p, (double*)d.buf.p);
+        else pack_factor_records_kernel<T><<<(unsigned)((e + 255) / 256), 256, 0, h->stream>>>(d.nval, d.val_src.p, d.val_dst8.p, vals, (double*)d.buf.p);
         FactorPipeDev pg;
         pg.buf = d.buf.p; pg.cta_step_ptr = d.cta_step_ptr.p; pg.step_off16 = d.step_off16.p; pg.step_bytes = d.step_bytes.p;
         pg.cta_ext_base = d.cta_ext_base.p; pg.cta_row_base = d.cta_row_base.p; pg.ext = d.ext.p; pg.fout = d.fout.p;
         pg.stage_bytes = d.stage_bytes; pg.nstages = d.nstages;
         int* bad = h->d_bad.p; int* err = h->d_err.p;
         void* args[] = {&pg, &bad, &err};
-        CK(cudaLaunchCooperativeKernel((void*)ilu0_factor_pipe_kernel, dim3(d.P), dim3(kFThreads), args, d.smem, h->stream));
+        CK(cudaLaunchCooperativeKernel((void*)ilu0_factor_pipe_kernel<T>, dim3(d.P), dim3(kFThreads), args, d.smem, h->stream));
         h->launches += 2;
         h->lu_lazy = true;
     } else {
@@ -771,7 +807,7 @@ int factor(opmgpu_handle h, int* bad_row)
         pg.fslots = h->progL.fslots.p;
         double* lu = h->d_lu.p; int* flags = h->d_flags.p; int epoch = ++h->epoch; int* bad = h->d_bad.p; int* err = h->d_err.p;
         void* args[] = {&pg, &lu, &flags, &epoch, &bad, &err};
-        CK(cudaLaunchCooperativeKernel((void*)ilu0_factor_tile_kernel, dim3(h->progL.P), dim3(kFactorThreads), args, 0, h->stream));
+        CK(cudaLaunchCooperativeKernel((void*)ilu0_factor_tile_kernel<T>, dim3(h->progL.P), dim3(kFactorThreads), args, 0, h->stream));
         h->launches++;
     }
     CK(cudaGetLastError());
@@ -782,6 +818,7 @@ int factor(opmgpu_handle h, int* bad_row)
         const unsigned gridU = (unsigned)std::min<size_t>((c.nvalU * 3 + 255) / 256, (size_t)h->sm_count * 16);
         if (pipe_factor) {
             const FactorPipeDevMem& f = h->pipeF;
+            const double* ilu_A = A_in_lu ? h->d_lu.p : static_cast<const double*>(h->d_vals);      // (double instance only)
             if (c.nvalL) repack_col_kernel<true><<<gridL, 256, 0, h->stream>>>(c.nvalL, c.valL_src.p, c.valL_dst.p, h->d_colidx.p, f.fpos.p, ilu_A, f.fout.p, c.recL.p);
             repack_col_kernel<false><<<gridU, 256, 0, h->stream>>>(c.nvalU, c.valU_src.p, c.valU_dst.p, h->d_colidx.p, f.fpos.p, ilu_A, f.fout.p, c.recU.p);
         } else {
@@ -796,14 +833,18 @@ int factor(opmgpu_handle h, int* bad_row)
         const FactorPipeDevMem& f = h->pipeF;
         if (h->pipeL.nval) {
             const size_t e = h->pipeL.nval * 3;
-            repack_pipe2_kernel<true, 0><<<(unsigned)((e + 255) / 256), 256, 0, h->stream>>>(h->pipeL.nval, h->pipeL.val_src.p, h->pipeL.val_dst8.p,
-                h->pipeL.val_stride.p, h->d_colidx.p, h->d_diag.p, f.fpos.p, ilu_A, f.fout.p, (double*)h->pipeL.buf.p);
+            if (A_in_lu) repack_pipe2_kernel<true, 0, double, T><<<(unsigned)((e + 255) / 256), 256, 0, h->stream>>>(h->pipeL.nval, h->pipeL.val_src.p, h->pipeL.val_dst8.p,
+                h->pipeL.val_stride.p, h->d_colidx.p, h->d_diag.p, f.fpos.p, h->d_lu.p, f.fout.p, (double*)h->pipeL.buf.p);
+            else repack_pipe2_kernel<true, 0, T, T><<<(unsigned)((e + 255) / 256), 256, 0, h->stream>>>(h->pipeL.nval, h->pipeL.val_src.p, h->pipeL.val_dst8.p,
+                h->pipeL.val_stride.p, h->d_colidx.p, h->d_diag.p, f.fpos.p, vals, f.fout.p, (double*)h->pipeL.buf.p);
             h->launches++;
         }
         if (h->pipeU.nval) {
             const size_t e = h->pipeU.nval * 3;
-            repack_pipe2_kernel<false, 0><<<(unsigned)((e + 255) / 256), 256, 0, h->stream>>>(h->pipeU.nval, h->pipeU.val_src.p, h->pipeU.val_dst8.p,
-                h->pipeU.val_stride.p, h->d_colidx.p, h->d_diag.p, f.fpos.p, ilu_A, f.fout.p, (double*)h->pipeU.buf.p);
+            if (A_in_lu) repack_pipe2_kernel<false, 0, double, T><<<(unsigned)((e + 255) / 256), 256, 0, h->stream>>>(h->pipeU.nval, h->pipeU.val_src.p, h->pipeU.val_dst8.p,
+                h->pipeU.val_stride.p, h->d_colidx.p, h->d_diag.p, f.fpos.p, h->d_lu.p, f.fout.p, (double*)h->pipeU.buf.p);
+            else repack_pipe2_kernel<false, 0, T, T><<<(unsigned)((e + 255) / 256), 256, 0, h->stream>>>(h->pipeU.nval, h->pipeU.val_src.p, h->pipeU.val_dst8.p,
+                h->pipeU.val_stride.p, h->d_colidx.p, h->d_diag.p, f.fpos.p, vals, f.fout.p, (double*)h->pipeU.buf.p);
             h->launches++;
         }
     } else if (h->use_pipe) {
@@ -852,13 +893,15 @@ int factor(opmgpu_handle h, int* bad_row)
     h->have_factors = true;
     return OPMGPU_OK;
 }
+int factor(opmgpu_handle h, int* bad_row) { return h->f32 ? factor_t<float>(h, bad_row) : factor_t<double>(h, bad_row); }
 
 // cooperative launch of a pipelined sweep, in thread-block clusters when the program asks for them
+template <class T>
 int launch_sweep(opmgpu_handle h, bool upper, const PipeDevMem& d, void** args)
 {
     if (d.cluster_size > 1) {
-        const void* fn = upper ? (const void*)ilu0_sweep_pipe_kernel<true, true, true> : (const void*)ilu0_sweep_pipe_kernel<false, true, true>;
-        if (h->gtrace_steps > 0 || (h->trace_cta >= 0 && h->d_trace.p))                     // debug tools only
+        const void* fn = upper ? (const void*)ilu0_sweep_pipe_kernel<true, true, true, false, T> : (const void*)ilu0_sweep_pipe_kernel<false, true, true, false, T>;
+        if (sizeof(T) == 8 && (h->gtrace_steps > 0 || (h->trace_cta >= 0 && h->d_trace.p)))                     // debug tools only
             fn = upper ? (const void*)ilu0_sweep_pipe_kernel<true, true, true, true> : (const void*)ilu0_sweep_pipe_kernel<false, true, true, true>;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(d.P); cfg.blockDim = dim3(kPipeThreads); cfg.dynamicSmemBytes = d.smem; cfg.stream = h->stream;
@@ -887,9 +930,9 @@ int launch_sweep(opmgpu_handle h, bool upper, const PipeDevMem& d, void** args)
         CK(le);
         return 0;
     }
-    const bool trace = (h->trace_cta >= 0 && h->d_trace.p) || h->gtrace_steps > 0;       // debug tools only
-    const void* fn = upper ? (d.lean ? (const void*)ilu0_sweep_pipe_kernel<true, true> : (const void*)ilu0_sweep_pipe_kernel<true, false>)
-                           : (d.lean ? (const void*)ilu0_sweep_pipe_kernel<false, true> : (const void*)ilu0_sweep_pipe_kernel<false, false>);
+    const bool trace = sizeof(T) == 8 && ((h->trace_cta >= 0 && h->d_trace.p) || h->gtrace_steps > 0);       // debug tools only
+    const void* fn = upper ? (d.lean ? (const void*)ilu0_sweep_pipe_kernel<true, true, false, false, T> : (const void*)ilu0_sweep_pipe_kernel<true, false, false, false, T>)
+                           : (d.lean ? (const void*)ilu0_sweep_pipe_kernel<false, true, false, false, T> : (const void*)ilu0_sweep_pipe_kernel<false, false, false, false, T>);
     if (trace)
         fn = upper ? (d.lean ? (const void*)ilu0_sweep_pipe_kernel<true, true, false, true> : (const void*)ilu0_sweep_pipe_kernel<true, false, false, true>)
                    : (d.lean ? (const void*)ilu0_sweep_pipe_kernel<false, true, false, true> : (const void*)ilu0_sweep_pipe_kernel<false, false, false, true>);
@@ -899,14 +942,18 @@ int launch_sweep(opmgpu_handle h, bool upper, const PipeDevMem& d, void** args)
 
 // v = w U^-1 L^-1 d, all device pointers; asynchronous
 // d_in_program_order: the producer of d already wrote it into pipeL.rhs_perm (fused permutation)
-int apply_precond(opmgpu_handle h, double w, const double* d, double* v, bool d_in_program_order = false)
+template <class T>
+int apply_precond(opmgpu_handle h, double w, const T* d, T* v, bool d_in_program_order = false)
 {
     const int scale = std::fabs(w - 1.0) > 1e-15 ? 1 : 0;      // relaxation_ flag of the reference
+    if (h->use_col && sizeof(T) == 4) return h->bad("the column-owned sweeps (OPMGPU_COL=1) exist for the double instance only");
     if (h->use_col) {
+        const double* dd = reinterpret_cast<const double*>(d);      // (double instance only)
+        double* vv = reinterpret_cast<double*>(v);
         ColDevMem& c = h->col;
         if (!d_in_program_order) {
             const size_t e = c.nperm * 3;
-            permute_rows_kernel<<<(unsigned)((e + 255) / 256), 256, 0, h->stream>>>(c.nperm, c.perm_row.p, d, c.rhsL.p);
+            permute_rows_kernel<double><<<(unsigned)((e + 255) / 256), 256, 0, h->stream>>>(c.nperm, c.perm_row.p, dd, c.rhsL.p);
         }
         for (int upper = 0; upper < 2; ++upper) {
             ColDev pg;
@@ -935,7 +982,7 @@ int apply_precond(opmgpu_handle h, double w, const double* d, double* v, bool d_
                 }
             }
             const double* rhs = upper ? c.rhsU.p : c.rhsL.p; double* hand = upper ? nullptr : c.rhsU.p;
-            double* out = upper ? v : nullptr; int* err = h->d_err.p;
+            double* out = upper ? vv : nullptr; int* err = h->d_err.p;
             void* args[] = {&pg, &rhs, &hand, &out, &w, (void*)&scale, &err};
             const void* fn = upper ? (prof ? (const void*)ilu0_sweep_col_kernel<true, true> : (const void*)ilu0_sweep_col_kernel<true, false>)
                                    : (prof ? (const void*)ilu0_sweep_col_kernel<false, true> : (const void*)ilu0_sweep_col_kernel<false, false>);
@@ -965,43 +1012,43 @@ int apply_precond(opmgpu_handle h, double w, const double* d, double* v, bool d_
     if (h->use_pipe) {
         if (!d_in_program_order) {
             const size_t e = h->pipeL.nperm * 3;
-            permute_rows_kernel<<<(unsigned)((e + 255) / 256), 256, 0, h->stream>>>(h->pipeL.nperm, h->pipeL.perm_row.p, d, h->pipeL.rhs_perm.p);
+            permute_rows_kernel<T><<<(unsigned)((e + 255) / 256), 256, 0, h->stream>>>(h->pipeL.nperm, h->pipeL.perm_row.p, d, h->pipeL.rhs_perm.p);
         }
         {
             PipeDev pg = pipe_dev(h->pipeL);
             if (h->trace_cta >= 0 && h->d_trace.p) { pg.trace = h->d_trace.p; pg.trace_cta = h->trace_cta; }
             if (h->gtrace_steps > 0) { pg.gtrace = h->d_gtrace.p; pg.gtrace_steps = h->gtrace_steps; }
             const double* rhs = h->pipeL.rhs_perm.p; double* work = h->d_yL.p; double* hand = h->pipeU.rhs_perm.p;
-            double* out = nullptr; int* err = h->d_err.p;
+            T* out = nullptr; int* err = h->d_err.p;
             void* args[] = {&pg, &rhs, &work, &hand, &out, &w, (void*)&scale, &err};
-            if (int rc = launch_sweep(h, false, h->pipeL, args)) return rc;
+            if (int rc = launch_sweep<T>(h, false, h->pipeL, args)) return rc;
         }
         {
             PipeDev pg = pipe_dev(h->pipeU);
             if (h->trace_cta >= 0 && h->d_trace.p) { pg.trace = h->d_trace.p + 512 * 16; pg.trace_cta = h->trace_cta; }
             if (h->gtrace_steps > 0) { pg.gtrace = h->d_gtrace.p + (size_t)h->pipeL.P * (h->gtrace_steps * 8 + 2048); pg.gtrace_steps = h->gtrace_steps; }
             const double* rhs = h->pipeU.rhs_perm.p; double* work = h->d_vU.p; double* hand = nullptr;
-            double* out = v; int* err = h->d_err.p;
+            T* out = v; int* err = h->d_err.p;
             void* args[] = {&pg, &rhs, &work, &hand, &out, &w, (void*)&scale, &err};
-            if (int rc = launch_sweep(h, true, h->pipeU, args)) return rc;
+            if (int rc = launch_sweep<T>(h, true, h->pipeU, args)) return rc;
         }
         h->launches += d_in_program_order ? 2 : 3;
         return 0;
     }
     {
         SweepDev pg = sweep_dev(h->progL);
-        const double* rhs = d; double* work = h->d_yL.p; double* out = nullptr;
+        const T* rhs = d; T* work = vec<T>(h->d_yL); T* out = nullptr;
         int* flags = h->d_flags.p; int epoch = ++h->epoch; int* err = h->d_err.p;
         void* args[] = {&pg, &rhs, &work, &out, &w, (void*)&scale, &flags, &epoch, &err};
-        CK(cudaLaunchCooperativeKernel((void*)ilu0_sweep_kernel<true>, dim3(h->progL.P), dim3(256), args, 0, h->stream));
+        CK(cudaLaunchCooperativeKernel((void*)ilu0_sweep_kernel<true, T>, dim3(h->progL.P), dim3(256), args, 0, h->stream));
         h->launches++;
     }
     {
         SweepDev pg = sweep_dev(h->progU);
-        const double* rhs = h->d_yL.p; double* work = h->d_vU.p; double* out = v;
+        const T* rhs = vec<T>(h->d_yL); T* work = vec<T>(h->d_vU); T* out = v;
         int* flags = h->d_flags.p; int epoch = ++h->epoch; int* err = h->d_err.p;
         void* args[] = {&pg, &rhs, &work, &out, &w, (void*)&scale, &flags, &epoch, &err};
-        CK(cudaLaunchCooperativeKernel((void*)ilu0_sweep_kernel<false>, dim3(h->progU.P), dim3(256), args, 0, h->stream));
+        CK(cudaLaunchCooperativeKernel((void*)ilu0_sweep_kernel<false, T>, dim3(h->progU.P), dim3(256), args, 0, h->stream));
         h->launches++;
     }
     return 0;
@@ -1081,35 +1128,42 @@ int read_scalars(opmgpu_handle h)
 }
 
 // Dune::BiCGSTABSolver::apply on device vectors.  In: d_r = b (x0 = 0).  Out: d_x.
+// T = float: every scalar of the recurrence is a float, as in Dune::BiCGSTABSolver<BlockVector<
+// FieldVector<float,3>>> (field_type = real_type = float; EPSILON = 1e-80 rounds to 0).
+template <class T>
 int bicgstab(opmgpu_handle h, const opmgpu_params* prm, opmgpu_result* res)
 {
-    const double EPSILON = 1e-80;
+    const T EPSILON = sizeof(T) == 8 ? (T)1e-80 : T(0);      // (float)1e-80
     const size_t n = (size_t)h->N * 3;
-    const double red = prm->linear_solver_reduction, w = prm->ilu_relaxation;
+    const T red = (T)prm->linear_solver_reduction;
+    const double w = prm->ilu_relaxation;
     const int maxit = prm->linear_solver_maxiter, half_limit = prm->max_half_steps;
     int rc;
     h->history.clear();
-    CK(cudaMemsetAsync(h->d_x.p, 0, n * sizeof(double), h->stream));
-    CK(cudaMemcpyAsync(h->d_rt.p, h->d_r.p, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    T* d_x = vec<T>(h->d_x); T* d_r = vec<T>(h->d_r); T* d_rt = vec<T>(h->d_rt); T* d_p = vec<T>(h->d_p);
+    T* d_v = vec<T>(h->d_v); T* d_t = vec<T>(h->d_t); T* d_y = vec<T>(h->d_y);
+    CK(cudaMemsetAsync(d_x, 0, n * sizeof(T), h->stream));
+    CK(cudaMemcpyAsync(d_rt, d_r, n * sizeof(T), cudaMemcpyDeviceToDevice, h->stream));
     // the vector kernels write the next right-hand side of the lower sweep in program order
     const int* lpos = h->use_pipe && h->fuse_permute ? (h->use_col ? h->col.pos_of_row.p : h->pipeL.pos_of_row.p) : nullptr;
     double* lperm = h->use_pipe ? (h->use_col ? h->col.rhsL.p : h->pipeL.rhs_perm.p) : nullptr;
     HostBox hb = next_hostbox(h);
-    bicg_init_kernel<<<kVecBlocks, 256, 0, h->stream>>>(n, h->d_r.p, h->d_S.p, h->ws(), hb);
+    bicg_init_kernel<T><<<kVecBlocks, 256, 0, h->stream>>>(n, d_r, h->d_S.p, h->ws(), hb);
     h->launches++;
     if ((rc = reduce_and_publish(h, 3, hb))) return rc;
     if ((rc = wait_scalars(h, hb))) return rc;
-    const double norm0 = std::sqrt(h->h_S[S_NRM2]);
-    double norm = norm0, rho = 1.0, omega = 1.0, it = 0.0;
+    const T norm0 = std::sqrt((T)h->h_S[S_NRM2]);
+    T norm = norm0, rho = T(1), omega = T(1);
+    double it = 0.0;
     // linear_solver_verbosity as dune's solvers read it: > 0 header and summary, > 1 a line per (half) iteration
     const int verbose = h->rank == 0 ? prm->linear_solver_verbosity : 0;
-    double norm_old = norm0;
+    T norm_old = norm0;
     if (verbose > 0) {
-        std::printf("=== opmgpu BiCGSTABSolver (ILU0, %d block rows)\n", h->N);
-        if (verbose > 1) std::printf(" Iter          Defect            Rate\n%5.1f %15.6e\n", 0.0, norm0);
+        std::printf("=== opmgpu BiCGSTABSolver (ILU0, %d block rows%s)\n", h->N, sizeof(T) == 4 ? ", single precision" : "");
+        if (verbose > 1) std::printf(" Iter          Defect            Rate\n%5.1f %15.6e\n", 0.0, (double)norm0);
     }
     auto report = [&](double itv) {
-        if (verbose > 1) std::printf("%5.1f %15.6e %15.6e\n", itv, norm, norm_old > 0 ? norm / norm_old : 0.0);
+        if (verbose > 1) std::printf("%5.1f %15.6e %15.6e\n", itv, (double)norm, norm_old > 0 ? (double)(norm / norm_old) : 0.0);
         norm_old = norm;
     };
     int half = 0, status = OPMGPU_OK, converged = 0;
@@ -1122,28 +1176,28 @@ int bicgstab(opmgpu_handle h, const opmgpu_params* prm, opmgpu_result* res)
         if (half_limit >= 0 && half >= half_limit) break;
         if (std::fabs(rho) <= EPSILON || std::fabs(omega) <= EPSILON) { status = OPMGPU_BREAKDOWN; break; }
         if (it < 1) {
-            CK(cudaMemcpyAsync(h->d_p.p, h->d_r.p, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+            CK(cudaMemcpyAsync(d_p, d_r, n * sizeof(T), cudaMemcpyDeviceToDevice, h->stream));
         } else {
             h->prof_begin(2);
-            bicg_update_p_kernel<<<kVecBlocks, 256, 0, h->stream>>>(n, h->d_p.p, h->d_r.p, h->d_v.p, h->d_S.p, lpos, lperm);
+            bicg_update_p_kernel<T><<<kVecBlocks, 256, 0, h->stream>>>(n, d_p, d_r, d_v, h->d_S.p, lpos, lperm);
             h->prof_end();
             h->launches++;
         }
         h->prof_begin(0);
-        if ((rc = apply_precond(h, w, h->d_p.p, h->d_y.p, lpos != nullptr && it >= 1))) return rc;
+        if ((rc = apply_precond<T>(h, w, d_p, d_y, lpos != nullptr && it >= 1))) return rc;
         h->prof_end();
         h->prof_begin(1);
-        if ((rc = spmv_with_dots(h, 1, h->d_y.p, h->d_v.p, h->d_rt.p))) return rc;
+        if ((rc = spmv_with_dots<T>(h, 1, d_y, d_v, d_rt))) return rc;
         h->prof_end();
         h->prof_begin(2);
         hb = next_hostbox(h);
-        bicg_update1_kernel<<<kVecBlocks, 256, 0, h->stream>>>(n, h->d_x.p, h->d_r.p, h->d_y.p, h->d_v.p, h->d_S.p, h->ws(), hb, lpos, lperm);
+        bicg_update1_kernel<T><<<kVecBlocks, 256, 0, h->stream>>>(n, d_x, d_r, d_y, d_v, h->d_S.p, h->ws(), hb, lpos, lperm);
         h->prof_end();
         h->launches++;
         if ((rc = reduce_and_publish(h, 2, hb))) return rc;
         if ((rc = wait_scalars(h, hb))) return rc;
-        if (std::fabs(h->h_S[S_H]) < EPSILON) { status = OPMGPU_BREAKDOWN; break; }
-        norm = std::sqrt(h->h_S[S_NRM2]);
+        if (std::fabs((T)h->h_S[S_H]) < EPSILON) { status = OPMGPU_BREAKDOWN; break; }
+        norm = std::sqrt((T)h->h_S[S_NRM2]);
         h->history.push_back(norm);
         report(it);
         ++half;
@@ -1152,21 +1206,21 @@ int bicgstab(opmgpu_handle h, const opmgpu_params* prm, opmgpu_result* res)
         if (half_limit >= 0 && half >= half_limit) break;
 
         h->prof_begin(0);
-        if ((rc = apply_precond(h, w, h->d_r.p, h->d_y.p, lpos != nullptr))) return rc;
+        if ((rc = apply_precond<T>(h, w, d_r, d_y, lpos != nullptr))) return rc;
         h->prof_end();
         h->prof_begin(1);
-        if ((rc = spmv_with_dots(h, 2, h->d_y.p, h->d_t.p, h->d_r.p))) return rc;
+        if ((rc = spmv_with_dots<T>(h, 2, d_y, d_t, d_r))) return rc;
         h->prof_end();
         h->prof_begin(2);
         hb = next_hostbox(h);
-        bicg_update2_kernel<<<kVecBlocks, 256, 0, h->stream>>>(n, h->d_x.p, h->d_r.p, h->d_y.p, h->d_t.p, h->d_rt.p, h->d_S.p, h->ws(), hb);
+        bicg_update2_kernel<T><<<kVecBlocks, 256, 0, h->stream>>>(n, d_x, d_r, d_y, d_t, d_rt, h->d_S.p, h->ws(), hb);
         h->prof_end();
         h->launches++;
         if ((rc = reduce_and_publish(h, 3, hb))) return rc;
         if ((rc = wait_scalars(h, hb))) return rc;
-        omega = h->h_S[S_OMEGA];
-        rho = h->h_S[S_RHO_OLD];
-        norm = std::sqrt(h->h_S[S_NRM2]);
+        omega = (T)h->h_S[S_OMEGA];
+        rho = (T)h->h_S[S_RHO_OLD];
+        norm = std::sqrt((T)h->h_S[S_NRM2]);
         h->history.push_back(norm);
         report(it);
         ++half;
@@ -1176,9 +1230,9 @@ int bicgstab(opmgpu_handle h, const opmgpu_params* prm, opmgpu_result* res)
     res->iterations = (int)std::ceil(it);
     res->converged = converged;
     res->half_steps = half;
-    res->reduction = norm / norm0;
-    if (verbose > 0) std::printf("=== rate=%g, IT=%d, reduction=%g, %s\n", res->iterations > 0 ? std::pow(norm / norm0, 1.0 / res->iterations) : 0.0,
-                                 res->iterations, norm / norm0, converged ? "converged" : "NOT converged");
+    res->reduction = (double)(norm / norm0);
+    if (verbose > 0) std::printf("=== rate=%g, IT=%d, reduction=%g, %s\n", res->iterations > 0 ? std::pow((double)(norm / norm0), 1.0 / res->iterations) : 0.0,
+                                 res->iterations, (double)(norm / norm0), converged ? "converged" : "NOT converged");
     if (status == OPMGPU_OK && !converged) status = OPMGPU_NOT_CONVERGED;
     if (status == OPMGPU_BREAKDOWN) h->err = "breakdown in BiCGSTAB (rho, omega or h below 1e-80)";
     return status;
@@ -1220,7 +1274,7 @@ int gmres(opmgpu_handle h, const opmgpu_params* prm, opmgpu_result* res)
         return 0;
     };
     auto precond_norm = [&](double* v0, double& nrm) -> int {          // v0 = W^-1 b, nrm = |v0|
-        if ((rc = apply_precond(h, w, b, v0))) return rc;
+        if ((rc = apply_precond<double>(h, w, b, v0))) return rc;
         gmres_dot_kernel<<<kVecBlocks, 256, 0, h->stream>>>(n, v0, v0, Hd, 0, h->ws());
         h->launches++;
         if ((rc = reduce_slots(0, 1))) return rc;
@@ -1249,8 +1303,8 @@ int gmres(opmgpu_handle h, const opmgpu_params* prm, opmgpu_result* res)
             // v[i+1] = A v[i] (the operand needs room for the ghost rows when partitioned), w = W^-1 v[i+1]
             double* xin = vi;
             if (h->world > 1) { CK(cudaMemcpyAsync(h->d_tmp.p, vi, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream)); xin = h->d_tmp.p; }
-            if ((rc = spmv_with_dots(h, 0, xin, vn, nullptr))) return rc;
-            if ((rc = apply_precond(h, w, vn, wv))) return rc;
+            if ((rc = spmv_with_dots<double>(h, 0, xin, vn, nullptr))) return rc;
+            if ((rc = apply_precond<double>(h, w, vn, wv))) return rc;
             // modified Gram-Schmidt: H[k][i] = v[k].w ; w -= H[k][i] v[k]
             gmres_dot_kernel<<<kVecBlocks, 256, 0, h->stream>>>(n, V, wv, Hd, 0, h->ws());
             h->launches++;
@@ -1294,12 +1348,12 @@ int gmres(opmgpu_handle h, const opmgpu_params* prm, opmgpu_result* res)
             const double* xin = h->d_x.p;
             if (h->world > 1) {
                 CK(cudaMemcpyAsync(h->d_tmp.p, h->d_x.p, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-                if ((rc = halo_exchange(h, h->d_tmp.p))) return rc;
+                if ((rc = halo_exchange<double>(h, h->d_tmp.p))) return rc;
                 xin = h->d_tmp.p;
             }
             const int* rowptr = h->world > 1 ? h->d_rowptr_full.p : h->d_rowptr.p;
             const int* colidx = h->world > 1 ? h->d_colidx_full.p : h->d_colidx.p;
-            residual3_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->N, rowptr, colidx, h->d_vals, xin, b);
+            residual3_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->N, rowptr, colidx, static_cast<const double*>(h->d_vals), xin, b);
             h->launches++;
             if ((rc = precond_norm(V, norm))) return rc;
         }
@@ -1341,7 +1395,11 @@ int solve_resident(opmgpu_handle h, const opmgpu_params* prm, opmgpu_result* res
     if (h->pattern_check.valid() && h->pattern_check.wait_for(std::chrono::seconds(0)) == std::future_status::ready &&
         !h->pattern_check.get()) return kPatternChanged;
     if (rc) { res->bad_row = badrow; return rc; }
-    rc = prm->newton_use_gmres ? gmres(h, prm, res) : bicgstab(h, prm, res);
+    if (prm->newton_use_gmres && h->f32) {
+        h->err = "restarted GMRES (newton_use_gmres) is available in the double-precision instance only";
+        return OPMGPU_BAD_ARGUMENT;
+    }
+    rc = prm->newton_use_gmres ? gmres(h, prm, res) : (h->f32 ? bicgstab<float>(h, prm, res) : bicgstab<double>(h, prm, res));
     cudaEventRecord(h->ev[2], h->stream);
     cudaEventSynchronize(h->ev[2]);
     res->ms_factor = ev_ms(h->ev[0], h->ev[1]);
@@ -1378,6 +1436,17 @@ bool same_csc_sizes(opmgpu_handle h, int N, const opmgpu_csc* b, bool full)
     for (int q = 0; q < 9; ++q)
         if ((int)h->csc_colptr[q].size() != N + 1 || h->csc_rowidx[q].size() != (size_t)b[q].colptr[N] || b[q].colptr[0] != 0) return false;
     return true;
+}
+
+// float instance: round the caller's doubles once into the handle's own float array (what the
+// assignment to the reference's float matrix does, ...Interleaved.cpp:189)
+int take_values_f32(opmgpu_handle h, const double* vals_dev)
+{
+    const size_t nv = (size_t)(h->world > 1 ? h->nnzb_full : h->nnzb) * 9;
+    CK(h->d_vals32.ensure(nv + 16));
+    if (int rc = convert<double, float>(h, nv, vals_dev, h->d_vals32.p)) return rc;
+    h->d_vals = h->d_vals32.p;
+    return 0;
 }
 
 bool same_csc_pattern(opmgpu_handle h, int N, const opmgpu_csc* b, bool full)
@@ -1442,7 +1511,7 @@ int opmgpu_create(int device, opmgpu_handle* out)
     int per_sm = 1;
     if (const char* s = getenv("OPMGPU_SWEEP_CTAS_PER_SM")) per_sm = std::max(1, atoi(s));
     int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ilu0_sweep_kernel<true>, 256, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ilu0_sweep_kernel<true, double>, 256, 0);
     per_sm = std::min(per_sm, std::max(occ, 1));
     h->sweep_ctas = h->sm_count * per_sm;
     if (const char* s = getenv("OPMGPU_SIMPLE_SWEEP")) h->force_simple = atoi(s) != 0;
@@ -1451,11 +1520,22 @@ int opmgpu_create(int device, opmgpu_handle* out)
     if (const char* s = getenv("OPMGPU_HOSTBOX")) h->use_hostbox = atoi(s) != 0;
     if (const char* s = getenv("OPMGPU_FUSE_PERMUTE")) h->fuse_permute = atoi(s) != 0;
     if (const char* s = getenv("OPMGPU_SPMV_SIMPLE")) h->spmv_tma = atoi(s) == 0;
-    cudaFuncSetAttribute(spmv3_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
-    cudaFuncSetAttribute(spmv3_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
-    cudaFuncSetAttribute(spmv3_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
+    cudaFuncSetAttribute(spmv3_tma_kernel<0, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
+    cudaFuncSetAttribute(spmv3_tma_kernel<1, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
+    cudaFuncSetAttribute(spmv3_tma_kernel<2, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
+    cudaFuncSetAttribute(spmv3_tma_kernel<0, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
+    cudaFuncSetAttribute(spmv3_tma_kernel<1, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
+    cudaFuncSetAttribute(spmv3_tma_kernel<2, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
     cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-    cudaFuncSetAttribute(ilu0_factor_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
+    cudaFuncSetAttribute(ilu0_factor_pipe_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
+    cudaFuncSetAttribute(ilu0_factor_pipe_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
+    // the float instance's sweeps (same records, float arithmetic)
+    cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<false, true, true, false, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
+    cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<true, true, true, false, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
+    cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<false, false, false, false, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
+    cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<true, false, false, false, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
+    cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<false, true, false, false, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
+    cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<true, true, false, false, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
     cudaFuncSetAttribute(ilu0_sweep_col_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
     cudaFuncSetAttribute(ilu0_sweep_col_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
     cudaFuncSetAttribute(ilu0_sweep_col_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
@@ -1542,7 +1622,7 @@ int opmgpu_destroy(opmgpu_handle h)
     cudaDeviceSynchronize();
     h->d_rowptr.release(); h->d_colidx.release(); h->d_diag.release(); h->d_lvl_rows.release();
     h->progL.release(); h->progU.release(); h->pipeL.release(); h->pipeU.release(); h->pipeF.release(); h->col.release();
-    h->d_vals_own.release(); h->d_lu.release();
+    h->d_vals_own.release(); h->d_lu.release(); h->d_stage.release(); h->d_vals32.release();
     h->d_x.release(); h->d_r.release(); h->d_rt.release(); h->d_p.release(); h->d_v.release();
     h->d_t.release(); h->d_y.release(); h->d_yL.release(); h->d_vU.release(); h->d_tmp.release(); h->d_tmp2.release();
     h->d_S.release(); h->d_partials.release(); h->d_ticket.release(); h->d_flags.release();
@@ -1584,8 +1664,9 @@ int opmgpu_set_values_bcrs3(opmgpu_handle h, const double* vals)
     const size_t nv = (size_t)(h->world > 1 ? h->nnzb_full : h->nnzb) * 9;
     CK(h->d_vals_own.ensure(nv));
     CK(cudaMemcpyAsync(h->d_vals_own.p, vals, nv * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (h->f32) { if (int rc = take_values_f32(h, h->d_vals_own.p)) return rc; }
+    else h->d_vals = h->d_vals_own.p;
     CK(cudaStreamSynchronize(h->stream));
-    h->d_vals = h->d_vals_own.p;
     h->have_values = true; h->have_factors = false;
     return OPMGPU_OK;
 }
@@ -1594,22 +1675,47 @@ int opmgpu_set_values_bcrs3_dev(opmgpu_handle h, const double* vals_dev)
 {
     if (!h || !vals_dev) return OPMGPU_BAD_ARGUMENT;
     if (!h->have_pattern) return h->bad("set the pattern first");
-    h->d_vals = vals_dev;
+    if (h->f32) {          // the float instance keeps its own (rounded) copy: nothing is borrowed
+        CK(cudaSetDevice(h->device));
+        if (int rc = take_values_f32(h, vals_dev)) return rc;
+    } else h->d_vals = vals_dev;
     h->have_values = true; h->have_factors = false;
     return OPMGPU_OK;
 }
+
+int opmgpu_set_precision(opmgpu_handle h, int single_precision)
+{
+    if (!h) return OPMGPU_BAD_ARGUMENT;
+    if (h->multi) return multi_set_precision(h->multi, single_precision, h->err);
+    const bool f32 = single_precision != 0;
+    if (f32 != h->f32) {          // values and factors belong to the other instance
+        h->f32 = f32;
+        h->have_values = false; h->have_factors = false; h->d_vals = nullptr;
+    }
+    return OPMGPU_OK;
+}
+int opmgpu_get_precision(opmgpu_handle h) { return h && h->f32 ? 1 : 0; }
 
 int opmgpu_spmv_dev(opmgpu_handle h, const double* x_dev, double* y_dev)
 {
     if (!h || !h->have_values) return OPMGPU_BAD_ARGUMENT;
     CK(cudaSetDevice(h->device));
-    if (h->world > 1) {          // x_dev has no ghost rows: stage it
-        CK(cudaMemcpyAsync(h->d_tmp.p, x_dev, (size_t)h->N * 3 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-        int rc = halo_exchange(h, h->d_tmp.p);
-        if (rc) return rc;
-        return launch_spmv(h, 0, h->d_tmp.p, y_dev, nullptr);
+    const size_t n = (size_t)h->N * 3;
+    if (h->f32) {                // doubles at the ABI, floats inside
+        float* xf = vec<float>(h->d_tmp); float* yf = vec<float>(h->d_tmp2);
+        int rc = convert<double, float>(h, n, x_dev, xf);
+        if (!rc) rc = halo_exchange<float>(h, xf);
+        if (!rc) rc = launch_spmv<float>(h, 0, xf, yf, nullptr);
+        if (!rc) rc = convert<float, double>(h, n, yf, y_dev);
+        return rc;
     }
-    return launch_spmv(h, 0, x_dev, y_dev, nullptr);
+    if (h->world > 1) {          // x_dev has no ghost rows: stage it
+        CK(cudaMemcpyAsync(h->d_tmp.p, x_dev, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        int rc = halo_exchange<double>(h, h->d_tmp.p);
+        if (rc) return rc;
+        return launch_spmv<double>(h, 0, h->d_tmp.p, y_dev, nullptr);
+    }
+    return launch_spmv<double>(h, 0, x_dev, y_dev, nullptr);
 }
 
 int opmgpu_spmv(opmgpu_handle h, const double* x, double* y)
@@ -1617,10 +1723,19 @@ int opmgpu_spmv(opmgpu_handle h, const double* x, double* y)
     if (!h || !h->have_values) return OPMGPU_BAD_ARGUMENT;
     CK(cudaSetDevice(h->device));
     const size_t n = (size_t)h->N * 3;
+    if (h->f32) {
+        CK(h->d_stage.ensure(n));
+        CK(cudaMemcpyAsync(h->d_stage.p, x, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        int rc = opmgpu_spmv_dev(h, h->d_stage.p, h->d_stage.p);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(y, h->d_stage.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return OPMGPU_OK;
+    }
     CK(cudaMemcpyAsync(h->d_tmp.p, x, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    int rc = halo_exchange(h, h->d_tmp.p);
+    int rc = halo_exchange<double>(h, h->d_tmp.p);
     if (rc) return rc;
-    rc = launch_spmv(h, 0, h->d_tmp.p, h->d_tmp2.p, nullptr);
+    rc = launch_spmv<double>(h, 0, h->d_tmp.p, h->d_tmp2.p, nullptr);
     if (rc) return rc;
     CK(cudaMemcpyAsync(y, h->d_tmp2.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -1644,10 +1759,13 @@ int opmgpu_ilu0_get_factors(opmgpu_handle h, double* lu)
     if (h->lu_lazy) {
         // the pipelined factorisation keeps only the pivots: build the BCRS factor array now
         // (in place on a copy of A; the matrix values must still be the ones that were factorised)
-        if (h->world == 1)
-            CK(cudaMemcpyAsync(h->d_lu.p, h->d_vals, (size_t)h->nnzb * 9 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        if (h->world == 1) {
+            if (h->f32) { if (int rc = convert<float, double>(h, (size_t)h->nnzb * 9, static_cast<const float*>(h->d_vals), h->d_lu.p)) return rc; }
+            else CK(cudaMemcpyAsync(h->d_lu.p, h->d_vals, (size_t)h->nnzb * 9 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        }
         const size_t e = (size_t)h->N * 3;
-        materialise_lu_kernel<<<(unsigned)((e + 255) / 256), 256, 0, h->stream>>>(h->N, h->d_rowptr.p, h->d_colidx.p, h->pipeF.fpos.p, h->pipeF.fout.p, h->d_lu.p);
+        if (h->f32) materialise_lu_kernel<float><<<(unsigned)((e + 255) / 256), 256, 0, h->stream>>>(h->N, h->d_rowptr.p, h->d_colidx.p, h->pipeF.fpos.p, h->pipeF.fout.p, h->d_lu.p);
+        else materialise_lu_kernel<double><<<(unsigned)((e + 255) / 256), 256, 0, h->stream>>>(h->N, h->d_rowptr.p, h->d_colidx.p, h->pipeF.fpos.p, h->pipeF.fout.p, h->d_lu.p);
         h->launches++;
         CK(cudaGetLastError());
         h->lu_lazy = false;
@@ -1661,7 +1779,15 @@ int opmgpu_ilu0_apply_dev(opmgpu_handle h, double w, const double* d_dev, double
 {
     if (!h || !h->have_factors) return OPMGPU_BAD_ARGUMENT;
     CK(cudaSetDevice(h->device));
-    return apply_precond(h, w, d_dev, v_dev);
+    if (h->f32) {                // doubles at the ABI, floats inside
+        const size_t n = (size_t)h->N * 3;
+        float* df = vec<float>(h->d_tmp); float* vf = vec<float>(h->d_tmp2);
+        int rc = convert<double, float>(h, n, d_dev, df);
+        if (!rc) rc = apply_precond<float>(h, w, df, vf);
+        if (!rc) rc = convert<float, double>(h, n, vf, v_dev);
+        return rc;
+    }
+    return apply_precond<double>(h, w, d_dev, v_dev);
 }
 
 int opmgpu_ilu0_apply(opmgpu_handle h, double w, const double* d, double* v)
@@ -1669,9 +1795,17 @@ int opmgpu_ilu0_apply(opmgpu_handle h, double w, const double* d, double* v)
     if (!h || !h->have_factors) return OPMGPU_BAD_ARGUMENT;
     CK(cudaSetDevice(h->device));
     const size_t n = (size_t)h->N * 3;
-    CK(cudaMemcpyAsync(h->d_tmp.p, d, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    int rc = apply_precond(h, w, h->d_tmp.p, h->d_tmp2.p);
-    if (rc) return rc;
+    int rc;
+    if (h->f32) {
+        CK(h->d_stage.ensure(n));
+        CK(cudaMemcpyAsync(h->d_stage.p, d, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        if ((rc = opmgpu_ilu0_apply_dev(h, w, h->d_stage.p, h->d_stage.p))) return rc;
+        CK(cudaMemcpyAsync(h->d_tmp2.p, h->d_stage.p, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    } else {
+        CK(cudaMemcpyAsync(h->d_tmp.p, d, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        rc = apply_precond<double>(h, w, h->d_tmp.p, h->d_tmp2.p);
+        if (rc) return rc;
+    }
     CK(cudaMemcpyAsync(v, h->d_tmp2.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(&h->h_flags2[0], h->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -1687,24 +1821,55 @@ int opmgpu_dot(opmgpu_handle h, const double* x, const double* y, int n, double*
     CK(a.ensure(n)); CK(b.ensure(n));
     CK(cudaMemcpyAsync(a.p, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(b.p, y, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
-    dot_kernel<<<kVecBlocks, 256, 0, h->stream>>>((size_t)n, a.p, b.p, h->d_S.p, h->ws());
+    DevArr<float> af, bf;
+    if (h->f32) {             // rounded to float, then the float scalar product
+        CK(af.ensure(n)); CK(bf.ensure(n));
+        int rc = convert<double, float>(h, (size_t)n, a.p, af.p);
+        if (!rc) rc = convert<double, float>(h, (size_t)n, b.p, bf.p);
+        if (rc) return rc;
+        dot_kernel<float><<<kVecBlocks, 256, 0, h->stream>>>((size_t)n, af.p, bf.p, h->d_S.p, h->ws());
+    } else dot_kernel<double><<<kVecBlocks, 256, 0, h->stream>>>((size_t)n, a.p, b.p, h->d_S.p, h->ws());
     h->launches++;
     CK(cudaMemcpyAsync(h->h_S, h->d_S.p, sizeof(double) * S_COUNT, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     *out = h->h_S[S_DOT];
-    a.release(); b.release();
+    a.release(); b.release(); af.release(); bf.release();
     return OPMGPU_OK;
 }
 
 int opmgpu_solve_bcrs3_dev(opmgpu_handle h, const double* vals_dev, const double* rhs_dev, double* x_dev,
                            const opmgpu_params* params, opmgpu_result* result)
 {
-    if (!h || !vals_dev || !rhs_dev || !x_dev || !params || !result) return OPMGPU_BAD_ARGUMENT;
+    if (!h || !rhs_dev || !x_dev || !params || !result) return OPMGPU_BAD_ARGUMENT;
     if (!h->have_pattern) return h->bad("set the pattern first");
+    if (!vals_dev && !h->have_values) return h->bad("vals_dev == NULL: no matrix values are resident (opmgpu_set_values_bcrs3[_dev])");
     std::memset(result, 0, sizeof *result);
     result->bad_row = -1;
     CK(cudaSetDevice(h->device));
     const size_t n = (size_t)h->N * 3;
+    if (h->f32 || !vals_dev) {
+        // values resident in the handle (vals_dev == NULL), or rounded into the float instance's own
+        // array (kept: they stay valid after the call)
+        int rc = 0;
+        if (vals_dev) rc = take_values_f32(h, vals_dev);
+        if (!rc && h->f32) rc = convert<double, float>(h, n, rhs_dev, vec<float>(h->d_r));
+        if (rc) return rc;
+        if (!h->f32) CK(cudaMemcpyAsync(h->d_r.p, rhs_dev, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        h->have_values = true; h->have_factors = false;
+        rc = solve_resident(h, params, result);
+        if (!h->f32) {
+            if (rc == OPMGPU_OK || rc == OPMGPU_NOT_CONVERGED) {
+                CK(cudaMemcpyAsync(x_dev, h->d_x.p, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+                CK(cudaStreamSynchronize(h->stream));
+            }
+            return rc;
+        }
+        if (rc == OPMGPU_OK || rc == OPMGPU_NOT_CONVERGED) {
+            if (int rc2 = convert<float, double>(h, n, vec<float>(h->d_x), x_dev)) return rc2;
+            CK(cudaStreamSynchronize(h->stream));
+        }
+        return rc;
+    }
     h->d_vals = vals_dev;
     h->have_values = true; h->have_factors = false;
     CK(cudaMemcpyAsync(h->d_r.p, rhs_dev, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
@@ -1731,16 +1896,25 @@ int opmgpu_solve_bcrs3(opmgpu_handle h, const double* vals, const double* rhs, d
     CK(cudaSetDevice(h->device));
     const size_t n = (size_t)h->N * 3, nv = (size_t)(h->world > 1 ? h->nnzb_full : h->nnzb) * 9;
     CK(h->d_vals_own.ensure(nv));
+    if (h->f32) CK(h->d_stage.ensure(n));
     cudaEventRecord(h->ev[3], h->stream);
     CK(cudaMemcpyAsync(h->d_vals_own.p, vals, nv * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->d_r.p, rhs, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->f32 ? h->d_stage.p : h->d_r.p, rhs, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     cudaEventRecord(h->ev[4], h->stream);
-    h->d_vals = h->d_vals_own.p;
+    if (h->f32) {
+        int rc = take_values_f32(h, h->d_vals_own.p);
+        if (!rc) rc = convert<double, float>(h, n, h->d_stage.p, vec<float>(h->d_r));
+        if (rc) return rc;
+    } else h->d_vals = h->d_vals_own.p;
     h->have_values = true; h->have_factors = false;
     int rc = solve_resident(h, params, result);
     result->ms_h2d = ev_ms(h->ev[3], h->ev[4]);
     if (rc == OPMGPU_OK || rc == OPMGPU_NOT_CONVERGED) {
         cudaEventRecord(h->ev[5], h->stream);
+        if (h->f32) {
+            if (int rc2 = convert<float, double>(h, n, vec<float>(h->d_x), h->d_stage.p)) return rc2;
+            CK(cudaMemcpyAsync(x, h->d_stage.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        } else
         CK(cudaMemcpyAsync(x, h->d_x.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         cudaEventRecord(h->ev[6], h->stream);
         CK(cudaStreamSynchronize(h->stream));
@@ -1833,8 +2007,9 @@ int opmgpu_solve_from_csc_blocks(opmgpu_handle h, int N, const opmgpu_csc blocks
         }
         CK(h->d_cscval.ensure((size_t)std::max<long long>(h->csc_total, 1)));
         CK(h->d_rhs_stage.ensure((size_t)N * 3));
-        CK(h->d_vals_own.ensure(nmap));
     }
+    if (h->f32) CK(h->d_vals32.ensure((size_t)h->nnzb * 9 + 16));
+    else CK(h->d_vals_own.ensure((size_t)h->nnzb * 9));
     const size_t n = (size_t)N * 3, nv = (size_t)h->nnzb * 9;
     cudaEventRecord(h->ev[3], h->stream);
     for (int q = 0; q < 9; ++q) {
@@ -1843,14 +2018,21 @@ int opmgpu_solve_from_csc_blocks(opmgpu_handle h, int N, const opmgpu_csc blocks
     }
     CK(cudaMemcpyAsync(h->d_rhs_stage.p, rhs_eqmajor, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     cudaEventRecord(h->ev[4], h->stream);
-    interleave_gather_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, h->stream>>>(nv, h->d_map9.p, h->d_cscval.p,
-        matbalscale[0], matbalscale[1], matbalscale[2], h->d_vals_own.p);
-    interleave_rhs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(N, h->d_rhs_stage.p,
-        matbalscale[0], matbalscale[1], matbalscale[2], h->d_r.p);
+    if (h->f32) {
+        interleave_gather_kernel<float><<<(unsigned)((nv + 255) / 256), 256, 0, h->stream>>>(nv, h->d_map9.p, h->d_cscval.p,
+            matbalscale[0], matbalscale[1], matbalscale[2], h->d_vals32.p);
+        interleave_rhs_kernel<float><<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(N, h->d_rhs_stage.p,
+            matbalscale[0], matbalscale[1], matbalscale[2], vec<float>(h->d_r));
+    } else {
+        interleave_gather_kernel<double><<<(unsigned)((nv + 255) / 256), 256, 0, h->stream>>>(nv, h->d_map9.p, h->d_cscval.p,
+            matbalscale[0], matbalscale[1], matbalscale[2], h->d_vals_own.p);
+        interleave_rhs_kernel<double><<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(N, h->d_rhs_stage.p,
+            matbalscale[0], matbalscale[1], matbalscale[2], h->d_r.p);
+    }
     h->launches += 2;
     CK(cudaGetLastError());
     cudaEventRecord(h->ev[5], h->stream);
-    h->d_vals = h->d_vals_own.p;
+    h->d_vals = h->f32 ? (const void*)h->d_vals32.p : (const void*)h->d_vals_own.p;
     h->have_values = true; h->have_factors = false;
     int rc = solve_resident(h, params, result);
     if (rc == kPatternChanged) {                  // the speculation failed: analyse the new pattern, start over
@@ -1867,7 +2049,8 @@ int opmgpu_solve_from_csc_blocks(opmgpu_handle h, int N, const opmgpu_csc blocks
     result->ms_interleave = ev_ms(h->ev[4], h->ev[5]);
     if (rc == OPMGPU_OK || rc == OPMGPU_NOT_CONVERGED) {
         cudaEventRecord(h->ev[5], h->stream);
-        deinterleave_x_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(N, h->d_x.p, h->d_tmp.p);
+        if (h->f32) deinterleave_x_kernel<float><<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(N, vec<float>(h->d_x), h->d_tmp.p);
+        else deinterleave_x_kernel<double><<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(N, h->d_x.p, h->d_tmp.p);
         h->launches++;
         CK(cudaMemcpyAsync(dx_varmajor, h->d_tmp.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         cudaEventRecord(h->ev[6], h->stream);

@@ -33,12 +33,15 @@ static_assert(kSpmvStages % 3 == 0, "stages must be a multiple of the consumer g
 
 // rowptr / colidx must be readable up to 16 bytes past their end (the solver's own buffers are
 // padded); vals is never read past its end (a misaligned last tile takes the direct path).
-template <int MODE>
+// T = float (the reference's Impl<3,float>): 36-byte blocks, so a tile's value range starts at a
+// multiple of four blocks (16-byte alignment of the bulk copy) instead of two.
+template <int MODE, class T>
 __global__ void __launch_bounds__(kSpmvThreads, 1)
 spmv3_tma_kernel(int N, int nnzb, const int* __restrict__ rowptr, const int* __restrict__ colidx,
-                 const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
-                 const double* __restrict__ w1, double* S, ReduceWs ws)
+                 const T* __restrict__ vals, const T* __restrict__ x, T* __restrict__ y,
+                 const T* __restrict__ w1, double* S, ReduceWs ws)
 {
+    constexpr int kAl = sizeof(T) == 8 ? 2 : 4;          // blocks per 16-byte aligned unit (144 bytes)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned long long* full = reinterpret_cast<unsigned long long*>(smem_raw);
     unsigned long long* empty = full + kSpmvStages;
@@ -52,7 +55,7 @@ spmv3_tma_kernel(int N, int nnzb, const int* __restrict__ rowptr, const int* __r
     }
     __syncthreads();
 
-    double d0 = 0.0, d1 = 0.0;                  // dot partials of this thread
+    T d0 = T(0), d1 = T(0);                     // dot partials of this thread
     if (warp == 0) {
         if (lane == 0) {
             int it = 0;
@@ -60,8 +63,8 @@ spmv3_tma_kernel(int N, int nnzb, const int* __restrict__ rowptr, const int* __r
                 const int st = it % kSpmvStages, k = it / kSpmvStages;
                 const int r0 = t * kSpmvRows, r1 = min(N, r0 + kSpmvRows);
                 const int b0 = rowptr[r0], b1 = rowptr[r1];
-                const int b0a = b0 & ~1;                                  // 16-byte aligned start
-                int b1a = (b1 + 1) & ~1;
+                const int b0a = b0 & ~(kAl - 1);                          // 16-byte aligned start
+                int b1a = (b1 + kAl - 1) & ~(kAl - 1);
                 const bool direct = (b1a > nnzb) || (b1a - b0a > kSpmvCapBlocks);   // odd tail / oversized tile
                 if (k > 0) { while (!mbar_try_wait(&empty[st], (unsigned)((k - 1) & 1))) {} }
                 unsigned char* stage = stages + (size_t)st * kSpmvStageBytes;
@@ -70,7 +73,7 @@ spmv3_tma_kernel(int N, int nnzb, const int* __restrict__ rowptr, const int* __r
                 const unsigned pbytes = (unsigned)(((r1 - r0 + 1) * 4 + 15) & ~15);
                 const int c0a = b0 & ~3;
                 const unsigned cbytes = direct ? 0u : (unsigned)((((b1 - c0a) * 4) + 15) & ~15);
-                const unsigned vbytes = direct ? 0u : (unsigned)((b1a - b0a) * 72);
+                const unsigned vbytes = direct ? 0u : (unsigned)((b1a - b0a) * 9 * (int)sizeof(T));
                 mbar_arrive_expect_tx(&full[st], pbytes + cbytes + vbytes);
                 tma_bulk_g2s(hdr, rowptr + r0, pbytes, &full[st]);
                 if (!direct) {
@@ -94,29 +97,29 @@ spmv3_tma_kernel(int N, int nnzb, const int* __restrict__ rowptr, const int* __r
             const unsigned char* stage = stages + (size_t)st * kSpmvStageBytes;
             const int* rp = reinterpret_cast<const int*>(stage + kSpmvValBytes + kSpmvColBytes);
             const int b0 = rp[0], b1 = rp[r1 - r0];
-            const int b0a = b0 & ~1, b1a = (b1 + 1) & ~1, c0a = b0 & ~3;
+            const int b0a = b0 & ~(kAl - 1), b1a = (b1 + kAl - 1) & ~(kAl - 1), c0a = b0 & ~3;
             const bool direct = (b1a > nnzb) || (b1a - b0a > kSpmvCapBlocks);
             const int r = r0 + rl;
             if (r < r1) {
                 const int kb = rp[rl], ke = rp[rl + 1];
-                double acc = 0.0;
+                T acc = T(0);
                 if (!direct) {
-                    const double* vs = reinterpret_cast<const double*>(stage) + c * 3;
+                    const T* vs = reinterpret_cast<const T*>(stage) + c * 3;
                     const int* cs = reinterpret_cast<const int*>(stage + kSpmvValBytes);
                     // all x gathers of up to eight blocks are issued before the FMA chain
                     for (int kk = kb; kk < ke; kk += 8) {
-                        double xv[8][3];
+                        T xv[8][3];
 #pragma unroll
                         for (int u = 0; u < 8; ++u) {
                             if (kk + u < ke) {
-                                const double* xj = x + (size_t)cs[kk + u - c0a] * 3;
+                                const T* xj = x + (size_t)cs[kk + u - c0a] * 3;
                                 xv[u][0] = xj[0]; xv[u][1] = xj[1]; xv[u][2] = xj[2];
                             }
                         }
 #pragma unroll
                         for (int u = 0; u < 8; ++u) {
                             if (kk + u < ke) {
-                                const double* a = vs + (size_t)(kk + u - b0a) * 9;
+                                const T* a = vs + (size_t)(kk + u - b0a) * 9;
                                 acc = fma(a[0], xv[u][0], acc);
                                 acc = fma(a[1], xv[u][1], acc);
                                 acc = fma(a[2], xv[u][2], acc);
@@ -125,8 +128,8 @@ spmv3_tma_kernel(int N, int nnzb, const int* __restrict__ rowptr, const int* __r
                     }
                 } else {
                     for (int kk = kb; kk < ke; ++kk) {
-                        const double* a = vals + (size_t)kk * 9 + c * 3;
-                        const double* xj = x + (size_t)colidx[kk] * 3;
+                        const T* a = vals + (size_t)kk * 9 + c * 3;
+                        const T* xj = x + (size_t)colidx[kk] * 3;
                         acc = fma(a[0], xj[0], acc);
                         acc = fma(a[1], xj[1], acc);
                         acc = fma(a[2], xj[2], acc);
@@ -142,11 +145,11 @@ spmv3_tma_kernel(int N, int nnzb, const int* __restrict__ rowptr, const int* __r
         }
     }
     if (MODE == 1) {
-        double v[1] = {d0};
-        grid_reduce<1>(v, ws, [=](double (&u)[1]) { S[S_H] = u[0]; });
+        T v[1] = {d0};
+        grid_reduce<1, T>(v, ws, [=](T (&u)[1]) { S[S_H] = u[0]; });
     } else if (MODE == 2) {
-        double v[2] = {d0, d1};
-        grid_reduce<2>(v, ws, [=](double (&u)[2]) { S[S_TR] = u[0]; S[S_TT] = u[1]; });
+        T v[2] = {d0, d1};
+        grid_reduce<2, T>(v, ws, [=](T (&u)[2]) { S[S_TR] = u[0]; S[S_TT] = u[1]; });
     }
 }
 

@@ -203,15 +203,17 @@ __device__ __forceinline__ void push_f64(double* p, double v)
 // loaded from the landed stage into registers one step ahead.  One thread owns the whole row
 // (all three components), so the chain needs no shuffles and its nine dependency loads are
 // issued once per row, not once per component.
-template <bool UPPER>
+// T: arithmetic type of the sweep (double, or float for the reference's Impl<3,float>); records,
+// window and push slots hold 8-byte containers either way (a float widened exactly).
+template <bool UPPER, class T>
 struct StepPre {
     int n, qbase, ext_end, ext_cnt;
     int4 ri0, ri1;              // rowinfo, dep0, dep1, dep2 | upos, push0, push1, own window slot
     uint32_t a0, a1, a2, aw;    // shared addresses of the three dependencies and of the own window slot
     bool on, has_cx;            // has_cx: some dependency arrives through distributed shared memory
-    double rhs[3];
-    double cf[27];              // cf[c*9 + k*3 + e]
-    double dv[9];               // dv[c*3 + e] (upper)
+    T rhs[3];
+    T cf[27];                   // cf[c*9 + k*3 + e]
+    T dv[9];                    // dv[c*3 + e] (upper)
 
     // stage = rhs area followed by the record
     __device__ __forceinline__ void load(const unsigned char* stage, int rhs_bytes, int r, bool lane_on, uint32_t dep_s = 0)
@@ -224,14 +226,14 @@ struct StepPre {
         if (on) {
             const double* cfp = reinterpret_cast<const double*>(rec + 32) + r * 27;
 #pragma unroll
-            for (int q = 0; q < 27; ++q) cf[q] = cfp[q];
-            const int T = 3 * n;
-            size_t off = 32 + (size_t)T * 72;
+            for (int q = 0; q < 27; ++q) cf[q] = (T)cfp[q];
+            const int T3 = 3 * n;
+            size_t off = 32 + (size_t)T3 * 72;
             if (UPPER) {
                 const double* dp = reinterpret_cast<const double*>(rec + off) + r * 9;
 #pragma unroll
-                for (int q = 0; q < 9; ++q) dv[q] = dp[q];
-                off += (size_t)T * 24;
+                for (int q = 0; q < 9; ++q) dv[q] = (T)dp[q];
+                off += (size_t)T3 * 24;
             }
             const int4* rip = reinterpret_cast<const int4*>(rec + ((off + 15) & ~(size_t)15)) + 2 * r;
             ri0 = rip[0]; ri1 = rip[1];
@@ -240,7 +242,7 @@ struct StepPre {
             aw = dep_s + 8u * (uint32_t)ri1.w;
             has_cx = max(ri0.y, max(ri0.z, ri0.w)) >= kCxBase * 3;
             const double* rp = reinterpret_cast<const double*>(stage) + 3 * r;
-            rhs[0] = rp[0]; rhs[1] = rp[1]; rhs[2] = rp[2];
+            rhs[0] = (T)rp[0]; rhs[1] = (T)rp[1]; rhs[2] = (T)rp[2];
         }
     }
 };
@@ -251,8 +253,9 @@ __device__ __forceinline__ const double* dep_ptr(int code, const double* dep, co
 }
 
 // blocks beyond the three held in registers (rows with many couplings, e.g. well cells)
+template <class T>
 __device__ __noinline__ void sweep_tail_blocks(const unsigned char* rec, int r, const double* dep,
-                                               const double* work, double (&acc)[3])
+                                               const double* work, T (&acc)[3])
 {
     const int* hdr = reinterpret_cast<const int*>(rec);
     const int n = hdr[0];
@@ -262,18 +265,19 @@ __device__ __noinline__ void sweep_tail_blocks(const unsigned char* rec, int r, 
     const double* tail_vals = reinterpret_cast<const double*>(rec + (size_t)hdr[6] * 8);
     for (int t = r ? tail_end[r - 1] : 0; t < tail_end[r]; ++t) {
         const double* yp = dep_ptr(tail_dep[t], dep, work);
-        const double y0 = yp[0], y1 = yp[1], y2 = yp[2];
+        const T y0 = (T)yp[0], y1 = (T)yp[1], y2 = (T)yp[2];
         const double* ap = tail_vals + (size_t)t * 9;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            acc[c] = fma(-ap[c * 3 + 0], y0, acc[c]);
-            acc[c] = fma(-ap[c * 3 + 1], y1, acc[c]);
-            acc[c] = fma(-ap[c * 3 + 2], y2, acc[c]);
+            acc[c] = fma(-(T)ap[c * 3 + 0], y0, acc[c]);
+            acc[c] = fma(-(T)ap[c * 3 + 1], y1, acc[c]);
+            acc[c] = fma(-(T)ap[c * 3 + 2], y2, acc[c]);
         }
     }
 }
 // pushes beyond the two held in registers
-__device__ __noinline__ void sweep_extra_pushes(const unsigned char* rec, int r, double* ext, const double (&acc)[3])
+template <class T>
+__device__ __noinline__ void sweep_extra_pushes(const unsigned char* rec, int r, double* ext, const T (&acc)[3])
 {
     const int* hdr = reinterpret_cast<const int*>(rec);
     const int n = hdr[0];
@@ -282,7 +286,7 @@ __device__ __noinline__ void sweep_extra_pushes(const unsigned char* rec, int r,
     const int* xpush_slot = lists + 2 * n + hdr[4];
     for (int t = r ? xpush_end[r - 1] : 0; t < xpush_end[r]; ++t) {
         double* sl = ext + (size_t)xpush_slot[t] * 3;
-        __stcg(sl, acc[0]); __stcg(sl + 1, acc[1]); __stcg(sl + 2, acc[2]);
+        __stcg(sl, (double)acc[0]); __stcg(sl + 1, (double)acc[1]); __stcg(sl + 2, (double)acc[2]);
     }
 }
 
@@ -318,9 +322,9 @@ __device__ __forceinline__ bool cx_entry_there(uint32_t a)
     return (h0 != -1) & (h1 != -1) & (h2 != -1);      // a result never has an all-ones upper half (that is a NaN no arithmetic produces)
 }
 
-template <bool UPPER, bool LEAN, bool CX = false>
-__device__ __forceinline__ void sweep_row_chain(const StepPre<UPPER>& p, const unsigned char* rec, int r,
-                                                double* dep, uint32_t dep_s, const double* work, double* ext, double (&acc)[3],
+template <bool UPPER, bool LEAN, bool CX = false, class T = double>
+__device__ __forceinline__ void sweep_row_chain(const StepPre<UPPER, T>& p, const unsigned char* rec, int r,
+                                                double* dep, uint32_t dep_s, const double* work, double* ext, T (&acc)[3],
                                                 PipeCtl* ctl = nullptr, int* err = nullptr)
 {
     if (CX && kCxUniformWait) {
@@ -340,9 +344,9 @@ __device__ __forceinline__ void sweep_row_chain(const StepPre<UPPER>& p, const u
             }
         }
     }
-    if (!p.on) { acc[0] = acc[1] = acc[2] = 0.0; }
+    if (!p.on) { acc[0] = acc[1] = acc[2] = T(0); }
     if (p.on) {
-        double y[9];
+        double y[9];        // containers as loaded (validity of cluster-delivered entries is a bit pattern)
         if (LEAN || (p.ri0.y | p.ri0.z | p.ri0.w) >= 0) {    // all three in shared memory (the common case)
             const uint32_t a0 = LEAN ? p.a0 : dep_s + 8u * (uint32_t)p.ri0.y, a1 = LEAN ? p.a1 : dep_s + 8u * (uint32_t)p.ri0.z,
                            a2 = LEAN ? p.a2 : dep_s + 8u * (uint32_t)p.ri0.w;
@@ -364,85 +368,87 @@ __device__ __forceinline__ void sweep_row_chain(const StepPre<UPPER>& p, const u
         acc[0] = p.rhs[0]; acc[1] = p.rhs[1]; acc[2] = p.rhs[2];
 #pragma unroll
         for (int q = 0; q < 9; ++q) {
-            acc[0] = fma(-p.cf[q], y[q], acc[0]);
-            acc[1] = fma(-p.cf[9 + q], y[q], acc[1]);
-            acc[2] = fma(-p.cf[18 + q], y[q], acc[2]);
+            const T yq = (T)y[q];
+            acc[0] = fma(-p.cf[q], yq, acc[0]);
+            acc[1] = fma(-p.cf[9 + q], yq, acc[1]);
+            acc[2] = fma(-p.cf[18 + q], yq, acc[2]);
         }
-        if (!LEAN && (p.ri0.x & kRowSlow)) sweep_tail_blocks(rec, r, dep, work, acc);
+        if (!LEAN && (p.ri0.x & kRowSlow)) sweep_tail_blocks<T>(rec, r, dep, work, acc);
         if (UPPER) {
-            double v[3];
+            T v[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                double t = 0.0;
+                T t = T(0);
                 t = fma(p.dv[c * 3 + 0], acc[0], t); t = fma(p.dv[c * 3 + 1], acc[1], t); t = fma(p.dv[c * 3 + 2], acc[2], t);
                 v[c] = t;
             }
             acc[0] = v[0]; acc[1] = v[1]; acc[2] = v[2];
         }
         const uint32_t w = LEAN ? p.aw : dep_s + 8u * (uint32_t)p.ri1.w;
-        sts_f64(w, acc[0]); sts_f64(w + 8, acc[1]); sts_f64(w + 16, acc[2]);
+        sts_f64(w, (double)acc[0]); sts_f64(w + 8, (double)acc[1]); sts_f64(w + 16, (double)acc[2]);
     }
 }
 // results other CTAs wait for.  Issued right after the hand-over to the next group: the
 // in-tile hand-over is on the critical path of every step, a tile crossing only once per tile.
 // result -> entry `id & 0xfffff` of CTA `(id >> 20) & 15` of this cluster (distributed shared memory)
-__device__ __forceinline__ void push_dsmem(uint32_t cx_s, int id, const double (&acc)[3])
+template <class T>
+__device__ __forceinline__ void push_dsmem(uint32_t cx_s, int id, const T (&acc)[3])
 {
     const uint32_t la = cx_s + 24u * (uint32_t)(id & 0xfffff);
     uint32_t ra;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"((id >> 20) & 0xf));
-    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra), "d"(acc[0]) : "memory");
-    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra + 8), "d"(acc[1]) : "memory");
-    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra + 16), "d"(acc[2]) : "memory");
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra), "d"((double)acc[0]) : "memory");
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra + 8), "d"((double)acc[1]) : "memory");
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra + 16), "d"((double)acc[2]) : "memory");
 }
 
-template <bool UPPER, bool LEAN, bool CX = false>
-__device__ __forceinline__ void sweep_row_pushes(const StepPre<UPPER>& p, const unsigned char* rec, int r,
-                                                 double* ext, const double (&acc)[3], uint32_t cx_s = 0)
+template <bool UPPER, bool LEAN, bool CX = false, class T = double>
+__device__ __forceinline__ void sweep_row_pushes(const StepPre<UPPER, T>& p, const unsigned char* rec, int r,
+                                                 double* ext, const T (&acc)[3], uint32_t cx_s = 0)
 {
     if (p.on) {
-        if (CX && p.ri1.y >= 0 && (p.ri1.y & kPushDsmem)) push_dsmem(cx_s, p.ri1.y, acc);
-        else if (p.ri1.y >= 0) { double* sl = ext + (size_t)p.ri1.y * 3; push_f64(sl, acc[0]); push_f64(sl + 1, acc[1]); push_f64(sl + 2, acc[2]); }
-        if (CX && p.ri1.z >= 0 && (p.ri1.z & kPushDsmem)) push_dsmem(cx_s, p.ri1.z, acc);
-        else if (p.ri1.z >= 0) { double* sl = ext + (size_t)p.ri1.z * 3; push_f64(sl, acc[0]); push_f64(sl + 1, acc[1]); push_f64(sl + 2, acc[2]); }
-        if (!LEAN && (p.ri0.x & kRowSlow)) sweep_extra_pushes(rec, r, ext, acc);
+        if (CX && p.ri1.y >= 0 && (p.ri1.y & kPushDsmem)) push_dsmem<T>(cx_s, p.ri1.y, acc);
+        else if (p.ri1.y >= 0) { double* sl = ext + (size_t)p.ri1.y * 3; push_f64(sl, (double)acc[0]); push_f64(sl + 1, (double)acc[1]); push_f64(sl + 2, (double)acc[2]); }
+        if (CX && p.ri1.z >= 0 && (p.ri1.z & kPushDsmem)) push_dsmem<T>(cx_s, p.ri1.z, acc);
+        else if (p.ri1.z >= 0) { double* sl = ext + (size_t)p.ri1.z * 3; push_f64(sl, (double)acc[0]); push_f64(sl + 1, (double)acc[1]); push_f64(sl + 2, (double)acc[2]); }
+        if (!LEAN && (p.ri0.x & kRowSlow)) sweep_extra_pushes<T>(rec, r, ext, acc);
     }
 }
 // ... and the part nobody waits for: results to HBM
-template <bool UPPER, bool LEAN>
-__device__ __forceinline__ void sweep_row_stores(const StepPre<UPPER>& p, const double (&acc)[3],
-                                                 double* work, double* hand_off, double* out, double w, int scale)
+template <bool UPPER, bool LEAN, class T>
+__device__ __forceinline__ void sweep_row_stores(const StepPre<UPPER, T>& p, const T (&acc)[3],
+                                                 double* work, double* hand_off, T* out, T w, int scale)
 {
     if (p.on) {
         const int row = p.ri0.x & kRowMask;
         if (UPPER) {
-            double* o = out + (size_t)row * 3;
+            T* o = out + (size_t)row * 3;
             o[0] = scale ? acc[0] * w : acc[0]; o[1] = scale ? acc[1] * w : acc[1]; o[2] = scale ? acc[2] * w : acc[2];
         } else {
             double* o = hand_off + (size_t)p.ri1.x * 3;
-            o[0] = acc[0]; o[1] = acc[1]; o[2] = acc[2];
+            o[0] = (double)acc[0]; o[1] = (double)acc[1]; o[2] = (double)acc[2];
         }
         if (!LEAN && (p.ri0.x & kRowWriteGlobal)) {
             double* o = work + (size_t)row * 3;
-            o[0] = acc[0]; o[1] = acc[1]; o[2] = acc[2];
+            o[0] = (double)acc[0]; o[1] = (double)acc[1]; o[2] = (double)acc[2];
         }
     }
 }
 
 // rows [kPipeRowsPerPass, n) of a step wider than one pass over the compute warps
-template <bool UPPER>
+template <bool UPPER, class T>
 __device__ __noinline__ void sweep_extra_rows(const unsigned char* stage, int rhs_bytes, int n, int r_first,
                                               double* dep, uint32_t dep_s, double* work, double* hand_off,
-                                              double* out, double* ext, double w, int scale)
+                                              T* out, double* ext, T w, int scale)
 {
     for (int rbase = kPipeRowsPerPass; rbase < n; rbase += kPipeRowsPerPass) {
         const int r = rbase + r_first;
-        StepPre<UPPER> p;
+        StepPre<UPPER, T> p;
         p.load(stage, rhs_bytes, r, true);
-        double acc[3];
-        sweep_row_chain<UPPER, false>(p, stage + rhs_bytes, r, dep, dep_s, work, ext, acc);
-        sweep_row_pushes<UPPER, false>(p, stage + rhs_bytes, r, ext, acc);
-        sweep_row_stores<UPPER, false>(p, acc, work, hand_off, out, w, scale);
+        T acc[3];
+        sweep_row_chain<UPPER, false, false, T>(p, stage + rhs_bytes, r, dep, dep_s, work, ext, acc);
+        sweep_row_pushes<UPPER, false, false, T>(p, stage + rhs_bytes, r, ext, acc);
+        sweep_row_stores<UPPER, false, T>(p, acc, work, hand_off, out, w, scale);
     }
 }
 
@@ -452,11 +458,12 @@ __device__ __noinline__ void sweep_extra_rows(const unsigned char* stage, int rh
 // into their shared memory (a tile crossing then costs a shared-memory round trip, not an L2 poll).
 // TRACE: the per-step time stamps of the debug tools (tools/trace_sweep.py, gtrace_sweep.py) are
 // compiled in; the production variants carry none of that code on the critical path.
-template <bool UPPER, bool LEAN, bool CX = false, bool TRACE = false>
+template <bool UPPER, bool LEAN, bool CX = false, bool TRACE = false, class T = double>
 __global__ void __launch_bounds__(kPipeThreads, 1)
 ilu0_sweep_pipe_kernel(PipeDev pg, const double* __restrict__ rhs_perm, double* work, double* hand_off,
-                       double* out, double w, int scale, int* err)
+                       T* out, double w_, int scale, int* err)
 {
+    const T w = (T)w_;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     PipeCtl* ctl = reinterpret_cast<PipeCtl*>(smem_raw);
     double* dep = reinterpret_cast<double*>(smem_raw + 512);      // window | pushed ring | zero entry
@@ -635,7 +642,7 @@ ilu0_sweep_pipe_kernel(PipeDev pg, const double* __restrict__ rhs_perm, double* 
         for (int s = g; s < nsteps; s += G) {
             const bool tr = TRACE && pg.trace && blockIdx.x == pg.trace_cta && elected && s < 512;
             const unsigned char* stage = stages + st * stage_stride;
-            StepPre<UPPER> p;
+            StepPre<UPPER, T> p;
             p.n = 0; p.qbase = 0; p.ext_end = 0; p.ext_cnt = 0; p.on = false; p.has_cx = false; p.a0 = p.a1 = p.a2 = p.aw = dep_s;
             if (!dead) {
                 if (pipe_wait(&ctl->full[st], par, ctl, err)) p.load(stage, pg.rhs_bytes, r_first, true, dep_s);
@@ -664,12 +671,12 @@ ilu0_sweep_pipe_kernel(PipeDev pg, const double* __restrict__ rhs_perm, double* 
             }
             if (gt) { gtr[s * 8 + 2] = pipe_gtime_after(ctl->ext_ready); gtr[s * 8 + 4] = p.ext_end; gtr[s * 8 + 5] = p.n; }
             if (tr) pg.trace[s * 16 + 5] = pipe_clock_after(ctl->ext_ready);
-            double acc[3];
-            sweep_row_chain<UPPER, LEAN, CX>(p, stage + pg.rhs_bytes, r_first, dep, dep_s, work, pg.ext, acc, ctl, err);
+            T acc[3];
+            sweep_row_chain<UPPER, LEAN, CX, T>(p, stage + pg.rhs_bytes, r_first, dep, dep_s, work, pg.ext, acc, ctl, err);
             if (!LEAN && p.n > kPipeRowsPerPass)
-                sweep_extra_rows<UPPER>(stage, pg.rhs_bytes, p.n, r_first, dep, dep_s, work, hand_off, out, pg.ext, w, scale);
-            if (tr) { pg.trace[s * 16 + 2] = pipe_clock_after(__double2hiint(acc[0])); pg.trace[s * 16 + 4] = p.n; }
-            if (gt) gtr[s * 8 + 3] = pipe_gtime_after(__double2hiint(acc[0]));
+                sweep_extra_rows<UPPER, T>(stage, pg.rhs_bytes, p.n, r_first, dep, dep_s, work, hand_off, out, pg.ext, w, scale);
+            if (tr) { pg.trace[s * 16 + 2] = pipe_clock_after(__double2hiint((double)acc[0])); pg.trace[s * 16 + 4] = p.n; }
+            if (gt) gtr[s * 8 + 3] = pipe_gtime_after(__double2hiint((double)acc[0]));
             long long rb = 0;           // trace: read the first pushed value back through L2
             const bool gt_rb = gt && p.on && p.ri1.y >= 0;
             if (gt_rb) asm volatile("ld.relaxed.gpu.global.s64 %0, [%1];" : "=l"(rb) : "l"(pg.ext + (size_t)p.ri1.y * 3) : "memory");
@@ -677,7 +684,7 @@ ilu0_sweep_pipe_kernel(PipeDev pg, const double* __restrict__ rhs_perm, double* 
                 __syncwarp();
                 if (lane == 0) asm volatile("red.shared.add.s32 [%0], 1;" ::"r"(ctl_s + (uint32_t)offsetof(PipeCtl, steps_done)) : "memory");
             } else asm volatile("bar.arrive %0, %1;" ::"r"(bar_own), "n"(NPP) : "memory");
-            sweep_row_pushes<UPPER, LEAN, CX>(p, stage + pg.rhs_bytes, r_first, pg.ext, acc, dep_s + 24u * (uint32_t)kCxBase);
+            sweep_row_pushes<UPPER, LEAN, CX, T>(p, stage + pg.rhs_bytes, r_first, pg.ext, acc, dep_s + 24u * (uint32_t)kCxBase);
             if (!LEAN) {            // tail lists of slow rows are read from the stage during the chain
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&ctl->empty[st]);
@@ -685,7 +692,7 @@ ilu0_sweep_pipe_kernel(PipeDev pg, const double* __restrict__ rhs_perm, double* 
             // every warp of this group passed the bar.sync of this step, i.e. is done with its
             // step s-G: release the pushed-result ring entries of that step
             if (elected && st_prev >= 0) ctl->ext_consumed = ext_prev_end;
-            if (!(pg.dbg & 1)) sweep_row_stores<UPPER, LEAN>(p, acc, work, hand_off, out, w, scale);
+            if (!(pg.dbg & 1)) sweep_row_stores<UPPER, LEAN, T>(p, acc, work, hand_off, out, w, scale);
             if (gt_rb) gtr[s * 8 + 6] = pipe_gtime_after((int)rb);
             if (tr) pg.trace[s * 16 + 3] = clock64();
             st_prev = st; ext_prev_end = p.ext_end;
@@ -702,15 +709,16 @@ ilu0_sweep_pipe_kernel(PipeDev pg, const double* __restrict__ rhs_perm, double* 
 }
 
 // natural order -> program order (right-hand side of the lower sweep); perm_row < 0 is padding
+template <class T>
 __global__ void __launch_bounds__(256)
-permute_rows_kernel(size_t nperm, const int* __restrict__ perm_row, const double* __restrict__ x,
+permute_rows_kernel(size_t nperm, const int* __restrict__ perm_row, const T* __restrict__ x,
                     double* __restrict__ xp)
 {
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= nperm * 3) return;
     const size_t q = e / 3;
     const int row = perm_row[q];
-    xp[e] = row >= 0 ? x[(size_t)row * 3 + (e - q * 3)] : 0.0;
+    xp[e] = row >= 0 ? (double)x[(size_t)row * 3 + (e - q * 3)] : 0.0;
 }
 
 }  // namespace opmgpu

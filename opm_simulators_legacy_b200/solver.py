@@ -147,6 +147,15 @@ class GpuLinearSolver:
             raise ValueError(msg or "bad argument")
         raise RuntimeError(msg)
 
+    def set_precision(self, single_precision: bool):
+        """Select the instance: False = the reference's Impl<3,double>, True = its Impl<3,float>
+        (LinearisedBlackoilResidual::singlePrecision, ...Interleaved.cpp:467-487).  The arrays that
+        cross this wrapper stay float64 either way."""
+        self._check(self.lib.opmgpu_set_precision(self.h, int(bool(single_precision))))
+
+    def single_precision(self) -> bool:
+        return bool(self.lib.opmgpu_get_precision(self.h))
+
     def use_torch_stream(self):
         import torch
         self._check(self.lib.opmgpu_set_stream(self.h, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
@@ -249,10 +258,12 @@ class GpuLinearSolver:
 
     def solve_bcrs_dev(self, vals_t, rhs_t, x_t, params: Optional[L.Params] = None,
                        raise_on_failure=True, **kw):
-        """Same with CUDA tensors (device-resident inputs)."""
+        """Same with CUDA tensors (device-resident inputs).  vals_t=None: the values set by
+        set_values / set_values_dev."""
         p = params if params is not None else make_params(**kw)
         res = L.Result()
-        rc = self.lib.opmgpu_solve_bcrs3_dev(self.h, C.c_void_p(vals_t.data_ptr()), C.c_void_p(rhs_t.data_ptr()),
+        rc = self.lib.opmgpu_solve_bcrs3_dev(self.h, C.c_void_p(vals_t.data_ptr()) if vals_t is not None else None,
+                                             C.c_void_p(rhs_t.data_ptr()),
                                              C.c_void_p(x_t.data_ptr()), C.byref(p), C.byref(res))
         self.last = res.as_dict()
         self.last["status"] = rc
@@ -378,7 +389,8 @@ class NewtonIterationBlackoilGPU:
         return self.parallelInformation_
 
     def computeNewtonIncrement(self, residual: LinearisedBlackoilResidual) -> np.ndarray:
-        """...Interleaved.cpp:202-292 (np = 3, double).  Returns dx ordered
+        """...Interleaved.cpp:202-292 (np = 3; the double or the float instance as
+        residual.singlePrecision asks, :467-487).  Returns dx ordered
         [p(N), sw(N), xvar(N), qs(nw*np), bhp(nw)]."""
         import scipy.sparse as sp
         npz = len(residual.material_balance_eq)
@@ -401,6 +413,9 @@ class NewtonIterationBlackoilGPU:
                 J.sort_indices()
                 blocks.append((J.indptr, J.indices, J.data))
         rhs = np.concatenate([eqs[p].value for p in range(3)])
+        # the dispatcher of the reference: Impl<3,float> when the residual asks for it (GMRES exists
+        # for the double instance only; that combination stays in double)
+        self._solver.set_precision(bool(residual.singlePrecision) and not self.parameters_.newton_use_gmres)
         try:
             dx, res = self._solver.solve_from_csc_blocks(N, blocks, residual.matbalscale, rhs,
                                                          params=self.parameters_)

@@ -9,7 +9,7 @@
  */
 #include "oracle.h"
 
-#include <math.h>
+#include <tgmath.h>     /* fma / sqrt / fabs follow the type of `real` */
 #include <stdlib.h>
 #include <string.h>
 
@@ -80,9 +80,9 @@ int oracle_interleave_pattern(int N, int np, const oracle_csc* blocks, int requi
 /* a6 + a7  scaling and value scatter (...Interleaved.cpp:234-236, :178-193).
  * AutoDiffBlock * scalar multiplies every Jacobian value once (AutoDiffBlock.hpp:617-626). */
 int oracle_interleave_values(int N, int np, const oracle_csc* blocks, const double* scale,
-                             const int* rowptr, const int* colidx, double* vals)
+                             const int* rowptr, const int* colidx, real* vals)
 {
-    memset(vals, 0, sizeof(double) * (size_t)rowptr[N] * np * np);
+    memset(vals, 0, sizeof(real) * (size_t)rowptr[N] * np * np);
     for (int p1 = 0; p1 < np; ++p1) {
         for (int p2 = 0; p2 < np; ++p2) {
             const oracle_csc* s = &blocks[p1 * np + p2];
@@ -97,7 +97,7 @@ int oracle_interleave_values(int N, int np, const oracle_csc* blocks, const doub
                         if (colidx[mid] < col) lo = mid + 1; else hi = mid - 1;
                     }
                     if (pos < 0) return -(k + 1);
-                    vals[(size_t)pos * np * np + p1 * np + p2] = s->val[k] * scale[p1];
+                    vals[(size_t)pos * np * np + p1 * np + p2] = (real)(s->val[k] * scale[p1]);   /* rounded once when real = float, like the assignment at :189 */
                 }
             }
         }
@@ -109,14 +109,14 @@ int oracle_interleave_values(int N, int np, const oracle_csc* blocks, const doub
  * a10  operator apply: Dune::MatrixAdapter::apply -> BCRSMatrix::mv -> block umv
  * (call site opm/autodiff/ISTLSolver.hpp:303)
  * ---------------------------------------------------------------------------------- */
-void oracle_spmv3(int N, const int* rowptr, const int* colidx, const double* vals,
-                  const double* x, double* y)
+void oracle_spmv3(int N, const int* rowptr, const int* colidx, const real* vals,
+                  const real* x, real* y)
 {
     for (int i = 0; i < N; ++i) {
-        double y0 = 0.0, y1 = 0.0, y2 = 0.0;
+        real y0 = 0.0, y1 = 0.0, y2 = 0.0;
         for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
-            const double* a = vals + (size_t)k * BB;
-            const double* xj = x + (size_t)colidx[k] * BS;
+            const real* a = vals + (size_t)k * BB;
+            const real* xj = x + (size_t)colidx[k] * BS;
             /* umv: y[r] += a[r][c] * x[c], r outer, c inner */
             y0 = fma(a[0], xj[0], y0); y0 = fma(a[1], xj[1], y0); y0 = fma(a[2], xj[2], y0);
             y1 = fma(a[3], xj[0], y1); y1 = fma(a[4], xj[1], y1); y1 = fma(a[5], xj[2], y1);
@@ -132,30 +132,30 @@ void oracle_spmv3(int N, const int* rowptr, const int* colidx, const double* val
  * ---------------------------------------------------------------------------------- */
 /* C = A * B with dune's DenseMatrix::{right,left}multiply accumulation: each entry starts
  * at 0 and adds k = 0,1,2 in turn. */
-static void mat3_mul(const double* A, const double* B, double* C)
+static void mat3_mul(const real* A, const real* B, real* C)
 {
     for (int i = 0; i < BS; ++i)
         for (int j = 0; j < BS; ++j) {
-            double s = 0.0;
+            real s = 0.0;
             for (int k = 0; k < BS; ++k) s = fma(A[i * BS + k], B[k * BS + j], s);
             C[i * BS + j] = s;
         }
 }
 
-/* Opm::MatrixBlock<double,3,3>::invert -> ISTLUtility::invertMatrix (adjugate / det,
+/* Opm::MatrixBlock<real,3,3>::invert -> ISTLUtility::invertMatrix (adjugate / det,
  * "code generated by maple").  Returns the determinant. */
-static double mat3_invert(double* M)
+static real mat3_invert(real* M)
 {
-    double A[BB];
+    real A[BB];
     memcpy(A, M, sizeof A);
-    const double t4 = A[0] * A[4];
-    const double t6 = A[0] * A[5];
-    const double t8 = A[1] * A[3];
-    const double t10 = A[2] * A[3];
-    const double t12 = A[1] * A[6];
-    const double t14 = A[2] * A[6];
-    const double det = (t4 * A[8] - t6 * A[7] - t8 * A[8] + t10 * A[7] + t12 * A[5] - t14 * A[4]);
-    const double t17 = 1.0 / det;
+    const real t4 = A[0] * A[4];
+    const real t6 = A[0] * A[5];
+    const real t8 = A[1] * A[3];
+    const real t10 = A[2] * A[3];
+    const real t12 = A[1] * A[6];
+    const real t14 = A[2] * A[6];
+    const real det = (t4 * A[8] - t6 * A[7] - t8 * A[8] + t10 * A[7] + t12 * A[5] - t14 * A[4]);
+    const real t17 = 1.0 / det;
     M[0] = (A[4] * A[8] - A[5] * A[7]) * t17;
     M[1] = -(A[1] * A[8] - A[2] * A[7]) * t17;
     M[2] = (A[1] * A[5] - A[2] * A[4]) * t17;
@@ -175,7 +175,7 @@ static int find_diag(const int* rowptr, const int* colidx, int i)
     return -1;
 }
 
-int oracle_ilu0_factor3(int N, const int* rowptr, const int* colidx, double* lu)
+int oracle_ilu0_factor3(int N, const int* rowptr, const int* colidx, real* lu)
 {
     int* diag = (int*)malloc(sizeof(int) * (size_t)(N > 0 ? N : 1));
     for (int i = 0; i < N; ++i) {
@@ -186,9 +186,9 @@ int oracle_ilu0_factor3(int N, const int* rowptr, const int* colidx, double* lu)
         const int iend = rowptr[i + 1];
         for (int ij = rowptr[i]; colidx[ij] < i; ++ij) {
             const int j = colidx[ij];
-            double* Aij = lu + (size_t)ij * BB;
+            real* Aij = lu + (size_t)ij * BB;
             /* L_ij = A_ij * inv(A_jj)   ((*ij).rightmultiply(*jj)) */
-            double L[BB];
+            real L[BB];
             mat3_mul(Aij, lu + (size_t)diag[j] * BB, L);
             memcpy(Aij, L, sizeof L);
             /* A_ik -= L_ij * A_jk for k > j present in both rows */
@@ -196,16 +196,16 @@ int oracle_ilu0_factor3(int N, const int* rowptr, const int* colidx, double* lu)
             const int jend = rowptr[j + 1];
             while (ik < iend && jk < jend) {
                 if (colidx[ik] == colidx[jk]) {
-                    double B[BB];
+                    real B[BB];
                     mat3_mul(L, lu + (size_t)jk * BB, B);        /* B.leftmultiply(*ij) */
-                    double* Aik = lu + (size_t)ik * BB;
+                    real* Aik = lu + (size_t)ik * BB;
                     for (int q = 0; q < BB; ++q) Aik[q] -= B[q];
                     ++ik; ++jk;
                 } else if (colidx[ik] < colidx[jk]) ++ik;
                 else ++jk;
             }
         }
-        const double det = mat3_invert(lu + (size_t)diag[i] * BB);
+        const real det = mat3_invert(lu + (size_t)diag[i] * BB);
         if (!(det != 0.0) || !isfinite(det)) { free(diag); return 1 + i; }
     }
     free(diag);
@@ -215,14 +215,14 @@ int oracle_ilu0_factor3(int N, const int* rowptr, const int* colidx, double* lu)
 /* a10  preconditioner apply: Opm::ParallelOverlappingILU0::apply, sequential case.
  * Lower sweep walks columns ascending; the upper factor is stored by convertToCRS in
  * reverse order, so the upper sweep walks columns DESCENDING; then v *= w. */
-void oracle_ilu0_apply3(int N, const int* rowptr, const int* colidx, const double* lu,
-                        double w, const double* d, double* v)
+void oracle_ilu0_apply3(int N, const int* rowptr, const int* colidx, const real* lu,
+                        double w, const real* d, real* v)
 {
     for (int i = 0; i < N; ++i) {
-        double r0 = d[(size_t)i * BS], r1 = d[(size_t)i * BS + 1], r2 = d[(size_t)i * BS + 2];
+        real r0 = d[(size_t)i * BS], r1 = d[(size_t)i * BS + 1], r2 = d[(size_t)i * BS + 2];
         for (int k = rowptr[i]; k < rowptr[i + 1] && colidx[k] < i; ++k) {
-            const double* a = lu + (size_t)k * BB;
-            const double* vj = v + (size_t)colidx[k] * BS;
+            const real* a = lu + (size_t)k * BB;
+            const real* vj = v + (size_t)colidx[k] * BS;
             /* mmv: y[r] -= a[r][c] * x[c] */
             r0 = fma(-a[0], vj[0], r0); r0 = fma(-a[1], vj[1], r0); r0 = fma(-a[2], vj[2], r0);
             r1 = fma(-a[3], vj[0], r1); r1 = fma(-a[4], vj[1], r1); r1 = fma(-a[5], vj[2], r1);
@@ -231,36 +231,36 @@ void oracle_ilu0_apply3(int N, const int* rowptr, const int* colidx, const doubl
         v[(size_t)i * BS] = r0; v[(size_t)i * BS + 1] = r1; v[(size_t)i * BS + 2] = r2;
     }
     for (int i = N - 1; i >= 0; --i) {
-        double r0 = v[(size_t)i * BS], r1 = v[(size_t)i * BS + 1], r2 = v[(size_t)i * BS + 2];
+        real r0 = v[(size_t)i * BS], r1 = v[(size_t)i * BS + 1], r2 = v[(size_t)i * BS + 2];
         int k = rowptr[i + 1] - 1;
         for (; colidx[k] > i; --k) {
-            const double* a = lu + (size_t)k * BB;
-            const double* vj = v + (size_t)colidx[k] * BS;
+            const real* a = lu + (size_t)k * BB;
+            const real* vj = v + (size_t)colidx[k] * BS;
             r0 = fma(-a[0], vj[0], r0); r0 = fma(-a[1], vj[1], r0); r0 = fma(-a[2], vj[2], r0);
             r1 = fma(-a[3], vj[0], r1); r1 = fma(-a[4], vj[1], r1); r1 = fma(-a[5], vj[2], r1);
             r2 = fma(-a[6], vj[0], r2); r2 = fma(-a[7], vj[1], r2); r2 = fma(-a[8], vj[2], r2);
         }
-        const double* di = lu + (size_t)k * BB;               /* k is the diagonal now */
+        const real* di = lu + (size_t)k * BB;               /* k is the diagonal now */
         /* inv_[i].mv(rhs, vBlock): y[r] = 0; y[r] += a[r][c]*x[c] */
-        double y0 = 0.0, y1 = 0.0, y2 = 0.0;
+        real y0 = 0.0, y1 = 0.0, y2 = 0.0;
         y0 = fma(di[0], r0, y0); y0 = fma(di[1], r1, y0); y0 = fma(di[2], r2, y0);
         y1 = fma(di[3], r0, y1); y1 = fma(di[4], r1, y1); y1 = fma(di[5], r2, y1);
         y2 = fma(di[6], r0, y2); y2 = fma(di[7], r1, y2); y2 = fma(di[8], r2, y2);
         v[(size_t)i * BS] = y0; v[(size_t)i * BS + 1] = y1; v[(size_t)i * BS + 2] = y2;
     }
     if (fabs(w - 1.0) > 1e-15)                                /* relaxation_ flag */
-        for (size_t q = 0; q < (size_t)N * BS; ++q) v[q] *= w;
+        for (size_t q = 0; q < (size_t)N * BS; ++q) v[q] *= (real)w;
 }
 
 /* ------------------------------------------------------------------------------------
  * a10  Dune::BiCGSTABSolver::apply  (call site opm/autodiff/ISTLSolver.hpp:267-272),
  * Dune::SeqScalarProduct dot / norm: per-block partial sums accumulated in block order.
  * ---------------------------------------------------------------------------------- */
-static double vdot(int N, const double* x, const double* y)
+static real vdot(int N, const real* x, const real* y)
 {
-    double sum = 0.0;
+    real sum = 0.0;
     for (int i = 0; i < N; ++i) {
-        double s = 0.0;
+        real s = 0.0;
         s = fma(x[(size_t)i * BS], y[(size_t)i * BS], s);
         s = fma(x[(size_t)i * BS + 1], y[(size_t)i * BS + 1], s);
         s = fma(x[(size_t)i * BS + 2], y[(size_t)i * BS + 2], s);
@@ -268,37 +268,39 @@ static double vdot(int N, const double* x, const double* y)
     }
     return sum;
 }
-static double vnorm(int N, const double* x) { return sqrt(vdot(N, x, x)); }
+static real vnorm(int N, const real* x) { return sqrt(vdot(N, x, x)); }
 
-static void precond(int N, const int* rowptr, const int* colidx, const double* lu, double w,
-                    const double* d, double* v)
+static void precond(int N, const int* rowptr, const int* colidx, const real* lu, double w,
+                    const real* d, real* v)
 {
     if (lu) oracle_ilu0_apply3(N, rowptr, colidx, lu, w, d, v);
-    else memcpy(v, d, sizeof(double) * (size_t)N * BS);
+    else memcpy(v, d, sizeof(real) * (size_t)N * BS);
 }
 
-void oracle_bicgstab3(int N, const int* rowptr, const int* colidx, const double* vals,
-                      const double* lu, double w, double* b, double* x,
-                      double reduction, int maxiter, int max_half_steps,
+void oracle_bicgstab3(int N, const int* rowptr, const int* colidx, const real* vals,
+                      const real* lu, double w, real* b, real* x,
+                      double reduction_, int maxiter, int max_half_steps,
                       double* history, int history_cap, oracle_result* res)
 {
-    const double EPSILON = 1e-80;
+    const real EPSILON = (real)1e-80;                          /* dune: real_type EPSILON = 1e-80 (0 in float) */
+    const real reduction = (real)reduction_;
     const size_t n = (size_t)N * BS;
-    double* r = b;                                            /* X& r = b */
-    double* p = (double*)calloc(n ? n : 1, sizeof(double));
-    double* v = (double*)calloc(n ? n : 1, sizeof(double));
-    double* t = (double*)calloc(n ? n : 1, sizeof(double));
-    double* y = (double*)calloc(n ? n : 1, sizeof(double));
-    double* rt = (double*)malloc(sizeof(double) * (n ? n : 1));
-    double rho = 1.0, alpha = 1.0, omega = 1.0, rho_new, beta, h;
-    double norm, norm_0, it;
+    real* r = b;                                            /* X& r = b */
+    real* p = (real*)calloc(n ? n : 1, sizeof(real));
+    real* v = (real*)calloc(n ? n : 1, sizeof(real));
+    real* t = (real*)calloc(n ? n : 1, sizeof(real));
+    real* y = (real*)calloc(n ? n : 1, sizeof(real));
+    real* rt = (real*)malloc(sizeof(real) * (n ? n : 1));
+    real rho = 1.0, alpha = 1.0, omega = 1.0, rho_new, beta, h;
+    real norm, norm_0;
+    double it;
     int half = 0;
 
     memset(res, 0, sizeof *res);
     /* r = b - A x   (_op.applyscaleadd(-1,x,r)); t doubles as scratch */
     oracle_spmv3(N, rowptr, colidx, vals, x, t);
     for (size_t q = 0; q < n; ++q) r[q] -= t[q];
-    memcpy(rt, r, sizeof(double) * n);
+    memcpy(rt, r, sizeof(real) * n);
     norm = norm_0 = vnorm(N, r);
     res->norm0 = norm_0;
 
@@ -312,16 +314,16 @@ void oracle_bicgstab3(int N, const int* rowptr, const int* colidx, const double*
         rho_new = vdot(N, rt, r);
         if (fabs(rho) <= EPSILON || fabs(omega) <= EPSILON) { res->status = 3; break; }
         if (it < 1) {
-            memcpy(p, r, sizeof(double) * n);
+            memcpy(p, r, sizeof(real) * n);
         } else {
             beta = (rho_new / rho) * (alpha / omega);
             for (size_t q = 0; q < n; ++q) {                  /* p.axpy(-omega,v); p*=beta; p+=r */
-                double pq = fma(-omega, v[q], p[q]);
+                real pq = fma(-omega, v[q], p[q]);
                 pq *= beta;
                 p[q] = pq + r[q];
             }
         }
-        memset(y, 0, sizeof(double) * n);
+        memset(y, 0, sizeof(real) * n);
         precond(N, rowptr, colidx, lu, w, p, y);
         oracle_spmv3(N, rowptr, colidx, vals, y, v);
         h = vdot(N, rt, v);
@@ -336,7 +338,7 @@ void oracle_bicgstab3(int N, const int* rowptr, const int* colidx, const double*
         it += 0.5;
         if (max_half_steps >= 0 && half >= max_half_steps) break;
 
-        memset(y, 0, sizeof(double) * n);
+        memset(y, 0, sizeof(real) * n);
         precond(N, rowptr, colidx, lu, w, r, y);
         oracle_spmv3(N, rowptr, colidx, vals, y, t);
         omega = vdot(N, t, r) / vdot(N, t, t);
@@ -367,40 +369,40 @@ done:
  * ("parity unpinned" at the dune level; pinned by scipy and known-answer tests).
  * b is overwritten (defect of the last restart), x0 as given.
  * ---------------------------------------------------------------------------------- */
-static void gen_rotation(double dx, double dy, double* cs, double* sn)
+static void gen_rotation(real dx, real dy, real* cs, real* sn)
 {
-    const double ndx = fabs(dx), ndy = fabs(dy);
+    const real ndx = fabs(dx), ndy = fabs(dy);
     if (ndy < 1e-15) { *cs = 1.0; *sn = 0.0; }
     else if (ndx < 1e-15) { *cs = 0.0; *sn = 1.0; }
     else if (ndy > ndx) {
-        const double temp = ndx / ndy;
+        const real temp = ndx / ndy;
         *cs = 1.0 / sqrt(1.0 + temp * temp);
         *sn = *cs;
         *cs *= temp;
         *sn *= dx / ndx;
         *sn *= dy / ndy;
     } else {
-        const double temp = ndy / ndx;
+        const real temp = ndy / ndx;
         *cs = 1.0 / sqrt(1.0 + temp * temp);
         *sn = *cs;
         *sn *= dy / dx;
     }
 }
-static void apply_rotation(double* dx, double* dy, double cs, double sn)
+static void apply_rotation(real* dx, real* dy, real cs, real sn)
 {
-    const double temp = cs * (*dx) + sn * (*dy);
+    const real temp = cs * (*dx) + sn * (*dy);
     *dy = -sn * (*dx) + cs * (*dy);
     *dx = temp;
 }
 /* b -= A x  (MatrixAdapter::applyscaleadd(-1,x,b) -> BCRSMatrix::usmv: per block y -= a*x) */
-static void residual_update(int N, const int* rowptr, const int* colidx, const double* vals,
-                            const double* x, double* b)
+static void residual_update(int N, const int* rowptr, const int* colidx, const real* vals,
+                            const real* x, real* b)
 {
     for (int i = 0; i < N; ++i) {
-        double r0 = b[(size_t)i * BS], r1 = b[(size_t)i * BS + 1], r2 = b[(size_t)i * BS + 2];
+        real r0 = b[(size_t)i * BS], r1 = b[(size_t)i * BS + 1], r2 = b[(size_t)i * BS + 2];
         for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
-            const double* a = vals + (size_t)k * BB;
-            const double* xj = x + (size_t)colidx[k] * BS;
+            const real* a = vals + (size_t)k * BB;
+            const real* xj = x + (size_t)colidx[k] * BS;
             r0 = fma(-a[0], xj[0], r0); r0 = fma(-a[1], xj[1], r0); r0 = fma(-a[2], xj[2], r0);
             r1 = fma(-a[3], xj[0], r1); r1 = fma(-a[4], xj[1], r1); r1 = fma(-a[5], xj[2], r1);
             r2 = fma(-a[6], xj[0], r2); r2 = fma(-a[7], xj[1], r2); r2 = fma(-a[8], xj[2], r2);
@@ -409,27 +411,28 @@ static void residual_update(int N, const int* rowptr, const int* colidx, const d
     }
 }
 
-void oracle_gmres3(int N, const int* rowptr, const int* colidx, const double* vals,
-                   const double* lu, double wrelax, double* b, double* x,
-                   double reduction, int maxiter, int restart,
+void oracle_gmres3(int N, const int* rowptr, const int* colidx, const real* vals,
+                   const real* lu, double wrelax, real* b, real* x,
+                   double reduction_, int maxiter, int restart,
                    double* history, int history_cap, oracle_result* res)
 {
-    const double EPSILON = 1e-80;
+    const real reduction = (real)reduction_;
+    const real EPSILON = 1e-80;
     const size_t n = (size_t)N * BS;
     const int m = restart;
-    double* s = (double*)calloc((size_t)m + 1, sizeof(double));
-    double* sn = (double*)calloc((size_t)m, sizeof(double));
-    double* cs = (double*)calloc((size_t)m, sizeof(double));
-    double* H = (double*)calloc((size_t)(m + 1) * m, sizeof(double));      /* H[k][i] = H[k*m + i] */
-    double* V = (double*)calloc((size_t)(m + 1) * (n ? n : 1), sizeof(double));
-    double* w = (double*)calloc(n ? n : 1, sizeof(double));
-    double* b2 = (double*)malloc(sizeof(double) * (n ? n : 1));
-    double* yv = (double*)calloc((size_t)m + 1, sizeof(double));
-    double norm, norm_0;
+    real* s = (real*)calloc((size_t)m + 1, sizeof(real));
+    real* sn = (real*)calloc((size_t)m, sizeof(real));
+    real* cs = (real*)calloc((size_t)m, sizeof(real));
+    real* H = (real*)calloc((size_t)(m + 1) * m, sizeof(real));      /* H[k][i] = H[k*m + i] */
+    real* V = (real*)calloc((size_t)(m + 1) * (n ? n : 1), sizeof(real));
+    real* w = (real*)calloc(n ? n : 1, sizeof(real));
+    real* b2 = (real*)malloc(sizeof(real) * (n ? n : 1));
+    real* yv = (real*)calloc((size_t)m + 1, sizeof(real));
+    real norm, norm_0;
     int j = 1, nh = 0;
 
     memset(res, 0, sizeof *res);
-    memcpy(b2, b, sizeof(double) * n);
+    memcpy(b2, b, sizeof(real) * n);
     residual_update(N, rowptr, colidx, vals, x, b);               /* b -= A x */
     precond(N, rowptr, colidx, lu, wrelax, b, V);                 /* v[0] = W^-1 b */
     norm_0 = vnorm(N, V);
@@ -439,25 +442,25 @@ void oracle_gmres3(int N, const int* rowptr, const int* colidx, const double* va
 
     while (j <= maxiter && !res->converged) {
         int i = 0;
-        const double inv = 1.0 / norm;
+        const real inv = 1.0 / norm;
         for (size_t q = 0; q < n; ++q) V[q] *= inv;               /* v[0] *= 1/norm */
         s[0] = norm;
         for (i = 1; i < m + 1; ++i) s[i] = 0.0;
         for (i = 0; i < m && j <= maxiter && !res->converged; ++i, ++j) {
-            double* vi = V + (size_t)i * n;
-            double* vn = V + (size_t)(i + 1) * n;
+            real* vi = V + (size_t)i * n;
+            real* vn = V + (size_t)(i + 1) * n;
             oracle_spmv3(N, rowptr, colidx, vals, vi, vn);        /* _A.apply(v[i], v[i+1]) */
             precond(N, rowptr, colidx, lu, wrelax, vn, w);        /* _W.apply(w, v[i+1]) */
             for (int k = 0; k < i + 1; ++k) {
-                const double* vk = V + (size_t)k * n;
-                const double hki = vdot(N, vk, w);
+                const real* vk = V + (size_t)k * n;
+                const real hki = vdot(N, vk, w);
                 H[(size_t)k * m + i] = hki;
                 for (size_t q = 0; q < n; ++q) w[q] = fma(-hki, vk[q], w[q]);     /* w.axpy(-H[k][i], v[k]) */
             }
-            const double hn = vnorm(N, w);
+            const real hn = vnorm(N, w);
             H[(size_t)(i + 1) * m + i] = hn;
             if (fabs(hn) < EPSILON) { res->status = 3; goto finish; }             /* breakdown */
-            const double hinv = 1.0 / hn;
+            const real hinv = 1.0 / hn;
             for (size_t q = 0; q < n; ++q) vn[q] = w[q] * hinv;                   /* v[i+1] = w; v[i+1] *= 1/H */
             for (int k = 0; k < i; ++k)
                 apply_rotation(&H[(size_t)k * m + i], &H[(size_t)(k + 1) * m + i], cs[k], sn[k]);
@@ -470,18 +473,18 @@ void oracle_gmres3(int N, const int* rowptr, const int* colidx, const double* va
             if (norm < reduction * norm_0) res->converged = 1;
         }
         /* update(w, i, H, s, v): back substitution, x += sum y[a] v[a] accumulated in w */
-        memset(w, 0, sizeof(double) * n);
+        memset(w, 0, sizeof(real) * n);
         for (int a = 0; a < m + 1; ++a) yv[a] = s[a];
         for (int a = i - 1; a >= 0; --a) {
-            double rhs = s[a];
+            real rhs = s[a];
             for (int c = a + 1; c < i; ++c) rhs -= H[(size_t)a * m + c] * yv[c];
             yv[a] = rhs / H[(size_t)a * m + a];
-            const double* va = V + (size_t)a * n;
+            const real* va = V + (size_t)a * n;
             for (size_t q = 0; q < n; ++q) w[q] = fma(yv[a], va[q], w[q]);
         }
         for (size_t q = 0; q < n; ++q) x[q] += w[q];
         if (!res->converged && j <= maxiter) {
-            memcpy(b, b2, sizeof(double) * n);
+            memcpy(b, b2, sizeof(real) * n);
             residual_update(N, rowptr, colidx, vals, x, b);
             precond(N, rowptr, colidx, lu, wrelax, b, V);
             norm = vnorm(N, V);
@@ -497,34 +500,34 @@ done:
 }
 
 /* factor + GMRES on a BCRS system (vals untouched), x0 = 0 */
-void oracle_solve_gmres_bcrs3(int N, const int* rowptr, const int* colidx, const double* vals,
-                              const double* rhs_cellmajor, double* x_cellmajor,
+void oracle_solve_gmres_bcrs3(int N, const int* rowptr, const int* colidx, const real* vals,
+                              const real* rhs_cellmajor, real* x_cellmajor,
                               double reduction, int maxiter, double relax, int restart,
                               oracle_result* res)
 {
     const size_t nnzb = (size_t)rowptr[N];
-    double* lu = (double*)malloc(sizeof(double) * (nnzb ? nnzb : 1) * BB);
-    double* b = (double*)malloc(sizeof(double) * ((size_t)N * BS + 1));
-    memcpy(lu, vals, sizeof(double) * nnzb * BB);
-    memcpy(b, rhs_cellmajor, sizeof(double) * (size_t)N * BS);
-    memset(x_cellmajor, 0, sizeof(double) * (size_t)N * BS);
+    real* lu = (real*)malloc(sizeof(real) * (nnzb ? nnzb : 1) * BB);
+    real* b = (real*)malloc(sizeof(real) * ((size_t)N * BS + 1));
+    memcpy(lu, vals, sizeof(real) * nnzb * BB);
+    memcpy(b, rhs_cellmajor, sizeof(real) * (size_t)N * BS);
+    memset(x_cellmajor, 0, sizeof(real) * (size_t)N * BS);
     const int bad = oracle_ilu0_factor3(N, rowptr, colidx, lu);
     if (bad) { memset(res, 0, sizeof *res); res->status = 2; res->bad_row = bad - 1; }
     else oracle_gmres3(N, rowptr, colidx, vals, lu, relax, b, x_cellmajor, reduction, maxiter, restart, NULL, 0, res);
     free(lu); free(b);
 }
 
-void oracle_solve_bcrs3(int N, const int* rowptr, const int* colidx, const double* vals,
-                        const double* rhs_cellmajor, double* x_cellmajor,
+void oracle_solve_bcrs3(int N, const int* rowptr, const int* colidx, const real* vals,
+                        const real* rhs_cellmajor, real* x_cellmajor,
                         double reduction, int maxiter, double relax, int max_half_steps,
                         oracle_result* res)
 {
     const size_t nnzb = (size_t)rowptr[N];
-    double* lu = (double*)malloc(sizeof(double) * (nnzb ? nnzb : 1) * BB);
-    double* b = (double*)malloc(sizeof(double) * ((size_t)N * BS + 1));
-    memcpy(lu, vals, sizeof(double) * nnzb * BB);             /* ILU works on a copy of A */
-    memcpy(b, rhs_cellmajor, sizeof(double) * (size_t)N * BS);
-    memset(x_cellmajor, 0, sizeof(double) * (size_t)N * BS);  /* x = 0.0, ...Interleaved.cpp:272-273 */
+    real* lu = (real*)malloc(sizeof(real) * (nnzb ? nnzb : 1) * BB);
+    real* b = (real*)malloc(sizeof(real) * ((size_t)N * BS + 1));
+    memcpy(lu, vals, sizeof(real) * nnzb * BB);             /* ILU works on a copy of A */
+    memcpy(b, rhs_cellmajor, sizeof(real) * (size_t)N * BS);
+    memset(x_cellmajor, 0, sizeof(real) * (size_t)N * BS);  /* x = 0.0, ...Interleaved.cpp:272-273 */
     const int bad = oracle_ilu0_factor3(N, rowptr, colidx, lu);
     if (bad) {
         memset(res, 0, sizeof *res);
@@ -536,7 +539,7 @@ void oracle_solve_bcrs3(int N, const int* rowptr, const int* colidx, const doubl
     free(lu); free(b);
 }
 
-/* a6..a11  Impl<3,double>::computeNewtonIncrement without wells (...Interleaved.cpp:234-283) */
+/* a6..a11  Impl<3,real>::computeNewtonIncrement without wells (...Interleaved.cpp:234-283) */
 void oracle_solve_from_csc_blocks(int N, const oracle_csc* blocks9, const double* matbalscale,
                                   const double* rhs_eqmajor, double* dx_varmajor,
                                   double reduction, int maxiter, double relax,
@@ -545,9 +548,9 @@ void oracle_solve_from_csc_blocks(int N, const oracle_csc* blocks9, const double
     int* rowptr = (int*)malloc(sizeof(int) * ((size_t)N + 1));
     int* colidx = NULL;
     const int nnzb = oracle_interleave_pattern(N, BS, blocks9, require_full, rowptr, &colidx);
-    double* vals = (double*)malloc(sizeof(double) * (size_t)(nnzb > 0 ? nnzb : 1) * BB);
-    double* b = (double*)malloc(sizeof(double) * ((size_t)N * BS + 1));
-    double* x = (double*)malloc(sizeof(double) * ((size_t)N * BS + 1));
+    real* vals = (real*)malloc(sizeof(real) * (size_t)(nnzb > 0 ? nnzb : 1) * BB);
+    real* b = (real*)malloc(sizeof(real) * ((size_t)N * BS + 1));
+    real* x = (real*)malloc(sizeof(real) * ((size_t)N * BS + 1));
     const int bad = oracle_interleave_values(N, BS, blocks9, matbalscale, rowptr, colidx, vals);
     if (bad) {
         memset(res, 0, sizeof *res);
@@ -556,7 +559,7 @@ void oracle_solve_from_csc_blocks(int N, const oracle_csc* blocks9, const double
         /* b is the concatenation of the SCALED equation values (:234-253), interleaved at :263-269 */
         for (int i = 0; i < N; ++i)
             for (int pp = 0; pp < BS; ++pp)
-                b[(size_t)i * BS + pp] = rhs_eqmajor[(size_t)pp * N + i] * matbalscale[pp];
+                b[(size_t)i * BS + pp] = (real)(rhs_eqmajor[(size_t)pp * N + i] * matbalscale[pp]);
         oracle_solve_bcrs3(N, rowptr, colidx, vals, b, x, reduction, maxiter, relax, -1, res);
         for (int i = 0; i < N; ++i)                           /* :279-283 */
             for (int pp = 0; pp < BS; ++pp)

@@ -37,6 +37,16 @@ typedef struct {
     const double* val;      /* nnz values                          */
 } oracle_csc;
 
+/* Scalar type of the instance: double = the reference's Impl<3,double>, float (build with
+ * -DORACLE_REAL=float -> liboracle_f32.so) = its Impl<3,float>, selected by
+ * LinearisedBlackoilResidual::singlePrecision (NewtonIterationBlackoilInterleaved.cpp:467-487).
+ * Matrix values, factors and vectors are `real`; the caller-side data (CSC Jacobian values,
+ * scaling, equation-major right-hand side and increment) and the parameters stay double. */
+#ifndef ORACLE_REAL
+#define ORACLE_REAL double
+#endif
+typedef ORACLE_REAL real;
+
 typedef struct {
     int    iterations;      /* ceil(it), dune convention                     */
     int    converged;       /* 1 when a stop test fired                      */
@@ -58,20 +68,20 @@ int oracle_interleave_pattern(int N, int np, const oracle_csc* blocks, int requi
  * block ([p1][p2]); eq p1 is multiplied by scale[p1] first.  Returns -(k+1) if entry k
  * falls outside the pattern (dune throws there).  ...Interleaved.cpp:178-193, :234-236. */
 int oracle_interleave_values(int N, int np, const oracle_csc* blocks, const double* scale,
-                             const int* rowptr, const int* colidx, double* vals);
+                             const int* rowptr, const int* colidx, real* vals);
 
 /* y = A x, Dune::BCRSMatrix::mv: y=0 then umv per block, ascending columns. */
-void oracle_spmv3(int N, const int* rowptr, const int* colidx, const double* vals,
-                  const double* x, double* y);
+void oracle_spmv3(int N, const int* rowptr, const int* colidx, const real* vals,
+                  const real* x, real* y);
 
 /* In-place block ILU(0), natural order (Dune::bilu0_decomposition); diagonal blocks end
  * up INVERTED (Opm::MatrixBlock 3x3 cofactor inverse).  Returns 0, or 1+row on a missing /
  * singular diagonal block. */
-int oracle_ilu0_factor3(int N, const int* rowptr, const int* colidx, double* lu);
+int oracle_ilu0_factor3(int N, const int* rowptr, const int* colidx, real* lu);
 
 /* v = w * U^-1 L^-1 d  (Opm::ParallelOverlappingILU0::apply, sequential case). */
-void oracle_ilu0_apply3(int N, const int* rowptr, const int* colidx, const double* lu,
-                        double w, const double* d, double* v);
+void oracle_ilu0_apply3(int N, const int* rowptr, const int* colidx, const real* lu,
+                        double w, const real* d, real* v);
 
 /* Dune::BiCGSTABSolver::apply with SeqScalarProduct, x0 as given (caller passes zeros),
  * preconditioner = oracle_ilu0_apply3 on `lu` (pass lu=NULL for the identity).
@@ -79,12 +89,12 @@ void oracle_ilu0_apply3(int N, const int* rowptr, const int* colidx, const doubl
  * extra limit; otherwise the loop also stops after that many half iterations (used to
  * compare iterates at equal half-step counts).  history (optional) receives |r| after
  * every half step, at most history_cap entries. */
-void oracle_bicgstab3(int N, const int* rowptr, const int* colidx, const double* vals,
-                      const double* lu, double w, double* b, double* x,
+void oracle_bicgstab3(int N, const int* rowptr, const int* colidx, const real* vals,
+                      const real* lu, double w, real* b, real* x,
                       double reduction, int maxiter, int max_half_steps,
                       double* history, int history_cap, oracle_result* res);
 
-/* The whole reference path a6..a11 for np = 3 (Impl<3,double>::computeNewtonIncrement,
+/* The whole reference path a6..a11 for np = 3 (Impl<3,real>::computeNewtonIncrement,
  * ...Interleaved.cpp:234-283, with the wells already eliminated): scale, pattern, values,
  * interleave rhs, ILU0, BiCGStab, de-interleave.  rhs_eqmajor / dx_varmajor have 3N
  * entries with stride N. */
@@ -94,20 +104,20 @@ void oracle_solve_from_csc_blocks(int N, const oracle_csc* blocks9, const double
                                   int require_full, oracle_result* res);
 
 /* Convenience: factor + solve on a BCRS system (vals untouched). */
-void oracle_solve_bcrs3(int N, const int* rowptr, const int* colidx, const double* vals,
-                        const double* rhs_cellmajor, double* x_cellmajor,
+void oracle_solve_bcrs3(int N, const int* rowptr, const int* colidx, const real* vals,
+                        const real* rhs_cellmajor, real* x_cellmajor,
                         double reduction, int maxiter, double relax, int max_half_steps,
                         oracle_result* res);
 
 /* Dune::RestartedGMResSolver::apply (dune-istl 2.6: left preconditioned, modified Gram-Schmidt,
  * Givens rotations; ISTLSolver.hpp:257-265 with restart = linear_solver_restart).  iterations =
  * Arnoldi steps; history receives the preconditioned defect norm after every step. */
-void oracle_gmres3(int N, const int* rowptr, const int* colidx, const double* vals,
-                   const double* lu, double w, double* b, double* x,
+void oracle_gmres3(int N, const int* rowptr, const int* colidx, const real* vals,
+                   const real* lu, double w, real* b, real* x,
                    double reduction, int maxiter, int restart,
                    double* history, int history_cap, oracle_result* res);
-void oracle_solve_gmres_bcrs3(int N, const int* rowptr, const int* colidx, const double* vals,
-                              const double* rhs_cellmajor, double* x_cellmajor,
+void oracle_solve_gmres_bcrs3(int N, const int* rowptr, const int* colidx, const real* vals,
+                              const real* rhs_cellmajor, real* x_cellmajor,
                               double reduction, int maxiter, double relax, int restart,
                               oracle_result* res);
 

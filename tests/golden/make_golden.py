@@ -19,7 +19,22 @@ from oracle import oracle_py as O  # noqa: E402
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
+def dump_f32(name, rp, ci, v, b, x_probe):
+    """The same quantities from the float instance of the oracle (Impl<3,float>): float32 arrays."""
+    F = O.f32
+    os.makedirs(os.path.join(HERE, "f32"), exist_ok=True)
+    lu, bad = F.ilu0_factor(rp, ci, v)
+    assert bad == -1
+    x, res = F.solve_bcrs(rp, ci, v, b)
+    np.savez_compressed(os.path.join(HERE, "f32", name + ".npz"), rowptr=rp, colidx=ci, vals=v, rhs=b, x_probe=x_probe,
+                        spmv=F.spmv(rp, ci, v, x_probe), lu=lu, apply_w09=F.ilu0_apply(rp, ci, lu, 0.9, b),
+                        apply_w1=F.ilu0_apply(rp, ci, lu, 1.0, b), x=x, iterations=res["iterations"],
+                        half_steps=res["half_steps"], reduction=res["reduction"])
+    print("f32/" + name, "iterations", res["iterations"])
+
+
 def dump(name, rp, ci, v, b, x_probe):
+    dump_f32(name, rp, ci, v, b, x_probe)
     lu, bad = O.ilu0_factor(rp, ci, v)
     assert bad == -1
     x, res = O.solve_bcrs(rp, ci, v, b)

@@ -191,3 +191,54 @@ def test_gmres_known_answers():
     rp, ci, v, b = s2.rowptr.numpy(), s2.colidx.numpy(), s2.vals.numpy(), s2.rhs.numpy()
     x, res = o.solve_gmres_bcrs(rp, ci, v, b, reduction=1e-14, maxiter=3)
     assert res["iterations"] == 3 and res["converged"] == 0 and res["status"] == 1
+
+
+# ---- the float instance of the oracle (Impl<3,float>, liboracle_f32.so) -----------------------------
+GOLDEN_F32 = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "f32", "*.npz")))
+
+
+def test_float_oracle_is_the_same_algorithm_in_float(oracle):
+    """Pins of the float build: (1) the interleaved values are the double ones rounded ONCE (the
+    assignment to a float matrix, ...Interleaved.cpp:189); (2) SpMV and ILU0 apply of float-representable
+    data agree with the double oracle to float accuracy and are float-valued; (3) block-tridiagonal
+    system: ILU0 is the exact LU, one iteration also in float; (4) iteration count at the reference's
+    tolerance equals the double instance's on a well-conditioned case."""
+    from opm_simulators_legacy_b200.jacobian import synth_blackoil_jacobian
+    s = synth_blackoil_jacobian(12, 9, 7, perm="lognormal")
+    rp, ci, v, b = s.rowptr.numpy(), s.colidx.numpy(), s.vals.numpy(), s.rhs.numpy()
+    blocks = s.csc_blocks()
+    rp64, ci64, v64 = oracle.interleave(s.N, blocks, s.matbalscale)
+    rp32, ci32, v32 = oracle.f32.interleave(s.N, blocks, s.matbalscale)
+    assert v32.dtype == np.float32 and np.array_equal(rp32, rp64) and np.array_equal(ci32, ci64)
+    assert np.array_equal(v32, v64.astype(np.float32))
+    x = s.xstar.numpy()
+    y32, y64 = oracle.f32.spmv(rp, ci, v, x), oracle.spmv(rp, ci, v, x)
+    assert y32.dtype == np.float32
+    assert np.abs(y32 - y64).max() <= 2e-5 * np.abs(y64).max()
+    lu32, bad = oracle.f32.ilu0_factor(rp, ci, v)
+    lu64, _ = oracle.ilu0_factor(rp, ci, v)
+    assert bad == -1 and np.abs(lu32 - lu64).max() <= 1e-4 * np.abs(lu64).max()
+    a32, a64 = oracle.f32.ilu0_apply(rp, ci, lu32, 0.9, b), oracle.ilu0_apply(rp, ci, lu64, 0.9, b)
+    assert np.abs(a32 - a64).max() <= 1e-3 * np.abs(a64).max()
+    x32, r32 = oracle.f32.solve_bcrs(rp, ci, v, b)
+    x64, r64 = oracle.solve_bcrs(rp, ci, v, b)
+    assert r32["iterations"] == r64["iterations"] and r32["converged"] == 1
+    t = synth_blackoil_jacobian(40, 1, 1, perm="lognormal")
+    rpt, cit, vt, bt = t.rowptr.numpy(), t.colidx.numpy(), t.vals.numpy(), t.rhs.numpy()
+    xt, rt = oracle.f32.solve_bcrs(rpt, cit, vt, bt, reduction=1e-4, relax=1.0)
+    assert rt["iterations"] == 1 and rt["converged"] == 1
+    assert np.abs(xt - t.xstar.numpy()).max() <= 1e-3 * np.abs(t.xstar.numpy()).max()
+
+
+@pytest.mark.parametrize("path", GOLDEN_F32, ids=[os.path.basename(p)[:-4] for p in GOLDEN_F32])
+def test_float_oracle_reproduces_golden(oracle, path):
+    g = np.load(path)
+    rp, ci, v, b = g["rowptr"], g["colidx"], g["vals"], g["rhs"]
+    F = oracle.f32
+    assert np.array_equal(F.spmv(rp, ci, v, g["x_probe"]), g["spmv"])
+    lu, bad = F.ilu0_factor(rp, ci, v)
+    assert bad == -1 and np.array_equal(lu, g["lu"])
+    assert np.array_equal(F.ilu0_apply(rp, ci, lu, 0.9, b), g["apply_w09"])
+    assert np.array_equal(F.ilu0_apply(rp, ci, lu, 1.0, b), g["apply_w1"])
+    x, res = F.solve_bcrs(rp, ci, v, b)
+    assert res["iterations"] == int(g["iterations"]) and np.array_equal(x, g["x"])
