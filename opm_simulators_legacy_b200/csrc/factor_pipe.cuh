@@ -61,8 +61,9 @@ __host__ __device__ inline size_t factor_pipe_smem_bytes(int nstages, int stage_
     return 512 + (size_t)kFDepBytes + (size_t)nstages * (size_t)stage_bytes;
 }
 
-// A blocks (BCRS) -> step records: one thread per block row (3 values; TA = type the blocks are stored in)
-template <class TA>
+// A blocks (BCRS) -> step records: one thread per block row (3 values).  TA = type the blocks are
+// stored in; CONT: they are containers already (the rank's diagonal block of a partitioned system)
+template <class TA, bool CONT = false>
 __global__ void __launch_bounds__(256)
 pack_factor_records_kernel(size_t nval, const int* __restrict__ src, const unsigned* __restrict__ dst8,
                            const TA* __restrict__ vals, double* __restrict__ bufd)
@@ -74,7 +75,8 @@ pack_factor_records_kernel(size_t nval, const int* __restrict__ src, const unsig
     const TA* a = vals + (size_t)src[b] * 9 + c * 3;
     double* d = bufd + (size_t)dst8[b] + c * 3;
     const TA a0 = a[0], a1 = a[1], a2 = a[2];
-    d[0] = (double)a0; d[1] = (double)a1; d[2] = (double)a2;
+    if (CONT) { d[0] = (double)a0; d[1] = (double)a1; d[2] = (double)a2; }       // (TA = double: a plain copy)
+    else { d[0] = enc(a0); d[1] = enc(a1); d[2] = enc(a2); }
 }
 
 template <class AT>
@@ -245,7 +247,7 @@ ilu0_factor_pipe_kernel(FactorPipeDev pg, int* bad_row, int* err)
                         ri0 = rip[0]; ri1 = rip[1]; ri2 = rip[2];
                         const double* vp = reinterpret_cast<const double*>(rec + 32 + (size_t)n * (kFRowInts * 4)) + (size_t)r * kFRowVals;
 #pragma unroll
-                        for (int q = 0; q < kFRowVals; ++q) v[q] = (AT)vp[q];
+                        for (int q = 0; q < kFRowVals; ++q) v[q] = dec<AT>(vp[q]);
                     }
                 } else dead = true;
             }
@@ -273,7 +275,7 @@ ilu0_factor_pipe_kernel(FactorPipeDev pg, int* bad_row, int* err)
                         const double* dj = dep + (size_t)de * kFEntry;
                         AT Dj[9], L[9];
 #pragma unroll
-                        for (int t = 0; t < 9; ++t) Dj[t] = (AT)dj[t];
+                        for (int t = 0; t < 9; ++t) Dj[t] = dec<AT>(dj[t]);
 #pragma unroll
                         for (int c = 0; c < 3; ++c)
 #pragma unroll
@@ -299,7 +301,7 @@ ilu0_factor_pipe_kernel(FactorPipeDev pg, int* bad_row, int* err)
                 det = factor_invert3(D);
                 double* w = dep + (size_t)ri1.w * kFEntry;
 #pragma unroll
-                for (int t = 0; t < 9; ++t) w[t] = (double)D[t];
+                for (int t = 0; t < 9; ++t) w[t] = enc(D[t]);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // window -> bulk store
             }
             asm volatile("bar.arrive %0, %1;" ::"r"(bar_own), "n"(NPP) : "memory");                // step s done
@@ -308,12 +310,12 @@ ilu0_factor_pipe_kernel(FactorPipeDev pg, int* bad_row, int* err)
                 if (ri1.y >= 0) {
                     double* sl = pg.ext + (size_t)ri1.y * 9;
 #pragma unroll
-                    for (int t = 0; t < 9; ++t) push_f64(sl + t, (double)D[t]);
+                    for (int t = 0; t < 9; ++t) push_f64(sl + t, enc(D[t]));
                 }
                 if (ri1.z >= 0) {
                     double* sl = pg.ext + (size_t)ri1.z * 9;
 #pragma unroll
-                    for (int t = 0; t < 9; ++t) push_f64(sl + t, (double)D[t]);
+                    for (int t = 0; t < 9; ++t) push_f64(sl + t, enc(D[t]));
                 }
             }
             if (elected && s > 0) factor_store_step(pg, dep, row_base, prev_q0, prev_n);
@@ -344,8 +346,8 @@ ilu0_factor_pipe_kernel(FactorPipeDev pg, int* bad_row, int* err)
 // inv(D_j) (the factorisation's own three fused multiply-adds per element), a diagonal block
 // becomes row c of inv(D_j), an upper block is A's.  Element [c][e] goes to dst8[b] + c*stride[b] + e.
 // PART 0: everything, 1: only the blocks copied from A, 2: only the pivots
-// TA: type A is stored in, AT: arithmetic type of the product.
-template <bool LOWER, int PART, class TA, class AT>
+// TA: type A is stored in (CONT: as containers), AT: arithmetic type of the product.
+template <bool LOWER, int PART, class TA, class AT, bool CONT = false>
 __global__ void __launch_bounds__(256)
 repack_pipe2_kernel(size_t nval, const int* __restrict__ src, const unsigned* __restrict__ dst8,
                     const int* __restrict__ stride, const int* __restrict__ colidx, const int* __restrict__ diag,
@@ -368,14 +370,16 @@ repack_pipe2_kernel(size_t nval, const int* __restrict__ src, const unsigned* __
             const TA* a = A + (size_t)k * 9 + c * 3;
             if (LOWER) {
                 const double* d = fout + (size_t)fpos[j] * kFEntry;
-                const AT a0 = (AT)a[0], a1 = (AT)a[1], a2 = (AT)a[2];
+                const AT a0 = CONT ? dec<AT>((double)a[0]) : (AT)a[0], a1 = CONT ? dec<AT>((double)a[1]) : (AT)a[1],
+                         a2 = CONT ? dec<AT>((double)a[2]) : (AT)a[2];
 #pragma unroll
                 for (int e = 0; e < 3; ++e) {
                     AT sacc = AT(0);
-                    sacc = fma(a0, (AT)d[e], sacc); sacc = fma(a1, (AT)d[3 + e], sacc); sacc = fma(a2, (AT)d[6 + e], sacc);
-                    o[e] = (double)sacc;
+                    sacc = fma(a0, dec<AT>(d[e]), sacc); sacc = fma(a1, dec<AT>(d[3 + e]), sacc); sacc = fma(a2, dec<AT>(d[6 + e]), sacc);
+                    o[e] = enc(sacc);
                 }
-            } else { o[0] = (double)a[0]; o[1] = (double)a[1]; o[2] = (double)a[2]; }
+            } else if (CONT) { o[0] = (double)a[0]; o[1] = (double)a[1]; o[2] = (double)a[2]; }
+            else { o[0] = enc((AT)a[0]); o[1] = enc((AT)a[1]); o[2] = enc((AT)a[2]); }
         }
         double* dst = bufd + (size_t)dst8[b] + (size_t)c * stride[b];
         dst[0] = o[0]; dst[1] = o[1]; dst[2] = o[2];
@@ -399,12 +403,12 @@ materialise_lu_kernel(int N, const int* __restrict__ rowptr, const int* __restri
         const double* d = fout + (size_t)fpos[j] * kFEntry;
         if (j == i) { a[0] = d[c * 3]; a[1] = d[c * 3 + 1]; a[2] = d[c * 3 + 2]; }
         else {
-            const AT a0 = (AT)a[0], a1 = (AT)a[1], a2 = (AT)a[2];
+            const AT a0 = dec<AT>(a[0]), a1 = dec<AT>(a[1]), a2 = dec<AT>(a[2]);
 #pragma unroll
             for (int e = 0; e < 3; ++e) {
                 AT sacc = AT(0);
-                sacc = fma(a0, (AT)d[e], sacc); sacc = fma(a1, (AT)d[3 + e], sacc); sacc = fma(a2, (AT)d[6 + e], sacc);
-                a[e] = (double)sacc;
+                sacc = fma(a0, dec<AT>(d[e]), sacc); sacc = fma(a1, dec<AT>(d[3 + e]), sacc); sacc = fma(a2, dec<AT>(d[6 + e]), sacc);
+                a[e] = enc(sacc);
             }
         }
     }

@@ -5,9 +5,9 @@
 // arithmetic is a template on the scalar type T: double is the reference's Impl<3,double>, float its
 // Impl<3,float> (NewtonIterationBlackoilInterleaved.cpp:478-480, selected by
 // LinearisedBlackoilResidual::singlePrecision).  In the float instance the matrix values and all
-// vectors are stored as float; the ILU0 factors, the sweep records and the scalar block keep
-// their 8-byte containers (every value in them is a float widened exactly), so the layouts the host
-// analysis produces are the same for both instances.  Arithmetic order inside
+// vectors are stored as float; the ILU0 factors and the sweep records keep their 8-byte containers
+// (enc / dec below), the scalar block holds floats widened exactly, so the layouts the host analysis
+// produces are the same for both instances.  Arithmetic order inside
 // a block row follows the reference's dune-istl loops so that SpMV, the ILU0 factors and the
 // ILU0 sweeps are bit-identical to the CPU oracle: every `y +-= a*x` is one fma(), nothing
 // else is contracted (the file is compiled with -fmad=false).
@@ -16,6 +16,17 @@
 #include <stdint.h>
 
 namespace opmgpu {
+
+// 8-byte containers of the factor arrays, sweep / factorisation records, windows, push slots and
+// program-ordered right-hand sides.  The double instance stores the value itself.  The float
+// instance stores the float's bit pattern in the UPPER word (lower word 0): reading it back is a
+// register move, not a conversion instruction on the sweeps' critical path, and the all-ones
+// "empty" pattern of the self-validating slots stays a NaN no arithmetic produces.
+template <class T> __device__ __forceinline__ T dec(double c);
+template <> __device__ __forceinline__ double dec<double>(double c) { return c; }
+template <> __device__ __forceinline__ float dec<float>(double c) { return __int_as_float(__double2hiint(c)); }
+__device__ __forceinline__ double enc(double v) { return v; }
+__device__ __forceinline__ double enc(float v) { return __hiloint2double(__float_as_int(v), 0); }
 
 constexpr int kBS = 3;
 constexpr int kBB = 9;
@@ -203,7 +214,7 @@ bicg_update_p_kernel(size_t n, T* __restrict__ p, const T* __restrict__ r,
         pq *= beta;
         const T pn = pq + r[i];
         p[i] = pn;
-        if (lpos) { const size_t row = i / 3; pperm[(size_t)lpos[row] * 3 + (i - row * 3)] = (double)pn; }
+        if (lpos) { const size_t row = i / 3; pperm[(size_t)lpos[row] * 3 + (i - row * 3)] = enc(pn); }
     }
 }
 
@@ -221,7 +232,7 @@ bicg_update1_kernel(size_t n, T* __restrict__ x, T* __restrict__ r,
         x[i] = fma(alpha, y[i], x[i]);
         const T ri = fma(-alpha, v[i], r[i]);
         r[i] = ri;
-        if (lpos) { const size_t row = i / 3; rperm[(size_t)lpos[row] * 3 + (i - row * 3)] = (double)ri; }     // see bicg_update_p_kernel
+        if (lpos) { const size_t row = i / 3; rperm[(size_t)lpos[row] * 3 + (i - row * 3)] = enc(ri); }     // see bicg_update_p_kernel
         s[0] = fma(ri, ri, s[0]);
     }
     grid_reduce<1, T>(s, ws, [=](T (&t)[1]) {
@@ -329,10 +340,10 @@ ilu0_factor_level_kernel(const int* __restrict__ lvl_rows, int begin, int end,
         AT Aij[9], Dj[9], L[9];
         const int jd = diag[j];
 #pragma unroll
-        for (int t = 0; t < 9; ++t) { Aij[t] = (AT)lu[(size_t)ij * 9 + t]; Dj[t] = (AT)lu[(size_t)jd * 9 + t]; }
+        for (int t = 0; t < 9; ++t) { Aij[t] = dec<AT>(lu[(size_t)ij * 9 + t]); Dj[t] = dec<AT>(lu[(size_t)jd * 9 + t]); }
         mat3_mul(Aij, Dj, L);                                 // L_ij = A_ij * inv(A_jj)
 #pragma unroll
-        for (int t = 0; t < 9; ++t) lu[(size_t)ij * 9 + t] = (double)L[t];
+        for (int t = 0; t < 9; ++t) lu[(size_t)ij * 9 + t] = enc(L[t]);
         int jk = jd + 1, ik = ij + 1;
         const int jend = rowptr[j + 1];
         while (ik < iend && jk < jend) {
@@ -340,10 +351,10 @@ ilu0_factor_level_kernel(const int* __restrict__ lvl_rows, int begin, int end,
             if (ci == cj) {
                 AT Ajk[9], B[9];
 #pragma unroll
-                for (int t = 0; t < 9; ++t) Ajk[t] = (AT)lu[(size_t)jk * 9 + t];
+                for (int t = 0; t < 9; ++t) Ajk[t] = dec<AT>(lu[(size_t)jk * 9 + t]);
                 mat3_mul(L, Ajk, B);                          // B = L_ij * A_jk
 #pragma unroll
-                for (int t = 0; t < 9; ++t) lu[(size_t)ik * 9 + t] = (double)((AT)lu[(size_t)ik * 9 + t] - B[t]);
+                for (int t = 0; t < 9; ++t) lu[(size_t)ik * 9 + t] = enc(dec<AT>(lu[(size_t)ik * 9 + t]) - B[t]);
                 ++ik; ++jk;
             } else if (ci < cj) ++ik;
             else ++jk;
@@ -351,10 +362,10 @@ ilu0_factor_level_kernel(const int* __restrict__ lvl_rows, int begin, int end,
     }
     AT D[9];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) D[t] = (AT)lu[(size_t)idiag * 9 + t];
+    for (int t = 0; t < 9; ++t) D[t] = dec<AT>(lu[(size_t)idiag * 9 + t]);
     const AT det = mat3_invert(D);
 #pragma unroll
-    for (int t = 0; t < 9; ++t) lu[(size_t)idiag * 9 + t] = (double)D[t];
+    for (int t = 0; t < 9; ++t) lu[(size_t)idiag * 9 + t] = enc(D[t]);
     if (!(det != AT(0)) || isinf(det) || isnan(det)) atomicMin(bad_row, i);
 }
 
@@ -395,7 +406,7 @@ __device__ __forceinline__ bool factor_poll_slot(const double* slot, AT (&d)[9],
         }
         if (ok) {
 #pragma unroll
-            for (int t = 0; t < 9; ++t) d[t] = (AT)__longlong_as_double(v[t]);
+            for (int t = 0; t < 9; ++t) d[t] = dec<AT>(__longlong_as_double(v[t]));
             return true;
         }
         if (++spins > (1u << 22)) { atomicExch(err, 6); return false; }
@@ -413,7 +424,7 @@ template <class AT>
 __device__ __forceinline__ void load9(AT (&d)[9], const double* p, bool bypass_l1)
 {
 #pragma unroll
-    for (int t = 0; t < 9; ++t) d[t] = (AT)(bypass_l1 ? __ldcg(p + t) : p[t]);
+    for (int t = 0; t < 9; ++t) d[t] = dec<AT>(bypass_l1 ? __ldcg(p + t) : p[t]);
 }
 __device__ __forceinline__ bool factor_wait_row(const int* flags, int j, int epoch, int* err)
 {
@@ -494,12 +505,12 @@ ilu0_factor_tile_kernel(FactorDev pg, double* lu, int* flags, int epoch, int* ba
                         jk0[k] = eb.x; rearm[k] = eb.w;
                     }
 #pragma unroll
-                for (int t = 0; t < 3; ++t) Drow[t] = (AT)lu[(size_t)idiag * 9 + c * 3 + t];
+                for (int t = 0; t < 3; ++t) Drow[t] = dec<AT>(lu[(size_t)idiag * 9 + c * 3 + t]);
 #pragma unroll
                 for (int k = 0; k < 3; ++k)
                     if (k < n) {
 #pragma unroll
-                        for (int t = 0; t < 3; ++t) Arow[k][t] = (AT)lu[(size_t)ea[k].x * 9 + c * 3 + t];
+                        for (int t = 0; t < 3; ++t) Arow[k][t] = dec<AT>(lu[(size_t)ea[k].x * 9 + c * 3 + t]);
                     }
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
@@ -523,7 +534,7 @@ ilu0_factor_tile_kernel(FactorDev pg, double* lu, int* flags, int epoch, int* ba
                         AT Lrow[3], Brow[3];
                         mat3_row_mul(Arow[k], Dj[k], Lrow);                 // L_ij = A_ij * inv(A_jj)
 #pragma unroll
-                        for (int t = 0; t < 3; ++t) lu[(size_t)ea[k].x * 9 + c * 3 + t] = (double)Lrow[t];
+                        for (int t = 0; t < 3; ++t) lu[(size_t)ea[k].x * 9 + c * 3 + t] = enc(Lrow[t]);
                         if (ea[k].w) {
                             mat3_row_mul(Lrow, Ajk[k], Brow);               // A_ii -= L_ij * A_ji
 #pragma unroll
@@ -545,7 +556,7 @@ ilu0_factor_tile_kernel(FactorDev pg, double* lu, int* flags, int epoch, int* ba
                     load9(Dj, lu + (size_t)ea.y * 9, ext);
                     mat3_mul(Aij, Dj, L);
 #pragma unroll
-                    for (int t = 0; t < 9; ++t) lu[(size_t)ij * 9 + t] = (double)L[t];
+                    for (int t = 0; t < 9; ++t) lu[(size_t)ij * 9 + t] = enc(L[t]);
                     for (int pp = eb.z; pp < eb.z + ea.w; ++pp) {
                         const int jk = pg.pair_jk[pp], ik = pg.pair_ik[pp];
                         AT Ajk[9], B[9];
@@ -556,13 +567,13 @@ ilu0_factor_tile_kernel(FactorDev pg, double* lu, int* flags, int epoch, int* ba
                             for (int t = 0; t < 9; ++t) D[t] -= B[t];
                         } else {
 #pragma unroll
-                            for (int t = 0; t < 9; ++t) lu[(size_t)ik * 9 + t] = (double)((AT)lu[(size_t)ik * 9 + t] - B[t]);
+                            for (int t = 0; t < 9; ++t) lu[(size_t)ik * 9 + t] = enc(dec<AT>(lu[(size_t)ik * 9 + t]) - B[t]);
                         }
                     }
                 }
                 const AT det = mat3_invert(D);
 #pragma unroll
-                for (int t = 0; t < 9; ++t) lu[(size_t)idiag * 9 + t] = (double)D[t];
+                for (int t = 0; t < 9; ++t) lu[(size_t)idiag * 9 + t] = enc(D[t]);
                 if (!(det != AT(0)) || isinf(det) || isnan(det)) atomicMin(bad_row, i);
             }
             // simple rows: gather the whole pivot block inside the warp, invert, store own row
@@ -573,9 +584,9 @@ ilu0_factor_tile_kernel(FactorDev pg, double* lu, int* flags, int epoch, int* ba
                 for (int t = 0; t < 3; ++t) D[m * 3 + t] = __shfl_sync(0xffffffffu, Drow[t], base + m);
             if (simple) {
                 const AT det = mat3_invert(D);
-                const double o0 = (double)(c == 0 ? D[0] : (c == 1 ? D[3] : D[6]));
-                const double o1 = (double)(c == 0 ? D[1] : (c == 1 ? D[4] : D[7]));
-                const double o2 = (double)(c == 0 ? D[2] : (c == 1 ? D[5] : D[8]));
+                const double o0 = enc(c == 0 ? D[0] : (c == 1 ? D[3] : D[6]));
+                const double o1 = enc(c == 0 ? D[1] : (c == 1 ? D[4] : D[7]));
+                const double o2 = enc(c == 0 ? D[2] : (c == 1 ? D[5] : D[8]));
                 double* dst = lu + (size_t)idiag * 9 + c * 3;
                 dst[0] = o0; dst[1] = o1; dst[2] = o2;
                 for (int t = pg.fpush_ptr[q]; t < pg.fpush_ptr[q + 1]; ++t) {      // push the pivot to other CTAs
@@ -698,16 +709,16 @@ ilu0_sweep_kernel(SweepDev pg, const T* __restrict__ rhs, T* work, T* out,
                     y0 = work[(size_t)j * 3]; y1 = work[(size_t)j * 3 + 1]; y2 = work[(size_t)j * 3 + 2];
                 }
                 const double* a = pg.pval + (size_t)b * 9;
-                r0 = fma(-(T)a[0], y0, r0); r0 = fma(-(T)a[1], y1, r0); r0 = fma(-(T)a[2], y2, r0);
-                r1 = fma(-(T)a[3], y0, r1); r1 = fma(-(T)a[4], y1, r1); r1 = fma(-(T)a[5], y2, r1);
-                r2 = fma(-(T)a[6], y0, r2); r2 = fma(-(T)a[7], y1, r2); r2 = fma(-(T)a[8], y2, r2);
+                r0 = fma(-dec<T>(a[0]), y0, r0); r0 = fma(-dec<T>(a[1]), y1, r0); r0 = fma(-dec<T>(a[2]), y2, r0);
+                r1 = fma(-dec<T>(a[3]), y0, r1); r1 = fma(-dec<T>(a[4]), y1, r1); r1 = fma(-dec<T>(a[5]), y2, r1);
+                r2 = fma(-dec<T>(a[6]), y0, r2); r2 = fma(-dec<T>(a[7]), y1, r2); r2 = fma(-dec<T>(a[8]), y2, r2);
             }
             if (!LOWER) {
                 const double* di = pg.pdinv + (size_t)q * 9;
                 T v0 = T(0), v1 = T(0), v2 = T(0);
-                v0 = fma((T)di[0], r0, v0); v0 = fma((T)di[1], r1, v0); v0 = fma((T)di[2], r2, v0);
-                v1 = fma((T)di[3], r0, v1); v1 = fma((T)di[4], r1, v1); v1 = fma((T)di[5], r2, v1);
-                v2 = fma((T)di[6], r0, v2); v2 = fma((T)di[7], r1, v2); v2 = fma((T)di[8], r2, v2);
+                v0 = fma(dec<T>(di[0]), r0, v0); v0 = fma(dec<T>(di[1]), r1, v0); v0 = fma(dec<T>(di[2]), r2, v0);
+                v1 = fma(dec<T>(di[3]), r0, v1); v1 = fma(dec<T>(di[4]), r1, v1); v1 = fma(dec<T>(di[5]), r2, v1);
+                v2 = fma(dec<T>(di[6]), r0, v2); v2 = fma(dec<T>(di[7]), r1, v2); v2 = fma(dec<T>(di[8]), r2, v2);
                 r0 = v0; r1 = v1; r2 = v2;
                 if (scale) { v0 *= w; v1 *= w; v2 *= w; }
                 out[(size_t)row * 3] = v0; out[(size_t)row * 3 + 1] = v1; out[(size_t)row * 3 + 2] = v2;
@@ -786,6 +797,20 @@ deinterleave_x_kernel(int N, const T* __restrict__ x_cellmajor, double* __restri
     if (e >= (size_t)N * 3) return;
     const size_t p = e / N, i = e - p * N;
     dx_varmajor[e] = (double)x_cellmajor[i * 3 + p];
+}
+
+// values -> containers and back (opmgpu_ilu0_get_factors hands the caller plain doubles)
+template <class T>
+__global__ void __launch_bounds__(256)
+encode_kernel(size_t n, const T* __restrict__ in, double* __restrict__ out)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = enc(in[i]);
+}
+template <class T>
+__global__ void __launch_bounds__(256)
+decode_kernel(size_t n, const double* __restrict__ in, double* __restrict__ out)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = (double)dec<T>(in[i]);
 }
 
 // plain conversions between the caller's doubles and the instance's scalar type

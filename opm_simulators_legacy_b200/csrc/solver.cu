@@ -540,6 +540,17 @@ int convert(opmgpu_handle h, size_t n, const TI* in, TO* out)
     return 0;
 }
 
+template <class T>
+int encode(opmgpu_handle h, size_t n, const T* in, double* out)
+{
+    if (!n) return 0;
+    const unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)h->sm_count * 16);
+    encode_kernel<T><<<grid, 256, 0, h->stream>>>(n, in, out);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
 int ensure_vectors(opmgpu_handle h)
 {
     const size_t n = (size_t)h->N * 3;
@@ -654,7 +665,7 @@ gather_blocks_kernel(size_t nblk, const int* __restrict__ src, const T* __restri
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= nblk * 9) return;
     const size_t b = e / 9;
-    lu[e] = (double)vals[(size_t)src[b] * 9 + (e - b * 9)];
+    lu[e] = enc(vals[(size_t)src[b] * 9 + (e - b * 9)]);
 }
 
 // x[N_local .. N_local + n_ghost) <- the owners' rows (ncclSend/ncclRecv over NVLink)
@@ -769,7 +780,7 @@ int factor_t(opmgpu_handle h, int* bad_row)
         h->launches++;
     } else if (!pipe_factor) {
         if (sizeof(T) == 8) CK(cudaMemcpyAsync(h->d_lu.p, h->d_vals, nv * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-        else if (int rc = convert<T, double>(h, nv, vals, h->d_lu.p)) return rc;
+        else if (int rc = encode<T>(h, nv, vals, h->d_lu.p)) return rc;
     }
     // the blocks of A the ILU0 is built on (the rank's diagonal block when partitioned: 8-byte containers)
     const bool A_in_lu = h->world > 1;
@@ -787,7 +798,7 @@ int factor_t(opmgpu_handle h, int* bad_row)
     } else if (pipe_factor) {
         FactorPipeDevMem& d = h->pipeF;
         const size_t e = d.nval * 3;
-        if (A_in_lu) pack_factor_records_kernel<double><<<(unsigned)((e + 255) / 256), 256, 0, h->stream>>>(d.nval, d.val_src.p, d.val_dst8.p, h->d_lu.p, (double*)d.buf.p);
+        if (A_in_lu) pack_factor_records_kernel<double, true><<<(unsigned)((e + 255) / 256), 256, 0, h->stream>>>(d.nval, d.val_src.p, d.val_dst8.p, h->d_lu.p, (double*)d.buf.p);
         else pack_factor_records_kernel<T><<<(unsigned)((e + 255) / 256), 256, 0, h->stream>>>(d.nval, d.val_src.p, d.val_dst8.p, vals, (double*)d.buf.p);
         FactorPipeDev pg;
         pg.buf = d.buf.p; pg.cta_step_ptr = d.cta_step_ptr.p; pg.step_off16 = d.step_off16.p; pg.step_bytes = d.step_bytes.p;
@@ -833,7 +844,7 @@ int factor_t(opmgpu_handle h, int* bad_row)
         const FactorPipeDevMem& f = h->pipeF;
         if (h->pipeL.nval) {
             const size_t e = h->pipeL.nval * 3;
-            if (A_in_lu) repack_pipe2_kernel<true, 0, double, T><<<(unsigned)((e + 255) / 256), 256, 0, h->stream>>>(h->pipeL.nval, h->pipeL.val_src.p, h->pipeL.val_dst8.p,
+            if (A_in_lu) repack_pipe2_kernel<true, 0, double, T, true><<<(unsigned)((e + 255) / 256), 256, 0, h->stream>>>(h->pipeL.nval, h->pipeL.val_src.p, h->pipeL.val_dst8.p,
                 h->pipeL.val_stride.p, h->d_colidx.p, h->d_diag.p, f.fpos.p, h->d_lu.p, f.fout.p, (double*)h->pipeL.buf.p);
             else repack_pipe2_kernel<true, 0, T, T><<<(unsigned)((e + 255) / 256), 256, 0, h->stream>>>(h->pipeL.nval, h->pipeL.val_src.p, h->pipeL.val_dst8.p,
                 h->pipeL.val_stride.p, h->d_colidx.p, h->d_diag.p, f.fpos.p, vals, f.fout.p, (double*)h->pipeL.buf.p);
@@ -841,7 +852,7 @@ int factor_t(opmgpu_handle h, int* bad_row)
         }
         if (h->pipeU.nval) {
             const size_t e = h->pipeU.nval * 3;
-            if (A_in_lu) repack_pipe2_kernel<false, 0, double, T><<<(unsigned)((e + 255) / 256), 256, 0, h->stream>>>(h->pipeU.nval, h->pipeU.val_src.p, h->pipeU.val_dst8.p,
+            if (A_in_lu) repack_pipe2_kernel<false, 0, double, T, true><<<(unsigned)((e + 255) / 256), 256, 0, h->stream>>>(h->pipeU.nval, h->pipeU.val_src.p, h->pipeU.val_dst8.p,
                 h->pipeU.val_stride.p, h->d_colidx.p, h->d_diag.p, f.fpos.p, h->d_lu.p, f.fout.p, (double*)h->pipeU.buf.p);
             else repack_pipe2_kernel<false, 0, T, T><<<(unsigned)((e + 255) / 256), 256, 0, h->stream>>>(h->pipeU.nval, h->pipeU.val_src.p, h->pipeU.val_dst8.p,
                 h->pipeU.val_stride.p, h->d_colidx.p, h->d_diag.p, f.fpos.p, vals, f.fout.p, (double*)h->pipeU.buf.p);
@@ -1760,7 +1771,7 @@ int opmgpu_ilu0_get_factors(opmgpu_handle h, double* lu)
         // the pipelined factorisation keeps only the pivots: build the BCRS factor array now
         // (in place on a copy of A; the matrix values must still be the ones that were factorised)
         if (h->world == 1) {
-            if (h->f32) { if (int rc = convert<float, double>(h, (size_t)h->nnzb * 9, static_cast<const float*>(h->d_vals), h->d_lu.p)) return rc; }
+            if (h->f32) { if (int rc = encode<float>(h, (size_t)h->nnzb * 9, static_cast<const float*>(h->d_vals), h->d_lu.p)) return rc; }
             else CK(cudaMemcpyAsync(h->d_lu.p, h->d_vals, (size_t)h->nnzb * 9 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
         }
         const size_t e = (size_t)h->N * 3;
@@ -1770,7 +1781,17 @@ int opmgpu_ilu0_get_factors(opmgpu_handle h, double* lu)
         CK(cudaGetLastError());
         h->lu_lazy = false;
     }
-    CK(cudaMemcpyAsync(lu, h->d_lu.p, (size_t)h->nnzb * 9 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    const double* src = h->d_lu.p;
+    if (h->f32) {             // the float instance's containers -> plain doubles for the caller
+        const size_t nv = (size_t)h->nnzb * 9;
+        CK(h->d_stage.ensure(nv));
+        const unsigned grid = (unsigned)std::min<size_t>((nv + 255) / 256, (size_t)h->sm_count * 16);
+        decode_kernel<float><<<grid, 256, 0, h->stream>>>(nv, h->d_lu.p, h->d_stage.p);
+        h->launches++;
+        CK(cudaGetLastError());
+        src = h->d_stage.p;
+    }
+    CK(cudaMemcpyAsync(lu, src, (size_t)h->nnzb * 9 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return OPMGPU_OK;
 }

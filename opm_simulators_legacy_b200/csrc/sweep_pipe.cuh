@@ -204,7 +204,7 @@ __device__ __forceinline__ void push_f64(double* p, double v)
 // (all three components), so the chain needs no shuffles and its nine dependency loads are
 // issued once per row, not once per component.
 // T: arithmetic type of the sweep (double, or float for the reference's Impl<3,float>); records,
-// window and push slots hold 8-byte containers either way (a float widened exactly).
+// window and push slots hold 8-byte containers either way (kernels.cuh: enc / dec).
 template <bool UPPER, class T>
 struct StepPre {
     int n, qbase, ext_end, ext_cnt;
@@ -226,13 +226,13 @@ struct StepPre {
         if (on) {
             const double* cfp = reinterpret_cast<const double*>(rec + 32) + r * 27;
 #pragma unroll
-            for (int q = 0; q < 27; ++q) cf[q] = (T)cfp[q];
+            for (int q = 0; q < 27; ++q) cf[q] = dec<T>(cfp[q]);
             const int T3 = 3 * n;
             size_t off = 32 + (size_t)T3 * 72;
             if (UPPER) {
                 const double* dp = reinterpret_cast<const double*>(rec + off) + r * 9;
 #pragma unroll
-                for (int q = 0; q < 9; ++q) dv[q] = (T)dp[q];
+                for (int q = 0; q < 9; ++q) dv[q] = dec<T>(dp[q]);
                 off += (size_t)T3 * 24;
             }
             const int4* rip = reinterpret_cast<const int4*>(rec + ((off + 15) & ~(size_t)15)) + 2 * r;
@@ -242,7 +242,7 @@ struct StepPre {
             aw = dep_s + 8u * (uint32_t)ri1.w;
             has_cx = max(ri0.y, max(ri0.z, ri0.w)) >= kCxBase * 3;
             const double* rp = reinterpret_cast<const double*>(stage) + 3 * r;
-            rhs[0] = (T)rp[0]; rhs[1] = (T)rp[1]; rhs[2] = (T)rp[2];
+            rhs[0] = dec<T>(rp[0]); rhs[1] = dec<T>(rp[1]); rhs[2] = dec<T>(rp[2]);
         }
     }
 };
@@ -265,13 +265,13 @@ __device__ __noinline__ void sweep_tail_blocks(const unsigned char* rec, int r, 
     const double* tail_vals = reinterpret_cast<const double*>(rec + (size_t)hdr[6] * 8);
     for (int t = r ? tail_end[r - 1] : 0; t < tail_end[r]; ++t) {
         const double* yp = dep_ptr(tail_dep[t], dep, work);
-        const T y0 = (T)yp[0], y1 = (T)yp[1], y2 = (T)yp[2];
+        const T y0 = dec<T>(yp[0]), y1 = dec<T>(yp[1]), y2 = dec<T>(yp[2]);
         const double* ap = tail_vals + (size_t)t * 9;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            acc[c] = fma(-(T)ap[c * 3 + 0], y0, acc[c]);
-            acc[c] = fma(-(T)ap[c * 3 + 1], y1, acc[c]);
-            acc[c] = fma(-(T)ap[c * 3 + 2], y2, acc[c]);
+            acc[c] = fma(-dec<T>(ap[c * 3 + 0]), y0, acc[c]);
+            acc[c] = fma(-dec<T>(ap[c * 3 + 1]), y1, acc[c]);
+            acc[c] = fma(-dec<T>(ap[c * 3 + 2]), y2, acc[c]);
         }
     }
 }
@@ -286,7 +286,7 @@ __device__ __noinline__ void sweep_extra_pushes(const unsigned char* rec, int r,
     const int* xpush_slot = lists + 2 * n + hdr[4];
     for (int t = r ? xpush_end[r - 1] : 0; t < xpush_end[r]; ++t) {
         double* sl = ext + (size_t)xpush_slot[t] * 3;
-        __stcg(sl, (double)acc[0]); __stcg(sl + 1, (double)acc[1]); __stcg(sl + 2, (double)acc[2]);
+        __stcg(sl, enc(acc[0])); __stcg(sl + 1, enc(acc[1])); __stcg(sl + 2, enc(acc[2]));
     }
 }
 
@@ -368,7 +368,7 @@ __device__ __forceinline__ void sweep_row_chain(const StepPre<UPPER, T>& p, cons
         acc[0] = p.rhs[0]; acc[1] = p.rhs[1]; acc[2] = p.rhs[2];
 #pragma unroll
         for (int q = 0; q < 9; ++q) {
-            const T yq = (T)y[q];
+            const T yq = dec<T>(y[q]);
             acc[0] = fma(-p.cf[q], yq, acc[0]);
             acc[1] = fma(-p.cf[9 + q], yq, acc[1]);
             acc[2] = fma(-p.cf[18 + q], yq, acc[2]);
@@ -385,7 +385,7 @@ __device__ __forceinline__ void sweep_row_chain(const StepPre<UPPER, T>& p, cons
             acc[0] = v[0]; acc[1] = v[1]; acc[2] = v[2];
         }
         const uint32_t w = LEAN ? p.aw : dep_s + 8u * (uint32_t)p.ri1.w;
-        sts_f64(w, (double)acc[0]); sts_f64(w + 8, (double)acc[1]); sts_f64(w + 16, (double)acc[2]);
+        sts_f64(w, enc(acc[0])); sts_f64(w + 8, enc(acc[1])); sts_f64(w + 16, enc(acc[2]));
     }
 }
 // results other CTAs wait for.  Issued right after the hand-over to the next group: the
@@ -397,9 +397,9 @@ __device__ __forceinline__ void push_dsmem(uint32_t cx_s, int id, const T (&acc)
     const uint32_t la = cx_s + 24u * (uint32_t)(id & 0xfffff);
     uint32_t ra;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"((id >> 20) & 0xf));
-    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra), "d"((double)acc[0]) : "memory");
-    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra + 8), "d"((double)acc[1]) : "memory");
-    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra + 16), "d"((double)acc[2]) : "memory");
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra), "d"(enc(acc[0])) : "memory");
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra + 8), "d"(enc(acc[1])) : "memory");
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra + 16), "d"(enc(acc[2])) : "memory");
 }
 
 template <bool UPPER, bool LEAN, bool CX = false, class T = double>
@@ -408,9 +408,9 @@ __device__ __forceinline__ void sweep_row_pushes(const StepPre<UPPER, T>& p, con
 {
     if (p.on) {
         if (CX && p.ri1.y >= 0 && (p.ri1.y & kPushDsmem)) push_dsmem<T>(cx_s, p.ri1.y, acc);
-        else if (p.ri1.y >= 0) { double* sl = ext + (size_t)p.ri1.y * 3; push_f64(sl, (double)acc[0]); push_f64(sl + 1, (double)acc[1]); push_f64(sl + 2, (double)acc[2]); }
+        else if (p.ri1.y >= 0) { double* sl = ext + (size_t)p.ri1.y * 3; push_f64(sl, enc(acc[0])); push_f64(sl + 1, enc(acc[1])); push_f64(sl + 2, enc(acc[2])); }
         if (CX && p.ri1.z >= 0 && (p.ri1.z & kPushDsmem)) push_dsmem<T>(cx_s, p.ri1.z, acc);
-        else if (p.ri1.z >= 0) { double* sl = ext + (size_t)p.ri1.z * 3; push_f64(sl, (double)acc[0]); push_f64(sl + 1, (double)acc[1]); push_f64(sl + 2, (double)acc[2]); }
+        else if (p.ri1.z >= 0) { double* sl = ext + (size_t)p.ri1.z * 3; push_f64(sl, enc(acc[0])); push_f64(sl + 1, enc(acc[1])); push_f64(sl + 2, enc(acc[2])); }
         if (!LEAN && (p.ri0.x & kRowSlow)) sweep_extra_pushes<T>(rec, r, ext, acc);
     }
 }
@@ -426,11 +426,11 @@ __device__ __forceinline__ void sweep_row_stores(const StepPre<UPPER, T>& p, con
             o[0] = scale ? acc[0] * w : acc[0]; o[1] = scale ? acc[1] * w : acc[1]; o[2] = scale ? acc[2] * w : acc[2];
         } else {
             double* o = hand_off + (size_t)p.ri1.x * 3;
-            o[0] = (double)acc[0]; o[1] = (double)acc[1]; o[2] = (double)acc[2];
+            o[0] = enc(acc[0]); o[1] = enc(acc[1]); o[2] = enc(acc[2]);
         }
         if (!LEAN && (p.ri0.x & kRowWriteGlobal)) {
             double* o = work + (size_t)row * 3;
-            o[0] = (double)acc[0]; o[1] = (double)acc[1]; o[2] = (double)acc[2];
+            o[0] = enc(acc[0]); o[1] = enc(acc[1]); o[2] = enc(acc[2]);
         }
     }
 }
@@ -675,8 +675,8 @@ ilu0_sweep_pipe_kernel(PipeDev pg, const double* __restrict__ rhs_perm, double* 
             sweep_row_chain<UPPER, LEAN, CX, T>(p, stage + pg.rhs_bytes, r_first, dep, dep_s, work, pg.ext, acc, ctl, err);
             if (!LEAN && p.n > kPipeRowsPerPass)
                 sweep_extra_rows<UPPER, T>(stage, pg.rhs_bytes, p.n, r_first, dep, dep_s, work, hand_off, out, pg.ext, w, scale);
-            if (tr) { pg.trace[s * 16 + 2] = pipe_clock_after(__double2hiint((double)acc[0])); pg.trace[s * 16 + 4] = p.n; }
-            if (gt) gtr[s * 8 + 3] = pipe_gtime_after(__double2hiint((double)acc[0]));
+            if (tr) { pg.trace[s * 16 + 2] = pipe_clock_after(__double2hiint(enc(acc[0]))); pg.trace[s * 16 + 4] = p.n; }
+            if (gt) gtr[s * 8 + 3] = pipe_gtime_after(__double2hiint(enc(acc[0])));
             long long rb = 0;           // trace: read the first pushed value back through L2
             const bool gt_rb = gt && p.on && p.ri1.y >= 0;
             if (gt_rb) asm volatile("ld.relaxed.gpu.global.s64 %0, [%1];" : "=l"(rb) : "l"(pg.ext + (size_t)p.ri1.y * 3) : "memory");
@@ -718,7 +718,7 @@ permute_rows_kernel(size_t nperm, const int* __restrict__ perm_row, const T* __r
     if (e >= nperm * 3) return;
     const size_t q = e / 3;
     const int row = perm_row[q];
-    xp[e] = row >= 0 ? (double)x[(size_t)row * 3 + (e - q * 3)] : 0.0;
+    xp[e] = row >= 0 ? enc(x[(size_t)row * 3 + (e - q * 3)]) : 0.0;
 }
 
 }  // namespace opmgpu

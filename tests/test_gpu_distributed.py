@@ -137,3 +137,30 @@ def test_cpp_host_mirror_on_two_gpus():
     exe = os.path.join(ROOT, "opm_simulators_legacy_b200", "host_selftest")
     out = subprocess.run([exe, "0,1"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
+
+
+@pytest.mark.parametrize("ngpus", [1, 2])
+def test_multi_handle_single_precision(oracle, ngpus):
+    """The float instance (Impl<3,float>) on a multi handle: every GPU runs in float (halo exchange of
+    float vectors); one GPU reproduces the float oracle's iteration count, two satisfy the partitioned
+    tolerance rule on the true residual."""
+    import numpy as np
+    from opm_simulators_legacy_b200.jacobian import synth_blackoil_jacobian
+    from opm_simulators_legacy_b200.solver import GpuLinearSolver
+    _need(ngpus)
+    s = synth_blackoil_jacobian(24, 20, 16, perm="lognormal")
+    rp, ci, v, b = s.rowptr.numpy(), s.colidx.numpy(), s.vals.numpy(), s.rhs.numpy()
+    g = GpuLinearSolver.multi(range(ngpus))
+    try:
+        g.set_precision(True)
+        g.set_pattern(rp, ci)
+        x, res = g.solve_bcrs(v, b)
+        assert res["converged"] == 1
+        assert np.array_equal(x, x.astype(np.float32).astype(np.float64))
+        assert _true_reduction(oracle, rp, ci, v, b, x) <= 1e-2 * 1.001
+        if ngpus == 1:
+            assert res["iterations"] == oracle.f32.solve_bcrs(rp, ci, v, b)[1]["iterations"]
+        dx, res = g.solve_from_csc_blocks(s.N, s.csc_blocks(), s.matbalscale, s.rhs_eqmajor_unscaled.numpy())
+        assert res["converged"] == 1 and _true_reduction(oracle, rp, ci, v, b, dx.reshape(3, -1).T) <= 1e-2 * 1.001
+    finally:
+        g.close()
