@@ -228,6 +228,15 @@ struct opmgpu_solver {
     ncclComm_t comm = nullptr;
     int n_ghost = 0, nnzb_full = 0;
     DevArr<int> d_rowptr_full, d_colidx_full, d_lu_src, d_send_rows;
+    // halo exchange beside the SpMV: rows that reference no ghost column are multiplied while the
+    // exchange is in flight on halo_stream, the boundary rows (d_bnd_rows; one bit per row in
+    // d_row_skip, a word per SpMV tile) when it has arrived
+    DevArr<int> d_bnd_rows;
+    DevArr<unsigned long long> d_row_skip;
+    int n_bnd_rows = 0;
+    cudaStream_t halo_stream = nullptr;
+    cudaEvent_t ev_x_ready = nullptr, ev_halo_done = nullptr;
+    bool overlap_halo = false;     // OPMGPU_HALO_OVERLAP=1: exchange beside the SpMV (measured: no gain over exchange-then-SpMV with NCCL send/recv, profiles/r02_halo_overlap.md)
     DevArr<double> d_sendbuf;
     std::vector<int> send_cnt, send_off, recv_cnt, recv_off;
     int n_send = 0;
@@ -670,18 +679,19 @@ gather_blocks_kernel(size_t nblk, const int* __restrict__ src, const T* __restri
 
 // x[N_local .. N_local + n_ghost) <- the owners' rows (ncclSend/ncclRecv over NVLink)
 template <class T>
-int halo_exchange(opmgpu_handle h, T* x)
+int halo_exchange(opmgpu_handle h, T* x, cudaStream_t stream = nullptr)
 {
     if (h->world == 1) return 0;
+    if (!stream) stream = h->stream;
     T* sendbuf = vec<T>(h->d_sendbuf);
     if (h->n_send) {
-        pack_rows_kernel<T><<<(h->n_send * 3 + 255) / 256, 256, 0, h->stream>>>(h->n_send, h->d_send_rows.p, x, sendbuf);
+        pack_rows_kernel<T><<<(h->n_send * 3 + 255) / 256, 256, 0, stream>>>(h->n_send, h->d_send_rows.p, x, sendbuf);
         h->launches++;
     }
     NK(g_nccl.GroupStart());
     for (int p = 0; p < h->world; ++p) {
-        if (h->send_cnt[p]) NK(g_nccl.Send(sendbuf + (size_t)h->send_off[p] * 3, (size_t)h->send_cnt[p] * 3, nccl_type<T>(), p, h->comm, h->stream));
-        if (h->recv_cnt[p]) NK(g_nccl.Recv(x + ((size_t)h->N + h->recv_off[p]) * 3, (size_t)h->recv_cnt[p] * 3, nccl_type<T>(), p, h->comm, h->stream));
+        if (h->send_cnt[p]) NK(g_nccl.Send(sendbuf + (size_t)h->send_off[p] * 3, (size_t)h->send_cnt[p] * 3, nccl_type<T>(), p, h->comm, stream));
+        if (h->recv_cnt[p]) NK(g_nccl.Recv(x + ((size_t)h->N + h->recv_off[p]) * 3, (size_t)h->recv_cnt[p] * 3, nccl_type<T>(), p, h->comm, stream));
     }
     NK(g_nccl.GroupEnd());
     return 0;
@@ -738,10 +748,50 @@ __global__ void dot_to_slot_kernel(size_t n, const T* __restrict__ a, const T* _
     grid_reduce<1, T>(v, ws, [=](T (&t)[1]) { S[slot] = t[0]; });
 }
 
+// Row-partitioned SpMV with the halo exchange in flight beside it ("fused
+// SpMV-with-halo step"): pack + ncclSend/ncclRecv run on halo_stream while the tiles that need no
+// ghost value are multiplied; the boundary tiles follow when the ghosts have arrived and add their
+// share of the fused dot products.  A few SMs are left to the exchange kernels.
+template <class T>
+int spmv_overlapped(opmgpu_handle h, int mode, T* x, T* y, const T* w1)
+{
+    const T* vals = static_cast<const T*>(h->d_vals);
+    CK(cudaEventRecord(h->ev_x_ready, h->stream));
+    CK(cudaStreamWaitEvent(h->halo_stream, h->ev_x_ready, 0));
+    if (int rc = halo_exchange<T>(h, x, h->halo_stream)) return rc;
+    CK(cudaEventRecord(h->ev_halo_done, h->halo_stream));
+    const int* rowptr = h->d_rowptr_full.p; const int* colidx = h->d_colidx_full.p;
+    const int nnzb = h->nnzb_full;
+    static const int reserve = getenv("OPMGPU_HALO_RESERVE") ? atoi(getenv("OPMGPU_HALO_RESERVE")) : 16;     // SMs left to the pack kernel and NCCL's send/recv kernel (32 p2p channels)
+    const int ntiles = (h->N + kSpmvRows - 1) / kSpmvRows;
+    const unsigned grid = (unsigned)std::max(1, std::min(ntiles, h->sm_count - reserve));
+    const unsigned long long* skip = h->d_row_skip.p;
+    if (mode == 0) spmv3_tma_kernel<0, T><<<grid, kSpmvThreads, kSpmvSmemBytes, h->stream>>>(h->N, nnzb, rowptr, colidx, vals, x, y, w1, h->d_S.p, h->ws(), skip);
+    else if (mode == 1) spmv3_tma_kernel<1, T><<<grid, kSpmvThreads, kSpmvSmemBytes, h->stream>>>(h->N, nnzb, rowptr, colidx, vals, x, y, w1, h->d_S.p, h->ws(), skip);
+    else spmv3_tma_kernel<2, T><<<grid, kSpmvThreads, kSpmvSmemBytes, h->stream>>>(h->N, nnzb, rowptr, colidx, vals, x, y, w1, h->d_S.p, h->ws(), skip);
+    CK(cudaStreamWaitEvent(h->stream, h->ev_halo_done, 0));
+    const unsigned gridb = (unsigned)std::max<size_t>(1, std::min<size_t>(((size_t)h->n_bnd_rows * 3 + 255) / 256, (size_t)kVecBlocks));
+    if (mode == 0) spmv3_rows_kernel<0, T><<<gridb, 256, 0, h->stream>>>(h->n_bnd_rows, h->d_bnd_rows.p, rowptr, colidx, vals, x, y, w1, h->d_S.p, h->ws());
+    else if (mode == 1) spmv3_rows_kernel<1, T><<<gridb, 256, 0, h->stream>>>(h->n_bnd_rows, h->d_bnd_rows.p, rowptr, colidx, vals, x, y, w1, h->d_S.p, h->ws());
+    else spmv3_rows_kernel<2, T><<<gridb, 256, 0, h->stream>>>(h->n_bnd_rows, h->d_bnd_rows.p, rowptr, colidx, vals, x, y, w1, h->d_S.p, h->ws());
+    h->launches += 2;
+    CK(cudaGetLastError());
+    return 0;
+}
+
 template <class T>
 int spmv_with_dots(opmgpu_handle h, int mode, T* x, T* y, const T* w1)
 {
-    int rc = halo_exchange<T>(h, x);
+    int rc;
+    if (h->world > 1 && h->overlap_halo && h->halo_stream && h->spmv_tma && h->n_bnd_rows > 0 &&
+        (reinterpret_cast<uintptr_t>(h->d_vals) & 15) == 0) {
+        rc = spmv_overlapped<T>(h, mode, x, y, w1);
+        if (rc) return rc;
+        if (mode == 1) rc = allreduce_slots(h, S_H, 1);
+        if (mode == 2) rc = allreduce_slots(h, S_TR, 2);
+        return rc;
+    }
+    rc = halo_exchange<T>(h, x);
     if (rc) return rc;
     rc = launch_spmv<T>(h, mode, x, y, w1);
     if (rc == -100) {
@@ -1537,6 +1587,7 @@ int opmgpu_create(int device, opmgpu_handle* out)
     cudaFuncSetAttribute(spmv3_tma_kernel<0, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
     cudaFuncSetAttribute(spmv3_tma_kernel<1, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
     cudaFuncSetAttribute(spmv3_tma_kernel<2, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
+    if (const char* s = getenv("OPMGPU_HALO_OVERLAP")) h->overlap_halo = atoi(s) != 0;
     cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     cudaFuncSetAttribute(ilu0_factor_pipe_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
     cudaFuncSetAttribute(ilu0_factor_pipe_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
@@ -1638,6 +1689,8 @@ int opmgpu_destroy(opmgpu_handle h)
     h->d_t.release(); h->d_y.release(); h->d_yL.release(); h->d_vU.release(); h->d_tmp.release(); h->d_tmp2.release();
     h->d_S.release(); h->d_partials.release(); h->d_ticket.release(); h->d_flags.release();
     h->d_rowptr_full.release(); h->d_colidx_full.release(); h->d_lu_src.release(); h->d_send_rows.release(); h->d_sendbuf.release();
+    h->d_bnd_rows.release(); h->d_row_skip.release();
+    if (h->halo_stream) { cudaStreamDestroy(h->halo_stream); cudaEventDestroy(h->ev_x_ready); cudaEventDestroy(h->ev_halo_done); h->halo_stream = nullptr; }
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     h->d_err.release(); h->d_bad.release(); h->d_map9.release(); h->d_cscval.release(); h->d_rhs_stage.release();
     if (h->h_S) cudaFreeHost(h->h_S);
@@ -1715,16 +1768,13 @@ int opmgpu_spmv_dev(opmgpu_handle h, const double* x_dev, double* y_dev)
     if (h->f32) {                // doubles at the ABI, floats inside
         float* xf = vec<float>(h->d_tmp); float* yf = vec<float>(h->d_tmp2);
         int rc = convert<double, float>(h, n, x_dev, xf);
-        if (!rc) rc = halo_exchange<float>(h, xf);
-        if (!rc) rc = launch_spmv<float>(h, 0, xf, yf, nullptr);
+        if (!rc) rc = spmv_with_dots<float>(h, 0, xf, yf, nullptr);
         if (!rc) rc = convert<float, double>(h, n, yf, y_dev);
         return rc;
     }
     if (h->world > 1) {          // x_dev has no ghost rows: stage it
         CK(cudaMemcpyAsync(h->d_tmp.p, x_dev, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-        int rc = halo_exchange<double>(h, h->d_tmp.p);
-        if (rc) return rc;
-        return launch_spmv<double>(h, 0, h->d_tmp.p, y_dev, nullptr);
+        return spmv_with_dots<double>(h, 0, h->d_tmp.p, y_dev, nullptr);
     }
     return launch_spmv<double>(h, 0, x_dev, y_dev, nullptr);
 }
@@ -1744,9 +1794,7 @@ int opmgpu_spmv(opmgpu_handle h, const double* x, double* y)
         return OPMGPU_OK;
     }
     CK(cudaMemcpyAsync(h->d_tmp.p, x, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    int rc = halo_exchange<double>(h, h->d_tmp.p);
-    if (rc) return rc;
-    rc = launch_spmv<double>(h, 0, h->d_tmp.p, h->d_tmp2.p, nullptr);
+    int rc = spmv_with_dots<double>(h, 0, h->d_tmp.p, h->d_tmp2.p, nullptr);
     if (rc) return rc;
     CK(cudaMemcpyAsync(y, h->d_tmp2.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -2259,6 +2307,30 @@ int opmgpu_set_pattern_bcrs_distributed(opmgpu_handle h, int N_local, int nnzb_l
     lp.colidx_full.resize(lp.colidx_full.size() + 8, 0);      // padding for the SpMV's 16-byte bulk copies
     if ((rc = upload(h, h->d_colidx_full, lp.colidx_full))) return rc;
     if ((rc = upload(h, h->d_lu_src, lp.lu_src))) return rc;
+    {
+        // rows that reference a ghost column wait for the halo; the others do not
+        static_assert(kSpmvRows == 64, "one 64-bit word of boundary-row flags per SpMV tile");
+        std::vector<int> bnd;
+        std::vector<unsigned long long> skip((size_t)(N_local + kSpmvRows - 1) / kSpmvRows + 1, 0ull);
+        for (int r = 0; r < N_local; ++r) {
+            bool ghost = false;
+            for (int k = rowptr[r]; k < rowptr[r + 1] && !ghost; ++k) ghost = lp.colidx_full[k] >= N_local;
+            if (ghost) { bnd.push_back(r); skip[r / kSpmvRows] |= 1ull << (r % kSpmvRows); }
+        }
+        h->n_bnd_rows = (int)bnd.size();
+        if (bnd.empty()) bnd.push_back(0);
+        if ((rc = upload(h, h->d_bnd_rows, bnd))) return rc;
+        if ((rc = upload(h, h->d_row_skip, skip))) return rc;
+        if (!h->halo_stream) {
+            int prio_lo = 0, prio_hi = 0;
+            cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+            CK(cudaStreamCreateWithPriority(&h->halo_stream, cudaStreamNonBlocking, prio_hi));      // its small kernels go first when SMs free up
+            CK(cudaEventCreateWithFlags(&h->ev_x_ready, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&h->ev_halo_done, cudaEventDisableTiming));
+        }
+        if (getenv("OPMGPU_DEBUG"))
+            fprintf(stderr, "[opmgpu] rank %d: %d of %d rows reference ghost columns (computed after the halo exchange)\n", h->rank, h->n_bnd_rows, N_local);
+    }
     // halo plan: tell every owner which of its rows this rank needs
     const int W = h->world;
     h->recv_cnt = lp.recv_cnt; h->recv_off = lp.recv_off;

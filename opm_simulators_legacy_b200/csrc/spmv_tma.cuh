@@ -35,11 +35,15 @@ static_assert(kSpmvStages % 3 == 0, "stages must be a multiple of the consumer g
 // padded); vals is never read past its end (a misaligned last tile takes the direct path).
 // T = float (the reference's Impl<3,float>): 36-byte blocks, so a tile's value range starts at a
 // multiple of four blocks (16-byte alignment of the bulk copy) instead of two.
+// row_skip != nullptr (row-partitioned systems): bit r of row_skip[t] marks row r of tile t as a
+// boundary row -- it references a ghost column whose value may still be in flight (the halo
+// exchange runs beside this kernel), so it is neither stored nor counted in the dot products here;
+// spmv3_rows_kernel computes those rows when the ghosts have arrived.
 template <int MODE, class T>
 __global__ void __launch_bounds__(kSpmvThreads, 1)
 spmv3_tma_kernel(int N, int nnzb, const int* __restrict__ rowptr, const int* __restrict__ colidx,
                  const T* __restrict__ vals, const T* __restrict__ x, T* __restrict__ y,
-                 const T* __restrict__ w1, double* S, ReduceWs ws)
+                 const T* __restrict__ w1, double* S, ReduceWs ws, const unsigned long long* __restrict__ row_skip = nullptr)
 {
     constexpr int kAl = sizeof(T) == 8 ? 2 : 4;          // blocks per 16-byte aligned unit (144 bytes)
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -100,7 +104,8 @@ spmv3_tma_kernel(int N, int nnzb, const int* __restrict__ rowptr, const int* __r
             const int b0a = b0 & ~(kAl - 1), b1a = (b1 + kAl - 1) & ~(kAl - 1), c0a = b0 & ~3;
             const bool direct = (b1a > nnzb) || (b1a - b0a > kSpmvCapBlocks);
             const int r = r0 + rl;
-            if (r < r1) {
+            const bool skip = row_skip && ((row_skip[t] >> rl) & 1ull);
+            if (r < r1 && !skip) {
                 const int kb = rp[rl], ke = rp[rl + 1];
                 T acc = T(0);
                 if (!direct) {
@@ -150,6 +155,40 @@ spmv3_tma_kernel(int N, int nnzb, const int* __restrict__ rowptr, const int* __r
     } else if (MODE == 2) {
         T v[2] = {d0, d1};
         grid_reduce<2, T>(v, ws, [=](T (&u)[2]) { S[S_TR] = u[0]; S[S_TT] = u[1]; });
+    }
+}
+
+// The boundary rows of a row-partitioned system (those spmv3_tma_kernel skipped): one thread per
+// (listed row, component), blocks in ascending column order as everywhere; the dot products of
+// MODE 1 / 2 are ADDED to what the first kernel left in the scalar slots.
+template <int MODE, class T>
+__global__ void __launch_bounds__(256)
+spmv3_rows_kernel(int nrows, const int* __restrict__ rows, const int* __restrict__ rowptr, const int* __restrict__ colidx,
+                  const T* __restrict__ vals, const T* __restrict__ x, T* __restrict__ y,
+                  const T* __restrict__ w1, double* S, ReduceWs ws)
+{
+    T d0 = T(0), d1 = T(0);
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < (size_t)nrows * 3; e += (size_t)gridDim.x * blockDim.x) {
+        const int row = rows[e / 3], c = (int)(e % 3);
+        T acc = T(0);
+        for (int k = rowptr[row]; k < rowptr[row + 1]; ++k) {
+            const T* a = vals + (size_t)k * 9 + c * 3;
+            const T* xj = x + (size_t)colidx[k] * 3;
+            acc = fma(a[0], xj[0], acc);
+            acc = fma(a[1], xj[1], acc);
+            acc = fma(a[2], xj[2], acc);
+        }
+        const size_t o = (size_t)row * 3 + c;
+        y[o] = acc;
+        if (MODE == 1) d0 = fma(w1[o], acc, d0);
+        if (MODE == 2) { d0 = fma(acc, w1[o], d0); d1 = fma(acc, acc, d1); }
+    }
+    if (MODE == 1) {
+        T v[1] = {d0};
+        grid_reduce<1, T>(v, ws, [=](T (&u)[1]) { S[S_H] = (double)((T)S[S_H] + u[0]); });
+    } else if (MODE == 2) {
+        T v[2] = {d0, d1};
+        grid_reduce<2, T>(v, ws, [=](T (&u)[2]) { S[S_TR] = (double)((T)S[S_TR] + u[0]); S[S_TT] = (double)((T)S[S_TT] + u[1]); });
     }
 }
 
