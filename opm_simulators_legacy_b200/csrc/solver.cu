@@ -16,6 +16,7 @@
 #include "multi.hpp"
 
 #include <dlfcn.h>
+#include <unistd.h>
 #include <nccl.h>      // types only: the library is resolved at run time with dlopen
 
 #include <algorithm>
@@ -166,6 +167,26 @@ struct FactorPipeDevMem {
 
 }  // namespace
 
+// Halo exchange through peer memory: a rank's boundary rows are stored straight into its neighbours'
+// ghost rows over NVLink (one small kernel), followed by an epoch flag; no send/recv pairing.
+constexpr int kMaxPeers = 8;
+struct PeerPushDesc {
+    void* y[kMaxPeers];                       // peer's SpMV input vector (its d_y), mapped here
+    unsigned long long* flags[kMaxPeers];     // peer's incoming-epoch array
+    long long dst_row0[kMaxPeers];            // first ghost row (in the peer's numbering) my rows go to
+    int send_off[kMaxPeers + 1];              // my send list, grouped by peer
+    int world, rank;
+};
+// Scalar all-reduce through peer memory: every rank stores its partial sums into every other
+// rank's inbox (double-buffered by the exchange's parity), then its epoch flag; each rank adds the
+// W contributions in rank order, so all ranks hold bit-identical sums.
+constexpr int kScalSlots = 16;                // = S_COUNT (kernels.cuh)
+struct PeerScalDesc {
+    double* inbox[kMaxPeers];                 // rank p's inbox [2][kMaxPeers][kScalSlots] (own entry: local pointer)
+    unsigned long long* flags[kMaxPeers];     // rank p's scalar-epoch array [kMaxPeers]
+    int world, rank;
+};
+
 struct opmgpu_solver {
     opmgpu::MultiSolver* multi = nullptr;      // opmgpu_create_multi: this handle only fronts one worker handle per GPU
     int device = 0;
@@ -236,6 +257,21 @@ struct opmgpu_solver {
     int n_bnd_rows = 0;
     cudaStream_t halo_stream = nullptr;
     cudaEvent_t ev_x_ready = nullptr, ev_halo_done = nullptr;
+    struct PeerHalo {
+        bool ready = false;
+        std::vector<void*> opened;                 // cudaIpcOpenMemHandle mappings to close
+        DevArr<unsigned long long> flags_in;       // [kMaxPeers] epoch of the last exchange each peer completed into my ghosts
+        DevArr<unsigned> ticket;
+        PeerPushDesc desc;
+        unsigned recv_mask = 0;
+        unsigned long long epoch = 0;
+        // scalar all-reduce
+        DevArr<double> inbox;                      // [2][kMaxPeers][kScalSlots]
+        DevArr<unsigned long long> sflags;         // [kMaxPeers]
+        PeerScalDesc sdesc;
+        unsigned long long sepoch = 0;
+    } peer;
+    bool use_peer_halo = true;     // OPMGPU_PEER_HALO=0: ncclSend/ncclRecv for every exchange
     bool overlap_halo = false;     // OPMGPU_HALO_OVERLAP=1: exchange beside the SpMV (measured: no gain over exchange-then-SpMV with NCCL send/recv, profiles/r02_halo_overlap.md)
     DevArr<double> d_sendbuf;
     std::vector<int> send_cnt, send_off, recv_cnt, recv_off;
@@ -697,10 +733,68 @@ int halo_exchange(opmgpu_handle h, T* x, cudaStream_t stream = nullptr)
     return 0;
 }
 
-int allreduce_slots(opmgpu_handle h, int slot, int count)
+// S[slot .. slot+count) <- sum over the ranks, through peer memory (see PeerScalDesc); optionally the
+// whole scalar block goes to the host mailbox afterwards (what publish_scalars_kernel does)
+__global__ void __launch_bounds__(128)
+peer_allreduce_kernel(PeerScalDesc d, double* S, int slot, int count, unsigned long long epoch, HostBox hb, int publish, int* err)
+{
+    const int t = threadIdx.x, W = d.world, me = d.rank;
+    const int par = (int)(epoch & 1ull);
+    const int p = t / kScalSlots, i = t % kScalSlots;
+    if (p < W && i < count) d.inbox[p][((size_t)par * kMaxPeers + me) * kScalSlots + i] = S[slot + i];
+    __threadfence_system();
+    __syncthreads();
+    if (t < W && t != me) {
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(d.flags[t] + me), "l"(epoch) : "memory");
+        unsigned long long v = 0;
+        unsigned spins = 0;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(d.flags[me] + t) : "memory");
+            if (v >= epoch) break;
+            if (++spins > (1u << 26)) { atomicExch(err, 11); break; }
+        }
+    }
+    __syncthreads();
+    if (t < count) {
+        const double* in = d.inbox[me] + (size_t)par * kMaxPeers * kScalSlots;
+        double sum = 0.0;
+        for (int q = 0; q < W; ++q) {
+            double v;
+            asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(in + (size_t)q * kScalSlots + t) : "memory");
+            sum += v;
+        }
+        S[slot + t] = sum;
+    }
+    if (publish) {
+        __syncthreads();
+        if (t < S_COUNT) hb.hS[t] = S[t];
+        __syncthreads();
+        if (t == 0) {
+            *hb.herr = S[S_ERRW] != 0.0 ? 9 : 0;
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned long long*>(hb.hseq) = hb.seq;
+        }
+    }
+}
+static_assert(kScalSlots == S_COUNT, "inbox rows hold the scalar block");
+static_assert(kMaxPeers * kScalSlots <= 128, "one thread per (peer, slot)");
+
+int allreduce_slots(opmgpu_handle h, int slot, int count, const HostBox* publish = nullptr)
 {
     if (h->world == 1) return 0;
+    if (h->peer.ready) {
+        HostBox hb;
+        if (publish) hb = *publish; else { hb.hS = nullptr; hb.herr = nullptr; hb.hseq = nullptr; hb.derr = nullptr; hb.seq = 0; }
+        peer_allreduce_kernel<<<1, 128, 0, h->stream>>>(h->peer.sdesc, h->d_S.p, slot, count, ++h->peer.sepoch, hb, publish ? 1 : 0, h->d_err.p);
+        h->launches++;
+        CK(cudaGetLastError());
+        return 0;
+    }
     NK(g_nccl.AllReduce(h->d_S.p + slot, h->d_S.p + slot, (size_t)count, ncclDouble, ncclSum, h->comm, h->stream));
+    if (publish) {
+        publish_scalars_kernel<<<1, 32, 0, h->stream>>>(h->d_S.p, *publish);
+        h->launches++;
+    }
     return 0;
 }
 
@@ -748,6 +842,64 @@ __global__ void dot_to_slot_kernel(size_t n, const T* __restrict__ a, const T* _
     grid_reduce<1, T>(v, ws, [=](T (&t)[1]) { S[slot] = t[0]; });
 }
 
+// my boundary rows -> the neighbours' ghost rows (peer memory), then the epoch flag of every neighbour
+template <class T>
+__global__ void __launch_bounds__(256)
+halo_push_kernel(PeerPushDesc d, int n_send, const int* __restrict__ rows, const T* __restrict__ x,
+                 unsigned long long epoch, unsigned* ticket)
+{
+    __shared__ bool is_last;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < (size_t)n_send * 3; e += (size_t)gridDim.x * blockDim.x) {
+        const int k = (int)(e / 3), c = (int)(e - (size_t)k * 3);
+        int p = 0;
+        while (p + 1 < d.world && k >= d.send_off[p + 1]) ++p;
+        T* dst = static_cast<T*>(d.y[p]) + (size_t)(d.dst_row0[p] + (k - d.send_off[p])) * 3 + c;
+        *dst = x[(size_t)rows[k] * 3 + c];
+    }
+    __threadfence_system();                   // my stores before the ticket
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1;
+    __syncthreads();
+    if (is_last && threadIdx.x < d.world) {
+        const int p = threadIdx.x;
+        if (d.send_off[p + 1] > d.send_off[p]) {
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(d.flags[p] + d.rank), "l"(epoch) : "memory");
+        }
+    }
+}
+// wait until every neighbour has delivered its rows of this exchange (bounded; raises the watchdog word)
+__global__ void halo_wait_kernel(const unsigned long long* flags_in, unsigned recv_mask, unsigned long long epoch, int* err)
+{
+    const int p = threadIdx.x;
+    if (p < kMaxPeers && ((recv_mask >> p) & 1u)) {
+        unsigned long long v = 0;
+        unsigned spins = 0;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags_in + p) : "memory");
+            if (v >= epoch) break;
+            if (++spins > (1u << 26)) { atomicExch(err, 10); break; }
+        }
+    }
+}
+
+template <class T>
+int halo_exchange_peer(opmgpu_handle h, T* x)
+{
+    const unsigned long long epoch = ++h->peer.epoch;
+    if (h->n_send) {
+        const unsigned grid = (unsigned)std::min<size_t>(((size_t)h->n_send * 3 + 255) / 256, 64);
+        halo_push_kernel<T><<<grid, 256, 0, h->stream>>>(h->peer.desc, h->n_send, h->d_send_rows.p, x, epoch, h->peer.ticket.p);
+        h->launches++;
+    }
+    if (h->peer.recv_mask) {
+        halo_wait_kernel<<<1, 32, 0, h->stream>>>(h->peer.flags_in.p, h->peer.recv_mask, epoch, h->d_err.p);
+        h->launches++;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
 // Row-partitioned SpMV with the halo exchange in flight beside it ("fused
 // SpMV-with-halo step"): pack + ncclSend/ncclRecv run on halo_stream while the tiles that need no
 // ghost value are multiplied; the boundary tiles follow when the ghosts have arrived and add their
@@ -791,7 +943,11 @@ int spmv_with_dots(opmgpu_handle h, int mode, T* x, T* y, const T* w1)
         if (mode == 2) rc = allreduce_slots(h, S_TR, 2);
         return rc;
     }
-    rc = halo_exchange<T>(h, x);
+    // Peer-memory exchange for the solver's own SpMVs: x is the handle's d_y (the buffer the
+    // neighbours have mapped) and an all-reduce follows every such SpMV, so no rank can overwrite
+    // ghost rows a neighbour is still reading.  Everything else takes ncclSend/ncclRecv.
+    if (h->world > 1 && h->peer.ready && mode != 0 && x == vec<T>(h->d_y)) rc = halo_exchange_peer<T>(h, x);
+    else rc = halo_exchange<T>(h, x);
     if (rc) return rc;
     rc = launch_spmv<T>(h, mode, x, y, w1);
     if (rc == -100) {
@@ -1150,12 +1306,9 @@ HostBox next_hostbox(opmgpu_handle h)
 int reduce_and_publish(opmgpu_handle h, int count, HostBox& hb)
 {
     if (h->world == 1) return 0;
-    if (int rc = allreduce_slots(h, S_NRM2, count)) return rc;
-    if (!h->use_hostbox) return 0;
+    if (!h->use_hostbox) return allreduce_slots(h, S_NRM2, count);
     hb.hS = h->h_S; hb.herr = &h->h_flags2[0]; hb.hseq = h->h_seq; hb.seq = ++h->seq;
-    publish_scalars_kernel<<<1, 32, 0, h->stream>>>(h->d_S.p, hb);
-    h->launches++;
-    return 0;
+    return allreduce_slots(h, S_NRM2, count, &hb);
 }
 
 int read_scalars(opmgpu_handle h);
@@ -1499,6 +1652,120 @@ bool same_csc_sizes(opmgpu_handle h, int N, const opmgpu_csc* b, bool full)
     return true;
 }
 
+// Peer-memory halo plan (once per pattern, collective): every rank publishes its ghost-row target
+// (the d_y vector) and its incoming-epoch array -- as CUDA IPC handles for ranks in other processes
+// (torchrun: one process per GPU), as plain pointers plus peer access for ranks that are threads of
+// this process (opmgpu_create_multi).  Any failure on any rank keeps ncclSend/ncclRecv on all of them.
+void close_peer_halo(opmgpu_handle h)
+{
+    for (void* p : h->peer.opened) cudaIpcCloseMemHandle(p);
+    h->peer.opened.clear();
+    h->peer.ready = false;
+}
+
+int setup_peer_halo(opmgpu_handle h)
+{
+    struct Info {
+        cudaIpcMemHandle_t y, flags, inbox, sflags;
+        long long pid;
+        void* raw_y; void* raw_flags; void* raw_inbox; void* raw_sflags;
+        int device, N_local;
+        int recv_off[kMaxPeers], recv_cnt[kMaxPeers];
+    };
+    close_peer_halo(h);
+    const int W = h->world;
+    if (W > kMaxPeers || !h->use_peer_halo) return 0;
+    CK(h->peer.flags_in.ensure(kMaxPeers));
+    CK(h->peer.ticket.ensure(1));
+    const bool first = h->peer.inbox.p == nullptr;      // first plan of this handle (epochs only grow afterwards)
+    CK(h->peer.inbox.ensure((size_t)2 * kMaxPeers * kScalSlots));
+    CK(h->peer.sflags.ensure(kMaxPeers));
+    if (first) {
+        CK(cudaMemsetAsync(h->peer.flags_in.p, 0, sizeof(unsigned long long) * kMaxPeers, h->stream));
+        CK(cudaMemsetAsync(h->peer.ticket.p, 0, sizeof(unsigned), h->stream));
+        CK(cudaMemsetAsync(h->peer.inbox.p, 0, sizeof(double) * 2 * kMaxPeers * kScalSlots, h->stream));
+        CK(cudaMemsetAsync(h->peer.sflags.p, 0, sizeof(unsigned long long) * kMaxPeers, h->stream));
+    }
+    Info mine;
+    std::memset(&mine, 0, sizeof mine);
+    int ok = 1;
+    if (cudaIpcGetMemHandle(&mine.y, h->d_y.p) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+    if (cudaIpcGetMemHandle(&mine.flags, h->peer.flags_in.p) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+    if (cudaIpcGetMemHandle(&mine.inbox, h->peer.inbox.p) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+    if (cudaIpcGetMemHandle(&mine.sflags, h->peer.sflags.p) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+    mine.pid = (long long)getpid();
+    mine.raw_y = h->d_y.p; mine.raw_flags = h->peer.flags_in.p;
+    mine.raw_inbox = h->peer.inbox.p; mine.raw_sflags = h->peer.sflags.p;
+    mine.device = h->device; mine.N_local = h->N;
+    for (int p = 0; p < W; ++p) { mine.recv_off[p] = h->recv_off[p]; mine.recv_cnt[p] = h->recv_cnt[p]; }
+    DevArr<unsigned char> d_mine, d_all;
+    CK(d_mine.ensure(sizeof(Info))); CK(d_all.ensure(sizeof(Info) * (size_t)W));
+    CK(cudaMemcpyAsync(d_mine.p, &mine, sizeof(Info), cudaMemcpyHostToDevice, h->stream));
+    NK(g_nccl.AllGather(d_mine.p, d_all.p, sizeof(Info), ncclUint8, h->comm, h->stream));
+    std::vector<Info> all((size_t)W);
+    CK(cudaMemcpyAsync(all.data(), d_all.p, sizeof(Info) * (size_t)W, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    PeerPushDesc& d = h->peer.desc;
+    std::memset(&d, 0, sizeof d);
+    d.world = W; d.rank = h->rank;
+    h->peer.recv_mask = 0;
+    for (int p = 0; p < W; ++p) {
+        d.send_off[p] = h->send_off[p];
+        if (h->recv_cnt[p] > 0) h->peer.recv_mask |= 1u << p;
+    }
+    d.send_off[W] = h->n_send;
+    PeerScalDesc& sd = h->peer.sdesc;
+    std::memset(&sd, 0, sizeof sd);
+    sd.world = W; sd.rank = h->rank;
+    sd.inbox[h->rank] = h->peer.inbox.p; sd.flags[h->rank] = h->peer.sflags.p;
+    auto map = [&](const cudaIpcMemHandle_t& hd, void*& out) {
+        if (cudaIpcOpenMemHandle(&out, hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return false; }
+        h->peer.opened.push_back(out);
+        return true;
+    };
+    for (int p = 0; p < W && ok; ++p) {
+        if (p == h->rank) continue;
+        const bool halo_peer = h->send_cnt[p] > 0;
+        if (halo_peer) {
+            if (all[p].recv_cnt[h->rank] != h->send_cnt[p]) { ok = 0; break; }
+            d.dst_row0[p] = (long long)all[p].N_local + all[p].recv_off[h->rank];
+        }
+        if (all[p].pid == mine.pid) {
+            // a thread of this process: plain pointers, peer access on
+            const cudaError_t e = cudaDeviceEnablePeerAccess(all[p].device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { ok = 0; cudaGetLastError(); break; }
+            cudaGetLastError();
+            if (halo_peer) { d.y[p] = all[p].raw_y; d.flags[p] = static_cast<unsigned long long*>(all[p].raw_flags); }
+            sd.inbox[p] = static_cast<double*>(all[p].raw_inbox); sd.flags[p] = static_cast<unsigned long long*>(all[p].raw_sflags);
+        } else {
+            void* q = nullptr;
+            if (halo_peer) {
+                if (!map(all[p].y, q)) { ok = 0; break; }
+                d.y[p] = q;
+                if (!map(all[p].flags, q)) { ok = 0; break; }
+                d.flags[p] = static_cast<unsigned long long*>(q);
+            }
+            if (!map(all[p].inbox, q)) { ok = 0; break; }
+            sd.inbox[p] = static_cast<double*>(q);
+            if (!map(all[p].sflags, q)) { ok = 0; break; }
+            sd.flags[p] = static_cast<unsigned long long*>(q);
+        }
+    }
+    // everybody or nobody
+    DevArr<int> d_ok;
+    CK(d_ok.ensure(1));
+    CK(cudaMemcpyAsync(d_ok.p, &ok, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    NK(g_nccl.AllReduce(d_ok.p, d_ok.p, 1, ncclInt32, ncclMin, h->comm, h->stream));
+    CK(cudaMemcpyAsync(&ok, d_ok.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    d_mine.release(); d_all.release(); d_ok.release();
+    if (!ok) { close_peer_halo(h); return 0; }
+    h->peer.ready = true;
+    if (getenv("OPMGPU_DEBUG")) fprintf(stderr, "[opmgpu] rank %d: halo exchange through peer memory (%s)\n", h->rank,
+                                        h->peer.opened.empty() ? "same process" : "CUDA IPC");
+    return 0;
+}
+
 // float instance: round the caller's doubles once into the handle's own float array (what the
 // assignment to the reference's float matrix does, ...Interleaved.cpp:189)
 int take_values_f32(opmgpu_handle h, const double* vals_dev)
@@ -1588,6 +1855,7 @@ int opmgpu_create(int device, opmgpu_handle* out)
     cudaFuncSetAttribute(spmv3_tma_kernel<1, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
     cudaFuncSetAttribute(spmv3_tma_kernel<2, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
     if (const char* s = getenv("OPMGPU_HALO_OVERLAP")) h->overlap_halo = atoi(s) != 0;
+    if (const char* s = getenv("OPMGPU_PEER_HALO")) h->use_peer_halo = atoi(s) != 0;
     cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     cudaFuncSetAttribute(ilu0_factor_pipe_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
     cudaFuncSetAttribute(ilu0_factor_pipe_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
@@ -1690,6 +1958,7 @@ int opmgpu_destroy(opmgpu_handle h)
     h->d_S.release(); h->d_partials.release(); h->d_ticket.release(); h->d_flags.release();
     h->d_rowptr_full.release(); h->d_colidx_full.release(); h->d_lu_src.release(); h->d_send_rows.release(); h->d_sendbuf.release();
     h->d_bnd_rows.release(); h->d_row_skip.release();
+    close_peer_halo(h); h->peer.flags_in.release(); h->peer.ticket.release(); h->peer.inbox.release(); h->peer.sflags.release();
     if (h->halo_stream) { cudaStreamDestroy(h->halo_stream); cudaEventDestroy(h->ev_x_ready); cudaEventDestroy(h->ev_halo_done); h->halo_stream = nullptr; }
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     h->d_err.release(); h->d_bad.release(); h->d_map9.release(); h->d_cscval.release(); h->d_rhs_stage.release();
@@ -2294,6 +2563,14 @@ int opmgpu_set_pattern_bcrs_distributed(opmgpu_handle h, int N_local, int nnzb_l
     if (N_local != (int)(row_offsets[h->rank + 1] - row_offsets[h->rank]) || rowptr[N_local] != nnzb_local)
         return h->bad("local row count does not match row_offsets");
     CK(cudaSetDevice(h->device));
+    if (h->peer.ready) {
+        // neighbours have this rank's vectors mapped: nobody may free or remap anything before every
+        // rank has dropped its mappings
+        CK(cudaStreamSynchronize(h->stream));
+        close_peer_halo(h);
+        NK(g_nccl.AllReduce(h->d_bad.p, h->d_bad.p, 1, ncclInt32, ncclMax, h->comm, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
     LocalPartition lp;
     partition_local_rows(N_local, rowptr, colidx_global, row_offsets, h->world, h->rank, lp);
     h->n_ghost = lp.n_ghost;
@@ -2369,6 +2646,7 @@ int opmgpu_set_pattern_bcrs_distributed(opmgpu_handle h, int N_local, int nnzb_l
     if ((rc = ensure_vectors(h))) return rc;
     CK(cudaStreamSynchronize(h->stream));
     d_cnt_mine.release(); d_cnt_all.release(); d_want.release(); d_asked.release();
+    if ((rc = setup_peer_halo(h))) return rc;
     h->have_pattern = true;
     return OPMGPU_OK;
 }
