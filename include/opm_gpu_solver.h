@@ -179,6 +179,11 @@ int  opmgpu_solve_from_csc_blocks(opmgpu_handle h, int N, const opmgpu_csc block
 
 /* ---- kernel-level entry points (parity tests, micro-benchmarks) -------------------------- */
 
+/* The operator alone: uploads the pattern for opmgpu_spmv* without the ILU0 analysis (the SpMV
+ * sweep of BASELINE.json config 5 reaches sizes where matrix + factor records exceed the HBM).
+ * Factorisation and solves answer OPMGPU_BAD_ARGUMENT until opmgpu_set_pattern_bcrs is called. */
+int  opmgpu_set_pattern_bcrs_operator_only(opmgpu_handle h, int N, int nnzb, const int* rowptr, const int* colidx);
+
 /* Upload BCRS values for the current pattern (device copy kept in the handle). */
 int  opmgpu_set_values_bcrs3(opmgpu_handle h, const double* vals);
 int  opmgpu_set_values_bcrs3_dev(opmgpu_handle h, const double* vals_dev);

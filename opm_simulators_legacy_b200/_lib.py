@@ -24,6 +24,7 @@ EXPORTS = [
     "opmgpu_ilu0_factor", "opmgpu_ilu0_get_factors", "opmgpu_ilu0_apply", "opmgpu_ilu0_apply_dev",
     "opmgpu_dot", "opmgpu_num_levels", "opmgpu_launch_count", "opmgpu_residual_history",
     "opmgpu_set_profiling", "opmgpu_get_profile", "opmgpu_set_precision", "opmgpu_get_precision",
+    "opmgpu_set_pattern_bcrs_operator_only",
 ]
 
 OK, NOT_CONVERGED, SINGULAR_BLOCK, BREAKDOWN, BAD_PATTERN, BAD_ARGUMENT = 0, 1, 2, 3, 4, 5
@@ -85,6 +86,7 @@ def load():
         "opmgpu_set_precision": (C.c_int, [H, C.c_int]),
         "opmgpu_get_precision": (C.c_int, [H]),
         "opmgpu_set_pattern_bcrs": (C.c_int, [H, C.c_int, C.c_int, ip, ip]),
+        "opmgpu_set_pattern_bcrs_operator_only": (C.c_int, [H, C.c_int, C.c_int, ip, ip]),
         "opmgpu_set_pattern_bcrs_distributed": (C.c_int, [H, C.c_int, C.c_int, ip, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
         "opmgpu_solve_bcrs3": (C.c_int, [H, dp, dp, dp, PP, RP]),
         "opmgpu_solve_bcrs3_dev": (C.c_int, [H, vp, vp, vp, PP, RP]),

@@ -226,6 +226,7 @@ struct opmgpu_solver {
     // arrays), factors / sweep records / scalar block keep their 8-byte containers.  The C ABI
     // exchanges doubles either way; d_stage holds them on their way in and out.
     bool f32 = false;
+    bool operator_only = false;    // opmgpu_set_pattern_bcrs_operator_only: no ILU0 programs, SpMV entry points only
     DevArr<double> d_vals_own, d_lu, d_stage;
     DevArr<float> d_vals32;
     const void* d_vals = nullptr;
@@ -616,6 +617,7 @@ int set_pattern(opmgpu_handle h, int N, int nnzb, const int* rowptr, const int* 
         }
     }
     h->have_pattern = h->have_values = h->have_factors = false;
+    h->operator_only = false;
     analyse_pattern(N, rowptr, colidx, h->sweep_ctas, h->an, h->force_simple, &h->caps);
     h->cluster_size = h->an.cluster_size;
     if (h->an.missing_diag_row >= 0) {
@@ -976,6 +978,7 @@ template <class T>
 int factor_t(opmgpu_handle h, int* bad_row)
 {
     if (!h->have_values) return h->bad("no matrix values set");
+    if (h->operator_only) return h->bad("the pattern was set operator-only (no ILU0 analysis): opmgpu_set_pattern_bcrs first");
     if (h->f32 && h->use_col) return h->bad("the column-owned sweeps (OPMGPU_COL=1) exist for the double instance only");
     const size_t nv = (size_t)h->nnzb * 9;
     const bool pipe_factor = h->pipeF.valid && !h->factor_by_levels;
@@ -1987,6 +1990,30 @@ int opmgpu_set_pattern_bcrs(opmgpu_handle h, int N, int nnzb, const int* rowptr,
     CK(cudaSetDevice(h->device));
     h->csc_colptr.clear(); h->csc_rowidx.clear();
     return set_pattern(h, N, nnzb, rowptr, colidx);
+}
+
+// Operator only: the pattern is uploaded for y = A x, no ILU0 analysis is run (micro-benchmarks of
+// the SpMV at sizes where the factor records would not fit beside the matrix; BASELINE.json config 5).
+int opmgpu_set_pattern_bcrs_operator_only(opmgpu_handle h, int N, int nnzb, const int* rowptr, const int* colidx)
+{
+    if (!h || !rowptr || !colidx) return OPMGPU_BAD_ARGUMENT;
+    if (h->multi || h->world > 1) return h->bad("operator-only patterns exist for plain single-GPU handles");
+    if (N < 1 || nnzb < N || rowptr[0] != 0 || rowptr[N] != nnzb) return h->bad("bad BCRS pattern sizes");
+    CK(cudaSetDevice(h->device));
+    h->have_pattern = h->have_values = h->have_factors = false;
+    h->csc_colptr.clear(); h->csc_rowidx.clear();
+    h->use_pipe = false; h->use_col = false;
+    h->pipeL.release(); h->pipeU.release(); h->pipeF.release(); h->progL.release(); h->progU.release(); h->d_lu.release();
+    h->N = N; h->nnzb = nnzb; h->n_ghost = 0;
+    CK(h->d_rowptr.ensure((size_t)N + 1 + 8));
+    CK(h->d_colidx.ensure((size_t)nnzb + 8));
+    CK(cudaMemcpyAsync(h->d_rowptr.p, rowptr, sizeof(int) * ((size_t)N + 1), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_colidx.p, colidx, sizeof(int) * (size_t)nnzb, cudaMemcpyHostToDevice, h->stream));
+    CK(h->d_tmp.ensure((size_t)N * 3)); CK(h->d_tmp2.ensure((size_t)N * 3));
+    CK(cudaStreamSynchronize(h->stream));
+    h->operator_only = true;
+    h->have_pattern = true;
+    return OPMGPU_OK;
 }
 
 int opmgpu_set_values_bcrs3(opmgpu_handle h, const double* vals)

@@ -167,6 +167,14 @@ class GpuLinearSolver:
         self.N, self.nnzb = rowptr.size - 1, colidx.size
         self._check(self.lib.opmgpu_set_pattern_bcrs(self.h, self.N, self.nnzb, _ip(rowptr), _ip(colidx)))
 
+    def set_pattern_operator_only(self, rowptr, colidx):
+        """Pattern for spmv / spmv_dev only (no ILU0 analysis): SpMV micro-benchmarks at sizes where
+        the factor records would not fit beside the matrix."""
+        rowptr = np.ascontiguousarray(rowptr, dtype=np.int32)
+        colidx = np.ascontiguousarray(colidx, dtype=np.int32)
+        self.N, self.nnzb = rowptr.size - 1, colidx.size
+        self._check(self.lib.opmgpu_set_pattern_bcrs_operator_only(self.h, self.N, self.nnzb, _ip(rowptr), _ip(colidx)))
+
     def set_values(self, vals):
         vals = np.ascontiguousarray(vals, dtype=np.float64)
         assert vals.size == self.nnzb * 9
