@@ -810,7 +810,20 @@ int launch_spmv(opmgpu_handle h, int mode, const T* x, T* y, const T* w1)
         const int nnzb = h->world > 1 ? h->nnzb_full : h->nnzb;
         const int ntiles = (h->N + kSpmvRows - 1) / kSpmvRows;
         const unsigned grid = (unsigned)std::min(ntiles, h->sm_count);
-        if (mode == 0) spmv3_tma_kernel<0, T><<<grid, kSpmvThreads, kSpmvSmemBytes, h->stream>>>(h->N, nnzb, rowptr, colidx, vals, x, y, w1, h->d_S.p, h->ws());
+        static const int rowt_env = getenv("OPMGPU_SPMV_ROWT") ? atoi(getenv("OPMGPU_SPMV_ROWT")) : -1;
+        const bool rowt = rowt_env >= 0 ? rowt_env != 0 : sizeof(T) == 4;      // thread per row: the float instance's default
+        if (sizeof(T) == 4 && rowt_env < 0) {
+            // float instance: 128-row tiles, one thread per row
+            const unsigned grid2 = (unsigned)std::min((h->N + kSpmvRowsF32 - 1) / kSpmvRowsF32, h->sm_count);
+            if (mode == 0) spmv3_tma_kernel<0, float, true, kSpmvRowsF32><<<grid2, kSpmvThreads, kSpmvSmemBytes, h->stream>>>(h->N, nnzb, rowptr, colidx, (const float*)vals, (const float*)x, (float*)y, (const float*)w1, h->d_S.p, h->ws());
+            else if (mode == 1) spmv3_tma_kernel<1, float, true, kSpmvRowsF32><<<grid2, kSpmvThreads, kSpmvSmemBytes, h->stream>>>(h->N, nnzb, rowptr, colidx, (const float*)vals, (const float*)x, (float*)y, (const float*)w1, h->d_S.p, h->ws());
+            else spmv3_tma_kernel<2, float, true, kSpmvRowsF32><<<grid2, kSpmvThreads, kSpmvSmemBytes, h->stream>>>(h->N, nnzb, rowptr, colidx, (const float*)vals, (const float*)x, (float*)y, (const float*)w1, h->d_S.p, h->ws());
+        } else if (rowt) {
+            if (mode == 0) spmv3_tma_kernel<0, T, true><<<grid, kSpmvThreads, kSpmvSmemBytes, h->stream>>>(h->N, nnzb, rowptr, colidx, vals, x, y, w1, h->d_S.p, h->ws());
+            else if (mode == 1) spmv3_tma_kernel<1, T, true><<<grid, kSpmvThreads, kSpmvSmemBytes, h->stream>>>(h->N, nnzb, rowptr, colidx, vals, x, y, w1, h->d_S.p, h->ws());
+            else spmv3_tma_kernel<2, T, true><<<grid, kSpmvThreads, kSpmvSmemBytes, h->stream>>>(h->N, nnzb, rowptr, colidx, vals, x, y, w1, h->d_S.p, h->ws());
+        }
+        else if (mode == 0) spmv3_tma_kernel<0, T><<<grid, kSpmvThreads, kSpmvSmemBytes, h->stream>>>(h->N, nnzb, rowptr, colidx, vals, x, y, w1, h->d_S.p, h->ws());
         else if (mode == 1) spmv3_tma_kernel<1, T><<<grid, kSpmvThreads, kSpmvSmemBytes, h->stream>>>(h->N, nnzb, rowptr, colidx, vals, x, y, w1, h->d_S.p, h->ws());
         else spmv3_tma_kernel<2, T><<<grid, kSpmvThreads, kSpmvSmemBytes, h->stream>>>(h->N, nnzb, rowptr, colidx, vals, x, y, w1, h->d_S.p, h->ws());
         h->launches++;
@@ -1857,6 +1870,15 @@ int opmgpu_create(int device, opmgpu_handle* out)
     cudaFuncSetAttribute(spmv3_tma_kernel<0, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
     cudaFuncSetAttribute(spmv3_tma_kernel<1, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
     cudaFuncSetAttribute(spmv3_tma_kernel<2, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
+    cudaFuncSetAttribute(spmv3_tma_kernel<0, float, true, kSpmvRowsF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
+    cudaFuncSetAttribute(spmv3_tma_kernel<1, float, true, kSpmvRowsF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
+    cudaFuncSetAttribute(spmv3_tma_kernel<2, float, true, kSpmvRowsF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
+    cudaFuncSetAttribute(spmv3_tma_kernel<0, float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
+    cudaFuncSetAttribute(spmv3_tma_kernel<1, float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
+    cudaFuncSetAttribute(spmv3_tma_kernel<2, float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
+    cudaFuncSetAttribute(spmv3_tma_kernel<0, double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
+    cudaFuncSetAttribute(spmv3_tma_kernel<1, double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
+    cudaFuncSetAttribute(spmv3_tma_kernel<2, double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
     if (const char* s = getenv("OPMGPU_HALO_OVERLAP")) h->overlap_halo = atoi(s) != 0;
     if (const char* s = getenv("OPMGPU_PEER_HALO")) h->use_peer_halo = atoi(s) != 0;
     cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);

@@ -30,6 +30,19 @@ constexpr int kSpmvPtrBytes = ((kSpmvRows + 1 + 3) * 4 + 15) / 16 * 16;
 constexpr int kSpmvStageBytes = kSpmvValBytes + kSpmvColBytes + kSpmvPtrBytes;
 constexpr size_t kSpmvSmemBytes = 128 + (size_t)kSpmvStages * kSpmvStageBytes;
 static_assert(kSpmvStages % 3 == 0, "stages must be a multiple of the consumer groups");
+// Float instance: 36-byte blocks, so a stage of the same size holds a tile of 128 rows (one thread
+// per row) -- half as many tiles, i.e. half the per-tile cost of the producer warp.
+constexpr int kSpmvRowsF32 = 128;
+constexpr int kSpmvCapBlocksF32 = kSpmvRowsF32 * 7 + 8;
+constexpr int kSpmvValBytesF32 = kSpmvCapBlocksF32 * 36;
+constexpr int kSpmvColBytesF32 = ((kSpmvCapBlocksF32 + 4) * 4 + 15) / 16 * 16;
+constexpr int kSpmvPtrBytesF32 = ((kSpmvRowsF32 + 1 + 3) * 4 + 15) / 16 * 16;
+static_assert(kSpmvValBytesF32 % 16 == 0 && kSpmvValBytesF32 + kSpmvColBytesF32 + kSpmvPtrBytesF32 <= kSpmvStageBytes, "float tiles fit the stage");
+template <int ROWS> struct SpmvTile {
+    static constexpr int cap = ROWS == kSpmvRows ? kSpmvCapBlocks : kSpmvCapBlocksF32;
+    static constexpr int val_bytes = ROWS == kSpmvRows ? kSpmvValBytes : kSpmvValBytesF32;
+    static constexpr int col_bytes = ROWS == kSpmvRows ? kSpmvColBytes : kSpmvColBytesF32;
+};
 
 // rowptr / colidx must be readable up to 16 bytes past their end (the solver's own buffers are
 // padded); vals is never read past its end (a misaligned last tile takes the direct path).
@@ -39,19 +52,24 @@ static_assert(kSpmvStages % 3 == 0, "stages must be a multiple of the consumer g
 // boundary row -- it references a ghost column whose value may still be in flight (the halo
 // exchange runs beside this kernel), so it is neither stored nor counted in the dot products here;
 // spmv3_rows_kernel computes those rows when the ghosts have arrived.
-template <int MODE, class T>
+// ROWT: one thread per block ROW (the first 64 threads of a group; three accumulators) instead of one
+// per (row, component): a third of the x gathers, which is what bounds the float instance once the
+// matrix bytes are halved.  Same operation order per component either way.
+template <int MODE, class T, bool ROWT = false, int ROWS = kSpmvRows>
 __global__ void __launch_bounds__(kSpmvThreads, 1)
 spmv3_tma_kernel(int N, int nnzb, const int* __restrict__ rowptr, const int* __restrict__ colidx,
                  const T* __restrict__ vals, const T* __restrict__ x, T* __restrict__ y,
                  const T* __restrict__ w1, double* S, ReduceWs ws, const unsigned long long* __restrict__ row_skip = nullptr)
 {
     constexpr int kAl = sizeof(T) == 8 ? 2 : 4;          // blocks per 16-byte aligned unit (144 bytes)
+    constexpr int kCap = SpmvTile<ROWS>::cap, kValB = SpmvTile<ROWS>::val_bytes, kColB = SpmvTile<ROWS>::col_bytes;
+    static_assert(ROWS == kSpmvRows || (ROWT && sizeof(T) == 4), "128-row tiles: float, one thread per row");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned long long* full = reinterpret_cast<unsigned long long*>(smem_raw);
     unsigned long long* empty = full + kSpmvStages;
     unsigned char* stages = smem_raw + 128;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int ntiles = (N + kSpmvRows - 1) / kSpmvRows;
+    const int ntiles = (N + ROWS - 1) / ROWS;
 
     if (tid == 0) {
         for (int i = 0; i < kSpmvStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kSpmvComputeWarps); }
@@ -61,56 +79,104 @@ spmv3_tma_kernel(int N, int nnzb, const int* __restrict__ rowptr, const int* __r
 
     T d0 = T(0), d1 = T(0);                     // dot partials of this thread
     if (warp == 0) {
-        if (lane == 0) {
-            int it = 0;
-            for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-                const int st = it % kSpmvStages, k = it / kSpmvStages;
-                const int r0 = t * kSpmvRows, r1 = min(N, r0 + kSpmvRows);
-                const int b0 = rowptr[r0], b1 = rowptr[r1];
-                const int b0a = b0 & ~(kAl - 1);                          // 16-byte aligned start
-                int b1a = (b1 + kAl - 1) & ~(kAl - 1);
-                const bool direct = (b1a > nnzb) || (b1a - b0a > kSpmvCapBlocks);   // odd tail / oversized tile
-                if (k > 0) { while (!mbar_try_wait(&empty[st], (unsigned)((k - 1) & 1))) {} }
-                unsigned char* stage = stages + (size_t)st * kSpmvStageBytes;
-                int* hdr = reinterpret_cast<int*>(stage + kSpmvValBytes + kSpmvColBytes);
-                // the row pointers always travel; values and columns unless the tile is direct
-                const unsigned pbytes = (unsigned)(((r1 - r0 + 1) * 4 + 15) & ~15);
-                const int c0a = b0 & ~3;
-                const unsigned cbytes = direct ? 0u : (unsigned)((((b1 - c0a) * 4) + 15) & ~15);
-                const unsigned vbytes = direct ? 0u : (unsigned)((b1a - b0a) * 9 * (int)sizeof(T));
-                mbar_arrive_expect_tx(&full[st], pbytes + cbytes + vbytes);
-                tma_bulk_g2s(hdr, rowptr + r0, pbytes, &full[st]);
-                if (!direct) {
-                    tma_bulk_g2s(stage, vals + (size_t)b0a * 9, vbytes, &full[st]);
-                    tma_bulk_g2s(stage + kSpmvValBytes, colidx + c0a, cbytes, &full[st]);
-                }
-            }
+        // Producer warp.  The per-tile cost of this loop bounds the whole kernel once the tiles are
+        // small (a tile is 32 KB of values in double, 16 KB in float): the block range of the NEXT tile
+        // is fetched while this one is issued, and the tile's three bulk copies (values, column
+        // indices, row pointers) leave as ONE warp instruction, lanes 0..2 with their own operands.
+        int it = 0;
+        int t = blockIdx.x;
+        int b0n = 0, b1n = 0;
+        if (t < ntiles) { b0n = rowptr[t * ROWS]; b1n = rowptr[min(N, t * ROWS + ROWS)]; }
+        for (; t < ntiles; t += gridDim.x, ++it) {
+            const int st = it % kSpmvStages, k = it / kSpmvStages;
+            const int r0 = t * ROWS, r1 = min(N, r0 + ROWS);
+            const int b0 = b0n, b1 = b1n;
+            const int tn = t + (int)gridDim.x;
+            if (tn < ntiles) { b0n = rowptr[tn * ROWS]; b1n = rowptr[min(N, tn * ROWS + ROWS)]; }
+            const int b0a = b0 & ~(kAl - 1);                          // 16-byte aligned start
+            int b1a = (b1 + kAl - 1) & ~(kAl - 1);
+            const bool direct = (b1a > nnzb) || (b1a - b0a > kCap);   // odd tail / oversized tile
+            if (k > 0) { while (!mbar_try_wait(&empty[st], (unsigned)((k - 1) & 1))) {} }
+            unsigned char* stage = stages + (size_t)st * kSpmvStageBytes;
+            // the row pointers always travel; values and columns unless the tile is direct
+            const unsigned pbytes = (unsigned)(((r1 - r0 + 1) * 4 + 15) & ~15);
+            const int c0a = b0 & ~3;
+            const unsigned cbytes = direct ? 0u : (unsigned)((((b1 - c0a) * 4) + 15) & ~15);
+            const unsigned vbytes = direct ? 0u : (unsigned)((b1a - b0a) * 9 * (int)sizeof(T));
+            if (lane == 0) mbar_arrive_expect_tx(&full[st], pbytes + cbytes + vbytes);
+            __syncwarp();
+            void* dst = lane == 0 ? (void*)stage : (lane == 1 ? (void*)(stage + kValB) : (void*)(stage + kValB + kColB));
+            const void* src = lane == 0 ? (const void*)(vals + (size_t)b0a * 9) : (lane == 1 ? (const void*)(colidx + c0a) : (const void*)(rowptr + r0));
+            const unsigned bytes = lane == 0 ? vbytes : (lane == 1 ? cbytes : pbytes);
+            if (lane < 3 && bytes > 0) tma_bulk_g2s(dst, src, bytes, &full[st]);
         }
     } else {
         // consumer group g takes every kSpmvGroups-th tile of this CTA, so several tiles' x
         // gathers (L2 latency) are in flight per SM
         const int g = (warp - 1) / kSpmvComputeWarps;
         const int ct = tid - 32 - g * kSpmvComputeWarps * 32;
-        const int rl = ct / 3, c = ct - rl * 3;
+        const int rl = ROWT ? ct : ct / 3, c = ROWT ? 0 : ct - rl * 3;
         int it = 0;
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
             if (it % kSpmvGroups != g) continue;
             const int st = it % kSpmvStages, k = it / kSpmvStages;
-            const int r0 = t * kSpmvRows, r1 = min(N, r0 + kSpmvRows);
+            const int r0 = t * ROWS, r1 = min(N, r0 + ROWS);
             while (!mbar_try_wait(&full[st], (unsigned)(k & 1))) {}
             const unsigned char* stage = stages + (size_t)st * kSpmvStageBytes;
-            const int* rp = reinterpret_cast<const int*>(stage + kSpmvValBytes + kSpmvColBytes);
+            const int* rp = reinterpret_cast<const int*>(stage + kValB + kColB);
             const int b0 = rp[0], b1 = rp[r1 - r0];
             const int b0a = b0 & ~(kAl - 1), b1a = (b1 + kAl - 1) & ~(kAl - 1), c0a = b0 & ~3;
-            const bool direct = (b1a > nnzb) || (b1a - b0a > kSpmvCapBlocks);
+            const bool direct = (b1a > nnzb) || (b1a - b0a > kCap);
             const int r = r0 + rl;
-            const bool skip = row_skip && ((row_skip[t] >> rl) & 1ull);
-            if (r < r1 && !skip) {
+            const bool skip = row_skip && rl < ROWS && ((row_skip[t] >> rl) & 1ull);
+            if (ROWT && rl < ROWS && r < r1 && !skip) {
+                const int kb = rp[rl], ke = rp[rl + 1];
+                T a0 = T(0), a1 = T(0), a2 = T(0);
+                if (!direct) {
+                    const T* vs = reinterpret_cast<const T*>(stage);
+                    const int* cs = reinterpret_cast<const int*>(stage + kValB);
+                    for (int kk = kb; kk < ke; kk += 8) {
+                        T xv[8][3];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            if (kk + u < ke) {
+                                const T* xj = x + (size_t)cs[kk + u - c0a] * 3;
+                                xv[u][0] = xj[0]; xv[u][1] = xj[1]; xv[u][2] = xj[2];
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            if (kk + u < ke) {
+                                const T* a = vs + (size_t)(kk + u - b0a) * 9;
+                                a0 = fma(a[0], xv[u][0], a0); a0 = fma(a[1], xv[u][1], a0); a0 = fma(a[2], xv[u][2], a0);
+                                a1 = fma(a[3], xv[u][0], a1); a1 = fma(a[4], xv[u][1], a1); a1 = fma(a[5], xv[u][2], a1);
+                                a2 = fma(a[6], xv[u][0], a2); a2 = fma(a[7], xv[u][1], a2); a2 = fma(a[8], xv[u][2], a2);
+                            }
+                        }
+                    }
+                } else {
+                    for (int kk = kb; kk < ke; ++kk) {
+                        const T* a = vals + (size_t)kk * 9;
+                        const T* xj = x + (size_t)colidx[kk] * 3;
+                        a0 = fma(a[0], xj[0], a0); a0 = fma(a[1], xj[1], a0); a0 = fma(a[2], xj[2], a0);
+                        a1 = fma(a[3], xj[0], a1); a1 = fma(a[4], xj[1], a1); a1 = fma(a[5], xj[2], a1);
+                        a2 = fma(a[6], xj[0], a2); a2 = fma(a[7], xj[1], a2); a2 = fma(a[8], xj[2], a2);
+                    }
+                }
+                const size_t o = (size_t)r * 3;
+                y[o] = a0; y[o + 1] = a1; y[o + 2] = a2;
+                if (MODE == 1) { d0 = fma(w1[o], a0, d0); d0 = fma(w1[o + 1], a1, d0); d0 = fma(w1[o + 2], a2, d0); }
+                if (MODE == 2) {
+                    d0 = fma(a0, w1[o], d0); d1 = fma(a0, a0, d1);
+                    d0 = fma(a1, w1[o + 1], d0); d1 = fma(a1, a1, d1);
+                    d0 = fma(a2, w1[o + 2], d0); d1 = fma(a2, a2, d1);
+                }
+            } else if (!ROWT && r < r1 && !skip) {
                 const int kb = rp[rl], ke = rp[rl + 1];
                 T acc = T(0);
                 if (!direct) {
                     const T* vs = reinterpret_cast<const T*>(stage) + c * 3;
-                    const int* cs = reinterpret_cast<const int*>(stage + kSpmvValBytes);
+                    const int* cs = reinterpret_cast<const int*>(stage + kValB);
                     // all x gathers of up to eight blocks are issued before the FMA chain
                     for (int kk = kb; kk < ke; kk += 8) {
                         T xv[8][3];
