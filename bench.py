@@ -383,8 +383,8 @@ def measure(workload, steps, warmup, rank, world, local, sample_clocks=True, sin
         if single or not with_allcores:
             raise RuntimeError("not measured for this sub-line (the OpenMP baseline exists for the double instance)")
         ncpu = len(os.sched_getaffinity(0))
-        x_b, rb = O.solve_bcrs_openmp(rp, ci, v, b, nthreads=ncpu)          # warm-up (page faults, thread pool)
-        x_b, rb = O.solve_bcrs_openmp(rp, ci, v, b, nthreads=ncpu)
+        x_b, rb = oracle_py.solve_bcrs_openmp(rp, ci, v, b, nthreads=ncpu)          # warm-up (page faults, thread pool)
+        x_b, rb = oracle_py.solve_bcrs_openmp(rp, ci, v, b, nthreads=ncpu)
         allcores = {"value": rb["ms_factor"] + rb["ms_solve"], "unit": "ms", "cores": rb["threads"], "kind": "port-openmp",
                     "note": "NOT the reference (its solver is sequential): oracle arithmetic, level-scheduled ILU0 factor / "
                             "sweeps, row-parallel SpMV, OpenMP reductions; level sets excluded like the GPU's pattern analysis",

@@ -2229,6 +2229,7 @@ int opmgpu_solve_bcrs3_dev(opmgpu_handle h, const double* vals_dev, const double
 {
     if (!h || !rhs_dev || !x_dev || !params || !result) return OPMGPU_BAD_ARGUMENT;
     if (!h->have_pattern) return h->bad("set the pattern first");
+    if (h->operator_only) return h->bad("the pattern was set operator-only (no ILU0 analysis): opmgpu_set_pattern_bcrs first");
     if (!vals_dev && !h->have_values) return h->bad("vals_dev == NULL: no matrix values are resident (opmgpu_set_values_bcrs3[_dev])");
     std::memset(result, 0, sizeof *result);
     result->bad_row = -1;
@@ -2278,6 +2279,7 @@ int opmgpu_solve_bcrs3(opmgpu_handle h, const double* vals, const double* rhs, d
     if (!h || !vals || !rhs || !x || !params || !result) return OPMGPU_BAD_ARGUMENT;
     if (h->multi) return multi_solve_bcrs3(h->multi, vals, rhs, x, params, result, h->err);
     if (!h->have_pattern) return h->bad("set the pattern first");
+    if (h->operator_only) return h->bad("the pattern was set operator-only (no ILU0 analysis): opmgpu_set_pattern_bcrs first");
     std::memset(result, 0, sizeof *result);
     result->bad_row = -1;
     CK(cudaSetDevice(h->device));

@@ -496,18 +496,27 @@ ilu0_sweep_pipe_kernel(PipeDev pg, const double* __restrict__ rhs_perm, double* 
     if (nsteps == 0) {
         // (cluster launch) nothing to do, but stay until the cluster is done
     } else if (warp == 0) {
-        // ------------------------------------------------ TMA producer (one elected lane)
-        if (lane == 0) {
-            for (int i = 0; i < nsteps; ++i) {
-                const int st = i % S, k = i / S;
-                const unsigned off16 = pg.step_off16[s0 + i], bytes = pg.step_bytes[s0 + i];
-                const unsigned rrow = pg.step_rhs_row[s0 + i], rbytes = pg.step_rhs_bytes[s0 + i];
-                if (k > 0 && !pipe_wait(&ctl->empty[st], (unsigned)((k - 1) & 1), ctl, err)) break;
-                unsigned char* stage = stages + st * stage_stride;
-                mbar_arrive_expect_tx(&ctl->full[st], bytes + rbytes);
-                tma_bulk_g2s(stage + pg.rhs_bytes, pg.buf + (size_t)off16 * 16, bytes, &ctl->full[st]);
-                tma_bulk_g2s(stage, rhs_perm + (size_t)rrow * 3, rbytes, &ctl->full[st]);
+        // ------------------------------------------------ TMA producer
+        // (the warp runs the loop uniformly: the descriptors of the NEXT step are fetched while this
+        // one is issued, and the step's two bulk copies -- record and right-hand side -- leave as one
+        // warp instruction, lanes 0 and 1 with their own operands)
+        unsigned off16n = 0, bytesn = 0, rrown = 0, rbytesn = 0;
+        if (nsteps > 0) { off16n = pg.step_off16[s0]; bytesn = pg.step_bytes[s0]; rrown = pg.step_rhs_row[s0]; rbytesn = pg.step_rhs_bytes[s0]; }
+        for (int i = 0; i < nsteps; ++i) {
+            const int st = i % S, k = i / S;
+            const unsigned off16 = off16n, bytes = bytesn, rrow = rrown, rbytes = rbytesn;
+            if (i + 1 < nsteps) {
+                off16n = pg.step_off16[s0 + i + 1]; bytesn = pg.step_bytes[s0 + i + 1];
+                rrown = pg.step_rhs_row[s0 + i + 1]; rbytesn = pg.step_rhs_bytes[s0 + i + 1];
             }
+            if (k > 0 && !pipe_wait(&ctl->empty[st], (unsigned)((k - 1) & 1), ctl, err)) break;
+            unsigned char* stage = stages + st * stage_stride;
+            if (lane == 0) mbar_arrive_expect_tx(&ctl->full[st], bytes + rbytes);
+            __syncwarp();
+            void* dst = lane == 0 ? (void*)(stage + pg.rhs_bytes) : (void*)stage;
+            const void* src = lane == 0 ? (const void*)(pg.buf + (size_t)off16 * 16) : (const void*)(rhs_perm + (size_t)rrow * 3);
+            const unsigned nb = lane == 0 ? bytes : rbytes;
+            if (lane < 2 && nb > 0) tma_bulk_g2s(dst, src, nb, &ctl->full[st]);
         }
     } else if (warp <= kPipeHelpers) {
         // ------------------------------------------------ pushed-result helpers

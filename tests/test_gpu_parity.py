@@ -443,3 +443,26 @@ def test_watchdog_trip_is_reported_and_recovered(gpu_solver, oracle):
         gpu_solver.ilu0_apply(0.9, b)
     lu_ref, _ = oracle.ilu0_factor(rp, ci, v)
     assert np.array_equal(gpu_solver.ilu0_apply(0.9, b), oracle.ilu0_apply(rp, ci, lu_ref, 0.9, b))
+
+
+def test_operator_only_pattern(oracle):
+    """opmgpu_set_pattern_bcrs_operator_only: y = A x without the ILU0 analysis (the SpMV sweep at
+    sizes where the factor records do not fit); factorisation and solves are refused until a full
+    pattern is set."""
+    s = synth_blackoil_jacobian(20, 16, 9, perm="lognormal")
+    rp, ci, v, b = _np(s)
+    g = GpuLinearSolver(0)
+    try:
+        g.set_pattern_operator_only(rp, ci)
+        g.set_values(v)
+        x = s.xstar.numpy()
+        assert np.array_equal(g.spmv(x), oracle.spmv(rp, ci, v, x))
+        with pytest.raises(ValueError):
+            g.ilu0_factor()
+        with pytest.raises(ValueError):
+            g.solve_bcrs(v, b)
+        g.set_pattern(rp, ci)
+        xs, res = g.solve_bcrs(v, b)
+        assert res["iterations"] == oracle.solve_bcrs(rp, ci, v, b)[1]["iterations"]
+    finally:
+        g.close()
