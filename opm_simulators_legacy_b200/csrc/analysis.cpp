@@ -2,6 +2,8 @@
 #include "analysis.hpp"
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -252,6 +254,45 @@ RecLayout rec_layout(int n, int ntail, int npushx, bool upper, bool has_lists)
     return L;
 }
 
+// Host threads for the per-CTA parts of the program builders (OPMGPU_ANALYSIS_THREADS, default: the
+// hardware's, at most 16).  Work items are handed out through an atomic counter; every item writes
+// to its own part of the output, so the result does not depend on the thread count.
+inline int analysis_threads()
+{
+    static const int n = [] {
+        if (const char* e = std::getenv("OPMGPU_ANALYSIS_THREADS")) return std::max(1, std::atoi(e));
+        return (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    }();
+    return n;
+}
+template <class F>
+void parallel_for(int n, F&& f)
+{
+    const int T = std::min(analysis_threads(), n);
+    if (T <= 1) { for (int i = 0; i < n; ++i) f(i); return; }
+    std::atomic<int> next{0};
+    std::vector<std::thread> th;
+    th.reserve(T);
+    for (int t = 0; t < T; ++t)
+        th.emplace_back([&]() { for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) f(i); });
+    for (auto& x : th) x.join();
+}
+// keys whose leading field is the owner: bucket by owner, sort the buckets side by side
+inline void sort_keys_by_owner(std::vector<unsigned long long>& key, const std::vector<int>& owner, int max_owner)
+{
+    const int N = (int)key.size();
+    std::vector<size_t> bptr((size_t)max_owner + 2, 0);
+    for (int r = 0; r < N; ++r) ++bptr[(size_t)owner[r] + 1];
+    for (int c = 0; c <= max_owner; ++c) bptr[c + 1] += bptr[c];
+    std::vector<unsigned long long> skey(N);
+    {
+        std::vector<size_t> fill(bptr.begin(), bptr.end() - 1);
+        for (int r = 0; r < N; ++r) skey[fill[owner[r]]++] = key[r];
+    }
+    parallel_for(max_owner + 1, [&](int c) { std::sort(skey.begin() + bptr[c], skey.begin() + bptr[c + 1]); });
+    key.swap(skey);
+}
+
 // upos_of_row: for the lower program, position of every natural row in the upper program's
 // order (the lower sweep hands its result to the upper sweep in that order); null for upper.
 // owner[r]: CTA of row r; tile[r]: its tile.  A CTA may own several tiles (large grids), which it
@@ -295,7 +336,7 @@ void build_pipe_program(int N, const int* rowptr, const int* colidx, const std::
                 const unsigned long long t = lower ? (unsigned long long)tile[r] : (unsigned long long)(max_tile - tile[r]);
                 key[r] = ((((unsigned long long)owner[r] << bt | t) << bl | (unsigned long long)level[r]) << br) | (unsigned long long)r;
             }
-            std::sort(key.begin(), key.end());
+            sort_keys_by_owner(key, owner, max_owner);
             const unsigned long long mask = (1ULL << br) - 1;
             for (int q = 0; q < N; ++q) order[q] = (int)(key[q] & mask);
         } else {
@@ -313,11 +354,18 @@ void build_pipe_program(int N, const int* rowptr, const int* colidx, const std::
         if (lower) { for (int k = rowptr[r]; k < diag[r]; ++k) fn(k); }
         else       { for (int k = rowptr[r + 1] - 1; k > diag[r]; --k) fn(k); }
     };
-    for (int r = 0; r < N; ++r)
-        for_deps(r, [&](int k) {
-            ++nblk[r];
-            if (tile[colidx[k]] != tile[r]) { if (!same_cluster(owner[colidx[k]], owner[r])) ++next[r]; ++npush[colidx[k]]; }
-        });
+    const int nchunk = std::max(1, std::min(256, N / 4096));
+    parallel_for(nchunk, [&](int ch) {          // (the push counts of other rows are the only shared writes)
+        const int r0 = (int)((long long)N * ch / nchunk), r1 = (int)((long long)N * (ch + 1) / nchunk);
+        for (int r = r0; r < r1; ++r)
+            for_deps(r, [&](int k) {
+                ++nblk[r];
+                if (tile[colidx[k]] != tile[r]) {
+                    if (!same_cluster(owner[colidx[k]], owner[r])) ++next[r];
+                    __atomic_fetch_add(&npush[colidx[k]], 1, __ATOMIC_RELAXED);
+                }
+            });
+    });
     auto tail_of = [&](int r) { return std::max(0, nblk[r] - kFastBlocks); };
     auto pushx_of = [&](int r) { return std::max(0, npush[r] - 2); };
     // steps: split CTA row lists at level changes and at the record limits
@@ -412,11 +460,14 @@ void build_pipe_program(int N, const int* rowptr, const int* colidx, const std::
     }
     // own results older than the window must also live in HBM (natural order)
     std::vector<unsigned char> write_global(N, 0);
-    for (int r = 0; r < N; ++r)
-        for_deps(r, [&](int k) {
-            const int j = colidx[k];
-            if (tile[j] == tile[r] && qlocal[j] + kWindowRows < step_end_q[r]) write_global[j] = 1;
-        });
+    parallel_for(nchunk, [&](int ch) {          // (concurrent writers of an entry all store 1)
+        const int r0 = (int)((long long)N * ch / nchunk), r1 = (int)((long long)N * (ch + 1) / nchunk);
+        for (int r = r0; r < r1; ++r)
+            for_deps(r, [&](int k) {
+                const int j = colidx[k];
+                if (tile[j] == tile[r] && qlocal[j] + kWindowRows < step_end_q[r]) write_global[j] = 1;
+            });
+    });
     tick__("positions + write_global");
     // record sizes
     size_t total_bytes = 0, total_ibytes = 0;
@@ -441,13 +492,23 @@ void build_pipe_program(int N, const int* rowptr, const int* colidx, const std::
     if (total_bytes / 16 >= (1ull << 32) || total_bytes / 8 >= (1ull << 32) || total_ibytes / 16 >= (1ull << 32)) return;
     pg.total_bytes = total_bytes + 16;
     pg.ibuf.assign(total_ibytes + 16, 0);
-    pg.val_src.reserve((size_t)rowptr[N] / 2 + N); pg.val_dst8.reserve((size_t)rowptr[N] / 2 + N); pg.val_stride.reserve((size_t)rowptr[N] / 2 + N);
-    bool any_slow = false, any_global = false;
-    tick__("sizes + buffer");
-    // emit
+    // where each CTA's (source block, destination) pairs go: known from the block counts
+    std::vector<size_t> val_off((size_t)P + 1, 0);
     for (int c = 0; c < P; ++c) {
+        size_t cnt = 0;
+        if (pg.cta_step_ptr[c + 1] > pg.cta_step_ptr[c])
+            for (int q = steps[pg.cta_step_ptr[c]].q0; q < steps[pg.cta_step_ptr[c + 1] - 1].q1; ++q) cnt += (size_t)nblk[order[q]] + (upper ? 1 : 0);
+        val_off[c + 1] = val_off[c] + cnt;
+    }
+    pg.val_src.resize(val_off[P]); pg.val_dst8.resize(val_off[P]); pg.val_stride.resize(val_off[P]);
+    std::atomic<bool> any_slow{false}, any_global{false};
+    tick__("sizes + buffer");
+    // emit (CTAs side by side: every CTA writes its own records and its own range of the value lists)
+    parallel_for(P, [&](int c) {
         long long e = 0;
         int cx = 0;
+        size_t vo = val_off[c];
+        bool cta_slow = false, cta_global = false;
         for (int sidx = pg.cta_step_ptr[c]; sidx < pg.cta_step_ptr[c + 1]; ++sidx) {
             const size_t rec_off = (size_t)pg.step_off16[sidx] * 16;
             unsigned char* irec = pg.ibuf.data() + (size_t)pg.step_ioff16[sidx] * 16;     // header | integer region
@@ -478,14 +539,16 @@ void build_pipe_program(int N, const int* rowptr, const int* colidx, const std::
                     else code = kDepGlobalBit | j;
                     if (kb < kFastBlocks) {
                         ri[1 + kb] = code;
-                        pg.val_src.push_back(k);
-                        pg.val_dst8.push_back((unsigned)((rec_off + L.cf) / 8 + (size_t)(3 * rr) * 9 + kb * 3));
-                        pg.val_stride.push_back(9);
+                        pg.val_src[vo] = k;
+                        pg.val_dst8[vo] = (unsigned)((rec_off + L.cf) / 8 + (size_t)(3 * rr) * 9 + kb * 3);
+                        pg.val_stride[vo] = 9;
+                        ++vo;
                     } else {
                         tail_dep[nt] = code;
-                        pg.val_src.push_back(k);
-                        pg.val_dst8.push_back((unsigned)((rec_off + L.tail_vals) / 8 + (size_t)nt * 9));
-                        pg.val_stride.push_back(3);
+                        pg.val_src[vo] = k;
+                        pg.val_dst8[vo] = (unsigned)((rec_off + L.tail_vals) / 8 + (size_t)nt * 9);
+                        pg.val_stride[vo] = 3;
+                        ++vo;
                         ++nt;
                     }
                     ++kb;
@@ -499,23 +562,26 @@ void build_pipe_program(int N, const int* rowptr, const int* colidx, const std::
                 }
                 if (has_lists) { tail_end[rr] = nt; xpush_end[rr] = npx; }
                 const bool slow = kb > kFastBlocks || np > 2;
-                any_slow |= slow; any_global |= write_global[r] != 0;
+                cta_slow |= slow; cta_global |= write_global[r] != 0;
                 ri[0] = r | (write_global[r] ? kRowWriteGlobal : 0) | (slow ? kRowSlow : 0);
                 ri[4] = (lower && upos_of_row) ? (*upos_of_row)[r] : 0;
                 if (ri4_index) (*ri4_index)[r] = (unsigned)((ri + 4) - (int*)pg.ibuf.data());
                 if (upper) {
-                    pg.val_src.push_back(diag[r]);
-                    pg.val_dst8.push_back((unsigned)((rec_off + L.dinv) / 8 + (size_t)(3 * rr) * 3));
-                    pg.val_stride.push_back(3);
+                    pg.val_src[vo] = diag[r];
+                    pg.val_dst8[vo] = (unsigned)((rec_off + L.dinv) / 8 + (size_t)(3 * rr) * 3);
+                    pg.val_stride[vo] = 3;
+                    ++vo;
                 }
             }
             hdr[0] = n; hdr[1] = steps[sidx].q0 - cta_q0; hdr[2] = (int)e; hdr[3] = (int)(e - e_before);
             hdr[4] = nt; hdr[5] = (int)(L.lists / 8); hdr[6] = (int)(L.tail_vals / 8);
             hdr[7] = has_lists ? 1 : 0;
         }
-    }
+        if (cta_slow) any_slow = true;
+        if (cta_global) any_global = true;
+    });
     tick__("emit");
-    pg.lean = !any_slow && !any_global && pg.max_step_rows <= kLeanStepRows;
+    pg.lean = !any_slow.load() && !any_global.load() && pg.max_step_rows <= kLeanStepRows;
     pg.valid = true;
 }
 
@@ -539,7 +605,7 @@ void build_factor_pipe_program(int N, const int* rowptr, const int* colidx, cons
             std::vector<unsigned long long> key(N);
             for (int r = 0; r < N; ++r)
                 key[r] = ((((unsigned long long)owner[r] << bt | (unsigned long long)tile[r]) << bl | (unsigned long long)level[r]) << br) | (unsigned long long)r;
-            std::sort(key.begin(), key.end());
+            sort_keys_by_owner(key, owner, max_owner);
             const unsigned long long mask = (1ULL << br) - 1;
             for (int q = 0; q < N; ++q) order[q] = (int)(key[q] & mask);
         } else {
@@ -553,17 +619,26 @@ void build_factor_pipe_program(int N, const int* rowptr, const int* colidx, cons
     }
     // every row simple?  slot of A_ji for every lower block (i,j), -1 when absent
     std::vector<int> ji_slot(rowptr[N], -1), next(N, 0), npush(N, 0);
-    for (int r = 0; r < N; ++r) {
-        if (diag[r] - rowptr[r] > kFastBlocks) return;
-        for (int k = rowptr[r]; k < diag[r]; ++k) {
-            const int j = colidx[k];
-            for (int kk = diag[j] + 1; kk < rowptr[j + 1]; ++kk) {
-                const int c2 = colidx[kk];
-                if (c2 == r) { ji_slot[k] = kk; continue; }
-                if (std::binary_search(colidx + rowptr[r], colidx + rowptr[r + 1], c2)) return;   // fill off the diagonal
+    {
+        // (row chunks side by side; the push counts of other rows are the only shared writes)
+        std::atomic<bool> not_simple{false};
+        const int nchunk = std::max(1, std::min(256, N / 4096));
+        parallel_for(nchunk, [&](int ch) {
+            const int r0 = (int)((long long)N * ch / nchunk), r1 = (int)((long long)N * (ch + 1) / nchunk);
+            for (int r = r0; r < r1 && !not_simple.load(std::memory_order_relaxed); ++r) {
+                if (diag[r] - rowptr[r] > kFastBlocks) { not_simple = true; return; }
+                for (int k = rowptr[r]; k < diag[r]; ++k) {
+                    const int j = colidx[k];
+                    for (int kk = diag[j] + 1; kk < rowptr[j + 1]; ++kk) {
+                        const int c2 = colidx[kk];
+                        if (c2 == r) { ji_slot[k] = kk; continue; }
+                        if (std::binary_search(colidx + rowptr[r], colidx + rowptr[r + 1], c2)) { not_simple = true; return; }   // fill off the diagonal
+                    }
+                    if (tile[j] != tile[r]) { ++next[r]; __atomic_fetch_add(&npush[j], 1, __ATOMIC_RELAXED); }
+                }
             }
-            if (tile[j] != tile[r]) { ++next[r]; ++npush[j]; }
-        }
+        });
+        if (not_simple) return;
     }
     for (int r = 0; r < N; ++r) if (npush[r] > 2) return;
     // steps = levels of the CTA's tile
@@ -655,10 +730,23 @@ void build_factor_pipe_program(int N, const int* rowptr, const int* colidx, cons
         }
         pg.ibuf.assign(total_ibytes + 16, 0);
     }
-    pg.val_src.reserve((size_t)rowptr[N]); pg.val_dst8.reserve((size_t)rowptr[N]);
+    // where each CTA's (source block, destination) pairs go
+    std::vector<size_t> val_off((size_t)P + 1, 0);
     for (int c = 0; c < P; ++c) {
+        size_t cnt = 0;
+        if (pg.cta_step_ptr[c + 1] > pg.cta_step_ptr[c])
+            for (int q = steps[pg.cta_step_ptr[c]].q0; q < steps[pg.cta_step_ptr[c + 1] - 1].q1; ++q) {
+                const int r = order[q];
+                cnt += 1 + (size_t)(diag[r] - rowptr[r]);
+                for (int k = rowptr[r]; k < diag[r]; ++k) cnt += ji_slot[k] >= 0 ? 1 : 0;
+            }
+        val_off[c + 1] = val_off[c] + cnt;
+    }
+    pg.val_src.resize(val_off[P]); pg.val_dst8.resize(val_off[P]);
+    parallel_for(P, [&](int c) {
         long long e = 0;
-        if (pg.cta_step_ptr[c] == pg.cta_step_ptr[c + 1]) continue;
+        size_t vo = val_off[c];
+        if (pg.cta_step_ptr[c] == pg.cta_step_ptr[c + 1]) return;
         const int cta_q0 = steps[pg.cta_step_ptr[c]].q0;
         for (int sidx = pg.cta_step_ptr[c]; sidx < pg.cta_step_ptr[c + 1]; ++sidx) {
             const size_t rec_off = (size_t)pg.step_off16[sidx] * 16;
@@ -676,17 +764,17 @@ void build_factor_pipe_program(int N, const int* rowptr, const int* colidx, cons
                 ri[0] = r; ri[1] = ri[2] = ri[3] = 0; ri[4] = 0; ri[5] = ri[6] = -1;
                 ri[7] = (steps[sidx].q0 - cta_q0 + rr) % kFWindow;
                 ri[8] = ri[9] = ri[10] = -1; ri[11] = diag[r];
-                pg.val_src.push_back(diag[r]); pg.val_dst8.push_back((unsigned)v8);
+                pg.val_src[vo] = diag[r]; pg.val_dst8[vo] = (unsigned)v8; ++vo;
                 int kb = 0;
                 for (int k = rowptr[r]; k < diag[r]; ++k, ++kb) {
                     const int j = colidx[k];
                     ri[1 + kb] = tile[j] != tile[r] ? kFWindow + (int)((e++) % kFRing) : qlocal[j] % kFWindow;
                     ri[4] |= 1 << kb;
                     ri[8 + kb] = k;
-                    pg.val_src.push_back(k); pg.val_dst8.push_back((unsigned)(v8 + 9 + kb * 18));
+                    pg.val_src[vo] = k; pg.val_dst8[vo] = (unsigned)(v8 + 9 + kb * 18); ++vo;
                     if (ji_slot[k] >= 0) {
                         ri[4] |= 1 << (4 + kb);
-                        pg.val_src.push_back(ji_slot[k]); pg.val_dst8.push_back((unsigned)(v8 + 18 + kb * 18));
+                        pg.val_src[vo] = ji_slot[k]; pg.val_dst8[vo] = (unsigned)(v8 + 18 + kb * 18); ++vo;
                     }
                 }
                 int np = 0;
@@ -695,7 +783,7 @@ void build_factor_pipe_program(int N, const int* rowptr, const int* colidx, cons
             hdr[0] = n; hdr[1] = steps[sidx].q0 - cta_q0; hdr[2] = (int)e; hdr[3] = (int)(e - e_before);
             hdr[4] = sidx > pg.cta_step_ptr[c] ? steps[sidx - 1].q1 - steps[sidx - 1].q0 : 0;      // rows of the previous step
         }
-    }
+    });
     pg.valid = true;
 }
 
@@ -1210,6 +1298,19 @@ void union_pattern_from_csc(int N, const CscView* blocks, int nblocks,
 // Debug entry (not part of the public ABI; used by the CPU test-suite to validate the host
 // analysis without a GPU): runs both pipelined sweep programs through the sequential
 // interpreter on factors given in BCRS layout.  Returns 0, or a negative code.
+// Debug (host only, no GPU): wall time of analyse_pattern in ms, with the cluster shape of a B200
+// (tools/analysis_time.py; OPMGPU_DEBUG=1 OPMGPU_DEBUG2=1 print the phases).
+extern "C" double opmgpu_debug_analyse_only(int N, const int* rowptr, const int* colidx, int P)
+{
+    using namespace opmgpu;
+    PatternAnalysis an;
+    ClusterCaps caps;
+    caps.max_ctas[0] = P; caps.max_ctas[1] = P; caps.max_ctas[2] = P / 4 * 4 - 16; caps.max_ctas[3] = P / 8 * 8 - 24;      // 148 / 132 / 120 at P = 148
+    const auto t0 = std::chrono::steady_clock::now();
+    analyse_pattern(N, rowptr, colidx, P, an, false, &caps);
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+
 extern "C" int opmgpu_debug_host_program_apply(int N, const int* rowptr, const int* colidx,
                                                const double* lu, int P, double w,
                                                const double* d, double* v, int* info /*[8]*/)
