@@ -1,5 +1,5 @@
 """Small driver for profiling: factor once, then a few ILU0 applies and SpMVs.
-Usage: python tools/apply_only.py NX NY NZ [napply]"""
+Usage: python tools/apply_only.py NX NY NZ [napply] [f32]"""
 import os
 import sys
 
@@ -11,8 +11,10 @@ from opm_simulators_legacy_b200.solver import GpuLinearSolver  # noqa: E402
 
 nx, ny, nz = (int(a) for a in sys.argv[1:4])
 napply = int(sys.argv[4]) if len(sys.argv) > 4 else 4
+single = len(sys.argv) > 5 and sys.argv[5] == "f32"
 s = synth_blackoil_jacobian(nx, ny, nz, perm="lognormal")
 g = GpuLinearSolver(0)
+g.set_precision(single)
 g.set_pattern(s.rowptr.numpy(), s.colidx.numpy())
 vals = s.vals.cuda(); rhs = s.rhs.cuda(); y = torch.zeros_like(rhs)
 g.set_values_dev(vals)
