@@ -207,3 +207,92 @@ def test_f32_cuda_path_reproduces_golden_vectors(f32_solver, path):
     x, res = f32_solver.solve_bcrs(v, b)
     assert res["iterations"] == int(g["iterations"]) and res["half_steps"] == int(g["half_steps"])
     assert np.abs(x - g["x"]).max() <= 1e-3 * np.abs(g["x"]).max()
+
+
+# ---- error contract and robustness of the float instance ------------------------------------------
+def test_f32_zero_rhs_and_error_contract(f32_solver, oracle):
+    from opm_simulators_legacy_b200.solver import LinearSolverProblem, NumericalIssue
+    s = synth_blackoil_jacobian(8, 8, 4, perm="lognormal")
+    rp, ci, v, b = _np(s)
+    f32_solver.set_pattern(rp, ci)
+    x, res = f32_solver.solve_bcrs(v, np.zeros_like(b))
+    assert res["iterations"] == 0 and res["converged"] == 1 and not x.any()
+    # not converged -> LinearSolverProblem, iterations still reported (ISTLSolver.hpp:358-368);
+    # the float oracle runs into maxiter at the same count
+    with pytest.raises(LinearSolverProblem):
+        f32_solver.solve_bcrs(v, b, linear_solver_reduction=1e-14, linear_solver_maxiter=2)
+    _, ref = oracle.f32.solve_bcrs(rp, ci, v, b, reduction=1e-14, maxiter=2)
+    assert f32_solver.last["iterations"] == ref["iterations"] == 2 and f32_solver.last["converged"] == 0
+    # singular pivot block -> NumericalIssue naming the row the float oracle names
+    v2 = v.copy()
+    row = 37
+    d = np.searchsorted(ci[rp[row]:rp[row + 1]], row) + rp[row]
+    v2[d] = 0.0
+    for k in range(rp[row], rp[row + 1]):
+        if ci[k] < row:
+            v2[k] = 0.0
+    _, bad = oracle.f32.ilu0_factor(rp, ci, v2)
+    with pytest.raises(NumericalIssue):
+        f32_solver.solve_bcrs(v2, b)
+    assert f32_solver.last["bad_row"] == bad == row
+
+
+def test_f32_nan_and_inf_end_the_solve(f32_solver):
+    """NaN / Inf in values or right-hand side: "not converged" or a singular-block error, promptly,
+    no watchdog trip (the float containers' empty marker is never a result), handle usable after."""
+    import time
+    from opm_simulators_legacy_b200.solver import LinearSolverProblem, NumericalIssue
+    s = synth_blackoil_jacobian(24, 20, 12, perm="lognormal")
+    rp, ci, v, b = _np(s)
+    f32_solver.set_pattern(rp, ci)
+    x_ok, res_ok = f32_solver.solve_bcrs(v, b)
+    for what in ("rhs_nan", "rhs_inf", "val_nan_offdiag", "val_nan_diag"):
+        v2, b2 = v.copy(), b.copy()
+        if what == "rhs_nan":
+            b2[777, 1] = np.nan
+        elif what == "rhs_inf":
+            b2[777, 1] = np.inf
+        elif what == "val_nan_offdiag":
+            v2[rp[900] + 1, 5] = np.nan
+        else:
+            d = np.searchsorted(ci[rp[900]:rp[901]], 900) + rp[900]
+            v2[d, 0] = np.nan
+        t0 = time.time()
+        with pytest.raises((LinearSolverProblem, NumericalIssue)):
+            f32_solver.solve_bcrs(v2, b2, linear_solver_maxiter=20)
+        assert time.time() - t0 < 5.0, what
+        assert "watchdog" not in f32_solver.error(), (what, f32_solver.error())
+        x, res = f32_solver.solve_bcrs(v, b)
+        assert res["iterations"] == res_ok["iterations"] and np.array_equal(x, x_ok), what
+
+
+def test_f32_full_size_properties():
+    """C3 (1M cells) in the float instance: size-independent properties -- the solve converges at the
+    reference's tolerance, the true residual (in double) is reduced accordingly, results are
+    deterministic run to run, the float SpMV (128-row tiles) agrees with the double one to float accuracy."""
+    import torch
+    s = synth_blackoil_jacobian(100, 100, 100, perm="lognormal")
+    g = GpuLinearSolver(0)
+    try:
+        g.set_pattern(s.rowptr.numpy(), s.colidx.numpy())
+        vals = s.vals.cuda(); rhs = s.rhs.cuda()
+        y64 = torch.zeros_like(rhs); y32 = torch.zeros_like(rhs)
+        g.set_values_dev(vals)
+        g.spmv_dev(rhs, y64)
+        g.set_precision(True)
+        g.set_values_dev(vals)
+        g.spmv_dev(rhs, y32)
+        torch.cuda.synchronize()
+        assert float((y32 - y64).abs().max()) <= 1e-5 * float(y64.abs().max())
+        x1 = torch.zeros_like(rhs); x2 = torch.zeros_like(rhs)
+        r1 = g.solve_bcrs_dev(None, rhs, x1)
+        r2 = g.solve_bcrs_dev(None, rhs, x2)
+        assert r1["converged"] == 1 and r1["iterations"] == r2["iterations"] and torch.equal(x1, x2)
+        g.set_precision(False)
+        g.set_values_dev(vals)
+        ax = torch.zeros_like(rhs)
+        g.spmv_dev(x1, ax)
+        torch.cuda.synchronize()
+        assert float((rhs - ax).norm() / rhs.norm()) <= 1e-2 * 1.01
+    finally:
+        g.close()
