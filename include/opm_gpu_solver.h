@@ -177,6 +177,28 @@ int  opmgpu_solve_from_csc_blocks(opmgpu_handle h, int N, const opmgpu_csc block
                                   double* dx_varmajor, const opmgpu_params* params,
                                   opmgpu_result* result);
 
+/* ---- block sizes other than 3 ----------------------------------------------------------------
+ * The reference's dispatcher instantiates Impl<np,Scalar> for np = 2..6
+ * (NewtonIterationBlackoilInterleaved.cpp:467-487, .hpp:73; np = 2: two-phase decks).  np = 3 runs
+ * the pipelined kernels; np = 2 runs level-scheduled kernels with the same arithmetic (one launch
+ * per dependency level: correct and bit-comparable, not tuned); np = 4..6 answer
+ * OPMGPU_BAD_ARGUMENT.  opmgpu_set_block_size prepares the NEXT pattern for that block size (call it
+ * before opmgpu_set_pattern_bcrs; opmgpu_solve_from_csc_blocks_np does both itself).  All arrays are
+ * the np-sized analogues of the np = 3 entry points: vals[nnzb*np*np], rhs/x[N*np] cell-major,
+ * blocks[np*np] with blocks[p1*np+p2] = d(eq p1)/d(var p2), rhs_eqmajor / dx_varmajor[np*N]. */
+int  opmgpu_set_block_size(opmgpu_handle h, int np);
+int  opmgpu_solve_bcrs_np(opmgpu_handle h, int np, const double* vals, const double* rhs, double* x,
+                          const opmgpu_params* params, opmgpu_result* result);
+int  opmgpu_solve_from_csc_blocks_np(opmgpu_handle h, int N, int np, const opmgpu_csc* blocks,
+                                     const double* matbalscale, const double* rhs_eqmajor,
+                                     double* dx_varmajor, const opmgpu_params* params,
+                                     opmgpu_result* result);
+/* kernel-level (parity tests): y = A x; ILU0 factors (lu_out, may be NULL) and v = w U^-1 L^-1 d
+ * (d / v may be NULL) of the given values */
+int  opmgpu_spmv_np(opmgpu_handle h, int np, const double* vals, const double* x, double* y);
+int  opmgpu_ilu0_np(opmgpu_handle h, int np, const double* vals, double* lu_out, double w,
+                    const double* d, double* v, int* bad_row);
+
 /* ---- kernel-level entry points (parity tests, micro-benchmarks) -------------------------- */
 
 /* The operator alone: uploads the pattern for opmgpu_spmv* without the ILU0 analysis (the SpMV

@@ -25,6 +25,7 @@ EXPORTS = [
     "opmgpu_dot", "opmgpu_num_levels", "opmgpu_launch_count", "opmgpu_residual_history",
     "opmgpu_set_profiling", "opmgpu_get_profile", "opmgpu_set_precision", "opmgpu_get_precision",
     "opmgpu_set_pattern_bcrs_operator_only",
+    "opmgpu_set_block_size", "opmgpu_solve_bcrs_np", "opmgpu_solve_from_csc_blocks_np", "opmgpu_spmv_np", "opmgpu_ilu0_np",
 ]
 
 OK, NOT_CONVERGED, SINGULAR_BLOCK, BREAKDOWN, BAD_PATTERN, BAD_ARGUMENT = 0, 1, 2, 3, 4, 5
@@ -87,6 +88,11 @@ def load():
         "opmgpu_get_precision": (C.c_int, [H]),
         "opmgpu_set_pattern_bcrs": (C.c_int, [H, C.c_int, C.c_int, ip, ip]),
         "opmgpu_set_pattern_bcrs_operator_only": (C.c_int, [H, C.c_int, C.c_int, ip, ip]),
+        "opmgpu_set_block_size": (C.c_int, [H, C.c_int]),
+        "opmgpu_solve_bcrs_np": (C.c_int, [H, C.c_int, dp, dp, dp, PP, RP]),
+        "opmgpu_solve_from_csc_blocks_np": (C.c_int, [H, C.c_int, C.c_int, C.POINTER(Csc), dp, dp, dp, PP, RP]),
+        "opmgpu_spmv_np": (C.c_int, [H, C.c_int, dp, dp, dp]),
+        "opmgpu_ilu0_np": (C.c_int, [H, C.c_int, dp, dp, C.c_double, dp, dp, ip]),
         "opmgpu_set_pattern_bcrs_distributed": (C.c_int, [H, C.c_int, C.c_int, ip, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
         "opmgpu_solve_bcrs3": (C.c_int, [H, dp, dp, dp, PP, RP]),
         "opmgpu_solve_bcrs3_dev": (C.c_int, [H, vp, vp, vp, PP, RP]),

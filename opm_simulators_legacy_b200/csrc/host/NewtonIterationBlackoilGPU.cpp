@@ -179,7 +179,8 @@ NewtonIterationBlackoilGPU::SolutionVector
 NewtonIterationBlackoilGPU::computeNewtonIncrement(const LinearisedBlackoilResidual& residual) const
 {
     const int np = (int)residual.material_balance_eq.size();
-    if (np != 3) throw std::logic_error("NewtonIterationBlackoilGPU: only np == 3 is built");
+    // the reference's switch instantiates Impl<np,Scalar> for np = 2..6 (...Interleaved.cpp:467-487)
+    if (np != 2 && np != 3) throw std::logic_error("NewtonIterationBlackoilGPU: np == 2 and np == 3 are built");
     std::vector<ADB> eqs(residual.material_balance_eq.begin(), residual.material_balance_eq.end());
     const bool hasWells = residual.well_flux_eq.size() > 0;
     std::vector<ADB> elim_eqs;
@@ -193,21 +194,21 @@ NewtonIterationBlackoilGPU::computeNewtonIncrement(const LinearisedBlackoilResid
     }
     const int N = eqs[0].size();
     opmgpu_csc blocks[9];
-    for (int p1 = 0; p1 < 3; ++p1)
-        for (int p2 = 0; p2 < 3; ++p2) {
+    for (int p1 = 0; p1 < np; ++p1)
+        for (int p2 = 0; p2 < np; ++p2) {
             const SparseCSC& s = eqs[p1].jac[p2];
-            blocks[p1 * 3 + p2] = opmgpu_csc{s.colptr.data(), s.rowidx.data(), s.val.data()};
+            blocks[p1 * np + p2] = opmgpu_csc{s.colptr.data(), s.rowidx.data(), s.val.data()};
         }
     std::vector<double> b;
-    b.reserve((size_t)3 * N);
-    for (int p = 0; p < 3; ++p) b.insert(b.end(), eqs[p].val.begin(), eqs[p].val.end());
-    SolutionVector dx((size_t)3 * N, 0.0);
-    const double scale[3] = {residual.matbalscale[0], residual.matbalscale[1], residual.matbalscale[2]};
+    b.reserve((size_t)np * N);
+    for (int p = 0; p < np; ++p) b.insert(b.end(), eqs[p].val.begin(), eqs[p].val.end());
+    SolutionVector dx((size_t)np * N, 0.0);
+    const double scale[3] = {residual.matbalscale[0], residual.matbalscale[1], np > 2 ? residual.matbalscale[2] : 1.0};
     // the reference's dispatcher (...Interleaved.cpp:467-487): the float instance when the residual asks
     // for it (restarted GMRES exists for the double instance only; that combination stays in double)
     if (opmgpu_set_precision(handle_, residual.singlePrecision && !parameters_.newton_use_gmres) != OPMGPU_OK)
         throw std::runtime_error(opmgpu_last_error(handle_));
-    const int rc = opmgpu_solve_from_csc_blocks(handle_, N, blocks, scale, b.data(), dx.data(), &parameters_, &last_);
+    const int rc = opmgpu_solve_from_csc_blocks_np(handle_, N, np, blocks, scale, b.data(), dx.data(), &parameters_, &last_);
     iterations_ = last_.iterations;             // before any throw
     switch (rc) {
     case OPMGPU_OK: break;

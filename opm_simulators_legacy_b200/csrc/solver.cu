@@ -13,6 +13,7 @@
 #include "sweep_col.cuh"
 #include "spmv_tma.cuh"
 #include "gmres.cuh"
+#include "generic_np.cuh"
 #include "multi.hpp"
 
 #include <dlfcn.h>
@@ -226,6 +227,15 @@ struct opmgpu_solver {
     // arrays), factors / sweep records / scalar block keep their 8-byte containers.  The C ABI
     // exchanges doubles either way; d_stage holds them on their way in and out.
     bool f32 = false;
+    // Block size.  np_req (opmgpu_set_block_size) is what the NEXT pattern is prepared for: np = 2 also
+    // gets the level sets of the upper triangle (generic_np.cuh runs one launch per level); np is the
+    // block size of the call in flight (3 except inside the *_np entry points).
+    int np_req = 3, np = 3;
+    std::vector<int> lvlU_ptr;
+    DevArr<int> d_lvlU_rows;
+    DevArr<long long> d_map_np;
+    std::vector<std::vector<int>> npcsc_colptr, npcsc_rowidx;      // CSC front end cache of the np path
+    std::vector<long long> npcsc_base;
     bool operator_only = false;    // opmgpu_set_pattern_bcrs_operator_only: no ILU0 programs, SpMV entry points only
     DevArr<double> d_vals_own, d_lu, d_stage;
     DevArr<float> d_vals32;
@@ -680,6 +690,24 @@ int set_pattern(opmgpu_handle h, int N, int nnzb, const int* rowptr, const int* 
         }
         h->progU.release();
     }
+    h->lvlU_ptr.clear();
+    if (h->np_req != 3) {
+        // level sets of the upper triangle (rows from the last to the first)
+        std::vector<int> lev(N, 0);
+        int nlev = 0;
+        for (int i = N - 1; i >= 0; --i) {
+            int l = 0;
+            for (int k = rowptr[i + 1] - 1; k >= rowptr[i] && colidx[k] > i; --k) l = std::max(l, lev[colidx[k]] + 1);
+            lev[i] = l; nlev = std::max(nlev, l + 1);
+        }
+        h->lvlU_ptr.assign((size_t)nlev + 1, 0);
+        for (int i = 0; i < N; ++i) ++h->lvlU_ptr[(size_t)lev[i] + 1];
+        for (int l = 0; l < nlev; ++l) h->lvlU_ptr[l + 1] += h->lvlU_ptr[l];
+        std::vector<int> rows(N), fill(h->lvlU_ptr.begin(), h->lvlU_ptr.end() - 1);
+        for (int i = 0; i < N; ++i) rows[fill[lev[i]]++] = i;
+        if ((rc = upload(h, h->d_lvlU_rows, rows))) return rc;
+        CK(cudaStreamSynchronize(h->stream));
+    }
     CK(h->d_lu.ensure((size_t)nnzb * 9));
     if ((rc = ensure_vectors(h))) return rc;
     CK(h->d_flags.ensure(N));
@@ -946,10 +974,31 @@ int spmv_overlapped(opmgpu_handle h, int mode, T* x, T* y, const T* w1)
     return 0;
 }
 
+// np = 2 (generic_np.cuh): y = A x, then the dot products as separate passes
+template <class T>
+int np_spmv_with_dots(opmgpu_handle h, int mode, const T* x, T* y, const T* w1)
+{
+    const size_t n = (size_t)h->N * h->np;
+    np_spmv_kernel<2, T><<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->N, h->d_rowptr.p, h->d_colidx.p,
+                                                                            static_cast<const T*>(h->d_vals), x, y);
+    h->launches++;
+    if (mode == 1) {
+        dot_to_slot_kernel<T><<<kVecBlocks, 256, 0, h->stream>>>(n, w1, (const T*)y, h->d_S.p, S_H, h->ws());
+        h->launches++;
+    } else if (mode == 2) {
+        dot_to_slot_kernel<T><<<kVecBlocks, 256, 0, h->stream>>>(n, (const T*)y, w1, h->d_S.p, S_TR, h->ws());
+        dot_to_slot_kernel<T><<<kVecBlocks, 256, 0, h->stream>>>(n, (const T*)y, (const T*)y, h->d_S.p, S_TT, h->ws());
+        h->launches += 2;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
 template <class T>
 int spmv_with_dots(opmgpu_handle h, int mode, T* x, T* y, const T* w1)
 {
     int rc;
+    if (h->np != 3) return np_spmv_with_dots<T>(h, mode, x, y, w1);
     if (h->world > 1 && h->overlap_halo && h->halo_stream && h->spmv_tma && h->n_bnd_rows > 0 &&
         (reinterpret_cast<uintptr_t>(h->d_vals) & 15) == 0) {
         rc = spmv_overlapped<T>(h, mode, x, y, w1);
@@ -987,9 +1036,43 @@ int sweep_watchdog(opmgpu_handle h);
 
 // T: scalar type of the instance (matrix values are stored as T, the arithmetic is T's; the factor
 // array, the records and the pivots are 8-byte containers)
+// np = 2: Dune::bilu0_decomposition level by level on a T copy of the values (generic_np.cuh)
+template <class T>
+int np_factor(opmgpu_handle h, int* bad_row)
+{
+    if (!h->have_values) return h->bad("no matrix values set");
+    if (h->lvlU_ptr.empty()) return h->bad("the pattern was not prepared for this block size: opmgpu_set_block_size before opmgpu_set_pattern_bcrs");
+    const size_t nv = (size_t)h->nnzb * h->np * h->np;
+    T* lu = reinterpret_cast<T*>(h->d_lu.p);
+    CK(cudaMemcpyAsync(lu, h->d_vals, nv * sizeof(T), cudaMemcpyDeviceToDevice, h->stream));
+    const int big = 0x7fffffff;
+    CK(cudaMemcpyAsync(h->d_bad.p, &big, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    const std::vector<int>& lp = h->an.lvl_ptr;
+    for (size_t l = 0; l + 1 < lp.size(); ++l) {
+        const int n = lp[l + 1] - lp[l];
+        if (n <= 0) continue;
+        np_factor_level_kernel<2, T><<<(n + 127) / 128, 128, 0, h->stream>>>(h->d_lvl_rows.p, lp[l], lp[l + 1], h->d_rowptr.p,
+                                                                              h->d_colidx.p, h->d_diag.p, lu, h->d_bad.p);
+        h->launches++;
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(&h->h_flags2[1], h->d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->h_flags2[1] != big) {
+        if (bad_row) *bad_row = h->h_flags2[1];
+        h->err = "singular diagonal block in ILU0 at block row " + std::to_string(h->h_flags2[1]);
+        h->have_factors = false;
+        return OPMGPU_SINGULAR_BLOCK;
+    }
+    if (bad_row) *bad_row = -1;
+    h->have_factors = true;
+    return OPMGPU_OK;
+}
+
 template <class T>
 int factor_t(opmgpu_handle h, int* bad_row)
 {
+    if (h->np != 3) return np_factor<T>(h, bad_row);
     if (!h->have_values) return h->bad("no matrix values set");
     if (h->operator_only) return h->bad("the pattern was set operator-only (no ILU0 analysis): opmgpu_set_pattern_bcrs first");
     if (h->f32 && h->use_col) return h->bad("the column-owned sweeps (OPMGPU_COL=1) exist for the double instance only");
@@ -1175,9 +1258,37 @@ int launch_sweep(opmgpu_handle h, bool upper, const PipeDevMem& d, void** args)
 
 // v = w U^-1 L^-1 d, all device pointers; asynchronous
 // d_in_program_order: the producer of d already wrote it into pipeL.rhs_perm (fused permutation)
+// np = 2: ParallelOverlappingILU0::apply level by level (generic_np.cuh)
+template <class T>
+int np_apply(opmgpu_handle h, double w, const T* d, T* v)
+{
+    const int scale = std::fabs(w - 1.0) > 1e-15 ? 1 : 0;
+    const T* lu = reinterpret_cast<const T*>(h->d_lu.p);
+    T* work = vec<T>(h->d_yL);
+    const std::vector<int>& lp = h->an.lvl_ptr;
+    for (size_t l = 0; l + 1 < lp.size(); ++l) {
+        const int n = lp[l + 1] - lp[l];
+        if (n <= 0) continue;
+        np_sweep_level_kernel<2, T, true><<<(n + 127) / 128, 128, 0, h->stream>>>(h->d_lvl_rows.p, lp[l], lp[l + 1], h->d_rowptr.p,
+            h->d_colidx.p, h->d_diag.p, lu, d, work, v, (T)w, scale);
+        h->launches++;
+    }
+    const std::vector<int>& up = h->lvlU_ptr;
+    for (size_t l = 0; l + 1 < up.size(); ++l) {
+        const int n = up[l + 1] - up[l];
+        if (n <= 0) continue;
+        np_sweep_level_kernel<2, T, false><<<(n + 127) / 128, 128, 0, h->stream>>>(h->d_lvlU_rows.p, up[l], up[l + 1], h->d_rowptr.p,
+            h->d_colidx.p, h->d_diag.p, lu, d, work, v, (T)w, scale);
+        h->launches++;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
 template <class T>
 int apply_precond(opmgpu_handle h, double w, const T* d, T* v, bool d_in_program_order = false)
 {
+    if (h->np != 3) return np_apply<T>(h, w, d, v);
     const int scale = std::fabs(w - 1.0) > 1e-15 ? 1 : 0;      // relaxation_ flag of the reference
     if (h->use_col && sizeof(T) == 4) return h->bad("the column-owned sweeps (OPMGPU_COL=1) exist for the double instance only");
     if (h->use_col) {
@@ -1364,7 +1475,7 @@ template <class T>
 int bicgstab(opmgpu_handle h, const opmgpu_params* prm, opmgpu_result* res)
 {
     const T EPSILON = sizeof(T) == 8 ? (T)1e-80 : T(0);      // (float)1e-80
-    const size_t n = (size_t)h->N * 3;
+    const size_t n = (size_t)h->N * h->np;
     const T red = (T)prm->linear_solver_reduction;
     const double w = prm->ilu_relaxation;
     const int maxit = prm->linear_solver_maxiter, half_limit = prm->max_half_steps;
@@ -1375,7 +1486,7 @@ int bicgstab(opmgpu_handle h, const opmgpu_params* prm, opmgpu_result* res)
     CK(cudaMemsetAsync(d_x, 0, n * sizeof(T), h->stream));
     CK(cudaMemcpyAsync(d_rt, d_r, n * sizeof(T), cudaMemcpyDeviceToDevice, h->stream));
     // the vector kernels write the next right-hand side of the lower sweep in program order
-    const int* lpos = h->use_pipe && h->fuse_permute ? (h->use_col ? h->col.pos_of_row.p : h->pipeL.pos_of_row.p) : nullptr;
+    const int* lpos = h->np == 3 && h->use_pipe && h->fuse_permute ? (h->use_col ? h->col.pos_of_row.p : h->pipeL.pos_of_row.p) : nullptr;
     double* lperm = h->use_pipe ? (h->use_col ? h->col.rhsL.p : h->pipeL.rhs_perm.p) : nullptr;
     HostBox hb = next_hostbox(h);
     bicg_init_kernel<T><<<kVecBlocks, 256, 0, h->stream>>>(n, d_r, h->d_S.p, h->ws(), hb);
@@ -1982,7 +2093,7 @@ int opmgpu_destroy(opmgpu_handle h)
     h->d_t.release(); h->d_y.release(); h->d_yL.release(); h->d_vU.release(); h->d_tmp.release(); h->d_tmp2.release();
     h->d_S.release(); h->d_partials.release(); h->d_ticket.release(); h->d_flags.release();
     h->d_rowptr_full.release(); h->d_colidx_full.release(); h->d_lu_src.release(); h->d_send_rows.release(); h->d_sendbuf.release();
-    h->d_bnd_rows.release(); h->d_row_skip.release();
+    h->d_bnd_rows.release(); h->d_row_skip.release(); h->d_lvlU_rows.release(); h->d_map_np.release();
     close_peer_halo(h); h->peer.flags_in.release(); h->peer.ticket.release(); h->peer.inbox.release(); h->peer.sflags.release();
     if (h->halo_stream) { cudaStreamDestroy(h->halo_stream); cudaEventDestroy(h->ev_x_ready); cudaEventDestroy(h->ev_halo_done); h->halo_stream = nullptr; }
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
@@ -2449,6 +2560,258 @@ int opmgpu_solve_from_csc_blocks(opmgpu_handle h, int N, const opmgpu_csc blocks
     return rc;
     }
     return h->bad("sparsity pattern changed during the call");
+}
+
+// ---- block sizes other than 3 (the reference's Impl<np,Scalar>, np = 2..6): np = 2 is built -------
+}  // extern "C"
+namespace {
+struct NpGuard {          // the block size of the call in flight; back to 3 on every way out
+    opmgpu_handle h;
+    NpGuard(opmgpu_handle h_, int np) : h(h_) { h->np = np; }
+    ~NpGuard() { h->np = 3; h->have_values = false; h->have_factors = false; h->d_vals = nullptr; }
+};
+int np_check(opmgpu_handle h, int np)
+{
+    if (np != 2) { h->err = "block size np = " + std::to_string(np) + " is not built (np = 2 and 3 are)"; return OPMGPU_BAD_ARGUMENT; }
+    if (h->multi || h->world > 1) return h->bad("np != 3 exists for plain single-GPU handles");
+    if (!h->have_pattern || h->operator_only) return h->bad("set the pattern first");
+    if (h->lvlU_ptr.empty()) return h->bad("the pattern was not prepared for this block size: opmgpu_set_block_size before opmgpu_set_pattern_bcrs");
+    return 0;
+}
+// host doubles -> the instance's values (T) on the device, through d_stage
+template <class T>
+int np_upload(opmgpu_handle h, const double* src, size_t n, T* dst)
+{
+    if (sizeof(T) == 8) { CK(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyHostToDevice, h->stream)); return 0; }
+    CK(h->d_stage.ensure(n));
+    CK(cudaMemcpyAsync(h->d_stage.p, src, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    return convert<double, T>(h, n, h->d_stage.p, dst);
+}
+template <class T>
+int np_download(opmgpu_handle h, const T* src, size_t n, double* dst)
+{
+    if (sizeof(T) == 8) { CK(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream)); }
+    else {
+        CK(h->d_stage.ensure(n));
+        if (int rc = convert<T, double>(h, n, src, h->d_stage.p)) return rc;
+        CK(cudaMemcpyAsync(dst, h->d_stage.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+// the values as the instance stores them: T array in d_vals_own (double) / d_vals32 (float)
+template <class T>
+T* np_vals_buffer(opmgpu_handle h, size_t nv)
+{
+    if (sizeof(T) == 8) { if (h->d_vals_own.ensure(nv) != cudaSuccess) return nullptr; return reinterpret_cast<T*>(h->d_vals_own.p); }
+    if (h->d_vals32.ensure(nv + 16) != cudaSuccess) return nullptr;
+    return reinterpret_cast<T*>(h->d_vals32.p);
+}
+template <class T>
+int np_solve_bcrs(opmgpu_handle h, int np, const double* vals, const double* rhs, double* x,
+                  const opmgpu_params* params, opmgpu_result* result)
+{
+    const size_t n = (size_t)h->N * np, nv = (size_t)h->nnzb * np * np;
+    T* dv = np_vals_buffer<T>(h, nv);
+    if (!dv) return h->fail(cudaErrorMemoryAllocation, "np values");
+    int rc = np_upload<T>(h, vals, nv, dv);
+    if (!rc) rc = np_upload<T>(h, rhs, n, vec<T>(h->d_r));
+    if (rc) return rc;
+    h->d_vals = dv;
+    h->have_values = true; h->have_factors = false;
+    rc = solve_resident(h, params, result);
+    if (rc == OPMGPU_OK || rc == OPMGPU_NOT_CONVERGED) { if (int rc2 = np_download<T>(h, vec<T>(h->d_x), n, x)) return rc2; }
+    return rc;
+}
+}  // namespace
+extern "C" {
+
+int opmgpu_set_block_size(opmgpu_handle h, int np)
+{
+    if (!h) return OPMGPU_BAD_ARGUMENT;
+    if (np != 2 && np != 3) { h->err = "block size np = " + std::to_string(np) + " is not built (np = 2 and 3 are)"; return OPMGPU_BAD_ARGUMENT; }
+    if (h->multi || h->world > 1) return np == 3 ? OPMGPU_OK : h->bad("np != 3 exists for plain single-GPU handles");
+    if (np != h->np_req) { h->np_req = np; h->have_pattern = false; h->have_values = false; h->have_factors = false; }
+    return OPMGPU_OK;
+}
+
+int opmgpu_solve_bcrs_np(opmgpu_handle h, int np, const double* vals, const double* rhs, double* x,
+                         const opmgpu_params* params, opmgpu_result* result)
+{
+    if (!h || !vals || !rhs || !x || !params || !result) return OPMGPU_BAD_ARGUMENT;
+    if (np == 3) return opmgpu_solve_bcrs3(h, vals, rhs, x, params, result);
+    if (int rc = np_check(h, np)) return rc;
+    if (params->newton_use_gmres) return h->bad("restarted GMRES exists for np = 3 only");
+    std::memset(result, 0, sizeof *result);
+    result->bad_row = -1;
+    CK(cudaSetDevice(h->device));
+    NpGuard guard(h, np);
+    return h->f32 ? np_solve_bcrs<float>(h, np, vals, rhs, x, params, result) : np_solve_bcrs<double>(h, np, vals, rhs, x, params, result);
+}
+
+// kernel-level entry points of the np path (parity tests): y = A x; factors and v = w U^-1 L^-1 d
+int opmgpu_spmv_np(opmgpu_handle h, int np, const double* vals, const double* x, double* y)
+{
+    if (!h || !vals || !x || !y) return OPMGPU_BAD_ARGUMENT;
+    if (int rc = np_check(h, np)) return rc;
+    CK(cudaSetDevice(h->device));
+    NpGuard guard(h, np);
+    const size_t n = (size_t)h->N * np, nv = (size_t)h->nnzb * np * np;
+    auto run = [&](auto tag) -> int {
+        using T = decltype(tag);
+        T* dv = np_vals_buffer<T>(h, nv);
+        if (!dv) return h->fail(cudaErrorMemoryAllocation, "np values");
+        int rc = np_upload<T>(h, vals, nv, dv);
+        if (!rc) rc = np_upload<T>(h, x, n, vec<T>(h->d_tmp));
+        if (rc) return rc;
+        h->d_vals = dv;
+        if ((rc = np_spmv_with_dots<T>(h, 0, vec<T>(h->d_tmp), vec<T>(h->d_tmp2), (const T*)nullptr))) return rc;
+        return np_download<T>(h, vec<T>(h->d_tmp2), n, y);
+    };
+    return h->f32 ? run(float()) : run(double());
+}
+
+int opmgpu_ilu0_np(opmgpu_handle h, int np, const double* vals, double* lu_out, double w, const double* d, double* v, int* bad_row)
+{
+    if (!h || !vals) return OPMGPU_BAD_ARGUMENT;
+    if (int rc = np_check(h, np)) return rc;
+    CK(cudaSetDevice(h->device));
+    NpGuard guard(h, np);
+    const size_t n = (size_t)h->N * np, nv = (size_t)h->nnzb * np * np;
+    auto run = [&](auto tag) -> int {
+        using T = decltype(tag);
+        T* dv = np_vals_buffer<T>(h, nv);
+        if (!dv) return h->fail(cudaErrorMemoryAllocation, "np values");
+        int rc = np_upload<T>(h, vals, nv, dv);
+        if (rc) return rc;
+        h->d_vals = dv; h->have_values = true;
+        if ((rc = np_factor<T>(h, bad_row))) return rc;
+        if (lu_out && (rc = np_download<T>(h, reinterpret_cast<const T*>(h->d_lu.p), nv, lu_out))) return rc;
+        if (d && v) {
+            if ((rc = np_upload<T>(h, d, n, vec<T>(h->d_tmp)))) return rc;
+            if ((rc = np_apply<T>(h, w, vec<T>(h->d_tmp), vec<T>(h->d_tmp2)))) return rc;
+            if ((rc = np_download<T>(h, vec<T>(h->d_tmp2), n, v))) return rc;
+        }
+        return OPMGPU_OK;
+    };
+    return h->f32 ? run(float()) : run(double());
+}
+
+int opmgpu_solve_from_csc_blocks_np(opmgpu_handle h, int N, int np, const opmgpu_csc* blocks,
+                                    const double* matbalscale, const double* rhs_eqmajor,
+                                    double* dx_varmajor, const opmgpu_params* params, opmgpu_result* result)
+{
+    if (!h || !blocks || !matbalscale || !rhs_eqmajor || !dx_varmajor || !params || !result || N < 1) return OPMGPU_BAD_ARGUMENT;
+    if (np == 3) return opmgpu_solve_from_csc_blocks(h, N, blocks, matbalscale, rhs_eqmajor, dx_varmajor, params, result);
+    if (np != 2) { h->err = "block size np = " + std::to_string(np) + " is not built (np = 2 and 3 are)"; return OPMGPU_BAD_ARGUMENT; }
+    if (h->multi || h->world > 1) return h->bad("np != 3 exists for plain single-GPU handles");
+    if (params->newton_use_gmres) return h->bad("restarted GMRES exists for np = 3 only");
+    std::memset(result, 0, sizeof *result);
+    result->bad_row = -1;
+    CK(cudaSetDevice(h->device));
+    const int bb = np * np;
+    const bool full = params->require_full_sparsity_pattern != 0;
+    // the pattern: compared with the cached one on the host (np = 2 systems are small next to C3)
+    bool same = h->have_pattern && h->np_req == np && h->N == N && (int)h->npcsc_colptr.size() == bb && !h->lvlU_ptr.empty() &&
+                h->csc_full_pattern == full;
+    for (int q = 0; q < bb && same; ++q) {
+        same = (int)h->npcsc_colptr[q].size() == N + 1 && std::memcmp(h->npcsc_colptr[q].data(), blocks[q].colptr, sizeof(int) * ((size_t)N + 1)) == 0 &&
+               h->npcsc_rowidx[q].size() == (size_t)blocks[q].colptr[N] &&
+               std::memcmp(h->npcsc_rowidx[q].data(), blocks[q].rowidx, sizeof(int) * h->npcsc_rowidx[q].size()) == 0;
+    }
+    if (!same) {
+        cudaEventRecord(h->ev[3], h->stream);
+        for (int q = 0; q < bb; ++q) {
+            const int* cp = blocks[q].colptr;
+            const int* ri = blocks[q].rowidx;
+            if (!cp || cp[0] != 0) return h->bad("CSC block: colptr[0] != 0");
+            for (int c = 0; c < N; ++c) {
+                if (cp[c + 1] < cp[c]) return h->bad("CSC block: colptr not monotone");
+                for (int k = cp[c]; k < cp[c + 1]; ++k) {
+                    if (ri[k] < 0 || ri[k] >= N) return h->bad("CSC block: row index out of range");
+                    if (k > cp[c] && ri[k] <= ri[k - 1]) return h->bad("CSC block: row indices not strictly ascending in a column");
+                }
+            }
+        }
+        std::vector<CscView> sel;
+        for (int p1 = 0; p1 < np; ++p1) sel.push_back({blocks[p1 * np].colptr, blocks[p1 * np].rowidx});
+        if (full)
+            for (int p1 = 0; p1 < np; ++p1)
+                for (int p2 = 1; p2 < np; ++p2) sel.push_back({blocks[p1 * np + p2].colptr, blocks[p1 * np + p2].rowidx});
+        std::vector<int> rowptr, colidx;
+        union_pattern_from_csc(N, sel.data(), (int)sel.size(), rowptr, colidx);
+        h->np_req = np;
+        h->csc_colptr.clear(); h->csc_rowidx.clear();
+        int rc = set_pattern(h, N, rowptr[N], rowptr.data(), colidx.data());
+        if (rc) return rc;
+        h->npcsc_colptr.assign(bb, {}); h->npcsc_rowidx.assign(bb, {}); h->npcsc_base.assign((size_t)bb + 1, 0);
+        for (int q = 0; q < bb; ++q) {
+            h->npcsc_colptr[q].assign(blocks[q].colptr, blocks[q].colptr + N + 1);
+            h->npcsc_rowidx[q].assign(blocks[q].rowidx, blocks[q].rowidx + blocks[q].colptr[N]);
+            h->npcsc_base[q + 1] = h->npcsc_base[q] + blocks[q].colptr[N];
+        }
+        h->csc_full_pattern = full;
+        const size_t nmap = (size_t)h->nnzb * bb;
+        CK(h->d_map_np.ensure(nmap));
+        CK(cudaMemsetAsync(h->d_map_np.p, 0xff, nmap * sizeof(long long), h->stream));
+        CK(cudaMemsetAsync(h->d_bad.p, 0, sizeof(int), h->stream));
+        DevArr<int> d_cp, d_ri;
+        CK(d_cp.ensure((size_t)N + 1));
+        size_t maxnnz = 1;
+        for (int q = 0; q < bb; ++q) maxnnz = std::max(maxnnz, h->npcsc_rowidx[q].size());
+        CK(d_ri.ensure(maxnnz));
+        for (int q = 0; q < bb; ++q) {
+            CK(cudaMemcpyAsync(d_cp.p, h->npcsc_colptr[q].data(), sizeof(int) * ((size_t)N + 1), cudaMemcpyHostToDevice, h->stream));
+            if (!h->npcsc_rowidx[q].empty())
+                CK(cudaMemcpyAsync(d_ri.p, h->npcsc_rowidx[q].data(), sizeof(int) * h->npcsc_rowidx[q].size(), cudaMemcpyHostToDevice, h->stream));
+            np_build_gather_map_kernel<<<(N + 255) / 256, 256, 0, h->stream>>>(N, q, bb, d_cp.p, d_ri.p, h->npcsc_base[q],
+                                                                               h->d_rowptr.p, h->d_colidx.p, h->d_map_np.p, h->d_bad.p);
+            h->launches++;
+            CK(cudaStreamSynchronize(h->stream));          // d_cp / d_ri are reused by the next block
+        }
+        CK(cudaMemcpyAsync(&h->h_flags2[1], h->d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        cudaEventRecord(h->ev[4], h->stream);
+        CK(cudaStreamSynchronize(h->stream));
+        d_cp.release(); d_ri.release();
+        result->ms_analysis = ev_ms(h->ev[3], h->ev[4]);
+        if (h->h_flags2[1]) {
+            h->have_pattern = false;
+            h->err = "Jacobian entry outside the interleaved sparsity pattern (set require_full_sparsity_pattern)";
+            return OPMGPU_BAD_PATTERN;
+        }
+    }
+    NpGuard guard(h, np);
+    const long long total = h->npcsc_base[bb];
+    const size_t n = (size_t)N * np, nv = (size_t)h->nnzb * bb;
+    CK(h->d_cscval.ensure((size_t)std::max<long long>(total, 1)));
+    CK(h->d_rhs_stage.ensure(n));
+    for (int q = 0; q < bb; ++q) {
+        const size_t nnz = (size_t)(h->npcsc_base[q + 1] - h->npcsc_base[q]);
+        if (nnz) CK(cudaMemcpyAsync(h->d_cscval.p + h->npcsc_base[q], blocks[q].val, nnz * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    }
+    CK(cudaMemcpyAsync(h->d_rhs_stage.p, rhs_eqmajor, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    NpScale sc;
+    for (int p = 0; p < 6; ++p) sc.s[p] = p < np ? matbalscale[p] : 1.0;
+    auto run = [&](auto tag) -> int {
+        using T = decltype(tag);
+        T* dv = np_vals_buffer<T>(h, nv);
+        if (!dv) return h->fail(cudaErrorMemoryAllocation, "np values");
+        np_interleave_gather_kernel<T><<<(unsigned)((nv + 255) / 256), 256, 0, h->stream>>>(nv, np, h->d_map_np.p, h->d_cscval.p, sc, dv);
+        np_interleave_rhs_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(N, np, h->d_rhs_stage.p, sc, vec<T>(h->d_r));
+        h->launches += 2;
+        CK(cudaGetLastError());
+        h->d_vals = dv;
+        h->have_values = true; h->have_factors = false;
+        int rc = solve_resident(h, params, result);
+        if (rc == OPMGPU_OK || rc == OPMGPU_NOT_CONVERGED) {
+            np_deinterleave_x_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(N, np, vec<T>(h->d_x), h->d_tmp.p);
+            h->launches++;
+            CK(cudaMemcpyAsync(dx_varmajor, h->d_tmp.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+        }
+        return rc;
+    };
+    return h->f32 ? run(float()) : run(double());
 }
 
 int opmgpu_num_levels(opmgpu_handle h, int* lower_levels, int* upper_levels)

@@ -175,6 +175,69 @@ class GpuLinearSolver:
         self.N, self.nnzb = rowptr.size - 1, colidx.size
         self._check(self.lib.opmgpu_set_pattern_bcrs_operator_only(self.h, self.N, self.nnzb, _ip(rowptr), _ip(colidx)))
 
+    # -- block sizes other than 3 (np = 2: two-phase decks) ------------------------------------
+    def set_block_size(self, np_: int):
+        """Prepare the NEXT pattern for block size np_ (2 or 3); call before set_pattern."""
+        self._check(self.lib.opmgpu_set_block_size(self.h, int(np_)))
+
+    def spmv_np(self, np_, vals, x):
+        vals = np.ascontiguousarray(vals, dtype=np.float64); x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.empty(self.N * np_)
+        self._check(self.lib.opmgpu_spmv_np(self.h, int(np_), _dp(vals), _dp(x), _dp(y)))
+        return y.reshape(self.N, np_)
+
+    def ilu0_np(self, np_, vals, w=0.9, d=None):
+        """-> (lu[nnzb, np*np], v[N, np] or None, bad_row)"""
+        vals = np.ascontiguousarray(vals, dtype=np.float64)
+        lu = np.empty((self.nnzb, np_ * np_))
+        bad = C.c_int(-1)
+        v = None
+        if d is not None:
+            d = np.ascontiguousarray(d, dtype=np.float64)
+            v = np.empty(self.N * np_)
+        rc = self.lib.opmgpu_ilu0_np(self.h, int(np_), _dp(vals), _dp(lu), float(w), _dp(d) if d is not None else None,
+                                     _dp(v) if v is not None else None, C.byref(bad))
+        if rc == L.SINGULAR_BLOCK:
+            return lu, None, bad.value
+        self._check(rc)
+        return lu, (v.reshape(self.N, np_) if v is not None else None), -1
+
+    def solve_bcrs_np(self, np_, vals, rhs, params: Optional[L.Params] = None, raise_on_failure=True, **kw):
+        p = params if params is not None else make_params(**kw)
+        vals = np.ascontiguousarray(vals, dtype=np.float64)
+        rhs = np.ascontiguousarray(rhs, dtype=np.float64)
+        x = np.zeros(self.N * np_)
+        res = L.Result()
+        rc = self.lib.opmgpu_solve_bcrs_np(self.h, int(np_), _dp(vals), _dp(rhs), _dp(x), C.byref(p), C.byref(res))
+        self.last = res.as_dict()
+        self.last["status"] = rc
+        self._check(rc, allow=() if raise_on_failure else (L.NOT_CONVERGED, L.SINGULAR_BLOCK, L.BREAKDOWN))
+        return x.reshape(self.N, np_), self.last
+
+    def solve_from_csc_blocks_np(self, N, np_, blocks, matbalscale, rhs_eqmajor, params: Optional[L.Params] = None,
+                                 raise_on_failure=True, **kw):
+        """...Interleaved.cpp:234-283 for np_ x np_ blocks; blocks[p1*np_+p2] = (colptr, rowidx, val)."""
+        p = params if params is not None else make_params(**kw)
+        arr = (L.Csc * (np_ * np_))()
+        keep = []
+        for q, (cp, ri, v) in enumerate(blocks):
+            cp = np.ascontiguousarray(cp, dtype=np.int32)
+            ri = np.ascontiguousarray(ri, dtype=np.int32)
+            v = np.ascontiguousarray(v, dtype=np.float64)
+            keep += [cp, ri, v]
+            arr[q].colptr, arr[q].rowidx, arr[q].val = _ip(cp), _ip(ri), _dp(v)
+        sc = np.ascontiguousarray(matbalscale, dtype=np.float64)
+        rhs = np.ascontiguousarray(rhs_eqmajor, dtype=np.float64)
+        dx = np.zeros(np_ * N)
+        res = L.Result()
+        rc = self.lib.opmgpu_solve_from_csc_blocks_np(self.h, int(N), int(np_), arr, _dp(sc), _dp(rhs), _dp(dx),
+                                                      C.byref(p), C.byref(res))
+        self.last = res.as_dict()
+        self.last["status"] = rc
+        self.N = N
+        self._check(rc, allow=() if raise_on_failure else (L.NOT_CONVERGED, L.SINGULAR_BLOCK, L.BREAKDOWN))
+        return dx, self.last
+
     def set_values(self, vals):
         vals = np.ascontiguousarray(vals, dtype=np.float64)
         assert vals.size == self.nnzb * 9
@@ -402,8 +465,8 @@ class NewtonIterationBlackoilGPU:
         [p(N), sw(N), xvar(N), qs(nw*np), bhp(nw)]."""
         import scipy.sparse as sp
         npz = len(residual.material_balance_eq)
-        if npz != 3:
-            raise NotImplementedError("NewtonIterationBlackoilGPU: only np == 3 (three-phase) is built")
+        if npz not in (2, 3):
+            raise NotImplementedError("NewtonIterationBlackoilGPU: np == 2 and np == 3 are built")
         eqs = list(residual.material_balance_eq)
         has_wells = residual.well_flux_eq is not None and residual.well_flux_eq.size() > 0
         elim = []
@@ -415,18 +478,22 @@ class NewtonIterationBlackoilGPU:
             eqs = eliminateVariable(eqs, npz)            # bhp unknowns
         N = eqs[0].size()
         blocks = []
-        for p1 in range(3):
-            for p2 in range(3):
+        for p1 in range(npz):
+            for p2 in range(npz):
                 J = sp.csc_matrix(eqs[p1].jac[p2])
                 J.sort_indices()
                 blocks.append((J.indptr, J.indices, J.data))
-        rhs = np.concatenate([eqs[p].value for p in range(3)])
+        rhs = np.concatenate([eqs[p].value for p in range(npz)])
         # the dispatcher of the reference: Impl<3,float> when the residual asks for it (GMRES exists
         # for the double instance only; that combination stays in double)
         self._solver.set_precision(bool(residual.singlePrecision) and not self.parameters_.newton_use_gmres)
         try:
-            dx, res = self._solver.solve_from_csc_blocks(N, blocks, residual.matbalscale, rhs,
-                                                         params=self.parameters_)
+            if npz == 3:
+                dx, res = self._solver.solve_from_csc_blocks(N, blocks, residual.matbalscale, rhs,
+                                                             params=self.parameters_)
+            else:
+                dx, res = self._solver.solve_from_csc_blocks_np(N, npz, blocks, residual.matbalscale[:npz], rhs,
+                                                                params=self.parameters_)
         finally:
             if self._solver.last is not None:            # valid also on the exception path
                 self.iterations_ = self._solver.last["iterations"]

@@ -13,8 +13,15 @@
 #include <stdlib.h>
 #include <string.h>
 
-#define BS 3          /* block size np */
-#define BB 9          /* BS*BS         */
+/* Block size np: 3 (three-phase black oil, the default build) or 2 (two-phase decks; the reference
+ * instantiates Impl<np,Scalar> for np = 2..6, NewtonIterationBlackoilInterleaved.cpp:467-487).
+ * -DORACLE_BS=2 builds liboracle_np2*.so: the same functions with generic loops in the same
+ * operation order (block umv / mmv: row outer, column inner) and dune's 2x2 inverse. */
+#ifndef ORACLE_BS
+#define ORACLE_BS 3
+#endif
+#define BS ORACLE_BS              /* block size np */
+#define BB (ORACLE_BS * ORACLE_BS)
 
 void oracle_free(void* p) { free(p); }
 
@@ -112,6 +119,20 @@ int oracle_interleave_values(int N, int np, const oracle_csc* blocks, const doub
 void oracle_spmv3(int N, const int* rowptr, const int* colidx, const real* vals,
                   const real* x, real* y)
 {
+#if BS != 3
+    for (int i = 0; i < N; ++i) {
+        real yb[BS];
+        for (int r = 0; r < BS; ++r) yb[r] = 0.0;
+        for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+            const real* a = vals + (size_t)k * BB;
+            const real* xj = x + (size_t)colidx[k] * BS;
+            for (int r = 0; r < BS; ++r)
+                for (int c = 0; c < BS; ++c) yb[r] = fma(a[r * BS + c], xj[c], yb[r]);
+        }
+        for (int r = 0; r < BS; ++r) y[(size_t)i * BS + r] = yb[r];
+    }
+    return;
+#else
     for (int i = 0; i < N; ++i) {
         real y0 = 0.0, y1 = 0.0, y2 = 0.0;
         for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
@@ -124,6 +145,7 @@ void oracle_spmv3(int N, const int* rowptr, const int* colidx, const real* vals,
         }
         y[(size_t)i * BS + 0] = y0; y[(size_t)i * BS + 1] = y1; y[(size_t)i * BS + 2] = y2;
     }
+#endif
 }
 
 /* ------------------------------------------------------------------------------------
@@ -146,6 +168,20 @@ static void mat3_mul(const real* A, const real* B, real* C)
  * "code generated by maple").  Returns the determinant. */
 static real mat3_invert(real* M)
 {
+#if BS == 2
+    /* Dune::FMatrixHelp / DenseMatrix::invert for 2x2 (OPM's MatrixBlock forwards to it):
+     * detinv = 1/(a00 a11 - a01 a10); a00 <-> a11 scaled, off-diagonals negated and scaled. */
+    const real det = M[0] * M[3] - M[1] * M[2];
+    const real detinv = (real)1.0 / det;
+    const real temp = M[0];
+    M[0] = M[3] * detinv;
+    M[1] = -M[1] * detinv;
+    M[2] = -M[2] * detinv;
+    M[3] = temp * detinv;
+    return det;
+#elif BS != 3
+#error "oracle: block sizes other than 2 and 3 are not restated (4x4: OPM's closed form; >4: dune's pivoted LU)"
+#else
     real A[BB];
     memcpy(A, M, sizeof A);
     const real t4 = A[0] * A[4];
@@ -166,6 +202,7 @@ static real mat3_invert(real* M)
     M[7] = -(A[0] * A[7] - t12) * t17;
     M[8] = (t4 - t8) * t17;
     return det;
+#endif
 }
 
 static int find_diag(const int* rowptr, const int* colidx, int i)
@@ -218,6 +255,39 @@ int oracle_ilu0_factor3(int N, const int* rowptr, const int* colidx, real* lu)
 void oracle_ilu0_apply3(int N, const int* rowptr, const int* colidx, const real* lu,
                         double w, const real* d, real* v)
 {
+#if BS != 3
+    for (int i = 0; i < N; ++i) {
+        real rb[BS];
+        for (int r = 0; r < BS; ++r) rb[r] = d[(size_t)i * BS + r];
+        for (int k = rowptr[i]; k < rowptr[i + 1] && colidx[k] < i; ++k) {
+            const real* a = lu + (size_t)k * BB;
+            const real* vj = v + (size_t)colidx[k] * BS;
+            for (int r = 0; r < BS; ++r)
+                for (int c = 0; c < BS; ++c) rb[r] = fma(-a[r * BS + c], vj[c], rb[r]);      /* mmv */
+        }
+        for (int r = 0; r < BS; ++r) v[(size_t)i * BS + r] = rb[r];
+    }
+    for (int i = N - 1; i >= 0; --i) {
+        real rb[BS], yb[BS];
+        for (int r = 0; r < BS; ++r) rb[r] = v[(size_t)i * BS + r];
+        int k = rowptr[i + 1] - 1;
+        for (; colidx[k] > i; --k) {
+            const real* a = lu + (size_t)k * BB;
+            const real* vj = v + (size_t)colidx[k] * BS;
+            for (int r = 0; r < BS; ++r)
+                for (int c = 0; c < BS; ++c) rb[r] = fma(-a[r * BS + c], vj[c], rb[r]);
+        }
+        const real* di = lu + (size_t)k * BB;
+        for (int r = 0; r < BS; ++r) {
+            yb[r] = 0.0;
+            for (int c = 0; c < BS; ++c) yb[r] = fma(di[r * BS + c], rb[c], yb[r]);           /* inv_[i].mv */
+        }
+        for (int r = 0; r < BS; ++r) v[(size_t)i * BS + r] = yb[r];
+    }
+    if (fabs(w - 1.0) > 1e-15)
+        for (size_t q = 0; q < (size_t)N * BS; ++q) v[q] *= (real)w;
+    return;
+#else
     for (int i = 0; i < N; ++i) {
         real r0 = d[(size_t)i * BS], r1 = d[(size_t)i * BS + 1], r2 = d[(size_t)i * BS + 2];
         for (int k = rowptr[i]; k < rowptr[i + 1] && colidx[k] < i; ++k) {
@@ -250,6 +320,7 @@ void oracle_ilu0_apply3(int N, const int* rowptr, const int* colidx, const real*
     }
     if (fabs(w - 1.0) > 1e-15)                                /* relaxation_ flag */
         for (size_t q = 0; q < (size_t)N * BS; ++q) v[q] *= (real)w;
+#endif
 }
 
 /* ------------------------------------------------------------------------------------
@@ -261,9 +332,7 @@ static real vdot(int N, const real* x, const real* y)
     real sum = 0.0;
     for (int i = 0; i < N; ++i) {
         real s = 0.0;
-        s = fma(x[(size_t)i * BS], y[(size_t)i * BS], s);
-        s = fma(x[(size_t)i * BS + 1], y[(size_t)i * BS + 1], s);
-        s = fma(x[(size_t)i * BS + 2], y[(size_t)i * BS + 2], s);
+        for (int c = 0; c < BS; ++c) s = fma(x[(size_t)i * BS + c], y[(size_t)i * BS + c], s);
         sum += s;
     }
     return sum;
@@ -398,6 +467,16 @@ static void apply_rotation(real* dx, real* dy, real cs, real sn)
 static void residual_update(int N, const int* rowptr, const int* colidx, const real* vals,
                             const real* x, real* b)
 {
+#if BS != 3
+    for (int i = 0; i < N; ++i)
+        for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+            const real* a = vals + (size_t)k * BB;
+            const real* xj = x + (size_t)colidx[k] * BS;
+            for (int r = 0; r < BS; ++r)
+                for (int c = 0; c < BS; ++c) b[(size_t)i * BS + r] = fma(-a[r * BS + c], xj[c], b[(size_t)i * BS + r]);
+        }
+    return;
+#endif
     for (int i = 0; i < N; ++i) {
         real r0 = b[(size_t)i * BS], r1 = b[(size_t)i * BS + 1], r2 = b[(size_t)i * BS + 2];
         for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {

@@ -43,7 +43,8 @@ class _Oracle:
     vectors cross the boundary as arrays of `real`; the caller-side data of the CSC front end
     (Jacobian values, scaling, equation-major vectors) and all parameters are doubles."""
 
-    def __init__(self, so_name, real_dtype):
+    def __init__(self, so_name, real_dtype, bs=3):
+        self.bs = bs                  # block size np the library was built for (ORACLE_BS)
         self.so = os.path.join(_HERE, "_build", so_name)
         self.real = np.dtype(real_dtype)
         self.c_real = C.c_float if self.real == np.float32 else C.c_double
@@ -99,8 +100,10 @@ class _Oracle:
     def _rp(self, a):
         return a.ctypes.data_as(C.POINTER(self.c_real))
 
-    def interleave(self, N, blocks, scale, require_full=False, np_=3):
+    def interleave(self, N, blocks, scale, require_full=False, np_=None):
         """-> rowptr, colidx, vals[nnzb, np*np] of the interleaved BCRS system."""
+        np_ = self.bs if np_ is None else np_
+        assert np_ == self.bs, "this oracle library was built for another block size"
         arr, keep = _csc_array(blocks)
         rowptr = np.zeros(N + 1, dtype=np.int32)
         out = C.POINTER(C.c_int)()
@@ -119,9 +122,9 @@ class _Oracle:
     def spmv(self, rowptr, colidx, vals, x):
         rowptr, prp = _i(rowptr); colidx, pci = _i(colidx); vals, pv = self._r(vals); x, px = self._r(x)
         N = rowptr.size - 1
-        y = np.zeros(N * 3, dtype=self.real)
+        y = np.zeros(N * self.bs, dtype=self.real)
         self.lib().oracle_spmv3(N, prp, pci, pv, px, self._rp(y))
-        return y.reshape(N, 3)
+        return y.reshape(N, self.bs)
 
     def ilu0_factor(self, rowptr, colidx, vals):
         """-> (lu[nnzb,9] with inverted diagonal blocks, bad_row or -1)."""
@@ -133,19 +136,19 @@ class _Oracle:
     def ilu0_apply(self, rowptr, colidx, lu, w, d):
         rowptr, prp = _i(rowptr); colidx, pci = _i(colidx); lu, plu = self._r(lu); d, pd = self._r(d)
         N = rowptr.size - 1
-        v = np.zeros(N * 3, dtype=self.real)
+        v = np.zeros(N * self.bs, dtype=self.real)
         self.lib().oracle_ilu0_apply3(N, prp, pci, plu, float(w), pd, self._rp(v))
-        return v.reshape(N, 3)
+        return v.reshape(N, self.bs)
 
     def solve_bcrs(self, rowptr, colidx, vals, rhs, reduction=1e-2, maxiter=150, relax=0.9, max_half_steps=-1):
         rowptr, prp = _i(rowptr); colidx, pci = _i(colidx); vals, pv = self._r(vals); rhs, pr = self._r(rhs)
         N = rowptr.size - 1
-        x = np.zeros(N * 3, dtype=self.real)
+        x = np.zeros(N * self.bs, dtype=self.real)
         res = OracleResult()
         self.lib().oracle_solve_bcrs3(N, prp, pci, pv, pr, self._rp(x),
                                       float(reduction), int(maxiter), float(relax), int(max_half_steps),
                                       C.byref(res))
-        return x.reshape(N, 3), res.as_dict()
+        return x.reshape(N, self.bs), res.as_dict()
 
     def bicgstab(self, rowptr, colidx, vals, lu, w, rhs, reduction=1e-2, maxiter=150, max_half_steps=-1,
                  history_cap=0):
@@ -153,7 +156,7 @@ class _Oracle:
         rowptr, prp = _i(rowptr); colidx, pci = _i(colidx); vals, pv = self._r(vals)
         N = rowptr.size - 1
         b = np.array(rhs, dtype=self.real, copy=True).reshape(-1)
-        x = np.zeros(N * 3, dtype=self.real)
+        x = np.zeros(N * self.bs, dtype=self.real)
         hist = np.zeros(max(history_cap, 1))
         plu = None
         if lu is not None:
@@ -163,24 +166,24 @@ class _Oracle:
                                     self._rp(x), float(reduction), int(maxiter),
                                     int(max_half_steps), hist.ctypes.data_as(C.POINTER(C.c_double)),
                                     int(history_cap), C.byref(res))
-        return x.reshape(N, 3), res.as_dict(), hist[:min(history_cap, res.half_steps)]
+        return x.reshape(N, self.bs), res.as_dict(), hist[:min(history_cap, res.half_steps)]
 
     def solve_gmres_bcrs(self, rowptr, colidx, vals, rhs, reduction=1e-2, maxiter=150, relax=0.9, restart=40):
         """ILU0 + Dune::RestartedGMResSolver (newton_use_gmres): x, result dict."""
         rowptr, prp = _i(rowptr); colidx, pci = _i(colidx); vals, pv = self._r(vals); rhs, pr = self._r(rhs)
         N = rowptr.size - 1
-        x = np.zeros(N * 3, dtype=self.real)
+        x = np.zeros(N * self.bs, dtype=self.real)
         res = OracleResult()
         self.lib().oracle_solve_gmres_bcrs3(N, prp, pci, pv, pr, self._rp(x),
                                             float(reduction), int(maxiter), float(relax), int(restart), C.byref(res))
-        return x.reshape(N, 3), res.as_dict()
+        return x.reshape(N, self.bs), res.as_dict()
 
     def gmres(self, rowptr, colidx, vals, lu, w, rhs, reduction=1e-2, maxiter=150, restart=40, history_cap=0):
         """lu=None -> identity preconditioner.  Returns x, result dict, preconditioned defect history."""
         rowptr, prp = _i(rowptr); colidx, pci = _i(colidx); vals, pv = self._r(vals)
         N = rowptr.size - 1
         b = np.array(rhs, dtype=self.real, copy=True).reshape(-1)
-        x = np.zeros(N * 3, dtype=self.real)
+        x = np.zeros(N * self.bs, dtype=self.real)
         hist = np.zeros(max(history_cap, 1))
         plu = None
         if lu is not None:
@@ -189,13 +192,13 @@ class _Oracle:
         self.lib().oracle_gmres3(N, prp, pci, pv, plu, float(w), self._rp(b),
                                  self._rp(x), float(reduction), int(maxiter), int(restart),
                                  hist.ctypes.data_as(C.POINTER(C.c_double)), int(history_cap), C.byref(res))
-        return x.reshape(N, 3), res.as_dict(), hist[:min(history_cap, res.half_steps)]
+        return x.reshape(N, self.bs), res.as_dict(), hist[:min(history_cap, res.half_steps)]
 
     def solve_from_csc_blocks(self, N, blocks9, matbalscale, rhs_eqmajor, reduction=1e-2, maxiter=150,
                               relax=0.9, require_full=False):
         arr, keep = _csc_array(blocks9)
         sc, psc = _d(matbalscale); rhs, pr = _d(rhs_eqmajor)
-        dx = np.zeros(3 * N)
+        dx = np.zeros(self.bs * N)
         res = OracleResult()
         self.lib().oracle_solve_from_csc_blocks(N, arr, psc, pr, dx.ctypes.data_as(C.POINTER(C.c_double)),
                                                 float(reduction), int(maxiter), float(relax),
@@ -225,9 +228,14 @@ def _csc_array(blocks):
 
 f64 = _Oracle("liboracle.so", np.float64)      # the reference's Impl<3,double>
 f32 = _Oracle("liboracle_f32.so", np.float32)  # the reference's Impl<3,float> (singlePrecision)
+np2 = _Oracle("liboracle_np2.so", np.float64, bs=2)          # Impl<2,double>: two-phase decks
+np2_f32 = _Oracle("liboracle_np2_f32.so", np.float32, bs=2)  # Impl<2,float>
 
 
-def instance(single_precision=False):
+def instance(single_precision=False, np_=3):
+    if np_ == 2:
+        return np2_f32 if single_precision else np2
+    assert np_ == 3, "the oracle restates block sizes 2 and 3"
     return f32 if single_precision else f64
 
 

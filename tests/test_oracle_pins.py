@@ -242,3 +242,51 @@ def test_float_oracle_reproduces_golden(oracle, path):
     assert np.array_equal(F.ilu0_apply(rp, ci, lu, 1.0, b), g["apply_w1"])
     x, res = F.solve_bcrs(rp, ci, v, b)
     assert res["iterations"] == int(g["iterations"]) and np.array_equal(x, g["x"])
+
+
+# ---- block size 2 (liboracle_np2*.so: the same file with -DORACLE_BS=2) ------------------------------
+def test_np2_oracle_pins(oracle):
+    """scipy bsr SpMV, a direct solve at a tight tolerance, the defining property (LU)_ij = A_ij on
+    the pattern, the block-tridiagonal known answer (ILU0 exact: one iteration), and the float build."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spl
+    from opm_simulators_legacy_b200.jacobian import synth_blackoil_jacobian
+    s = synth_blackoil_jacobian(10, 9, 5, perm="lognormal")
+    rp, ci = s.rowptr.numpy(), s.colidx.numpy()
+    v = np.ascontiguousarray(s.vals.numpy()[:, [0, 1, 3, 4]])
+    v[np.repeat(np.arange(s.N), np.diff(rp)) == ci] *= 1.3      # (the water / oil sub-system alone is close to singular)
+    b = np.ascontiguousarray(s.rhs.numpy()[:, :2])
+    N = s.N
+    A = sp.bsr_matrix((v.reshape(-1, 2, 2), ci, rp), shape=(2 * N, 2 * N))
+    x = np.ascontiguousarray(s.xstar.numpy()[:, :2])
+    y = oracle.np2.spmv(rp, ci, v, x)
+    assert np.abs(y.ravel() - A @ x.ravel()).max() <= 1e-12 * np.abs(y).max()
+    xs, res = oracle.np2.solve_bcrs(rp, ci, v, b, reduction=1e-12, maxiter=400)
+    assert res["converged"] == 1
+    ref = spl.spsolve(A.tocsc(), b.ravel())
+    assert np.abs(xs.ravel() - ref).max() <= 1e-8 * np.abs(ref).max()
+    # (LU)_ij = A_ij on the pattern: L unit lower (stored blocks), U upper, diagonal stored inverted
+    lu, bad = oracle.np2.ilu0_factor(rp, ci, v)
+    assert bad == -1
+    Lm = sp.lil_matrix((2 * N, 2 * N)); Um = sp.lil_matrix((2 * N, 2 * N))
+    for i in range(N):
+        for k in range(rp[i], rp[i + 1]):
+            j = ci[k]; blk = lu[k].reshape(2, 2)
+            if j < i:
+                Lm[2 * i:2 * i + 2, 2 * j:2 * j + 2] = blk
+            elif j == i:
+                Um[2 * i:2 * i + 2, 2 * i:2 * i + 2] = np.linalg.inv(blk)
+                Lm[2 * i:2 * i + 2, 2 * i:2 * i + 2] = np.eye(2)
+            else:
+                Um[2 * i:2 * i + 2, 2 * j:2 * j + 2] = blk
+    P = (Lm.tocsr() @ Um.tocsr()).toarray()
+    Ad = A.toarray()
+    mask = np.kron((sp.csr_matrix((np.ones(len(ci)), ci, rp), shape=(N, N)).toarray() != 0), np.ones((2, 2))) != 0
+    assert np.abs(P - Ad)[mask].max() <= 1e-10 * np.abs(Ad).max()
+    t = synth_blackoil_jacobian(40, 1, 1, perm="lognormal")
+    vt = np.ascontiguousarray(t.vals.numpy()[:, [0, 1, 3, 4]]); bt = np.ascontiguousarray(t.rhs.numpy()[:, :2])
+    _, rt = oracle.np2.solve_bcrs(t.rowptr.numpy(), t.colidx.numpy(), vt, bt, reduction=1e-10, relax=1.0)
+    assert rt["iterations"] == 1 and rt["converged"] == 1
+    x32, r32 = oracle.np2_f32.solve_bcrs(rp, ci, v, b)
+    x64, r64 = oracle.np2.solve_bcrs(rp, ci, v, b)
+    assert x32.dtype == np.float32 and r32["iterations"] == r64["iterations"]
