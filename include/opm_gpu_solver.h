@@ -199,6 +199,25 @@ int  opmgpu_spmv_np(opmgpu_handle h, int np, const double* vals, const double* x
 int  opmgpu_ilu0_np(opmgpu_handle h, int np, const double* vals, double* lu_out, double w,
                     const double* d, double* v, int* bad_row);
 
+/* ---- multicolour ILU0: a FLAGGED VARIANT, not the reference's preconditioner --------------------
+ * The reference factorises in the natural cell order (Dune::bilu0_decomposition on istlA,
+ * ISTLSolver.hpp:201-211), whose sweeps are a chain of nx+ny+nz-2 dependency levels.  With
+ * OPMGPU_ILU_MULTICOLOUR the same ILU0 is built of the symmetric permutation P A P^T that sorts the
+ * rows by colour (greedy colouring of the symmetrised block graph in natural order: red-black on a
+ * 7-point stencil), so each sweep is one fully parallel pass per colour.  This is a different
+ * preconditioner: iteration counts differ from the reference's and are reported separately, never
+ * as parity.  What IS bit-comparable: factors and applies against the oracle run on P A P^T.
+ * BiCGStab / GMRES, the operator and every vector stay in the caller's ordering.
+ * opmgpu_set_ilu_ordering prepares the NEXT pattern (call it before opmgpu_set_pattern_bcrs or the
+ * first opmgpu_solve_from_csc_blocks); plain single-GPU handles, 3x3 blocks, both precisions. */
+enum { OPMGPU_ILU_NATURAL = 0, OPMGPU_ILU_MULTICOLOUR = 1 };
+int  opmgpu_set_ilu_ordering(opmgpu_handle h, int ordering);
+int  opmgpu_get_ilu_ordering(opmgpu_handle h);
+/* Colours and permutation of the current pattern (n2p[i] = position of row i in P A P^T). */
+int  opmgpu_get_ilu_permutation(opmgpu_handle h, int* ncolours, int* n2p);
+/* The ordering rule alone, host only (no GPU, no handle); any output may be NULL. */
+int  opmgpu_multicolour_order(int N, const int* rowptr, const int* colidx, int* ncolours, int* colour, int* n2p);
+
 /* ---- kernel-level entry points (parity tests, micro-benchmarks) -------------------------- */
 
 /* The operator alone: uploads the pattern for opmgpu_spmv* without the ILU0 analysis (the SpMV

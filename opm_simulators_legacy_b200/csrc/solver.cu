@@ -14,6 +14,8 @@
 #include "spmv_tma.cuh"
 #include "gmres.cuh"
 #include "generic_np.cuh"
+#include "mcorder.hpp"
+#include "mc_ilu.cuh"
 #include "multi.hpp"
 
 #include <dlfcn.h>
@@ -148,6 +150,22 @@ struct ColDevMem {
     }
 };
 
+// multicolour ILU0 variant (mcorder.hpp, mc_ilu.cuh)
+struct McDevMem {
+    bool valid = false;
+    int ncolours = 0;
+    long long nnzL = 0, nnzU = 0, offD = 0, offU = 0, total_blocks = 0;
+    std::vector<int> colour_ptr, lvl_ptr, p2n_host, n2p_host;
+    DevArr<int> p2n, prowptr, pcol, pdiag, psrc, ppos, Lrowptr, Lcol, Urowptr, Ucol, lvl_rows;
+    DevArr<double> uni;          // [ L | Dinv | U ] blocks of T (allocated for doubles)
+    void release()
+    {
+        valid = false;
+        p2n.release(); prowptr.release(); pcol.release(); pdiag.release(); psrc.release(); ppos.release();
+        Lrowptr.release(); Lcol.release(); Urowptr.release(); Ucol.release(); lvl_rows.release(); uni.release();
+    }
+};
+
 struct FactorPipeDevMem {
     DevArr<unsigned char> buf;
     DevArr<int> cta_step_ptr, val_src, cta_row_base, fpos;
@@ -236,6 +254,10 @@ struct opmgpu_solver {
     DevArr<long long> d_map_np;
     std::vector<std::vector<int>> npcsc_colptr, npcsc_rowidx;      // CSC front end cache of the np path
     std::vector<long long> npcsc_base;
+    // ILU0 ordering: 0 natural (the reference's), 1 multicolour (flagged variant).  ilu_order_req is what
+    // the NEXT pattern is prepared for (opmgpu_set_ilu_ordering), mc.valid what the current one runs.
+    int ilu_order_req = 0;
+    McDevMem mc;
     bool operator_only = false;    // opmgpu_set_pattern_bcrs_operator_only: no ILU0 programs, SpMV entry points only
     DevArr<double> d_vals_own, d_lu, d_stage;
     DevArr<float> d_vals32;
@@ -616,6 +638,57 @@ int ensure_vectors(opmgpu_handle h)
     return 0;
 }
 
+// Multicolour variant: colours, permutation, permuted pattern and the operand layouts of the sweeps;
+// none of the natural-order sweep programs is built.
+int set_pattern_mc(opmgpu_handle h, int N, int nnzb, const int* rowptr, const int* colidx)
+{
+    if (h->np_req != 3) return h->bad("the multicolour ILU0 variant exists for 3x3 blocks");
+    for (int i = 0; i < N; ++i) {
+        bool have_diag = false;
+        for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) have_diag |= colidx[k] == i;
+        if (!have_diag) {
+            h->err = "diagonal entry missing in block row " + std::to_string(i);
+            return OPMGPU_SINGULAR_BLOCK;
+        }
+    }
+    McProgram m;
+    build_mc_program(N, rowptr, colidx, m);
+    h->use_pipe = false; h->use_col = false; h->cluster_size = 1;
+    h->pipeL.release(); h->pipeU.release(); h->pipeF.release(); h->progL.release(); h->progU.release(); h->col.release();
+    h->d_lu.release();                  // built on demand by opmgpu_ilu0_get_factors
+    h->lvlU_ptr.clear();
+    h->N = N; h->nnzb = nnzb; h->n_ghost = 0;
+    h->N_for_upload = N;
+    CK(h->d_rowptr.ensure((size_t)N + 1 + 8));
+    CK(h->d_colidx.ensure((size_t)nnzb + 8));
+    CK(cudaMemcpyAsync(h->d_rowptr.p, rowptr, sizeof(int) * ((size_t)N + 1), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_colidx.p, colidx, sizeof(int) * (size_t)nnzb, cudaMemcpyHostToDevice, h->stream));
+    McDevMem& d = h->mc;
+    d.valid = false;
+    // the sweeps' bulk copies round sizes up to 16 bytes: 8 ints of slack behind the index arrays
+    auto up = [&](DevArr<int>& dst, const std::vector<int>& v) -> int {
+        CK(dst.ensure(v.size() + 8));
+        if (!v.empty()) CK(cudaMemcpyAsync(dst.p, v.data(), sizeof(int) * v.size(), cudaMemcpyHostToDevice, h->stream));
+        return 0;
+    };
+    int rc;
+    if ((rc = up(d.p2n, m.ord.p2n)) || (rc = up(d.prowptr, m.prowptr)) || (rc = up(d.pcol, m.pcol)) || (rc = up(d.pdiag, m.pdiag)) ||
+        (rc = up(d.psrc, m.psrc)) || (rc = up(d.ppos, m.ppos)) || (rc = up(d.Lrowptr, m.Lrowptr)) || (rc = up(d.Lcol, m.Lcol)) ||
+        (rc = up(d.Urowptr, m.Urowptr)) || (rc = up(d.Ucol, m.Ucol)) || (rc = up(d.lvl_rows, m.lvl_rows))) return rc;
+    CK(d.uni.ensure((size_t)m.total_blocks * 9));
+    CK(cudaMemsetAsync(d.uni.p, 0, sizeof(double) * (size_t)m.total_blocks * 9, h->stream));
+    if ((rc = ensure_vectors(h))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    d.ncolours = m.ord.ncolours;
+    d.nnzL = m.Lrowptr[N]; d.nnzU = m.Urowptr[N]; d.offD = m.offD; d.offU = m.offU; d.total_blocks = m.total_blocks;
+    d.colour_ptr = m.ord.colour_ptr; d.lvl_ptr = m.lvl_ptr;
+    d.p2n_host = std::move(m.ord.p2n); d.n2p_host = std::move(m.ord.n2p);
+    d.valid = true;
+    h->nlevL = h->nlevU = d.ncolours;
+    h->have_pattern = true;
+    return OPMGPU_OK;
+}
+
 int set_pattern(opmgpu_handle h, int N, int nnzb, const int* rowptr, const int* colidx)
 {
     if (N < 1 || nnzb < N || rowptr[0] != 0 || rowptr[N] != nnzb) return h->bad("bad BCRS pattern sizes");
@@ -628,6 +701,8 @@ int set_pattern(opmgpu_handle h, int N, int nnzb, const int* rowptr, const int* 
     }
     h->have_pattern = h->have_values = h->have_factors = false;
     h->operator_only = false;
+    if (h->ilu_order_req == 1) return set_pattern_mc(h, N, nnzb, rowptr, colidx);
+    h->mc.release();
     analyse_pattern(N, rowptr, colidx, h->sweep_ctas, h->an, h->force_simple, &h->caps);
     h->cluster_size = h->an.cluster_size;
     if (h->an.missing_diag_row >= 0) {
@@ -1069,10 +1144,45 @@ int np_factor(opmgpu_handle h, int* bad_row)
     return OPMGPU_OK;
 }
 
+// Multicolour variant: A -> [ L | Dinv | U ] in permuted order, then bilu0_decomposition level by level
+template <class T>
+int mc_factor(opmgpu_handle h, int* bad_row)
+{
+    if (!h->have_values) return h->bad("no matrix values set");
+    McDevMem& d = h->mc;
+    T* uni = reinterpret_cast<T*>(d.uni.p);
+    const size_t nscal = (size_t)h->nnzb * 9;
+    mc_gather_values_kernel<T><<<(unsigned)((nscal + 255) / 256), 256, 0, h->stream>>>(nscal, d.psrc.p, d.ppos.p, static_cast<const T*>(h->d_vals), uni);
+    h->launches++;
+    const int big = 0x7fffffff;
+    CK(cudaMemcpyAsync(h->d_bad.p, &big, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    for (size_t l = 0; l + 1 < d.lvl_ptr.size(); ++l) {
+        const int n = d.lvl_ptr[l + 1] - d.lvl_ptr[l];
+        if (n <= 0) continue;
+        mc_factor_level_kernel<T><<<(n + 127) / 128, 128, 0, h->stream>>>(d.lvl_rows.p, d.lvl_ptr[l], d.lvl_ptr[l + 1], d.prowptr.p, d.pcol.p,
+                                                                          d.pdiag.p, d.ppos.p, uni, h->d_bad.p);
+        h->launches++;
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(&h->h_flags2[1], h->d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->h_flags2[1] != big) {
+        const int row = d.p2n_host[h->h_flags2[1]];          // reported in the caller's numbering
+        if (bad_row) *bad_row = row;
+        h->err = "singular diagonal block in ILU0 at block row " + std::to_string(row) + " (multicolour ordering)";
+        h->have_factors = false;
+        return OPMGPU_SINGULAR_BLOCK;
+    }
+    if (bad_row) *bad_row = -1;
+    h->have_factors = true;
+    return OPMGPU_OK;
+}
+
 template <class T>
 int factor_t(opmgpu_handle h, int* bad_row)
 {
     if (h->np != 3) return np_factor<T>(h, bad_row);
+    if (h->mc.valid) return mc_factor<T>(h, bad_row);
     if (!h->have_values) return h->bad("no matrix values set");
     if (h->operator_only) return h->bad("the pattern was set operator-only (no ILU0 analysis): opmgpu_set_pattern_bcrs first");
     if (h->f32 && h->use_col) return h->bad("the column-owned sweeps (OPMGPU_COL=1) exist for the double instance only");
@@ -1285,10 +1395,55 @@ int np_apply(opmgpu_handle h, double w, const T* d, T* v)
     return 0;
 }
 
+// Multicolour variant: v = w P^T U^-1 L^-1 P d, one pass per colour and direction; the first colour's
+// lower pass is a gather, the last colour's lower and upper passes are one kernel
+template <int KIND, class T>
+int mc_launch(opmgpu_handle h, McSweepArgs& a)
+{
+    static const int rowt_env = getenv("OPMGPU_MC_ROWT") ? atoi(getenv("OPMGPU_MC_ROWT")) : -1;
+    const void* fn;
+    int rows;
+    if (sizeof(T) == 4) { fn = (const void*)mc_sweep_tma_kernel<KIND, float, true, kSpmvRowsF32>; rows = kSpmvRowsF32; }
+    else if (rowt_env == 1) { fn = (const void*)mc_sweep_tma_kernel<KIND, double, true, kSpmvRows>; rows = kSpmvRows; }
+    else { fn = (const void*)mc_sweep_tma_kernel<KIND, double, false, kSpmvRows>; rows = kSpmvRows; }
+    const int ntiles = (a.row1 + rows - 1) / rows - a.row0 / rows;
+    if (ntiles <= 0) return 0;
+    void* args[] = {&a};
+    CK(cudaLaunchKernel(fn, dim3((unsigned)std::min(ntiles, h->sm_count)), dim3(kSpmvThreads), args, kMcSmemBytes, h->stream));
+    h->launches++;
+    return 0;
+}
+
+template <class T>
+int mc_apply(opmgpu_handle h, double w, const T* d, T* v)
+{
+    McDevMem& m = h->mc;
+    const int C = m.ncolours;
+    const T* uni = reinterpret_cast<const T*>(m.uni.p);
+    McSweepArgs a;
+    a.N = h->N; a.p2n = m.p2n.p; a.d = d; a.W = vec<T>(h->d_yL); a.dinv = uni + (size_t)m.offD * 9; a.out = v;
+    a.w = w; a.scale = std::fabs(w - 1.0) > 1e-15 ? 1 : 0;
+    auto lower = [&](int c) { a.nnz = (int)m.nnzL; a.rowptr = m.Lrowptr.p; a.colidx = m.Lcol.p; a.vals = uni; a.row0 = m.colour_ptr[c]; a.row1 = m.colour_ptr[c + 1]; };
+    auto upper = [&](int c) { a.nnz = (int)m.nnzU; a.rowptr = m.Urowptr.p; a.colidx = m.Ucol.p; a.vals = uni + (size_t)m.offU * 9; a.row0 = m.colour_ptr[c]; a.row1 = m.colour_ptr[c + 1]; };
+    int rc;
+    if (C > 1) {
+        const size_t e = (size_t)(m.colour_ptr[1] - m.colour_ptr[0]) * 3;
+        mc_copy_rows_kernel<T><<<(unsigned)((e + 255) / 256), 256, 0, h->stream>>>(m.colour_ptr[0], m.colour_ptr[1], m.p2n.p, d, vec<T>(h->d_yL));
+        h->launches++;
+        for (int c = 1; c + 1 < C; ++c) { lower(c); if ((rc = mc_launch<0, T>(h, a))) return rc; }
+    }
+    lower(C - 1);
+    if ((rc = mc_launch<1, T>(h, a))) return rc;
+    for (int c = C - 2; c >= 0; --c) { upper(c); if ((rc = mc_launch<2, T>(h, a))) return rc; }
+    CK(cudaGetLastError());
+    return 0;
+}
+
 template <class T>
 int apply_precond(opmgpu_handle h, double w, const T* d, T* v, bool d_in_program_order = false)
 {
     if (h->np != 3) return np_apply<T>(h, w, d, v);
+    if (h->mc.valid) return mc_apply<T>(h, w, d, v);
     const int scale = std::fabs(w - 1.0) > 1e-15 ? 1 : 0;      // relaxation_ flag of the reference
     if (h->use_col && sizeof(T) == 4) return h->bad("the column-owned sweeps (OPMGPU_COL=1) exist for the double instance only");
     if (h->use_col) {
@@ -1990,6 +2145,15 @@ int opmgpu_create(int device, opmgpu_handle* out)
     cudaFuncSetAttribute(spmv3_tma_kernel<0, double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
     cudaFuncSetAttribute(spmv3_tma_kernel<1, double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
     cudaFuncSetAttribute(spmv3_tma_kernel<2, double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
+    cudaFuncSetAttribute(mc_sweep_tma_kernel<0, double, false, kSpmvRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMcSmemBytes);
+    cudaFuncSetAttribute(mc_sweep_tma_kernel<1, double, false, kSpmvRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMcSmemBytes);
+    cudaFuncSetAttribute(mc_sweep_tma_kernel<2, double, false, kSpmvRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMcSmemBytes);
+    cudaFuncSetAttribute(mc_sweep_tma_kernel<0, double, true, kSpmvRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMcSmemBytes);
+    cudaFuncSetAttribute(mc_sweep_tma_kernel<1, double, true, kSpmvRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMcSmemBytes);
+    cudaFuncSetAttribute(mc_sweep_tma_kernel<2, double, true, kSpmvRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMcSmemBytes);
+    cudaFuncSetAttribute(mc_sweep_tma_kernel<0, float, true, kSpmvRowsF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMcSmemBytes);
+    cudaFuncSetAttribute(mc_sweep_tma_kernel<1, float, true, kSpmvRowsF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMcSmemBytes);
+    cudaFuncSetAttribute(mc_sweep_tma_kernel<2, float, true, kSpmvRowsF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMcSmemBytes);
     if (const char* s = getenv("OPMGPU_HALO_OVERLAP")) h->overlap_halo = atoi(s) != 0;
     if (const char* s = getenv("OPMGPU_PEER_HALO")) h->use_peer_halo = atoi(s) != 0;
     cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
@@ -2088,6 +2252,7 @@ int opmgpu_destroy(opmgpu_handle h)
     cudaDeviceSynchronize();
     h->d_rowptr.release(); h->d_colidx.release(); h->d_diag.release(); h->d_lvl_rows.release();
     h->progL.release(); h->progU.release(); h->pipeL.release(); h->pipeU.release(); h->pipeF.release(); h->col.release();
+    h->mc.release();
     h->d_vals_own.release(); h->d_lu.release(); h->d_stage.release(); h->d_vals32.release();
     h->d_x.release(); h->d_r.release(); h->d_rt.release(); h->d_p.release(); h->d_v.release();
     h->d_t.release(); h->d_y.release(); h->d_yL.release(); h->d_vU.release(); h->d_tmp.release(); h->d_tmp2.release();
@@ -2241,6 +2406,19 @@ int opmgpu_ilu0_get_factors(opmgpu_handle h, double* lu)
 {
     if (!h || !h->have_factors) return OPMGPU_BAD_ARGUMENT;
     CK(cudaSetDevice(h->device));
+    if (h->mc.valid && h->np == 3) {
+        // multicolour variant: the factors of P A P^T, returned in the slots of the caller's BCRS pattern
+        // (slot of (i,j) holds the factor block of (p(i), p(j)): L where p(j) < p(i), U where p(j) > p(i))
+        const size_t nscal = (size_t)h->nnzb * 9;
+        CK(h->d_stage.ensure(nscal));
+        if (h->f32) mc_scatter_factors_kernel<float><<<(unsigned)((nscal + 255) / 256), 256, 0, h->stream>>>(nscal, h->mc.psrc.p, h->mc.ppos.p, reinterpret_cast<const float*>(h->mc.uni.p), h->d_stage.p);
+        else mc_scatter_factors_kernel<double><<<(unsigned)((nscal + 255) / 256), 256, 0, h->stream>>>(nscal, h->mc.psrc.p, h->mc.ppos.p, h->mc.uni.p, h->d_stage.p);
+        h->launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(lu, h->d_stage.p, nscal * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return OPMGPU_OK;
+    }
     if (h->lu_lazy && !h->have_values)
         return h->bad("the factorised matrix values were only borrowed for the solve call (opmgpu_solve_bcrs3_dev): "
                       "set them again (opmgpu_set_values_bcrs3[_dev]) and factorise before asking for the factors");
@@ -2812,6 +2990,42 @@ int opmgpu_solve_from_csc_blocks_np(opmgpu_handle h, int N, int np, const opmgpu
         return rc;
     };
     return h->f32 ? run(float()) : run(double());
+}
+
+// ---- multicolour ILU0 variant (flagged: NOT the reference's preconditioner) ----------------------
+int opmgpu_set_ilu_ordering(opmgpu_handle h, int ordering)
+{
+    if (!h) return OPMGPU_BAD_ARGUMENT;
+    if (ordering != OPMGPU_ILU_NATURAL && ordering != OPMGPU_ILU_MULTICOLOUR) return h->bad("unknown ILU0 ordering");
+    if (ordering != OPMGPU_ILU_NATURAL && (h->multi || h->world > 1))
+        return h->bad("the multicolour ILU0 variant exists for plain single-GPU handles");
+    if (ordering != h->ilu_order_req) {          // takes effect with the next pattern
+        h->ilu_order_req = ordering;
+        h->have_pattern = h->have_values = h->have_factors = false;
+        h->csc_colptr.clear(); h->csc_rowidx.clear();
+    }
+    return OPMGPU_OK;
+}
+int opmgpu_get_ilu_ordering(opmgpu_handle h) { return h && h->ilu_order_req == 1 ? OPMGPU_ILU_MULTICOLOUR : OPMGPU_ILU_NATURAL; }
+
+int opmgpu_multicolour_order(int N, const int* rowptr, const int* colidx, int* ncolours, int* colour, int* n2p)
+{
+    if (N < 1 || !rowptr || !colidx) return OPMGPU_BAD_ARGUMENT;
+    McOrder o;
+    multicolour_order(N, rowptr, colidx, o);
+    if (ncolours) *ncolours = o.ncolours;
+    if (colour) std::copy(o.colour.begin(), o.colour.end(), colour);
+    if (n2p) std::copy(o.n2p.begin(), o.n2p.end(), n2p);
+    return OPMGPU_OK;
+}
+
+int opmgpu_get_ilu_permutation(opmgpu_handle h, int* ncolours, int* n2p)
+{
+    if (!h || !h->have_pattern) return OPMGPU_BAD_ARGUMENT;
+    if (!h->mc.valid) return h->bad("the current pattern uses the natural ordering");
+    if (ncolours) *ncolours = h->mc.ncolours;
+    if (n2p) std::copy(h->mc.n2p_host.begin(), h->mc.n2p_host.end(), n2p);
+    return OPMGPU_OK;
 }
 
 int opmgpu_num_levels(opmgpu_handle h, int* lower_levels, int* upper_levels)

@@ -81,6 +81,22 @@ def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 
 
+def multicolour_order(rowptr, colidx):
+    """The ordering rule of the multicolour ILU0 variant alone (host code of the library, no GPU):
+    returns (ncolours, colour[N], n2p[N])."""
+    lib = L.load()
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int32)
+    colidx = np.ascontiguousarray(colidx, dtype=np.int32)
+    N = rowptr.size - 1
+    nc = C.c_int(0)
+    colour = np.empty(N, dtype=np.int32)
+    n2p = np.empty(N, dtype=np.int32)
+    rc = lib.opmgpu_multicolour_order(N, _ip(rowptr), _ip(colidx), C.byref(nc), _ip(colour), _ip(n2p))
+    if rc != L.OK:
+        raise ValueError("opmgpu_multicolour_order: bad pattern")
+    return nc.value, colour, n2p
+
+
 class GpuLinearSolver:
     """One opmgpu handle (one GPU, one stream)."""
 
@@ -174,6 +190,22 @@ class GpuLinearSolver:
         colidx = np.ascontiguousarray(colidx, dtype=np.int32)
         self.N, self.nnzb = rowptr.size - 1, colidx.size
         self._check(self.lib.opmgpu_set_pattern_bcrs_operator_only(self.h, self.N, self.nnzb, _ip(rowptr), _ip(colidx)))
+
+    # -- multicolour ILU0: a flagged variant, not the reference's preconditioner ----------------
+    def set_ilu_ordering(self, multicolour: bool):
+        """Prepare the NEXT pattern for the natural (reference) or the multicolour ordering of the
+        ILU0 (include/opm_gpu_solver.h: iteration counts of the variant are never parity)."""
+        self._check(self.lib.opmgpu_set_ilu_ordering(self.h, L.ILU_MULTICOLOUR if multicolour else L.ILU_NATURAL))
+
+    def ilu_ordering(self) -> int:
+        return int(self.lib.opmgpu_get_ilu_ordering(self.h))
+
+    def ilu_permutation(self):
+        """(ncolours, n2p) of the current multicolour pattern; n2p[i] = position of row i in P A P^T."""
+        nc = C.c_int(0)
+        n2p = np.empty(self.N, dtype=np.int32)
+        self._check(self.lib.opmgpu_get_ilu_permutation(self.h, C.byref(nc), _ip(n2p)))
+        return nc.value, n2p
 
     # -- block sizes other than 3 (np = 2: two-phase decks) ------------------------------------
     def set_block_size(self, np_: int):

@@ -15,8 +15,10 @@
 
 /* Block size np: 3 (three-phase black oil, the default build) or 2 (two-phase decks; the reference
  * instantiates Impl<np,Scalar> for np = 2..6, NewtonIterationBlackoilInterleaved.cpp:467-487).
- * -DORACLE_BS=2 builds liboracle_np2*.so: the same functions with generic loops in the same
- * operation order (block umv / mmv: row outer, column inner) and dune's 2x2 inverse. */
+ * -DORACLE_BS=2 / 4 / 5 / 6 builds liboracle_np<bs>*.so: the same functions with generic loops in
+ * the same operation order (block umv / mmv: row outer, column inner) and the block inverse the
+ * reference's MatrixBlock uses for that size (2x2: dune's closed form; 4x4: OPM's closed form;
+ * 5, 6: dune's thresholded-pivoting LU). */
 #ifndef ORACLE_BS
 #define ORACLE_BS 3
 #endif
@@ -179,8 +181,113 @@ static real mat3_invert(real* M)
     M[2] = -M[2] * detinv;
     M[3] = temp * detinv;
     return det;
-#elif BS != 3
-#error "oracle: block sizes other than 2 and 3 are not restated (4x4: OPM's closed form; >4: dune's pivoted LU)"
+#elif BS == 4
+    /* Opm's invertMatrix(FieldMatrix<K,4,4>&) (opm-simulators MatrixBlock.hpp / ISTLUtility; not in the
+     * reference tree): the cofactor expansion published with Mesa's GLU (gluInvertMatrix), every entry
+     * a left-to-right sum of six signed triple products (a*b)*c, det = first row . first column of the
+     * adjugate, inverse = adjugate * (1/det).  inv4_terms[e] lists the products of adjugate entry e
+     * (flat index 4*row+col); the first product carries inv4_lead[e], the signs then go - - + + - / + + - - +. */
+    static const unsigned char inv4_terms[16][6][3] = {
+        {{5,10,15},{5,11,14},{9,6,15},{9,7,14},{13,6,11},{13,7,10}},   /* 0 */
+        {{1,10,15},{1,11,14},{9,2,15},{9,3,14},{13,2,11},{13,3,10}},   /* 1 */
+        {{1,6,15},{1,7,14},{5,2,15},{5,3,14},{13,2,7},{13,3,6}},       /* 2 */
+        {{1,6,11},{1,7,10},{5,2,11},{5,3,10},{9,2,7},{9,3,6}},         /* 3 */
+        {{4,10,15},{4,11,14},{8,6,15},{8,7,14},{12,6,11},{12,7,10}},   /* 4 */
+        {{0,10,15},{0,11,14},{8,2,15},{8,3,14},{12,2,11},{12,3,10}},   /* 5 */
+        {{0,6,15},{0,7,14},{4,2,15},{4,3,14},{12,2,7},{12,3,6}},       /* 6 */
+        {{0,6,11},{0,7,10},{4,2,11},{4,3,10},{8,2,7},{8,3,6}},         /* 7 */
+        {{4,9,15},{4,11,13},{8,5,15},{8,7,13},{12,5,11},{12,7,9}},     /* 8 */
+        {{0,9,15},{0,11,13},{8,1,15},{8,3,13},{12,1,11},{12,3,9}},     /* 9 */
+        {{0,5,15},{0,7,13},{4,1,15},{4,3,13},{12,1,7},{12,3,5}},       /* 10 */
+        {{0,5,11},{0,7,9},{4,1,11},{4,3,9},{8,1,7},{8,3,5}},           /* 11 */
+        {{4,9,14},{4,10,13},{8,5,14},{8,6,13},{12,5,10},{12,6,9}},     /* 12 */
+        {{0,9,14},{0,10,13},{8,1,14},{8,2,13},{12,1,10},{12,2,9}},     /* 13 */
+        {{0,5,14},{0,6,13},{4,1,14},{4,2,13},{12,1,6},{12,2,5}},       /* 14 */
+        {{0,5,10},{0,6,9},{4,1,10},{4,2,9},{8,1,6},{8,2,5}},           /* 15 */
+    };
+    /* leading sign of entry e: + where row+col is even */
+    static const signed char sgn[6] = {+1, -1, -1, +1, +1, -1};
+    real A[BB], inv[BB];
+    memcpy(A, M, sizeof A);
+    for (int e = 0; e < 16; ++e) {
+        const int lead = (((e >> 2) + (e & 3)) & 1) ? -1 : +1;
+        real acc = 0.0;
+        for (int t = 0; t < 6; ++t) {
+            const unsigned char* q = inv4_terms[e][t];
+            const real prod = A[q[0]] * A[q[1]] * A[q[2]];
+            if (t == 0) acc = (lead * sgn[0] > 0) ? prod : -prod;
+            else if (lead * sgn[t] > 0) acc = acc + prod;
+            else acc = acc - prod;
+        }
+        inv[e] = acc;
+    }
+    const real det = A[0] * inv[0] + A[1] * inv[4] + A[2] * inv[8] + A[3] * inv[12];
+    const real inv_det = (real)1.0 / det;
+    for (int e = 0; e < 16; ++e) M[e] = inv[e] * inv_det;
+    return det;
+#elif BS > 4
+    /* Dune::DenseMatrix::invert, generic branch (dune-common 2.6 densematrix.hh; OPM's MatrixBlock
+     * forwards to it for block sizes without a closed form): LU decomposition with row pivoting only
+     * where |A_ii| < max(absolute_limit, |A|_inf * pivoting_limit) (FMatrixPrecision: 1e-80, 1e-8),
+     * singular where the pivot is below max(absolute_limit, |A|_inf * singular_limit) (1e-14); then
+     * L Y = I, U X = Y, and the recorded row swaps undone as column swaps, last first.
+     * Returns the product of the pivots (sign of the swaps included), 0 where dune throws "matrix is singular". */
+    real A[BS][BS], X[BS][BS];
+    int pivot[BS];
+    real norm = 0.0;
+    for (int i = 0; i < BS; ++i) {
+        real srow = 0.0;
+        for (int j = 0; j < BS; ++j) { A[i][j] = M[i * BS + j]; srow += fabs(A[i][j]); }
+        if (srow > norm) norm = srow;
+        pivot[i] = i;
+    }
+    const real abslim = (real)1e-80;
+    real pivthres = norm * (real)1e-8, singthres = norm * (real)1e-14;
+    if (pivthres < abslim) pivthres = abslim;
+    if (singthres < abslim) singthres = abslim;
+    real det = 1.0;
+    for (int i = 0; i < BS; ++i) {
+        real pivmax = fabs(A[i][i]);
+        if (pivmax < pivthres) {
+            int imax = i;
+            for (int k = i + 1; k < BS; ++k) {
+                const real ab = fabs(A[k][i]);
+                if (ab > pivmax) { pivmax = ab; imax = k; }
+            }
+            if (imax != i) {
+                for (int j = 0; j < BS; ++j) { const real t = A[i][j]; A[i][j] = A[imax][j]; A[imax][j] = t; }
+                pivot[i] = imax;
+                det = -det;
+            }
+        }
+        if (!(pivmax >= singthres)) return 0.0;      /* dune: FMatrixError "matrix is singular" (also catches NaN) */
+        det *= A[i][i];
+        for (int k = i + 1; k < BS; ++k) {
+            const real factor = A[k][i] / A[i][i];
+            A[k][i] = factor;
+            for (int j = i + 1; j < BS; ++j) A[k][j] -= factor * A[i][j];
+        }
+    }
+    for (int i = 0; i < BS; ++i)
+        for (int j = 0; j < BS; ++j) X[i][j] = (i == j) ? 1.0 : 0.0;
+    for (int i = 0; i < BS; ++i)
+        for (int j = 0; j < i; ++j)
+            for (int k = 0; k < BS; ++k) X[i][k] -= A[i][j] * X[j][k];
+    for (int i = BS; i > 0;) {
+        --i;
+        for (int k = 0; k < BS; ++k) {
+            for (int j = i + 1; j < BS; ++j) X[i][k] -= A[i][j] * X[j][k];
+            X[i][k] /= A[i][i];
+        }
+    }
+    for (int i = BS; i > 0;) {
+        --i;
+        if (i != pivot[i])
+            for (int j = 0; j < BS; ++j) { const real t = X[j][pivot[i]]; X[j][pivot[i]] = X[j][i]; X[j][i] = t; }
+    }
+    for (int i = 0; i < BS; ++i)
+        for (int j = 0; j < BS; ++j) M[i * BS + j] = X[i][j];
+    return det;
 #else
     real A[BB];
     memcpy(A, M, sizeof A);

@@ -1,0 +1,91 @@
+"""Multicolour ILU0 variant, host side (no GPU): the ordering rule exported by libopmgpu.so
+(opmgpu_multicolour_order) against its definition, and the oracle on the permuted system (what the
+GPU parity tests of the variant compare with).  The variant is the reference's ILU0 of P A P^T
+(compare the reference's own ilu_redblack option, opm/autodiff/ISTLSolver.hpp:207-209): its iteration
+counts are NOT the reference's natural-order counts and are never reported as parity."""
+import numpy as np
+
+from opm_simulators_legacy_b200.jacobian import synth_blackoil_jacobian, random_bcrs
+from opm_simulators_legacy_b200.solver import multicolour_order
+
+
+def greedy_reference(rp, ci):
+    """Definition: natural row order, smallest colour no already coloured neighbour (either direction) has."""
+    N = rp.size - 1
+    nbr = [set() for _ in range(N)]
+    for i in range(N):
+        for k in range(rp[i], rp[i + 1]):
+            j = int(ci[k])
+            if j != i:
+                nbr[i].add(j); nbr[j].add(i)
+    colour = -np.ones(N, dtype=np.int32)
+    for i in range(N):
+        used = {int(colour[j]) for j in nbr[i] if j < i}
+        c = 0
+        while c in used:
+            c += 1
+        colour[i] = c
+    return colour, nbr
+
+
+def permute_bcrs(rp, ci, v, n2p):
+    """BCRS of P A P^T (rows and columns renumbered by n2p, columns ascending) and, for every slot of
+    the permuted pattern, the slot of the original pattern it came from."""
+    N = rp.size - 1
+    rows = np.repeat(np.arange(N), np.diff(rp))
+    pr, pc = n2p[rows], n2p[ci]
+    order = np.lexsort((pc, pr))
+    prp = np.zeros(N + 1, dtype=np.int32)
+    np.cumsum(np.bincount(pr, minlength=N), out=prp[1:])
+    return prp, pc[order].astype(np.int32), np.ascontiguousarray(v[order]), order
+
+
+def test_cartesian_stencil_gets_red_black():
+    s = synth_blackoil_jacobian(7, 6, 5, perm="homogeneous")
+    rp, ci = s.rowptr.numpy(), s.colidx.numpy()
+    nc, colour, n2p = multicolour_order(rp, ci)
+    assert nc == 2
+    i, j, k = np.meshgrid(np.arange(7), np.arange(6), np.arange(5), indexing="ij")
+    cell = (i + 7 * (j + 6 * k)).ravel()
+    expect = np.empty(cell.size, dtype=np.int32)
+    expect[cell] = ((i + j + k) % 2).ravel()
+    assert np.array_equal(colour, expect)
+
+
+def test_ordering_follows_its_definition_on_general_patterns():
+    for seed, dense in ((1, 0), (2, 9), (3, 17)):
+        rp, ci, _ = random_bcrs(300, extra_per_row=2, seed=seed, dense_group=dense)
+        # make the pattern structurally nonsymmetric: drop a few strictly upper entries
+        rows = np.repeat(np.arange(300), np.diff(rp))
+        keep = ~((ci > rows) & ((rows * 7 + ci) % 5 == 0))
+        ci2 = ci[keep]
+        rp2 = np.zeros(301, dtype=np.int32)
+        np.cumsum(np.bincount(rows[keep], minlength=300), out=rp2[1:])
+        nc, colour, n2p = multicolour_order(rp2, ci2)
+        ref, nbr = greedy_reference(rp2, ci2)
+        assert np.array_equal(colour, ref) and nc == ref.max() + 1
+        if dense:
+            assert nc >= dense                      # a clique needs a colour per member
+        for i in range(300):
+            assert all(colour[j] != colour[i] for j in nbr[i])
+        # rows sorted by (colour, natural index)
+        p2n = np.argsort(n2p, kind="stable")
+        assert np.array_equal(np.sort(n2p), np.arange(300))
+        key = colour[p2n].astype(np.int64) * 300 + p2n
+        assert (np.diff(key) > 0).all()
+
+
+def test_oracle_on_the_permuted_system_solves_the_same_problem(oracle):
+    s = synth_blackoil_jacobian(12, 10, 8, perm="lognormal")
+    rp, ci, v, b = s.rowptr.numpy(), s.colidx.numpy(), s.vals.numpy(), s.rhs.numpy()
+    nc, colour, n2p = multicolour_order(rp, ci)
+    p2n = np.argsort(n2p)
+    prp, pci, pv, order = permute_bcrs(rp, ci, v, n2p)
+    xp, resp = oracle.solve_bcrs(prp, pci, pv, b.reshape(-1, 3)[p2n], reduction=1e-10)
+    xn, resn = oracle.solve_bcrs(rp, ci, v, b, reduction=1e-10)
+    assert resp["converged"] and resn["converged"]
+    x = np.empty_like(xp)
+    x[p2n] = xp
+    assert np.abs(x - xn).max() <= 1e-6 * np.abs(xn).max()
+    # a different preconditioner: the counts need not agree (and do not on this system)
+    assert resp["iterations"] != resn["iterations"]

@@ -34,6 +34,8 @@ def main():
     st = torch.cuda.Stream()
     torch.cuda.set_stream(st)
     g.use_torch_stream()
+    if os.environ.get("MB_MULTICOLOUR"):          # the flagged multicolour-ILU0 variant
+        g.set_ilu_ordering(True)
     t0 = time.time()
     g.set_pattern(s.rowptr.numpy(), s.colidx.numpy())
     tan = time.time() - t0
