@@ -179,10 +179,13 @@ int  opmgpu_solve_from_csc_blocks(opmgpu_handle h, int N, const opmgpu_csc block
 
 /* ---- block sizes other than 3 ----------------------------------------------------------------
  * The reference's dispatcher instantiates Impl<np,Scalar> for np = 2..6
- * (NewtonIterationBlackoilInterleaved.cpp:467-487, .hpp:73; np = 2: two-phase decks).  np = 3 runs
- * the pipelined kernels; np = 2 runs level-scheduled kernels with the same arithmetic (one launch
- * per dependency level: correct and bit-comparable, not tuned); np = 4..6 answer
- * OPMGPU_BAD_ARGUMENT.  opmgpu_set_block_size prepares the NEXT pattern for that block size (call it
+ * (NewtonIterationBlackoilInterleaved.cpp:467-487, .hpp:73; np = 2: two-phase decks, np >= 4: the
+ * polymer / solvent extensions).  np = 3 runs the pipelined kernels; np = 2, 4, 5, 6 run
+ * level-scheduled kernels with the same arithmetic (one launch per dependency level: correct and
+ * bit-comparable with the oracle of that block size, not tuned); the diagonal blocks are inverted as
+ * the reference's MatrixBlock does for that size (2, 3, 4: closed forms; 5, 6: dune's LU with
+ * thresholded row pivoting).  Any other np answers OPMGPU_BAD_ARGUMENT.
+ * opmgpu_set_block_size prepares the NEXT pattern for that block size (call it
  * before opmgpu_set_pattern_bcrs; opmgpu_solve_from_csc_blocks_np does both itself).  All arrays are
  * the np-sized analogues of the np = 3 entry points: vals[nnzb*np*np], rhs/x[N*np] cell-major,
  * blocks[np*np] with blocks[p1*np+p2] = d(eq p1)/d(var p2), rhs_eqmajor / dx_varmajor[np*N]. */

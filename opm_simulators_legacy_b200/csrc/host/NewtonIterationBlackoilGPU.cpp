@@ -180,7 +180,7 @@ NewtonIterationBlackoilGPU::computeNewtonIncrement(const LinearisedBlackoilResid
 {
     const int np = (int)residual.material_balance_eq.size();
     // the reference's switch instantiates Impl<np,Scalar> for np = 2..6 (...Interleaved.cpp:467-487)
-    if (np != 2 && np != 3) throw std::logic_error("NewtonIterationBlackoilGPU: np == 2 and np == 3 are built");
+    if (np < 2 || np > 6) throw std::logic_error("NewtonIterationBlackoilGPU: np out of the reference's range 2..6");
     std::vector<ADB> eqs(residual.material_balance_eq.begin(), residual.material_balance_eq.end());
     const bool hasWells = residual.well_flux_eq.size() > 0;
     std::vector<ADB> elim_eqs;
@@ -203,7 +203,8 @@ NewtonIterationBlackoilGPU::computeNewtonIncrement(const LinearisedBlackoilResid
     b.reserve((size_t)np * N);
     for (int p = 0; p < np; ++p) b.insert(b.end(), eqs[p].val.begin(), eqs[p].val.end());
     SolutionVector dx((size_t)np * N, 0.0);
-    const double scale[3] = {residual.matbalscale[0], residual.matbalscale[1], np > 2 ? residual.matbalscale[2] : 1.0};
+    double scale[6] = {1.0, 1.0, 1.0, 1.0, 1.0, 1.0};
+    for (int p = 0; p < np && p < (int)residual.matbalscale.size(); ++p) scale[p] = residual.matbalscale[p];
     // the reference's dispatcher (...Interleaved.cpp:467-487): the float instance when the residual asks
     // for it (restarted GMRES exists for the double instance only; that combination stays in double)
     if (opmgpu_set_precision(handle_, residual.singlePrecision && !parameters_.newton_use_gmres) != OPMGPU_OK)

@@ -375,6 +375,16 @@ struct opmgpu_solver {
         if (r__ != ncclSuccess) return h->nccl_fail(r__, #call);          \
     } while (0)
 
+// block sizes of the level-scheduled path (generic_np.cuh): NPV is the compile-time block size inside CALL
+#define NP_DISPATCH(np, CALL)                                             \
+    switch (np) {                                                         \
+    case 2: { constexpr int NPV = 2; CALL; } break;                       \
+    case 4: { constexpr int NPV = 4; CALL; } break;                       \
+    case 5: { constexpr int NPV = 5; CALL; } break;                       \
+    case 6: { constexpr int NPV = 6; CALL; } break;                       \
+    default: return h->bad("block size not built");                       \
+    }
+
 #define CK(call)                                                          \
     do {                                                                  \
         cudaError_t e__ = (call);                                         \
@@ -631,7 +641,7 @@ int encode(opmgpu_handle h, size_t n, const T* in, double* out)
 
 int ensure_vectors(opmgpu_handle h)
 {
-    const size_t n = (size_t)h->N * 3;
+    const size_t n = (size_t)h->N * std::max(3, h->np_req);          // np = 4..6: longer vectors
     CK(h->d_x.ensure(n)); CK(h->d_r.ensure(n)); CK(h->d_rt.ensure(n)); CK(h->d_p.ensure(n));
     CK(h->d_v.ensure(n)); CK(h->d_t.ensure(n)); CK(h->d_y.ensure(n + (size_t)h->n_ghost * 3)); CK(h->d_yL.ensure(n));
     CK(h->d_vU.ensure(n)); CK(h->d_tmp.ensure(n + (size_t)h->n_ghost * 3)); CK(h->d_tmp2.ensure(n));
@@ -783,7 +793,7 @@ int set_pattern(opmgpu_handle h, int N, int nnzb, const int* rowptr, const int* 
         if ((rc = upload(h, h->d_lvlU_rows, rows))) return rc;
         CK(cudaStreamSynchronize(h->stream));
     }
-    CK(h->d_lu.ensure((size_t)nnzb * 9));
+    CK(h->d_lu.ensure((size_t)nnzb * std::max(9, h->np_req * h->np_req)));
     if ((rc = ensure_vectors(h))) return rc;
     CK(h->d_flags.ensure(N));
     CK(cudaMemsetAsync(h->d_flags.p, 0, sizeof(int) * (size_t)N, h->stream));
@@ -1054,8 +1064,8 @@ template <class T>
 int np_spmv_with_dots(opmgpu_handle h, int mode, const T* x, T* y, const T* w1)
 {
     const size_t n = (size_t)h->N * h->np;
-    np_spmv_kernel<2, T><<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->N, h->d_rowptr.p, h->d_colidx.p,
-                                                                            static_cast<const T*>(h->d_vals), x, y);
+    NP_DISPATCH(h->np, (np_spmv_kernel<NPV, T><<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->N, h->d_rowptr.p, h->d_colidx.p,
+                                                                            static_cast<const T*>(h->d_vals), x, y)));
     h->launches++;
     if (mode == 1) {
         dot_to_slot_kernel<T><<<kVecBlocks, 256, 0, h->stream>>>(n, w1, (const T*)y, h->d_S.p, S_H, h->ws());
@@ -1126,8 +1136,8 @@ int np_factor(opmgpu_handle h, int* bad_row)
     for (size_t l = 0; l + 1 < lp.size(); ++l) {
         const int n = lp[l + 1] - lp[l];
         if (n <= 0) continue;
-        np_factor_level_kernel<2, T><<<(n + 127) / 128, 128, 0, h->stream>>>(h->d_lvl_rows.p, lp[l], lp[l + 1], h->d_rowptr.p,
-                                                                              h->d_colidx.p, h->d_diag.p, lu, h->d_bad.p);
+        NP_DISPATCH(h->np, (np_factor_level_kernel<NPV, T><<<(n + 127) / 128, 128, 0, h->stream>>>(h->d_lvl_rows.p, lp[l], lp[l + 1], h->d_rowptr.p,
+                                                                              h->d_colidx.p, h->d_diag.p, lu, h->d_bad.p)));
         h->launches++;
     }
     CK(cudaGetLastError());
@@ -1379,16 +1389,16 @@ int np_apply(opmgpu_handle h, double w, const T* d, T* v)
     for (size_t l = 0; l + 1 < lp.size(); ++l) {
         const int n = lp[l + 1] - lp[l];
         if (n <= 0) continue;
-        np_sweep_level_kernel<2, T, true><<<(n + 127) / 128, 128, 0, h->stream>>>(h->d_lvl_rows.p, lp[l], lp[l + 1], h->d_rowptr.p,
-            h->d_colidx.p, h->d_diag.p, lu, d, work, v, (T)w, scale);
+        NP_DISPATCH(h->np, (np_sweep_level_kernel<NPV, T, true><<<(n + 127) / 128, 128, 0, h->stream>>>(h->d_lvl_rows.p, lp[l], lp[l + 1], h->d_rowptr.p,
+            h->d_colidx.p, h->d_diag.p, lu, d, work, v, (T)w, scale)));
         h->launches++;
     }
     const std::vector<int>& up = h->lvlU_ptr;
     for (size_t l = 0; l + 1 < up.size(); ++l) {
         const int n = up[l + 1] - up[l];
         if (n <= 0) continue;
-        np_sweep_level_kernel<2, T, false><<<(n + 127) / 128, 128, 0, h->stream>>>(h->d_lvlU_rows.p, up[l], up[l + 1], h->d_rowptr.p,
-            h->d_colidx.p, h->d_diag.p, lu, d, work, v, (T)w, scale);
+        NP_DISPATCH(h->np, (np_sweep_level_kernel<NPV, T, false><<<(n + 127) / 128, 128, 0, h->stream>>>(h->d_lvlU_rows.p, up[l], up[l + 1], h->d_rowptr.p,
+            h->d_colidx.p, h->d_diag.p, lu, d, work, v, (T)w, scale)));
         h->launches++;
     }
     CK(cudaGetLastError());
@@ -2740,7 +2750,7 @@ int opmgpu_solve_from_csc_blocks(opmgpu_handle h, int N, const opmgpu_csc blocks
     return h->bad("sparsity pattern changed during the call");
 }
 
-// ---- block sizes other than 3 (the reference's Impl<np,Scalar>, np = 2..6): np = 2 is built -------
+// ---- block sizes other than 3 (the reference's Impl<np,Scalar>, np = 2..6) ---------------------------
 }  // extern "C"
 namespace {
 struct NpGuard {          // the block size of the call in flight; back to 3 on every way out
@@ -2750,9 +2760,10 @@ struct NpGuard {          // the block size of the call in flight; back to 3 on 
 };
 int np_check(opmgpu_handle h, int np)
 {
-    if (np != 2) { h->err = "block size np = " + std::to_string(np) + " is not built (np = 2 and 3 are)"; return OPMGPU_BAD_ARGUMENT; }
+    if (np < 2 || np > 6) { h->err = "block size np = " + std::to_string(np) + " is not built (the reference instantiates np = 2..6)"; return OPMGPU_BAD_ARGUMENT; }
     if (h->multi || h->world > 1) return h->bad("np != 3 exists for plain single-GPU handles");
     if (!h->have_pattern || h->operator_only) return h->bad("set the pattern first");
+    if (np != h->np_req) return h->bad("the pattern was prepared for another block size: opmgpu_set_block_size before opmgpu_set_pattern_bcrs");
     if (h->lvlU_ptr.empty()) return h->bad("the pattern was not prepared for this block size: opmgpu_set_block_size before opmgpu_set_pattern_bcrs");
     return 0;
 }
@@ -2807,7 +2818,7 @@ extern "C" {
 int opmgpu_set_block_size(opmgpu_handle h, int np)
 {
     if (!h) return OPMGPU_BAD_ARGUMENT;
-    if (np != 2 && np != 3) { h->err = "block size np = " + std::to_string(np) + " is not built (np = 2 and 3 are)"; return OPMGPU_BAD_ARGUMENT; }
+    if (np < 2 || np > 6) { h->err = "block size np = " + std::to_string(np) + " is not built (the reference instantiates np = 2..6)"; return OPMGPU_BAD_ARGUMENT; }
     if (h->multi || h->world > 1) return np == 3 ? OPMGPU_OK : h->bad("np != 3 exists for plain single-GPU handles");
     if (np != h->np_req) { h->np_req = np; h->have_pattern = false; h->have_values = false; h->have_factors = false; }
     return OPMGPU_OK;
@@ -2881,7 +2892,7 @@ int opmgpu_solve_from_csc_blocks_np(opmgpu_handle h, int N, int np, const opmgpu
 {
     if (!h || !blocks || !matbalscale || !rhs_eqmajor || !dx_varmajor || !params || !result || N < 1) return OPMGPU_BAD_ARGUMENT;
     if (np == 3) return opmgpu_solve_from_csc_blocks(h, N, blocks, matbalscale, rhs_eqmajor, dx_varmajor, params, result);
-    if (np != 2) { h->err = "block size np = " + std::to_string(np) + " is not built (np = 2 and 3 are)"; return OPMGPU_BAD_ARGUMENT; }
+    if (np < 2 || np > 6) { h->err = "block size np = " + std::to_string(np) + " is not built (the reference instantiates np = 2..6)"; return OPMGPU_BAD_ARGUMENT; }
     if (h->multi || h->world > 1) return h->bad("np != 3 exists for plain single-GPU handles");
     if (params->newton_use_gmres) return h->bad("restarted GMRES exists for np = 3 only");
     std::memset(result, 0, sizeof *result);

@@ -291,3 +291,24 @@ def random_bcrs(N: int, extra_per_row: int = 3, seed: int = 1, dense_group: int 
     dmask = rows == cols
     vals[dmask] += (np.eye(3).reshape(1, 9)) * (diag_boost * absrow[rows[dmask]]).reshape(-1, 1) / 3.0
     return rowptr, cols, np.ascontiguousarray(vals)
+
+
+def block_system_np(rowptr, colidx, np_: int, seed: int = 1, diag_boost: float = 3.0):
+    """Values and right-hand side of an np_ x np_ block system on a given BCRS pattern (block sizes
+    4..6: the reference's Impl<np,Scalar> for the polymer / solvent extensions,
+    opm/autodiff/NewtonIterationBlackoilInterleaved.cpp:467-487): random blocks, block rows made
+    diagonally dominant.  Returns vals[nnzb, np_*np_], rhs[N, np_], xstar[N, np_] (numpy)."""
+    rowptr = np.asarray(rowptr); colidx = np.asarray(colidx)
+    N = rowptr.size - 1
+    rng = np.random.default_rng(seed)
+    rows = np.repeat(np.arange(N), np.diff(rowptr))
+    vals = rng.standard_normal((colidx.size, np_ * np_))
+    absrow = np.zeros(N)
+    np.add.at(absrow, rows, np.abs(vals).sum(1))
+    dmask = rows == colidx
+    vals[dmask] += np.eye(np_).reshape(1, -1) * (diag_boost * absrow[rows[dmask]]).reshape(-1, 1) / np_
+    xstar = rng.standard_normal((N, np_))
+    rhs = np.zeros((N, np_))
+    prod = np.einsum("kij,kj->ki", vals.reshape(-1, np_, np_), xstar[colidx])
+    np.add.at(rhs, rows, prod)
+    return np.ascontiguousarray(vals), rhs, xstar

@@ -209,7 +209,7 @@ class GpuLinearSolver:
 
     # -- block sizes other than 3 (np = 2: two-phase decks) ------------------------------------
     def set_block_size(self, np_: int):
-        """Prepare the NEXT pattern for block size np_ (2 or 3); call before set_pattern."""
+        """Prepare the NEXT pattern for block size np_ (2..6); call before set_pattern."""
         self._check(self.lib.opmgpu_set_block_size(self.h, int(np_)))
 
     def spmv_np(self, np_, vals, x):
@@ -492,13 +492,13 @@ class NewtonIterationBlackoilGPU:
         return self.parallelInformation_
 
     def computeNewtonIncrement(self, residual: LinearisedBlackoilResidual) -> np.ndarray:
-        """...Interleaved.cpp:202-292 (np = 3; the double or the float instance as
+        """...Interleaved.cpp:202-292 (np = 2..6; the double or the float instance as
         residual.singlePrecision asks, :467-487).  Returns dx ordered
         [p(N), sw(N), xvar(N), qs(nw*np), bhp(nw)]."""
         import scipy.sparse as sp
         npz = len(residual.material_balance_eq)
-        if npz not in (2, 3):
-            raise NotImplementedError("NewtonIterationBlackoilGPU: np == 2 and np == 3 are built")
+        if not 2 <= npz <= 6:
+            raise NotImplementedError("NewtonIterationBlackoilGPU: np outside the reference's range 2..6")
         eqs = list(residual.material_balance_eq)
         has_wells = residual.well_flux_eq is not None and residual.well_flux_eq.size() > 0
         elim = []

@@ -230,12 +230,17 @@ f64 = _Oracle("liboracle.so", np.float64)      # the reference's Impl<3,double>
 f32 = _Oracle("liboracle_f32.so", np.float32)  # the reference's Impl<3,float> (singlePrecision)
 np2 = _Oracle("liboracle_np2.so", np.float64, bs=2)          # Impl<2,double>: two-phase decks
 np2_f32 = _Oracle("liboracle_np2_f32.so", np.float32, bs=2)  # Impl<2,float>
+# Impl<4..6,Scalar> (polymer / solvent extensions of the black-oil model)
+_npN = {(b, f): _Oracle(f"liboracle_np{b}{'_f32' if f else ''}.so", np.float32 if f else np.float64, bs=b)
+        for b in (4, 5, 6) for f in (False, True)}
 
 
 def instance(single_precision=False, np_=3):
     if np_ == 2:
         return np2_f32 if single_precision else np2
-    assert np_ == 3, "the oracle restates block sizes 2 and 3"
+    if np_ in (4, 5, 6):
+        return _npN[(np_, bool(single_precision))]
+    assert np_ == 3, "the oracle restates block sizes 2..6"
     return f32 if single_precision else f64
 
 

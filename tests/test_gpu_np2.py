@@ -145,11 +145,13 @@ def test_np2_general_pattern_and_errors(np2_solver, oracle):
             v2[k] = 0.0
     _, bad_ref = oracle.np2.ilu0_factor(rp, ci, v2)
     assert g.ilu0_np(2, v2)[2] == bad_ref == row
-    # block sizes that are not built
+    # block sizes outside the reference's range 2..6, and one the pattern was not prepared for
     with pytest.raises(ValueError):
-        g.set_block_size(4)
+        g.set_block_size(7)
     with pytest.raises(ValueError):
-        g.solve_bcrs_np(5, v, b)
+        g.set_block_size(1)
+    with pytest.raises(ValueError):
+        g.solve_bcrs_np(5, np.zeros((len(ci), 25)), np.zeros((500, 5)))
     # a pattern that was not prepared for np = 2
     h = GpuLinearSolver(0)
     h.set_pattern(rp, ci)

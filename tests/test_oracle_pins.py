@@ -290,3 +290,52 @@ def test_np2_oracle_pins(oracle):
     x32, r32 = oracle.np2_f32.solve_bcrs(rp, ci, v, b)
     x64, r64 = oracle.np2.solve_bcrs(rp, ci, v, b)
     assert x32.dtype == np.float32 and r32["iterations"] == r64["iterations"]
+
+
+# ---- block sizes 4..6 (liboracle_np<bs>*.so: the same file with -DORACLE_BS=4 / 5 / 6) ----------------
+@pytest.mark.parametrize("bs", [4, 5, 6])
+def test_np456_oracle_pins(oracle, bs):
+    """The block inverse of each size against numpy (4x4: OPM's closed form; 5, 6: dune's LU with
+    thresholded row pivoting, including a block that needs the row swaps and a singular one), scipy
+    bsr SpMV, a direct solve, the block-tridiagonal known answer (ILU0 exact), and the float build."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spl
+    from opm_simulators_legacy_b200.jacobian import synth_blackoil_jacobian, block_system_np
+    O, O32 = oracle.instance(False, bs), oracle.instance(True, bs)
+    rng = np.random.default_rng(bs)
+    one_rp, one_ci = np.array([0, 1], dtype=np.int32), np.array([0], dtype=np.int32)
+    # ILU0 of a 1 x 1 block matrix = the block inverse
+    for trial in range(20):
+        A = rng.standard_normal((bs, bs)) + (3.0 if trial % 2 else 0.0) * np.eye(bs)
+        if trial >= 16:
+            A[0, 0] = 0.0                       # forces dune's row swap at the first pivot (no-op for the 4x4 closed form)
+        if trial == 19:
+            A[2, 0] = A[1, 0] = 0.0             # and again at a later column
+        lu, bad = O.ilu0_factor(one_rp, one_ci, A.reshape(1, -1))
+        assert bad == -1
+        assert np.abs(lu.reshape(bs, bs) @ A - np.eye(bs)).max() <= 1e-10 * np.linalg.cond(A)
+        assert np.abs(lu.reshape(bs, bs) - np.linalg.inv(A)).max() <= 1e-10 * np.linalg.cond(A) * np.abs(np.linalg.inv(A)).max()
+    S = np.ones((bs, bs))                        # singular: reported as the failing row
+    _, bad = O.ilu0_factor(one_rp, one_ci, S.reshape(1, -1))
+    assert bad == 0
+    s = synth_blackoil_jacobian(9, 8, 5, perm="homogeneous")
+    rp, ci = s.rowptr.numpy(), s.colidx.numpy()
+    v, b, xstar = block_system_np(rp, ci, bs, seed=3)
+    N = s.N
+    A = sp.bsr_matrix((v.reshape(-1, bs, bs), ci, rp), shape=(bs * N, bs * N))
+    y = O.spmv(rp, ci, v, xstar)
+    assert y.shape == (N, bs) and np.abs(y.ravel() - A @ xstar.ravel()).max() <= 1e-12 * np.abs(y).max()
+    xs, res = O.solve_bcrs(rp, ci, v, b, reduction=1e-12, maxiter=400)
+    assert res["converged"] == 1
+    assert np.abs(xs - xstar).max() <= 1e-8 * np.abs(xstar).max()
+    ref = spl.spsolve(A.tocsc(), b.ravel())
+    assert np.abs(xs.ravel() - ref).max() <= 1e-8 * np.abs(ref).max()
+    # block tridiagonal: ILU0 is the exact factorisation, one iteration with w = 1
+    t = synth_blackoil_jacobian(30, 1, 1, perm="homogeneous")
+    vt, bt, _ = block_system_np(t.rowptr.numpy(), t.colidx.numpy(), bs, seed=4)
+    _, rt = O.solve_bcrs(t.rowptr.numpy(), t.colidx.numpy(), vt, bt, reduction=1e-10, relax=1.0)
+    assert rt["iterations"] == 1 and rt["converged"] == 1
+    x32, r32 = O32.solve_bcrs(rp, ci, v, b)
+    x64, r64 = O.solve_bcrs(rp, ci, v, b)
+    assert x32.dtype == np.float32 and r32["iterations"] == r64["iterations"]
+    assert np.abs(x32 - x64).max() <= 1e-2 * np.abs(x64).max()
