@@ -21,7 +21,7 @@ static SparseCSC fromDense(const std::vector<double>& d, int r, int c)
 }
 
 // np material-balance equations (3: black oil; 2: a two-phase deck, the reference's Impl<2,Scalar>) + wells
-static int run_case(const std::string& devices, const int np)
+static int run_case(const std::string& devices, const int np, bool redblack = false)
 {
     const int N = 60, nw = 2, ne = np + 2;
     std::vector<int> sizes(ne, N);
@@ -60,6 +60,7 @@ static int run_case(const std::string& devices, const int np)
     std::map<std::string, std::string> kv = {{"linear_solver_reduction", "1e-12"}, {"linear_solver_maxiter", "200"},
                                              {"require_full_sparsity_pattern", "true"}};
     if (!devices.empty()) kv["gpu_devices"] = devices;
+    if (redblack) kv["ilu_redblack"] = "true";      // the multicolour variant behind the reference's key
     NewtonIterationBlackoilGPU solver{ParameterGroup(kv)};
     const auto dx = solver.computeNewtonIncrement(res);
     // dense reference: Gaussian elimination on the full system
@@ -81,7 +82,7 @@ static int run_case(const std::string& devices, const int np)
     }
     double err = 0.0, ref = 0.0;
     for (int i = 0; i < nt; ++i) { err = std::fmax(err, std::fabs(dx[i] - x[i])); ref = std::fmax(ref, std::fabs(x[i])); }
-    std::printf("host_selftest[%s, np = %d]: size %zu iterations %d max_abs_err %.3e (ref %.3e)\n", devices.empty() ? "1 GPU" : devices.c_str(), np, dx.size(), solver.iterations(), err, ref);
+    std::printf("host_selftest[%s, np = %d%s]: size %zu iterations %d max_abs_err %.3e (ref %.3e)\n", devices.empty() ? "1 GPU" : devices.c_str(), np, redblack ? ", ilu_redblack" : "", dx.size(), solver.iterations(), err, ref);
     // error contract: not converged -> LinearSolverProblem, iterations still reported
     bool threw = false;
     std::map<std::string, std::string> kv2 = {{"linear_solver_reduction", "1e-14"}, {"linear_solver_maxiter", "1"},
@@ -98,6 +99,11 @@ int main(int argc, char** argv)
 {
     const std::string devices = argc > 1 ? argv[1] : "";
     int rc = run_case(devices, 3);
-    if (devices.find(',') == std::string::npos) rc |= run_case(devices, 2);      // np = 2 exists for single-GPU handles
+    if (devices.find(',') == std::string::npos) {      // single-GPU handles: the other block sizes and the multicolour variant
+        rc |= run_case(devices, 2);
+        rc |= run_case(devices, 4);
+        rc |= run_case(devices, 6);
+        rc |= run_case(devices, 3, true);
+    }
     return rc;
 }

@@ -47,7 +47,7 @@ _PARAM_KEYS = {
 }
 # keys of FlowLinearSolverParameters this solver accepts only at their default value
 _UNSUPPORTED = {"linear_solver_use_amg": False, "ilu_fillin_level": 0,
-                "ilu_milu": "ILU", "ilu_redblack": False}
+                "ilu_milu": "ILU"}
 
 
 def make_params(param: Optional[dict] = None, **kw) -> L.Params:
@@ -484,6 +484,14 @@ class NewtonIterationBlackoilGPU:
         self.parallelInformation_ = parallelInformation      # empty boost::any: serial branches
         self.iterations_ = 0
         self._solver = GpuLinearSolver(device)
+        # ilu_redblack (ISTLSolver.hpp:207-209): the ILU0 of a colour-sorted reordering -- here the library's
+        # multicolour variant (greedy natural-order colouring, not the reference's Welsh-Powell / sphere
+        # reordering of opm-simulators' GraphColoring.hpp: iteration counts match neither reference ordering)
+        rb = (param or {}).get("ilu_redblack", False)
+        if isinstance(rb, str):
+            rb = rb.lower() in ("1", "true", "yes")
+        if rb:
+            self._solver.set_ilu_ordering(True)
 
     def iterations(self) -> int:
         return self.iterations_

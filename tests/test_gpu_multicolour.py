@@ -183,3 +183,33 @@ def test_multicolour_is_refused_where_it_is_not_built():
             g.set_pattern(rp, ci)
     finally:
         g.close()
+
+
+def test_ilu_redblack_key_selects_the_variant_in_the_drop_in(oracle):
+    """ilu_redblack (FlowLinearSolverParameters, ISTLSolver.hpp:207-209) behind NewtonIterationBlackoilGPU."""
+    import scipy.sparse as sp
+    from opm_simulators_legacy_b200.solver import NewtonIterationBlackoilGPU, ADB, LinearisedBlackoilResidual
+    s = synth_blackoil_jacobian(14, 11, 7, perm="lognormal")
+    blocks, N = s.csc_blocks(), s.N
+    rhs = s.rhs_eqmajor_unscaled.numpy()
+    eqs = []
+    for p1 in range(3):
+        jac = [sp.csc_matrix((blocks[p1 * 3 + p2][2], blocks[p1 * 3 + p2][1], blocks[p1 * 3 + p2][0]), shape=(N, N)) for p2 in range(3)]
+        eqs.append(ADB(rhs[p1 * N:(p1 + 1) * N].copy(), jac))
+    res = LinearisedBlackoilResidual(eqs, matbalscale=s.matbalscale, singlePrecision=False)
+    nat = NewtonIterationBlackoilGPU({})
+    rb = NewtonIterationBlackoilGPU({"ilu_redblack": "true"})
+    dx_nat, dx_rb = nat.computeNewtonIncrement(res), rb.computeNewtonIncrement(res)
+    orp, oci, ov = oracle.interleave(N, blocks, s.matbalscale)
+    nc, colour, n2p = multicolour_order(orp, oci)
+    prp, pci, pv, order = permute_bcrs(orp, oci, ov, n2p)
+    p2n = np.argsort(n2p)
+    rhs_cell = (rhs.reshape(3, N) * np.asarray(s.matbalscale).reshape(3, 1)).T
+    xp, ref = oracle.solve_bcrs(prp, pci, pv, rhs_cell[p2n].reshape(-1))
+    assert rb.iterations() == ref["iterations"]
+    assert nat.iterations() == oracle.solve_from_csc_blocks(N, blocks, s.matbalscale, rhs)[1]["iterations"]
+    # two preconditioners, one system: both increments reduce the true residual by linear_solver_reduction
+    for dx in (dx_nat, dx_rb):
+        x_cell = np.ascontiguousarray(dx.reshape(3, N).T)
+        r = rhs_cell - oracle.spmv(orp, oci, ov, x_cell)
+        assert np.linalg.norm(r) <= 1.0001e-2 * np.linalg.norm(rhs_cell)
