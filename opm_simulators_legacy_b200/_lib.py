@@ -12,6 +12,13 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # OPMGPU_LIB: alternative build of the same library (kernel experiments), else the in-tree one
 LIB_PATH = os.environ.get("OPMGPU_LIB") or os.path.join(_HERE, "libopmgpu.so")
+# the experiments build (make exp; -DOPMGPU_EXPERIMENTS): slower kernel variants kept for A/B
+# measurements, the tuning switches of DESIGN.md section 10, tracing entry points.  Never the product.
+EXP_LIB_PATH = os.path.join(_HERE, "libopmgpu_exp.so")
+# test hooks (include/opm_gpu_solver_testhooks.h): in the shipping library / in the experiments build only
+TEST_HOOKS = ["opmgpu_debug_analyse_only", "opmgpu_debug_host_program_apply", "opmgpu_debug_host_factor_program",
+              "opmgpu_debug_partition", "opmgpu_debug_set_watchdog_word"]
+EXP_HOOKS = ["opmgpu_debug_host_col_apply", "opmgpu_debug_trace_apply", "opmgpu_debug_gtrace_apply"]
 
 # every symbol include/opm_gpu_solver.h declares (tests check the export list against this)
 EXPORTS = [
@@ -62,6 +69,18 @@ class Csc(C.Structure):
 
 
 _lib = None
+_exp = None
+
+
+def load_experiments():
+    """Load libopmgpu_exp.so (same C ABI plus the experiment hooks); for A/B tools and the tests of
+    the experimental kernel variants only."""
+    global _exp
+    if _exp is None:
+        if not os.path.exists(EXP_LIB_PATH):
+            raise RuntimeError(f"{EXP_LIB_PATH} is missing: make -C opm_simulators_legacy_b200/csrc exp")
+        _exp = _bind(C.CDLL(EXP_LIB_PATH))
+    return _exp
 
 
 def load():
@@ -72,7 +91,11 @@ def load():
     if not os.path.exists(LIB_PATH):
         raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                            "(or make -C opm_simulators_legacy_b200/csrc). There is no CPU fallback.")
-    lib = C.CDLL(LIB_PATH)
+    _lib = _bind(C.CDLL(LIB_PATH))
+    return _lib
+
+
+def _bind(lib):
     H = C.c_void_p
     ip, dp, vp = C.POINTER(C.c_int), C.POINTER(C.c_double), C.c_void_p
     PP, RP = C.POINTER(Params), C.POINTER(Result)
@@ -121,5 +144,4 @@ def load():
     for name, (res, args) in sig.items():
         f = getattr(lib, name)
         f.restype, f.argtypes = res, args
-    _lib = lib
     return lib

@@ -870,7 +870,7 @@ void analyse_pattern(int N, const int* rowptr, const int* colidx, int P, Pattern
         if (cartesian) {
             int pa, pb, ca, cb;
             choose_tiling(nx, ny, nz, caps, pa, pb, ca, cb);
-            if (const char* e = std::getenv("OPMGPU_TILING")) {       // experiments: "AxB" or "AxB/CxD" (cluster shape)
+            if (const char* e = exp_env("OPMGPU_TILING")) {       // experiments: "AxB" or "AxB/CxD" (cluster shape)
                 int a = 0, b = 0, c = 1, d = 1;
                 const int got = std::sscanf(e, "%dx%d/%dx%d", &a, &b, &c, &d);
                 if (got < 4) { c = d = 1; }
@@ -884,8 +884,8 @@ void analyse_pattern(int N, const int* rowptr, const int* colidx, int P, Pattern
             // wavefront order (ascending i0 + j0), so that a CTA walks its tiles one after the other
             // while the wavefront moves on; tile-to-tile dependencies all go through push slots.
             int rounds = 1;
-            if (cs == 1 && ((nx + pa - 1) / pa) * ((ny + pb - 1) / pb) > kLeanStepRows && !std::getenv("OPMGPU_TILING") &&
-                !std::getenv("OPMGPU_ONE_TILE_PER_CTA")) {
+            if (cs == 1 && ((nx + pa - 1) / pa) * ((ny + pb - 1) / pb) > kLeanStepRows && !exp_env("OPMGPU_TILING") &&
+                !exp_env("OPMGPU_ONE_TILE_PER_CTA")) {
                 double best = 1e300;
                 for (int a = 1; a <= nx; ++a)
                     for (int b = 1; b <= ny; ++b) {
@@ -970,7 +970,7 @@ void analyse_pattern(int N, const int* rowptr, const int* colidx, int P, Pattern
     // the flag-synchronised tile kernel's program is only needed when the pipelined factorisation
     // is not available (or switched off): built on demand from the partition kept here
     out.owner_ = owner; out.level_lower_ = lvlL;
-    if (force_simple || !out.pipeF.valid || std::getenv("OPMGPU_FACTOR_TILE") || std::getenv("OPMGPU_FACTOR_BY_LEVELS")) {
+    if (force_simple || !out.pipeF.valid || exp_env("OPMGPU_FACTOR_TILE") || exp_env("OPMGPU_FACTOR_BY_LEVELS")) {
         build_tile_factor_program(rowptr, colidx, out);
         tick("tile-kernel factorisation program");
     }

@@ -14,7 +14,15 @@
 //     ParallelOverlappingILU0::apply), so a CTA streams its part of the factors linearly.
 #pragma once
 #include <cstdint>
+#include <cstdlib>
 #include <vector>
+
+// tuning switches of experiments exist only in builds with -DOPMGPU_EXPERIMENTS (libopmgpu_exp.so)
+#ifdef OPMGPU_EXPERIMENTS
+static inline const char* exp_env(const char* name) { return std::getenv(name); }
+#else
+static inline const char* exp_env(const char*) { return nullptr; }
+#endif
 
 namespace opmgpu {
 

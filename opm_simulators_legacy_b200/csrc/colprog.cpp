@@ -1,5 +1,6 @@
 // See colprog.hpp.  Plain C++17, no CUDA: runs once per sparsity pattern.
 #include "colprog.hpp"
+#include "analysis.hpp"      // exp_env
 
 #include <algorithm>
 #include <cmath>
@@ -79,7 +80,7 @@ void build_col_program(int N, const int* rowptr, const int* colidx, const std::v
     ColGeom best_g = {};
     double best = 1e300;
     Shape forced = {0, 0, 0, 0};
-    if (const char* e = std::getenv("OPMGPU_COL_SHAPE")) {          // experiments: "PWxPH/TAxTB"
+    if (const char* e = exp_env("OPMGPU_COL_SHAPE")) {          // experiments: "PWxPH/TAxTB"
         if (std::sscanf(e, "%dx%d/%dx%d", &forced.pw, &forced.ph, &forced.ta, &forced.tb) != 4) forced = {0, 0, 0, 0};
         if (forced.pw < 1 || forced.ph < 1 || forced.pw * forced.ph > 32 || forced.ta < 1 || forced.tb < 1) forced = {0, 0, 0, 0};
     }

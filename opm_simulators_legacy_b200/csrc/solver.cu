@@ -10,7 +10,6 @@
 #include "sweep_pipe.cuh"
 #include "factor_pipe.cuh"
 #include "colprog.hpp"
-#include "sweep_col.cuh"
 #include "spmv_tma.cuh"
 #include "gmres.cuh"
 #include "generic_np.cuh"
@@ -34,6 +33,15 @@
 #include <string>
 #include <thread>
 #include <vector>
+
+// Experiments -- slower kernel variants kept for A/B measurements (column-owned sweeps, level-by-level
+// factorisation, ...), tuning switches and the tracing entry points -- exist only in builds with
+// -DOPMGPU_EXPERIMENTS (`make exp` -> libopmgpu_exp.so, loaded with OPMGPU_LIB).  The shipping
+// library reads none of those switches and has one path per pattern class.
+// (exp_env, analysis.hpp: getenv in such builds, nullptr otherwise.)
+#ifdef OPMGPU_EXPERIMENTS
+#include "sweep_col.cuh"
+#endif
 
 using namespace opmgpu;
 
@@ -515,7 +523,7 @@ int upload_pipe(opmgpu_handle h, const PipeProgram& p, PipeDevMem& d)
     const size_t per_stage = (size_t)d.stage_bytes + d.rhs_bytes;
     int S = (size_t)h->max_smem_optin > fixed ? (int)(((size_t)h->max_smem_optin - fixed) / per_stage) : 0;
     d.nstages = std::min(S, kPipeMaxStages);
-    if (const char* e = std::getenv("OPMGPU_PIPE_STAGES")) d.nstages = std::max(kPipeGroups, std::min(d.nstages, std::atoi(e)));
+    if (const char* e = exp_env("OPMGPU_PIPE_STAGES")) d.nstages = std::max(kPipeGroups, std::min(d.nstages, std::atoi(e)));
     d.smem = pipe_smem_bytes(d.nstages, d.stage_bytes, d.rhs_bytes, d.cx_bytes);
     return 0;
 }
@@ -547,6 +555,7 @@ int upload_factor_pipe(opmgpu_handle h, const FactorPipeProgram& p, FactorPipeDe
     return 0;
 }
 
+#ifdef OPMGPU_EXPERIMENTS
 int upload_col(opmgpu_handle h, const ColProgram& p, ColDevMem& d)
 {
     int rc;
@@ -555,7 +564,7 @@ int upload_col(opmgpu_handle h, const ColProgram& p, ColDevMem& d)
     d.nvalL = p.valL_src.size(); d.nvalU = p.valU_src.size();
     d.nstagesL = col_stage_count(p.g, false, (size_t)h->max_smem_optin);
     d.nstagesU = col_stage_count(p.g, true, (size_t)h->max_smem_optin);
-    if (const char* e = std::getenv("OPMGPU_COL_STAGES")) {
+    if (const char* e = exp_env("OPMGPU_COL_STAGES")) {
         d.nstagesL = std::max(2, std::min(d.nstagesL, std::atoi(e))); d.nstagesU = std::max(2, std::min(d.nstagesU, std::atoi(e)));
     }
     if (d.nstagesL < 2 || d.nstagesU < 2) return 0;
@@ -590,6 +599,7 @@ int upload_col(opmgpu_handle h, const ColProgram& p, ColDevMem& d)
     d.valid = true;
     return 0;
 }
+#endif
 
 PipeDev pipe_dev(const PipeDevMem& d)
 {
@@ -599,7 +609,7 @@ PipeDev pipe_dev(const PipeDevMem& d)
     p.cta_ext_base = d.cta_ext_base.p; p.ext = d.ext.p;
     p.stage_bytes = d.stage_bytes; p.rhs_bytes = d.rhs_bytes; p.nstages = d.nstages;
     p.trace = nullptr; p.trace_cta = -1; p.gtrace = nullptr; p.gtrace_steps = 0;
-    p.dbg = getenv("OPMGPU_SDEBUG") ? atoi(getenv("OPMGPU_SDEBUG")) : 0;
+    p.dbg = exp_env("OPMGPU_SDEBUG") ? atoi(exp_env("OPMGPU_SDEBUG")) : 0;
     p.cluster_size = d.cluster_size; p.cx_bytes = d.cx_bytes;
     return p;
 }
@@ -730,6 +740,7 @@ int set_pattern(opmgpu_handle h, int N, int nnzb, const int* rowptr, const int* 
     h->use_pipe = h->an.pipeL.valid && h->an.pipeU.valid;
     h->N_for_upload = N;
     h->use_col = false;
+#ifdef OPMGPU_EXPERIMENTS
     if (h->use_pipe && h->allow_col && h->an.grid_nx > 0) {
         // exact Cartesian stencil: column-owned sweeps (colprog.hpp) instead of the general pipelined ones
         ColProgram cp;
@@ -740,6 +751,7 @@ int set_pattern(opmgpu_handle h, int N, int nnzb, const int* rowptr, const int* 
             h->use_col = h->col.valid;
         }
     }
+#endif
     if (!h->use_col) h->col.release();
     if (h->use_pipe && !h->use_col) {
         if ((rc = upload_pipe(h, h->an.pipeL, h->pipeL))) return rc;
@@ -923,7 +935,7 @@ int launch_spmv(opmgpu_handle h, int mode, const T* x, T* y, const T* w1)
         const int nnzb = h->world > 1 ? h->nnzb_full : h->nnzb;
         const int ntiles = (h->N + kSpmvRows - 1) / kSpmvRows;
         const unsigned grid = (unsigned)std::min(ntiles, h->sm_count);
-        static const int rowt_env = getenv("OPMGPU_SPMV_ROWT") ? atoi(getenv("OPMGPU_SPMV_ROWT")) : -1;
+        static const int rowt_env = exp_env("OPMGPU_SPMV_ROWT") ? atoi(exp_env("OPMGPU_SPMV_ROWT")) : -1;
         const bool rowt = rowt_env >= 0 ? rowt_env != 0 : sizeof(T) == 4;      // thread per row: the float instance's default
         if (sizeof(T) == 4 && rowt_env < 0) {
             // float instance: 128-row tiles, one thread per row
@@ -1042,7 +1054,7 @@ int spmv_overlapped(opmgpu_handle h, int mode, T* x, T* y, const T* w1)
     CK(cudaEventRecord(h->ev_halo_done, h->halo_stream));
     const int* rowptr = h->d_rowptr_full.p; const int* colidx = h->d_colidx_full.p;
     const int nnzb = h->nnzb_full;
-    static const int reserve = getenv("OPMGPU_HALO_RESERVE") ? atoi(getenv("OPMGPU_HALO_RESERVE")) : 16;     // SMs left to the pack kernel and NCCL's send/recv kernel (32 p2p channels)
+    static const int reserve = exp_env("OPMGPU_HALO_RESERVE") ? atoi(exp_env("OPMGPU_HALO_RESERVE")) : 16;     // SMs left to the pack kernel and NCCL's send/recv kernel (32 p2p channels)
     const int ntiles = (h->N + kSpmvRows - 1) / kSpmvRows;
     const unsigned grid = (unsigned)std::max(1, std::min(ntiles, h->sm_count - reserve));
     const unsigned long long* skip = h->d_row_skip.p;
@@ -1211,6 +1223,7 @@ int factor_t(opmgpu_handle h, int* bad_row)
     const bool A_in_lu = h->world > 1;
     const int big = 0x7fffffff;
     CK(cudaMemcpyAsync(h->d_bad.p, &big, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+#ifdef OPMGPU_EXPERIMENTS
     if (h->factor_by_levels) {
         const std::vector<int>& lp = h->an.lvl_ptr;
         for (size_t l = 0; l + 1 < lp.size(); ++l) {
@@ -1220,7 +1233,9 @@ int factor_t(opmgpu_handle h, int* bad_row)
                 h->d_lvl_rows.p, lp[l], lp[l + 1], h->d_rowptr.p, h->d_colidx.p, h->d_diag.p, h->d_lu.p, h->d_bad.p);
             h->launches++;
         }
-    } else if (pipe_factor) {
+    } else
+#endif
+    if (pipe_factor) {
         FactorPipeDevMem& d = h->pipeF;
         const size_t e = d.nval * 3;
         if (A_in_lu) pack_factor_records_kernel<double, true><<<(unsigned)((e + 255) / 256), 256, 0, h->stream>>>(d.nval, d.val_src.p, d.val_dst8.p, h->d_lu.p, (double*)d.buf.p);
@@ -1248,6 +1263,7 @@ int factor_t(opmgpu_handle h, int* bad_row)
     }
     CK(cudaGetLastError());
     // stream the factors into the sweep programs' layout
+#ifdef OPMGPU_EXPERIMENTS
     if (h->use_col) {
         ColDevMem& c = h->col;
         const unsigned gridL = (unsigned)std::min<size_t>((c.nvalL * 3 + 255) / 256, (size_t)h->sm_count * 16);
@@ -1262,7 +1278,9 @@ int factor_t(opmgpu_handle h, int* bad_row)
             repack_col_from_lu_kernel<false><<<gridU, 256, 0, h->stream>>>(c.nvalU, c.valU_src.p, c.valU_dst.p, h->d_lu.p, c.recU.p);
         }
         h->launches += c.nvalL ? 2 : 1;
-    } else if (h->use_pipe && pipe_factor) {
+    } else
+#endif
+    if (h->use_pipe && pipe_factor) {
         // L_ij = A_ij * inv(D_j) is formed here, from A and the program-ordered pivots.  (Copying the
         // U blocks on a second stream beside the factorisation kernel was measured: it slows that
         // latency-bound kernel down by more than the copy costs, 0.84 -> 0.99 ms per factorisation.)
@@ -1337,8 +1355,10 @@ int launch_sweep(opmgpu_handle h, bool upper, const PipeDevMem& d, void** args)
 {
     if (d.cluster_size > 1) {
         const void* fn = upper ? (const void*)ilu0_sweep_pipe_kernel<true, true, true, false, T> : (const void*)ilu0_sweep_pipe_kernel<false, true, true, false, T>;
+#ifdef OPMGPU_EXPERIMENTS
         if (sizeof(T) == 8 && (h->gtrace_steps > 0 || (h->trace_cta >= 0 && h->d_trace.p)))                     // debug tools only
             fn = upper ? (const void*)ilu0_sweep_pipe_kernel<true, true, true, true> : (const void*)ilu0_sweep_pipe_kernel<false, true, true, true>;
+#endif
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(d.P); cfg.blockDim = dim3(kPipeThreads); cfg.dynamicSmemBytes = d.smem; cfg.stream = h->stream;
         cudaLaunchAttribute at[2];
@@ -1366,12 +1386,13 @@ int launch_sweep(opmgpu_handle h, bool upper, const PipeDevMem& d, void** args)
         CK(le);
         return 0;
     }
-    const bool trace = sizeof(T) == 8 && ((h->trace_cta >= 0 && h->d_trace.p) || h->gtrace_steps > 0);       // debug tools only
     const void* fn = upper ? (d.lean ? (const void*)ilu0_sweep_pipe_kernel<true, true, false, false, T> : (const void*)ilu0_sweep_pipe_kernel<true, false, false, false, T>)
                            : (d.lean ? (const void*)ilu0_sweep_pipe_kernel<false, true, false, false, T> : (const void*)ilu0_sweep_pipe_kernel<false, false, false, false, T>);
-    if (trace)
+#ifdef OPMGPU_EXPERIMENTS
+    if (sizeof(T) == 8 && ((h->trace_cta >= 0 && h->d_trace.p) || h->gtrace_steps > 0))       // debug tools only
         fn = upper ? (d.lean ? (const void*)ilu0_sweep_pipe_kernel<true, true, false, true> : (const void*)ilu0_sweep_pipe_kernel<true, false, false, true>)
                    : (d.lean ? (const void*)ilu0_sweep_pipe_kernel<false, true, false, true> : (const void*)ilu0_sweep_pipe_kernel<false, false, false, true>);
+#endif
     CK(cudaLaunchCooperativeKernel(fn, dim3(d.P), dim3(kPipeThreads), args, d.smem, h->stream));
     return 0;
 }
@@ -1410,7 +1431,7 @@ int np_apply(opmgpu_handle h, double w, const T* d, T* v)
 template <int KIND, class T>
 int mc_launch(opmgpu_handle h, McSweepArgs& a)
 {
-    static const int rowt_env = getenv("OPMGPU_MC_ROWT") ? atoi(getenv("OPMGPU_MC_ROWT")) : -1;
+    static const int rowt_env = exp_env("OPMGPU_MC_ROWT") ? atoi(exp_env("OPMGPU_MC_ROWT")) : -1;
     const void* fn;
     int rows;
     if (sizeof(T) == 4) { fn = (const void*)mc_sweep_tma_kernel<KIND, float, true, kSpmvRowsF32>; rows = kSpmvRowsF32; }
@@ -1456,6 +1477,7 @@ int apply_precond(opmgpu_handle h, double w, const T* d, T* v, bool d_in_program
     if (h->mc.valid) return mc_apply<T>(h, w, d, v);
     const int scale = std::fabs(w - 1.0) > 1e-15 ? 1 : 0;      // relaxation_ flag of the reference
     if (h->use_col && sizeof(T) == 4) return h->bad("the column-owned sweeps (OPMGPU_COL=1) exist for the double instance only");
+#ifdef OPMGPU_EXPERIMENTS
     if (h->use_col) {
         const double* dd = reinterpret_cast<const double*>(d);      // (double instance only)
         double* vv = reinterpret_cast<double*>(v);
@@ -1469,17 +1491,17 @@ int apply_precond(opmgpu_handle h, double w, const T* d, T* v, bool d_in_program
             pg.g = c.g; pg.rec = upper ? c.recU.p : c.recL.p; pg.cta_tile_ptr = c.tile_ptr.p;
             pg.cta_tiles = upper ? c.tilesU.p : c.tilesL.p; pg.ext = upper ? c.extU.p : c.extL.p;
             pg.nstages = upper ? c.nstagesU : c.nstagesL;
-            static const int pf = getenv("OPMGPU_COL_PF") ? atoi(getenv("OPMGPU_COL_PF")) : 12;
+            static const int pf = exp_env("OPMGPU_COL_PF") ? atoi(exp_env("OPMGPU_COL_PF")) : 12;
             pg.pf_ahead = pf;
             // service warps: with W <= 3 every compute warp keeps a scheduler (SM sub-partition) to
             // itself and the producer (mostly asleep) shares one with the helper
-            static const int roles = getenv("OPMGPU_COL_ROLES") ? atoi(getenv("OPMGPU_COL_ROLES")) : 1;
+            static const int roles = exp_env("OPMGPU_COL_ROLES") ? atoi(exp_env("OPMGPU_COL_ROLES")) : 1;
             int nwarps = c.g.W + 2;
             pg.producer_warp = c.g.W; pg.helper_warp = c.g.W + 1;
             if (roles == 1 && c.g.W <= 3) { nwarps = 8; pg.producer_warp = 3; pg.helper_warp = 7; }
             pg.prof = nullptr; pg.trace = nullptr; pg.trace_cta = -1;
-            static const int trace_cta = getenv("OPMGPU_COL_TRACE") ? atoi(getenv("OPMGPU_COL_TRACE")) : -1;
-            static const bool prof = getenv("OPMGPU_COL_PROF") != nullptr;
+            static const int trace_cta = exp_env("OPMGPU_COL_TRACE") ? atoi(exp_env("OPMGPU_COL_TRACE")) : -1;
+            static const bool prof = exp_env("OPMGPU_COL_PROF") != nullptr;
             if (prof) {
                 CK(h->d_trace.ensure((size_t)c.P * 8 * 4));
                 CK(cudaMemsetAsync(h->d_trace.p, 0, sizeof(long long) * (size_t)c.P * 8 * 4, h->stream));
@@ -1518,6 +1540,7 @@ int apply_precond(opmgpu_handle h, double w, const T* d, T* v, bool d_in_program
         h->launches += d_in_program_order ? 2 : 3;
         return 0;
     }
+#endif
     if (h->use_pipe) {
         if (!d_in_program_order) {
             const size_t e = h->pipeL.nperm * 3;
@@ -2129,17 +2152,17 @@ int opmgpu_create(int device, opmgpu_handle* out)
     h->device = device;
     h->sm_count = prop.multiProcessorCount;
     int per_sm = 1;
-    if (const char* s = getenv("OPMGPU_SWEEP_CTAS_PER_SM")) per_sm = std::max(1, atoi(s));
+    if (const char* s = exp_env("OPMGPU_SWEEP_CTAS_PER_SM")) per_sm = std::max(1, atoi(s));
     int occ = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ilu0_sweep_kernel<true, double>, 256, 0);
     per_sm = std::min(per_sm, std::max(occ, 1));
     h->sweep_ctas = h->sm_count * per_sm;
-    if (const char* s = getenv("OPMGPU_SIMPLE_SWEEP")) h->force_simple = atoi(s) != 0;
-    if (const char* s = getenv("OPMGPU_FACTOR_BY_LEVELS")) h->factor_by_levels = atoi(s) != 0;
-    if (const char* s = getenv("OPMGPU_FACTOR_TILE")) h->factor_tile = atoi(s) != 0;
-    if (const char* s = getenv("OPMGPU_HOSTBOX")) h->use_hostbox = atoi(s) != 0;
-    if (const char* s = getenv("OPMGPU_FUSE_PERMUTE")) h->fuse_permute = atoi(s) != 0;
-    if (const char* s = getenv("OPMGPU_SPMV_SIMPLE")) h->spmv_tma = atoi(s) == 0;
+    if (const char* s = exp_env("OPMGPU_SIMPLE_SWEEP")) h->force_simple = atoi(s) != 0;
+    if (const char* s = exp_env("OPMGPU_FACTOR_BY_LEVELS")) h->factor_by_levels = atoi(s) != 0;
+    if (const char* s = exp_env("OPMGPU_FACTOR_TILE")) h->factor_tile = atoi(s) != 0;
+    if (const char* s = exp_env("OPMGPU_HOSTBOX")) h->use_hostbox = atoi(s) != 0;
+    if (const char* s = exp_env("OPMGPU_FUSE_PERMUTE")) h->fuse_permute = atoi(s) != 0;
+    if (const char* s = exp_env("OPMGPU_SPMV_SIMPLE")) h->spmv_tma = atoi(s) == 0;
     cudaFuncSetAttribute(spmv3_tma_kernel<0, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
     cudaFuncSetAttribute(spmv3_tma_kernel<1, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
     cudaFuncSetAttribute(spmv3_tma_kernel<2, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
@@ -2164,7 +2187,7 @@ int opmgpu_create(int device, opmgpu_handle* out)
     cudaFuncSetAttribute(mc_sweep_tma_kernel<0, float, true, kSpmvRowsF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMcSmemBytes);
     cudaFuncSetAttribute(mc_sweep_tma_kernel<1, float, true, kSpmvRowsF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMcSmemBytes);
     cudaFuncSetAttribute(mc_sweep_tma_kernel<2, float, true, kSpmvRowsF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMcSmemBytes);
-    if (const char* s = getenv("OPMGPU_HALO_OVERLAP")) h->overlap_halo = atoi(s) != 0;
+    if (const char* s = exp_env("OPMGPU_HALO_OVERLAP")) h->overlap_halo = atoi(s) != 0;
     if (const char* s = getenv("OPMGPU_PEER_HALO")) h->use_peer_halo = atoi(s) != 0;
     cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     cudaFuncSetAttribute(ilu0_factor_pipe_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
@@ -2176,24 +2199,30 @@ int opmgpu_create(int device, opmgpu_handle* out)
     cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<true, false, false, false, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
     cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<false, true, false, false, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
     cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<true, true, false, false, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
+#ifdef OPMGPU_EXPERIMENTS
     cudaFuncSetAttribute(ilu0_sweep_col_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
     cudaFuncSetAttribute(ilu0_sweep_col_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
     cudaFuncSetAttribute(ilu0_sweep_col_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
     cudaFuncSetAttribute(ilu0_sweep_col_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
-    if (const char* s = getenv("OPMGPU_COL")) h->allow_col = atoi(s) != 0;
+#endif
+    if (const char* s = exp_env("OPMGPU_COL")) h->allow_col = atoi(s) != 0;
+#ifdef OPMGPU_EXPERIMENTS
     cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
     cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
     cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
     cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<true, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
+#endif
     cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
     cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
+#ifdef OPMGPU_EXPERIMENTS
     cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<false, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
     cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<true, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
+#endif
     {
         // how many CTAs of the cluster variants can be co-resident (one CTA per SM, all of its
         // shared memory): GPCs do not divide evenly into clusters of 4 or 8
         int want = 8;                                        // OPMGPU_CLUSTER=0: no clusters; 2/4/8: largest size tried
-        if (const char* s = getenv("OPMGPU_CLUSTER")) want = atoi(s);
+        if (const char* s = exp_env("OPMGPU_CLUSTER")) want = atoi(s);
         if (h->world > 1) want = 0;
         for (int lg = 1; lg <= 3; ++lg) {
             const int cs = 1 << lg;
@@ -2218,7 +2247,7 @@ int opmgpu_create(int device, opmgpu_handle* out)
     cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
     cudaFuncSetAttribute(ilu0_sweep_pipe_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
     if (!h->force_simple) h->sweep_ctas = h->sm_count;      // the pipelined sweep owns a whole SM per CTA
-    if (const char* s = getenv("OPMGPU_PIPE_CTAS")) h->sweep_ctas = std::max(1, std::min(h->sm_count, atoi(s)));
+    if (const char* s = exp_env("OPMGPU_PIPE_CTAS")) h->sweep_ctas = std::max(1, std::min(h->sm_count, atoi(s)));
     if (getenv("OPMGPU_DEBUG")) {
         cudaFuncAttributes fa;
         cudaFuncGetAttributes(&fa, ilu0_sweep_pipe_kernel<false, true>);
@@ -3072,7 +3101,7 @@ int opmgpu_get_profile(opmgpu_handle h, double ms[4], long long count[4])
     return OPMGPU_OK;
 }
 
-// Debug (not in the public header; tests of the recovery path): sets the device watchdog word
+// Test hook (declared in the header; tests of the recovery path): sets the device watchdog word
 // as a sweep kernel does when a dependency is never delivered.  The next call that collects it
 // must fail with OPMGPU_CUDA_ERROR ("sweep watchdog"), re-arm the push slots and leave the handle usable.
 int opmgpu_debug_set_watchdog_word(opmgpu_handle h, int code)
@@ -3084,6 +3113,7 @@ int opmgpu_debug_set_watchdog_word(opmgpu_handle h, int code)
     return OPMGPU_OK;
 }
 
+#ifdef OPMGPU_EXPERIMENTS
 // Debug (not in the public header): clock64 stamps of one CTA of the next pipelined apply.
 // out[2][512][8]: lower then upper sweep; per step {enter, landed, computed, after barrier,
 // nrows, bulk issued, rhs gather issued, -}.
@@ -3123,6 +3153,8 @@ int opmgpu_debug_gtrace_apply(opmgpu_handle h, int steps, double w, const double
     CK(cudaStreamSynchronize(h->stream));
     return OPMGPU_OK;
 }
+
+#endif
 
 // ---- multi-GPU entry points -------------------------------------------------------------------
 int opmgpu_nccl_unique_id(void* id128)

@@ -100,8 +100,9 @@ def multicolour_order(rowptr, colidx):
 class GpuLinearSolver:
     """One opmgpu handle (one GPU, one stream)."""
 
-    def __init__(self, device: int = 0):
-        self.lib = L.load()
+    def __init__(self, device: int = 0, experiments: bool = False):
+        # experiments: bind libopmgpu_exp.so (A/B tools and tests of experimental kernel variants only)
+        self.lib = L.load_experiments() if experiments else L.load()
         self.h = C.c_void_p()
         rc = self.lib.opmgpu_create(int(device), C.byref(self.h))
         if rc != L.OK:

@@ -27,6 +27,23 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), name
 
 
+def test_test_hooks_and_experiment_symbols():
+    """include/opm_gpu_solver_testhooks.h: the shipping library exports the five test hooks and none of
+    the experiment entry points; the experiments build exports both and the whole C ABI."""
+    import ctypes
+    hdr = open(os.path.join(ROOT, "include", "opm_gpu_solver_testhooks.h")).read()
+    declared = sorted(set(re.findall(r"\b(opmgpu_debug_[a-z0-9_]+)\s*\(", hdr)))
+    assert declared == sorted(_lib.TEST_HOOKS + _lib.EXP_HOOKS)
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in _lib.TEST_HOOKS:
+        assert hasattr(lib, name), name
+    for name in _lib.EXP_HOOKS:
+        assert not hasattr(lib, name), f"{name} must not be in the shipping library"
+    exp = _lib.load_experiments()
+    for name in _lib.TEST_HOOKS + _lib.EXP_HOOKS + _lib.EXPORTS:
+        assert hasattr(exp, name), name
+
+
 def test_default_params_are_the_reference_defaults():
     p = make_params()
     assert p.linear_solver_reduction == 1e-2 and p.linear_solver_maxiter == 150

@@ -11,7 +11,7 @@ from opm_simulators_legacy_b200.jacobian import synth_blackoil_jacobian, random_
 
 
 def _host_col_apply(rp, ci, dims, lu, P, w, d):
-    lib = _lib.load()
+    lib = _lib.load_experiments()          # the column-owned sweeps exist in the experiments build only
     f = lib.opmgpu_debug_host_col_apply
     ip, dp = C.POINTER(C.c_int), C.POINTER(C.c_double)
     f.argtypes = [C.c_int, ip, ip, C.c_int, C.c_int, C.c_int, dp, C.c_int, C.c_double, dp, dp, ip]

@@ -346,12 +346,12 @@ def test_cpp_host_mirror_selftest():
 
 @pytest.mark.parametrize("dims", [(24, 20, 12), (40, 40, 20), (120, 125, 6), (7, 6, 40), (64, 1, 1)])
 def test_column_owned_sweeps_bit_exact(oracle, dims, monkeypatch):
-    """The experimental column-owned sweep kernels (OPMGPU_COL=1, sweep_col.cuh): same bits as
-    ParallelOverlappingILU0::apply, same iteration counts."""
+    """The experimental column-owned sweep kernels (experiments build libopmgpu_exp.so, OPMGPU_COL=1,
+    sweep_col.cuh): same bits as ParallelOverlappingILU0::apply, same iteration counts."""
     monkeypatch.setenv("OPMGPU_COL", "1")
     s = synth_blackoil_jacobian(*dims, perm="lognormal")
     rp, ci, v, b = _np(s)
-    g = GpuLinearSolver(0)
+    g = GpuLinearSolver(0, experiments=True)
     try:
         g.set_pattern(rp, ci)
         g.set_values(v)

@@ -16,7 +16,7 @@ from oracle import oracle_py  # noqa: E402
 def parity(dims):
     s = synth_blackoil_jacobian(*dims, perm="lognormal")
     rp, ci, v, b = s.rowptr.numpy(), s.colidx.numpy(), s.vals.numpy(), s.rhs.numpy()
-    g = GpuLinearSolver(0)
+    g = GpuLinearSolver(0, experiments=True)          # column-owned sweeps: experiments build
     g.set_pattern(rp, ci)
     g.set_values(v)
     assert g.ilu0_factor() == -1
@@ -41,7 +41,7 @@ def parity(dims):
 
 def timing(dims, reps):
     s = synth_blackoil_jacobian(*dims, perm="lognormal")
-    g = GpuLinearSolver(0)
+    g = GpuLinearSolver(0, experiments=True)          # column-owned sweeps: experiments build
     t0 = time.time()
     g.set_pattern(s.rowptr.numpy(), s.colidx.numpy())
     t1 = time.time()

@@ -16,7 +16,7 @@ from opm_simulators_legacy_b200.solver import GpuLinearSolver  # noqa: E402
 nx, ny, nz = (int(a) for a in sys.argv[1:4])
 STEPS = 256
 s = synth_blackoil_jacobian(nx, ny, nz, perm="lognormal")
-g = GpuLinearSolver(0)
+g = GpuLinearSolver(0, experiments=True)          # tracing entry points: experiments build
 st = torch.cuda.Stream(); torch.cuda.set_stream(st); g.use_torch_stream()
 g.set_pattern(s.rowptr.numpy(), s.colidx.numpy())
 vals = s.vals.cuda(); rhs = s.rhs.cuda(); y = torch.zeros_like(rhs)

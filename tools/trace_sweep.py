@@ -18,7 +18,7 @@ G = 3
 nx, ny, nz = (int(a) for a in sys.argv[1:4])
 ctas = [int(a) for a in sys.argv[4:]] or [0, 70, 142]
 s = synth_blackoil_jacobian(nx, ny, nz, perm="lognormal")
-g = GpuLinearSolver(0)
+g = GpuLinearSolver(0, experiments=True)          # tracing entry points: experiments build
 g.set_pattern(s.rowptr.numpy(), s.colidx.numpy())
 vals = s.vals.cuda(); rhs = s.rhs.cuda(); y = torch.zeros_like(rhs)
 g.set_values_dev(vals)
