@@ -2341,6 +2341,7 @@ int opmgpu_set_pattern_bcrs_operator_only(opmgpu_handle h, int N, int nnzb, cons
     h->csc_colptr.clear(); h->csc_rowidx.clear();
     h->use_pipe = false; h->use_col = false;
     h->pipeL.release(); h->pipeU.release(); h->pipeF.release(); h->progL.release(); h->progU.release(); h->d_lu.release();
+    h->mc.release();
     h->N = N; h->nnzb = nnzb; h->n_ghost = 0;
     CK(h->d_rowptr.ensure((size_t)N + 1 + 8));
     CK(h->d_colidx.ensure((size_t)nnzb + 8));
@@ -3037,7 +3038,7 @@ int opmgpu_set_ilu_ordering(opmgpu_handle h, int ordering)
 {
     if (!h) return OPMGPU_BAD_ARGUMENT;
     if (ordering != OPMGPU_ILU_NATURAL && ordering != OPMGPU_ILU_MULTICOLOUR) return h->bad("unknown ILU0 ordering");
-    if (ordering != OPMGPU_ILU_NATURAL && (h->multi || h->world > 1))
+    if (ordering != OPMGPU_ILU_NATURAL && (h->multi || h->world > 1 || h->comm))
         return h->bad("the multicolour ILU0 variant exists for plain single-GPU handles");
     if (ordering != h->ilu_order_req) {          // takes effect with the next pattern
         h->ilu_order_req = ordering;
