@@ -404,7 +404,7 @@ def measure(workload, steps, warmup, rank, world, local, sample_clocks=True, sin
     return out
 
 
-def measure_multicolour(workload, steps, warmup, local):
+def measure_multicolour(workload, steps, warmup, local, lines=False):
     """The flagged multicolour-ILU0 variant on one GPU (OPMGPU_ILU_MULTICOLOUR): a DIFFERENT
     preconditioner (ILU0 of P A P^T), so its iteration count stands beside the natural-order one and is
     checked against the oracle run on the permuted system, never against the reference's count."""
@@ -417,7 +417,7 @@ def measure_multicolour(workload, steps, warmup, local):
     params = make_params()
     g = GpuLinearSolver(local)
     g.use_torch_stream()
-    g.set_ilu_ordering(True)
+    g.set_ilu_ordering("lines" if lines else True)
     t0 = time.perf_counter()
     g.set_pattern(s.rowptr.numpy(), s.colidx.numpy())
     analysis_ms = (time.perf_counter() - t0) * 1e3
@@ -464,9 +464,9 @@ def measure_multicolour(workload, steps, warmup, local):
                 "iterations_gpu": res["iterations"], "iterations_cpu_oracle": ref["iterations"],
                 "max_rel_diff_increment": float((np.abs(x_nat - x_ref).max(0) / np.abs(x_ref).max(0)).max()),
                 "true_residual_reduction": true_red},
-            "note": "FLAGGED VARIANT, not the reference's preconditioner: ILU0 of the colour-sorted permutation P A P^T "
-                    "(red-black on this stencil), one HBM-bound pass per colour and direction; its iteration count is not "
-                    "comparable with the natural-order (reference) count above"}
+            "ordering": "k-lines: red-black over the (i,j) columns, natural order along k" if lines else "red-black points (greedy colouring)",
+            "note": "FLAGGED VARIANT, not the reference's preconditioner: ILU0 of the colour-sorted permutation P A P^T; "
+                    "its iteration count is not comparable with the natural-order (reference) count above"}
 
 
 def run_gpu(args, rank, world):
@@ -499,12 +499,15 @@ def run_gpu(args, rank, world):
                    "note": "Impl<3,float>: matrix values and vectors in float (SpMV 40 B/block + 28 B/row), ILU0 factors and sweep "
                            "records keep 8-byte containers (float arithmetic, bit-exact against the float oracle)"}
     # the multicolour-ILU0 variant (north star: "level-set (or multicolour) scheduling"), flagged
-    mc = None
+    mc = mc_lines = None
     if world == 1 and not single and not args.no_multicolour:
         import gc
         gc.collect()
         torch.cuda.empty_cache()
         mc = measure_multicolour(args.workload, args.steps, 3, local)
+        gc.collect()
+        torch.cuda.empty_cache()
+        mc_lines = measure_multicolour(args.workload, args.steps, 3, local, lines=True)
     # the strong-scaling configuration (BASELINE.json config 4: 8M cells) beside the headline
     c4 = None
     if args.workload == "c3" and not args.no_c4:
@@ -532,7 +535,7 @@ def run_gpu(args, rank, world):
             "cpu_baseline": m["cpu_baseline"], "cpu_baseline_allcores": m["cpu_baseline_allcores"],
             "iterations": m["iterations"], "reduction": m["reduction"], "analysis_ms_once_per_pattern": m["analysis_ms"],
             "solve_breakdown_ms": m["breakdown"], "parity": m["parity"], "c4": c4, "f32": f32,
-            "multicolour_variant": mc}
+            "multicolour_variant": mc, "multicolour_lines_variant": mc_lines}
     print(json.dumps(line), flush=True)
 
 

@@ -212,14 +212,24 @@ int  opmgpu_ilu0_np(opmgpu_handle h, int np, const double* vals, double* lu_out,
  * as parity.  What IS bit-comparable: factors and applies against the oracle run on P A P^T.
  * BiCGStab / GMRES, the operator and every vector stay in the caller's ordering.
  * opmgpu_set_ilu_ordering prepares the NEXT pattern (call it before opmgpu_set_pattern_bcrs or the
- * first opmgpu_solve_from_csc_blocks); plain single-GPU handles, 3x3 blocks, both precisions. */
-enum { OPMGPU_ILU_NATURAL = 0, OPMGPU_ILU_MULTICOLOUR = 1 };
+ * first opmgpu_solve_from_csc_blocks); plain single-GPU handles, 3x3 blocks, both precisions.
+ *
+ * OPMGPU_ILU_MULTICOLOUR_LINES ("k-lines"): for Cartesian stencil patterns in natural numbering the two
+ * colours are taken over the (i,j) COLUMNS of the grid and the natural order is kept along k, i.e. the
+ * vertical couplings -- the strong ones of a reservoir grid -- stay in the reference's order and only
+ * the horizontal ones are re-ordered.  Each column is then a chain owned by one thread triple and each
+ * sweep is two launches that walk the planes.  Any other pattern answers OPMGPU_BAD_ARGUMENT at
+ * opmgpu_set_pattern_bcrs (checked row by row, not guessed).  Same rules: flagged, bit-comparable with
+ * the oracle on P A P^T, never parity with the natural-order solve. */
+enum { OPMGPU_ILU_NATURAL = 0, OPMGPU_ILU_MULTICOLOUR = 1, OPMGPU_ILU_MULTICOLOUR_LINES = 2 };
 int  opmgpu_set_ilu_ordering(opmgpu_handle h, int ordering);
 int  opmgpu_get_ilu_ordering(opmgpu_handle h);
 /* Colours and permutation of the current pattern (n2p[i] = position of row i in P A P^T). */
 int  opmgpu_get_ilu_permutation(opmgpu_handle h, int* ncolours, int* n2p);
 /* The ordering rule alone, host only (no GPU, no handle); any output may be NULL. */
 int  opmgpu_multicolour_order(int N, const int* rowptr, const int* colidx, int* ncolours, int* colour, int* n2p);
+/* The k-line ordering of an nx x ny x nz grid in natural numbering, host only. */
+int  opmgpu_line_order(int nx, int ny, int nz, int* n2p);
 
 /* ---- kernel-level entry points (parity tests, micro-benchmarks) -------------------------- */
 

@@ -32,13 +32,13 @@ EXPORTS = [
     "opmgpu_dot", "opmgpu_num_levels", "opmgpu_launch_count", "opmgpu_residual_history",
     "opmgpu_set_profiling", "opmgpu_get_profile", "opmgpu_set_precision", "opmgpu_get_precision",
     "opmgpu_set_pattern_bcrs_operator_only",
-    "opmgpu_set_ilu_ordering", "opmgpu_get_ilu_ordering", "opmgpu_get_ilu_permutation", "opmgpu_multicolour_order",
+    "opmgpu_set_ilu_ordering", "opmgpu_get_ilu_ordering", "opmgpu_get_ilu_permutation", "opmgpu_multicolour_order", "opmgpu_line_order",
     "opmgpu_set_block_size", "opmgpu_solve_bcrs_np", "opmgpu_solve_from_csc_blocks_np", "opmgpu_spmv_np", "opmgpu_ilu0_np",
 ]
 
 OK, NOT_CONVERGED, SINGULAR_BLOCK, BREAKDOWN, BAD_PATTERN, BAD_ARGUMENT = 0, 1, 2, 3, 4, 5
 CUDA_ERROR, NCCL_ERROR = -1, -2
-ILU_NATURAL, ILU_MULTICOLOUR = 0, 1
+ILU_NATURAL, ILU_MULTICOLOUR, ILU_MULTICOLOUR_LINES = 0, 1, 2
 
 
 class Params(C.Structure):
@@ -118,6 +118,7 @@ def _bind(lib):
         "opmgpu_get_ilu_ordering": (C.c_int, [H]),
         "opmgpu_get_ilu_permutation": (C.c_int, [H, ip, ip]),
         "opmgpu_multicolour_order": (C.c_int, [C.c_int, ip, ip, ip, ip, ip]),
+        "opmgpu_line_order": (C.c_int, [C.c_int, C.c_int, C.c_int, ip]),
         "opmgpu_solve_bcrs_np": (C.c_int, [H, C.c_int, dp, dp, dp, PP, RP]),
         "opmgpu_solve_from_csc_blocks_np": (C.c_int, [H, C.c_int, C.c_int, C.POINTER(Csc), dp, dp, dp, PP, RP]),
         "opmgpu_spmv_np": (C.c_int, [H, C.c_int, dp, dp, dp]),

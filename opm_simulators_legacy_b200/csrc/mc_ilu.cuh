@@ -44,55 +44,72 @@ mc_scatter_factors_kernel(size_t nscal, const int* __restrict__ psrc, const int*
     lu[(size_t)psrc[kp] * 9 + t] = (double)uni[(size_t)ppos[kp] * 9 + t];
 }
 
-// Dune::bilu0_decomposition on the permuted pattern, one dependency level per launch, one thread
-// per row; entry b of the permuted pattern lives at block ppos[b] of the unified array
+// Dune::bilu0_decomposition of one row of the permuted pattern.  Lower entry l of the row (block l of the
+// unified array) eliminates with the inverted pivot of row j = Lcol[l] (block offD + j); the blocks it
+// updates were found on the host (pair lists: the same pairs, in the same order, as the reference's walk
+// over both rows).
 template <class T>
-__global__ void __launch_bounds__(128)
-mc_factor_level_kernel(const int* __restrict__ lvl_rows, int begin, int end, const int* __restrict__ prowptr,
-                       const int* __restrict__ pcol, const int* __restrict__ pdiag, const int* __restrict__ ppos,
-                       T* uni, int* bad_row)
+__device__ __forceinline__ void mc_factor_row(int i, const int* __restrict__ Lrowptr, const int* __restrict__ Lcol,
+                                              const int* __restrict__ pair_ptr, const int* __restrict__ pair_jk,
+                                              const int* __restrict__ pair_ik, long long offD, T* uni, int* bad_row)
 {
-    const int s = begin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= end) return;
-    const int i = lvl_rows[s];
-    const int iend = prowptr[i + 1], idiag = pdiag[i];
-    for (int ij = prowptr[i]; ij < idiag; ++ij) {
-        const int j = pcol[ij];
+    const int lend = Lrowptr[i + 1];
+    for (int l = Lrowptr[i]; l < lend; ++l) {
+        const int j = Lcol[l];
         T Aij[9], Dj[9], L[9];
-        const int jd = pdiag[j];
-        T* pij = uni + (size_t)ppos[ij] * 9;
-        const T* pjd = uni + (size_t)ppos[jd] * 9;
+        T* pij = uni + (size_t)l * 9;
+        const T* pjd = uni + (size_t)(offD + j) * 9;
 #pragma unroll
         for (int t = 0; t < 9; ++t) { Aij[t] = pij[t]; Dj[t] = pjd[t]; }
         mat3_mul(Aij, Dj, L);                                 // L_ij = A_ij * inv(A_jj)
 #pragma unroll
         for (int t = 0; t < 9; ++t) pij[t] = L[t];
-        int jk = jd + 1, ik = ij + 1;
-        const int jend = prowptr[j + 1];
-        while (ik < iend && jk < jend) {
-            const int ci = pcol[ik], cj = pcol[jk];
-            if (ci == cj) {
-                T Ajk[9], B[9];
-                const T* pjk = uni + (size_t)ppos[jk] * 9;
-                T* pik = uni + (size_t)ppos[ik] * 9;
+        const int pend = pair_ptr[l + 1];
+        for (int p = pair_ptr[l]; p < pend; ++p) {
+            T Ajk[9], B[9];
+            const T* pjk = uni + (size_t)pair_jk[p] * 9;
+            T* pik = uni + (size_t)pair_ik[p] * 9;
 #pragma unroll
-                for (int t = 0; t < 9; ++t) Ajk[t] = pjk[t];
-                mat3_mul(L, Ajk, B);                          // A_ik -= L_ij * A_jk
+            for (int t = 0; t < 9; ++t) Ajk[t] = pjk[t];
+            mat3_mul(L, Ajk, B);                              // A_ik -= L_ij * A_jk
 #pragma unroll
-                for (int t = 0; t < 9; ++t) pik[t] = pik[t] - B[t];
-                ++ik; ++jk;
-            } else if (ci < cj) ++ik;
-            else ++jk;
+            for (int t = 0; t < 9; ++t) pik[t] = pik[t] - B[t];
         }
     }
     T D[9];
-    T* pd = uni + (size_t)ppos[idiag] * 9;
+    T* pd = uni + (size_t)(offD + i) * 9;
 #pragma unroll
     for (int t = 0; t < 9; ++t) D[t] = pd[t];
     const T det = mat3_invert(D);
 #pragma unroll
     for (int t = 0; t < 9; ++t) pd[t] = D[t];
     if (!(det != T(0)) || isinf(det) || isnan(det)) atomicMin(bad_row, i);
+}
+
+// one dependency level per launch, one thread per row of the level
+template <class T>
+__global__ void __launch_bounds__(128)
+mc_factor_level_kernel(const int* __restrict__ lvl_rows, int begin, int end, const int* __restrict__ Lrowptr,
+                       const int* __restrict__ Lcol, const int* __restrict__ pair_ptr, const int* __restrict__ pair_jk,
+                       const int* __restrict__ pair_ik, long long offD, T* uni, int* bad_row)
+{
+    const int s = begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= end) return;
+    mc_factor_row<T>(lvl_rows[s], Lrowptr, Lcol, pair_ptr, pair_jk, pair_ik, offD, uni, bad_row);
+}
+
+// k-line ordering: one launch per colour, one thread per column walking the planes (a column's rows depend
+// on each other and on rows of the colour factorised by the previous launch)
+template <class T>
+__global__ void __launch_bounds__(32)
+mc_factor_lines_kernel(int base, int ncols, int nz, const int* __restrict__ Lrowptr, const int* __restrict__ Lcol,
+                       const int* __restrict__ pair_ptr, const int* __restrict__ pair_jk, const int* __restrict__ pair_ik,
+                       long long offD, T* uni, int* bad_row)
+{
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= ncols) return;
+    for (int k = 0; k < nz; ++k)
+        mc_factor_row<T>(base + k * ncols + col, Lrowptr, Lcol, pair_ptr, pair_jk, pair_ik, offD, uni, bad_row);
 }
 
 // rows of the first colour have no lower blocks: y = P d
@@ -327,6 +344,296 @@ mc_sweep_tma_kernel(McSweepArgs a)
             ++mine;
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[st]);
+        }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// k-line variant (OPMGPU_ILU_MULTICOLOUR_LINES): red-black over the (i,j) COLUMNS of a Cartesian grid,
+// natural order along k inside a column.  The strong vertical couplings keep their natural order (one
+// half step more than the reference's ordering at 1M cells, where point red-black more than doubles
+// the count: tools/ordering_study.py), and a column is a chain that belongs to ONE thread triple: in
+// the reference's visiting order the chain's own previous row is the LAST block of a row, so only its
+// three fused multiply-adds per component (and Dinv in the upper sweep) wait for the previous step.
+// No result ever travels between CTAs inside a launch: a CTA owns RB columns of one colour and walks
+// the planes, its rows of a plane being one contiguous tile of the permuted operand (TMA-streamed
+// several planes ahead); the other colour's results were written by the previous launch.
+// Per step: block rows from shared memory, neighbours' results gathered from L2, chain values kept
+// in registers; the three components of a row meet through shared memory once per step.
+// ------------------------------------------------------------------------------------------------
+struct McLineArgs {
+    int nnz;                     // blocks of the operand (L or U)
+    const int* rowptr;           // operand row pointers (permuted rows)
+    const int* colidx;           // permuted columns (L ascending, U descending)
+    const void* vals;
+    int base, ncols, nz, rb;     // the colour's first permuted row, its columns, planes, columns per CTA
+    const int* p2n;
+    const void* d;               // right-hand side, natural order (lower sweep)
+    void* W;                     // work vector, permuted order, updated in place
+    const void* dinv;
+    void* out;                   // result, natural order (upper sweep)
+    double w;
+    int scale;
+    int obase, oncols, nx, plane;      // the other colour's first row and columns, grid width, cells per plane (L2 prefetch ranges)
+    long long* trace;                  // experiments build: clock64 stamps of CTA 0, first consumer warp, [nz][8]
+};
+
+// L2 prefetch of a byte range (rounded outwards to 16 bytes, clipped to [lo, hi))
+__device__ __forceinline__ void line_prefetch_l2(const void* base, long long lo_byte, long long hi_byte, long long limit_byte)
+{
+    lo_byte = lo_byte < 0 ? 0 : (lo_byte & ~15ll);
+    hi_byte = (hi_byte + 15) & ~15ll;
+    if (hi_byte > (limit_byte & ~15ll)) hi_byte = limit_byte & ~15ll;
+    if (hi_byte <= lo_byte) return;
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(static_cast<const char*>(base) + lo_byte), "r"((unsigned)(hi_byte - lo_byte)) : "memory");
+}
+
+constexpr int kLineGroupThreads = kSpmvComputeWarps * 32;          // 192 = 64 rows x 3 components
+constexpr int kLineThreads = 32 + kLineGroupThreads;
+constexpr int kLineStages = 6;
+constexpr int kLineStageBytes = kSpmvValBytes + kSpmvColBytes;
+constexpr size_t kLineSmemBytes = 128 + (size_t)kLineStages * kLineStageBytes + 2 * kLineGroupThreads * sizeof(double);
+
+template <bool UPPER, class T>
+__global__ void __launch_bounds__(kLineThreads, 1)
+mc_line_sweep_kernel(McLineArgs a)
+{
+    constexpr int kAl = sizeof(T) == 8 ? 2 : 4;
+    constexpr int kCap = kSpmvCapBlocks;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(smem_raw);
+    unsigned long long* empty = full + kLineStages;
+    unsigned char* stages = smem_raw + 128;
+    T* scratch = reinterpret_cast<T*>(smem_raw + 128 + (size_t)kLineStages * kLineStageBytes);      // [2][kLineGroupThreads]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nnzb = a.nnz;
+    const int* __restrict__ rowptr = a.rowptr;
+    const int* __restrict__ colidx = a.colidx;
+    const T* __restrict__ vals = static_cast<const T*>(a.vals);
+    const T* __restrict__ dinv = static_cast<const T*>(a.dinv);
+    const int* __restrict__ p2n = a.p2n;
+    const T* __restrict__ drhs = static_cast<const T*>(a.d);
+    T* W = static_cast<T*>(a.W);
+    T* out = static_cast<T*>(a.out);
+    const T wrel = (T)a.w;
+    const int col0 = blockIdx.x * a.rb;
+    const int cnt = min(a.rb, a.ncols - col0);            // rows of a tile
+    const int nz = a.nz;
+
+    if (tid == 0) {
+        for (int i = 0; i < kLineStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kSpmvComputeWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        // producer: the blocks and column indices of the tile of every plane, several planes ahead.  The
+        // tile's block range comes from the row pointers: lane l fetches the range of plane s + l once per
+        // 32 planes (a load per plane would serialise this loop on its own latency)
+        int rb0 = 0, rb1 = 0;
+        for (int s = 0; s < nz; ++s) {
+            const int st = s % kLineStages, ph = s / kLineStages;
+            if ((s & 31) == 0) {
+                const int sl = s + lane;
+                if (sl < nz) {
+                    const int ql = a.base + (UPPER ? nz - 1 - sl : sl) * a.ncols + col0;
+                    rb0 = rowptr[ql]; rb1 = rowptr[ql + cnt];
+                }
+            }
+            const int b0 = __shfl_sync(0xffffffffu, rb0, s & 31), b1 = __shfl_sync(0xffffffffu, rb1, s & 31);
+            const int b0a = b0 & ~(kAl - 1);
+            const int b1a = (b1 + kAl - 1) & ~(kAl - 1);
+            const bool direct = (b1a > nnzb) || (b1a - b0a > kCap);
+            if (ph > 0) { while (!mbar_try_wait(&empty[st], (unsigned)((ph - 1) & 1))) {} }
+            unsigned char* stage = stages + (size_t)st * kLineStageBytes;
+            const int c0a = b0 & ~3;
+            const unsigned cbytes = (direct || b1 == b0) ? 0u : (unsigned)((((b1 - c0a) * 4) + 15) & ~15);
+            const unsigned vbytes = (direct || b1 == b0) ? 0u : (unsigned)((b1a - b0a) * 9 * (int)sizeof(T));
+            if (lane == 0) {
+                if (cbytes + vbytes == 0) mbar_arrive(&full[st]);
+                else mbar_arrive_expect_tx(&full[st], cbytes + vbytes);
+            }
+            __syncwarp();
+            void* dst = lane == 0 ? (void*)stage : (void*)(stage + kSpmvValBytes);
+            const void* src = lane == 0 ? (const void*)(vals + (size_t)b0a * 9) : (const void*)(colidx + c0a);
+            const unsigned bytes = lane == 0 ? vbytes : cbytes;
+            if (lane < 2 && bytes > 0) tma_bulk_g2s(dst, src, bytes, &full[st]);
+            // what the consumers load themselves (their rows' pointers, permutation, pivots, right-hand side
+            // and the other colour's results around their columns) is pulled into L2 at the same lead
+            {
+                const int k = UPPER ? nz - 1 - s : s;
+                const long long q0 = a.base + (long long)k * a.ncols + col0;
+                const long long ntot = (long long)a.plane * nz;
+                if (lane == 2) line_prefetch_l2(rowptr, q0 * 4, (q0 + cnt + 1) * 4, (ntot + 1) * 4);
+                if (lane == 3) line_prefetch_l2(p2n, q0 * 4, (q0 + cnt) * 4, ntot * 4);
+                if (lane == 4 && UPPER) line_prefetch_l2(dinv, q0 * 9 * (long long)sizeof(T), (q0 + cnt) * 9 * (long long)sizeof(T), ntot * 9 * (long long)sizeof(T));
+                if (lane == 5 && UPPER) line_prefetch_l2(W, q0 * 3 * (long long)sizeof(T), (q0 + cnt) * 3 * (long long)sizeof(T), ntot * 3 * (long long)sizeof(T));
+                if (lane == 5 && !UPPER) {          // right-hand side: the cells of my columns in plane k (natural numbering)
+                    const long long c_lo = (long long)k * a.plane + 2ll * col0 - 2, c_hi = (long long)k * a.plane + 2ll * (col0 + cnt) + 2;
+                    line_prefetch_l2(drhs, c_lo * 3 * (long long)sizeof(T), c_hi * 3 * (long long)sizeof(T), ntot * 3 * (long long)sizeof(T));
+                }
+                if (lane == 6 && a.oncols > 0 && b1 - b0 > cnt) {      // rows with horizontal neighbours: the other colour's plane-k results near my columns
+                    const long long o0 = a.obase + (long long)k * a.oncols + col0 - (a.nx / 2 + 2), o1 = a.obase + (long long)k * a.oncols + col0 + cnt + (a.nx / 2 + 2);
+                    const long long lo = a.obase + (long long)k * a.oncols, hi = lo + a.oncols;
+                    line_prefetch_l2(W, (o0 < lo ? lo : o0) * 3 * (long long)sizeof(T), (o1 > hi ? hi : o1) * 3 * (long long)sizeof(T), ntot * 3 * (long long)sizeof(T));
+                }
+            }
+        }
+    } else {
+        const int ct = tid - 32;
+        const int rl = ct / 3, c = ct - rl * 3;
+        const bool active = rl < cnt;
+        T y0 = T(0), y1 = T(0), y2 = T(0);          // the chain: my row's result of the previous plane
+        int buf = 0;
+        // operands that do not depend on the tile's blocks are fetched one plane ahead
+        int q = a.base + (UPPER ? nz - 1 : 0) * a.ncols + col0 + rl;
+        int kb = 0, ke = 0, rn = 0, rn_n = 0, tb0 = 0, tb1 = 0;
+        T init = T(0);
+        T di[9];
+        {
+            const int q0 = q - rl;
+            tb0 = rowptr[q0]; tb1 = rowptr[q0 + cnt];
+            if (active) {
+                kb = rowptr[q]; ke = rowptr[q + 1]; rn = p2n[q];
+                if (nz > 1) rn_n = p2n[a.base + (UPPER ? nz - 2 : 1) * a.ncols + col0 + rl];
+                init = UPPER ? W[(size_t)q * 3 + c] : drhs[(size_t)rn * 3 + c];
+                if (UPPER) {
+#pragma unroll
+                    for (int e = 0; e < 9; ++e) di[e] = dinv[(size_t)q * 9 + e];
+                }
+            }
+        }
+        for (int s = 0; s < nz; ++s) {
+            const int st = s % kLineStages, ph = s / kLineStages;
+            // next plane's operands (in flight while this plane is computed)
+            const int qn = a.base + (UPPER ? nz - 2 - s : s + 1) * a.ncols + col0 + rl;
+            int kb_n = 0, ke_n = 0, rn_nn = 0, tb0_n = 0, tb1_n = 0;
+            T init_n = T(0);
+            T di_n[9];
+            if (s + 1 < nz) {
+                tb0_n = rowptr[qn - rl]; tb1_n = rowptr[qn - rl + cnt];
+                if (active) {
+                    kb_n = rowptr[qn]; ke_n = rowptr[qn + 1];
+                    if (s + 2 < nz) rn_nn = p2n[a.base + (UPPER ? nz - 3 - s : s + 2) * a.ncols + col0 + rl];      // two planes ahead: the gather below depends on it
+                    init_n = UPPER ? W[(size_t)qn * 3 + c] : drhs[(size_t)rn_n * 3 + c];
+                    if (UPPER) {
+#pragma unroll
+                        for (int e = 0; e < 9; ++e) di_n[e] = dinv[(size_t)qn * 9 + e];
+                    }
+                }
+            }
+            const bool tr = a.trace && blockIdx.x == 0 && ct == 0;
+            if (tr) a.trace[s * 8 + 0] = clock64();
+            const int b0 = tb0, b1 = tb1;
+            const int b0a = b0 & ~(kAl - 1), b1a = (b1 + kAl - 1) & ~(kAl - 1), c0a = b0 & ~3;
+            const bool direct = (b1a > nnzb) || (b1a - b0a > kCap);
+            const int qchain = s == 0 ? -1 : (UPPER ? q + a.ncols : q - a.ncols);      // my column one plane back in the walk
+            while (!mbar_try_wait(&full[st], (unsigned)(ph & 1))) {}
+            const unsigned char* stage = stages + (size_t)st * kLineStageBytes;
+            if (tr) a.trace[s * 8 + 1] = clock64();
+            T acc = init;
+            if (tr) a.trace[s * 8 + 2] = pipe_clock_after((int)__double_as_longlong((double)acc));
+            // every block but the chain's is gathered from the work vector (written by earlier launches); the
+            // chain's block comes last (mcorder.cpp checks it) and uses the values this thread kept.
+            // (Two copies of the loop: pointers into the stage must stay shared-memory pointers for the
+            // compiler -- a pointer that may also be global turns every access into a generic load, which was
+            // measured at ~400 cycles per dependent load on this path.)
+            auto row_blocks = [&](const T* vs, const int* cs) {
+                for (int kk = kb; kk < ke; kk += 8) {
+                    T xv[8][3];
+                    int cj[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        if (kk + u < ke) {
+                            cj[u] = cs[kk + u];
+                            if (cj[u] != qchain) {
+                                const T* xj = W + (size_t)cj[u] * 3;
+                                xv[u][0] = xj[0]; xv[u][1] = xj[1]; xv[u][2] = xj[2];
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        if (kk + u < ke) {
+                            const T* m = vs + (size_t)(kk + u) * 9;
+                            const bool chain = cj[u] == qchain;
+                            const T x0 = chain ? y0 : xv[u][0], x1 = chain ? y1 : xv[u][1], x2 = chain ? y2 : xv[u][2];
+                            acc = fma(-m[0], x0, acc);
+                            acc = fma(-m[1], x1, acc);
+                            acc = fma(-m[2], x2, acc);
+                        }
+                    }
+                }
+            };
+            if (active) {
+                if (!direct) {
+                    const T* vs = reinterpret_cast<const T*>(stage) + c * 3;
+                    const int* cs = reinterpret_cast<const int*>(stage + kSpmvValBytes);
+                    // (indices relative to the stage: blocks from b0a, columns from c0a)
+                    for (int kk = kb; kk < ke; kk += 8) {
+                        T xv[8][3];
+                        int cj[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            if (kk + u < ke) {
+                                cj[u] = cs[kk + u - c0a];
+                                if (cj[u] != qchain) {
+                                    const T* xj = W + (size_t)cj[u] * 3;
+                                    xv[u][0] = xj[0]; xv[u][1] = xj[1]; xv[u][2] = xj[2];
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            if (kk + u < ke) {
+                                const T* m = vs + (size_t)(kk + u - b0a) * 9;
+                                const bool chain = cj[u] == qchain;
+                                const T x0 = chain ? y0 : xv[u][0], x1 = chain ? y1 : xv[u][1], x2 = chain ? y2 : xv[u][2];
+                                acc = fma(-m[0], x0, acc);
+                                acc = fma(-m[1], x1, acc);
+                                acc = fma(-m[2], x2, acc);
+                            }
+                        }
+                    }
+                } else {
+                    row_blocks(vals + (size_t)c * 3, colidx);
+                }
+            }
+            // the three components of a row meet (a row's threads may sit in two warps)
+            if (tr) a.trace[s * 8 + 3] = pipe_clock_after((int)__double_as_longlong((double)acc));
+            T* sc = scratch + (size_t)buf * kLineGroupThreads;
+            sc[ct] = acc;
+            asm volatile("bar.sync 1, %0;" ::"n"(kLineGroupThreads) : "memory");
+            buf ^= 1;
+            if (tr) a.trace[s * 8 + 4] = clock64();
+            if (active) {
+                const T r0v = sc[rl * 3], r1v = sc[rl * 3 + 1], r2v = sc[rl * 3 + 2];
+                if (!UPPER) {
+                    y0 = r0v; y1 = r1v; y2 = r2v;
+                    W[(size_t)q * 3 + c] = acc;
+                } else {
+                    T v0 = T(0), v1 = T(0), v2 = T(0);
+                    v0 = fma(di[0], r0v, v0); v0 = fma(di[1], r1v, v0); v0 = fma(di[2], r2v, v0);
+                    v1 = fma(di[3], r0v, v1); v1 = fma(di[4], r1v, v1); v1 = fma(di[5], r2v, v1);
+                    v2 = fma(di[6], r0v, v2); v2 = fma(di[7], r1v, v2); v2 = fma(di[8], r2v, v2);
+                    y0 = v0; y1 = v1; y2 = v2;
+                    const T v = c == 0 ? v0 : (c == 1 ? v1 : v2);
+                    W[(size_t)q * 3 + c] = v;
+                    out[(size_t)rn * 3 + c] = a.scale ? v * wrel : v;
+                }
+            }
+            if (tr) a.trace[s * 8 + 5] = pipe_clock_after((int)__double_as_longlong((double)y0));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[st]);
+            if (tr) a.trace[s * 8 + 6] = clock64();
+            // roll the prefetched operands
+            q = qn; kb = kb_n; ke = ke_n; tb0 = tb0_n; tb1 = tb1_n; rn = rn_n; rn_n = rn_nn; init = init_n;
+            if (UPPER) {
+#pragma unroll
+                for (int e = 0; e < 9; ++e) di[e] = di_n[e];
+            }
+            if (tr) a.trace[s * 8 + 7] = pipe_clock_after(kb + rn + (int)__double_as_longlong((double)init));
         }
     }
 }

@@ -1,5 +1,6 @@
 // Host analysis of the multicolour ILU0 variant (mcorder.hpp).  Once per pattern.
 #include "mcorder.hpp"
+#include "analysis.hpp"      // infer_cartesian_grid
 
 #include <algorithm>
 #include <numeric>
@@ -42,9 +43,37 @@ void multicolour_order(int N, const int* rowptr, const int* colidx, McOrder& o)
     }
 }
 
-void build_mc_program(int N, const int* rowptr, const int* colidx, McProgram& m)
+void line_order(int nx, int ny, int nz, McOrder& o)
 {
-    multicolour_order(N, rowptr, colidx, m.ord);
+    const int N = nx * ny * nz, plane = nx * ny;
+    o = McOrder();
+    o.lines = true; o.nx = nx; o.nz = nz; o.ncolours = plane > 1 ? 2 : 1;
+    std::vector<int> rank(plane);          // rank of a column among the columns of its colour, natural (i + nx j) order
+    for (int j = 0; j < ny; ++j)
+        for (int i = 0; i < nx; ++i) rank[i + nx * j] = o.ncols[(i + j) & 1]++;
+    o.base[0] = 0; o.base[1] = nz * o.ncols[0];
+    o.colour.resize(N); o.p2n.resize(N); o.n2p.resize(N);
+    for (int k = 0; k < nz; ++k)
+        for (int j = 0; j < ny; ++j)
+            for (int i = 0; i < nx; ++i) {
+                const int cell = i + nx * (j + ny * k), c = (i + j) & 1;
+                const int q = o.base[c] + k * o.ncols[c] + rank[i + nx * j];
+                o.colour[cell] = c; o.n2p[cell] = q; o.p2n[q] = cell;
+            }
+    o.colour_ptr = {0, o.base[1]};
+    if (o.ncolours == 2) o.colour_ptr.push_back(N);
+}
+
+bool build_mc_program(int N, const int* rowptr, const int* colidx, McProgram& m, bool lines)
+{
+    if (lines) {
+        int nx = 0, ny = 0, nz = 0;
+        infer_cartesian_grid(N, rowptr, colidx, nx, ny, nz);
+        if (nx <= 0 || (long long)nx * ny * nz != N) return false;
+        line_order(nx, ny, nz, m.ord);
+    } else {
+        multicolour_order(N, rowptr, colidx, m.ord);
+    }
     const std::vector<int>& p2n = m.ord.p2n;
     const std::vector<int>& n2p = m.ord.n2p;
     const int nnzb = rowptr[N];
@@ -89,6 +118,23 @@ void build_mc_program(int N, const int* rowptr, const int* colidx, McProgram& m)
             }
         }
     }
+    // update lists of the factorisation (what Dune::bilu0_decomposition finds by walking both rows)
+    m.pair_ptr.assign((size_t)nnzL + 1, 0);
+    m.pair_jk.clear(); m.pair_ik.clear();
+    for (int q = 0; q < N; ++q) {
+        const int iend = m.prowptr[q + 1];
+        for (int ij = m.prowptr[q]; ij < m.pdiag[q]; ++ij) {
+            const int j = m.pcol[ij];
+            int jk = m.pdiag[j] + 1, ik = ij + 1;
+            const int jend = m.prowptr[j + 1];
+            while (ik < iend && jk < jend) {
+                if (m.pcol[ik] == m.pcol[jk]) { m.pair_jk.push_back(m.ppos[jk]); m.pair_ik.push_back(m.ppos[ik]); ++ik; ++jk; }
+                else if (m.pcol[ik] < m.pcol[jk]) ++ik;
+                else ++jk;
+            }
+            m.pair_ptr[(size_t)m.ppos[ij] + 1] = (int)m.pair_jk.size();
+        }
+    }
     // level sets of the permuted lower triangle
     std::vector<int> lev(N, 0);
     int nlev = 0;
@@ -103,6 +149,21 @@ void build_mc_program(int N, const int* rowptr, const int* colidx, McProgram& m)
     m.lvl_rows.resize(N);
     std::vector<int> f(m.lvl_ptr.begin(), m.lvl_ptr.end() - 1);
     for (int q = 0; q < N; ++q) m.lvl_rows[f[lev[q]]++] = q;
+    if (lines) {
+        // what the line kernels rely on, checked for EVERY row (the grid inference is only a heuristic): the
+        // one same-colour lower block is the row's own column one plane down, the one same-colour upper
+        // block its own column one plane up; being the highest lower / lowest upper column they are the
+        // last blocks the sweeps visit
+        for (int q = 0; q < N; ++q) {
+            const int c = q >= m.ord.base[1] && m.ord.ncolours == 2 ? 1 : 0;
+            const int lo = m.ord.base[c], hi = c == 0 && m.ord.ncolours == 2 ? m.ord.base[1] : N, nc = m.ord.ncols[c];
+            for (int k = m.Lrowptr[q]; k < m.Lrowptr[q + 1]; ++k)
+                if (m.Lcol[k] >= lo && m.Lcol[k] < hi && m.Lcol[k] != q - nc) return false;
+            for (int k = m.Urowptr[q]; k < m.Urowptr[q + 1]; ++k)
+                if (m.Ucol[k] >= lo && m.Ucol[k] < hi && m.Ucol[k] != q + nc) return false;
+        }
+    }
+    return true;
 }
 
 }  // namespace opmgpu

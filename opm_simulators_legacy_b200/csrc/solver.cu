@@ -162,14 +162,16 @@ struct ColDevMem {
 struct McDevMem {
     bool valid = false;
     int ncolours = 0;
+    bool lines = false;          // k-line ordering (mc_line_sweep_kernel): per colour the columns, planes, columns per CTA
+    int nz = 0, nx = 0, ncols[2] = {0, 0}, base[2] = {0, 0}, rb[2] = {4, 4};
     long long nnzL = 0, nnzU = 0, offD = 0, offU = 0, total_blocks = 0;
     std::vector<int> colour_ptr, lvl_ptr, p2n_host, n2p_host;
-    DevArr<int> p2n, prowptr, pcol, pdiag, psrc, ppos, Lrowptr, Lcol, Urowptr, Ucol, lvl_rows;
+    DevArr<int> p2n, psrc, ppos, Lrowptr, Lcol, Urowptr, Ucol, lvl_rows, pair_ptr, pair_jk, pair_ik;
     DevArr<double> uni;          // [ L | Dinv | U ] blocks of T (allocated for doubles)
     void release()
     {
         valid = false;
-        p2n.release(); prowptr.release(); pcol.release(); pdiag.release(); psrc.release(); ppos.release();
+        p2n.release(); psrc.release(); ppos.release(); pair_ptr.release(); pair_jk.release(); pair_ik.release();
         Lrowptr.release(); Lcol.release(); Urowptr.release(); Ucol.release(); lvl_rows.release(); uni.release();
     }
 };
@@ -672,7 +674,10 @@ int set_pattern_mc(opmgpu_handle h, int N, int nnzb, const int* rowptr, const in
         }
     }
     McProgram m;
-    build_mc_program(N, rowptr, colidx, m);
+    const bool lines = h->ilu_order_req == OPMGPU_ILU_MULTICOLOUR_LINES;
+    if (!build_mc_program(N, rowptr, colidx, m, lines))
+        return h->bad("the k-line ordering needs a Cartesian stencil pattern in natural numbering whose only same-colour "
+                      "couplings are the vertical ones (use OPMGPU_ILU_MULTICOLOUR for general patterns)");
     h->use_pipe = false; h->use_col = false; h->cluster_size = 1;
     h->pipeL.release(); h->pipeU.release(); h->pipeF.release(); h->progL.release(); h->progU.release(); h->col.release();
     h->d_lu.release();                  // built on demand by opmgpu_ilu0_get_factors
@@ -692,7 +697,7 @@ int set_pattern_mc(opmgpu_handle h, int N, int nnzb, const int* rowptr, const in
         return 0;
     };
     int rc;
-    if ((rc = up(d.p2n, m.ord.p2n)) || (rc = up(d.prowptr, m.prowptr)) || (rc = up(d.pcol, m.pcol)) || (rc = up(d.pdiag, m.pdiag)) ||
+    if ((rc = up(d.p2n, m.ord.p2n)) || (rc = up(d.pair_ptr, m.pair_ptr)) || (rc = up(d.pair_jk, m.pair_jk)) || (rc = up(d.pair_ik, m.pair_ik)) ||
         (rc = up(d.psrc, m.psrc)) || (rc = up(d.ppos, m.ppos)) || (rc = up(d.Lrowptr, m.Lrowptr)) || (rc = up(d.Lcol, m.Lcol)) ||
         (rc = up(d.Urowptr, m.Urowptr)) || (rc = up(d.Ucol, m.Ucol)) || (rc = up(d.lvl_rows, m.lvl_rows))) return rc;
     CK(d.uni.ensure((size_t)m.total_blocks * 9));
@@ -703,8 +708,14 @@ int set_pattern_mc(opmgpu_handle h, int N, int nnzb, const int* rowptr, const in
     d.nnzL = m.Lrowptr[N]; d.nnzU = m.Urowptr[N]; d.offD = m.offD; d.offU = m.offU; d.total_blocks = m.total_blocks;
     d.colour_ptr = m.ord.colour_ptr; d.lvl_ptr = m.lvl_ptr;
     d.p2n_host = std::move(m.ord.p2n); d.n2p_host = std::move(m.ord.n2p);
+    d.lines = lines; d.nz = m.ord.nz; d.nx = m.ord.nx;
+    for (int c = 0; c < 2; ++c) {
+        d.ncols[c] = m.ord.ncols[c]; d.base[c] = m.ord.base[c];
+        const int per_cta = (d.ncols[c] + h->sm_count - 1) / std::max(1, h->sm_count);
+        d.rb[c] = std::min(kSpmvRows, std::max(4, (per_cta + 3) / 4 * 4));
+    }
     d.valid = true;
-    h->nlevL = h->nlevU = d.ncolours;
+    h->nlevL = h->nlevU = lines ? d.ncolours * d.nz : d.ncolours;
     h->have_pattern = true;
     return OPMGPU_OK;
 }
@@ -721,7 +732,7 @@ int set_pattern(opmgpu_handle h, int N, int nnzb, const int* rowptr, const int* 
     }
     h->have_pattern = h->have_values = h->have_factors = false;
     h->operator_only = false;
-    if (h->ilu_order_req == 1) return set_pattern_mc(h, N, nnzb, rowptr, colidx);
+    if (h->ilu_order_req != OPMGPU_ILU_NATURAL) return set_pattern_mc(h, N, nnzb, rowptr, colidx);
     h->mc.release();
     analyse_pattern(N, rowptr, colidx, h->sweep_ctas, h->an, h->force_simple, &h->caps);
     h->cluster_size = h->an.cluster_size;
@@ -1178,11 +1189,19 @@ int mc_factor(opmgpu_handle h, int* bad_row)
     h->launches++;
     const int big = 0x7fffffff;
     CK(cudaMemcpyAsync(h->d_bad.p, &big, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    if (d.lines) {
+        for (int c = 0; c < d.ncolours; ++c) {
+            if (d.ncols[c] <= 0) continue;
+            mc_factor_lines_kernel<T><<<(d.ncols[c] + 31) / 32, 32, 0, h->stream>>>(d.base[c], d.ncols[c], d.nz, d.Lrowptr.p, d.Lcol.p, d.pair_ptr.p,
+                                                                                    d.pair_jk.p, d.pair_ik.p, d.offD, uni, h->d_bad.p);
+            h->launches++;
+        }
+    } else
     for (size_t l = 0; l + 1 < d.lvl_ptr.size(); ++l) {
         const int n = d.lvl_ptr[l + 1] - d.lvl_ptr[l];
         if (n <= 0) continue;
-        mc_factor_level_kernel<T><<<(n + 127) / 128, 128, 0, h->stream>>>(d.lvl_rows.p, d.lvl_ptr[l], d.lvl_ptr[l + 1], d.prowptr.p, d.pcol.p,
-                                                                          d.pdiag.p, d.ppos.p, uni, h->d_bad.p);
+        mc_factor_level_kernel<T><<<(n + 127) / 128, 128, 0, h->stream>>>(d.lvl_rows.p, d.lvl_ptr[l], d.lvl_ptr[l + 1], d.Lrowptr.p, d.Lcol.p,
+                                                                          d.pair_ptr.p, d.pair_jk.p, d.pair_ik.p, d.offD, uni, h->d_bad.p);
         h->launches++;
     }
     CK(cudaGetLastError());
@@ -1445,10 +1464,53 @@ int mc_launch(opmgpu_handle h, McSweepArgs& a)
     return 0;
 }
 
+// k-line ordering: lower sweep colour by colour, upper sweep in the opposite order; a launch walks the planes
+template <class T>
+int mc_apply_lines(opmgpu_handle h, double w, const T* d, T* v)
+{
+    McDevMem& m = h->mc;
+    const T* uni = reinterpret_cast<const T*>(m.uni.p);
+    McLineArgs a;
+    a.nz = m.nz; a.p2n = m.p2n.p; a.d = d; a.W = vec<T>(h->d_yL); a.dinv = uni + (size_t)m.offD * 9; a.out = v;
+    a.w = w; a.scale = std::fabs(w - 1.0) > 1e-15 ? 1 : 0;
+    for (int pass = 0; pass < 2 * m.ncolours; ++pass) {
+        const bool upper = pass >= m.ncolours;
+        const int c = upper ? 2 * m.ncolours - 1 - pass : pass;
+        if (m.ncols[c] <= 0) continue;
+        a.base = m.base[c]; a.ncols = m.ncols[c]; a.rb = m.rb[c];
+        a.obase = m.base[1 - c]; a.oncols = m.ncolours == 2 ? m.ncols[1 - c] : 0; a.nx = m.nx; a.plane = m.ncols[0] + m.ncols[1];
+        if (upper) { a.nnz = (int)m.nnzU; a.rowptr = m.Urowptr.p; a.colidx = m.Ucol.p; a.vals = uni + (size_t)m.offU * 9; }
+        else { a.nnz = (int)m.nnzL; a.rowptr = m.Lrowptr.p; a.colidx = m.Lcol.p; a.vals = uni; }
+        const void* fn = upper ? (const void*)mc_line_sweep_kernel<true, T> : (const void*)mc_line_sweep_kernel<false, T>;
+        a.trace = nullptr;
+        const bool trace = exp_env("OPMGPU_LINE_TRACE") != nullptr;          // (experiments build) per-step clock stamps of one warp
+        if (trace) {
+            CK(h->d_trace.ensure((size_t)m.nz * 8));
+            CK(cudaMemsetAsync(h->d_trace.p, 0, sizeof(long long) * (size_t)m.nz * 8, h->stream));
+            a.trace = h->d_trace.p;
+        }
+        void* args[] = {&a};
+        CK(cudaLaunchKernel(fn, dim3((unsigned)((a.ncols + a.rb - 1) / a.rb)), dim3(kLineThreads), args, kLineSmemBytes, h->stream));
+        h->launches++;
+        if (trace) {
+            std::vector<long long> tr((size_t)m.nz * 8);
+            CK(cudaMemcpyAsync(tr.data(), h->d_trace.p, sizeof(long long) * tr.size(), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            fprintf(stderr, "[opmgpu] line sweep %s colour %d: step | start(rel) wait first-use chain exchange result arrive roll (cycles)\n", upper ? "upper" : "lower", c);
+            for (int s2 = 20; s2 < std::min(m.nz, 28); ++s2) {
+                const long long* q = &tr[(size_t)s2 * 8];
+                fprintf(stderr, "  %3d | %7lld %5lld %5lld %5lld %5lld %5lld %5lld %5lld\n", s2, q[0] - tr[20 * 8], q[1] - q[0], q[2] - q[1], q[3] - q[2], q[4] - q[3], q[5] - q[4], q[6] - q[5], q[7] - q[6]);
+            }
+        }
+    }
+    return 0;
+}
+
 template <class T>
 int mc_apply(opmgpu_handle h, double w, const T* d, T* v)
 {
     McDevMem& m = h->mc;
+    if (m.lines) return mc_apply_lines<T>(h, w, d, v);
     const int C = m.ncolours;
     const T* uni = reinterpret_cast<const T*>(m.uni.p);
     McSweepArgs a;
@@ -2178,6 +2240,10 @@ int opmgpu_create(int device, opmgpu_handle* out)
     cudaFuncSetAttribute(spmv3_tma_kernel<0, double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
     cudaFuncSetAttribute(spmv3_tma_kernel<1, double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
     cudaFuncSetAttribute(spmv3_tma_kernel<2, double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes);
+    cudaFuncSetAttribute(mc_line_sweep_kernel<false, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLineSmemBytes);
+    cudaFuncSetAttribute(mc_line_sweep_kernel<true, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLineSmemBytes);
+    cudaFuncSetAttribute(mc_line_sweep_kernel<false, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLineSmemBytes);
+    cudaFuncSetAttribute(mc_line_sweep_kernel<true, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLineSmemBytes);
     cudaFuncSetAttribute(mc_sweep_tma_kernel<0, double, false, kSpmvRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMcSmemBytes);
     cudaFuncSetAttribute(mc_sweep_tma_kernel<1, double, false, kSpmvRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMcSmemBytes);
     cudaFuncSetAttribute(mc_sweep_tma_kernel<2, double, false, kSpmvRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMcSmemBytes);
@@ -3037,7 +3103,8 @@ int opmgpu_solve_from_csc_blocks_np(opmgpu_handle h, int N, int np, const opmgpu
 int opmgpu_set_ilu_ordering(opmgpu_handle h, int ordering)
 {
     if (!h) return OPMGPU_BAD_ARGUMENT;
-    if (ordering != OPMGPU_ILU_NATURAL && ordering != OPMGPU_ILU_MULTICOLOUR) return h->bad("unknown ILU0 ordering");
+    if (ordering != OPMGPU_ILU_NATURAL && ordering != OPMGPU_ILU_MULTICOLOUR && ordering != OPMGPU_ILU_MULTICOLOUR_LINES)
+        return h->bad("unknown ILU0 ordering");
     if (ordering != OPMGPU_ILU_NATURAL && (h->multi || h->world > 1 || h->comm))
         return h->bad("the multicolour ILU0 variant exists for plain single-GPU handles");
     if (ordering != h->ilu_order_req) {          // takes effect with the next pattern
@@ -3047,7 +3114,7 @@ int opmgpu_set_ilu_ordering(opmgpu_handle h, int ordering)
     }
     return OPMGPU_OK;
 }
-int opmgpu_get_ilu_ordering(opmgpu_handle h) { return h && h->ilu_order_req == 1 ? OPMGPU_ILU_MULTICOLOUR : OPMGPU_ILU_NATURAL; }
+int opmgpu_get_ilu_ordering(opmgpu_handle h) { return h ? h->ilu_order_req : OPMGPU_ILU_NATURAL; }
 
 int opmgpu_multicolour_order(int N, const int* rowptr, const int* colidx, int* ncolours, int* colour, int* n2p)
 {
@@ -3057,6 +3124,15 @@ int opmgpu_multicolour_order(int N, const int* rowptr, const int* colidx, int* n
     if (ncolours) *ncolours = o.ncolours;
     if (colour) std::copy(o.colour.begin(), o.colour.end(), colour);
     if (n2p) std::copy(o.n2p.begin(), o.n2p.end(), n2p);
+    return OPMGPU_OK;
+}
+
+int opmgpu_line_order(int nx, int ny, int nz, int* n2p)
+{
+    if (nx < 1 || ny < 1 || nz < 1 || !n2p) return OPMGPU_BAD_ARGUMENT;
+    McOrder o;
+    line_order(nx, ny, nz, o);
+    std::copy(o.n2p.begin(), o.n2p.end(), n2p);
     return OPMGPU_OK;
 }
 

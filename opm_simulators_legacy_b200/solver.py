@@ -97,6 +97,15 @@ def multicolour_order(rowptr, colidx):
     return nc.value, colour, n2p
 
 
+def line_order(nx, ny, nz):
+    """n2p of the k-line ordering (red-black over the (i,j) columns, natural order along k); host only."""
+    lib = L.load()
+    n2p = np.empty(nx * ny * nz, dtype=np.int32)
+    if lib.opmgpu_line_order(int(nx), int(ny), int(nz), _ip(n2p)) != L.OK:
+        raise ValueError("opmgpu_line_order: bad dimensions")
+    return n2p
+
+
 class GpuLinearSolver:
     """One opmgpu handle (one GPU, one stream)."""
 
@@ -193,10 +202,12 @@ class GpuLinearSolver:
         self._check(self.lib.opmgpu_set_pattern_bcrs_operator_only(self.h, self.N, self.nnzb, _ip(rowptr), _ip(colidx)))
 
     # -- multicolour ILU0: a flagged variant, not the reference's preconditioner ----------------
-    def set_ilu_ordering(self, multicolour: bool):
-        """Prepare the NEXT pattern for the natural (reference) or the multicolour ordering of the
-        ILU0 (include/opm_gpu_solver.h: iteration counts of the variant are never parity)."""
-        self._check(self.lib.opmgpu_set_ilu_ordering(self.h, L.ILU_MULTICOLOUR if multicolour else L.ILU_NATURAL))
+    def set_ilu_ordering(self, multicolour):
+        """Prepare the NEXT pattern for the natural (reference) ordering of the ILU0 (False / 0), the
+        multicolour ordering (True / 1) or the k-line ordering ("lines" / 2; Cartesian stencils only).
+        include/opm_gpu_solver.h: iteration counts of the variants are never parity."""
+        o = L.ILU_MULTICOLOUR_LINES if multicolour == "lines" else int(multicolour)
+        self._check(self.lib.opmgpu_set_ilu_ordering(self.h, o))
 
     def ilu_ordering(self) -> int:
         return int(self.lib.opmgpu_get_ilu_ordering(self.h))

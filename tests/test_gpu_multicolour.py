@@ -213,3 +213,86 @@ def test_ilu_redblack_key_selects_the_variant_in_the_drop_in(oracle):
         x_cell = np.ascontiguousarray(dx.reshape(3, N).T)
         r = rhs_cell - oracle.spmv(orp, oci, ov, x_cell)
         assert np.linalg.norm(r) <= 1.0001e-2 * np.linalg.norm(rhs_cell)
+
+
+# ---- k-line ordering (OPMGPU_ILU_MULTICOLOUR_LINES): Cartesian stencils only -------------------------
+LINE_CASES = {
+    "c1_spe1_shape": ((10, 10, 3), "homogeneous"),
+    "small_lognormal": ((24, 20, 12), "lognormal"),
+    "odd_sizes": ((33, 17, 5), "lognormal"),            # column counts of the colours differ, not multiples of 4
+    "tall": ((7, 6, 40), "lognormal"),                  # more planes than pipeline stages, tiny tiles
+    "plane_2d": ((30, 17, 1), "lognormal"),             # one plane: point red-black
+    "mid_lognormal": ((40, 40, 20), "lognormal"),
+    "wide": ((120, 125, 6), "lognormal"),               # 64-row tiles, several column blocks per SM
+}
+
+
+@pytest.fixture(scope="module", params=list(LINE_CASES))
+def line_case(request):
+    dims, perm = LINE_CASES[request.param]
+    return dims, _stencil(dims, perm)
+
+
+@pytest.fixture(scope="module", params=["f64", "f32"])
+def line_solver(request):
+    s = GpuLinearSolver(0)
+    s.set_precision(request.param == "f32")
+    s.set_ilu_ordering("lines")
+    s.f32 = request.param == "f32"
+    yield s
+    s.close()
+
+
+def test_lines_factor_apply_bit_exact_and_iteration_parity(line_solver, oracle, line_case):
+    from opm_simulators_legacy_b200.solver import line_order
+    dims, (rp, ci, v, b) = line_case
+    g = line_solver
+    orc = oracle.f32 if g.f32 else oracle
+    g.set_pattern(rp, ci)
+    nc, n2p = g.ilu_permutation()
+    assert np.array_equal(n2p, line_order(*dims))
+    g.set_values(v)
+    assert g.ilu0_factor() == -1
+    prp, pci, pv, order, p2n = _permuted(rp, ci, v, n2p)
+    lu_ref, bad = orc.ilu0_factor(prp, pci, pv)
+    assert bad == -1
+    assert np.array_equal(g.ilu0_factors()[order], lu_ref.astype(np.float64))
+    for w in (0.9, 1.0):
+        got = g.ilu0_apply(w, b.reshape(-1))
+        ref = orc.ilu0_apply(prp, pci, lu_ref, w, b[p2n].reshape(-1)).astype(np.float64)
+        back = np.empty_like(ref)
+        back[p2n] = ref
+        assert np.array_equal(got.reshape(-1, 3), back)
+    x, res = g.solve_bcrs(v, b.reshape(-1))
+    xp, ref = orc.solve_bcrs(prp, pci, pv, b[p2n].reshape(-1))
+    assert res["converged"] == 1 and res["reduction"] < 1e-2
+    if g.f32:
+        assert abs(res["half_steps"] - ref["half_steps"]) <= 1
+    else:
+        assert res["iterations"] == ref["iterations"] and res["half_steps"] == ref["half_steps"]
+    x_ref = np.empty((rp.size - 1, 3))
+    x_ref[p2n] = xp
+    tol = 3e-2 if g.f32 else 1e-6
+    assert (np.abs(x.reshape(-1, 3) - x_ref).max(0) <= tol * np.abs(x_ref).max(0)).all()
+
+
+def test_lines_refuse_patterns_that_are_not_cartesian_stencils():
+    g = GpuLinearSolver(0)
+    try:
+        g.set_ilu_ordering("lines")
+        rp, ci, v, b = _general(500, 3, 6)
+        with pytest.raises(ValueError, match="Cartesian"):
+            g.set_pattern(rp, ci)
+        # a stencil with one extra same-colour coupling (a well's Schur fill between two cells of one column colour)
+        s = synth_blackoil_jacobian(8, 8, 4, perm="homogeneous")
+        rp, ci = s.rowptr.numpy(), s.colidx.numpy()
+        import scipy.sparse as sp
+        A = sp.csr_matrix((np.ones(ci.size), ci, rp)).tolil()
+        A[0, 2] = 1; A[2, 0] = 1                           # cells (0,0,0) and (2,0,0): same colour
+        A = A.tocsr(); A.sort_indices()
+        with pytest.raises(ValueError, match="Cartesian"):
+            g.set_pattern(A.indptr.astype(np.int32), A.indices.astype(np.int32))
+        g.set_ilu_ordering(True)                            # the point colouring takes any pattern
+        g.set_pattern(A.indptr.astype(np.int32), A.indices.astype(np.int32))
+    finally:
+        g.close()

@@ -6,7 +6,7 @@ counts are NOT the reference's natural-order counts and are never reported as pa
 import numpy as np
 
 from opm_simulators_legacy_b200.jacobian import synth_blackoil_jacobian, random_bcrs
-from opm_simulators_legacy_b200.solver import multicolour_order
+from opm_simulators_legacy_b200.solver import multicolour_order, line_order
 
 
 def greedy_reference(rp, ci):
@@ -89,3 +89,29 @@ def test_oracle_on_the_permuted_system_solves_the_same_problem(oracle):
     assert np.abs(x - xn).max() <= 1e-6 * np.abs(xn).max()
     # a different preconditioner: the counts need not agree (and do not on this system)
     assert resp["iterations"] != resn["iterations"]
+
+
+def test_line_order_is_red_black_over_columns_with_natural_order_inside(oracle):
+    nx, ny, nz = 7, 5, 6
+    n2p = line_order(nx, ny, nz)
+    k, j, i = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    i, j, k = i.ravel(), j.ravel(), k.ravel()
+    nat = np.arange(nx * ny * nz)
+    p2n_ref = np.lexsort((nat, (i + j) % 2))                # colour, then natural index (k-major inside a colour)
+    assert np.array_equal(np.argsort(n2p), p2n_ref)
+    # a column's cells keep their order and are one colour-plane stride apart
+    ncols = [((i + j) % 2 == c)[:nx * ny].sum() for c in (0, 1)]
+    col = 3 + nx * 2                                        # column (3, 2): colour 1
+    q = n2p[col + nx * ny * np.arange(nz)]
+    assert (np.diff(q) == ncols[1]).all() and q[0] >= nz * ncols[0]
+    # on a reservoir-like system (strong vertical couplings) the ordering is at least as good as point red-black
+    s = synth_blackoil_jacobian(14, 12, 10, perm="lognormal")
+    rp, ci, v, b = s.rowptr.numpy(), s.colidx.numpy(), s.vals.numpy(), s.rhs.numpy()
+    n2p = line_order(14, 12, 10)
+    p2n = np.argsort(n2p)
+    prp, pci, pv, order = permute_bcrs(rp, ci, v, n2p)
+    xl, rl = oracle.solve_bcrs(prp, pci, pv, b.reshape(-1, 3)[p2n])
+    nc, colour, n2p_rb = multicolour_order(rp, ci)
+    prp, pci, pv, order = permute_bcrs(rp, ci, v, n2p_rb)
+    xr, rr = oracle.solve_bcrs(prp, pci, pv, b.reshape(-1, 3)[np.argsort(n2p_rb)])
+    assert rl["converged"] and rr["converged"] and rl["half_steps"] <= rr["half_steps"]

@@ -16,7 +16,7 @@ s = synth_blackoil_jacobian(nx, ny, nz, perm="lognormal")
 g = GpuLinearSolver(0)
 g.set_precision(single)
 if os.environ.get("MB_MULTICOLOUR"):          # the flagged multicolour-ILU0 variant
-    g.set_ilu_ordering(True)
+    g.set_ilu_ordering("lines" if os.environ["MB_MULTICOLOUR"] == "lines" else True)
 g.set_pattern(s.rowptr.numpy(), s.colidx.numpy())
 vals = s.vals.cuda(); rhs = s.rhs.cuda(); y = torch.zeros_like(rhs)
 g.set_values_dev(vals)

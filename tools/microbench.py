@@ -35,7 +35,7 @@ def main():
     torch.cuda.set_stream(st)
     g.use_torch_stream()
     if os.environ.get("MB_MULTICOLOUR"):          # the flagged multicolour-ILU0 variant
-        g.set_ilu_ordering(True)
+        g.set_ilu_ordering("lines" if os.environ["MB_MULTICOLOUR"] == "lines" else True)
     t0 = time.time()
     g.set_pattern(s.rowptr.numpy(), s.colidx.numpy())
     tan = time.time() - t0
