@@ -391,9 +391,20 @@ __device__ __forceinline__ void line_prefetch_l2(const void* base, long long lo_
 
 constexpr int kLineGroupThreads = kSpmvComputeWarps * 32;          // 192 = 64 rows x 3 components
 constexpr int kLineThreads = 32 + kLineGroupThreads;
-constexpr int kLineStages = 6;
+constexpr int kLineStages = 5;
+constexpr int kLineAhead = 4;             // planes the per-row operands are fetched ahead
 constexpr int kLineStageBytes = kSpmvValBytes + kSpmvColBytes;
-constexpr size_t kLineSmemBytes = 128 + (size_t)kLineStages * kLineStageBytes + 2 * kLineGroupThreads * sizeof(double);
+// barriers | tile headers | stages | scratch [4][threads] | value ring [ahead][threads][4] | index ring [ahead][threads][2] | p2n ring [2*ahead][threads]
+constexpr size_t kLineSmemBytes = 256 + (size_t)kLineStages * kLineStageBytes + 4 * kLineGroupThreads * sizeof(double) +
+                                  (size_t)kLineAhead * kLineGroupThreads * (4 * sizeof(double) + 2 * sizeof(int)) +
+                                  (size_t)2 * kLineAhead * kLineGroupThreads * sizeof(int);
+static_assert(kLineSmemBytes <= 227 * 1024, "line sweep: shared memory of one CTA");
+
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void* dst_smem, const void* src_gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "n"(BYTES) : "memory");
+}
 
 template <bool UPPER, class T>
 __global__ void __launch_bounds__(kLineThreads, 1)
@@ -404,8 +415,13 @@ mc_line_sweep_kernel(McLineArgs a)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned long long* full = reinterpret_cast<unsigned long long*>(smem_raw);
     unsigned long long* empty = full + kLineStages;
-    unsigned char* stages = smem_raw + 128;
-    T* scratch = reinterpret_cast<T*>(smem_raw + 128 + (size_t)kLineStages * kLineStageBytes);      // [2][kLineGroupThreads]
+    int* hdr = reinterpret_cast<int*>(smem_raw + 128);          // [stages][2]: block range of the tile in the stage
+    unsigned char* stages = smem_raw + 256;
+    T* scratch = reinterpret_cast<T*>(smem_raw + 256 + (size_t)kLineStages * kLineStageBytes);      // [4][kLineGroupThreads]
+    T* ring_v = reinterpret_cast<T*>(smem_raw + 256 + (size_t)kLineStages * kLineStageBytes + 4 * kLineGroupThreads * sizeof(double));
+    int* ring_i = reinterpret_cast<int*>(smem_raw + 256 + (size_t)kLineStages * kLineStageBytes + 4 * kLineGroupThreads * sizeof(double) +
+                                         (size_t)kLineAhead * kLineGroupThreads * 4 * sizeof(double));
+    int* ring_rn = ring_i + (size_t)kLineAhead * kLineGroupThreads * 2;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nnzb = a.nnz;
     const int* __restrict__ rowptr = a.rowptr;
@@ -451,6 +467,7 @@ mc_line_sweep_kernel(McLineArgs a)
             const unsigned cbytes = (direct || b1 == b0) ? 0u : (unsigned)((((b1 - c0a) * 4) + 15) & ~15);
             const unsigned vbytes = (direct || b1 == b0) ? 0u : (unsigned)((b1a - b0a) * 9 * (int)sizeof(T));
             if (lane == 0) {
+                hdr[st * 2] = b0; hdr[st * 2 + 1] = b1;          // (the arrive below releases them to the consumers)
                 if (cbytes + vbytes == 0) mbar_arrive(&full[st]);
                 else mbar_arrive_expect_tx(&full[st], cbytes + vbytes);
             }
@@ -481,96 +498,75 @@ mc_line_sweep_kernel(McLineArgs a)
             }
         }
     } else {
+        // Consumers.  What a row needs besides its blocks (block range, natural row, right-hand side or
+        // lower result, its row of Dinv) is fetched kLineAhead planes ahead with cp.async into a small
+        // per-thread ring in shared memory (the natural row two rings ahead, because the right-hand side
+        // is gathered through it): a load issued at plane s and consumed at plane s + 1 costs a full
+        // memory latency (~1.1 us measured) per plane.
         const int ct = tid - 32;
         const int rl = ct / 3, c = ct - rl * 3;
         const bool active = rl < cnt;
         T y0 = T(0), y1 = T(0), y2 = T(0);          // the chain: my row's result of the previous plane
         int buf = 0;
-        // operands that do not depend on the tile's blocks are fetched one plane ahead
-        int q = a.base + (UPPER ? nz - 1 : 0) * a.ncols + col0 + rl;
-        int kb = 0, ke = 0, rn = 0, rn_n = 0, tb0 = 0, tb1 = 0;
-        T init = T(0);
-        T di[9];
-        {
-            const int q0 = q - rl;
-            tb0 = rowptr[q0]; tb1 = rowptr[q0 + cnt];
+        auto row_of = [&](int s) { return a.base + (UPPER ? nz - 1 - s : s) * a.ncols + col0 + rl; };
+        auto issue = [&](int s) {                   // loads of plane s (p2n of plane s + kLineAhead); one group
             if (active) {
-                kb = rowptr[q]; ke = rowptr[q + 1]; rn = p2n[q];
-                if (nz > 1) rn_n = p2n[a.base + (UPPER ? nz - 2 : 1) * a.ncols + col0 + rl];
-                init = UPPER ? W[(size_t)q * 3 + c] : drhs[(size_t)rn * 3 + c];
-                if (UPPER) {
-#pragma unroll
-                    for (int e = 0; e < 9; ++e) di[e] = dinv[(size_t)q * 9 + e];
-                }
-            }
-        }
-        for (int s = 0; s < nz; ++s) {
-            const int st = s % kLineStages, ph = s / kLineStages;
-            // next plane's operands (in flight while this plane is computed)
-            const int qn = a.base + (UPPER ? nz - 2 - s : s + 1) * a.ncols + col0 + rl;
-            int kb_n = 0, ke_n = 0, rn_nn = 0, tb0_n = 0, tb1_n = 0;
-            T init_n = T(0);
-            T di_n[9];
-            if (s + 1 < nz) {
-                tb0_n = rowptr[qn - rl]; tb1_n = rowptr[qn - rl + cnt];
-                if (active) {
-                    kb_n = rowptr[qn]; ke_n = rowptr[qn + 1];
-                    if (s + 2 < nz) rn_nn = p2n[a.base + (UPPER ? nz - 3 - s : s + 2) * a.ncols + col0 + rl];      // two planes ahead: the gather below depends on it
-                    init_n = UPPER ? W[(size_t)qn * 3 + c] : drhs[(size_t)rn_n * 3 + c];
+                if (s < nz) {
+                    const int q = row_of(s);
+                    int* ri = ring_i + ((size_t)(s % kLineAhead) * kLineGroupThreads + ct) * 2;
+                    T* rv = ring_v + ((size_t)(s % kLineAhead) * kLineGroupThreads + ct) * 4;
+                    cp_async<4>(ri, rowptr + q); cp_async<4>(ri + 1, rowptr + q + 1);
                     if (UPPER) {
-#pragma unroll
-                        for (int e = 0; e < 9; ++e) di_n[e] = dinv[(size_t)qn * 9 + e];
+                        cp_async<sizeof(T)>(rv, W + (size_t)q * 3 + c);
+                        cp_async<sizeof(T)>(rv + 1, dinv + (size_t)q * 9 + c * 3);
+                        cp_async<sizeof(T)>(rv + 2, dinv + (size_t)q * 9 + c * 3 + 1);
+                        cp_async<sizeof(T)>(rv + 3, dinv + (size_t)q * 9 + c * 3 + 2);
+                    } else {
+                        const int rn4 = ring_rn[(size_t)(s % (2 * kLineAhead)) * kLineGroupThreads + ct];
+                        cp_async<sizeof(T)>(rv, drhs + (size_t)rn4 * 3 + c);
                     }
                 }
+                if (s + kLineAhead < nz) cp_async<4>(ring_rn + (size_t)((s + kLineAhead) % (2 * kLineAhead)) * kLineGroupThreads + ct, p2n + row_of(s + kLineAhead));
             }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        // prologue: natural rows of the first kLineAhead planes, then the planes themselves
+        if (active)
+            for (int s = 0; s < kLineAhead && s < nz; ++s) cp_async<4>(ring_rn + (size_t)s * kLineGroupThreads + ct, p2n + row_of(s));
+        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+        for (int s = 0; s < kLineAhead; ++s) issue(s);
+        for (int s = 0; s < nz; ++s) {
+            const int st = s % kLineStages, ph = s / kLineStages;
+            asm volatile("cp.async.wait_group %0;" ::"n"(kLineAhead - 1) : "memory");      // the group of plane s has landed
+            const int q = row_of(s);
+            int kb = 0, ke = 0, rn = 0;
+            T init = T(0), di0 = T(0), di1 = T(0), di2 = T(0);
+            if (active) {
+                const int* ri = ring_i + ((size_t)(s % kLineAhead) * kLineGroupThreads + ct) * 2;
+                const T* rv = ring_v + ((size_t)(s % kLineAhead) * kLineGroupThreads + ct) * 4;
+                kb = ri[0]; ke = ri[1]; init = rv[0];
+                if (UPPER) { di0 = rv[1]; di1 = rv[2]; di2 = rv[3]; }
+                rn = ring_rn[(size_t)(s % (2 * kLineAhead)) * kLineGroupThreads + ct];
+            }
+            issue(s + kLineAhead);
             const bool tr = a.trace && blockIdx.x == 0 && ct == 0;
             if (tr) a.trace[s * 8 + 0] = clock64();
-            const int b0 = tb0, b1 = tb1;
-            const int b0a = b0 & ~(kAl - 1), b1a = (b1 + kAl - 1) & ~(kAl - 1), c0a = b0 & ~3;
-            const bool direct = (b1a > nnzb) || (b1a - b0a > kCap);
             const int qchain = s == 0 ? -1 : (UPPER ? q + a.ncols : q - a.ncols);      // my column one plane back in the walk
             while (!mbar_try_wait(&full[st], (unsigned)(ph & 1))) {}
             const unsigned char* stage = stages + (size_t)st * kLineStageBytes;
+            const int b0 = hdr[st * 2], b1 = hdr[st * 2 + 1];          // the tile's block range, left by the producer
+            const int b0a = b0 & ~(kAl - 1), b1a = (b1 + kAl - 1) & ~(kAl - 1), c0a = b0 & ~3;
+            const bool direct = (b1a > nnzb) || (b1a - b0a > kCap);
             if (tr) a.trace[s * 8 + 1] = clock64();
             T acc = init;
             if (tr) a.trace[s * 8 + 2] = pipe_clock_after((int)__double_as_longlong((double)acc));
             // every block but the chain's is gathered from the work vector (written by earlier launches); the
             // chain's block comes last (mcorder.cpp checks it) and uses the values this thread kept.
-            // (Two copies of the loop: pointers into the stage must stay shared-memory pointers for the
-            // compiler -- a pointer that may also be global turns every access into a generic load, which was
-            // measured at ~400 cycles per dependent load on this path.)
-            auto row_blocks = [&](const T* vs, const int* cs) {
-                for (int kk = kb; kk < ke; kk += 8) {
-                    T xv[8][3];
-                    int cj[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        if (kk + u < ke) {
-                            cj[u] = cs[kk + u];
-                            if (cj[u] != qchain) {
-                                const T* xj = W + (size_t)cj[u] * 3;
-                                xv[u][0] = xj[0]; xv[u][1] = xj[1]; xv[u][2] = xj[2];
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        if (kk + u < ke) {
-                            const T* m = vs + (size_t)(kk + u) * 9;
-                            const bool chain = cj[u] == qchain;
-                            const T x0 = chain ? y0 : xv[u][0], x1 = chain ? y1 : xv[u][1], x2 = chain ? y2 : xv[u][2];
-                            acc = fma(-m[0], x0, acc);
-                            acc = fma(-m[1], x1, acc);
-                            acc = fma(-m[2], x2, acc);
-                        }
-                    }
-                }
-            };
+            // (Pointers into the stage must stay shared-memory pointers for the compiler: two copies of the loop.)
             if (active) {
                 if (!direct) {
                     const T* vs = reinterpret_cast<const T*>(stage) + c * 3;
                     const int* cs = reinterpret_cast<const int*>(stage + kSpmvValBytes);
-                    // (indices relative to the stage: blocks from b0a, columns from c0a)
                     for (int kk = kb; kk < ke; kk += 8) {
                         T xv[8][3];
                         int cj[8];
@@ -597,44 +593,53 @@ mc_line_sweep_kernel(McLineArgs a)
                         }
                     }
                 } else {
-                    row_blocks(vals + (size_t)c * 3, colidx);
+                    for (int kk = kb; kk < ke; ++kk) {
+                        const T* m = vals + (size_t)kk * 9 + c * 3;
+                        const int cjk = colidx[kk];
+                        const bool chain = cjk == qchain;
+                        const T* xj = W + (size_t)(chain ? 0 : cjk) * 3;
+                        const T x0 = chain ? y0 : xj[0], x1 = chain ? y1 : xj[1], x2 = chain ? y2 : xj[2];
+                        acc = fma(-m[0], x0, acc);
+                        acc = fma(-m[1], x1, acc);
+                        acc = fma(-m[2], x2, acc);
+                    }
                 }
             }
-            // the three components of a row meet (a row's threads may sit in two warps)
             if (tr) a.trace[s * 8 + 3] = pipe_clock_after((int)__double_as_longlong((double)acc));
+            // the three components of a row meet (a row's threads may sit in two warps)
             T* sc = scratch + (size_t)buf * kLineGroupThreads;
             sc[ct] = acc;
             asm volatile("bar.sync 1, %0;" ::"n"(kLineGroupThreads) : "memory");
-            buf ^= 1;
             if (tr) a.trace[s * 8 + 4] = clock64();
+            T mine = acc;
             if (active) {
                 const T r0v = sc[rl * 3], r1v = sc[rl * 3 + 1], r2v = sc[rl * 3 + 2];
                 if (!UPPER) {
                     y0 = r0v; y1 = r1v; y2 = r2v;
-                    W[(size_t)q * 3 + c] = acc;
                 } else {
-                    T v0 = T(0), v1 = T(0), v2 = T(0);
-                    v0 = fma(di[0], r0v, v0); v0 = fma(di[1], r1v, v0); v0 = fma(di[2], r2v, v0);
-                    v1 = fma(di[3], r0v, v1); v1 = fma(di[4], r1v, v1); v1 = fma(di[5], r2v, v1);
-                    v2 = fma(di[6], r0v, v2); v2 = fma(di[7], r1v, v2); v2 = fma(di[8], r2v, v2);
-                    y0 = v0; y1 = v1; y2 = v2;
-                    const T v = c == 0 ? v0 : (c == 1 ? v1 : v2);
-                    W[(size_t)q * 3 + c] = v;
-                    out[(size_t)rn * 3 + c] = a.scale ? v * wrel : v;
+                    T v = T(0);
+                    v = fma(di0, r0v, v); v = fma(di1, r1v, v); v = fma(di2, r2v, v);
+                    mine = v;
                 }
+            }
+            if (UPPER) {          // the next plane needs all three components of x: a second meeting
+                T* sx = scratch + (size_t)(2 + buf) * kLineGroupThreads;
+                sx[ct] = mine;
+                asm volatile("bar.sync 1, %0;" ::"n"(kLineGroupThreads) : "memory");
+                if (active) { y0 = sx[rl * 3]; y1 = sx[rl * 3 + 1]; y2 = sx[rl * 3 + 2]; }
+            }
+            buf ^= 1;
+            if (active) {
+                W[(size_t)q * 3 + c] = mine;
+                if (UPPER) out[(size_t)rn * 3 + c] = a.scale ? mine * wrel : mine;
             }
             if (tr) a.trace[s * 8 + 5] = pipe_clock_after((int)__double_as_longlong((double)y0));
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[st]);
             if (tr) a.trace[s * 8 + 6] = clock64();
-            // roll the prefetched operands
-            q = qn; kb = kb_n; ke = ke_n; tb0 = tb0_n; tb1 = tb1_n; rn = rn_n; rn_n = rn_nn; init = init_n;
-            if (UPPER) {
-#pragma unroll
-                for (int e = 0; e < 9; ++e) di[e] = di_n[e];
-            }
-            if (tr) a.trace[s * 8 + 7] = pipe_clock_after(kb + rn + (int)__double_as_longlong((double)init));
+            if (tr) a.trace[s * 8 + 7] = clock64();
         }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
 }
 
