@@ -3,7 +3,7 @@
  * (include/opm_gpu_solver.h is): a caller of the solver never needs these.  They let the test suite
  * check host-side analysis code without a GPU and inject a failure the recovery path must survive.
  *
- * Shipping library (libopmgpu.so): the five hooks of the first section.
+ * Shipping library (libopmgpu.so): the six hooks of the first section.
  * Experiments build (libopmgpu_exp.so, `make -C opm_simulators_legacy_b200/csrc exp`, -DOPMGPU_EXPERIMENTS):
  * additionally the hooks of the second section, the slower kernel variants kept for A/B measurements and
  * the tuning switches of DESIGN.md section 10.
@@ -32,6 +32,11 @@ int opmgpu_debug_partition(int N_local, const int* rowptr, const long long* coli
                            const long long* row_offsets, int world, int rank, int* colidx_full,
                            long long* ghost_global, int* recv_cnt, int* rowptr_diag, int* colidx_diag,
                            int* lu_src, int* nnzb_diag_out);
+/* Host only: the multicolour ILU0 program (permutation, [ L | Dinv | U ] layout, update lists) interpreted
+ * sequentially as the kernels index it: factors in the caller's slots (lu_out, may be NULL) and
+ * v = w P^T U^-1 L^-1 P d; lines != 0: the k-line ordering (returns -2 when it refuses the pattern). */
+int opmgpu_debug_host_mc_apply(int N, const int* rowptr, const int* colidx, const double* vals, int lines,
+                               double w, const double* d, double* v, double* lu_out, int* info /*[2]*/);
 /* Sets the device watchdog word as a sweep kernel does when a dependency is never delivered: the
  * next call that collects it must fail with OPMGPU_CUDA_ERROR, re-arm and leave the handle usable. */
 int opmgpu_debug_set_watchdog_word(opmgpu_handle h, int code);

@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("OPMGPU_LIB") or os.path.join(_HERE, "libopmgpu.so")
 EXP_LIB_PATH = os.path.join(_HERE, "libopmgpu_exp.so")
 # test hooks (include/opm_gpu_solver_testhooks.h): in the shipping library / in the experiments build only
 TEST_HOOKS = ["opmgpu_debug_analyse_only", "opmgpu_debug_host_program_apply", "opmgpu_debug_host_factor_program",
-              "opmgpu_debug_partition", "opmgpu_debug_set_watchdog_word"]
+              "opmgpu_debug_partition", "opmgpu_debug_set_watchdog_word", "opmgpu_debug_host_mc_apply"]
 EXP_HOOKS = ["opmgpu_debug_host_col_apply", "opmgpu_debug_trace_apply", "opmgpu_debug_gtrace_apply"]
 
 # every symbol include/opm_gpu_solver.h declares (tests check the export list against this)

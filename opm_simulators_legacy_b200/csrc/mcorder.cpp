@@ -3,6 +3,7 @@
 #include "analysis.hpp"      // infer_cartesian_grid
 
 #include <algorithm>
+#include <cmath>
 #include <numeric>
 
 namespace opmgpu {
@@ -167,3 +168,106 @@ bool build_mc_program(int N, const int* rowptr, const int* colidx, McProgram& m,
 }
 
 }  // namespace opmgpu
+
+using namespace opmgpu;
+
+// ---- test hook (host only, no GPU): the multicolour program interpreted sequentially -------------------
+// Gathers A into [ L | Dinv | U ] through psrc / ppos, factorises row by row with the update lists and
+// applies v = w P^T U^-1 L^-1 P d walking the operands exactly as the kernels index them (L ascending, U in
+// stored = descending order, the inverted pivot last).  Same arithmetic as mc_ilu.cuh (one fma per y -= a x,
+// OPM's 3x3 adjugate inverse), so the result must be bit-identical to the oracle run on P A P^T.
+// lu_out (may be NULL): factors in the slots of the caller's pattern.  Returns 0, -2 when the k-line
+// ordering refuses the pattern, 1 + row for a singular pivot (caller's numbering); info = {colours, levels}.
+namespace {
+void host_mat3_mul(const double* A, const double* B, double* C)
+{
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            double s = 0.0;
+            for (int k = 0; k < 3; ++k) s = std::fma(A[i * 3 + k], B[k * 3 + j], s);
+            C[i * 3 + j] = s;
+        }
+}
+double host_mat3_invert(double* M)
+{
+    double A[9];
+    for (int q = 0; q < 9; ++q) A[q] = M[q];
+    const double t4 = A[0] * A[4], t6 = A[0] * A[5], t8 = A[1] * A[3];
+    const double t10 = A[2] * A[3], t12 = A[1] * A[6], t14 = A[2] * A[6];
+    const double det = (t4 * A[8] - t6 * A[7] - t8 * A[8] + t10 * A[7] + t12 * A[5] - t14 * A[4]);
+    const double t17 = 1.0 / det;
+    M[0] = (A[4] * A[8] - A[5] * A[7]) * t17;
+    M[1] = -(A[1] * A[8] - A[2] * A[7]) * t17;
+    M[2] = (A[1] * A[5] - A[2] * A[4]) * t17;
+    M[3] = -(A[3] * A[8] - A[5] * A[6]) * t17;
+    M[4] = (A[0] * A[8] - t14) * t17;
+    M[5] = -(t6 - t10) * t17;
+    M[6] = (A[3] * A[7] - A[4] * A[6]) * t17;
+    M[7] = -(A[0] * A[7] - t12) * t17;
+    M[8] = (t4 - t8) * t17;
+    return det;
+}
+}  // namespace
+
+extern "C" int opmgpu_debug_host_mc_apply(int N, const int* rowptr, const int* colidx, const double* vals, int lines,
+                                          double w, const double* d, double* v, double* lu_out, int* info /*[2]*/)
+{
+    McProgram m;
+    if (!build_mc_program(N, rowptr, colidx, m, lines != 0)) return -2;
+    const int nnzb = rowptr[N];
+    std::vector<double> uni((size_t)m.total_blocks * 9, 0.0);
+    for (int b = 0; b < nnzb; ++b)
+        for (int t = 0; t < 9; ++t) uni[(size_t)m.ppos[b] * 9 + t] = vals[(size_t)m.psrc[b] * 9 + t];
+    if (info) { info[0] = m.ord.ncolours; info[1] = (int)m.lvl_ptr.size() - 1; }
+    // factorisation in level order (what the device launches), rows of a level in ascending order
+    for (int q : m.lvl_rows) {
+        for (int l = m.Lrowptr[q]; l < m.Lrowptr[q + 1]; ++l) {
+            const int j = m.Lcol[l];
+            double L[9];
+            host_mat3_mul(&uni[(size_t)l * 9], &uni[(size_t)(m.offD + j) * 9], L);
+            for (int t = 0; t < 9; ++t) uni[(size_t)l * 9 + t] = L[t];
+            for (int p = m.pair_ptr[l]; p < m.pair_ptr[l + 1]; ++p) {
+                double B[9];
+                host_mat3_mul(L, &uni[(size_t)m.pair_jk[p] * 9], B);
+                for (int t = 0; t < 9; ++t) uni[(size_t)m.pair_ik[p] * 9 + t] -= B[t];
+            }
+        }
+        const double det = host_mat3_invert(&uni[(size_t)(m.offD + q) * 9]);
+        if (!(det != 0.0) || std::isinf(det) || std::isnan(det)) return 1 + m.ord.p2n[q];
+    }
+    if (lu_out)
+        for (int b = 0; b < nnzb; ++b)
+            for (int t = 0; t < 9; ++t) lu_out[(size_t)m.psrc[b] * 9 + t] = uni[(size_t)m.ppos[b] * 9 + t];
+    if (!d || !v) return 0;
+    const int scale = std::fabs(w - 1.0) > 1e-15 ? 1 : 0;
+    std::vector<double> W((size_t)N * 3);
+    for (int q = 0; q < N; ++q) {
+        double rb[3];
+        for (int r = 0; r < 3; ++r) rb[r] = d[(size_t)m.ord.p2n[q] * 3 + r];
+        for (int l = m.Lrowptr[q]; l < m.Lrowptr[q + 1]; ++l) {
+            const double* a = &uni[(size_t)l * 9];
+            const double* y = &W[(size_t)m.Lcol[l] * 3];
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c) rb[r] = std::fma(-a[r * 3 + c], y[c], rb[r]);
+        }
+        for (int r = 0; r < 3; ++r) W[(size_t)q * 3 + r] = rb[r];
+    }
+    for (int q = N - 1; q >= 0; --q) {
+        double rb[3];
+        for (int r = 0; r < 3; ++r) rb[r] = W[(size_t)q * 3 + r];
+        for (int u = m.Urowptr[q]; u < m.Urowptr[q + 1]; ++u) {          // stored in descending column order
+            const double* a = &uni[(size_t)(m.offU + u) * 9];
+            const double* x = &W[(size_t)m.Ucol[u] * 3];
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c) rb[r] = std::fma(-a[r * 3 + c], x[c], rb[r]);
+        }
+        const double* di = &uni[(size_t)(m.offD + q) * 9];
+        for (int r = 0; r < 3; ++r) {
+            double y = 0.0;
+            for (int c = 0; c < 3; ++c) y = std::fma(di[r * 3 + c], rb[c], y);
+            W[(size_t)q * 3 + r] = y;
+        }
+        for (int r = 0; r < 3; ++r) v[(size_t)m.ord.p2n[q] * 3 + r] = scale ? W[(size_t)q * 3 + r] * w : W[(size_t)q * 3 + r];
+    }
+    return 0;
+}

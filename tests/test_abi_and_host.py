@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_test_hooks_and_experiment_symbols():
-    """include/opm_gpu_solver_testhooks.h: the shipping library exports the five test hooks and none of
+    """include/opm_gpu_solver_testhooks.h: the shipping library exports its test hooks and none of
     the experiment entry points; the experiments build exports both and the whole C ABI."""
     import ctypes
     hdr = open(os.path.join(ROOT, "include", "opm_gpu_solver_testhooks.h")).read()

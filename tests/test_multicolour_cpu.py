@@ -4,6 +4,7 @@ GPU parity tests of the variant compare with).  The variant is the reference's I
 (compare the reference's own ilu_redblack option, opm/autodiff/ISTLSolver.hpp:207-209): its iteration
 counts are NOT the reference's natural-order counts and are never reported as parity."""
 import numpy as np
+import pytest
 
 from opm_simulators_legacy_b200.jacobian import synth_blackoil_jacobian, random_bcrs
 from opm_simulators_legacy_b200.solver import multicolour_order, line_order
@@ -115,3 +116,66 @@ def test_line_order_is_red_black_over_columns_with_natural_order_inside(oracle):
     prp, pci, pv, order = permute_bcrs(rp, ci, v, n2p_rb)
     xr, rr = oracle.solve_bcrs(prp, pci, pv, b.reshape(-1, 3)[np.argsort(n2p_rb)])
     assert rl["converged"] and rr["converged"] and rl["half_steps"] <= rr["half_steps"]
+
+
+def _host_mc(rp, ci, v, lines, w, d):
+    """opmgpu_debug_host_mc_apply: the multicolour program (permutation, [L | Dinv | U] layout, update
+    lists) interpreted sequentially on the host exactly as the kernels index it."""
+    import ctypes as C
+    from opm_simulators_legacy_b200 import _lib
+    lib = _lib.load()
+    f = lib.opmgpu_debug_host_mc_apply
+    ip, dp = C.POINTER(C.c_int), C.POINTER(C.c_double)
+    f.argtypes = [C.c_int, ip, ip, dp, C.c_int, C.c_double, dp, dp, dp, ip]
+    f.restype = C.c_int
+    rp = np.ascontiguousarray(rp, dtype=np.int32); ci = np.ascontiguousarray(ci, dtype=np.int32)
+    v = np.ascontiguousarray(v, dtype=np.float64); d = np.ascontiguousarray(d, dtype=np.float64)
+    out = np.zeros_like(d); lu = np.zeros_like(v); info = np.zeros(2, dtype=np.int32)
+    rc = f(rp.size - 1, rp.ctypes.data_as(ip), ci.ctypes.data_as(ip), v.ctypes.data_as(dp), int(lines), float(w),
+           d.ctypes.data_as(dp), out.ctypes.data_as(dp), lu.ctypes.data_as(dp), info.ctypes.data_as(ip))
+    return rc, out, lu, info
+
+
+@pytest.mark.parametrize("lines", [False, True], ids=["points", "k-lines"])
+@pytest.mark.parametrize("dims", [(10, 10, 3), (9, 7, 12), (33, 17, 5), (30, 17, 1), (64, 1, 1)])
+def test_multicolour_program_is_exact_on_the_host(oracle, dims, lines):
+    """Host-side data of both orderings against the oracle on P A P^T, bit for bit: permutation, L / U split
+    (U stored in descending column order), unified factor layout, update lists of the factorisation."""
+    s = synth_blackoil_jacobian(*dims, perm="lognormal")
+    rp, ci, v, b = s.rowptr.numpy(), s.colidx.numpy(), s.vals.numpy(), s.rhs.numpy().reshape(-1, 3)
+    n2p = line_order(*dims) if lines else multicolour_order(rp, ci)[2]
+    p2n = np.argsort(n2p)
+    prp, pci, pv, order = permute_bcrs(rp, ci, v, n2p)
+    lu_ref, bad = oracle.ilu0_factor(prp, pci, pv)
+    assert bad == -1
+    for w in (0.9, 1.0):
+        rc, out, lu, info = _host_mc(rp, ci, v, lines, w, b.reshape(-1))
+        assert rc == 0
+        assert np.array_equal(lu[order], lu_ref)
+        ref = oracle.ilu0_apply(prp, pci, lu_ref, w, b[p2n].reshape(-1))
+        back = np.empty_like(ref); back[p2n] = ref
+        assert np.array_equal(out.reshape(-1, 3), back)
+
+
+def test_multicolour_program_general_pattern_and_refusals(oracle):
+    rp, ci, v = random_bcrs(600, extra_per_row=3, seed=9, dense_group=15)
+    b = np.random.default_rng(1).standard_normal((600, 3))
+    nc, colour, n2p = multicolour_order(rp, ci)
+    p2n = np.argsort(n2p)
+    prp, pci, pv, order = permute_bcrs(rp, ci, v, n2p)
+    lu_ref, bad = oracle.ilu0_factor(prp, pci, pv)
+    rc, out, lu, info = _host_mc(rp, ci, v, False, 0.9, b.reshape(-1))
+    assert rc == 0 and info[0] == nc >= 15
+    assert np.array_equal(lu[order], lu_ref)               # update lists that touch off-diagonal blocks too
+    ref = oracle.ilu0_apply(prp, pci, lu_ref, 0.9, b[p2n].reshape(-1))
+    back = np.empty_like(ref); back[p2n] = ref
+    assert np.array_equal(out.reshape(-1, 3), back)
+    # the k-line ordering refuses what is not a Cartesian stencil with vertical same-colour couplings only
+    assert _host_mc(rp, ci, v, True, 0.9, b.reshape(-1))[0] == -2
+    # a singular pivot is reported in the caller's numbering
+    s = synth_blackoil_jacobian(6, 5, 4, perm="homogeneous")
+    rp, ci, v = s.rowptr.numpy(), s.colidx.numpy(), s.vals.numpy().copy()
+    rows = np.repeat(np.arange(s.N), np.diff(rp))
+    v[rows == 17] = 0.0
+    for lines in (False, True):
+        assert _host_mc(rp, ci, v, lines, 0.9, s.rhs.numpy().reshape(-1))[0] == 1 + 17
